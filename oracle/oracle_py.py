@@ -1,0 +1,353 @@
+"""ctypes binding of the CPU oracle (oracle/libtrl_oracle.so).
+
+TEST INFRASTRUCTURE -- may be imported only by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py. The product never imports this module.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtrl_oracle.so")
+_DATA = os.path.join(_HERE, "..", "terrainrlsim_b200", "data")
+
+JOINT_COLS, BODY_COLS, PD_COLS = 19, 17, 18
+GROUND_NONE, GROUND_VAR2D, GROUND_VAR3D, GROUND_PLANE = 0, 1, 2, 3
+OBS_TERRAIN_RL, OBS_TERRAIN_RL_HOPPER, OBS_CT, OBS_CT_3D = 0, 1, 2, 3
+SAMPLER_LINE, SAMPLER_GRID = 0, 1
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_up = C.POINTER(C.c_ubyte)
+
+
+class CModel(C.Structure):
+    _fields_ = [("num_joints", C.c_int), ("num_dof", C.c_int), ("joint_mat", _dp), ("body_defs", _dp),
+                ("pd_params", _dp), ("gravity", C.c_double * 3), ("num_frames", C.c_int), ("frames", _dp),
+                ("loop", C.c_int)]
+
+
+class CGround(C.Structure):
+    _fields_ = [("kind", C.c_int), ("num_pieces", C.c_int), ("data", _fp * 4), ("res", (C.c_int * 2) * 4),
+                ("origin", (C.c_double * 3) * 4), ("scale", (C.c_double * 3) * 4), ("bounds", (C.c_double * 4) * 4)]
+
+
+class CObsCfg(C.Structure):
+    _fields_ = [("obs_kind", C.c_int), ("sampler", C.c_int), ("num_samples", C.c_int), ("grid_res", C.c_int),
+                ("view_min", C.c_double), ("view_max", C.c_double), ("num_phase_bins", C.c_int)]
+
+
+class CStepIO(C.Structure):
+    _fields_ = [("num_envs", C.c_int), ("dt", C.c_double),
+                ("pose", _dp), ("vel", _dp), ("tar_pose", _dp), ("tar_vel", _dp), ("joint_active", _up),
+                ("kin_time", _dp), ("origin_pos", _dp), ("origin_rot", _dp), ("body_pos", _dp), ("body_vel", _dp),
+                ("phase", _dp), ("flip", _up), ("grounds", C.POINTER(CGround)), ("env_to_ground", _ip),
+                ("num_grounds", C.c_int),
+                ("tau", _dp), ("kin_pose", _dp), ("kin_vel", _dp), ("kin_body_pos", _dp), ("state", _dp)]
+
+
+def build_lib(force=False):
+    if force or not os.path.exists(_LIB_PATH) or \
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "trl_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_lib())
+        _lib.trlo_sample_height.restype = C.c_double
+        _lib.trlo_calc_heading.restype = C.c_double
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _u(a):
+    return a.ctypes.data_as(_up) if a is not None else None
+
+
+def _c(a, dtype=np.float64):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def load_model_json(name):
+    with open(os.path.join(_DATA, name + ".json")) as f:
+        return json.load(f)
+
+
+class Model:
+    """Flat model arrays + the C struct the oracle consumes."""
+
+    def __init__(self, name=None, joint_mat=None, body_defs=None, pd_params=None, frames=None, loop=False,
+                 gravity=(0.0, -9.8, 0.0), with_motion=True):
+        self.meta = {}
+        if name is not None:
+            d = load_model_json(name)
+            self.meta = d
+            joint_mat, body_defs, pd_params = d["joint_mat"], d["body_defs"], d["pd_params"]
+            if with_motion and "motion" in d:
+                frames = np.array(d["motion"]["frames"], dtype=np.float64)
+                loop = d["motion"]["loop"]
+        self.name = name
+        self.joint_mat = np.ascontiguousarray(joint_mat, dtype=np.float64)
+        self.body_defs = np.ascontiguousarray(body_defs, dtype=np.float64)
+        self.pd_params = np.ascontiguousarray(pd_params, dtype=np.float64)
+        self.N = self.joint_mat.shape[0]
+        assert self.joint_mat.shape == (self.N, JOINT_COLS)
+        assert self.body_defs.shape == (self.N, BODY_COLS)
+        assert self.pd_params.shape == (self.N, PD_COLS)
+        self.gravity = np.array(gravity, dtype=np.float64)
+        self.loop = bool(loop)
+        self.frames_raw = None
+        self.frames = None
+        if frames is not None:
+            self.frames_raw = np.ascontiguousarray(frames, dtype=np.float64)
+            fr = self.frames_raw.copy()
+            # cMotion::PostProcessFrames (anim/Motion.cpp:207-217): durations -> cumulative start times
+            t = 0.0
+            for f in range(fr.shape[0]):
+                dur = fr[f, 0]
+                fr[f, 0] = t
+                t += dur
+            self.frames = fr
+        self.parent = self.joint_mat[:, 1].astype(int)
+        self.jtype = self.joint_mat[:, 0].astype(int)
+        self.offset = self.joint_mat[:, 18].astype(int)
+        sizes = {0: 1, 1: 3, 2: 1, 3: 0, 4: 4, 5: 0}
+        self.size = np.array([7 if self.parent[j] == -1 else sizes[self.jtype[j]] for j in range(self.N)])
+        self.n = int(self.offset[-1] + self.size[-1])
+        self.c = CModel()
+        self.c.num_joints = self.N
+        self.c.num_dof = self.n
+        self.c.joint_mat = _d(self.joint_mat)
+        self.c.body_defs = _d(self.body_defs)
+        self.c.pd_params = _d(self.pd_params)
+        self.c.gravity[:] = list(self.gravity)
+        self.c.num_frames = 0 if self.frames is None else self.frames.shape[0]
+        self.c.frames = _d(self.frames)
+        self.c.loop = int(self.loop)
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+    def quat_slots(self):
+        """Offsets of quaternion (w,x,y,z) blocks in a pose vector."""
+        out = [3]
+        for j in range(1, self.N):
+            if self.jtype[j] == 4:
+                out.append(int(self.offset[j]))
+        return out
+
+    # ---- single-env wrappers ----
+    def rbd_update(self, pose, vel):
+        pose, vel = _c(pose), _c(vel)
+        M = np.zeros((self.n, self.n))
+        Cb = np.zeros(self.n)
+        lib().trlo_rbd_update(self.ref, _d(pose), _d(vel), _d(M), _d(Cb))
+        return M, Cb
+
+    def inv_dyna(self, pose, vel, acc):
+        pose, vel, acc = _c(pose), _c(vel), _c(acc)
+        tau = np.zeros(self.n)
+        lib().trlo_solve_inv_dyna(self.ref, _d(pose), _d(vel), _d(acc), _d(tau))
+        return tau
+
+    def imp_pd(self, dt, pose, vel, tar_pose, tar_vel, active=None, kp=None, kd=None, tau0=None):
+        pose, vel, tar_pose, tar_vel = _c(pose), _c(vel), _c(tar_pose), _c(tar_vel)
+        active = _c(active, np.uint8)
+        kp, kd = _c(kp), _c(kd)
+        tau = np.zeros(self.n) if tau0 is None else np.array(tau0, dtype=np.float64)
+        M = np.zeros((self.n, self.n))
+        Cb = np.zeros(self.n)
+        zp = lib().trlo_imp_pd_control_force(self.ref, C.c_double(dt), _d(pose), _d(vel), _d(tar_pose), _d(tar_vel),
+                                             _u(active), _d(kp), _d(kd), _d(tau), _d(M), _d(Cb))
+        return tau, M, Cb, zp
+
+    def joint_world_trans(self, pose, j):
+        pose = _c(pose)
+        out = np.zeros((4, 4))
+        lib().trlo_joint_world_trans(self.ref, _d(pose), C.c_int(j), _d(out))
+        return out
+
+    def child_parent_trans(self, pose, j):
+        pose = _c(pose)
+        out = np.zeros((4, 4))
+        lib().trlo_child_parent_trans(self.ref, _d(pose), C.c_int(j), _d(out))
+        return out
+
+    def body_part_pos(self, pose, j):
+        pose = _c(pose)
+        out = np.zeros(3)
+        lib().trlo_body_part_pos(self.ref, _d(pose), C.c_int(j), _d(out))
+        return out
+
+    def inertia_spatial(self, j):
+        out = np.zeros((6, 6))
+        lib().trlo_inertia_spatial(self.ref, C.c_int(j), _d(out))
+        return out
+
+    def vel_to_pose_diff(self, pose, vel):
+        pose, vel = _c(pose), _c(vel)
+        out = np.zeros(self.n)
+        lib().trlo_vel_to_pose_diff(self.ref, _d(pose), _d(vel), _d(out))
+        return out
+
+    def post_process_pose(self, pose):
+        pose = np.array(pose, dtype=np.float64)
+        lib().trlo_post_process_pose(self.ref, _d(pose))
+        return pose
+
+    def calc_vel(self, pose0, pose1, dt):
+        pose0, pose1 = _c(pose0), _c(pose1)
+        out = np.zeros(self.n)
+        lib().trlo_calc_vel(self.ref, _d(pose0), _d(pose1), C.c_double(dt), _d(out))
+        return out
+
+    def lerp_poses(self, pose0, pose1, t):
+        pose0, pose1 = _c(pose0), _c(pose1)
+        out = np.zeros(self.n)
+        lib().trlo_lerp_poses(self.ref, _d(pose0), _d(pose1), C.c_double(t), _d(out))
+        return out
+
+    def motion_index_phase(self, t):
+        idx = C.c_int()
+        ph = C.c_double()
+        lib().trlo_motion_index_phase(self.ref, C.c_double(t), C.byref(idx), C.byref(ph))
+        return idx.value, ph.value
+
+    def kin_char_pose(self, t, origin_pos=None, origin_rot=None):
+        pose = np.zeros(self.n)
+        vel = np.zeros(self.n)
+        op, orr = _c(origin_pos), _c(origin_rot)
+        lib().trlo_kin_char_pose(self.ref, C.c_double(t), _d(op), _d(orr), _d(pose), _d(vel))
+        return pose, vel
+
+
+def ldlt_solve(A, b):
+    A, b = _c(A), _c(b)
+    n = A.shape[0]
+    x = np.zeros(n)
+    zp = lib().trlo_ldlt_solve(C.c_int(n), _d(A), _d(b), _d(x))
+    return x, zp
+
+
+class Ground:
+    """One env's terrain: list of pieces (data float32 2-D array [res_z][res_x] or 1-D row)."""
+
+    def __init__(self, kind, pieces=()):
+        self.kind = kind
+        self.c = CGround()
+        self.c.kind = kind
+        self.c.num_pieces = len(pieces)
+        self._keep = []
+        self.pieces = list(pieces)
+        for s, p in enumerate(pieces):
+            data = np.ascontiguousarray(p["data"], dtype=np.float32)
+            self._keep.append(data)
+            self.c.data[s] = data.ctypes.data_as(_fp)
+            self.c.res[s][0] = int(p["res"][0])
+            self.c.res[s][1] = int(p["res"][1])
+            for k in range(3):
+                self.c.origin[s][k] = float(p["origin"][k])
+                self.c.scale[s][k] = float(p["scale"][k])
+            for k in range(4):
+                self.c.bounds[s][k] = float(p["bounds"][k])
+
+    def sample_height(self, pos):
+        pos = _c(pos)
+        valid = C.c_int()
+        cell = (C.c_int * 3)()
+        h = lib().trlo_sample_height(C.byref(self.c), _d(pos), C.byref(valid), cell)
+        return h, bool(valid.value), (cell[0], cell[1], cell[2])
+
+
+def obs_cfg(obs_kind=OBS_TERRAIN_RL, sampler=SAMPLER_LINE, num_samples=200, grid_res=0, view_min=-0.5,
+            view_max=10.0, num_phase_bins=-1):
+    c = CObsCfg()
+    c.obs_kind, c.sampler, c.num_samples, c.grid_res = obs_kind, sampler, num_samples, grid_res
+    c.view_min, c.view_max, c.num_phase_bins = view_min, view_max, num_phase_bins
+    return c
+
+
+def poli_state_size(model, cfg):
+    return lib().trlo_poli_state_size(model.ref, C.byref(cfg))
+
+
+def parse_ground(ground, cfg, pose, flip=0):
+    pose = _c(pose)
+    G = cfg.num_samples
+    out = np.zeros(G)
+    cells = np.zeros((G, 3), dtype=np.int32)
+    lib().trlo_parse_ground(C.byref(ground.c) if ground is not None else None, C.byref(cfg), _d(pose), C.c_int(flip),
+                            _d(out), cells.ctypes.data_as(_ip))
+    return out, cells
+
+
+def build_poli_state(model, ground, cfg, pose, vel, body_pos, body_vel, body_quat=None, body_angvel=None,
+                     ground_vel=None, phase=0.0, flip=0):
+    F = poli_state_size(model, cfg)
+    out = np.zeros(F)
+    pose, vel, body_pos, body_vel = _c(pose), _c(vel), _c(body_pos), _c(body_vel)
+    body_quat, body_angvel, ground_vel = _c(body_quat), _c(body_angvel), _c(ground_vel)
+    lib().trlo_build_poli_state(model.ref, C.byref(ground.c) if ground is not None else None, C.byref(cfg),
+                                _d(pose), _d(vel), _d(body_pos), _d(body_vel), _d(body_quat), _d(body_angvel),
+                                _d(ground_vel), C.c_double(phase), C.c_int(flip), _d(out))
+    return out
+
+
+def step_range(model, cfg, arrays, grounds, dt, env_begin=0, env_end=None, env_to_ground=None):
+    """Run the fused oracle step over envs [env_begin, env_end). `arrays` is a dict of numpy arrays
+    (inputs: pose, vel, tar_pose, tar_vel, joint_active, kin_time, origin_pos, origin_rot, body_pos, body_vel,
+    phase, flip; outputs are allocated if absent: tau, kin_pose, kin_vel, kin_body_pos, state)."""
+    E = arrays["pose"].shape[0]
+    n, N = model.n, model.N
+    F = poli_state_size(model, cfg)
+    io = CStepIO()
+    io.num_envs = E
+    io.dt = dt
+    keep = []
+
+    def get(name, dtype=np.float64):
+        a = arrays.get(name)
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        arrays[name] = a
+        return a
+
+    for name in ("pose", "vel", "tar_pose", "tar_vel", "kin_time", "origin_pos", "origin_rot", "body_pos",
+                 "body_vel", "phase"):
+        setattr(io, name, _d(get(name)))
+    io.joint_active = _u(get("joint_active", np.uint8))
+    io.flip = _u(get("flip", np.uint8))
+    garr = None
+    if grounds:
+        garr = (CGround * len(grounds))(*[g.c for g in grounds])
+        io.grounds = garr
+        io.num_grounds = len(grounds)
+        if env_to_ground is not None:
+            e2g = np.ascontiguousarray(env_to_ground, dtype=np.int32)
+            keep.append(e2g)
+            io.env_to_ground = e2g.ctypes.data_as(_ip)
+    shapes = {"tau": (E, n), "kin_pose": (E, n), "kin_vel": (E, n), "kin_body_pos": (E, N, 3), "state": (E, F)}
+    for name, shp in shapes.items():
+        if name not in arrays or arrays[name] is None:
+            arrays[name] = np.zeros(shp)
+        setattr(io, name, _d(arrays[name]))
+    if env_end is None:
+        env_end = E
+    lib().trlo_step_range(model.ref, C.byref(cfg), C.byref(io), C.c_int(env_begin), C.c_int(env_end))
+    return arrays

@@ -1,0 +1,179 @@
+"""The oracle is 'parity unpinned' (the reference ships no golden vectors), so it is pinned here by
+mathematical identities that do not depend on the restatement itself:
+  * M symmetric, PSD; dead dofs (root slot 6, Q1) exactly zero
+  * RNEA(q, qd, qdd) = M qdd + C           (CRBA and RNEA agree)
+  * 1/2 qd^T M qd = kinetic energy from finite-differenced FK (independent numpy evaluation)
+  * C(q, 0) = dV/dq from finite-differenced potential energy
+  * pivoted LDLT solves A x = b and zeroes null components
+"""
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES
+from terrainrlsim_b200 import synth
+
+
+def _inputs(name, E=6):
+    return synth.make_inputs(name, E)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_mass_matrix_symmetric_psd_and_dead_dofs(oracle, name):
+    m = oracle.Model(name)
+    x = _inputs(name)
+    for e in range(x["pose"].shape[0]):
+        M, C = m.rbd_update(x["pose"][e], x["vel"][e])
+        assert np.allclose(M, M.T, rtol=0, atol=1e-12 * np.abs(M).max())
+        assert np.all(M[6, :] == 0) and np.all(M[:, 6] == 0)
+        dead = [6] + [int(m.offset[j]) + 3 for j in range(1, m.N) if m.jtype[j] == 4]
+        live = [i for i in range(m.n) if i not in dead]
+        for i in dead:
+            assert np.all(M[i, :] == 0)
+            assert C[i] == 0
+        w = np.linalg.eigvalsh(M[np.ix_(live, live)])
+        assert w.min() > 0
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_rnea_equals_mass_times_acc_plus_bias(oracle, name):
+    m = oracle.Model(name)
+    x = _inputs(name)
+    rng = np.random.default_rng(1)
+    for e in range(x["pose"].shape[0]):
+        pose, vel = x["pose"][e], x["vel"][e]
+        M, C = m.rbd_update(pose, vel)
+        acc = rng.normal(size=m.n)
+        tau = m.inv_dyna(pose, vel, acc)
+        ref = M @ acc + C
+        assert np.allclose(tau, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+
+
+def _integrate(m, pose, qd, eps):
+    """pose (+) eps*qd using the reference's own quaternion-rate map (VelToPoseDiff) + renormalise."""
+    d = m.vel_to_pose_diff(pose, qd)
+    return m.post_process_pose(pose + eps * d)
+
+
+def _body_frames(m, pose):
+    out = []
+    for j in range(m.N):
+        T = m.joint_world_trans(pose, j)
+        out.append(T)
+    return out
+
+
+def _energies(m, pose, qd, eps=1e-6):
+    """Kinetic energy via central finite differences of body frames; potential energy m g y."""
+    p1, p0 = _integrate(m, pose, qd, eps), _integrate(m, pose, qd, -eps)
+    F1, F0, Fc = _body_frames(m, p1), _body_frames(m, p0), _body_frames(m, pose)
+    T = 0.0
+    V = 0.0
+    for j in range(m.N):
+        I = m.inertia_spatial(j)  # about the joint origin, joint-frame axes
+        R = Fc[j][:3, :3]
+        v_origin = (F1[j][:3, 3] - F0[j][:3, 3]) / (2 * eps)
+        Rd = (F1[j][:3, :3] - F0[j][:3, :3]) / (2 * eps)
+        W = R.T @ Rd  # [w]x in the joint frame
+        w = np.array([W[2, 1] - W[1, 2], W[0, 2] - W[2, 0], W[1, 0] - W[0, 1]]) * 0.5
+        sv = np.concatenate([w, R.T @ v_origin])
+        T += 0.5 * sv @ I @ sv
+        mass = I[3, 3]
+        # com in joint frame from the spatial inertia: upper-right block = m [c]x
+        mc = np.array([I[2, 4], I[0, 5], I[1, 3]])
+        com_world = Fc[j][:3, 3] + R @ (mc / mass)
+        V += mass * (-m.gravity) @ com_world
+    return T, V
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_kinetic_energy_matches_finite_difference_fk(oracle, name):
+    m = oracle.Model(name)
+    x = _inputs(name, E=3)
+    for e in range(3):
+        pose, vel = x["pose"][e], x["vel"][e]
+        M, _ = m.rbd_update(pose, vel)
+        T_fd, _ = _energies(m, pose, vel)
+        T_m = 0.5 * vel @ M @ vel
+        assert T_m == pytest.approx(T_fd, rel=2e-7)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_gravity_bias_matches_potential_gradient(oracle, name):
+    m = oracle.Model(name)
+    x = _inputs(name, E=2)
+    for e in range(2):
+        pose = x["pose"][e]
+        _, C0 = m.rbd_update(pose, np.zeros(m.n))
+        dead = [6] + [int(m.offset[j]) + 3 for j in range(1, m.N) if m.jtype[j] == 4]
+        eps = 1e-6
+        for i in range(m.n):
+            if i in dead:
+                continue
+            d = np.zeros(m.n)
+            d[i] = 1.0
+            _, V1 = _energies(m, _integrate(m, pose, d, eps), np.zeros(m.n))
+            _, V0 = _energies(m, _integrate(m, pose, d, -eps), np.zeros(m.n))
+            dV = (V1 - V0) / (2 * eps)
+            assert C0[i] == pytest.approx(dV, rel=1e-6, abs=1e-6)
+
+
+def test_ldlt_restatement(oracle):
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 9, 27):
+        A = rng.normal(size=(n, n))
+        A = A @ A.T + n * np.eye(n)
+        b = rng.normal(size=n)
+        x, zp = oracle.ldlt_solve(A, b)
+        assert zp == 0
+        assert np.allclose(A @ x, b, rtol=1e-11, atol=1e-11)
+    # structurally-null row/column -> that component is 0 and the rest solves the reduced system (Q1)
+    n = 8
+    A = rng.normal(size=(n, n))
+    A = A @ A.T + n * np.eye(n)
+    A[3, :] = 0
+    A[:, 3] = 0
+    b = rng.normal(size=n)
+    x, zp = oracle.ldlt_solve(A, b)
+    keep = [i for i in range(n) if i != 3]
+    assert zp == 1 and x[3] == 0
+    assert np.allclose(A[np.ix_(keep, keep)] @ x[keep], b[keep], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_stable_pd_definition(oracle, name):
+    """tau = Kp e_p + Kd (e_v - dt qdd), (M + dt Kd) qdd = Kp e_p + Kd e_v - C, evaluated independently in numpy
+    from the oracle's own M, C and error vectors; root torque entries are 0; inactive joints use masked gains on
+    the right-hand side but the unmasked Kd on the diagonal (Q2)."""
+    m = oracle.Model(name)
+    x = _inputs(name, E=4)
+    dt = 1.0 / 600
+    for e in range(4):
+        pose, vel, tp, tv = x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e]
+        act = x["joint_active"][e].copy()
+        if e == 1 and m.N > 2:
+            act[2] = 0
+        tau, M, C, zp = m.imp_pd(dt, pose, vel, tp, tv, act)
+        kp = np.zeros(m.n)
+        kd = np.zeros(m.n)
+        kd_diag = np.zeros(m.n)
+        for j in range(1, m.N):
+            o, s = int(m.offset[j]), int(m.size[j])
+            kd_diag[o:o + s] = m.pd_params[j, 2]
+            if act[j]:
+                kp[o:o + s] = m.pd_params[j, 1]
+                kd[o:o + s] = m.pd_params[j, 2]
+        pose_inc = m.post_process_pose(pose + dt * m.vel_to_pose_diff(pose, vel))
+        tpe = tp.copy()
+        tpe[:7] = 0
+        e_p = m.calc_vel(pose_inc, tpe, 1.0)
+        e_v = tv - vel
+        e_v[:7] = -vel[:7]
+        A = M + np.diag(dt * kd_diag)
+        rhs = kp * e_p + kd * e_v - C
+        live = [i for i in range(m.n) if A[i, i] != 0]
+        qdd = np.zeros(m.n)
+        qdd[live] = np.linalg.solve(A[np.ix_(live, live)], rhs[live])
+        ref = kp * e_p + kd * (e_v - dt * qdd)
+        assert np.all(tau[:7] == 0)
+        assert np.allclose(tau, ref, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(ref).max()))
+        assert zp >= 1  # root slot 6
