@@ -1120,6 +1120,14 @@ int trlo_imp_pd_control_force(const trlo_model* m, double dt, const double* pose
             tar_pose[off + i] = tar_pose_in[off + i];
             tar_vel[off + i] = tar_vel_in[off + i];
         }
+        if (trlo_joint_type(m, j) == TRLO_JOINT_SPHERICAL) {
+            /* targets enter through SetTargetTheta / SetTargetVel, which post-process spherical joints
+             * (sim/PDController.cpp:191-211,430-461): zero quaternion -> identity, else normalise; vel slot 3 = 0 */
+            double* t = tar_pose + off;
+            if (t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3] == 0) t[0] = 1;
+            else normalize4(t);
+            tar_vel[off + size - 1] = 0;
+        }
     }
     /* mask gains of invalid / inactive controllers :151-161 */
     for (int i = 0; i < n; ++i) { Kp[i] = mKp[i]; Kd[i] = mKd[i]; }

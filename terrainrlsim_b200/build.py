@@ -1,0 +1,46 @@
+"""In-tree build of libtrl_b200.so (nvcc, sm_100a). Used by __graft_entry__.build() and on first import."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libtrl_b200.so")
+SOURCES = ["trl_model.cpp", "trl_api.cpp", "trl_kernels.cu"]
+HEADERS = ["trl_internal.h", "trl_device.cuh", os.path.join("..", "..", "include", "trl_b200.h")]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc")
+    if p:
+        return p
+    p = "/usr/local/cuda/bin/nvcc"
+    return p if os.path.exists(p) else None
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    for f in SOURCES + HEADERS:
+        if os.path.getmtime(os.path.join(CSRC, f)) > t:
+            return True
+    return False
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into terrainrlsim_b200/lib/libtrl_b200.so."""
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = nvcc_path()
+    if nvcc is None:
+        raise RuntimeError("nvcc not found: cannot build libtrl_b200.so (there is no CPU fallback)")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177", "-o", LIB_PATH] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB_PATH

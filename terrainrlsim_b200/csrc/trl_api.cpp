@@ -1,0 +1,465 @@
+// C ABI: batch lifetime, pointer-mode staging and kernel sequencing. No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "trl_internal.h"
+
+int trl_obs_state_size(int N, const trl_obs_cfg& cfg);
+double trl_fp64_probe_tflops(void* stream);
+
+namespace {
+
+bool cuda_ok(cudaError_t err, const char* what) {
+    if (err == cudaSuccess) return true;
+    trl_set_error(std::string(what) + ": " + cudaGetErrorString(err));
+    return false;
+}
+
+// grow-only device buffer used for HOST pointer mode staging
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        if (!cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc(staging)")) return false;
+        cap = bytes;
+        return true;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct trl_batch {
+    const trl_model* model = nullptr;
+    int E = 0;
+    int device = 0;
+    int ptr_mode = TRL_PTR_HOST;
+    trl_obs_cfg cfg{};
+    int F = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    DevModel* d_model = nullptr;
+    double* d_frames = nullptr;
+    int* d_status = nullptr;
+    // ground
+    DevGround ground{};
+    float* d_ground_data = nullptr;
+    DevPiece* d_pieces = nullptr;
+    int* d_env_to_field = nullptr;
+    long long launches = 0;
+    // staging (host pointer mode): a small pool of grow-only device buffers handed out per call
+    std::vector<DevBuf> pool;
+    size_t pool_next = 0;
+
+    void* stage_in(const void* host, size_t bytes) {
+        if (!host) return nullptr;
+        if (pool_next >= pool.size()) pool.emplace_back();
+        DevBuf& b = pool[pool_next++];
+        if (!b.reserve(bytes)) return nullptr;
+        if (!cuda_ok(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, stream), "H2D")) return nullptr;
+        return b.p;
+    }
+    void* stage_out(size_t bytes) {
+        if (pool_next >= pool.size()) pool.emplace_back();
+        DevBuf& b = pool[pool_next++];
+        if (!b.reserve(bytes)) return nullptr;
+        return b.p;
+    }
+};
+
+namespace {
+
+struct Guard {  // selects the batch's device for the duration of a call
+    int prev = -1;
+    explicit Guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~Guard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// Resolves an input array according to the pointer mode. Returns false on error.
+template <typename T>
+bool in_ptr(trl_batch* b, const T* user, size_t count, const T** out) {
+    if (!user) { *out = nullptr; return true; }
+    if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
+    *out = static_cast<const T*>(b->stage_in(user, count * sizeof(T)));
+    return *out != nullptr;
+}
+
+// Output array: device pointer to write to (+ remembers the host destination for the copy back).
+struct OutCopy { void* host; void* dev; size_t bytes; };
+
+template <typename T>
+bool out_ptr(trl_batch* b, T* user, size_t count, T** out, std::vector<OutCopy>& copies, bool preload = false) {
+    if (!user) { *out = nullptr; return true; }
+    if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
+    void* d = preload ? b->stage_in(user, count * sizeof(T)) : b->stage_out(count * sizeof(T));
+    if (!d) return false;
+    *out = static_cast<T*>(d);
+    copies.push_back({user, d, count * sizeof(T)});
+    return true;
+}
+
+int finish(trl_batch* b, std::vector<OutCopy>& copies, int launch_rc) {
+    if (launch_rc != 0) {
+        trl_set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t)launch_rc));
+        return TRL_ERR_CUDA;
+    }
+    if (b->ptr_mode == TRL_PTR_HOST) {
+        for (auto& c : copies)
+            if (!cuda_ok(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, b->stream), "D2H")) return TRL_ERR_CUDA;
+        if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return TRL_ERR_CUDA;
+    }
+    return TRL_OK;
+}
+
+}  // namespace
+
+extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int device, const trl_obs_cfg* cfg) {
+    if (!m || num_envs < 1 || device < 0) {
+        trl_set_error("trl_batch_create: invalid argument (device must be >= 0: there is no CPU fallback)");
+        return nullptr;
+    }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count <= device) {
+        trl_set_error(std::string("trl_batch_create: no usable CUDA device ") + std::to_string(device) + " (" +
+                      (err != cudaSuccess ? cudaGetErrorString(err) : "device ordinal out of range") +
+                      "); this library has no CPU fallback");
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::unique_ptr<trl_batch> b(new trl_batch());
+    b->model = m;
+    b->E = num_envs;
+    b->device = device;
+    if (cfg) b->cfg = *cfg;
+    else { b->cfg = trl_obs_cfg{TRL_OBS_TERRAIN_RL, TRL_SAMPLER_LINE, 200, 0, -0.5, 10.0, -1}; }
+    if (b->cfg.num_samples < 0 || (b->cfg.sampler == TRL_SAMPLER_GRID && b->cfg.grid_res * b->cfg.grid_res != b->cfg.num_samples)) {
+        trl_set_error("trl_batch_create: inconsistent observation config");
+        return nullptr;
+    }
+    b->F = trl_obs_state_size(m->N, b->cfg);
+    Guard g(device);
+    if (!cuda_ok(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
+    b->stream = b->own_stream;
+    if (!cuda_ok(cudaMalloc((void**)&b->d_model, sizeof(DevModel)), "cudaMalloc(model)")) return nullptr;
+    if (!cuda_ok(cudaMemcpy(b->d_model, &m->dev, sizeof(DevModel), cudaMemcpyHostToDevice), "H2D(model)")) return nullptr;
+    if (m->num_frames > 0) {
+        size_t bytes = m->frames.size() * sizeof(double);
+        if (!cuda_ok(cudaMalloc((void**)&b->d_frames, bytes), "cudaMalloc(frames)")) return nullptr;
+        if (!cuda_ok(cudaMemcpy(b->d_frames, m->frames.data(), bytes, cudaMemcpyHostToDevice), "H2D(frames)")) return nullptr;
+    }
+    if (!cuda_ok(cudaMalloc((void**)&b->d_status, sizeof(int) * (size_t)num_envs), "cudaMalloc(status)")) return nullptr;
+    cudaMemset(b->d_status, 0, sizeof(int) * (size_t)num_envs);
+    std::memset(&b->ground, 0, sizeof(b->ground));
+    return b.release();
+}
+
+extern "C" void trl_batch_destroy(trl_batch* b) {
+    if (!b) return;
+    Guard g(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (auto& p : b->pool) p.release();
+    if (b->d_model) cudaFree(b->d_model);
+    if (b->d_frames) cudaFree(b->d_frames);
+    if (b->d_status) cudaFree(b->d_status);
+    if (b->d_ground_data) cudaFree(b->d_ground_data);
+    if (b->d_pieces) cudaFree(b->d_pieces);
+    if (b->d_env_to_field) cudaFree(b->d_env_to_field);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    delete b;
+}
+
+extern "C" int trl_batch_set_pointer_mode(trl_batch* b, int mode) {
+    if (!b || (mode != TRL_PTR_HOST && mode != TRL_PTR_DEVICE)) return TRL_ERR_INVALID_ARG;
+    b->ptr_mode = mode;
+    return TRL_OK;
+}
+
+extern "C" int trl_batch_set_stream(trl_batch* b, void* cuda_stream) {
+    if (!b) return TRL_ERR_INVALID_ARG;
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return TRL_OK;
+}
+
+extern "C" int trl_batch_sync(trl_batch* b) {
+    if (!b) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? TRL_OK : TRL_ERR_CUDA;
+}
+
+extern "C" int trl_poli_state_size(const trl_batch* b) { return b ? b->F : TRL_ERR_INVALID_ARG; }
+extern "C" int trl_batch_num_envs(const trl_batch* b) { return b ? b->E : TRL_ERR_INVALID_ARG; }
+extern "C" long long trl_batch_launch_count(const trl_batch* b) { return b ? b->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int trl_imp_pd_update_control_force(trl_batch* b, double dt, const double* pose, const double* vel,
+                                               const double* tar_pose, const double* tar_vel,
+                                               const unsigned char* joint_active, const double* kp, const double* kd,
+                                               double* inout_tau, double* out_mass, double* out_bias) {
+    if (!b || !pose || !vel || !tar_pose || !tar_vel || !inout_tau) {
+        trl_set_error("trl_imp_pd_update_control_force: null argument");
+        return TRL_ERR_INVALID_ARG;
+    }
+    if (!(dt > 0)) return TRL_OK;  // UpdateControlForce does nothing for time_step <= 0 (ImpPDController.cpp:56)
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    StepPtrs p{};
+    p.dt = dt;
+    p.tau_accumulate = 1;
+    p.status = b->d_status;
+    if (!in_ptr(b, pose, E * n, &p.pose) || !in_ptr(b, vel, E * n, &p.vel) || !in_ptr(b, tar_pose, E * n, &p.tar_pose) ||
+        !in_ptr(b, tar_vel, E * n, &p.tar_vel) || !in_ptr(b, joint_active, E * N, &p.joint_active) ||
+        !in_ptr(b, kp, E * N, &p.kp) || !in_ptr(b, kd, E * N, &p.kd) ||
+        !out_ptr(b, inout_tau, E * n, &p.tau, copies, true) || !out_ptr(b, out_mass, E * n * n, &p.out_mass, copies) ||
+        !out_ptr(b, out_bias, E * n, &p.out_bias, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_kin_tree_fk(trl_batch* b, const double* pose, double* out_joint_world, double* out_body_pos) {
+    if (!b || !pose) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double* d_pose;
+    double *d_jw, *d_bp;
+    if (!in_ptr(b, pose, E * n, &d_pose) || !out_ptr(b, out_joint_world, E * N * 12, &d_jw, copies) ||
+        !out_ptr(b, out_body_pos, E * N * 3, &d_bp, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_fk(b->d_model, b->model->dev, b->E, d_pose, d_jw, d_bp, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_kin_char_pose(trl_batch* b, const double* time, const double* origin_pos, const double* origin_rot,
+                                 double* out_pose, double* out_vel) {
+    if (!b || !time || !out_pose) return TRL_ERR_INVALID_ARG;
+    if (b->model->num_frames < 2) { trl_set_error("model has no motion"); return TRL_ERR_NO_MOTION; }
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double *d_t, *d_op, *d_or;
+    double *d_p, *d_v;
+    if (!in_ptr(b, time, E, &d_t) || !in_ptr(b, origin_pos, E * 3, &d_op) || !in_ptr(b, origin_rot, E * 4, &d_or) ||
+        !out_ptr(b, out_pose, E * n, &d_p, copies) || !out_ptr(b, out_vel, E * n, &d_v, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_kin_char(b->d_model, b->model->dev, b->d_frames, b->E, d_t, d_op, d_or, d_p, d_v, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_fields, int pieces_per_field,
+                                           const float* data, long long data_count, const long long* data_offset,
+                                           const int* res, const double* origin, const double* scale,
+                                           const double* bounds, const int* env_to_field) {
+    if (!b) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    cudaStreamSynchronize(b->stream);
+    if (b->d_ground_data) { cudaFree(b->d_ground_data); b->d_ground_data = nullptr; }
+    if (b->d_pieces) { cudaFree(b->d_pieces); b->d_pieces = nullptr; }
+    if (b->d_env_to_field) { cudaFree(b->d_env_to_field); b->d_env_to_field = nullptr; }
+    std::memset(&b->ground, 0, sizeof(b->ground));
+    b->ground.kind = kind;
+    if (kind == 0 || kind == 3) return TRL_OK;
+    if ((kind != 1 && kind != 2) || num_fields < 1 || pieces_per_field < 1 || pieces_per_field > 4 || !data ||
+        data_count < 1 || !data_offset || !res || !origin || !scale || !bounds) {
+        trl_set_error("trl_ground_set_heightfields: invalid argument");
+        b->ground.kind = 0;
+        return TRL_ERR_INVALID_ARG;
+    }
+    const size_t np = (size_t)num_fields * pieces_per_field;
+    std::vector<DevPiece> pieces(np);
+    for (size_t i = 0; i < np; ++i) {
+        DevPiece& pc = pieces[i];
+        pc.data_offset = data_offset[i];
+        pc.res_x = res[2 * i];
+        pc.res_z = res[2 * i + 1];
+        if (pc.res_x < 2 || pc.res_z < 1 || pc.data_offset < 0 ||
+            pc.data_offset + (long long)pc.res_x * pc.res_z > data_count) {
+            trl_set_error("trl_ground_set_heightfields: piece outside the data array");
+            b->ground.kind = 0;
+            return TRL_ERR_INVALID_ARG;
+        }
+        for (int k = 0; k < 3; ++k) { pc.origin[k] = origin[3 * i + k]; pc.scale[k] = scale[3 * i + k]; }
+        for (int k = 0; k < 4; ++k) pc.bounds[k] = bounds[4 * i + k];
+    }
+    if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * (size_t)data_count), "cudaMalloc(heightfields)") ||
+        !cuda_ok(cudaMemcpy(b->d_ground_data, data, sizeof(float) * (size_t)data_count, cudaMemcpyHostToDevice), "H2D(heightfields)") ||
+        !cuda_ok(cudaMalloc((void**)&b->d_pieces, sizeof(DevPiece) * np), "cudaMalloc(pieces)") ||
+        !cuda_ok(cudaMemcpy(b->d_pieces, pieces.data(), sizeof(DevPiece) * np, cudaMemcpyHostToDevice), "H2D(pieces)")) {
+        b->ground.kind = 0;
+        return TRL_ERR_CUDA;
+    }
+    if (env_to_field) {
+        for (int e = 0; e < b->E; ++e)
+            if (env_to_field[e] < 0 || env_to_field[e] >= num_fields) {
+                trl_set_error("trl_ground_set_heightfields: env_to_field out of range");
+                b->ground.kind = 0;
+                return TRL_ERR_INVALID_ARG;
+            }
+        if (!cuda_ok(cudaMalloc((void**)&b->d_env_to_field, sizeof(int) * (size_t)b->E), "cudaMalloc(env_to_field)") ||
+            !cuda_ok(cudaMemcpy(b->d_env_to_field, env_to_field, sizeof(int) * (size_t)b->E, cudaMemcpyHostToDevice), "H2D(env_to_field)")) {
+            b->ground.kind = 0;
+            return TRL_ERR_CUDA;
+        }
+    }
+    b->ground.num_fields = num_fields;
+    b->ground.pieces_per_field = pieces_per_field;
+    b->ground.data = b->d_ground_data;
+    b->ground.pieces = b->d_pieces;
+    b->ground.env_to_field = b->d_env_to_field;
+    return TRL_OK;
+}
+
+extern "C" int trl_ground_sample_height(trl_batch* b, const double* pos, int S, double* out_h,
+                                        unsigned char* out_valid, int* out_cell) {
+    if (!b || !pos || !out_h || S < 1) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    const size_t E = b->E;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double* d_pos;
+    double* d_h;
+    unsigned char* d_v;
+    int* d_c;
+    if (!in_ptr(b, pos, E * S * 3, &d_pos) || !out_ptr(b, out_h, E * S, &d_h, copies) ||
+        !out_ptr(b, out_valid, E * S, &d_v, copies) || !out_ptr(b, out_cell, E * S * 3, &d_c, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_sample_height(b->ground, b->E, d_pos, S, d_h, d_v, d_c, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const double* vel, const double* body_pos,
+                                    const double* body_vel, const double* body_quat, const double* body_angvel,
+                                    const double* ground_vel, const double* phase, const unsigned char* flip,
+                                    double* out_state, int* out_cell) {
+    if (!b || !pose || !body_pos || !body_vel || !out_state) return TRL_ERR_INVALID_ARG;
+    if (b->cfg.obs_kind == TRL_OBS_CT_3D && (!body_quat || !body_angvel)) {
+        trl_set_error("TRL_OBS_CT_3D needs body_quat and body_angvel");
+        return TRL_ERR_INVALID_ARG;
+    }
+    if (b->cfg.obs_kind == TRL_OBS_TERRAIN_RL_HOPPER && !vel) {
+        trl_set_error("TRL_OBS_TERRAIN_RL_HOPPER needs vel");
+        return TRL_ERR_INVALID_ARG;
+    }
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double *d_pose, *d_vel, *d_bp, *d_bv, *d_bq, *d_ba, *d_gv, *d_ph;
+    const unsigned char* d_fl;
+    double* d_state;
+    int* d_cell;
+    if (!in_ptr(b, pose, E * n, &d_pose) || !in_ptr(b, vel, E * n, &d_vel) || !in_ptr(b, body_pos, E * N * 3, &d_bp) ||
+        !in_ptr(b, body_vel, E * N * 3, &d_bv) || !in_ptr(b, body_quat, E * N * 4, &d_bq) ||
+        !in_ptr(b, body_angvel, E * N * 3, &d_ba) || !in_ptr(b, ground_vel, E * 3, &d_gv) || !in_ptr(b, phase, E, &d_ph) ||
+        !in_ptr(b, flip, E, &d_fl) || !out_ptr(b, out_state, E * (size_t)b->F, &d_state, copies) ||
+        !out_ptr(b, out_cell, E * (size_t)b->cfg.num_samples * 3, &d_cell, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, d_pose, d_vel, d_bp, d_bv,
+                                   d_bq, d_ba, d_gv, d_ph, d_fl, d_state, d_cell, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
+    if (!b || !a || !a->pose || !a->vel) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    StepPtrs p{};
+    p.dt = a->dt;
+    p.tau_accumulate = 0;
+    p.status = b->d_status;
+    const double *d_time, *d_op, *d_or, *d_bp, *d_bv, *d_ph;
+    const unsigned char* d_fl;
+    double *d_kp, *d_kv, *d_kbp, *d_state;
+    if (!in_ptr(b, a->pose, E * n, &p.pose) || !in_ptr(b, a->vel, E * n, &p.vel) ||
+        !in_ptr(b, a->tar_pose, E * n, &p.tar_pose) || !in_ptr(b, a->tar_vel, E * n, &p.tar_vel) ||
+        !in_ptr(b, a->joint_active, E * N, &p.joint_active) || !in_ptr(b, a->kin_time, E, &d_time) ||
+        !in_ptr(b, a->origin_pos, E * 3, &d_op) || !in_ptr(b, a->origin_rot, E * 4, &d_or) ||
+        !in_ptr(b, a->body_pos, E * N * 3, &d_bp) || !in_ptr(b, a->body_vel, E * N * 3, &d_bv) ||
+        !in_ptr(b, a->phase, E, &d_ph) || !in_ptr(b, a->flip, E, &d_fl) ||
+        !out_ptr(b, a->out_tau, E * n, &p.tau, copies) || !out_ptr(b, a->out_kin_pose, E * n, &d_kp, copies) ||
+        !out_ptr(b, a->out_kin_vel, E * n, &d_kv, copies) || !out_ptr(b, a->out_kin_body_pos, E * N * 3, &d_kbp, copies) ||
+        !out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies))
+        return TRL_ERR_CUDA;
+    int rc = 0;
+    if (p.tau) {
+        if (!p.tar_pose || !p.tar_vel) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
+        if (a->dt > 0) {
+            rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->stream);
+            b->launches += 1;
+        } else {
+            cudaMemsetAsync(p.tau, 0, sizeof(double) * E * n, b->stream);
+        }
+    }
+    if (!rc && d_kp) {
+        if (b->model->num_frames < 2 || !d_time) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
+        rc = trl_launch_kin_char(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, b->stream);
+        b->launches += 1;
+        if (!rc && d_kbp) {
+            rc = trl_launch_fk(b->d_model, b->model->dev, b->E, d_kp, nullptr, d_kbp, b->stream);
+            b->launches += 1;
+        }
+    }
+    if (!rc && d_state) {
+        if (!d_bp || !d_bv) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
+        rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, d_state, nullptr, b->stream);
+        b->launches += 1;
+    }
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_batch_get_status(trl_batch* b, int* out_status) {
+    if (!b || !out_status) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    cudaMemcpyKind kind = (b->ptr_mode == TRL_PTR_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (!cuda_ok(cudaMemcpyAsync(out_status, b->d_status, sizeof(int) * (size_t)b->E, kind, b->stream), "status copy")) return TRL_ERR_CUDA;
+    if (b->ptr_mode == TRL_PTR_HOST && !cuda_ok(cudaStreamSynchronize(b->stream), "sync")) return TRL_ERR_CUDA;
+    return TRL_OK;
+}
+
+extern "C" int trl_device_fp64_probe(int device, double* out_tflops) {
+    if (!out_tflops || device < 0) return TRL_ERR_INVALID_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= device) {
+        cudaGetLastError();
+        trl_set_error("trl_device_fp64_probe: no usable CUDA device");
+        return TRL_ERR_NO_DEVICE;
+    }
+    Guard g(device);
+    const double tf = trl_fp64_probe_tflops(nullptr);
+    if (tf < 0) { trl_set_error("fp64 probe failed"); return TRL_ERR_CUDA; }
+    *out_tflops = tf;
+    return TRL_OK;
+}

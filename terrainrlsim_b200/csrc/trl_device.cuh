@@ -1,0 +1,268 @@
+// Device-side math shared by the kernels: quaternion / rotation helpers (cMathUtil restated for the GPU),
+// joint-local transforms (cKinTree::ChildParentTrans*), and heightfield sampling (cGroundVar2D/3D).
+#pragma once
+
+#include <cfloat>
+#include <cuda_runtime.h>
+
+#include "trl_internal.h"
+
+#define TRL_DEV __device__ __forceinline__
+
+// ---- 3-vectors / 3x3 (row-major) ----
+TRL_DEV void cross3(const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+TRL_DEV void mat3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+
+TRL_DEV void mat3_mulv(const double* A, const double* x, double* y) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) y[r] = A[r * 3] * x[0] + A[r * 3 + 1] * x[1] + A[r * 3 + 2] * x[2];
+}
+
+TRL_DEV void mat3T_mulv(const double* A, const double* x, double* y) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) y[r] = A[r] * x[0] + A[3 + r] * x[1] + A[6 + r] * x[2];
+}
+
+// cMathUtil::RotateMat(quaternion): divides by |q|^2 (util/MathUtil.cpp:176-206). q = (w,x,y,z)
+TRL_DEV void quat_to_mat(double w, double x, double y, double z, double* R) {
+    double sqw = w * w, sqx = x * x, sqy = y * y, sqz = z * z;
+    double invs = 1.0 / (sqx + sqy + sqz + sqw);
+    R[0] = (sqx - sqy - sqz + sqw) * invs;
+    R[4] = (-sqx + sqy - sqz + sqw) * invs;
+    R[8] = (-sqx - sqy + sqz + sqw) * invs;
+    double t1 = x * y, t2 = z * w;
+    R[3] = 2.0 * (t1 + t2) * invs;
+    R[1] = 2.0 * (t1 - t2) * invs;
+    t1 = x * z; t2 = y * w;
+    R[6] = 2.0 * (t1 - t2) * invs;
+    R[2] = 2.0 * (t1 + t2) * invs;
+    t1 = y * z; t2 = x * w;
+    R[7] = 2.0 * (t1 + t2) * invs;
+    R[5] = 2.0 * (t1 - t2) * invs;
+}
+
+// Hamilton product, (w,x,y,z)
+TRL_DEV void quat_mul(const double* a, const double* b, double* r) {
+    r[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    r[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    r[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    r[3] = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+}
+
+TRL_DEV void quat_normalize(double* q) {
+    double n2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0];
+    if (n2 > 0) {
+        double n = sqrt(n2);
+        q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+    }
+}
+
+// Eigen's q * v  (v + w*t + u x t, t = 2 u x v)
+TRL_DEV void quat_rot_vec(const double* q, const double* v, double* o) {
+    double uv[3], uuv[3];
+    cross3(q + 1, v, uv);
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    cross3(q + 1, uv, uuv);
+    o[0] = v[0] + q[0] * uv[0] + uuv[0];
+    o[1] = v[1] + q[0] * uv[1] + uuv[1];
+    o[2] = v[2] + q[0] * uv[2] + uuv[2];
+}
+
+// cMathUtil::BuildQuaternionDiffMat(q) * w4 (util/MathUtil.cpp:418-426)
+TRL_DEV void quat_diff_mul(const double* q, const double* w, double* o) {
+    o[0] = -0.5 * q[1] * w[0] + -0.5 * q[2] * w[1] + -0.5 * q[3] * w[2];
+    o[1] = 0.5 * q[0] * w[0] + -0.5 * q[3] * w[1] + 0.5 * q[2] * w[2];
+    o[2] = 0.5 * q[3] * w[0] + 0.5 * q[0] * w[1] + -0.5 * q[1] * w[2];
+    o[3] = -0.5 * q[2] * w[0] + 0.5 * q[1] * w[1] + 0.5 * q[0] * w[2] + w[3];
+}
+
+// cMathUtil::CalcQuaternionVelRel (util/MathUtil.cpp:437-445) with QuaternionToAxisAngle's asin form (:399-416, Q3)
+TRL_DEV void quat_vel_rel(const double* q0, const double* q1, double dt, double* o) {
+    double c[4] = {q0[0], -q0[1], -q0[2], -q0[3]};
+    double d[4];
+    quat_mul(c, q1, d);
+    double st = sqrt(d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+    double theta = 0, ax = 0, ay = 0, az = 1;
+    if (st > 0.0001) {
+        double sg = (double)((0.0 < d[0]) - (d[0] < 0.0));
+        theta = 2 * sg * asin(st);
+        ax = d[1] / st; ay = d[2] / st; az = d[3] / st;
+    }
+    double s = theta / dt;
+    o[0] = s * ax; o[1] = s * ay; o[2] = s * az; o[3] = s * 0.0;
+}
+
+// Eigen 3.3 slerp followed by normalize (anim/KinTree.cpp:1544-1545)
+TRL_DEV void quat_slerp_norm(const double* a, double t, const double* b, double* r) {
+    const double one = 1.0 - DBL_EPSILON;
+    double d = a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[0] * b[0];
+    double ad = fabs(d);
+    double s0, s1;
+    if (ad >= one) {
+        s0 = 1.0 - t;
+        s1 = t;
+    } else {
+        double th = acos(ad);
+        double sn = sin(th);
+        s0 = sin((1.0 - t) * th) / sn;
+        s1 = sin(t * th) / sn;
+    }
+    if (d < 0) s1 = -s1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = s0 * a[i] + s1 * b[i];
+    quat_normalize(r);
+}
+
+// ---- joint-local child->parent transform [R(9) | t(3)], cKinTree::ChildParentTrans* (anim/KinTree.cpp:1794-1866) ----
+// For the root pass world=true to get A*T(pos)*R(quat); otherwise callers treat the root frame as the origin.
+TRL_DEV void joint_local_trans(const DevModel* __restrict__ M, int j, const double* q /* joint params */, double* R,
+                               double* t) {
+    const double* A = M->attR[j];
+    const double* at = M->attT[j];
+    const int type = (M->parent[j] == -1) ? -1 : M->type[j];
+    if (type == -1) {  // root: A * T * R
+        double Rq[9];
+        quat_to_mat(q[3], q[4], q[5], q[6], Rq);
+        mat3_mul(A, Rq, R);
+        mat3_mulv(A, q, t);
+        t[0] += at[0]; t[1] += at[1]; t[2] += at[2];
+    } else if (type == JT_REVOLUTE || type == JT_PLANAR) {
+        double th = (type == JT_REVOLUTE) ? q[0] : q[2];
+        double s, c;
+        sincos(th, &s, &c);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            R[r * 3 + 0] = A[r * 3 + 0] * c + A[r * 3 + 1] * s;
+            R[r * 3 + 1] = A[r * 3 + 1] * c - A[r * 3 + 0] * s;
+            R[r * 3 + 2] = A[r * 3 + 2];
+        }
+        if (type == JT_PLANAR) {  // A * R * T
+#pragma unroll
+            for (int r = 0; r < 3; ++r) t[r] = at[r] + R[r * 3] * q[0] + R[r * 3 + 1] * q[1];
+        } else {
+            t[0] = at[0]; t[1] = at[1]; t[2] = at[2];
+        }
+    } else if (type == JT_PRISMATIC) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = A[i];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) t[r] = at[r] + A[r * 3] * q[0];
+    } else if (type == JT_SPHERICAL) {
+        double Rq[9];
+        quat_to_mat(q[0], q[1], q[2], q[3], Rq);
+        mat3_mul(A, Rq, R);
+        t[0] = at[0]; t[1] = at[1]; t[2] = at[2];
+    } else {  // fixed
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = A[i];
+        t[0] = at[0]; t[1] = at[1]; t[2] = at[2];
+    }
+}
+
+// ---- heightfield sampling. Index arithmetic uses explicit round-to-nearest intrinsics so that nvcc never
+// contracts it into FMAs: cell indices must be bit-exact with the reference's double expression
+// (sim/GroundVar2D.cpp:652-681, GroundVar3D.cpp:602-621; SURVEY.md "Bit-exact terrain indices"). ----
+TRL_DEV double clampd(double v, double lo, double hi) {
+    double t = (v < hi) ? v : hi;
+    return (lo < t) ? t : lo;
+}
+
+TRL_DEV double grid_coord(double pos, double origin, double scale, int res) {
+    double c = __dsub_rn(pos, origin);
+    c = __ddiv_rn(c, scale);
+    return __dadd_rn(c, __dmul_rn((double)(res - 1), 0.5));
+}
+
+TRL_DEV double sample_segment_2d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
+                                 int* valid, int* cell) {
+    const double tol = 0.0001;
+    const int w = pc.res_x, l = pc.res_z;
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], w);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], l);
+    if (c0 > -tol && c0 < w - 1 + tol && c1 > -tol && c1 < l - 1 + tol) {
+        c0 = clampd(c0, 0.0, w - 1.0);
+        c1 = clampd(c1, 0.0, l - 1.0);
+    }
+    const bool outside = (c0 < 0 || c0 > w - 1 || c1 < 0 || c1 > l - 1);
+    *valid = !outside;
+    c0 = clampd(c0, 0.0, w - 1.0);
+    const int i = (int)c0;
+    const int j = (w - 1 < i + 1) ? (w - 1) : (i + 1);
+    const double lerp = __dsub_rn(c0, (double)i);
+    const float* row = data + pc.data_offset;
+    const double a = __dmul_rn((double)__ldg(row + i), pc.scale[1]);
+    const double b = __dmul_rn((double)__ldg(row + j), pc.scale[1]);
+    cell[0] = s; cell[1] = i; cell[2] = j;
+    return __dadd_rn(__dmul_rn(__dsub_rn(1.0, lerp), a), __dmul_rn(lerp, b));
+}
+
+TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
+                              int* valid, int* cell) {
+    const double tol = 0.0001;
+    const int rx = pc.res_x, rz = pc.res_z;
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], rx);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], rz);
+    c0 = clampd(c0, 0.0, rx - 1.0 - tol);
+    c1 = clampd(c1, 0.0, rz - 1.0 - tol);
+    const int i = (int)c0, j = (int)c1;
+    const double lx = __dsub_rn(c0, (double)i), lz = __dsub_rn(c1, (double)j);
+    const bool lower = (lz <= lx);
+    const int i0 = lower ? i : i + 1, j0 = lower ? j : j + 1;
+    const int i1 = lower ? i + 1 : i, j1 = lower ? j : j + 1;
+    const int i2 = lower ? i + 1 : i, j2 = lower ? j + 1 : j;
+    const float* base = data + pc.data_offset;
+    const double v0 = __dmul_rn((double)__ldg(base + (long long)j0 * rx + i0), pc.scale[1]);
+    const double v1 = __dmul_rn((double)__ldg(base + (long long)j1 * rx + i1), pc.scale[1]);
+    const double v2 = __dmul_rn((double)__ldg(base + (long long)j2 * rx + i2), pc.scale[1]);
+    // cMathUtil::CalcBarycentric on the unit triangle, same expression order (util/MathUtil.cpp:630-647)
+    double ax, az, bx, bz, cx, cz;
+    if (lower) { ax = 0; az = 0; bx = 1; bz = 0; cx = 1; cz = 1; }
+    else { ax = 1; az = 1; bx = 0; bz = 1; cx = 0; cz = 0; }
+    const double v0x = __dsub_rn(bx, ax), v0z = __dsub_rn(bz, az);
+    const double v1x = __dsub_rn(cx, ax), v1z = __dsub_rn(cz, az);
+    const double v2x = __dsub_rn(lx, ax), v2z = __dsub_rn(lz, az);
+    const double d00 = __dadd_rn(__dmul_rn(v0x, v0x), __dmul_rn(v0z, v0z));
+    const double d01 = __dadd_rn(__dmul_rn(v0x, v1x), __dmul_rn(v0z, v1z));
+    const double d11 = __dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1z, v1z));
+    const double d20 = __dadd_rn(__dmul_rn(v2x, v0x), __dmul_rn(v2z, v0z));
+    const double d21 = __dadd_rn(__dmul_rn(v2x, v1x), __dmul_rn(v2z, v1z));
+    const double denom = __dsub_rn(__dmul_rn(d00, d11), __dmul_rn(d01, d01));
+    const double bv = __ddiv_rn(__dsub_rn(__dmul_rn(d11, d20), __dmul_rn(d01, d21)), denom);
+    const double bw = __ddiv_rn(__dsub_rn(__dmul_rn(d00, d21), __dmul_rn(d01, d20)), denom);
+    const double bu = __dsub_rn(__dsub_rn(1.0, bv), bw);
+    *valid = 1;
+    cell[0] = s; cell[1] = i; cell[2] = j;
+    return __dadd_rn(__dadd_rn(__dmul_rn(bu, v0), __dmul_rn(bv, v1)), __dmul_rn(bw, v2));
+}
+
+// cGroundVar2D::SampleHeight / cGroundVar3D::SampleHeight (first containing piece wins; none: -inf, invalid)
+TRL_DEV double ground_sample_height(const DevGround& g, int env, double px, double pz, int* valid, int* cell) {
+    cell[0] = -1; cell[1] = 0; cell[2] = 0;
+    if (g.kind == 0 || g.kind == 3) {  // cGround::SampleHeight (sim/Ground.cpp:176-186)
+        *valid = 1;
+        return 0.0;
+    }
+    const int field = g.env_to_field ? __ldg(g.env_to_field + env) : (env % g.num_fields);
+    const DevPiece* pcs = g.pieces + (long long)field * g.pieces_per_field;
+    *valid = 0;
+    for (int s = 0; s < g.pieces_per_field; ++s) {
+        const DevPiece& pc = pcs[s];
+        if (g.kind == 1) {
+            if (px >= pc.bounds[0] && px <= pc.bounds[1]) return sample_segment_2d(pc, g.data, s, px, pz, valid, cell);
+        } else {
+            if (px >= pc.bounds[0] && px <= pc.bounds[1] && pz >= pc.bounds[2] && pz <= pc.bounds[3])
+                return sample_slab_3d(pc, g.data, s, px, pz, valid, cell);
+        }
+    }
+    return -CUDART_INF;
+}

@@ -1,0 +1,118 @@
+// Internal definitions shared by the host runtime and the CUDA kernels.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../include/trl_b200.h"
+
+// joint types, anim/KinTree.h:13-22
+enum { JT_REVOLUTE = 0, JT_PLANAR = 1, JT_PRISMATIC = 2, JT_FIXED = 3, JT_SPHERICAL = 4, JT_NONE = 5 };
+
+// live dof column kinds (how a column of the joint subspace S looks in the root frame),
+// cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828
+enum { CK_ANG = 0,      // omega = R_j[:,axis], v = p_j x omega   (revolute z, spherical x/y/z, planar theta, root ang)
+       CK_LIN = 1,      // omega = 0, v = R_j[:,axis]             (prismatic x, planar x/y)
+       CK_ROOT_LIN = 2  // omega = 0, v = row `axis` of R(root quat) (root translation, RBDUtil.cpp:776-783)
+};
+
+// Flattened, immutable character model as the kernels read it (resident in HBM, ~7 KB).
+struct DevModel {
+    int N;           // joints
+    int n;           // dofs incl. dead slots (cKinTree::GetNumDof)
+    int nl;          // live dof columns (dead: root slot 6, spherical slot 3)
+    int num_levels;  // tree depth levels
+    int num_frames;  // motion frames (0 = none)
+    int loop;
+    int has_spherical;
+    int pad0;
+    double gravity[3];
+    double motion_duration;
+    double cycle_delta[3];  // cKinCharacter::CalcCycleRootDelta, anim/KinCharacter.cpp:264-277
+
+    int parent[TRL_MAX_JOINTS];
+    int type[TRL_MAX_JOINTS];
+    int offset[TRL_MAX_JOINTS];
+    int size[TRL_MAX_JOINTS];
+    int valid_body[TRL_MAX_JOINTS];
+    int pd_valid[TRL_MAX_JOINTS];
+    int level[TRL_MAX_JOINTS];
+    int first_col[TRL_MAX_JOINTS];
+    int ncol[TRL_MAX_JOINTS];
+    int level_start[TRL_MAX_JOINTS + 1];
+    int level_joint[TRL_MAX_JOINTS];
+    double attR[TRL_MAX_JOINTS][9];  // cKinTree::BuildAttachTrans rotation (Rz*Ry*Rx of AttachTheta), row-major
+    double attT[TRL_MAX_JOINTS][3];  // attach point
+    double mass[TRL_MAX_JOINTS];
+    double com[TRL_MAX_JOINTS][3];    // body attach point = CoM in joint coordinates (RBDUtil.cpp:675-684)
+    double idiag[TRL_MAX_JOINTS][3];  // BuildMomentInertia{Box,Capsule} diagonal (RBDUtil.cpp:623-673)
+    double kp[TRL_MAX_JOINTS];
+    double kd[TRL_MAX_JOINTS];
+
+    int col_joint[TRL_MAX_DOF];
+    int col_kind[TRL_MAX_DOF];
+    int col_axis[TRL_MAX_DOF];
+    int col_dof[TRL_MAX_DOF];     // index into pose/vel vectors
+    int col_parent[TRL_MAX_DOF];  // Featherstone's lambda() expanded to dof columns, -1 at the top
+    int dof_col[TRL_MAX_DOF];     // dof -> live column or -1
+    int dof_joint[TRL_MAX_DOF];
+};
+
+struct trl_model {
+    int N = 0, n = 0;
+    std::vector<double> joint_mat, body_defs, pd_params;
+    std::vector<double> frames;  // [F][1+n], col 0 cumulative time
+    int num_frames = 0;
+    int loop = 0;
+    double gravity[3] = {0, -9.8, 0};
+    DevModel dev;
+};
+
+// per-piece terrain descriptor in HBM
+struct DevPiece {
+    long long data_offset;
+    int res_x, res_z;
+    double origin[3];
+    double scale[3];
+    double bounds[4];
+};
+
+struct DevGround {
+    int kind;  // 0 none, 1 var2d, 2 var3d, 3 plane
+    int num_fields;
+    int pieces_per_field;
+    int pad;
+    const float* data;
+    const DevPiece* pieces;   // [F][P]
+    const int* env_to_field;  // [E] or nullptr
+};
+
+void trl_set_error(const std::string& msg);
+int trl_build_dev_model(trl_model* m);  // fills m->dev; returns status
+
+// kernel launchers (trl_kernels.cu); all enqueue on `stream` and return a cudaError_t as int
+struct StepPtrs {
+    double dt;
+    const double *pose, *vel, *tar_pose, *tar_vel;
+    const unsigned char* joint_active;
+    const double *kp, *kd;
+    double* tau;
+    int tau_accumulate;
+    double *out_mass, *out_bias;
+    int* status;
+};
+
+size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block);
+int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream);
+int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
+                  double* out_body_pos, void* stream);
+int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
+                        const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
+                        void* stream);
+int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,
+                             unsigned char* out_valid, int* out_cell, void* stream);
+int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g, const trl_obs_cfg& cfg, int F,
+                          int E, const double* pose, const double* vel, const double* body_pos,
+                          const double* body_vel, const double* body_quat, const double* body_angvel,
+                          const double* ground_vel, const double* phase, const unsigned char* flip,
+                          double* out_state, int* out_cell, void* stream);

@@ -1,0 +1,971 @@
+// CUDA kernels (sm_100a) for the batched control-and-observation step.
+//
+// Layout: one warp per environment. All per-env intermediates live in a shared-memory workspace
+// (no global scratch), inputs/outputs are env-major in HBM so the lanes of a warp read/write
+// consecutive doubles of one env (coalesced).
+//
+// Stable PD (k_imp_pd), per env:
+//   P1  joint-local transforms (lanes <-> joints)                 cKinTree::ChildParentTrans
+//   P2  root-frame transforms by tree level (lanes <-> elements)  cRBDUtil::CalcWorldJointTransforms
+//   P3  joint subspace columns in the root frame                  cRBDUtil::BuildJointSubspace*
+//   P4  velocities / bias accelerations by level                  cRBDUtil::SolveInvDyna forward pass (qdd = 0)
+//   P5  rigid-body inertias (10-parameter form) + body forces     BuildInertiaSpatialMat, SolveInvDyna
+//   P6  subtree sums (composite inertias, forces)                 BuildMassMat reverse sweep, SolveInvDyna backward
+//   P7  mass matrix H and bias C on the live dofs                 BuildMassMat column walks
+//   P8  PD errors, right-hand side, H += dt*Kd                    cImpPDController::CalcControlForces
+//   P9  LDL^T factorisation + solve (live dofs only)              Eigen LDLT (zero pivot => 0)
+//   P10 tau = Kp e_p + Kd (e_v - dt qdd)
+// Everything is expressed in the root-joint frame: there, parent->child transforms are pure additions
+// for composite inertias and forces, so the only level-serial work is the 3x4 transform composition
+// and a 6-vector recurrence. Numbers agree with the reference's joint-local formulation to ~1e-13.
+#include <cstdint>
+#include <math_constants.h>
+
+#include "trl_device.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+// shared-memory workspace layout (in doubles) of k_imp_pd
+struct PdLayout {
+    int q, qd, Tl, T0, Rq, g0, cj, sj, V, A, IF, S, F, C, ep, ev, kpm, kdm, kdu, x, H, ldh, total;
+};
+
+__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl) {
+    PdLayout L;
+    int o = 0;
+    L.q = o; o += n;
+    L.qd = o; o += n;
+    L.Tl = o; o += 12 * N;
+    L.T0 = o; o += 12 * N;
+    L.Rq = o; o += 9;
+    L.g0 = o; o += 3;
+    L.cj = o; o += 3;
+    L.sj = o; o += 6 * N;
+    L.V = o; o += 6 * N;
+    L.A = o; o += 6 * N;
+    L.IF = o; o += 16 * N;
+    L.S = o; o += 6 * nl;
+    L.F = o; o += 6 * nl;
+    L.C = o; o += nl;
+    L.ep = o; o += n;
+    L.ev = o; o += n;
+    L.kpm = o; o += n;
+    L.kdm = o; o += n;
+    L.kdu = o; o += n;
+    L.x = o; o += nl;
+    L.ldh = nl | 1;  // odd row stride: conflict-free row-per-lane access
+    L.H = o; o += nl * L.ldh;
+    L.total = (o + 1) & ~1;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transforms in the root frame: Tl (local) -> T0 (root frame), level by level
+// ------------------------------------------------------------------------------------------------
+TRL_DEV void compose_levels(const DevModel* __restrict__ M, const double* Tl, double* T0, int lane, int first_level) {
+    const int nlev = M->num_levels;
+    for (int lv = first_level; lv < nlev; ++lv) {
+        const int beg = M->level_start[lv];
+        const int cnt = M->level_start[lv + 1] - beg;
+        for (int it = lane; it < cnt * 12; it += 32) {
+            const int j = M->level_joint[beg + it / 12];
+            const int el = it % 12;
+            const int p = M->parent[j];
+            const double* Rp = T0 + 12 * p;
+            const double* L = Tl + 12 * j;
+            double v;
+            if (el < 9) {
+                const int r = el / 3, c = el % 3;
+                v = Rp[r * 3] * L[c] + Rp[r * 3 + 1] * L[3 + c] + Rp[r * 3 + 2] * L[6 + c];
+            } else {
+                const int r = el - 9;
+                v = Rp[9 + r] + (Rp[r * 3] * L[9] + Rp[r * 3 + 1] * L[10] + Rp[r * 3 + 2] * L[11]);
+            }
+            T0[12 * j + el] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_imp_pd: stable-PD torques (and optionally M, C) -- one warp per env
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= E) return;
+    const int N = M->N, n = M->n, nl = M->nl;
+    const PdLayout L = pd_layout(N, n, nl);
+    double* ws = smem + (size_t)warp * L.total;
+    double* q = ws + L.q;
+    double* qd = ws + L.qd;
+    double* Tl = ws + L.Tl;
+    double* T0 = ws + L.T0;
+    double* Rq = ws + L.Rq;
+    double* g0 = ws + L.g0;
+    double* cj = ws + L.cj;
+    double* sj = ws + L.sj;
+    double* V = ws + L.V;
+    double* A = ws + L.A;
+    double* IF = ws + L.IF;
+    double* S = ws + L.S;
+    double* F = ws + L.F;
+    double* C = ws + L.C;
+    double* ep = ws + L.ep;
+    double* ev = ws + L.ev;
+    double* kpm = ws + L.kpm;
+    double* kdm = ws + L.kdm;
+    double* kdu = ws + L.kdu;
+    double* x = ws + L.x;
+    double* H = ws + L.H;
+    const int ldh = L.ldh;
+    const double dt = p.dt;
+
+    // P0: stage pose / vel (coalesced)
+    for (int i = lane; i < n; i += 32) {
+        q[i] = p.pose[(size_t)e * n + i];
+        qd[i] = p.vel[(size_t)e * n + i];
+    }
+    for (int i = lane; i < nl * ldh; i += 32) H[i] = 0.0;
+    __syncwarp();
+
+    // P1: joint-local transforms; the root lane also prepares R(q_root), gravity and c_root in the root frame
+    if (lane < N) {
+        const int j = lane;
+        double R[9], t[3];
+        if (j == 0) {
+            double Rw[9], tw[3];
+            joint_local_trans(M, 0, q, Rw, tw);  // world <- root (A*T*R)
+            double rq[9];
+            quat_to_mat(q[3], q[4], q[5], q[6], rq);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rq[i] = rq[i];
+            // a_0 = X_{world->root}(0, -g): E = Rw^T  (RBDUtil.cpp:17-18,59-60)
+            const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
+            double gg[3];
+            mat3T_mulv(Rw, ng, gg);
+            g0[0] = gg[0]; g0[1] = gg[1]; g0[2] = gg[2];
+            // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
+            double dq[4];
+            quat_diff_mul(q + 3, qd + 3, dq);
+            const double qw = q[3], qx = q[4], qy = q[5], qz = q[6];
+            const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
+            double m00 = 4 * (qw * dw + qx * dx), m11 = 4 * (qw * dw + qy * dy), m22 = 4 * (qw * dw + qz * dz);
+            double m10 = 2 * (dx * qy + qx * dy - dw * qz - qw * dz);
+            double m01 = 2 * (dx * qy + qx * dy + dw * qz + qw * dz);
+            double m20 = 2 * (dx * qz + qx * dz + dw * qy + qw * dy);
+            double m02 = 2 * (dx * qz + qx * dz - dw * qy - qw * dy);
+            double m21 = 2 * (dy * qz + qy * dz - dw * qx - qw * dx);
+            double m12 = 2 * (dy * qz + qy * dz + dw * qx + qw * dx);
+            cj[0] = m00 * qd[0] + m01 * qd[1] + m02 * qd[2];
+            cj[1] = m10 * qd[0] + m11 * qd[1] + m12 * qd[2];
+            cj[2] = m20 * qd[0] + m21 * qd[1] + m22 * qd[2];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            t[0] = t[1] = t[2] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) T0[i] = R[i];
+            T0[9] = T0[10] = T0[11] = 0.0;
+        } else {
+            joint_local_trans(M, j, q + M->offset[j], R, t);
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) Tl[12 * j + i] = R[i];
+        Tl[12 * j + 9] = t[0]; Tl[12 * j + 10] = t[1]; Tl[12 * j + 11] = t[2];
+    }
+    __syncwarp();
+
+    // P2: root-frame transforms
+    compose_levels(M, Tl, T0, lane, 1);
+
+    // P3: subspace columns S_c (6) in the root frame; then s_j = S_j qd_j
+    for (int c = lane; c < nl; c += 32) {
+        const int j = M->col_joint[c], kind = M->col_kind[c], a = M->col_axis[c];
+        const double* T = T0 + 12 * j;
+        double w[3] = {0, 0, 0}, v[3];
+        if (kind == CK_ANG) {
+            w[0] = T[a]; w[1] = T[3 + a]; w[2] = T[6 + a];
+            cross3(T + 9, w, v);
+        } else if (kind == CK_LIN) {
+            v[0] = T[a]; v[1] = T[3 + a]; v[2] = T[6 + a];
+        } else {  // CK_ROOT_LIN: row a of R(q_root)
+            v[0] = Rq[3 * a]; v[1] = Rq[3 * a + 1]; v[2] = Rq[3 * a + 2];
+        }
+        S[6 * c] = w[0]; S[6 * c + 1] = w[1]; S[6 * c + 2] = w[2];
+        S[6 * c + 3] = v[0]; S[6 * c + 4] = v[1]; S[6 * c + 5] = v[2];
+    }
+    __syncwarp();
+    if (lane < N) {
+        const int j = lane;
+        double s[6] = {0, 0, 0, 0, 0, 0};
+        const int c0 = M->first_col[j], nc = M->ncol[j];
+        for (int c = c0; c < c0 + nc; ++c) {
+            const double w = qd[M->col_dof[c]];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s[k] += S[6 * c + k] * w;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sj[6 * j + k] = s[k];
+        if (j == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) V[k] = s[k];
+            A[0] = A[1] = A[2] = 0.0;
+            A[3] = g0[0] + cj[0]; A[4] = g0[1] + cj[1]; A[5] = g0[2] + cj[2];
+        }
+    }
+    __syncwarp();
+
+    // P4: V_j = V_p + s_j ; a_j = a_p + V_p x s_j (motion cross product; V_j x s_j = V_p x s_j)
+    for (int lv = 1; lv < M->num_levels; ++lv) {
+        const int beg = M->level_start[lv];
+        const int cnt = M->level_start[lv + 1] - beg;
+        for (int it = lane; it < cnt * 6; it += 32) {
+            const int j = M->level_joint[beg + it / 6];
+            const int k = it % 6;
+            const int pj = M->parent[j];
+            const double* Vp = V + 6 * pj;
+            const double* s = sj + 6 * j;
+            const int i0 = k % 3, i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+            double cr;
+            if (k < 3) {
+                cr = Vp[i1] * s[i2] - Vp[i2] * s[i1];
+            } else {
+                cr = (Vp[3 + i1] * s[i2] - Vp[3 + i2] * s[i1]) + (Vp[i1] * s[3 + i2] - Vp[i2] * s[3 + i1]);
+            }
+            V[6 * j + k] = Vp[k] + s[k];
+            A[6 * j + k] = A[6 * pj + k] + cr;
+        }
+        __syncwarp();
+    }
+
+    // P5: body inertia in the root frame (m, h = m c, I about the frame origin) and f = I a + V x* (I V)
+    if (lane < N) {
+        const int j = lane;
+        double I[10];
+        double f[6] = {0, 0, 0, 0, 0, 0};
+        if (M->valid_body[j]) {
+            const double* T = T0 + 12 * j;
+            const double m = M->mass[j];
+            double c[3];
+            mat3_mulv(T, M->com[j], c);
+            c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
+            const double d0 = M->idiag[j][0], d1 = M->idiag[j][1], d2 = M->idiag[j][2];
+            // R diag R^T
+            double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
+            double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
+            double Ixz = T[0] * T[6] * d0 + T[1] * T[7] * d1 + T[2] * T[8] * d2;
+            double Iyy = T[3] * T[3] * d0 + T[4] * T[4] * d1 + T[5] * T[5] * d2;
+            double Iyz = T[3] * T[6] * d0 + T[4] * T[7] * d1 + T[5] * T[8] * d2;
+            double Izz = T[6] * T[6] * d0 + T[7] * T[7] * d1 + T[8] * T[8] * d2;
+            // parallel axis: + m (|c|^2 1 - c c^T)
+            Ixx += m * (c[1] * c[1] + c[2] * c[2]);
+            Iyy += m * (c[0] * c[0] + c[2] * c[2]);
+            Izz += m * (c[0] * c[0] + c[1] * c[1]);
+            Ixy -= m * c[0] * c[1];
+            Ixz -= m * c[0] * c[2];
+            Iyz -= m * c[1] * c[2];
+            I[0] = m; I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
+            I[4] = Ixx; I[5] = Ixy; I[6] = Ixz; I[7] = Iyy; I[8] = Iyz; I[9] = Izz;
+            const double* Vj = V + 6 * j;
+            const double* Aj = A + 6 * j;
+            const double* h = I + 1;
+            // I * a
+            double hxv[3], hxw[3];
+            cross3(h, Aj + 3, hxv);
+            cross3(h, Aj, hxw);
+            double na[3] = {Ixx * Aj[0] + Ixy * Aj[1] + Ixz * Aj[2] + hxv[0], Ixy * Aj[0] + Iyy * Aj[1] + Iyz * Aj[2] + hxv[1],
+                            Ixz * Aj[0] + Iyz * Aj[1] + Izz * Aj[2] + hxv[2]};
+            double fa[3] = {m * Aj[3] - hxw[0], m * Aj[4] - hxw[1], m * Aj[5] - hxw[2]};
+            // I * V
+            cross3(h, Vj + 3, hxv);
+            cross3(h, Vj, hxw);
+            double nv[3] = {Ixx * Vj[0] + Ixy * Vj[1] + Ixz * Vj[2] + hxv[0], Ixy * Vj[0] + Iyy * Vj[1] + Iyz * Vj[2] + hxv[1],
+                            Ixz * Vj[0] + Iyz * Vj[1] + Izz * Vj[2] + hxv[2]};
+            double fv[3] = {m * Vj[3] - hxw[0], m * Vj[4] - hxw[1], m * Vj[5] - hxw[2]};
+            // V x* (I V) = (w x n + v x f ; w x f)
+            double wxn[3], vxf[3], wxf[3];
+            cross3(Vj, nv, wxn);
+            cross3(Vj + 3, fv, vxf);
+            cross3(Vj, fv, wxf);
+            f[0] = na[0] + wxn[0] + vxf[0]; f[1] = na[1] + wxn[1] + vxf[1]; f[2] = na[2] + wxn[2] + vxf[2];
+            f[3] = fa[0] + wxf[0]; f[4] = fa[1] + wxf[1]; f[5] = fa[2] + wxf[2];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 10; ++i) I[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) IF[16 * j + i] = I[i];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) IF[16 * j + 10 + i] = f[i];
+    }
+    __syncwarp();
+
+    // P6: subtree sums, leaves -> root (joints are ordered parents-first, anim/KinTree.cpp:479-493)
+    for (int j = N - 1; j >= 1; --j) {
+        if (lane < 16) IF[16 * M->parent[j] + lane] += IF[16 * j + lane];
+        __syncwarp();
+    }
+
+    // P7: F_c = Ic_j S_c ; C_c = S_c . f_subtree ; H[c][c'] = F_c . S_c' along the ancestor chain
+    for (int c = lane; c < nl; c += 32) {
+        const int j = M->col_joint[c];
+        const double* I = IF + 16 * j;
+        const double* s = S + 6 * c;
+        const double m = I[0];
+        const double* h = I + 1;
+        double hxv[3], hxw[3];
+        cross3(h, s + 3, hxv);
+        cross3(h, s, hxw);
+        double Fc[6];
+        Fc[0] = I[4] * s[0] + I[5] * s[1] + I[6] * s[2] + hxv[0];
+        Fc[1] = I[5] * s[0] + I[7] * s[1] + I[8] * s[2] + hxv[1];
+        Fc[2] = I[6] * s[0] + I[8] * s[1] + I[9] * s[2] + hxv[2];
+        Fc[3] = m * s[3] - hxw[0];
+        Fc[4] = m * s[4] - hxw[1];
+        Fc[5] = m * s[5] - hxw[2];
+        const double* f = I + 10;
+        C[c] = s[0] * f[0] + s[1] * f[1] + s[2] * f[2] + s[3] * f[3] + s[4] * f[4] + s[5] * f[5];
+        for (int a = c; a >= 0; a = M->col_parent[a]) {
+            const double* sa = S + 6 * a;
+            const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
+            H[c * ldh + a] = hv;
+            H[a * ldh + c] = hv;
+        }
+    }
+    __syncwarp();
+
+    // optional outputs: cRBDModel::GetMassMat / GetBiasForce on the full n-dof layout (dead dofs are exact zeros)
+    if (p.out_mass) {
+        double* om = p.out_mass + (size_t)e * n * n;
+        for (int idx = lane; idx < n * n; idx += 32) {
+            const int ci = M->dof_col[idx / n], ck = M->dof_col[idx % n];
+            om[idx] = (ci >= 0 && ck >= 0) ? H[ci * ldh + ck] : 0.0;
+        }
+    }
+    if (p.out_bias) {
+        double* ob = p.out_bias + (size_t)e * n;
+        for (int i = lane; i < n; i += 32) {
+            const int ci = M->dof_col[i];
+            ob[i] = (ci >= 0) ? C[ci] : 0.0;
+        }
+    }
+
+    // P8: PD errors (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196)
+    if (lane < N) {
+        const int j = lane;
+        const int o = M->offset[j], sz = M->size[j];
+        const bool valid = M->pd_valid[j] != 0;
+        const bool active = valid && (p.joint_active ? (p.joint_active[(size_t)e * N + j] != 0) : true);
+        double kp = 0.0, kd = 0.0;
+        if (valid) {
+            kp = p.kp ? p.kp[(size_t)e * N + j] : M->kp[j];
+            kd = p.kd ? p.kd[(size_t)e * N + j] : M->kd[j];
+        }
+        const double* tq = p.tar_pose + (size_t)e * n + o;
+        const double* tqd = p.tar_vel + (size_t)e * n + o;
+        for (int i = 0; i < sz; ++i) {
+            kpm[o + i] = active ? kp : 0.0;
+            kdm[o + i] = active ? kd : 0.0;
+            kdu[o + i] = kd;  // unmasked gains go on the diagonal
+        }
+        if (!valid) {
+            for (int i = 0; i < sz; ++i) { ep[o + i] = 0.0; ev[o + i] = 0.0; }
+        } else if (M->type[j] == JT_SPHERICAL) {
+            double dq[4], qi[4], tar[4];
+            quat_diff_mul(q + o, qd + o, dq);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qi[i] = q[o + i] + dt * dq[i];
+            quat_normalize(qi);
+            // cPDController::PostProcessTargetPose / PostProcessTargetVel (PDController.cpp:430-461)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tar[i] = tq[i];
+            if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
+            else quat_normalize(tar);
+            double er[4];
+            quat_vel_rel(qi, tar, 1.0, er);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ep[o + i] = er[i];
+            ev[o] = tqd[0] - qd[o]; ev[o + 1] = tqd[1] - qd[o + 1]; ev[o + 2] = tqd[2] - qd[o + 2];
+            ev[o + 3] = 0.0 - qd[o + 3];
+        } else {
+            for (int i = 0; i < sz; ++i) {
+                const double pinc = q[o + i] + dt * qd[o + i];
+                ep[o + i] = (tq[i] - pinc) / 1.0;
+                ev[o + i] = tqd[i] - qd[o + i];
+            }
+        }
+    }
+    __syncwarp();
+    for (int c = lane; c < nl; c += 32) {
+        const int i = M->col_dof[c];
+        x[c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
+        H[c * ldh + c] += dt * kdu[i];
+    }
+    __syncwarp();
+
+    // P9: LDL^T (left-looking; lower = L, upper = L*D, diagonal = D), row i = k + lane so the pivot is in lane 0
+    int bad = 0;
+    for (int k = 0; k < nl; ++k) {
+        double v0 = 0.0, v1 = 0.0;
+        const int i0 = k + lane, i1 = k + lane + 32;
+        if (i0 < nl) {
+            v0 = H[i0 * ldh + k];
+            for (int qq = 0; qq < k; ++qq) v0 -= H[i0 * ldh + qq] * H[qq * ldh + k];
+        }
+        if (i1 < nl) {
+            v1 = H[i1 * ldh + k];
+            for (int qq = 0; qq < k; ++qq) v1 -= H[i1 * ldh + qq] * H[qq * ldh + k];
+        }
+        const double d = __shfl_sync(0xffffffffu, v0, 0);
+        const bool ok = fabs(d) > DBL_MIN;
+        if (!(d > DBL_MIN)) bad |= 2;
+        const double rd = ok ? 1.0 / d : 0.0;
+        __syncwarp();
+        if (i0 < nl) {
+            if (lane == 0) {
+                H[k * ldh + k] = d;
+            } else {
+                H[k * ldh + i0] = ok ? v0 : 0.0;
+                H[i0 * ldh + k] = v0 * rd;
+            }
+        }
+        if (i1 < nl) {
+            H[k * ldh + i1] = ok ? v1 : 0.0;
+            H[i1 * ldh + k] = v1 * rd;
+        }
+        __syncwarp();
+    }
+    // forward substitution L y = b
+    for (int k = 0; k < nl; ++k) {
+        const double yk = x[k];
+        for (int i = k + 1 + lane; i < nl; i += 32) x[i] -= H[i * ldh + k] * yk;
+        __syncwarp();
+    }
+    // D^-1 (zero pivot => 0, Eigen's pseudo-inverse of D)
+    for (int i = lane; i < nl; i += 32) {
+        const double d = H[i * ldh + i];
+        x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0;
+    }
+    __syncwarp();
+    // backward substitution L^T x = z
+    for (int k = nl - 1; k >= 0; --k) {
+        const double xk = x[k];
+        for (int i = lane; i < k; i += 32) x[i] -= H[k * ldh + i] * xk;
+        __syncwarp();
+    }
+
+    // P10: tau = Kp e_p + Kd (e_v - dt qdd)
+    for (int i = lane; i < n; i += 32) {
+        const int c = M->dof_col[i];
+        double acc;
+        if (c >= 0) {
+            acc = x[c];
+        } else {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
+            const double dg = dt * kdu[i];
+            const double rhs = kpm[i] * ep[i] + kdm[i] * ev[i];
+            acc = (fabs(dg) > DBL_MIN) ? rhs / dg : 0.0;
+        }
+        const double t = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
+        if (!isfinite(t)) bad |= 1;
+        double* out = p.tau + (size_t)e * n + i;
+        *out = p.tau_accumulate ? (*out + t) : t;
+    }
+    if (p.status) {
+        bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
+        if (lane == 0) p.status[e] = bad;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fk: cKinTree::JointWorldTrans for all joints + CalcBodyPartPos -- one warp per env
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_fk(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, double* __restrict__ out_joint_world,
+     double* __restrict__ out_body_pos) {
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= E) return;
+    const int N = M->N, n = M->n;
+    double* ws = smem + (size_t)warp * (n + 24 * N);
+    double* q = ws;
+    double* Tl = ws + n;
+    double* Tw = Tl + 12 * N;
+    for (int i = lane; i < n; i += 32) q[i] = pose[(size_t)e * n + i];
+    __syncwarp();
+    if (lane < N) {
+        double R[9], t[3];
+        joint_local_trans(M, lane, q + M->offset[lane], R, t);
+        double* dst = (lane == 0) ? Tw : (Tl + 12 * lane);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dst[i] = R[i];
+        dst[9] = t[0]; dst[10] = t[1]; dst[11] = t[2];
+    }
+    __syncwarp();
+    compose_levels(M, Tl, Tw, lane, 1);
+    if (out_joint_world) {
+        double* o = out_joint_world + (size_t)e * N * 12;
+        for (int idx = lane; idx < N * 12; idx += 32) {
+            const int j = idx / 12, el = idx % 12, r = el / 4, c = el % 4;
+            o[idx] = (c < 3) ? Tw[12 * j + r * 3 + c] : Tw[12 * j + 9 + r];
+        }
+    }
+    if (out_body_pos) {
+        double* o = out_body_pos + (size_t)e * N * 3;
+        for (int idx = lane; idx < N * 3; idx += 32) {
+            const int j = idx / 3, r = idx % 3;
+            const double* T = Tw + 12 * j;
+            const double* c = M->com[j];
+            o[idx] = M->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_kin_char: cKinCharacter::Pose(t) -- one thread per (env, joint)
+// ------------------------------------------------------------------------------------------------
+TRL_DEV void motion_index_phase(const DevModel* __restrict__ M, const double* __restrict__ frames, int fs, double time,
+                                int* idx, double* phase) {  // cMotion::CalcIndexPhase, anim/Motion.cpp:240-273
+    const double max_time = M->motion_duration;
+    const int nf = M->num_frames;
+    if (!M->loop) {
+        if (time <= 0) { *idx = 0; *phase = 0; return; }
+        if (time >= max_time) { *idx = nf - 2; *phase = 1; return; }
+    }
+    time = fmod(time, max_time);
+    if (time < 0) time += max_time;
+    int lo = 0, hi = nf;  // upper_bound
+    while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        if (!(time < __ldg(frames + (size_t)mid * fs))) lo = mid + 1; else hi = mid;
+    }
+    const int i = lo - 1;
+    const double t0 = __ldg(frames + (size_t)i * fs), t1 = __ldg(frames + (size_t)(i + 1) * fs);
+    *idx = i;
+    *phase = (time - t0) / (t1 - t0);
+}
+
+// pose of one joint at `time` (root: with cycle offset and origin transform, anim/KinCharacter.cpp:280-315)
+TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const double* __restrict__ frames, int fs, int j, double time,
+                            const double* opos, const double* orot, double* out /* size[j] */) {
+    int idx;
+    double ph;
+    motion_index_phase(M, frames, fs, time, &idx, &ph);
+    const double lerp = clampd(ph, 0.0, 1.0);
+    const int o = M->offset[j], sz = M->size[j];
+    const double* f0 = frames + (size_t)idx * fs + 1 + o;
+    const double* f1 = frames + (size_t)(idx + 1) * fs + 1 + o;
+    if (j == 0) {
+        double p[3], qa[4], qb[4], qr[4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = (1 - lerp) * __ldg(f0 + i) + lerp * __ldg(f1 + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + 3 + i); qb[i] = __ldg(f1 + 3 + i); }
+        quat_slerp_norm(qa, lerp, qb, qr);
+        double delta[3] = {0, 0, 0};
+        if (M->loop) {  // cMotion::CalcCycleCount, Motion.cpp:231-238
+            const int cyc = (int)floor(time / M->motion_duration);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) delta[i] = cyc * M->cycle_delta[i];
+        }
+        const double ident[4] = {1, 0, 0, 0};
+        double rdr[4], rr[4], rp[3];
+        quat_mul(orot, ident, rdr);
+        quat_mul(rdr, qr, rr);
+        quat_rot_vec(rdr, p, rp);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) out[i] = rp[i] + (delta[i] + opos[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[3 + i] = rr[i];
+    } else if (M->type[j] == JT_SPHERICAL) {
+        double qa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + i); qb[i] = __ldg(f1 + i); }
+        quat_slerp_norm(qa, lerp, qb, out);
+    } else {
+        for (int i = 0; i < sz; ++i) out[i] = (1 - lerp) * __ldg(f0 + i) + lerp * __ldg(f1 + i);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
+           const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
+           double* __restrict__ out_vel) {
+    const int N = M->N, n = M->n;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)E * N) return;
+    const int e = (int)(tid / N), j = (int)(tid % N);
+    const int fs = n + 1;
+    const double t = time[e];
+    double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
+    if (j == 0) {
+        if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
+        if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
+    }
+    double p0[7], p1[7];
+    kin_joint_pose(M, frames, fs, j, t, opos, orot, p0);
+    const int o = M->offset[j], sz = M->size[j];
+    for (int i = 0; i < sz; ++i) out_pose[(size_t)e * n + o + i] = p0[i];
+    if (out_vel) {
+        const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
+        kin_joint_pose(M, frames, fs, j, t + ddt, opos, orot, p1);
+        double v[7];
+        if (j == 0) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+            quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
+        } else if (M->type[j] == JT_SPHERICAL) {
+            quat_vel_rel(p0, p1, ddt, v);
+        } else {
+            for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+        }
+        for (int i = 0; i < sz; ++i) out_vel[(size_t)e * n + o + i] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_sample_height: cGround::SampleHeight(MatrixXd, VectorXd&) with the scalar overload's numerics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sample_height(DevGround g, int E, const double* __restrict__ pos, int S, double* __restrict__ out_h,
+                unsigned char* __restrict__ out_valid, int* __restrict__ out_cell) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)E * S) return;
+    const int e = (int)(tid / S);
+    int valid, cell[3];
+    const double h = ground_sample_height(g, e, pos[3 * tid], pos[3 * tid + 2], &valid, cell);
+    out_h[tid] = h;
+    if (out_valid) out_valid[tid] = (unsigned char)valid;
+    if (out_cell) { out_cell[3 * tid] = cell[0]; out_cell[3 * tid + 1] = cell[1]; out_cell[3 * tid + 2] = cell[2]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_poli_state: ParseGround + BuildPoliState -- one warp per env
+// ------------------------------------------------------------------------------------------------
+struct ObsDims { int G, psize, vsize, pos_dim, is_ct, is3d, F; };
+
+__host__ __device__ inline ObsDims obs_dims(int N, const trl_obs_cfg& cfg) {
+    ObsDims d;
+    d.G = cfg.num_samples;
+    d.is_ct = (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
+    d.is3d = (cfg.obs_kind == TRL_OBS_CT_3D);
+    d.pos_dim = d.is3d ? 3 : 2;
+    if (cfg.obs_kind == TRL_OBS_CT) { d.psize = N * 2 + 1; d.vsize = N * 2; }
+    else if (cfg.obs_kind == TRL_OBS_CT_3D) { d.psize = N * 7 + 1; d.vsize = N * 6; }
+    else { d.psize = N * 2 - 1; d.vsize = N * 2; }
+    d.F = d.G + d.psize + d.vsize + (cfg.num_phase_bins >= 0 ? 1 + cfg.num_phase_bins : 0);
+    return d;
+}
+
+// cMathUtil::RotMatToQuaternion (util/MathUtil.cpp:272-307) for a rotation about y by angle a: R = Ry(a)
+TRL_DEV void roty_to_quat(double c, double s, double m11, double* q) {
+    // R = [[c,0,s],[0,1,0],[-s,0,c]]
+    const double m00 = c, m22 = c;
+    const double tr = m00 + m11 + m22;
+    if (tr > 0) {
+        const double S = sqrt(tr + 1.0) * 2;
+        q[0] = 0.25 * S; q[1] = (0.0 - 0.0) / S; q[2] = (s - (-s)) / S; q[3] = (0.0 - 0.0) / S;
+    } else if ((m00 > m11) && (m00 > m22)) {
+        const double S = sqrt(1.0 + m00 - m11 - m22) * 2;
+        q[0] = (0.0 - 0.0) / S; q[1] = 0.25 * S; q[2] = (0.0 + 0.0) / S; q[3] = (s + (-s)) / S;
+    } else if (m11 > m22) {
+        const double S = sqrt(1.0 + m11 - m00 - m22) * 2;
+        q[0] = (s - (-s)) / S; q[1] = (0.0 + 0.0) / S; q[2] = 0.25 * S; q[3] = (0.0 + 0.0) / S;
+    } else {
+        const double S = sqrt(1.0 + m22 - m00 - m11) * 2;
+        q[0] = (0.0 - 0.0) / S; q[1] = (s + (-s)) / S; q[2] = (0.0 + 0.0) / S; q[3] = 0.25 * S;
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
+             const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
+             const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
+             const double* __restrict__ ground_vel, const double* __restrict__ phase,
+             const unsigned char* __restrict__ flip_arr, double* __restrict__ out_state, int* __restrict__ out_cell) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kWarpsPerBlock + warp;
+    if (e >= E) return;
+    const int N = M->N, n = M->n;
+    const ObsDims D = obs_dims(N, cfg);
+    const double* q = pose + (size_t)e * n;
+    double* out = out_state + (size_t)e * D.F;
+    const int flip = flip_arr ? (flip_arr[e] != 0) : 0;
+    const bool has_ground = g.kind != 0;
+
+    // cKinTree::CalcHeading / BuildOriginTrans (anim/KinTree.cpp:1604-1639): origin = Ry(-heading) * T(-root_xz)
+    const double rx = q[0], ry = q[1], rz = q[2];
+    const double qr[4] = {q[3], q[4], q[5], q[6]};
+    const double xdir[3] = {1, 0, 0};
+    double rd[3];
+    quat_rot_vec(qr, xdir, rd);
+    const double heading = atan2(-rd[2], rd[0]);
+    double sh, ch;
+    sincos(-heading, &sh, &ch);
+    // RotateMat(axis y, theta): [[c,0,s],[0,1,0],[-s,0,c]] (c + y*y*(1-c) on the diagonal, util/MathUtil.cpp:157-174)
+    const double o00 = ch, o02 = sh, o20 = -sh, o22 = ch;
+    const double o11 = ch + (1 - ch);
+    const double oz = 0.0;  // structurally-zero entries, kept in the products so inf/NaN propagate like the reference
+    // origin_trans = rot * translate(-origin): translation column = rot * (-x, -0, -z)
+    const double nx = -rx, ny = -0.0, nz = -rz;
+    const double ot0 = o00 * nx + oz * ny + o02 * nz;
+    const double ot1 = oz * nx + o11 * ny + oz * nz;
+    const double ot2 = o20 * nx + oz * ny + o22 * nz;
+
+    // ground height under the root (TerrainRLCharController.cpp:261-279,370-380)
+    int v0, c0[3];
+    double ground_h = 0.0;
+    if (has_ground) ground_h = ground_sample_height(g, e, rx, rz, &v0, c0);
+    const double ground_h_finite = isfinite(ground_h) ? ground_h : 0.0;
+
+    // ground sample transform = InvRigid(origin_trans), y += ground_h (finite)
+    // inverse rotation = transpose; translation = -(R^T t)
+    const double i00 = o00, i02 = o20, i20 = o02, i22 = o22, i11 = o11;
+    const double it0 = -(i00 * ot0 + oz * ot1 + i02 * ot2);
+    const double it1 = -(oz * ot0 + i11 * ot1 + oz * ot2) + ground_h_finite;
+    const double it2 = -(i20 * ot0 + oz * ot1 + i22 * ot2);
+
+    // ---- ground block ----
+    for (int s = lane; s < D.G; s += 32) {
+        double hs = 0.0;
+        int cell[3] = {-1, 0, 0};
+        if (has_ground) {
+            double lx, lz;
+            if (cfg.sampler == TRL_SAMPLER_LINE) {
+                lx = ((cfg.view_max - cfg.view_min) * s) / (D.G - 1) + cfg.view_min;
+                lz = 0.0;
+            } else {
+                const int res = cfg.grid_res;
+                const double ox = 0.5 * (cfg.view_max + cfg.view_min);
+                const double w = cfg.view_max - cfg.view_min;
+                const double u = (double)(s % res) / (res - 1);
+                const double v = (double)(s / res) / (res - 1);
+                lx = ox + (u - 0.5) * w;
+                lz = (v - 0.5) * w;
+                if (flip && D.is_ct) lz = -lz;
+            }
+            const double px = i00 * lx + i02 * lz + it0;
+            const double pz = i20 * lx + i22 * lz + it2;
+            int vs;
+            hs = ground_sample_height(g, e, px, pz, &vs, cell) - it1;
+        }
+        out[s] = hs;
+        if (out_cell) {
+            int* oc = out_cell + ((size_t)e * D.G + s) * 3;
+            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+        }
+    }
+
+    // ---- pose block ----
+    double* opose = out + D.G;
+    double* ovel = opose + D.psize;
+    const double zsign = (D.is_ct && flip) ? -1.0 : 1.0;
+    // root_pos_rel = origin_trans * (root - ground_h ey)
+    const double ryg = ry - ground_h;
+    const double rr0 = o00 * rx + oz * ryg + o02 * rz + ot0;
+    const double rr1 = oz * rx + o11 * ryg + oz * rz + ot1;
+    const double rr2 = zsign * (o20 * rx + oz * ryg + o22 * rz + ot2);
+    if (lane == 0) opose[0] = rr1;
+    const int first = D.is_ct ? 0 : 1;
+    const int per = D.pos_dim + (D.is3d ? 4 : 0);
+    // feature slot of body i: valid bodies are packed in index order
+    for (int i = first + lane; i < N; i += 32) {
+        if (!M->valid_body[i]) continue;
+        int slot = 0;
+        for (int k = first; k < i; ++k) slot += M->valid_body[k] ? 1 : 0;
+        const double* bp = body_pos + ((size_t)e * N + i) * 3;
+        const double bx = bp[0], by = bp[1] - ground_h, bz = bp[2];
+        const double f0 = (o00 * bx + oz * by + o02 * bz + ot0) - rr0;
+        const double f1 = (oz * bx + o11 * by + oz * bz + ot1) - rr1;
+        const double f2 = zsign * (o20 * bx + oz * by + o22 * bz + ot2) - rr2;
+        double* dst = opose + 1 + slot * per;
+        dst[0] = f0; dst[1] = f1;
+        if (D.is3d) {
+            dst[2] = f2;
+            double oq[4], bq[4], rq[4];
+            roty_to_quat(ch, sh, o11, oq);
+            const double* bqp = body_quat + ((size_t)e * N + i) * 4;
+            bq[0] = bqp[0]; bq[1] = bqp[1]; bq[2] = bqp[2]; bq[3] = bqp[3];
+            quat_mul(oq, bq, rq);
+            if (flip) { rq[1] = -rq[1]; rq[2] = -rq[2]; }
+            if (rq[0] < 0) { rq[0] = -rq[0]; rq[1] = -rq[1]; rq[2] = -rq[2]; rq[3] = -rq[3]; }
+            dst[3] = rq[0]; dst[4] = rq[1]; dst[5] = rq[2]; dst[6] = rq[3];
+        }
+    }
+    // ---- vel block ----
+    double gv[3] = {0, 0, 0};
+    if (ground_vel) { gv[0] = ground_vel[3 * (size_t)e]; gv[1] = ground_vel[3 * (size_t)e + 1]; gv[2] = ground_vel[3 * (size_t)e + 2]; }
+    const int vper = D.pos_dim + (D.is3d ? 3 : 0);
+    for (int i = lane; i < N; i += 32) {
+        const double* bv = body_vel + ((size_t)e * N + i) * 3;
+        const double vx = bv[0] - gv[0], vy = bv[1] - gv[1], vz = bv[2] - gv[2];
+        double* dst = ovel + i * vper;
+        dst[0] = o00 * vx + oz * vy + o02 * vz;
+        dst[1] = oz * vx + o11 * vy + oz * vz;
+        if (D.is3d) {
+            dst[2] = zsign * (o20 * vx + oz * vy + o22 * vz);
+            const double* av = body_angvel + ((size_t)e * N + i) * 3;
+            double a0 = o00 * av[0] + o02 * av[2];
+            double a1 = o11 * av[1];
+            double a2 = zsign * (o20 * av[0] + o22 * av[2]);
+            if (flip) { a0 = -a0; a1 = -a1; a2 = -a2; }
+            dst[3] = a0; dst[4] = a1; dst[5] = a2;
+        }
+    }
+    __syncwarp();
+    if (cfg.obs_kind == TRL_OBS_TERRAIN_RL_HOPPER && lane == 0) {
+        // cMonopedHopperController overrides: signed root rotation angle, root omega_z
+        double R[9];
+        quat_to_mat(qr[0], qr[1], qr[2], qr[3], R);
+        double c = (R[0] + R[4] + R[8] - 1) * 0.5;
+        c = clampd(c, -1.0, 1.0);
+        double theta = acos(c);
+        double az = 1.0;
+        if (!(fabs(theta) < 0.00001)) {
+            const double m21 = R[7] - R[5], m02 = R[2] - R[6], m10 = R[3] - R[1];
+            az = m10 / sqrt(m21 * m21 + m02 * m02 + m10 * m10);
+        }
+        if (az < 0) theta = -theta;
+        opose[D.psize - 1] = theta;
+        ovel[D.vsize - 1] = vel[(size_t)e * n + 5];
+    }
+    if (!D.is_ct && flip && lane == 0) {  // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830)
+        const int nlp = ((N - 1) / 2) * 2;
+        for (int i = 0; i < nlp; ++i) {
+            int a = D.psize - i - 1, b = D.psize - nlp - i - 1;
+            double t = opose[a]; opose[a] = opose[b]; opose[b] = t;
+            a = D.vsize - i - 1; b = D.vsize - nlp - i - 1;
+            t = ovel[a]; ovel[a] = ovel[b]; ovel[b] = t;
+        }
+    }
+    if (cfg.num_phase_bins >= 0 && lane == 0) {  // cCtPhaseController::BuildPhaseState (CtPhaseController.cpp:120-139)
+        double* ph = ovel + D.vsize;
+        const double pv = phase ? phase[e] : 0.0;
+        for (int i = 0; i < 1 + cfg.num_phase_bins; ++i) ph[i] = 0.0;
+        ph[0] = pv;
+        if (cfg.num_phase_bins > 0) {
+            const int bin = (int)(pv * cfg.num_phase_bins);
+            if (bin >= 0 && bin < cfg.num_phase_bins) ph[bin + 1] = 1.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_fp64_probe: register-resident DFMA chains, the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keeps the chain live, never true in practice
+}
+
+}  // namespace
+
+// returns achieved FP64 TFLOP/s of a pure DFMA loop on the current device (<0: CUDA error)
+double trl_fp64_probe_tflops(void* stream) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* out = nullptr;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_fp64_probe<<<blocks, threads, 0, st>>>(out, 64, 0.999999, 1e-9);  // warm-up
+    double best = -1.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, st);
+        k_fp64_probe<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, st);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block) {
+    return (size_t)pd_layout(hm.N, hm.n, hm.nl).total * sizeof(double) * (size_t)warps_per_block;
+}
+
+static int ensure_smem(const void* func, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (err != cudaSuccess) return (int)err;
+    }
+    return 0;
+}
+
+int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+    const size_t smem = trl_pd_smem_bytes(hm, kWarpsPerBlock);
+    int rc = ensure_smem((const void*)k_imp_pd, smem);
+    if (rc) return rc;
+    const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    k_imp_pd<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
+                  double* out_body_pos, void* stream) {
+    const size_t smem = (size_t)(hm.n + 24 * hm.N) * sizeof(double) * kWarpsPerBlock;
+    const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    k_fk<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(dm, E, pose, out_joint_world, out_body_pos);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
+                        const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
+                        void* stream) {
+    const long long total = (long long)E * hm.N;
+    const int blocks = (int)((total + 127) / 128);
+    k_kin_char<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,
+                             unsigned char* out_valid, int* out_cell, void* stream) {
+    const long long total = (long long)E * S;
+    const int blocks = (int)((total + 255) / 256);
+    k_sample_height<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, E, pos, S, out_h, out_valid, out_cell);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g, const trl_obs_cfg& cfg, int F,
+                          int E, const double* pose, const double* vel, const double* body_pos,
+                          const double* body_vel, const double* body_quat, const double* body_angvel,
+                          const double* ground_vel, const double* phase, const unsigned char* flip,
+                          double* out_state, int* out_cell, void* stream) {
+    (void)hm; (void)F;
+    const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    k_poli_state<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel,
+                                                                          body_quat, body_angvel, ground_vel, phase,
+                                                                          flip, out_state, out_cell);
+    return (int)cudaGetLastError();
+}
+
+int trl_obs_state_size(int N, const trl_obs_cfg& cfg) { return obs_dims(N, cfg).F; }

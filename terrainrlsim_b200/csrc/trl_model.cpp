@@ -1,0 +1,571 @@
+// Host-side model loader: reference character / motion JSON and arg files -> flat DevModel.
+// Mirrors the *data formats* of the reference loaders (cited per function); the parser is our own.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <sstream>
+
+#include "trl_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// error string (thread local, like errno)
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void trl_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* trl_last_error(void) { return g_last_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// minimal JSON reader (objects, arrays, strings, numbers, true/false/null, // and /* */ comments,
+// which the reference's jsoncpp reader also tolerates)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct JVal {
+    enum Kind { NUL, BOOL, NUM, STR, ARR, OBJ } kind = NUL;
+    double num = 0;
+    bool b = false;
+    std::string str;
+    std::vector<JVal> arr;
+    std::vector<std::pair<std::string, JVal>> obj;
+
+    const JVal* get(const std::string& key) const {
+        if (kind != OBJ) return nullptr;
+        for (const auto& kv : obj)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    bool is_null() const { return kind == NUL; }
+    bool is_numeric() const { return kind == NUM || kind == BOOL; }  // Json::Value::isNumeric counts bools
+    double as_double() const { return kind == NUM ? num : (kind == BOOL ? (b ? 1.0 : 0.0) : 0.0); }
+};
+
+class JParser {
+public:
+    explicit JParser(const std::string& s) : s_(s) {}
+    bool parse(JVal& out, std::string& err) {
+        try {
+            skip();
+            out = value();
+            skip();
+            if (p_ != s_.size()) throw std::string("trailing characters");
+            return true;
+        } catch (const std::string& e) {
+            std::ostringstream os;
+            os << e << " at byte " << p_;
+            err = os.str();
+            return false;
+        }
+    }
+
+private:
+    const std::string& s_;
+    size_t p_ = 0;
+
+    void skip() {
+        for (;;) {
+            while (p_ < s_.size() && (s_[p_] == ' ' || s_[p_] == '\t' || s_[p_] == '\n' || s_[p_] == '\r')) ++p_;
+            if (p_ + 1 < s_.size() && s_[p_] == '/' && s_[p_ + 1] == '/') {
+                while (p_ < s_.size() && s_[p_] != '\n') ++p_;
+            } else if (p_ + 1 < s_.size() && s_[p_] == '/' && s_[p_ + 1] == '*') {
+                p_ += 2;
+                while (p_ + 1 < s_.size() && !(s_[p_] == '*' && s_[p_ + 1] == '/')) ++p_;
+                p_ += 2;
+            } else {
+                return;
+            }
+        }
+    }
+    char peek() const { return p_ < s_.size() ? s_[p_] : '\0'; }
+    void expect(char c) {
+        if (peek() != c) throw std::string("expected '") + c + "'";
+        ++p_;
+    }
+    JVal value() {
+        skip();
+        char c = peek();
+        if (c == '{') return object();
+        if (c == '[') return array();
+        if (c == '"') {
+            JVal v;
+            v.kind = JVal::STR;
+            v.str = string();
+            return v;
+        }
+        if (s_.compare(p_, 4, "true") == 0) { p_ += 4; JVal v; v.kind = JVal::BOOL; v.b = true; return v; }
+        if (s_.compare(p_, 5, "false") == 0) { p_ += 5; JVal v; v.kind = JVal::BOOL; v.b = false; return v; }
+        if (s_.compare(p_, 4, "null") == 0) { p_ += 4; return JVal(); }
+        return number();
+    }
+    JVal number() {
+        const char* start = s_.c_str() + p_;
+        char* end = nullptr;
+        JVal v;
+        v.kind = JVal::NUM;
+        if (s_.compare(p_, 8, "Infinity") == 0) { p_ += 8; v.num = std::numeric_limits<double>::infinity(); return v; }
+        if (s_.compare(p_, 9, "-Infinity") == 0) { p_ += 9; v.num = -std::numeric_limits<double>::infinity(); return v; }
+        v.num = std::strtod(start, &end);
+        if (end == start) throw std::string("bad number");
+        p_ += static_cast<size_t>(end - start);
+        return v;
+    }
+    std::string string() {
+        expect('"');
+        std::string out;
+        while (p_ < s_.size() && s_[p_] != '"') {
+            if (s_[p_] == '\\' && p_ + 1 < s_.size()) {
+                char e = s_[p_ + 1];
+                switch (e) {
+                case 'n': out += '\n'; break;
+                case 't': out += '\t'; break;
+                case 'r': out += '\r'; break;
+                default: out += e; break;
+                }
+                p_ += 2;
+            } else {
+                out += s_[p_++];
+            }
+        }
+        expect('"');
+        return out;
+    }
+    JVal array() {
+        JVal v;
+        v.kind = JVal::ARR;
+        expect('[');
+        skip();
+        if (peek() == ']') { ++p_; return v; }
+        for (;;) {
+            v.arr.push_back(value());
+            skip();
+            if (peek() == ',') { ++p_; skip(); if (peek() == ']') { ++p_; return v; } continue; }
+            expect(']');
+            return v;
+        }
+    }
+    JVal object() {
+        JVal v;
+        v.kind = JVal::OBJ;
+        expect('{');
+        skip();
+        if (peek() == '}') { ++p_; return v; }
+        for (;;) {
+            skip();
+            std::string k = string();
+            skip();
+            expect(':');
+            JVal val = value();
+            v.obj.emplace_back(std::move(k), std::move(val));
+            skip();
+            if (peek() == ',') { ++p_; skip(); if (peek() == '}') { ++p_; return v; } continue; }
+            expect('}');
+            return v;
+        }
+    }
+};
+
+bool read_file(const char* path, std::string& out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+const char* kJointTypeNames[] = {"revolute", "planar", "prismatic", "fixed", "spherical", "none"};
+// key order = column order, anim/KinTree.cpp:25-46 (the last column's JSON key is "Offset")
+const char* kJointKeys[TRL_JOINT_COLS] = {"Type", "Parent", "AttachX", "AttachY", "AttachZ", "AttachThetaX",
+                                          "AttachThetaY", "AttachThetaZ", "LimLow0", "LimLow1", "LimLow2", "LimHigh0",
+                                          "LimHigh1", "LimHigh2", "TorqueLim", "ForceLim", "IsEndEffector",
+                                          "DiffWeight", "Offset"};
+// anim/KinTree.cpp:49-68
+const char* kBodyKeys[TRL_BODY_COLS] = {"Shape", "Mass", "ColGroup", "EnableFallContact", "AttachX", "AttachY",
+                                        "AttachZ", "AttachThetaX", "AttachThetaY", "AttachThetaZ", "Param0", "Param1",
+                                        "Param2", "ColorR", "ColorG", "ColorB", "ColorA"};
+// sim/PDController.cpp:8-27
+const char* kPDKeys[TRL_PD_COLS] = {"JointID", "Kp", "Kd", "TargetTheta0", "TargetTheta1", "TargetTheta2",
+                                    "TargetTheta3", "TargetTheta4", "TargetTheta5", "TargetTheta6", "TargetVel0",
+                                    "TargetVel1", "TargetVel2", "TargetVel3", "TargetVel4", "TargetVel5", "TargetVel6",
+                                    "UseWorldCoord"};
+
+int joint_param_size(int type) {  // cKinTree::GetJointParamSize, anim/KinTree.cpp:797-823
+    switch (type) {
+    case JT_REVOLUTE: return 1;
+    case JT_PRISMATIC: return 1;
+    case JT_PLANAR: return 3;
+    case JT_FIXED: return 0;
+    case JT_SPHERICAL: return 4;
+    default: return -1;
+    }
+}
+
+// cMathUtil::RotateMat(euler) = Rz*Ry*Rx, util/MathUtil.cpp:128-155
+void euler_to_mat(const double e[3], double R[9]) {
+    double xs = std::sin(e[0]), xc = std::cos(e[0]);
+    double ys = std::sin(e[1]), yc = std::cos(e[1]);
+    double zs = std::sin(e[2]), zc = std::cos(e[2]);
+    R[0] = yc * zc; R[3] = yc * zs; R[6] = -ys;
+    R[1] = xs * ys * zc - xc * zs; R[4] = xs * ys * zs + xc * zc; R[7] = xs * yc;
+    R[2] = xc * ys * zc + xs * zs; R[5] = xc * ys * zs - xs * zc; R[8] = xc * yc;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// flatten to DevModel
+// ------------------------------------------------------------------------------------------------
+int trl_build_dev_model(trl_model* m) {
+    DevModel& d = m->dev;
+    std::memset(&d, 0, sizeof(d));
+    const int N = m->N;
+    if (N < 1 || N > TRL_MAX_JOINTS) {
+        trl_set_error("model has too many joints (max 32)");
+        return TRL_ERR_UNSUPPORTED;
+    }
+    d.N = N;
+    int off = 0;
+    for (int j = 0; j < N; ++j) {
+        const double* jr = &m->joint_mat[(size_t)j * TRL_JOINT_COLS];
+        const double* br = &m->body_defs[(size_t)j * TRL_BODY_COLS];
+        const double* pr = &m->pd_params[(size_t)j * TRL_PD_COLS];
+        int type = (int)jr[0];
+        int parent = (int)jr[1];
+        if (j == 0 && parent != -1) { trl_set_error("joint 0 must be the root (Parent = -1)"); return TRL_ERR_UNSUPPORTED; }
+        if (j > 0 && (parent < 0 || parent >= j)) {  // anim/KinTree.cpp:479-493
+            trl_set_error("Parent id must be < child id");
+            return TRL_ERR_UNSUPPORTED;
+        }
+        int size = (parent == -1) ? 7 : joint_param_size(type);  // root is always 7 (KinTree.cpp:789-795)
+        if (size < 0) { trl_set_error("unsupported joint type"); return TRL_ERR_UNSUPPORTED; }
+        d.parent[j] = parent;
+        d.type[j] = type;
+        d.offset[j] = off;
+        d.size[j] = size;
+        off += size;
+        int shape = (int)br[0];
+        d.valid_body[j] = shape < 2;  // cKinTree::IsValidBody, KinTree.cpp:390-398
+        d.pd_valid[j] = (parent != -1) && d.valid_body[j];
+        euler_to_mat(jr + 5, d.attR[j]);
+        d.attT[j][0] = jr[2]; d.attT[j][1] = jr[3]; d.attT[j][2] = jr[4];
+        if (parent == -1) d.attT[j][0] = d.attT[j][1] = d.attT[j][2] = 0;  // PostProcessJointMat :1038-1040
+        d.level[j] = (parent == -1) ? 0 : d.level[parent] + 1;
+        d.mass[j] = 0;
+        if (d.valid_body[j]) {
+            double mass = br[1];
+            d.mass[j] = mass;
+            d.com[j][0] = br[4]; d.com[j][1] = br[5]; d.com[j][2] = br[6];
+            if (shape == 0) {  // box, RBDUtil.cpp:623-644
+                double sx = br[10], sy = br[11], sz = br[12];
+                d.idiag[j][0] = mass / 12.0 * (sy * sy + sz * sz);
+                d.idiag[j][1] = mass / 12.0 * (sx * sx + sz * sz);
+                d.idiag[j][2] = mass / 12.0 * (sx * sx + sy * sy);
+            } else {  // capsule, RBDUtil.cpp:646-673 (with the cm*cm term)
+                double r = br[10], h = br[11];
+                double c_vol = M_PI * r * r * h;
+                double hs_vol = M_PI * 2.0 / 3.0 * r * r * r;
+                double density = mass / (c_vol + 2 * hs_vol);
+                double cm = c_vol * density;
+                double hsm = hs_vol * density;
+                double x = cm * (0.25 * r * r + (1.0 / 12.0) * cm * h * h) +
+                           2 * hsm * (0.4 * r * r + 0.375 * r * h + 0.25 * h * h);
+                d.idiag[j][0] = x;
+                d.idiag[j][1] = (0.5 * cm + 0.8 * hsm) * r * r;
+                d.idiag[j][2] = x;
+            }
+        }
+        d.kp[j] = d.pd_valid[j] ? pr[1] : 0.0;  // cImpPDController::InitGains, ImpPDController.cpp:100-121
+        d.kd[j] = d.pd_valid[j] ? pr[2] : 0.0;
+        if (type == JT_SPHERICAL && parent != -1) d.has_spherical = 1;
+    }
+    d.n = off;
+    m->n = off;
+    if (off > TRL_MAX_DOF) { trl_set_error("model has too many dofs (max 64)"); return TRL_ERR_UNSUPPORTED; }
+
+    // live dof columns
+    int nl = 0;
+    for (int i = 0; i < TRL_MAX_DOF; ++i) d.dof_col[i] = -1;
+    for (int j = 0; j < N; ++j) {
+        d.first_col[j] = nl;
+        int o = d.offset[j];
+        auto add = [&](int kind, int axis, int dof) {
+            d.col_joint[nl] = j; d.col_kind[nl] = kind; d.col_axis[nl] = axis; d.col_dof[nl] = dof;
+            d.dof_col[dof] = nl;
+            ++nl;
+        };
+        if (d.parent[j] == -1) {
+            for (int k = 0; k < 3; ++k) add(CK_ROOT_LIN, k, o + k);
+            for (int k = 0; k < 3; ++k) add(CK_ANG, k, o + 3 + k);
+        } else {
+            switch (d.type[j]) {
+            case JT_REVOLUTE: add(CK_ANG, 2, o); break;
+            case JT_PRISMATIC: add(CK_LIN, 0, o); break;
+            case JT_PLANAR: add(CK_LIN, 0, o); add(CK_LIN, 1, o + 1); add(CK_ANG, 2, o + 2); break;
+            case JT_SPHERICAL: for (int k = 0; k < 3; ++k) add(CK_ANG, k, o + k); break;
+            default: break;
+            }
+        }
+        d.ncol[j] = nl - d.first_col[j];
+        for (int i = 0; i < d.size[j]; ++i) d.dof_joint[o + i] = j;
+    }
+    d.nl = nl;
+    for (int c = 0; c < nl; ++c) {
+        int j = d.col_joint[c];
+        if (c > d.first_col[j]) {
+            d.col_parent[c] = c - 1;
+        } else {
+            int p = d.parent[j];
+            while (p != -1 && d.ncol[p] == 0) p = d.parent[p];
+            d.col_parent[c] = (p == -1) ? -1 : d.first_col[p] + d.ncol[p] - 1;
+        }
+    }
+    // levels
+    int max_level = 0;
+    for (int j = 0; j < N; ++j) max_level = std::max(max_level, d.level[j]);
+    d.num_levels = max_level + 1;
+    int pos = 0;
+    for (int l = 0; l <= max_level; ++l) {
+        d.level_start[l] = pos;
+        for (int j = 0; j < N; ++j)
+            if (d.level[j] == l) d.level_joint[pos++] = j;
+    }
+    d.level_start[max_level + 1] = pos;
+
+    for (int k = 0; k < 3; ++k) d.gravity[k] = m->gravity[k];
+    d.num_frames = m->num_frames;
+    d.loop = m->loop;
+    if (m->num_frames > 0) {
+        const int fs = m->n + 1;
+        d.motion_duration = m->frames[(size_t)(m->num_frames - 1) * fs];  // cMotion::GetDuration, Motion.cpp:219-224
+        for (int k = 0; k < 3; ++k)
+            d.cycle_delta[k] = m->frames[(size_t)(m->num_frames - 1) * fs + 1 + k] - m->frames[1 + k];
+    }
+    return TRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: model
+// ------------------------------------------------------------------------------------------------
+extern "C" trl_model* trl_model_create(int num_joints, const double* joint_mat, const double* body_defs,
+                                       const double* pd_params, int num_frames, const double* frames, int loop,
+                                       const double* gravity) {
+    if (num_joints < 1 || !joint_mat || !body_defs || !pd_params) {
+        trl_set_error("trl_model_create: null matrix or num_joints < 1");
+        return nullptr;
+    }
+    std::unique_ptr<trl_model> m(new trl_model());
+    m->N = num_joints;
+    m->joint_mat.assign(joint_mat, joint_mat + (size_t)num_joints * TRL_JOINT_COLS);
+    m->body_defs.assign(body_defs, body_defs + (size_t)num_joints * TRL_BODY_COLS);
+    m->pd_params.assign(pd_params, pd_params + (size_t)num_joints * TRL_PD_COLS);
+    if (gravity) for (int k = 0; k < 3; ++k) m->gravity[k] = gravity[k];
+    // PostProcessJointMat (KinTree.cpp:1026-1041): recompute param offsets, zero the root attach point
+    {
+        int off = 0;
+        for (int j = 0; j < num_joints; ++j) {
+            double* jr = &m->joint_mat[(size_t)j * TRL_JOINT_COLS];
+            int size = ((int)jr[1] == -1) ? 7 : joint_param_size((int)jr[0]);
+            if (size < 0) { trl_set_error("unsupported joint type"); return nullptr; }
+            jr[18] = off;
+            off += size;
+        }
+        m->joint_mat[2] = m->joint_mat[3] = m->joint_mat[4] = 0;
+        m->n = off;
+    }
+    m->num_frames = 0;
+    m->loop = loop ? 1 : 0;
+    if (frames && num_frames > 0) {
+        const int fs = m->n + 1;
+        m->frames.assign(frames, frames + (size_t)num_frames * fs);
+        m->num_frames = num_frames;
+        double t = 0;  // cMotion::PostProcessFrames, Motion.cpp:207-217
+        for (int f = 0; f < num_frames; ++f) {
+            double dur = m->frames[(size_t)f * fs];
+            m->frames[(size_t)f * fs] = t;
+            t += dur;
+        }
+    }
+    if (trl_build_dev_model(m.get()) != TRL_OK) return nullptr;
+    return m.release();
+}
+
+extern "C" trl_model* trl_model_load(const char* character_json_path, const char* motion_json_path,
+                                     const double* gravity) {
+    if (!character_json_path) { trl_set_error("trl_model_load: null path"); return nullptr; }
+    std::string text, err;
+    if (!read_file(character_json_path, text)) {
+        trl_set_error(std::string("Failed to open ") + character_json_path);
+        return nullptr;
+    }
+    JVal root;
+    if (!JParser(text).parse(root, err)) {
+        trl_set_error(std::string("Failed to parse Json from ") + character_json_path + ": " + err);
+        return nullptr;
+    }
+    const JVal* skel = root.get("Skeleton");  // cCharacter::LoadSkeleton -> cKinTree::Load
+    const JVal* joints = skel ? skel->get("Joints") : nullptr;
+    const JVal* bodies = root.get("BodyDefs");
+    const JVal* pds = root.get("PDControllers");
+    if (!joints || joints->kind != JVal::ARR || joints->arr.empty()) {
+        trl_set_error("character file has no Skeleton.Joints");
+        return nullptr;
+    }
+    const int N = (int)joints->arr.size();
+    std::vector<double> jm((size_t)N * TRL_JOINT_COLS), bd((size_t)N * TRL_BODY_COLS, 0.0), pd((size_t)N * TRL_PD_COLS, 0.0);
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int j = 0; j < N; ++j) {
+        // cKinTree::BuildJointDesc defaults (KinTree.cpp:1153-1177) then ParseJoint (:980-1008)
+        double* r = &jm[(size_t)j * TRL_JOINT_COLS];
+        const double def[TRL_JOINT_COLS] = {0, -1, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 0, 0, inf, inf, 0, 1, 0};
+        std::memcpy(r, def, sizeof(def));
+        const JVal& jj = joints->arr[j];
+        const JVal* t = jj.get("Type");
+        int type = JT_NONE;
+        if (t && t->kind == JVal::STR) {
+            bool found = false;
+            for (int k = 0; k < 6; ++k)
+                if (t->str == kJointTypeNames[k]) { type = k; found = true; }
+            if (!found) { trl_set_error("Unsupported joint type: " + t->str); return nullptr; }
+        }
+        r[0] = type;
+        for (int k = 1; k < TRL_JOINT_COLS; ++k) {
+            const JVal* v = jj.get(kJointKeys[k]);
+            if (v && !v->is_null()) r[k] = v->as_double();
+        }
+    }
+    if (bodies && bodies->kind == JVal::ARR) {
+        if ((int)bodies->arr.size() != N) { trl_set_error("BodyDefs count != joint count"); return nullptr; }
+        for (int j = 0; j < N; ++j) {
+            // BuildBodyDef defaults (KinTree.cpp:1179-1200) then ParseBodyDef (:176-199)
+            double* r = &bd[(size_t)j * TRL_BODY_COLS];
+            r[2] = -1;
+            r[16] = 1;
+            const JVal& bj = bodies->arr[j];
+            const JVal* s = bj.get("Shape");
+            std::string shape = (s && s->kind == JVal::STR) ? s->str : "";
+            if (shape == "box") r[0] = 0;
+            else if (shape == "capsule") r[0] = 1;
+            else if (shape == "null") r[0] = 3;
+            else { trl_set_error("Unsupported body shape " + shape); return nullptr; }
+            for (int k = 0; k < TRL_BODY_COLS; ++k) {
+                const JVal* v = bj.get(kBodyKeys[k]);
+                if (v && !v->is_null() && v->is_numeric()) r[k] = v->as_double();
+            }
+        }
+    } else {
+        trl_set_error("Failed to load body definition");
+        return nullptr;
+    }
+    if (pds && pds->kind == JVal::ARR) {
+        if ((int)pds->arr.size() != N) { trl_set_error("PDControllers count != joint count"); return nullptr; }
+        for (int j = 0; j < N; ++j) {  // cPDController::ParsePDParams (PDController.cpp:73-91), JointID = index (:55)
+            double* r = &pd[(size_t)j * TRL_PD_COLS];
+            for (int k = 0; k < TRL_PD_COLS; ++k) {
+                const JVal* v = pds->arr[j].get(kPDKeys[k]);
+                if (v && !v->is_null() && v->is_numeric()) r[k] = v->as_double();
+            }
+            r[0] = j;
+        }
+    } else {
+        for (int j = 0; j < N; ++j) pd[(size_t)j * TRL_PD_COLS] = j;
+    }
+
+    std::vector<double> frames;
+    int num_frames = 0, loop = 0;
+    if (motion_json_path && motion_json_path[0]) {
+        std::string mt;
+        if (!read_file(motion_json_path, mt)) {
+            trl_set_error(std::string("Failed to load motion from file ") + motion_json_path);
+            return nullptr;
+        }
+        JVal mr;
+        if (!JParser(mt).parse(mr, err)) {
+            trl_set_error(std::string("Failed to parse Json from ") + motion_json_path + ": " + err);
+            return nullptr;
+        }
+        const JVal* lp = mr.get("Loop");
+        if (lp && !lp->is_null()) loop = lp->as_double() != 0;
+        const JVal* fr = mr.get("Frames");
+        if (fr && fr->kind == JVal::ARR && !fr->arr.empty()) {
+            num_frames = (int)fr->arr.size();
+            size_t fs = fr->arr[0].arr.size();
+            for (int f = 0; f < num_frames; ++f) {
+                if (fr->arr[f].kind != JVal::ARR || fr->arr[f].arr.size() != fs) {
+                    trl_set_error("motion frames have inconsistent sizes");
+                    return nullptr;
+                }
+                for (size_t i = 0; i < fs; ++i) frames.push_back(fr->arr[f].arr[i].as_double());
+            }
+            // dof check of cKinCharacter::LoadMotion (anim/KinCharacter.cpp:205-218)
+            int n = 0;
+            for (int j = 0; j < N; ++j) n += ((int)jm[(size_t)j * TRL_JOINT_COLS + 1] == -1) ? 7 : std::max(0, joint_param_size((int)jm[(size_t)j * TRL_JOINT_COLS]));
+            if ((int)fs != n + 1) {
+                char buf[128];
+                std::snprintf(buf, sizeof(buf), "DOF mismatch, char dof: %i, motion dof: %i", n, (int)fs - 1);
+                trl_set_error(buf);
+                return nullptr;
+            }
+        }
+    }
+    return trl_model_create(N, jm.data(), bd.data(), pd.data(), num_frames, frames.empty() ? nullptr : frames.data(),
+                            loop, gravity);
+}
+
+extern "C" int trl_model_dims(const trl_model* m, int* num_joints, int* num_dof, int* num_frames) {
+    if (!m) return TRL_ERR_INVALID_ARG;
+    if (num_joints) *num_joints = m->N;
+    if (num_dof) *num_dof = m->n;
+    if (num_frames) *num_frames = m->num_frames;
+    return TRL_OK;
+}
+
+extern "C" int trl_model_get_matrices(const trl_model* m, double* joint_mat, double* body_defs, double* pd_params) {
+    if (!m) return TRL_ERR_INVALID_ARG;
+    if (joint_mat) std::memcpy(joint_mat, m->joint_mat.data(), m->joint_mat.size() * sizeof(double));
+    if (body_defs) std::memcpy(body_defs, m->body_defs.data(), m->body_defs.size() * sizeof(double));
+    if (pd_params) std::memcpy(pd_params, m->pd_params.data(), m->pd_params.size() * sizeof(double));
+    return TRL_OK;
+}
+
+extern "C" int trl_model_get_motion(const trl_model* m, double* frames, int* loop) {
+    if (!m) return TRL_ERR_INVALID_ARG;
+    if (m->num_frames == 0) return TRL_ERR_NO_MOTION;
+    if (frames) std::memcpy(frames, m->frames.data(), m->frames.size() * sizeof(double));
+    if (loop) *loop = m->loop;
+    return TRL_OK;
+}
+
+extern "C" void trl_model_free(trl_model* m) { delete m; }
+
+// cArgParser file format (util/ArgParser.cpp): whitespace-separated tokens, "-key=" starts a key, the tokens
+// that follow (until the next key) are its values; "//" starts a comment to end of line.
+extern "C" int trl_arg_file_get(const char* path, const char* key, char* out_value, int out_capacity) {
+    if (!path || !key || !out_value || out_capacity < 1) return TRL_ERR_INVALID_ARG;
+    std::string text;
+    if (!read_file(path, text)) { trl_set_error(std::string("Failed to open ") + path); return TRL_ERR_IO; }
+    std::istringstream lines(text);
+    std::string line, cur_key, found;
+    bool have = false;
+    while (std::getline(lines, line)) {
+        size_t c = line.find("//");
+        if (c != std::string::npos) line = line.substr(0, c);
+        std::istringstream toks(line);
+        std::string tok;
+        while (toks >> tok) {
+            if (tok.size() > 2 && tok[0] == '-' && tok.back() == '=' && !(tok.size() > 1 && (isdigit(tok[1]) || tok[1] == '.'))) {
+                cur_key = tok.substr(1, tok.size() - 2);
+                if (cur_key == key) { have = true; found.clear(); }
+            } else if (cur_key == key && have) {
+                if (!found.empty()) found += ' ';
+                found += tok;
+            }
+        }
+    }
+    if (!have) return TRL_ERR_INVALID_ARG;
+    std::snprintf(out_value, (size_t)out_capacity, "%s", found.c_str());
+    return TRL_OK;
+}

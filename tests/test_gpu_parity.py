@@ -1,0 +1,287 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI
+(terrainrlsim_b200.api -> ctypes -> libtrl_b200.so), against the CPU oracle on the same seeded inputs.
+Bars: 1e-9 relative on torques / features / kinematics, bit-exact integer terrain cells and validity."""
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES
+from helpers import assert_close, oracle_cfg, product_cfg, oracle_grounds, rel_err
+from terrainrlsim_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def trl():
+    import terrainrlsim_b200 as t
+    return t
+
+
+def _setup(trl, oracle, name, E, with_ground=True, num_fields=8):
+    om = oracle.Model(name)
+    pm = trl.CharModel.from_name(name)
+    batch = trl.Batch(pm, E, 0, product_cfg(trl, name))
+    x = synth.make_inputs(name, E)
+    grounds = None
+    if with_ground:
+        kind, fields = synth.make_grounds(name, num_fields)
+        batch.ground_set_heightfields(kind, fields)
+        grounds = oracle_grounds(oracle, kind, fields)
+    return om, pm, batch, x, grounds
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_imp_pd_torque_mass_bias(trl, oracle, name):
+    E = 192
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    dt = 1.0 / 600
+    rng = np.random.default_rng(5)
+    tau0 = rng.normal(size=(E, om.n))
+    tau = tau0.copy()
+    tau, mass, bias = batch.imp_pd_update_control_force(dt, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"],
+                                                        joint_active=x["joint_active"], tau=tau, want_mass=True,
+                                                        want_bias=True)
+    ref_tau = np.zeros_like(tau)
+    ref_M = np.zeros_like(mass)
+    ref_C = np.zeros_like(bias)
+    for e in range(E):
+        ref_tau[e], ref_M[e], ref_C[e], _ = om.imp_pd(dt, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e],
+                                                       x["joint_active"][e], tau0=tau0[e])
+    assert_close(mass.reshape(E, -1), ref_M.reshape(E, -1), "mass matrix")
+    assert_close(bias, ref_C, "bias force")
+    assert_close(tau, ref_tau, "torque")
+    # dead dofs are exact zeros in M and C (Q1)
+    assert np.all(mass[:, 6, :] == 0) and np.all(mass[:, :, 6] == 0) and np.all(bias[:, 6] == 0)
+    assert np.all(batch.status() == 0)
+
+
+@pytest.mark.parametrize("name", ["hopper", "biped3d"])
+def test_imp_pd_gain_overrides_and_hopper_dt(trl, oracle, name):
+    E = 64
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    dt = 1.0 / 2400
+    rng = np.random.default_rng(7)
+    kp = rng.uniform(0, 500, size=(E, om.N))
+    kd = rng.uniform(0, 50, size=(E, om.N))
+    kd[:, -1] = 0  # a zero Kd on a live joint: diagonal gets nothing extra
+    act = (rng.uniform(size=(E, om.N)) < 0.7).astype(np.uint8)
+    tau, _, _ = batch.imp_pd_update_control_force(dt, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"],
+                                                  joint_active=act, kp=kp, kd=kd)
+    ref = np.zeros_like(tau)
+    for e in range(E):
+        ref[e] = om.imp_pd(dt, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e], act[e], kp[e], kd[e])[0]
+    assert_close(tau, ref, "torque with overrides")
+    # dt <= 0: UpdateControlForce does nothing
+    t2 = np.full((E, om.n), 3.0)
+    batch.imp_pd_update_control_force(0.0, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"], tau=t2)
+    assert np.all(t2 == 3.0)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_kin_tree_fk(trl, oracle, name):
+    E = 96
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    jw, bp = batch.kin_tree_fk(x["pose"])
+    ref_jw = np.zeros_like(jw)
+    ref_bp = np.zeros_like(bp)
+    for e in range(E):
+        for j in range(om.N):
+            ref_jw[e, j] = om.joint_world_trans(x["pose"][e], j)[:3, :].reshape(-1)
+            ref_bp[e, j] = om.body_part_pos(x["pose"][e], j)
+    assert_close(jw.reshape(E, -1), ref_jw.reshape(E, -1), "joint world transforms")
+    assert_close(bp.reshape(E, -1), ref_bp.reshape(E, -1), "body positions")
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_kin_char_pose(trl, oracle, name):
+    E = 128
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    t = x["kin_time"].copy()
+    t[:8] = [0.0, -0.37, 1e-9, om.frames[-1, 0], 2 * om.frames[-1, 0], om.frames[1, 0], -5.2, 123.456]
+    pose, vel = batch.kin_char_pose(t, x["origin_pos"], x["origin_rot"])
+    ref_p = np.zeros_like(pose)
+    ref_v = np.zeros_like(vel)
+    for e in range(E):
+        ref_p[e], ref_v[e] = om.kin_char_pose(t[e], x["origin_pos"][e], x["origin_rot"][e])
+    assert_close(pose, ref_p, "kin pose")
+    assert_close(vel, ref_v, "kin vel", rtol=1e-8)  # finite difference /(1/60) amplifies rounding by 60x
+    # NULL origin = zero / identity
+    pose2, _ = batch.kin_char_pose(t, None, None)
+    for e in range(4):
+        assert rel_err(pose2[e], om.kin_char_pose(t[e])[0]) <= 1e-9
+
+
+def test_kin_char_pose_non_looping(trl, oracle):
+    d = dict(synth.load_model_dict("dog"))
+    d["motion"] = {"loop": False, "frames": d["motion"]["frames"]}
+    om = oracle.Model(joint_mat=d["joint_mat"], body_defs=d["body_defs"], pd_params=d["pd_params"],
+                      frames=np.array(d["motion"]["frames"]), loop=False)
+    pm = trl.CharModel.from_dict(d)
+    E = 32
+    batch = trl.Batch(pm, E, 0)
+    t = np.linspace(-0.2, 1.2 * om.frames[-1, 0], E)
+    pose, vel = batch.kin_char_pose(t)
+    for e in range(E):
+        rp, rv = om.kin_char_pose(t[e])
+        assert rel_err(pose[e], rp) <= 1e-9
+        assert rel_err(vel[e], rv) <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["dog", "biped3d"])
+def test_ground_sample_height_bit_exact(trl, oracle, name):
+    E, S = 16, 300
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=5)
+    rng = np.random.default_rng(11)
+    pos = np.zeros((E, S, 3))
+    pos[:, :, 0] = rng.uniform(-45, 45, (E, S))
+    pos[:, :, 1] = rng.normal(size=(E, S))
+    pos[:, :, 2] = rng.uniform(-45, 45, (E, S)) if name == "biped3d" else rng.uniform(-1.2, 1.2, (E, S))
+    # exact grid vertices, piece boundaries, the tolerance band, and points far outside
+    pc = grounds[0].pieces[1]
+    sx = pc["scale"][0]
+    for k in range(40):
+        pos[0, k, 0] = pc["origin"][0] + sx * (k - (pc["res"][0] - 1) * 0.5)
+    pos[1, :6, 0] = [pc["bounds"][0], pc["bounds"][1], pc["bounds"][0] - 1e-12, pc["bounds"][1] + 1e-12, 1e9, -1e9]
+    pos[2, :4, 0] = [pc["origin"][0] + sx * ((pc["res"][0] - 1) * 0.5 + 0.00005),
+                     pc["origin"][0] + sx * ((pc["res"][0] - 1) * 0.5 + 0.0002), 0.0, -0.0]
+    h, valid, cell = batch.ground_sample_height(pos)
+    for e in range(E):
+        g = grounds[e % len(grounds)]
+        for s in range(S):
+            rh, rv, rc = g.sample_height(pos[e, s])
+            assert tuple(cell[e, s]) == rc, (e, s, cell[e, s], rc)
+            assert bool(valid[e, s]) == rv
+            assert (h[e, s] == rh) or (np.isnan(h[e, s]) and np.isnan(rh)), (e, s, h[e, s], rh)
+    assert np.any(~np.isfinite(h)) and np.any(valid == 0) and np.any(valid == 1)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_build_poli_state(trl, oracle, name):
+    E = 96
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=6)
+    cfg = oracle_cfg(oracle, name)
+    assert batch.F == oracle.poli_state_size(om, cfg)
+    state, cells = batch.build_poli_state(x["pose"], x["body_pos"], x["body_vel"], vel=x["vel"], phase=x["phase"],
+                                          flip=x["flip"], want_cells=True)
+    ref = np.zeros_like(state)
+    mism = 0
+    for e in range(E):
+        g = grounds[e % len(grounds)]
+        ref[e] = oracle.build_poli_state(om, g, cfg, x["pose"][e], x["vel"][e], x["body_pos"][e], x["body_vel"][e],
+                                         phase=x["phase"][e], flip=int(x["flip"][e]))
+        if cfg.num_samples > 0:
+            _, rc = oracle.parse_ground(g, cfg, x["pose"][e], int(x["flip"][e]))
+            mism += int(np.sum(np.any(rc != cells[e, :cfg.num_samples], axis=1)))
+    assert_close(state, ref, "policy state")
+    assert mism == 0, "terrain cell index mismatches: %d" % mism
+
+
+def test_build_poli_state_ct3d_and_no_ground(trl, oracle):
+    name = "biped3d"
+    E = 48
+    om = oracle.Model(name)
+    pm = trl.CharModel.from_name(name)
+    pcfg = trl.make_obs_cfg(obs_kind=3, sampler=1, num_samples=64, grid_res=8, view_min=-1.0, view_max=3.0, num_phase_bins=4)
+    ocfg = oracle.obs_cfg(obs_kind=3, sampler=1, num_samples=64, grid_res=8, view_min=-1.0, view_max=3.0, num_phase_bins=4)
+    batch = trl.Batch(pm, E, 0, pcfg)
+    x = synth.make_inputs(name, E)
+    rng = np.random.default_rng(3)
+    bq = rng.normal(size=(E, om.N, 4))
+    bq /= np.linalg.norm(bq, axis=2, keepdims=True)
+    ba = rng.normal(size=(E, om.N, 3))
+    gv = rng.normal(size=(E, 3)) * 0.1
+    kind, fields = synth.make_grounds(name, 3)
+    batch.ground_set_heightfields(kind, fields)
+    grounds = oracle_grounds(oracle, kind, fields)
+    state = batch.build_poli_state(x["pose"], x["body_pos"], x["body_vel"], vel=x["vel"], body_quat=bq, body_angvel=ba,
+                                   ground_vel=gv, phase=x["phase"], flip=x["flip"])
+    for e in range(E):
+        ref = oracle.build_poli_state(om, grounds[e % 3], ocfg, x["pose"][e], x["vel"][e], x["body_pos"][e],
+                                      x["body_vel"][e], bq[e], ba[e], gv[e], x["phase"][e], int(x["flip"][e]))
+        assert rel_err(state[e], ref) <= 1e-9
+    # no ground registered: samples are zeros (cTerrainRLCharController::ParseGround without a ground)
+    batch.ground_set_heightfields(0, None)
+    state = batch.build_poli_state(x["pose"], x["body_pos"], x["body_vel"], vel=x["vel"], body_quat=bq, body_angvel=ba,
+                                   phase=x["phase"], flip=x["flip"])
+    for e in range(4):
+        ref = oracle.build_poli_state(om, None, ocfg, x["pose"][e], x["vel"][e], x["body_pos"][e], x["body_vel"][e],
+                                      bq[e], ba[e], None, x["phase"][e], int(x["flip"][e]))
+        assert rel_err(state[e], ref) <= 1e-9
+
+
+def test_root_outside_terrain_features_propagate_inf(trl, oracle):
+    """Q11: a root outside every piece gives -inf heights; ParseGround replaces the root height by 0 but the
+    pose block still carries the non-finite values, exactly like the reference arithmetic."""
+    name = "dog"
+    E = 8
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=2)
+    x["pose"][:, 0] = 500.0
+    cfg = oracle_cfg(oracle, name)
+    state = batch.build_poli_state(x["pose"], x["body_pos"], x["body_vel"], vel=x["vel"])
+    for e in range(E):
+        ref = oracle.build_poli_state(om, grounds[e % 2], cfg, x["pose"][e], x["vel"][e], x["body_pos"][e], x["body_vel"][e])
+        assert np.array_equal(np.isnan(state[e]), np.isnan(ref))
+        assert np.array_equal(np.isinf(state[e]), np.isinf(ref))
+        assert rel_err(state[e], ref) <= 1e-9
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_step_fused_matches_oracle(trl, oracle, name):
+    E = 128
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=7)
+    cfg = oracle_cfg(oracle, name)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    out = batch.step_fused(dt, x)
+    ref = oracle.step_range(om, cfg, dict(x), grounds, dt)
+    assert_close(out["tau"], ref["tau"], "fused tau")
+    assert_close(out["state"], ref["state"], "fused state")
+    assert_close(out["kin_pose"], ref["kin_pose"], "fused kin pose")
+    assert_close(out["kin_vel"], ref["kin_vel"], "fused kin vel", rtol=1e-8)
+    assert_close(out["kin_body_pos"].reshape(E, -1), ref["kin_body_pos"].reshape(E, -1), "fused kin body pos")
+
+
+def test_device_pointer_mode_equals_host_mode(trl, oracle):
+    import torch
+    name = "biped3d"
+    E = 256
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=4)
+    dt = 1.0 / 600
+    host = batch.step_fused(dt, x)
+    dev_in = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
+    batch.use_torch_stream()
+    dev = batch.step_fused(dt, dev_in)
+    batch.sync()
+    torch.cuda.synchronize()
+    for k in host:
+        assert np.array_equal(host[k], dev[k].cpu().numpy(), equal_nan=True), k
+    batch.set_stream(None)
+
+
+@pytest.mark.parametrize("name,E", [("hopper", 4096), ("dog", 4096), ("raptor", 8192), ("biped3d", 16384), ("biped2d", 4096)])
+def test_full_size_properties(trl, oracle, name, E):
+    """BASELINE.json full sizes: determinism, env-permutation equivariance (bit-exact), and oracle parity on a
+    random subset of 128 envs."""
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=16)
+    cfg = oracle_cfg(oracle, name)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    out1 = {k: v.copy() for k, v in batch.step_fused(dt, x).items()}
+    out2 = batch.step_fused(dt, x)
+    for k in out1:
+        assert np.array_equal(out1[k], out2[k], equal_nan=True), "non-deterministic " + k
+    # permutation that keeps each env on its terrain (env % 16 preserved)
+    rng = np.random.default_rng(2)
+    perm = np.arange(E).reshape(-1, 16)
+    perm = perm[rng.permutation(perm.shape[0])].reshape(-1)
+    xp = {k: np.ascontiguousarray(v[perm]) for k, v in x.items()}
+    outp = batch.step_fused(dt, xp)
+    for k in out1:
+        assert np.array_equal(out1[k][perm], outp[k], equal_nan=True), "not permutation-equivariant: " + k
+    assert np.all(batch.status() == 0)
+    sub = np.sort(rng.choice(E, 128, replace=False))
+    xs = {k: np.ascontiguousarray(v[sub]) for k, v in x.items()}
+    ref = oracle.step_range(om, cfg, xs, grounds, dt, env_to_ground=(sub % 16).astype(np.int32))
+    assert_close(out1["tau"][sub], ref["tau"], "full-size tau")
+    assert_close(out1["state"][sub], ref["state"], "full-size state")
+    assert_close(out1["kin_pose"][sub], ref["kin_pose"], "full-size kin pose")
