@@ -1,0 +1,501 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/sec of the batched stable-PD + FK/mocap + terrain + feature-pack step.
+
+    python bench.py --gpus N --steps K --warmup W [--config biped3d] [--impl reference]
+
+One "step" = one pass of the fused hot path (trl_step_fused) over the E environments of one GPU:
+stable-PD torque (CRBA + RNEA + LDL^T), kin-char pose+vel, FK of the kin pose, G terrain samples, F packed
+features. Default workload: biped3D, 16384 envs/GPU -- the configuration
+BASELINE.json's north_star target is quoted on; the other configs' throughput is measured in the same run
+and reported under "other_workloads" (short runs), hopper (configs[1]) included.
+
+value  : whole-job env-steps/s with every input already resident in HBM (DEVICE pointer mode, CUDA events,
+         max over ranks). L2 is defeated by rotating over R input/output sets whose total footprint is > 2.5x L2.
+e2e    : same metric through the public HOST-pointer API (pinned host buffers; H2D of every input and D2H of
+         every output inside the timed region, each step).
+roofline: dominant kernel (k_imp_pd) -- algorithmic FP64 flops per launch (SURVEY.md 8d table x E) over its
+         CUDA-event time, against the FP64 DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry);
+         roofline_step_hbm does the same for the whole step's algorithmic bytes against the measured HBM copy peak.
+cpu_baseline / --impl reference: the CPU oracle (a faithful restatement of the reference's algorithms; the
+         reference itself needs Eigen+Bullet and cannot be built here) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "stable-PD+FK+terrain env-steps/sec"
+UNIT = "env-steps/s"
+L2_BYTES = 126 * 1024 * 1024
+
+# SURVEY.md section 8(d) cost model (structure-exploiting count), per env-step
+ROOFLINE_MODEL = {
+    # name: (PD+RBD flops, total flops, algorithmic bytes)
+    "biped2d": (12.6e3, 14.2e3, 1.56e3),
+    "hopper": (3.3e3, 7.8e3, 3.7e3),
+    "dog": (27.9e3, 34.7e3, 5.7e3),
+    "raptor": (23.0e3, 29.5e3, 5.5e3),
+    "biped3d": (16.3e3, 33.0e3, 6.5e3),
+}
+WORKLOAD_NAMES = {
+    "biped2d": "genBiped2D imitation (biped2D_full.txt, ct_pd_phase)",
+    "hopper": "monopedHopper (monoped_hopper0.txt) on var2d_mixed",
+    "dog": "dog 2D (dog.txt) on var2d_mixed",
+    "raptor": "raptor 2D (raptor.txt) on var2d_flat",
+    "biped3d": "biped3D (biped_3D.txt) 3D stable-PD on var3d_flat",
+}
+
+
+def roofline_model(name):
+    pd, total, byt = ROOFLINE_MODEL[name]
+    return {"pd_flops_per_env_step": pd, "total_flops_per_env_step": total, "bytes_per_env_step": byt}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (test infrastructure used here only as the measured CPU baseline)
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_run(name, sample_envs, passes, threads):
+    """Runs `passes` passes of the oracle's fused step over `sample_envs` envs split across `threads` threads
+    (one thread per env range, like cScenarioTrain::Run). Returns seconds."""
+    from oracle import oracle_py
+    from terrainrlsim_b200 import synth
+    om = oracle_py.Model(name)
+    cfg = oracle_py.obs_cfg(**synth.obs_config(name))
+    kind, fields = synth.make_grounds(name, min(sample_envs, 32))
+    grounds = [oracle_py.Ground(kind, p) for p in fields]
+    x = synth.make_inputs(name, sample_envs)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    arrays = dict(x)
+    oracle_py.step_range(om, cfg, arrays, grounds, dt, 0, min(8, sample_envs))  # allocate outputs, warm up
+    bounds = np.linspace(0, sample_envs, threads + 1).astype(int)
+
+    def work(lo, hi):
+        for _ in range(passes):
+            oracle_py.step_range(om, cfg, arrays, grounds, dt, int(lo), int(hi))
+
+    ts = [threading.Thread(target=work, args=(bounds[i], bounds[i + 1])) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(name, target_seconds=6.0):
+    threads = os.cpu_count() or 1
+    sample = 256 * threads
+    t = cpu_oracle_run(name, sample, 1, threads)
+    passes = max(1, int(target_seconds / max(t, 1e-6)))
+    t = cpu_oracle_run(name, sample, passes, threads)
+    val = sample * passes / t
+    return {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs x %d passes of the C oracle (faithful restatement; faster than the Eigen reference: "
+                      "no heap temporaries), one thread per env range, %d threads" % (sample, passes, threads)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port on all host cores."""
+    if rank != 0:
+        return
+    name = args.config
+    threads = os.cpu_count() or 1
+    sample = 128 * threads
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_run(name, sample, 1, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_oracle_run(name, sample, 1, threads)
+    val = sample * args.steps / t
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD_NAMES[name], "envs_per_step_sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "each step = one oracle pass over %d envs (bounded sample of the workload), "
+                                       "%d threads" % (sample, threads)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s in sm if s >= 0.5 * max(sm)]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class Workload:
+    """One config on one GPU: model, batch, terrain, R rotating device-resident input/output sets."""
+
+    def __init__(self, name, E, device, rank, sets=None, fields=None):
+        import torch
+        import terrainrlsim_b200 as trl
+        from terrainrlsim_b200 import synth
+        self.name, self.E, self.device = name, E, device
+        self.d = synth.load_model_dict(name)
+        self.dt = (1.0 / 30) / self.d["num_update_steps"]
+        self.model = trl.CharModel.from_name(name)
+        self.batch = trl.Batch(self.model, E, device, trl.make_obs_cfg(**synth.obs_config(name)))
+        is3d = self.d["terrain"].startswith("var3d")
+        if fields is None:
+            fields = min(E, 1024 if is3d else 4096)
+        self.num_fields = fields
+        kind, fl = synth.make_grounds(name, fields, rank=rank)
+        self.batch.ground_set_heightfields(kind, fl)
+        del fl
+        n, N, F = self.model.num_dof, self.model.num_joints, self.batch.F
+        self.in_bytes = E * (4 * n * 8 + N + 8 + 3 * 8 + 4 * 8 + 2 * N * 3 * 8 + 8 + 1)
+        self.out_bytes = E * (3 * n * 8 + N * 3 * 8 + F * 8)
+        if sets is None:
+            sets = max(2, int(np.ceil(2.5 * L2_BYTES / (self.in_bytes + self.out_bytes))))
+        self.sets = sets
+        dev = torch.device("cuda", device)
+        self.host_inputs = synth.make_inputs(name, E, rank=rank)
+        self.inputs, self.outputs, self.args = [], [], []
+        self.batch.use_torch_stream()
+        for s in range(sets):
+            x = self.host_inputs if s == 0 else synth.make_inputs(name, E, seed=0xB200 + 7919 * s + rank)
+            xin = {k: torch.from_numpy(v).to(dev) for k, v in x.items()}
+            out = {"tau": torch.empty((E, n), dtype=torch.float64, device=dev),
+                   "kin_pose": torch.empty((E, n), dtype=torch.float64, device=dev),
+                   "kin_vel": torch.empty((E, n), dtype=torch.float64, device=dev),
+                   "kin_body_pos": torch.empty((E, N, 3), dtype=torch.float64, device=dev),
+                   "state": torch.empty((E, F), dtype=torch.float64, device=dev)}
+            self.inputs.append(xin)
+            self.outputs.append(out)
+            self.args.append(self.batch.make_step_args(self.dt, xin, out))
+        self.i = 0
+        self.graph = None
+        self.pd_graph = None
+        self.launches_per_step = 0
+
+    def capture(self):
+        """Capture one pass over all R sets (R fused steps) into a CUDA graph: the hot loop is launch-bound from
+        Python otherwise. Also captures the stable-PD entry point alone for the roofline measurement."""
+        import torch
+        torch.cuda.synchronize()
+        l0 = self.batch.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.batch.use_torch_stream()
+            for _ in range(self.sets):
+                self.step()
+        self.launches_per_step = (self.batch.launch_count() - l0) // self.sets
+        self.pd_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.pd_graph):
+            self.batch.use_torch_stream()
+            for _ in range(self.sets):
+                self.pd_only()
+        self.batch.use_torch_stream()
+        torch.cuda.synchronize()
+
+    def run_steps(self, k):
+        """exactly k fused steps: whole graph replays (R steps each) + the remainder launched directly"""
+        if self.graph is None:
+            for _ in range(k):
+                self.step()
+            return
+        for _ in range(k // self.sets):
+            self.graph.replay()
+        for _ in range(k % self.sets):
+            self.step()
+
+    def run_pd(self, k):
+        for _ in range(k // self.sets):
+            self.pd_graph.replay()
+
+    def step(self):
+        rc = self.batch.step_fused_args(self.args[self.i % self.sets])
+        self.i += 1
+        if rc != 0:
+            from terrainrlsim_b200 import _capi
+            raise RuntimeError("trl_step_fused failed: " + _capi.last_error())
+
+    def pd_only(self):
+        s = self.i % self.sets
+        self.i += 1
+        x, o = self.inputs[s], self.outputs[s]
+        self.batch.imp_pd_update_control_force(self.dt, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"],
+                                               joint_active=x["joint_active"], tau=o["tau"])
+
+
+def timed_loop(fn, steps, barrier=None):
+    """fn(steps) bracketed by (barrier +) synchronize on both sides, CUDA events on the current stream (the stream
+    the library launches on). Returns ms total."""
+    import torch
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; terrainrlsim_b200 has no CPU fallback (use --impl reference)")
+    from terrainrlsim_b200 import _capi, synth
+    import ctypes as C
+
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if not use_dist:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    name = args.config
+    E = args.envs or synth.load_model_dict(name)["envs_per_gpu"]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    side = torch.cuda.Stream(device=local_rank)  # a real (non-legacy) stream: events and kernels share it
+    torch.cuda.set_stream(side)
+    w = Workload(name, E, local_rank, rank)
+    for _ in range(3):
+        w.step()
+    if not args.no_graph:
+        w.capture()
+
+    # warm-up: at least W steps and at least ~0.3 s so the clock sampler sees the GPU under load
+    t_end = time.perf_counter() + 0.3
+    k = 0
+    while k < max(args.warmup, 3) or time.perf_counter() < t_end:
+        w.run_steps(w.sets)
+        k += w.sets
+        torch.cuda.synchronize()
+
+    l0 = w.batch.launch_count()
+    ms = timed_loop(w.run_steps, args.steps, barrier)
+    if w.graph is not None:
+        launches = (args.steps // w.sets) * w.sets * w.launches_per_step + (w.batch.launch_count() - l0)
+    else:
+        launches = w.batch.launch_count() - l0
+    ms = max_over_ranks(ms)
+    value = world * E * args.steps / (ms * 1e-3)
+
+    # dominant kernel (stable PD) timed alone on the same rotating sets
+    pd_steps = max(4, min(args.steps, 400) // w.sets) * w.sets
+    if w.pd_graph is not None:
+        w.run_pd(w.sets)
+        ms_pd = timed_loop(w.run_pd, pd_steps) / pd_steps
+    else:
+        def _pd(k):
+            for _ in range(k):
+                w.pd_only()
+        _pd(5)
+        ms_pd = timed_loop(_pd, pd_steps) / pd_steps
+
+    # end-to-end through the public HOST-pointer API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        hin = {}
+        for kname, v in w.host_inputs.items():
+            t = torch.from_numpy(v).pin_memory()
+            hin[kname] = t.numpy()
+            hin["_keep_" + kname] = t
+        n, N, F = w.model.num_dof, w.model.num_joints, w.batch.F
+        hout_t = {"tau": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                  "kin_pose": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                  "kin_vel": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                  "kin_body_pos": torch.empty((E, N, 3), dtype=torch.float64).pin_memory(),
+                  "state": torch.empty((E, F), dtype=torch.float64).pin_memory()}
+        hout = {kname: t.numpy() for kname, t in hout_t.items()}
+        hin_clean = {kname: v for kname, v in hin.items() if not kname.startswith("_keep_")}
+        w.batch.set_stream(None)
+        for _ in range(3):
+            w.batch.step_fused(w.dt, hin_clean, hout)
+        e2e_steps = max(5, min(args.steps, 50))
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            w.batch.step_fused(w.dt, hin_clean, hout)  # synchronous: returns when outputs are in host memory
+        t1 = time.perf_counter()
+        barrier()
+        e2e_ms = max_over_ranks((t1 - t0) * 1e3)
+        h2d = sum(v.nbytes for v in hin_clean.values())
+        d2h = sum(v.nbytes for v in hout.values())
+        e2e = {"value": world * E * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "timer": "host perf_counter around synchronous calls"}
+        w.batch.use_torch_stream()
+
+    # FP64 peak probe (register-resident DFMA chains) for the roofline denominator
+    tf = C.c_double(0)
+    fp64_peak = None
+    if _capi.lib().trl_device_fp64_probe(local_rank, C.byref(tf)) == 0:
+        fp64_peak = tf.value
+    clocks = sampler.stop() if sampler else None
+
+    # optional episode-statistics all-gather over NCCL (outside the timed region, 64-byte record per GPU)
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+    stats[0] = float(args.steps * E)
+    stats[1] = float(w.outputs[0]["tau"].abs().max().item())
+    stats[2] = float((~torch.isfinite(w.outputs[0]["state"])).sum().item())
+    gathered = None
+    if use_dist:
+        lst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(lst, stats)
+        gathered = [x.cpu().tolist() for x in lst]
+
+    others = {}
+    if rank == 0 and not args.no_others and world == 1:
+        del w.inputs[1:], w.outputs[1:], w.args[1:]
+        for oname in ROOFLINE_MODEL:
+            if oname == name:
+                continue
+            oE = synth.load_model_dict(oname)["envs_per_gpu"]
+            ow = Workload(oname, oE, local_rank, rank)
+            for _ in range(3):
+                ow.step()
+            if not args.no_graph:
+                ow.capture()
+            ok = 20 * ow.sets
+            ow.run_steps(ok)
+            oms = timed_loop(ow.run_steps, ok)
+            opd = timed_loop(ow.run_pd, ok) / ok if ow.pd_graph is not None else None
+            others[oname] = {"envs_per_gpu": oE, "value": oE * ok / (oms * 1e-3), "unit": UNIT,
+                             "ms_per_step": oms / ok, "ms_per_pd_launch": opd}
+            del ow
+
+    if rank == 0:
+        pd_flops, total_flops, bytes_step = ROOFLINE_MODEL[name]
+        hbm_peak, hbm_src = measured_peaks()
+        ach_tf = pd_flops * E / (ms_pd * 1e-3) / 1e12
+        nominal = 37.2
+        peak_tf = fp64_peak if fp64_peak else nominal
+        roof = {"bound": "fp64", "kernel": "k_imp_pd", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf, "traffic": None,
+                "peak_source": "DFMA probe measured in this run" if fp64_peak else "nominal 148 SM x 64 x 2 x 1.965 GHz",
+                "ms_per_launch": ms_pd, "algorithmic_flops_per_launch": pd_flops * E}
+        ms_step = ms / args.steps
+        ach_gbs = bytes_step * E / (ms_step * 1e-3) / 1e9
+        roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                    "peak_source": hbm_src, "whole_step_fp64_tflops": total_flops * E / (ms_step * 1e-3) / 1e12}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(name)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES[name], "envs_per_gpu": E, "joints": w.model.num_joints,
+                           "dofs": w.model.num_dof, "ground_samples": w.batch.cfg.num_samples, "features": w.batch.F,
+                           "dt": w.dt, "terrains_per_gpu": w.num_fields,
+                           "l2": "rotating %d device-resident input/output sets, %.0f MB total > L2 (126 MB)" %
+                                 (w.sets, w.sets * (w.in_bytes + w.out_bytes) / 1e6),
+                           "sharding": "envs partitioned by rank, no hot-path collective"},
+                "e2e": e2e, "gpu_launches": int(launches), "launch": "direct" if args.no_graph else
+                "CUDA graph of %d fused steps (%d kernels each) replayed" % (w.sets, w.launches_per_step),
+                "clocks": clocks, "roofline": roof,
+                "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
+                "host_cores": os.cpu_count(), "other_workloads": others,
+                "episode_stats_allgather": gathered}
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="biped3d", choices=sorted(ROOFLINE_MODEL))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's BASELINE.json size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a CUDA graph")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -113,7 +113,10 @@ typedef enum trl_pointer_mode { TRL_PTR_HOST = 0, TRL_PTR_DEVICE = 1 } trl_point
 trl_batch* trl_batch_create(const trl_model* m, int num_envs, int device, const trl_obs_cfg* cfg);
 void trl_batch_destroy(trl_batch* b);
 int trl_batch_set_pointer_mode(trl_batch* b, int mode);
-/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the batch's own stream */
+/* Use an existing cudaStream_t (e.g. torch's current stream). As in CUDA, NULL is the legacy default stream;
+ * TRL_STREAM_OWN switches back to the batch's own non-blocking stream (the initial state). Kernels enqueued by
+ * this library can be captured into a CUDA graph on that stream (DEVICE pointer mode only). */
+#define TRL_STREAM_OWN ((void*)(~(unsigned long long)0))
 int trl_batch_set_stream(trl_batch* b, void* cuda_stream);
 int trl_batch_sync(trl_batch* b);
 /* GetPoliStateSize() (sim/TerrainRLCharController.cpp:438-493, CtController.cpp:482-504) */

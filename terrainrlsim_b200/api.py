@@ -120,7 +120,9 @@ class Batch:
             pass
 
     def set_stream(self, cuda_stream_ptr):
-        check(_capi.lib().trl_batch_set_stream(self._h, C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None), "set_stream")
+        """cuda_stream_ptr: a cudaStream_t handle (0 = CUDA's legacy default stream); None = the batch's own stream."""
+        h = C.c_void_p(0xFFFFFFFFFFFFFFFF) if cuda_stream_ptr is None else C.c_void_p(int(cuda_stream_ptr))
+        check(_capi.lib().trl_batch_set_stream(self._h, h), "set_stream")
 
     def use_torch_stream(self):
         import torch

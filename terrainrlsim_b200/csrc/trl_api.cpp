@@ -98,7 +98,7 @@ struct Guard {  // selects the batch's device for the duration of a call
 // Resolves an input array according to the pointer mode. Returns false on error.
 template <typename T>
 bool in_ptr(trl_batch* b, const T* user, size_t count, const T** out) {
-    if (!user) { *out = nullptr; return true; }
+    if (!user || count == 0) { *out = nullptr; return true; }
     if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
     *out = static_cast<const T*>(b->stage_in(user, count * sizeof(T)));
     return *out != nullptr;
@@ -109,7 +109,7 @@ struct OutCopy { void* host; void* dev; size_t bytes; };
 
 template <typename T>
 bool out_ptr(trl_batch* b, T* user, size_t count, T** out, std::vector<OutCopy>& copies, bool preload = false) {
-    if (!user) { *out = nullptr; return true; }
+    if (!user || count == 0) { *out = nullptr; return true; }
     if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
     void* d = preload ? b->stage_in(user, count * sizeof(T)) : b->stage_out(count * sizeof(T));
     if (!d) return false;
@@ -197,7 +197,7 @@ extern "C" int trl_batch_set_pointer_mode(trl_batch* b, int mode) {
 
 extern "C" int trl_batch_set_stream(trl_batch* b, void* cuda_stream) {
     if (!b) return TRL_ERR_INVALID_ARG;
-    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    b->stream = (cuda_stream == TRL_STREAM_OWN) ? b->own_stream : (cudaStream_t)cuda_stream;
     return TRL_OK;
 }
 

@@ -914,7 +914,9 @@ size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block) {
 }
 
 static int ensure_smem(const void* func, size_t bytes) {
-    if (bytes > 48 * 1024) {
+    static size_t granted = 0;  // set once per size: cudaFuncSetAttribute is kept out of graph captures
+    if (bytes > 48 * 1024 && bytes > granted) {
+        granted = bytes;
         cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (err != cudaSuccess) return (int)err;
     }
