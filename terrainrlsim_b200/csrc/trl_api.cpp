@@ -54,6 +54,7 @@ struct trl_batch {
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
     int* d_status = nullptr;
+    double* d_sample_local = nullptr;  // [G][2] local (x, z) of every ground sample
     // ground
     DevGround ground{};
     float* d_ground_data = nullptr;
@@ -168,6 +169,28 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaMalloc((void**)&b->d_frames, bytes), "cudaMalloc(frames)")) return nullptr;
         if (!cuda_ok(cudaMemcpy(b->d_frames, m->frames.data(), bytes, cudaMemcpyHostToDevice), "H2D(frames)")) return nullptr;
     }
+    if (b->cfg.num_samples > 0) {
+        // CalcGroundSamplePos in the sampling frame, same expression order as the reference
+        // (TerrainRLCharController.cpp:310-319; CtController.cpp:189-211 / BipedController3D.cpp:1932-1949)
+        const int G = b->cfg.num_samples;
+        std::vector<double> loc((size_t)G * 2);
+        for (int s = 0; s < G; ++s) {
+            if (b->cfg.sampler == TRL_SAMPLER_LINE) {
+                loc[2 * s] = ((b->cfg.view_max - b->cfg.view_min) * s) / (G - 1) + b->cfg.view_min;
+                loc[2 * s + 1] = 0.0;
+            } else {
+                const int res = b->cfg.grid_res;
+                const double ox = 0.5 * (b->cfg.view_max + b->cfg.view_min);
+                const double w = b->cfg.view_max - b->cfg.view_min;
+                const double u = static_cast<double>(s % res) / (res - 1);
+                const double v = static_cast<double>(s / res) / (res - 1);
+                loc[2 * s] = ox + (u - 0.5) * w;
+                loc[2 * s + 1] = 0.0 + (v - 0.5) * w;
+            }
+        }
+        if (!cuda_ok(cudaMalloc((void**)&b->d_sample_local, sizeof(double) * loc.size()), "cudaMalloc(samples)")) return nullptr;
+        if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
+    }
     if (!cuda_ok(cudaMalloc((void**)&b->d_status, sizeof(int) * (size_t)num_envs), "cudaMalloc(status)")) return nullptr;
     cudaMemset(b->d_status, 0, sizeof(int) * (size_t)num_envs);
     std::memset(&b->ground, 0, sizeof(b->ground));
@@ -182,6 +205,7 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     if (b->d_model) cudaFree(b->d_model);
     if (b->d_frames) cudaFree(b->d_frames);
     if (b->d_status) cudaFree(b->d_status);
+    if (b->d_sample_local) cudaFree(b->d_sample_local);
     if (b->d_ground_data) cudaFree(b->d_ground_data);
     if (b->d_pieces) cudaFree(b->d_pieces);
     if (b->d_env_to_field) cudaFree(b->d_env_to_field);
@@ -384,7 +408,7 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
         !out_ptr(b, out_cell, E * (size_t)b->cfg.num_samples * 3, &d_cell, copies))
         return TRL_ERR_CUDA;
     int rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, d_pose, d_vel, d_bp, d_bv,
-                                   d_bq, d_ba, d_gv, d_ph, d_fl, d_state, d_cell, b->stream);
+                                   d_bq, d_ba, d_gv, d_ph, d_fl, b->d_sample_local, d_state, d_cell, b->stream);
     b->launches += 1;
     return finish(b, copies, rc);
 }
@@ -434,7 +458,7 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (!rc && d_state) {
         if (!d_bp || !d_bv) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
-                                   nullptr, nullptr, nullptr, d_ph, d_fl, d_state, nullptr, b->stream);
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, d_state, nullptr, b->stream);
         b->launches += 1;
     }
     return finish(b, copies, rc);

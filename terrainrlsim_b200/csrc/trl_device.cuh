@@ -4,6 +4,7 @@
 
 #include <cfloat>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 #include "trl_internal.h"
 
@@ -224,45 +225,55 @@ TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data
     const double v0 = __dmul_rn((double)__ldg(base + (long long)j0 * rx + i0), pc.scale[1]);
     const double v1 = __dmul_rn((double)__ldg(base + (long long)j1 * rx + i1), pc.scale[1]);
     const double v2 = __dmul_rn((double)__ldg(base + (long long)j2 * rx + i2), pc.scale[1]);
-    // cMathUtil::CalcBarycentric on the unit triangle, same expression order (util/MathUtil.cpp:630-647)
-    double ax, az, bx, bz, cx, cz;
-    if (lower) { ax = 0; az = 0; bx = 1; bz = 0; cx = 1; cz = 1; }
-    else { ax = 1; az = 1; bx = 0; bz = 1; cx = 0; cz = 0; }
-    const double v0x = __dsub_rn(bx, ax), v0z = __dsub_rn(bz, az);
-    const double v1x = __dsub_rn(cx, ax), v1z = __dsub_rn(cz, az);
-    const double v2x = __dsub_rn(lx, ax), v2z = __dsub_rn(lz, az);
-    const double d00 = __dadd_rn(__dmul_rn(v0x, v0x), __dmul_rn(v0z, v0z));
-    const double d01 = __dadd_rn(__dmul_rn(v0x, v1x), __dmul_rn(v0z, v1z));
-    const double d11 = __dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1z, v1z));
-    const double d20 = __dadd_rn(__dmul_rn(v2x, v0x), __dmul_rn(v2z, v0z));
-    const double d21 = __dadd_rn(__dmul_rn(v2x, v1x), __dmul_rn(v2z, v1z));
-    const double denom = __dsub_rn(__dmul_rn(d00, d11), __dmul_rn(d01, d01));
-    const double bv = __ddiv_rn(__dsub_rn(__dmul_rn(d11, d20), __dmul_rn(d01, d21)), denom);
-    const double bw = __ddiv_rn(__dsub_rn(__dmul_rn(d00, d21), __dmul_rn(d01, d20)), denom);
+    // cMathUtil::CalcBarycentric (util/MathUtil.cpp:630-647) on the two unit triangles. With a = (0,0), b = (1,0),
+    // c = (1,1) (lower) or a = (1,1), b = (0,1), c = (0,0) (upper) the general expression has d00 = d01 = 1,
+    // d11 = 2, denom = 1 exactly, so every product by them and the division are exact and the reference's
+    // rounding sequence reduces to the few roundings below (bit-identical, checked by the parity tests).
+    double d20, d21;
+    if (lower) {
+        d20 = lx;                 // v2 = (lx, lz), v0 = (1, 0)
+        d21 = __dadd_rn(lx, lz);  // v1 = (1, 1)
+    } else {
+        const double ax = __dsub_rn(lx, 1.0), az = __dsub_rn(lz, 1.0);  // v2 = p - (1,1)
+        d20 = -ax;                                                      // v0 = (-1, 0)
+        d21 = __dadd_rn(-ax, -az);                                      // v1 = (-1, -1)
+    }
+    const double bv = __dsub_rn(__dmul_rn(2.0, d20), d21);
+    const double bw = __dsub_rn(d21, d20);
     const double bu = __dsub_rn(__dsub_rn(1.0, bv), bw);
     *valid = 1;
     cell[0] = s; cell[1] = i; cell[2] = j;
     return __dadd_rn(__dadd_rn(__dmul_rn(bu, v0), __dmul_rn(bv, v1)), __dmul_rn(bw, v2));
 }
 
-// cGroundVar2D::SampleHeight / cGroundVar3D::SampleHeight (first containing piece wins; none: -inf, invalid)
-TRL_DEV double ground_sample_height(const DevGround& g, int env, double px, double pz, int* valid, int* cell) {
+// cGroundVar2D::SampleHeight / cGroundVar3D::SampleHeight (first containing piece wins; none: -inf, invalid).
+// `pcs` may point to global or shared memory (the observation kernel stages the env's pieces in shared memory).
+TRL_DEV double ground_sample_pieces(int kind, int num_pieces, const DevPiece* pcs, const float* __restrict__ data,
+                                    double px, double pz, int* valid, int* cell) {
     cell[0] = -1; cell[1] = 0; cell[2] = 0;
-    if (g.kind == 0 || g.kind == 3) {  // cGround::SampleHeight (sim/Ground.cpp:176-186)
+    if (kind == 0 || kind == 3) {  // cGround::SampleHeight (sim/Ground.cpp:176-186)
         *valid = 1;
         return 0.0;
     }
-    const int field = g.env_to_field ? __ldg(g.env_to_field + env) : (env % g.num_fields);
-    const DevPiece* pcs = g.pieces + (long long)field * g.pieces_per_field;
     *valid = 0;
-    for (int s = 0; s < g.pieces_per_field; ++s) {
+    for (int s = 0; s < num_pieces; ++s) {
         const DevPiece& pc = pcs[s];
-        if (g.kind == 1) {
-            if (px >= pc.bounds[0] && px <= pc.bounds[1]) return sample_segment_2d(pc, g.data, s, px, pz, valid, cell);
+        if (kind == 1) {
+            if (px >= pc.bounds[0] && px <= pc.bounds[1]) return sample_segment_2d(pc, data, s, px, pz, valid, cell);
         } else {
             if (px >= pc.bounds[0] && px <= pc.bounds[1] && pz >= pc.bounds[2] && pz <= pc.bounds[3])
-                return sample_slab_3d(pc, g.data, s, px, pz, valid, cell);
+                return sample_slab_3d(pc, data, s, px, pz, valid, cell);
         }
     }
     return -CUDART_INF;
+}
+
+TRL_DEV int ground_field_of_env(const DevGround& g, int env) {
+    return g.env_to_field ? __ldg(g.env_to_field + env) : (env % g.num_fields);
+}
+
+TRL_DEV double ground_sample_height(const DevGround& g, int env, double px, double pz, int* valid, int* cell) {
+    const DevPiece* pcs = nullptr;
+    if (g.kind == 1 || g.kind == 2) pcs = g.pieces + (long long)ground_field_of_env(g, env) * g.pieces_per_field;
+    return ground_sample_pieces(g.kind, g.pieces_per_field, pcs, g.data, px, pz, valid, cell);
 }

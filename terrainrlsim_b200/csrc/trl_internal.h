@@ -41,6 +41,8 @@ struct DevModel {
     int ncol[TRL_MAX_JOINTS];
     int level_start[TRL_MAX_JOINTS + 1];
     int level_joint[TRL_MAX_JOINTS];
+    int slot_base[TRL_MAX_JOINTS];  // pose-feature slot of body j, cTerrainRLCharController packing (bodies 1..N-1)
+    int slot_ct[TRL_MAX_JOINTS];    // same for cCtController packing (bodies 0..N-1); -1 = invalid body
     double attR[TRL_MAX_JOINTS][9];  // cKinTree::BuildAttachTrans rotation (Rz*Ry*Rx of AttachTheta), row-major
     double attT[TRL_MAX_JOINTS][3];  // attach point
     double mass[TRL_MAX_JOINTS];
@@ -115,4 +117,4 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          double* out_state, int* out_cell, void* stream);
+                          const double* sample_local, double* out_state, int* out_cell, void* stream);

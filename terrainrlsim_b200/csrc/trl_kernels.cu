@@ -19,6 +19,7 @@
 // for composite inertias and forces, so the only level-serial work is the 3x4 transform composition
 // and a 6-vector recurrence. Numbers agree with the reference's joint-local formulation to ~1e-13.
 #include <cstdint>
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "trl_device.cuh"
@@ -27,18 +28,28 @@ namespace {
 
 constexpr int kWarpsPerBlock = 4;
 
-// shared-memory workspace layout (in doubles) of k_imp_pd
+// shared-memory workspace layout (in doubles) of k_imp_pd, per env. The PD vectors (ep, ev, kpm, kdm, kdu: 5n)
+// alias the transform arrays Tl/T0 (24N >= 5n), which are dead by the time the PD errors are formed.
 struct PdLayout {
-    int q, qd, Tl, T0, Rq, g0, cj, sj, V, A, IF, S, F, C, ep, ev, kpm, kdm, kdu, x, H, ldh, total;
+    int q, qd, Tl, T0, Rq, g0, cj, sj, V, A, IF, S, C, ep, ev, kpm, kdm, kdu, x, H, ldh, total;
 };
 
-__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl) {
+__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax) {
     PdLayout L;
     int o = 0;
     L.q = o; o += n;
     L.qd = o; o += n;
     L.Tl = o; o += 12 * N;
     L.T0 = o; o += 12 * N;
+    {
+        int a = L.Tl;
+        L.ep = a; a += n;
+        L.ev = a; a += n;
+        L.kpm = a; a += n;
+        L.kdm = a; a += n;
+        L.kdu = a; a += n;
+        if (a > o) o = a;
+    }
     L.Rq = o; o += 9;
     L.g0 = o; o += 3;
     L.cj = o; o += 3;
@@ -47,16 +58,11 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl) {
     L.A = o; o += 6 * N;
     L.IF = o; o += 16 * N;
     L.S = o; o += 6 * nl;
-    L.F = o; o += 6 * nl;
     L.C = o; o += nl;
-    L.ep = o; o += n;
-    L.ev = o; o += n;
-    L.kpm = o; o += n;
-    L.kdm = o; o += n;
-    L.kdu = o; o += n;
-    L.x = o; o += nl;
-    L.ldh = nl | 1;  // odd row stride: conflict-free row-per-lane access
-    L.H = o; o += nl * L.ldh;
+    const int rows = nlmax > 0 ? nlmax : nl;
+    L.x = o; o += rows;
+    L.ldh = rows | 1;  // odd row stride: conflict-free column loads / row-per-lane access
+    L.H = o; o += rows * L.ldh + (nlmax > 0 ? 32 : 0);  // + slack: lanes >= NLMAX read (and ignore) past the last row
     L.total = (o + 1) & ~1;
     return L;
 }
@@ -64,12 +70,13 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl) {
 // ------------------------------------------------------------------------------------------------
 // transforms in the root frame: Tl (local) -> T0 (root frame), level by level
 // ------------------------------------------------------------------------------------------------
-TRL_DEV void compose_levels(const DevModel* __restrict__ M, const double* Tl, double* T0, int lane, int first_level) {
+TRL_DEV void compose_levels(const DevModel* __restrict__ M, const double* Tl, double* T0, int lane, int first_level,
+                            int G = 32) {
     const int nlev = M->num_levels;
     for (int lv = first_level; lv < nlev; ++lv) {
         const int beg = M->level_start[lv];
         const int cnt = M->level_start[lv + 1] - beg;
-        for (int it = lane; it < cnt * 12; it += 32) {
+        for (int it = lane; it < cnt * 12; it += G) {
             const int j = M->level_joint[beg + it / 12];
             const int el = it % 12;
             const int p = M->parent[j];
@@ -90,18 +97,139 @@ TRL_DEV void compose_levels(const DevModel* __restrict__ M, const double* Tl, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// LDL^T + solve, register-resident: lane j owns column j (= row j, the matrix is kept fully symmetric) of the
+// n x n system in NLMAX registers; step k broadcasts column k with shuffles. Rows/columns >= nl are identity
+// padding, so the fully unrolled code needs no bounds checks. No pivoting: M + dt*Kd is SPD on the live dofs
+// (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot zeroes that solution component like
+// Eigen's pseudo-inverse of D does.
+// ------------------------------------------------------------------------------------------------
+TRL_DEV double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+template <int NLMAX>
+TRL_DEV int ldlt_solve_regs(const double* H, int ldh, double* x, int nl, int lane) {
+    double a[NLMAX];
+    const bool live = lane < nl;
+    // H is NLMAX x NLMAX with identity padding beyond nl (prepared by the caller); lanes >= NLMAX read slack
+#pragma unroll
+    for (int i = 0; i < NLMAX; ++i) a[i] = H[i * ldh + lane];
+    double b = (lane < NLMAX) ? x[lane] : 0.0;
+    double rdiag = 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int k = 0; k < NLMAX; ++k) {
+        const double d = __shfl_sync(0xffffffffu, a[k], k);
+        const bool ok = fabs(d) > DBL_MIN;
+        if (!(d > DBL_MIN)) bad |= 2;
+        const double r = ok ? fast_rcp(d) : 0.0;
+        if (lane == k) rdiag = r;
+        const double c = (lane > k && lane < NLMAX) ? a[k] * r : 0.0;  // L[lane][k]; 0 keeps columns <= k untouched
+#pragma unroll
+        for (int i = k + 1; i < NLMAX; ++i) {
+            const double t = __shfl_sync(0xffffffffu, a[i], k);  // A[i][k] = L[i][k] d_k
+            a[i] = fma(-t, c, a[i]);
+        }
+    }
+    // forward: L y = b  (lane i: b -= (L[i][k] d_k) * (y_k / d_k))
+#pragma unroll
+    for (int k = 0; k < NLMAX; ++k) {
+        const double zk = __shfl_sync(0xffffffffu, b * rdiag, k);
+        const double ak = (lane > k) ? a[k] : 0.0;
+        b = fma(-ak, zk, b);
+    }
+    // backward: L^T x = D^-1 y  (lane k: x_k = z_k - (1/d_k) sum_{i>k} (L[i][k] d_k) x_i)
+    const double z = b * rdiag;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = NLMAX - 1; i >= 0; --i) {
+        const double xi = __shfl_sync(0xffffffffu, fma(-rdiag, acc, z), i);
+        const double ai = (lane < i) ? a[i] : 0.0;
+        acc = fma(ai, xi, acc);
+    }
+    if (live) x[lane] = fma(-rdiag, acc, z);
+    return bad;
+}
+
+// generic shared-memory fallback (any nl <= 64): left-looking; lower = L, upper = L*D, diagonal = D
+TRL_DEV int ldlt_solve_smem(double* H, int ldh, double* x, int nl, int lane) {
+    int bad = 0;
+    for (int k = 0; k < nl; ++k) {
+        double v0 = 0.0, v1 = 0.0;
+        const int i0 = k + lane, i1 = k + lane + 32;
+        if (i0 < nl) {
+            v0 = H[i0 * ldh + k];
+            for (int qq = 0; qq < k; ++qq) v0 -= H[i0 * ldh + qq] * H[qq * ldh + k];
+        }
+        if (i1 < nl) {
+            v1 = H[i1 * ldh + k];
+            for (int qq = 0; qq < k; ++qq) v1 -= H[i1 * ldh + qq] * H[qq * ldh + k];
+        }
+        const double d = __shfl_sync(0xffffffffu, v0, 0);
+        const bool ok = fabs(d) > DBL_MIN;
+        if (!(d > DBL_MIN)) bad |= 2;
+        const double rd = ok ? 1.0 / d : 0.0;
+        __syncwarp();
+        if (i0 < nl) {
+            if (lane == 0) {
+                H[k * ldh + k] = d;
+            } else {
+                H[k * ldh + i0] = ok ? v0 : 0.0;
+                H[i0 * ldh + k] = v0 * rd;
+            }
+        }
+        if (i1 < nl) {
+            H[k * ldh + i1] = ok ? v1 : 0.0;
+            H[i1 * ldh + k] = v1 * rd;
+        }
+        __syncwarp();
+    }
+    for (int k = 0; k < nl; ++k) {  // forward substitution L y = b
+        const double yk = x[k];
+        for (int i = k + 1 + lane; i < nl; i += 32) x[i] -= H[i * ldh + k] * yk;
+        __syncwarp();
+    }
+    for (int i = lane; i < nl; i += 32) {  // D^-1 (zero pivot => 0, Eigen's pseudo-inverse of D)
+        const double d = H[i * ldh + i];
+        x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0;
+    }
+    __syncwarp();
+    for (int k = nl - 1; k >= 0; --k) {  // backward substitution L^T x = z
+        const double xk = x[k];
+        for (int i = lane; i < k; i += 32) x[i] -= H[k * ldh + i] * xk;
+        __syncwarp();
+    }
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_imp_pd: stable-PD torques (and optionally M, C) -- one warp per env
 // ------------------------------------------------------------------------------------------------
+// G = lanes per env (32 / G envs share a warp; G >= N so one lane owns one joint in the per-joint phases).
+// NLMAX > 0: register-resident LDL^T for nl <= NLMAX <= 32; NLMAX == 0: shared-memory fallback (G = 32 only).
+template <int G, int NLMAX>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31;
+    constexpr int EPW = 32 / G;  // envs per warp
+    const int wlane = threadIdx.x & 31;
+    const int lane = wlane % G;  // lane within the env's group
+    const int sub = wlane / G;
     const int warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= E) return;
+    const int wpb = blockDim.x >> 5;  // warps per block: chosen by the launcher to maximise resident warps
+    const int e_raw = (blockIdx.x * wpb + warp) * EPW + sub;
+    if ((blockIdx.x * wpb + warp) * EPW >= E) return;  // whole warp idle
+    const bool env_ok = e_raw < E;
+    const int e = env_ok ? e_raw : E - 1;  // tail groups recompute the last env and store nothing
     const int N = M->N, n = M->n, nl = M->nl;
-    const PdLayout L = pd_layout(N, n, nl);
-    double* ws = smem + (size_t)warp * L.total;
+    const PdLayout L = pd_layout(N, n, nl, NLMAX);
+    double* ws = smem + (size_t)(warp * EPW + sub) * L.total;
     double* q = ws + L.q;
     double* qd = ws + L.qd;
     double* Tl = ws + L.Tl;
@@ -114,7 +242,6 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     double* A = ws + L.A;
     double* IF = ws + L.IF;
     double* S = ws + L.S;
-    double* F = ws + L.F;
     double* C = ws + L.C;
     double* ep = ws + L.ep;
     double* ev = ws + L.ev;
@@ -126,13 +253,16 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     const int ldh = L.ldh;
     const double dt = p.dt;
 
-    // P0: stage pose / vel (coalesced)
-    for (int i = lane; i < n; i += 32) {
+    // P0: stage pose / vel (coalesced); H = 0 with identity padding beyond nl
+    for (int i = lane; i < n; i += G) {
         q[i] = p.pose[(size_t)e * n + i];
         qd[i] = p.vel[(size_t)e * n + i];
     }
-    for (int i = lane; i < nl * ldh; i += 32) H[i] = 0.0;
+    const int hrows = NLMAX > 0 ? NLMAX : nl;
+    for (int i = lane; i < hrows * ldh; i += G) H[i] = 0.0;
+    for (int i = lane; i < hrows; i += G) x[i] = 0.0;
     __syncwarp();
+    for (int r = nl + lane; r < hrows; r += G) H[r * ldh + r] = 1.0;  // identity padding (ordered by the next sync)
 
     // P1: joint-local transforms; the root lane also prepares R(q_root), gravity and c_root in the root frame
     if (lane < N) {
@@ -181,10 +311,10 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     __syncwarp();
 
     // P2: root-frame transforms
-    compose_levels(M, Tl, T0, lane, 1);
+    compose_levels(M, Tl, T0, lane, 1, G);
 
     // P3: subspace columns S_c (6) in the root frame; then s_j = S_j qd_j
-    for (int c = lane; c < nl; c += 32) {
+    for (int c = lane; c < nl; c += G) {
         const int j = M->col_joint[c], kind = M->col_kind[c], a = M->col_axis[c];
         const double* T = T0 + 12 * j;
         double w[3] = {0, 0, 0}, v[3];
@@ -224,7 +354,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     for (int lv = 1; lv < M->num_levels; ++lv) {
         const int beg = M->level_start[lv];
         const int cnt = M->level_start[lv + 1] - beg;
-        for (int it = lane; it < cnt * 6; it += 32) {
+        for (int it = lane; it < cnt * 6; it += G) {
             const int j = M->level_joint[beg + it / 6];
             const int k = it % 6;
             const int pj = M->parent[j];
@@ -307,12 +437,12 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
 
     // P6: subtree sums, leaves -> root (joints are ordered parents-first, anim/KinTree.cpp:479-493)
     for (int j = N - 1; j >= 1; --j) {
-        if (lane < 16) IF[16 * M->parent[j] + lane] += IF[16 * j + lane];
+        for (int c = lane; c < 16; c += G) IF[16 * M->parent[j] + c] += IF[16 * j + c];
         __syncwarp();
     }
 
     // P7: F_c = Ic_j S_c ; C_c = S_c . f_subtree ; H[c][c'] = F_c . S_c' along the ancestor chain
-    for (int c = lane; c < nl; c += 32) {
+    for (int c = lane; c < nl; c += G) {
         const int j = M->col_joint[c];
         const double* I = IF + 16 * j;
         const double* s = S + 6 * c;
@@ -340,16 +470,16 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     __syncwarp();
 
     // optional outputs: cRBDModel::GetMassMat / GetBiasForce on the full n-dof layout (dead dofs are exact zeros)
-    if (p.out_mass) {
+    if (p.out_mass && env_ok) {
         double* om = p.out_mass + (size_t)e * n * n;
-        for (int idx = lane; idx < n * n; idx += 32) {
+        for (int idx = lane; idx < n * n; idx += G) {
             const int ci = M->dof_col[idx / n], ck = M->dof_col[idx % n];
             om[idx] = (ci >= 0 && ck >= 0) ? H[ci * ldh + ck] : 0.0;
         }
     }
-    if (p.out_bias) {
+    if (p.out_bias && env_ok) {
         double* ob = p.out_bias + (size_t)e * n;
-        for (int i = lane; i < n; i += 32) {
+        for (int i = lane; i < n; i += G) {
             const int ci = M->dof_col[i];
             ob[i] = (ci >= 0) ? C[ci] : 0.0;
         }
@@ -401,66 +531,30 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
         }
     }
     __syncwarp();
-    for (int c = lane; c < nl; c += 32) {
+    for (int c = lane; c < nl; c += G) {
         const int i = M->col_dof[c];
         x[c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
         H[c * ldh + c] += dt * kdu[i];
     }
     __syncwarp();
 
-    // P9: LDL^T (left-looking; lower = L, upper = L*D, diagonal = D), row i = k + lane so the pivot is in lane 0
+    // P9: LDL^T factorisation + solve of (M + dt Kd) qdd = rhs on the live dofs; x <- qdd.
+    // The envs sharing this warp are factorised one after the other, each by all 32 lanes (lane <-> column).
     int bad = 0;
-    for (int k = 0; k < nl; ++k) {
-        double v0 = 0.0, v1 = 0.0;
-        const int i0 = k + lane, i1 = k + lane + 32;
-        if (i0 < nl) {
-            v0 = H[i0 * ldh + k];
-            for (int qq = 0; qq < k; ++qq) v0 -= H[i0 * ldh + qq] * H[qq * ldh + k];
+    if (NLMAX > 0) {
+#pragma unroll 1
+        for (int s2 = 0; s2 < EPW; ++s2) {
+            double* wss = smem + (size_t)(warp * EPW + s2) * L.total;
+            const int b2 = ldlt_solve_regs<(NLMAX > 0 ? NLMAX : 1)>(wss + L.H, ldh, wss + L.x, nl, wlane);
+            if (s2 == sub) bad = b2;
         }
-        if (i1 < nl) {
-            v1 = H[i1 * ldh + k];
-            for (int qq = 0; qq < k; ++qq) v1 -= H[i1 * ldh + qq] * H[qq * ldh + k];
-        }
-        const double d = __shfl_sync(0xffffffffu, v0, 0);
-        const bool ok = fabs(d) > DBL_MIN;
-        if (!(d > DBL_MIN)) bad |= 2;
-        const double rd = ok ? 1.0 / d : 0.0;
-        __syncwarp();
-        if (i0 < nl) {
-            if (lane == 0) {
-                H[k * ldh + k] = d;
-            } else {
-                H[k * ldh + i0] = ok ? v0 : 0.0;
-                H[i0 * ldh + k] = v0 * rd;
-            }
-        }
-        if (i1 < nl) {
-            H[k * ldh + i1] = ok ? v1 : 0.0;
-            H[i1 * ldh + k] = v1 * rd;
-        }
-        __syncwarp();
-    }
-    // forward substitution L y = b
-    for (int k = 0; k < nl; ++k) {
-        const double yk = x[k];
-        for (int i = k + 1 + lane; i < nl; i += 32) x[i] -= H[i * ldh + k] * yk;
-        __syncwarp();
-    }
-    // D^-1 (zero pivot => 0, Eigen's pseudo-inverse of D)
-    for (int i = lane; i < nl; i += 32) {
-        const double d = H[i * ldh + i];
-        x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0;
+    } else {
+        bad = ldlt_solve_smem(H, ldh, x, nl, wlane);
     }
     __syncwarp();
-    // backward substitution L^T x = z
-    for (int k = nl - 1; k >= 0; --k) {
-        const double xk = x[k];
-        for (int i = lane; i < k; i += 32) x[i] -= H[k * ldh + i] * xk;
-        __syncwarp();
-    }
 
     // P10: tau = Kp e_p + Kd (e_v - dt qdd)
-    for (int i = lane; i < n; i += 32) {
+    for (int i = lane; i < n; i += G) {
         const int c = M->dof_col[i];
         double acc;
         if (c >= 0) {
@@ -472,12 +566,16 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
         }
         const double t = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
         if (!isfinite(t)) bad |= 1;
-        double* out = p.tau + (size_t)e * n + i;
-        *out = p.tau_accumulate ? (*out + t) : t;
+        if (env_ok) {
+            double* out = p.tau + (size_t)e * n + i;
+            *out = p.tau_accumulate ? (*out + t) : t;
+        }
     }
     if (p.status) {
-        bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
-        if (lane == 0) p.status[e] = bad;
+        // OR-reduce `bad` over the env's G lanes
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+        if (lane == 0 && env_ok) p.status[e] = bad;
     }
 }
 
@@ -688,13 +786,26 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
              const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
              const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
              const double* __restrict__ ground_vel, const double* __restrict__ phase,
-             const unsigned char* __restrict__ flip_arr, double* __restrict__ out_state, int* __restrict__ out_cell) {
+             const unsigned char* __restrict__ flip_arr, const double* __restrict__ sample_local,
+             double* __restrict__ out_state, int* __restrict__ out_cell) {
+    __shared__ DevPiece s_pieces[kWarpsPerBlock][4];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int e = blockIdx.x * kWarpsPerBlock + warp;
     if (e >= E) return;
     const int N = M->N, n = M->n;
     const ObsDims D = obs_dims(N, cfg);
+    // stage this env's terrain piece descriptors (<= 4 x 96 B) in shared memory: every sample reads them
+    const int gkind = g.kind, gP = g.pieces_per_field;
+    if (gkind == 1 || gkind == 2) {
+        const unsigned long long* src =
+            reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_pieces[warp]);
+        const int words = gP * (int)(sizeof(DevPiece) / 8);
+        for (int i = lane; i < words; i += 32) dst[i] = __ldg(src + i);
+    }
+    __syncwarp();
+    const DevPiece* pcs = s_pieces[warp];
     const double* q = pose + (size_t)e * n;
     double* out = out_state + (size_t)e * D.F;
     const int flip = flip_arr ? (flip_arr[e] != 0) : 0;
@@ -722,7 +833,7 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     // ground height under the root (TerrainRLCharController.cpp:261-279,370-380)
     int v0, c0[3];
     double ground_h = 0.0;
-    if (has_ground) ground_h = ground_sample_height(g, e, rx, rz, &v0, c0);
+    if (has_ground) ground_h = ground_sample_pieces(gkind, gP, pcs, g.data, rx, rz, &v0, c0);
     const double ground_h_finite = isfinite(ground_h) ? ground_h : 0.0;
 
     // ground sample transform = InvRigid(origin_trans), y += ground_h (finite)
@@ -732,29 +843,18 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     const double it1 = -(oz * ot0 + i11 * ot1 + oz * ot2) + ground_h_finite;
     const double it2 = -(i20 * ot0 + oz * ot1 + i22 * ot2);
 
-    // ---- ground block ----
+    // ---- ground block ---- (sample_local[s] = CalcGroundSamplePos's local (x, z), precomputed once per batch)
     for (int s = lane; s < D.G; s += 32) {
         double hs = 0.0;
         int cell[3] = {-1, 0, 0};
         if (has_ground) {
-            double lx, lz;
-            if (cfg.sampler == TRL_SAMPLER_LINE) {
-                lx = ((cfg.view_max - cfg.view_min) * s) / (D.G - 1) + cfg.view_min;
-                lz = 0.0;
-            } else {
-                const int res = cfg.grid_res;
-                const double ox = 0.5 * (cfg.view_max + cfg.view_min);
-                const double w = cfg.view_max - cfg.view_min;
-                const double u = (double)(s % res) / (res - 1);
-                const double v = (double)(s / res) / (res - 1);
-                lx = ox + (u - 0.5) * w;
-                lz = (v - 0.5) * w;
-                if (flip && D.is_ct) lz = -lz;
-            }
-            const double px = i00 * lx + i02 * lz + it0;
-            const double pz = i20 * lx + i22 * lz + it2;
+            const double lx = __ldg(sample_local + 2 * s);
+            double lz = __ldg(sample_local + 2 * s + 1);
+            if (flip && D.is_ct) lz = -lz;
+            const double px = i00 * lx + oz * 0.0 + i02 * lz + it0;
+            const double pz = i20 * lx + oz * 0.0 + i22 * lz + it2;
             int vs;
-            hs = ground_sample_height(g, e, px, pz, &vs, cell) - it1;
+            hs = ground_sample_pieces(gkind, gP, pcs, g.data, px, pz, &vs, cell) - it1;
         }
         out[s] = hs;
         if (out_cell) {
@@ -777,9 +877,8 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     const int per = D.pos_dim + (D.is3d ? 4 : 0);
     // feature slot of body i: valid bodies are packed in index order
     for (int i = first + lane; i < N; i += 32) {
-        if (!M->valid_body[i]) continue;
-        int slot = 0;
-        for (int k = first; k < i; ++k) slot += M->valid_body[k] ? 1 : 0;
+        const int slot = D.is_ct ? M->slot_ct[i] : M->slot_base[i];
+        if (slot < 0) continue;
         const double* bp = body_pos + ((size_t)e * N + i) * 3;
         const double bx = bp[0], by = bp[1] - ground_h, bz = bp[2];
         const double f0 = (o00 * bx + oz * by + o02 * bz + ot0) - rr0;
@@ -836,9 +935,9 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
         opose[D.psize - 1] = theta;
         ovel[D.vsize - 1] = vel[(size_t)e * n + 5];
     }
-    if (!D.is_ct && flip && lane == 0) {  // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830)
+    if (!D.is_ct && flip) {  // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830)
         const int nlp = ((N - 1) / 2) * 2;
-        for (int i = 0; i < nlp; ++i) {
+        for (int i = lane; i < nlp; i += 32) {
             int a = D.psize - i - 1, b = D.psize - nlp - i - 1;
             double t = opose[a]; opose[a] = opose[b]; opose[b] = t;
             a = D.vsize - i - 1; b = D.vsize - nlp - i - 1;
@@ -910,26 +1009,66 @@ double trl_fp64_probe_tflops(void* stream) {
 // launchers
 // ------------------------------------------------------------------------------------------------
 size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block) {
-    return (size_t)pd_layout(hm.N, hm.n, hm.nl).total * sizeof(double) * (size_t)warps_per_block;
+    return (size_t)pd_layout(hm.N, hm.n, hm.nl, hm.nl <= 32 ? 32 : 0).total * sizeof(double) * (size_t)warps_per_block;
 }
 
 static int ensure_smem(const void* func, size_t bytes) {
-    static size_t granted = 0;  // set once per size: cudaFuncSetAttribute is kept out of graph captures
-    if (bytes > 48 * 1024 && bytes > granted) {
-        granted = bytes;
+    // set once per (kernel, size): cudaFuncSetAttribute is kept out of graph captures
+    static const void* seen_func[16];
+    static size_t seen_bytes[16];
+    static int nseen = 0;
+    if (bytes > 48 * 1024) {
+        for (int i = 0; i < nseen; ++i)
+            if (seen_func[i] == func && seen_bytes[i] >= bytes) return 0;
+        if (nseen < 16) { seen_func[nseen] = func; seen_bytes[nseen] = bytes; ++nseen; }
         cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (err != cudaSuccess) return (int)err;
     }
     return 0;
 }
 
-int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
-    const size_t smem = trl_pd_smem_bytes(hm, kWarpsPerBlock);
-    int rc = ensure_smem((const void*)k_imp_pd, smem);
+template <int G, int NLMAX>
+static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+    constexpr int EPW = 32 / G;
+    const size_t per_warp = (size_t)pd_layout(hm.N, hm.n, hm.nl, NLMAX).total * sizeof(double) * EPW;
+    // warps per block: maximise resident warps per SM under the 227 KB shared-memory budget (1 KB reserved per block)
+    int wpb = 1, best = 0;
+    for (int w = kWarpsPerBlock; w >= 1; w >>= 1) {
+        const size_t blk = per_warp * w + 1024;
+        const int resident = (int)((227 * 1024) / blk) * w;
+        if (resident > best) { best = resident; wpb = w; }
+    }
+    const size_t smem = per_warp * wpb;
+    int rc = ensure_smem((const void*)k_imp_pd<G, NLMAX>, smem);
     if (rc) return rc;
-    const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    k_imp_pd<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
+    const int envs_per_block = wpb * EPW;
+    const int blocks = (E + envs_per_block - 1) / envs_per_block;
+    k_imp_pd<G, NLMAX><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
     return (int)cudaGetLastError();
+}
+
+// lanes per env: heuristic, or forced with the TRL_PD_GROUP environment variable (8 / 16 / 32; tuning and tests)
+static int pd_group_override() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TRL_PD_GROUP");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+    const int nl = hm.nl, N = hm.N;
+    int G = (N <= 8) ? 8 : (N <= 16 ? 16 : 32);
+    const int ov = pd_group_override();
+    if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
+    if (nl > 32) return launch_imp_pd_t<32, 0>(dm, hm, E, p, stream);
+#define TRL_PD_CASE(GG, NL) if (G == GG && nl <= NL) return launch_imp_pd_t<GG, NL>(dm, hm, E, p, stream);
+    TRL_PD_CASE(8, 8) TRL_PD_CASE(8, 20) TRL_PD_CASE(8, 32)
+    TRL_PD_CASE(16, 8) TRL_PD_CASE(16, 18) TRL_PD_CASE(16, 20) TRL_PD_CASE(16, 32)
+    TRL_PD_CASE(32, 8) TRL_PD_CASE(32, 18) TRL_PD_CASE(32, 20) TRL_PD_CASE(32, 24) TRL_PD_CASE(32, 26) TRL_PD_CASE(32, 32)
+#undef TRL_PD_CASE
+    return launch_imp_pd_t<32, 0>(dm, hm, E, p, stream);
 }
 
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
@@ -961,12 +1100,12 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          double* out_state, int* out_cell, void* stream) {
+                          const double* sample_local, double* out_state, int* out_cell, void* stream) {
     (void)hm; (void)F;
     const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
     k_poli_state<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel,
                                                                           body_quat, body_angvel, ground_vel, phase,
-                                                                          flip, out_state, out_cell);
+                                                                          flip, sample_local, out_state, out_cell);
     return (int)cudaGetLastError();
 }
 

@@ -334,6 +334,13 @@ int trl_build_dev_model(trl_model* m) {
             if (d.level[j] == l) d.level_joint[pos++] = j;
     }
     d.level_start[max_level + 1] = pos;
+    {
+        int sb = 0, sc = 0;
+        for (int j = 0; j < N; ++j) {
+            d.slot_base[j] = (j >= 1 && d.valid_body[j]) ? sb++ : -1;
+            d.slot_ct[j] = d.valid_body[j] ? sc++ : -1;
+        }
+    }
 
     for (int k = 0; k < 3; ++k) d.gravity[k] = m->gravity[k];
     d.num_frames = m->num_frames;
