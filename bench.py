@@ -271,6 +271,49 @@ class Workload:
             from terrainrlsim_b200 import _capi
             raise RuntimeError("trl_step_fused failed: " + _capi.last_error())
 
+    def breakdown(self, reps=20):
+        """CUDA-event time of each entry point alone (graph of one pass over the R sets, replayed): ms per launch."""
+        import torch
+        res = {}
+        b = self.batch
+
+        def f_pd(x, o):
+            b.imp_pd_update_control_force(self.dt, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"],
+                                          joint_active=x["joint_active"], tau=o["tau"])
+
+        def f_kin(x, o):
+            from terrainrlsim_b200 import _capi
+            p = b._prep([(x["kin_time"], np.float64), (x["origin_pos"], np.float64), (x["origin_rot"], np.float64),
+                         (o["kin_pose"], np.float64), (o["kin_vel"], np.float64)])
+            _capi.lib().trl_kin_char_pose(b._h, *p)
+
+        def f_fk(x, o):
+            from terrainrlsim_b200 import _capi
+            p = b._prep([(o["kin_pose"], np.float64), (None, np.float64), (o["kin_body_pos"], np.float64)])
+            _capi.lib().trl_kin_tree_fk(b._h, *p)
+
+        def f_obs(x, o):
+            from terrainrlsim_b200 import _capi
+            p = b._prep([(x["pose"], np.float64), (x["vel"], np.float64), (x["body_pos"], np.float64),
+                         (x["body_vel"], np.float64), (None, np.float64), (None, np.float64), (None, np.float64),
+                         (x["phase"], np.float64), (x["flip"], np.uint8), (o["state"], np.float64), (None, np.int32)])
+            _capi.lib().trl_build_poli_state(b._h, *p)
+
+        for name, fn in (("imp_pd", f_pd), ("kin_char", f_kin), ("fk", f_fk), ("poli_state", f_obs)):
+            for s in range(self.sets):
+                fn(self.inputs[s], self.outputs[s])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                b.use_torch_stream()
+                for s in range(self.sets):
+                    fn(self.inputs[s], self.outputs[s])
+            b.use_torch_stream()
+            g.replay()
+            ms = timed_loop(lambda k: [g.replay() for _ in range(k)], reps)
+            res[name] = ms / (reps * self.sets)
+        return res
+
     def pd_only(self):
         s = self.i % self.sets
         self.i += 1
@@ -395,6 +438,8 @@ def run_ours(args, rank, local_rank, world):
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "timer": "host perf_counter around synchronous calls"}
         w.batch.use_torch_stream()
 
+    kernel_ms = w.breakdown() if not args.no_graph else None
+
     # FP64 peak probe (register-resident DFMA chains) for the roofline denominator
     tf = C.c_double(0)
     fp64_peak = None
@@ -462,7 +507,7 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": e2e, "gpu_launches": int(launches), "launch": "direct" if args.no_graph else
                 "CUDA graph of %d fused steps (%d kernels each) replayed" % (w.sets, w.launches_per_step),
                 "clocks": clocks, "roofline": roof,
-                "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
+                "kernel_ms": kernel_ms, "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
                 "host_cores": os.cpu_count(), "other_workloads": others,
                 "episode_stats_allgather": gathered}
         print(json.dumps(line))

@@ -273,6 +273,17 @@ class Ground:
         return h, bool(valid.value), (cell[0], cell[1], cell[2])
 
 
+def sample_height_batch(ground, pos):
+    pos = _c(pos).reshape(-1, 3)
+    n = pos.shape[0]
+    h = np.zeros(n)
+    valid = np.zeros(n, dtype=np.int32)
+    cell = np.zeros((n, 3), dtype=np.int32)
+    lib().trlo_sample_height_batch(C.byref(ground.c), C.c_int(n), _d(pos), _d(h), valid.ctypes.data_as(_ip),
+                                   cell.ctypes.data_as(_ip))
+    return h, valid, cell
+
+
 def obs_cfg(obs_kind=OBS_TERRAIN_RL, sampler=SAMPLER_LINE, num_samples=200, grid_res=0, view_min=-0.5,
             view_max=10.0, num_phase_bins=-1):
     c = CObsCfg()

@@ -1330,6 +1330,17 @@ double trlo_sample_height(const trlo_ground* g, const double pos[3], int* out_va
     return h;
 }
 
+/* batch form of cGround::SampleHeight(MatrixXd, VectorXd&) with the scalar overload's numerics (test helper) */
+void trlo_sample_height_batch(const trlo_ground* g, int count, const double* pos, double* out_h, int* out_valid, int* out_cell)
+{
+    for (int i = 0; i < count; ++i) {
+        int v, c[3];
+        out_h[i] = trlo_sample_height(g, pos + 3 * (size_t)i, &v, c);
+        if (out_valid) out_valid[i] = v;
+        if (out_cell) { out_cell[3 * i] = c[0]; out_cell[3 * i + 1] = c[1]; out_cell[3 * i + 2] = c[2]; }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------
  * observation (sim/TerrainRLCharController.cpp:261-436, sim/CtController.cpp:189-228,482-632,
  *              sim/CtPhaseController.cpp:120-139, sim/BipedController3D.cpp:1927-1965,

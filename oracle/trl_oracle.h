@@ -124,6 +124,8 @@ void trlo_kin_char_pose(const trlo_model* m, double time, const double origin_po
 /* ---- ground (sim/GroundVar2D.cpp, sim/GroundVar3D.cpp) ---- */
 /* out_cell: piece, i, j (piece=-1 if no piece contains pos) */
 double trlo_sample_height(const trlo_ground* g, const double pos[3], int* out_valid, int out_cell[3]);
+void trlo_sample_height_batch(const trlo_ground* g, int count, const double* pos, double* out_h, int* out_valid,
+                              int* out_cell);
 
 /* ---- observation (sim/TerrainRLCharController.cpp, sim/CtController.cpp, ...) ---- */
 int trlo_poli_state_size(const trlo_model* m, const trlo_obs_cfg* cfg);

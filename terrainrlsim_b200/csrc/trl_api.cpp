@@ -55,6 +55,7 @@ struct trl_batch {
     double* d_frames = nullptr;
     int* d_status = nullptr;
     double* d_sample_local = nullptr;  // [G][2] local (x, z) of every ground sample
+    void* d_env_rec = nullptr;         // [E] per-env sampling transform handed from k_obs_env to k_obs_samples
     // ground
     DevGround ground{};
     float* d_ground_data = nullptr;
@@ -191,6 +192,7 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaMalloc((void**)&b->d_sample_local, sizeof(double) * loc.size()), "cudaMalloc(samples)")) return nullptr;
         if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
     }
+    if (!cuda_ok(cudaMalloc(&b->d_env_rec, trl_obs_env_rec_bytes() * (size_t)num_envs), "cudaMalloc(env_rec)")) return nullptr;
     if (!cuda_ok(cudaMalloc((void**)&b->d_status, sizeof(int) * (size_t)num_envs), "cudaMalloc(status)")) return nullptr;
     cudaMemset(b->d_status, 0, sizeof(int) * (size_t)num_envs);
     std::memset(&b->ground, 0, sizeof(b->ground));
@@ -206,6 +208,7 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     if (b->d_frames) cudaFree(b->d_frames);
     if (b->d_status) cudaFree(b->d_status);
     if (b->d_sample_local) cudaFree(b->d_sample_local);
+    if (b->d_env_rec) cudaFree(b->d_env_rec);
     if (b->d_ground_data) cudaFree(b->d_ground_data);
     if (b->d_pieces) cudaFree(b->d_pieces);
     if (b->d_env_to_field) cudaFree(b->d_env_to_field);
@@ -311,6 +314,11 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
     std::memset(&b->ground, 0, sizeof(b->ground));
     b->ground.kind = kind;
     if (kind == 0 || kind == 3) return TRL_OK;
+    if (data_count >= (1LL << 32)) {
+        trl_set_error("trl_ground_set_heightfields: more than 2^32 height values");
+        b->ground.kind = 0;
+        return TRL_ERR_UNSUPPORTED;
+    }
     if ((kind != 1 && kind != 2) || num_fields < 1 || pieces_per_field < 1 || pieces_per_field > 4 || !data ||
         data_count < 1 || !data_offset || !res || !origin || !scale || !bounds) {
         trl_set_error("trl_ground_set_heightfields: invalid argument");
@@ -332,6 +340,8 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         }
         for (int k = 0; k < 3; ++k) { pc.origin[k] = origin[3 * i + k]; pc.scale[k] = scale[3 * i + k]; }
         for (int k = 0; k < 4; ++k) pc.bounds[k] = bounds[4 * i + k];
+        pc.rscale[0] = 1.0 / pc.scale[0];
+        pc.rscale[1] = 1.0 / pc.scale[2];
     }
     if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * (size_t)data_count), "cudaMalloc(heightfields)") ||
         !cuda_ok(cudaMemcpy(b->d_ground_data, data, sizeof(float) * (size_t)data_count, cudaMemcpyHostToDevice), "H2D(heightfields)") ||
@@ -408,8 +418,8 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
         !out_ptr(b, out_cell, E * (size_t)b->cfg.num_samples * 3, &d_cell, copies))
         return TRL_ERR_CUDA;
     int rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, d_pose, d_vel, d_bp, d_bv,
-                                   d_bq, d_ba, d_gv, d_ph, d_fl, b->d_sample_local, d_state, d_cell, b->stream);
-    b->launches += 1;
+                                   d_bq, d_ba, d_gv, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, d_cell, b->stream);
+    b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
     return finish(b, copies, rc);
 }
 
@@ -458,8 +468,8 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (!rc && d_state) {
         if (!d_bp || !d_bv) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
-                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, d_state, nullptr, b->stream);
-        b->launches += 1;
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, b->stream);
+        b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
     }
     return finish(b, copies, rc);
 }

@@ -178,41 +178,74 @@ TRL_DEV double clampd(double v, double lo, double hi) {
     return (lo < t) ? t : lo;
 }
 
-TRL_DEV double grid_coord(double pos, double origin, double scale, int res) {
+// Correctly-rounded x / d from the correctly-rounded reciprocal r = RN(1/d) (computed once per piece on the host):
+// Markstein's FMA sequence -- q0 = RN(x r) is within 2 ulp, one residual correction makes it faithful, and a second
+// one with the exact residual yields RN(x / d) (Markstein 1990, "Computation of elementary functions on the IBM RISC
+// System/6000 processor", Thm. on division by correction with a correctly rounded reciprocal). 5 instructions instead
+// of the ~35 of a full IEEE division; bit-identical to `x / d` for normal-range operands, which is asserted over 1e7
+// random operands in tests/test_gpu_parity.py. Outside the safe range (inf, NaN, tiny, huge) it falls back to __ddiv_rn.
+TRL_DEV double div_by_const(double x, double d, double r) {
+    const double ax = fabs(x);
+    if (!(ax > 1e-200 && ax < 1e200)) return __ddiv_rn(x, d);
+    const double q0 = __dmul_rn(x, r);
+    const double e0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(e0, r, q0);
+    const double e1 = __fma_rn(-q1, d, x);
+    return __fma_rn(e1, r, q1);
+}
+
+TRL_DEV double grid_coord(double pos, double origin, double scale, double rscale, int res) {
     double c = __dsub_rn(pos, origin);
-    c = __ddiv_rn(c, scale);
+    c = div_by_const(c, scale, rscale);
     return __dadd_rn(c, __dmul_rn((double)(res - 1), 0.5));
 }
 
-TRL_DEV double sample_segment_2d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
-                                 int* valid, int* cell) {
+// A height sample split in two halves so callers can batch the (dependent-address) heightfield loads of several
+// samples before combining them: prep computes cell indices / weights, finish applies the reference's interpolation.
+struct SamplePrep {
+    unsigned int o0, o1, o2;  // element offsets into the float heightfield array (< 2^32 floats; o2 unused in 2-D)
+    double w0, w1, w2;     // 2-D: (1-lerp, lerp, -) ; 3-D: barycentric (u, v, w)
+    double sy;             // scale.y
+    int valid;
+    int cell[3];           // piece, i, j
+};
+
+TRL_DEV void sample_prep_2d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
     const double tol = 0.0001;
     const int w = pc.res_x, l = pc.res_z;
-    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], w);
-    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], l);
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], w);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], l);
     if (c0 > -tol && c0 < w - 1 + tol && c1 > -tol && c1 < l - 1 + tol) {
         c0 = clampd(c0, 0.0, w - 1.0);
         c1 = clampd(c1, 0.0, l - 1.0);
     }
     const bool outside = (c0 < 0 || c0 > w - 1 || c1 < 0 || c1 > l - 1);
-    *valid = !outside;
+    sp.valid = !outside;
     c0 = clampd(c0, 0.0, w - 1.0);
     const int i = (int)c0;
     const int j = (w - 1 < i + 1) ? (w - 1) : (i + 1);
     const double lerp = __dsub_rn(c0, (double)i);
-    const float* row = data + pc.data_offset;
-    const double a = __dmul_rn((double)__ldg(row + i), pc.scale[1]);
-    const double b = __dmul_rn((double)__ldg(row + j), pc.scale[1]);
-    cell[0] = s; cell[1] = i; cell[2] = j;
-    return __dadd_rn(__dmul_rn(__dsub_rn(1.0, lerp), a), __dmul_rn(lerp, b));
+    sp.o0 = (unsigned int)(pc.data_offset + i);
+    sp.o1 = (unsigned int)(pc.data_offset + j);
+    sp.o2 = sp.o0;
+    sp.w0 = __dsub_rn(1.0, lerp);
+    sp.w1 = lerp;
+    sp.w2 = 0.0;
+    sp.sy = pc.scale[1];
+    sp.cell[0] = s; sp.cell[1] = i; sp.cell[2] = j;
 }
 
-TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
-                              int* valid, int* cell) {
+TRL_DEV double sample_finish_2d(const SamplePrep& sp, float f0, float f1) {
+    const double a = __dmul_rn((double)f0, sp.sy);  // GetVertex(i,0)[1] (row 0 only)
+    const double b = __dmul_rn((double)f1, sp.sy);
+    return __dadd_rn(__dmul_rn(sp.w0, a), __dmul_rn(sp.w1, b));
+}
+
+TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
     const double tol = 0.0001;
     const int rx = pc.res_x, rz = pc.res_z;
-    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], rx);
-    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], rz);
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], rx);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], rz);
     c0 = clampd(c0, 0.0, rx - 1.0 - tol);
     c1 = clampd(c1, 0.0, rz - 1.0 - tol);
     const int i = (int)c0, j = (int)c1;
@@ -221,10 +254,9 @@ TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data
     const int i0 = lower ? i : i + 1, j0 = lower ? j : j + 1;
     const int i1 = lower ? i + 1 : i, j1 = lower ? j : j + 1;
     const int i2 = lower ? i + 1 : i, j2 = lower ? j + 1 : j;
-    const float* base = data + pc.data_offset;
-    const double v0 = __dmul_rn((double)__ldg(base + (long long)j0 * rx + i0), pc.scale[1]);
-    const double v1 = __dmul_rn((double)__ldg(base + (long long)j1 * rx + i1), pc.scale[1]);
-    const double v2 = __dmul_rn((double)__ldg(base + (long long)j2 * rx + i2), pc.scale[1]);
+    sp.o0 = (unsigned int)(pc.data_offset + (long long)j0 * rx + i0);
+    sp.o1 = (unsigned int)(pc.data_offset + (long long)j1 * rx + i1);
+    sp.o2 = (unsigned int)(pc.data_offset + (long long)j2 * rx + i2);
     // cMathUtil::CalcBarycentric (util/MathUtil.cpp:630-647) on the two unit triangles. With a = (0,0), b = (1,0),
     // c = (1,1) (lower) or a = (1,1), b = (0,1), c = (0,0) (upper) the general expression has d00 = d01 = 1,
     // d11 = 2, denom = 1 exactly, so every product by them and the division are exact and the reference's
@@ -240,32 +272,70 @@ TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data
     }
     const double bv = __dsub_rn(__dmul_rn(2.0, d20), d21);
     const double bw = __dsub_rn(d21, d20);
-    const double bu = __dsub_rn(__dsub_rn(1.0, bv), bw);
-    *valid = 1;
-    cell[0] = s; cell[1] = i; cell[2] = j;
-    return __dadd_rn(__dadd_rn(__dmul_rn(bu, v0), __dmul_rn(bv, v1)), __dmul_rn(bw, v2));
+    sp.w0 = __dsub_rn(__dsub_rn(1.0, bv), bw);
+    sp.w1 = bv;
+    sp.w2 = bw;
+    sp.sy = pc.scale[1];
+    sp.valid = 1;
+    sp.cell[0] = s; sp.cell[1] = i; sp.cell[2] = j;
 }
 
-// cGroundVar2D::SampleHeight / cGroundVar3D::SampleHeight (first containing piece wins; none: -inf, invalid).
-// `pcs` may point to global or shared memory (the observation kernel stages the env's pieces in shared memory).
+TRL_DEV double sample_finish_3d(const SamplePrep& sp, float f0, float f1, float f2) {
+    const double v0 = __dmul_rn((double)f0, sp.sy);
+    const double v1 = __dmul_rn((double)f1, sp.sy);
+    const double v2 = __dmul_rn((double)f2, sp.sy);
+    return __dadd_rn(__dadd_rn(__dmul_rn(sp.w0, v0), __dmul_rn(sp.w1, v1)), __dmul_rn(sp.w2, v2));
+}
+
+TRL_DEV double sample_segment_2d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
+                                 int* valid, int* cell) {
+    SamplePrep sp;
+    sample_prep_2d(pc, s, px, pz, sp);
+    *valid = sp.valid;
+    cell[0] = sp.cell[0]; cell[1] = sp.cell[1]; cell[2] = sp.cell[2];
+    return sample_finish_2d(sp, __ldg(data + sp.o0), __ldg(data + sp.o1));
+}
+
+TRL_DEV double sample_slab_3d(const DevPiece& pc, const float* __restrict__ data, int s, double px, double pz,
+                              int* valid, int* cell) {
+    SamplePrep sp;
+    sample_prep_3d(pc, s, px, pz, sp);
+    *valid = sp.valid;
+    cell[0] = sp.cell[0]; cell[1] = sp.cell[1]; cell[2] = sp.cell[2];
+    return sample_finish_3d(sp, __ldg(data + sp.o0), __ldg(data + sp.o1), __ldg(data + sp.o2));
+}
+
+TRL_DEV bool piece_contains(int kind, const DevPiece& pc, double px, double pz) {
+    if (kind == 1) return px >= pc.bounds[0] && px <= pc.bounds[1];
+    return px >= pc.bounds[0] && px <= pc.bounds[1] && pz >= pc.bounds[2] && pz <= pc.bounds[3];
+}
+
+// index of the first piece containing (px, pz), or -1 (the reference scans the pieces in order and stops at the first)
+TRL_DEV int ground_find_piece(int kind, int num_pieces, const DevPiece* pcs, double px, double pz) {
+    for (int s = 0; s < num_pieces; ++s)
+        if (piece_contains(kind, pcs[s], px, pz)) return s;
+    return -1;
+}
+
+TRL_DEV double ground_sample_piece(int kind, const DevPiece* pcs, int s, const float* __restrict__ data, double px,
+                                   double pz, int* valid, int* cell) {
+    if (s < 0) {
+        *valid = 0;
+        cell[0] = -1; cell[1] = 0; cell[2] = 0;
+        return -CUDART_INF;
+    }
+    return (kind == 1) ? sample_segment_2d(pcs[s], data, s, px, pz, valid, cell)
+                       : sample_slab_3d(pcs[s], data, s, px, pz, valid, cell);
+}
+
 TRL_DEV double ground_sample_pieces(int kind, int num_pieces, const DevPiece* pcs, const float* __restrict__ data,
                                     double px, double pz, int* valid, int* cell) {
-    cell[0] = -1; cell[1] = 0; cell[2] = 0;
     if (kind == 0 || kind == 3) {  // cGround::SampleHeight (sim/Ground.cpp:176-186)
         *valid = 1;
+        cell[0] = -1; cell[1] = 0; cell[2] = 0;
         return 0.0;
     }
-    *valid = 0;
-    for (int s = 0; s < num_pieces; ++s) {
-        const DevPiece& pc = pcs[s];
-        if (kind == 1) {
-            if (px >= pc.bounds[0] && px <= pc.bounds[1]) return sample_segment_2d(pc, data, s, px, pz, valid, cell);
-        } else {
-            if (px >= pc.bounds[0] && px <= pc.bounds[1] && pz >= pc.bounds[2] && pz <= pc.bounds[3])
-                return sample_slab_3d(pc, data, s, px, pz, valid, cell);
-        }
-    }
-    return -CUDART_INF;
+    return ground_sample_piece(kind, pcs, ground_find_piece(kind, num_pieces, pcs, px, pz), data, px, pz, valid, cell);
 }
 
 TRL_DEV int ground_field_of_env(const DevGround& g, int env) {

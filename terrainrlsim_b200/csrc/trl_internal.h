@@ -77,6 +77,7 @@ struct DevPiece {
     double origin[3];
     double scale[3];
     double bounds[4];
+    double rscale[2];  // correctly-rounded 1/scale_x, 1/scale_z (host IEEE division) for div_by_const
 };
 
 struct DevGround {
@@ -117,4 +118,5 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          const double* sample_local, double* out_state, int* out_cell, void* stream);
+                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream);
+size_t trl_obs_env_rec_bytes();

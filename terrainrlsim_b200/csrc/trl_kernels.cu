@@ -781,35 +781,36 @@ TRL_DEV void roty_to_quat(double c, double s, double m11, double* q) {
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
-             const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
-             const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
-             const double* __restrict__ ground_vel, const double* __restrict__ phase,
-             const unsigned char* __restrict__ flip_arr, const double* __restrict__ sample_local,
-             double* __restrict__ out_state, int* __restrict__ out_cell) {
-    __shared__ DevPiece s_pieces[kWarpsPerBlock][4];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int e = blockIdx.x * kWarpsPerBlock + warp;
-    if (e >= E) return;
+// Per-env record handed from k_obs_env to k_obs_samples: the ground-sample transform (InvRigid(origin_trans) with
+// y += ground height under the root) and the stance flip.
+struct ObsEnvRec {
+    double i00, i02, i20, i22, it0, it1, it2;
+    int flip;
+    int pad;
+};
+
+// k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env.
+// Everything that is per-env (heading, origin transform, ground height under the root) is computed once here.
+constexpr int kObsG = 8;
+
+__global__ void __launch_bounds__(128)
+k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
+          const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
+          const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
+          const double* __restrict__ ground_vel, const double* __restrict__ phase,
+          const unsigned char* __restrict__ flip_arr, ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = tid % kObsG;
+    const int e_raw = tid / kObsG;
+    const bool env_ok = e_raw < E;
+    const int e = env_ok ? e_raw : E - 1;
     const int N = M->N, n = M->n;
     const ObsDims D = obs_dims(N, cfg);
-    // stage this env's terrain piece descriptors (<= 4 x 96 B) in shared memory: every sample reads them
-    const int gkind = g.kind, gP = g.pieces_per_field;
-    if (gkind == 1 || gkind == 2) {
-        const unsigned long long* src =
-            reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_pieces[warp]);
-        const int words = gP * (int)(sizeof(DevPiece) / 8);
-        for (int i = lane; i < words; i += 32) dst[i] = __ldg(src + i);
-    }
-    __syncwarp();
-    const DevPiece* pcs = s_pieces[warp];
     const double* q = pose + (size_t)e * n;
     double* out = out_state + (size_t)e * D.F;
     const int flip = flip_arr ? (flip_arr[e] != 0) : 0;
-    const bool has_ground = g.kind != 0;
+    const int gkind = g.kind, gP = g.pieces_per_field;
+    const bool has_ground = gkind != 0;
 
     // cKinTree::CalcHeading / BuildOriginTrans (anim/KinTree.cpp:1604-1639): origin = Ry(-heading) * T(-root_xz)
     const double rx = q[0], ry = q[1], rz = q[2];
@@ -824,50 +825,37 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     const double o00 = ch, o02 = sh, o20 = -sh, o22 = ch;
     const double o11 = ch + (1 - ch);
     const double oz = 0.0;  // structurally-zero entries, kept in the products so inf/NaN propagate like the reference
-    // origin_trans = rot * translate(-origin): translation column = rot * (-x, -0, -z)
     const double nx = -rx, ny = -0.0, nz = -rz;
     const double ot0 = o00 * nx + oz * ny + o02 * nz;
     const double ot1 = oz * nx + o11 * ny + oz * nz;
     const double ot2 = o20 * nx + oz * ny + o22 * nz;
 
     // ground height under the root (TerrainRLCharController.cpp:261-279,370-380)
-    int v0, c0[3];
     double ground_h = 0.0;
-    if (has_ground) ground_h = ground_sample_pieces(gkind, gP, pcs, g.data, rx, rz, &v0, c0);
+    if (gkind == 1 || gkind == 2) {
+        const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
+        int v0, c0[3];
+        ground_h = ground_sample_pieces(gkind, gP, pcs, g.data, rx, rz, &v0, c0);
+    }
     const double ground_h_finite = isfinite(ground_h) ? ground_h : 0.0;
 
     // ground sample transform = InvRigid(origin_trans), y += ground_h (finite)
-    // inverse rotation = transpose; translation = -(R^T t)
     const double i00 = o00, i02 = o20, i20 = o02, i22 = o22, i11 = o11;
     const double it0 = -(i00 * ot0 + oz * ot1 + i02 * ot2);
     const double it1 = -(oz * ot0 + i11 * ot1 + oz * ot2) + ground_h_finite;
     const double it2 = -(i20 * ot0 + oz * ot1 + i22 * ot2);
-
-    // ---- ground block ---- (sample_local[s] = CalcGroundSamplePos's local (x, z), precomputed once per batch)
-    for (int s = lane; s < D.G; s += 32) {
-        double hs = 0.0;
-        int cell[3] = {-1, 0, 0};
-        if (has_ground) {
-            const double lx = __ldg(sample_local + 2 * s);
-            double lz = __ldg(sample_local + 2 * s + 1);
-            if (flip && D.is_ct) lz = -lz;
-            const double px = i00 * lx + oz * 0.0 + i02 * lz + it0;
-            const double pz = i20 * lx + oz * 0.0 + i22 * lz + it2;
-            int vs;
-            hs = ground_sample_pieces(gkind, gP, pcs, g.data, px, pz, &vs, cell) - it1;
-        }
-        out[s] = hs;
-        if (out_cell) {
-            int* oc = out_cell + ((size_t)e * D.G + s) * 3;
-            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
-        }
+    if (lane == 0 && env_ok) {
+        ObsEnvRec r;
+        r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
+        r.flip = flip; r.pad = has_ground ? 1 : 0;
+        rec[e] = r;
     }
+    if (!env_ok) return;
 
     // ---- pose block ----
     double* opose = out + D.G;
     double* ovel = opose + D.psize;
     const double zsign = (D.is_ct && flip) ? -1.0 : 1.0;
-    // root_pos_rel = origin_trans * (root - ground_h ey)
     const double ryg = ry - ground_h;
     const double rr0 = o00 * rx + oz * ryg + o02 * rz + ot0;
     const double rr1 = oz * rx + o11 * ryg + oz * rz + ot1;
@@ -875,8 +863,17 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     if (lane == 0) opose[0] = rr1;
     const int first = D.is_ct ? 0 : 1;
     const int per = D.pos_dim + (D.is3d ? 4 : 0);
-    // feature slot of body i: valid bodies are packed in index order
-    for (int i = first + lane; i < N; i += 32) {
+    // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830) swaps the two leg blocks at the tail
+    // of the pose / vel feature vectors; it is applied on the fly as an index permutation of the writes.
+    const int nlp = (!D.is_ct && flip) ? ((N - 1) / 2) * 2 : 0;
+    auto perm = [nlp](int idx, int size) {
+        if (nlp == 0) return idx;
+        const int a = size - 1 - idx;          // distance from the end
+        if (a < nlp) return idx - nlp;          // second leg block -> first
+        if (a < 2 * nlp) return idx + nlp;      // first leg block -> second
+        return idx;
+    };
+    for (int i = first + lane; i < N; i += kObsG) {
         const int slot = D.is_ct ? M->slot_ct[i] : M->slot_base[i];
         if (slot < 0) continue;
         const double* bp = body_pos + ((size_t)e * N + i) * 3;
@@ -884,9 +881,11 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
         const double f0 = (o00 * bx + oz * by + o02 * bz + ot0) - rr0;
         const double f1 = (oz * bx + o11 * by + oz * bz + ot1) - rr1;
         const double f2 = zsign * (o20 * bx + oz * by + o22 * bz + ot2) - rr2;
-        double* dst = opose + 1 + slot * per;
-        dst[0] = f0; dst[1] = f1;
+        const int b0 = 1 + slot * per;
+        opose[perm(b0, D.psize)] = f0;
+        opose[perm(b0 + 1, D.psize)] = f1;
         if (D.is3d) {
+            double* dst = opose + b0;
             dst[2] = f2;
             double oq[4], bq[4], rq[4];
             roty_to_quat(ch, sh, o11, oq);
@@ -902,25 +901,31 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
     double gv[3] = {0, 0, 0};
     if (ground_vel) { gv[0] = ground_vel[3 * (size_t)e]; gv[1] = ground_vel[3 * (size_t)e + 1]; gv[2] = ground_vel[3 * (size_t)e + 2]; }
     const int vper = D.pos_dim + (D.is3d ? 3 : 0);
-    for (int i = lane; i < N; i += 32) {
+    const bool hopper = cfg.obs_kind == TRL_OBS_TERRAIN_RL_HOPPER;
+    for (int i = lane; i < N; i += kObsG) {
         const double* bv = body_vel + ((size_t)e * N + i) * 3;
         const double vx = bv[0] - gv[0], vy = bv[1] - gv[1], vz = bv[2] - gv[2];
-        double* dst = ovel + i * vper;
-        dst[0] = o00 * vx + oz * vy + o02 * vz;
-        dst[1] = oz * vx + o11 * vy + oz * vz;
+        const int b0 = i * vper;
+        const double w0 = o00 * vx + oz * vy + o02 * vz;
+        double w1 = oz * vx + o11 * vy + oz * vz;
+        if (hopper && b0 + 1 == D.vsize - 1) w1 = vel[(size_t)e * n + 5];  // root omega_z (MonopedHopperController.cpp:1545-1552)
+        ovel[perm(b0, D.vsize)] = w0;
+        ovel[perm(b0 + 1, D.vsize)] = w1;
         if (D.is3d) {
+            double* dst = ovel + b0;
             dst[2] = zsign * (o20 * vx + oz * vy + o22 * vz);
             const double* av = body_angvel + ((size_t)e * N + i) * 3;
-            double a0 = o00 * av[0] + o02 * av[2];
-            double a1 = o11 * av[1];
-            double a2 = zsign * (o20 * av[0] + o22 * av[2]);
+            double a0 = o00 * av[0] + oz * av[1] + o02 * av[2];
+            double a1 = oz * av[0] + o11 * av[1] + oz * av[2];
+            double a2 = zsign * (o20 * av[0] + oz * av[1] + o22 * av[2]);
             if (flip) { a0 = -a0; a1 = -a1; a2 = -a2; }
             dst[3] = a0; dst[4] = a1; dst[5] = a2;
         }
     }
-    __syncwarp();
-    if (cfg.obs_kind == TRL_OBS_TERRAIN_RL_HOPPER && lane == 0) {
-        // cMonopedHopperController overrides: signed root rotation angle, root omega_z
+    // cMonopedHopperController::BuildPoliStatePose: the last pose entry is overwritten by the signed root rotation
+    // angle (cSimCharacter::GetRootRotation -> RotMatToAxisAngle, util/MathUtil.cpp:239-260). That entry belongs to
+    // body N-1, so the write is issued from that body's lane to keep program order.
+    if (hopper && lane == ((N - 1 - first) % kObsG)) {
         double R[9];
         quat_to_mat(qr[0], qr[1], qr[2], qr[3], R);
         double c = (R[0] + R[4] + R[8] - 1) * 0.5;
@@ -933,16 +938,6 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
         }
         if (az < 0) theta = -theta;
         opose[D.psize - 1] = theta;
-        ovel[D.vsize - 1] = vel[(size_t)e * n + 5];
-    }
-    if (!D.is_ct && flip) {  // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830)
-        const int nlp = ((N - 1) / 2) * 2;
-        for (int i = lane; i < nlp; i += 32) {
-            int a = D.psize - i - 1, b = D.psize - nlp - i - 1;
-            double t = opose[a]; opose[a] = opose[b]; opose[b] = t;
-            a = D.vsize - i - 1; b = D.vsize - nlp - i - 1;
-            t = ovel[a]; ovel[a] = ovel[b]; ovel[b] = t;
-        }
     }
     if (cfg.num_phase_bins >= 0 && lane == 0) {  // cCtPhaseController::BuildPhaseState (CtPhaseController.cpp:120-139)
         double* ph = ovel + D.vsize;
@@ -952,6 +947,51 @@ k_poli_state(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E
         if (cfg.num_phase_bins > 0) {
             const int bin = (int)(pv * cfg.num_phase_bins);
             if (bin >= 0 && bin < cfg.num_phase_bins) ph[bin + 1] = 1.0;
+        }
+    }
+}
+
+// k_obs_samples: ParseGround's sample loop -- one thread per (env, sample); block = one env, so the env's record and
+// terrain piece descriptors are staged once in shared memory and every thread is an independent load chain.
+__global__ void __launch_bounds__(256)
+k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
+              const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
+    __shared__ DevPiece s_pieces[4];
+    __shared__ ObsEnvRec s_rec;
+    const int e = blockIdx.x;
+    const int G = cfg.num_samples;
+    const int gkind = g.kind, gP = g.pieces_per_field;
+    if (gkind == 1 || gkind == 2) {
+        const unsigned long long* src =
+            reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_pieces);
+        const int words = gP * (int)(sizeof(DevPiece) / 8);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x < (int)(sizeof(ObsEnvRec) / 8))
+        reinterpret_cast<unsigned long long*>(&s_rec)[threadIdx.x] =
+            __ldg(reinterpret_cast<const unsigned long long*>(rec + e) + threadIdx.x);
+    __syncthreads();
+    const bool is_ct = (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
+    const bool has_ground = gkind != 0;
+    const double oz = 0.0;
+    double* out = out_state + (size_t)e * F;
+    for (int s = threadIdx.x; s < G; s += blockDim.x) {
+        double hs = 0.0;
+        int cell[3] = {-1, 0, 0};
+        if (has_ground) {
+            const double lx = __ldg(sample_local + 2 * s);
+            double lz = __ldg(sample_local + 2 * s + 1);
+            if (s_rec.flip && is_ct) lz = -lz;
+            const double px = s_rec.i00 * lx + oz * 0.0 + s_rec.i02 * lz + s_rec.it0;
+            const double pz = s_rec.i20 * lx + oz * 0.0 + s_rec.i22 * lz + s_rec.it2;
+            int vs;
+            hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+        }
+        out[s] = hs;
+        if (out_cell) {
+            int* oc = out_cell + ((size_t)e * G + s) * 3;
+            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
         }
     }
 }
@@ -1059,7 +1099,8 @@ static int pd_group_override() {
 
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
     const int nl = hm.nl, N = hm.N;
-    int G = (N <= 8) ? 8 : (N <= 16 ? 16 : 32);
+    int G = 32;  // measured on B200: with the shared-memory workspace limiting residency, one env per warp is fastest
+    (void)N;
     const int ov = pd_group_override();
     if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
     if (nl > 32) return launch_imp_pd_t<32, 0>(dm, hm, E, p, stream);
@@ -1100,13 +1141,21 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          const double* sample_local, double* out_state, int* out_cell, void* stream) {
-    (void)hm; (void)F;
-    const int blocks = (E + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    k_poli_state<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel,
-                                                                          body_quat, body_angvel, ground_vel, phase,
-                                                                          flip, sample_local, out_state, out_cell);
+                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream) {
+    (void)hm;
+    const long long threads = (long long)E * kObsG;
+    const int blocks = (int)((threads + 127) / 128);
+    k_obs_env<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel, body_quat,
+                                                        body_angvel, ground_vel, phase, flip, (ObsEnvRec*)env_rec,
+                                                        out_state);
+    int rc = (int)cudaGetLastError();
+    if (rc || cfg.num_samples <= 0) return rc;
+    const int tpb = cfg.num_samples >= 192 ? 256 : (cfg.num_samples >= 96 ? 128 : 64);
+    k_obs_samples<<<E, tpb, 0, (cudaStream_t)stream>>>(g, cfg, F, E, (const ObsEnvRec*)env_rec, sample_local, out_state,
+                                                       out_cell);
     return (int)cudaGetLastError();
 }
+
+size_t trl_obs_env_rec_bytes() { return sizeof(ObsEnvRec); }
 
 int trl_obs_state_size(int N, const trl_obs_cfg& cfg) { return obs_dims(N, cfg).F; }

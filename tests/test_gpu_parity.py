@@ -155,6 +155,25 @@ def test_ground_sample_height_bit_exact(trl, oracle, name):
     assert np.any(~np.isfinite(h)) and np.any(valid == 0) and np.any(valid == 1)
 
 
+@pytest.mark.parametrize("name", ["dog", "biped3d"])
+def test_ground_sample_height_bit_exact_large(trl, oracle, name):
+    """3e6 random positions per terrain kind: cell indices, validity and heights bit-identical to the oracle. This is
+    also the exactness check of the FMA-based division by the (constant) grid spacing used on the GPU."""
+    E, S = 32, 100000
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=4)
+    rng = np.random.default_rng(17)
+    pos = np.zeros((E, S, 3))
+    pos[:, :, 0] = rng.uniform(-41, 41, (E, S))
+    pos[:, :, 2] = rng.uniform(-41, 41, (E, S)) if name == "biped3d" else rng.uniform(-1.1, 1.1, (E, S))
+    pos[:, : S // 4, 0] *= 1e-3  # many samples near the shared piece boundary at x = 0
+    h, valid, cell = batch.ground_sample_height(pos)
+    for e in range(E):
+        rh, rv, rc = oracle.sample_height_batch(grounds[e % len(grounds)], pos[e])
+        assert np.array_equal(cell[e], rc)
+        assert np.array_equal(valid[e].astype(np.int32), rv)
+        assert np.array_equal(h[e], rh)
+
+
 @pytest.mark.parametrize("name", CONFIG_NAMES)
 def test_build_poli_state(trl, oracle, name):
     E = 96
