@@ -66,6 +66,7 @@ def lib():
                                    "terrainrlsim_b200 has no CPU fallback")
             if _build.nvcc_path() is not None:
                 path = _build.build()
+        path = os.environ.get("TRL_LIB", path)  # tuning hook: load an alternative build of the same ABI
         l = C.CDLL(path)
         for name, res, args in SYMBOLS:
             f = getattr(l, name)  # AttributeError here = the library does not export the ABI

@@ -350,15 +350,18 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         b->ground.kind = 0;
         return TRL_ERR_CUDA;
     }
-    if (env_to_field) {
-        for (int e = 0; e < b->E; ++e)
-            if (env_to_field[e] < 0 || env_to_field[e] >= num_fields) {
+    {
+        std::vector<int> e2f((size_t)b->E);
+        for (int e = 0; e < b->E; ++e) {
+            e2f[e] = env_to_field ? env_to_field[e] : (e % num_fields);
+            if (e2f[e] < 0 || e2f[e] >= num_fields) {
                 trl_set_error("trl_ground_set_heightfields: env_to_field out of range");
                 b->ground.kind = 0;
                 return TRL_ERR_INVALID_ARG;
             }
+        }
         if (!cuda_ok(cudaMalloc((void**)&b->d_env_to_field, sizeof(int) * (size_t)b->E), "cudaMalloc(env_to_field)") ||
-            !cuda_ok(cudaMemcpy(b->d_env_to_field, env_to_field, sizeof(int) * (size_t)b->E, cudaMemcpyHostToDevice), "H2D(env_to_field)")) {
+            !cuda_ok(cudaMemcpy(b->d_env_to_field, e2f.data(), sizeof(int) * (size_t)b->E, cudaMemcpyHostToDevice), "H2D(env_to_field)")) {
             b->ground.kind = 0;
             return TRL_ERR_CUDA;
         }

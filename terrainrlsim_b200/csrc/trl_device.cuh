@@ -254,9 +254,10 @@ TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, Sam
     const int i0 = lower ? i : i + 1, j0 = lower ? j : j + 1;
     const int i1 = lower ? i + 1 : i, j1 = lower ? j : j + 1;
     const int i2 = lower ? i + 1 : i, j2 = lower ? j + 1 : j;
-    sp.o0 = (unsigned int)(pc.data_offset + (long long)j0 * rx + i0);
-    sp.o1 = (unsigned int)(pc.data_offset + (long long)j1 * rx + i1);
-    sp.o2 = (unsigned int)(pc.data_offset + (long long)j2 * rx + i2);
+    const unsigned int base = (unsigned int)pc.data_offset;  // < 2^32 floats (checked at registration)
+    sp.o0 = base + (unsigned int)(j0 * rx + i0);
+    sp.o1 = base + (unsigned int)(j1 * rx + i1);
+    sp.o2 = base + (unsigned int)(j2 * rx + i2);
     // cMathUtil::CalcBarycentric (util/MathUtil.cpp:630-647) on the two unit triangles. With a = (0,0), b = (1,0),
     // c = (1,1) (lower) or a = (1,1), b = (0,1), c = (0,0) (upper) the general expression has d00 = d01 = 1,
     // d11 = 2, denom = 1 exactly, so every product by them and the division are exact and the reference's
@@ -310,11 +311,14 @@ TRL_DEV bool piece_contains(int kind, const DevPiece& pc, double px, double pz) 
     return px >= pc.bounds[0] && px <= pc.bounds[1] && pz >= pc.bounds[2] && pz <= pc.bounds[3];
 }
 
-// index of the first piece containing (px, pz), or -1 (the reference scans the pieces in order and stops at the first)
+// index of the first piece containing (px, pz), or -1 (the reference scans the pieces in order and stops at the
+// first). Branch-free: all (<= 4) containment tests are evaluated and the lowest set bit wins.
 TRL_DEV int ground_find_piece(int kind, int num_pieces, const DevPiece* pcs, double px, double pz) {
-    for (int s = 0; s < num_pieces; ++s)
-        if (piece_contains(kind, pcs[s], px, pz)) return s;
-    return -1;
+    unsigned mask = 0;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (s < num_pieces && piece_contains(kind, pcs[s], px, pz)) mask |= 1u << s;
+    return mask ? (__ffs(mask) - 1) : -1;
 }
 
 TRL_DEV double ground_sample_piece(int kind, const DevPiece* pcs, int s, const float* __restrict__ data, double px,
@@ -339,7 +343,7 @@ TRL_DEV double ground_sample_pieces(int kind, int num_pieces, const DevPiece* pc
 }
 
 TRL_DEV int ground_field_of_env(const DevGround& g, int env) {
-    return g.env_to_field ? __ldg(g.env_to_field + env) : (env % g.num_fields);
+    return __ldg(g.env_to_field + env);  // always materialised at registration (env % num_fields by default)
 }
 
 TRL_DEV double ground_sample_height(const DevGround& g, int env, double px, double pz, int* valid, int* cell) {

@@ -27,6 +27,9 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef TRL_PD_MIN_BLOCKS
+#define TRL_PD_MIN_BLOCKS 4
+#endif
 
 // shared-memory workspace layout (in doubles) of k_imp_pd, per env. The PD vectors (ep, ev, kpm, kdm, kdu: 5n)
 // alias the transform arrays Tl/T0 (24N >= 5n), which are dead by the time the PD errors are formed.
@@ -214,7 +217,7 @@ TRL_DEV int ldlt_solve_smem(double* H, int ldh, double* x, int nl, int lane) {
 // G = lanes per env (32 / G envs share a warp; G >= N so one lane owns one joint in the per-joint phases).
 // NLMAX > 0: register-resident LDL^T for nl <= NLMAX <= 32; NLMAX == 0: shared-memory fallback (G = 32 only).
 template <int G, int NLMAX>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, TRL_PD_MIN_BLOCKS)
 k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     extern __shared__ double smem[];
     constexpr int EPW = 32 / G;  // envs per warp
@@ -953,6 +956,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
 
 // k_obs_samples: ParseGround's sample loop -- one thread per (env, sample); block = one env, so the env's record and
 // terrain piece descriptors are staged once in shared memory and every thread is an independent load chain.
+template <int KIND>  // ground kind (1 = var2d, 2 = var3d, 0/3 = none/plane) as a compile-time constant
 __global__ void __launch_bounds__(256)
 k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
               const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
@@ -960,13 +964,15 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
     __shared__ ObsEnvRec s_rec;
     const int e = blockIdx.x;
     const int G = cfg.num_samples;
-    const int gkind = g.kind, gP = g.pieces_per_field;
+    constexpr int gkind = KIND;
+    const int gP = g.pieces_per_field;
     if (gkind == 1 || gkind == 2) {
-        const unsigned long long* src =
-            reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_pieces);
         const int words = gP * (int)(sizeof(DevPiece) / 8);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+        if ((int)threadIdx.x < words) {
+            const unsigned long long* src =
+                reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
+            reinterpret_cast<unsigned long long*>(s_pieces)[threadIdx.x] = __ldg(src + threadIdx.x);
+        }
     }
     if (threadIdx.x < (int)(sizeof(ObsEnvRec) / 8))
         reinterpret_cast<unsigned long long*>(&s_rec)[threadIdx.x] =
@@ -1151,8 +1157,12 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
     const int tpb = cfg.num_samples >= 192 ? 256 : (cfg.num_samples >= 96 ? 128 : 64);
-    k_obs_samples<<<E, tpb, 0, (cudaStream_t)stream>>>(g, cfg, F, E, (const ObsEnvRec*)env_rec, sample_local, out_state,
-                                                       out_cell);
+    const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g.kind == 1) k_obs_samples<1><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+    else if (g.kind == 2) k_obs_samples<2><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+    else if (g.kind == 3) k_obs_samples<3><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+    else k_obs_samples<0><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
     return (int)cudaGetLastError();
 }
 

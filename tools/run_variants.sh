@@ -1,7 +1,6 @@
-for k in 2 4; do
-  sed -i "s/constexpr int kSB = [0-9];/constexpr int kSB = $k;/" terrainrlsim_b200/csrc/trl_kernels.cu
-  python -c "from terrainrlsim_b200 import build; build.build(force=True)"
-  python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-e2e --no-others > gpurun_out/bench_k$k.json 2> gpurun_out/bench_k$k.err; tail -2 gpurun_out/bench_k$k.err
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+for v in "" _mb5 _mb6; do
+  TRL_LIB=$PWD/terrainrlsim_b200/lib/libtrl_b200$v.so python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-e2e > gpurun_out/bench_v$v.json 2> gpurun_out/bench_v$v.err; tail -2 gpurun_out/bench_v$v.err
   python -c "
-import json; d=json.load(open('gpurun_out/bench_k$k.json')); print('kSB=$k', d['ms_per_step'], d['kernel_ms'])"
+import json; d=json.load(open('gpurun_out/bench_v$v.json')); print('variant=$v', d['ms_per_step'], d['kernel_ms']); print({k:(round(v['ms_per_step'],4),round(v['ms_per_pd_launch'],4)) for k,v in d['other_workloads'].items()})"
 done
