@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libtrl_b200.so (there is no CPU fallback)")
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177", "-o", LIB_PATH] + SOURCES
+           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,128", "-o", LIB_PATH] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

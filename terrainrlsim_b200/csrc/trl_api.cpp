@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -51,11 +52,17 @@ struct trl_batch {
     int F = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // fork/join plumbing of trl_step_fused: the three independent kernel chains of a step (stable PD | kin-char + FK |
+    // observation) run concurrently on the main stream and two side streams (captured as parallel graph branches)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int overlap = 1;
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
     int* d_status = nullptr;
     double* d_sample_local = nullptr;  // [G][2] local (x, z) of every ground sample
     void* d_env_rec = nullptr;         // [E] per-env sampling transform handed from k_obs_env to k_obs_samples
+    double* d_pd_scratch = nullptr;    // [E][stride] assembled (M + dt Kd, rhs, tau terms) between the two PD kernels
     // ground
     DevGround ground{};
     float* d_ground_data = nullptr;
@@ -163,6 +170,15 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     Guard g(device);
     if (!cuda_ok(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
     b->stream = b->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        if (!cuda_ok(cudaStreamCreateWithFlags(&b->side[i], cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
+        if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    }
+    if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    {
+        const char* ov = getenv("TRL_STEP_OVERLAP");  // tuning hook: 0 serialises the chains on one stream
+        if (ov) b->overlap = atoi(ov) != 0;
+    }
     if (!cuda_ok(cudaMalloc((void**)&b->d_model, sizeof(DevModel)), "cudaMalloc(model)")) return nullptr;
     if (!cuda_ok(cudaMemcpy(b->d_model, &m->dev, sizeof(DevModel), cudaMemcpyHostToDevice), "H2D(model)")) return nullptr;
     if (m->num_frames > 0) {
@@ -192,6 +208,11 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaMalloc((void**)&b->d_sample_local, sizeof(double) * loc.size()), "cudaMalloc(samples)")) return nullptr;
         if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
     }
+    {
+        const size_t bytes = trl_pd_scratch_doubles(m->dev) * sizeof(double) * (size_t)num_envs;
+        if (!cuda_ok(cudaMalloc((void**)&b->d_pd_scratch, bytes), "cudaMalloc(pd scratch)")) return nullptr;
+        cudaMemset(b->d_pd_scratch, 0, bytes);  // structurally-zero entries of the packed matrix are never written
+    }
     if (!cuda_ok(cudaMalloc(&b->d_env_rec, trl_obs_env_rec_bytes() * (size_t)num_envs), "cudaMalloc(env_rec)")) return nullptr;
     if (!cuda_ok(cudaMalloc((void**)&b->d_status, sizeof(int) * (size_t)num_envs), "cudaMalloc(status)")) return nullptr;
     cudaMemset(b->d_status, 0, sizeof(int) * (size_t)num_envs);
@@ -209,9 +230,15 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     if (b->d_status) cudaFree(b->d_status);
     if (b->d_sample_local) cudaFree(b->d_sample_local);
     if (b->d_env_rec) cudaFree(b->d_env_rec);
+    if (b->d_pd_scratch) cudaFree(b->d_pd_scratch);
     if (b->d_ground_data) cudaFree(b->d_ground_data);
     if (b->d_pieces) cudaFree(b->d_pieces);
     if (b->d_env_to_field) cudaFree(b->d_env_to_field);
+    for (int i = 0; i < 2; ++i) {
+        if (b->side[i]) { cudaStreamSynchronize(b->side[i]); cudaStreamDestroy(b->side[i]); }
+        if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
+    }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
@@ -262,8 +289,8 @@ extern "C" int trl_imp_pd_update_control_force(trl_batch* b, double dt, const do
         !out_ptr(b, inout_tau, E * n, &p.tau, copies, true) || !out_ptr(b, out_mass, E * n * n, &p.out_mass, copies) ||
         !out_ptr(b, out_bias, E * n, &p.out_bias, copies))
         return TRL_ERR_CUDA;
-    int rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->stream);
-    b->launches += 1;
+    int rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->d_pd_scratch, b->stream);
+    if (rc > 0) { b->launches += rc; rc = 0; } else { rc = -rc; }
     return finish(b, copies, rc);
 }
 
@@ -450,29 +477,43 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
         !out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies))
         return TRL_ERR_CUDA;
     int rc = 0;
+    if (p.tau && (!p.tar_pose || !p.tar_vel)) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
+    if (d_kp && (b->model->num_frames < 2 || !d_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
+    if (d_state && (!d_bp || !d_bv)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
+    if (d_state && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
+    // Three independent chains: (A) stable PD on the main stream, (B) kin-char pose + FK, (C) observation. With
+    // overlap on, B and C fork onto side streams after the inputs are staged and join before the outputs are read.
+    const bool fork = b->overlap && ((p.tau ? 1 : 0) + (d_kp ? 1 : 0) + (d_state ? 1 : 0)) > 1;
+    cudaStream_t sA = b->stream, sB = b->stream, sC = b->stream;
+    if (fork) {
+        if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
+        if (d_kp && p.tau) { sB = b->side[0]; cudaStreamWaitEvent(sB, b->ev_fork, 0); }
+        if (d_state && (p.tau || d_kp)) { sC = b->side[1]; cudaStreamWaitEvent(sC, b->ev_fork, 0); }
+    }
     if (p.tau) {
-        if (!p.tar_pose || !p.tar_vel) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
         if (a->dt > 0) {
-            rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->stream);
-            b->launches += 1;
+            rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->d_pd_scratch, sA);
+            if (rc > 0) { b->launches += rc; rc = 0; } else { rc = -rc; }
         } else {
-            cudaMemsetAsync(p.tau, 0, sizeof(double) * E * n, b->stream);
+            cudaMemsetAsync(p.tau, 0, sizeof(double) * E * n, sA);
         }
     }
     if (!rc && d_kp) {
-        if (b->model->num_frames < 2 || !d_time) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
-        rc = trl_launch_kin_char(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, b->stream);
+        rc = trl_launch_kin_char(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, sB);
         b->launches += 1;
         if (!rc && d_kbp) {
-            rc = trl_launch_fk(b->d_model, b->model->dev, b->E, d_kp, nullptr, d_kbp, b->stream);
+            rc = trl_launch_fk(b->d_model, b->model->dev, b->E, d_kp, nullptr, d_kbp, sB);
             b->launches += 1;
         }
     }
     if (!rc && d_state) {
-        if (!d_bp || !d_bv) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
-                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, b->stream);
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC);
         b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+    }
+    if (fork) {  // join (also on error, so the streams stay consistent / a capture stays closed)
+        if (sB != b->stream) { cudaEventRecord(b->ev_join[0], sB); cudaStreamWaitEvent(b->stream, b->ev_join[0], 0); }
+        if (sC != b->stream) { cudaEventRecord(b->ev_join[1], sC); cudaStreamWaitEvent(b->stream, b->ev_join[1], 0); }
     }
     return finish(b, copies, rc);
 }

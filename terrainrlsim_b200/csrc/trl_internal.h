@@ -105,8 +105,9 @@ struct StepPtrs {
     int* status;
 };
 
-size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block);
-int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream);
+size_t trl_pd_scratch_doubles(const DevModel& hm);
+// returns the number of kernels launched (> 0) or a negative cudaError_t
+int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream);
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
                   double* out_body_pos, void* stream);
 int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,

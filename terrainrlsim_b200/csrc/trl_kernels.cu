@@ -37,7 +37,7 @@ struct PdLayout {
     int q, qd, Tl, T0, Rq, g0, cj, sj, V, A, IF, S, C, ep, ev, kpm, kdm, kdu, x, H, ldh, total;
 };
 
-__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax) {
+__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, bool split = false) {
     PdLayout L;
     int o = 0;
     L.q = o; o += n;
@@ -63,11 +63,29 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax) {
     L.S = o; o += 6 * nl;
     L.C = o; o += nl;
     const int rows = nlmax > 0 ? nlmax : nl;
-    L.x = o; o += rows;
     L.ldh = rows | 1;  // odd row stride: conflict-free column loads / row-per-lane access
-    L.H = o; o += rows * L.ldh + (nlmax > 0 ? 32 : 0);  // + slack: lanes >= NLMAX read (and ignore) past the last row
+    if (split) {  // H / rhs go to the global scratch; only the diagonal is stashed (x = Hd)
+        L.x = o; o += nl;
+        L.H = o;
+    } else {
+        L.x = o; o += rows;
+        L.H = o; o += rows * L.ldh + (nlmax > 0 ? 32 : 0);  // + slack: lanes >= NLMAX read (and ignore) past the last row
+    }
     L.total = (o + 1) & ~1;
     return L;
+}
+
+// global scratch handed from k_imp_pd<.., SPLIT> to k_pd_solve, per env (doubles):
+//   [Hp: nl(nl+1)/2 packed lower of M + dt*Kd][rhs: nl][t0: n][t1: n]     tau_i = t0_i - t1_i * qdd_col(i)
+struct PdScratch { int np, rhs, t0, t1, stride; };
+__host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
+    PdScratch s;
+    s.np = nl * (nl + 1) / 2;
+    s.rhs = s.np;
+    s.t0 = s.rhs + nl;
+    s.t1 = s.t0 + n;
+    s.stride = (s.t1 + n + 1) & ~1;
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,16 +134,10 @@ TRL_DEV double fast_rcp(double d) {
     return r;
 }
 
+// Core: a[] = column `lane` of the symmetric system (identity-padded to NLMAX), b = rhs[lane]. Returns x[lane].
 template <int NLMAX>
-TRL_DEV int ldlt_solve_regs(const double* H, int ldh, double* x, int nl, int lane) {
-    double a[NLMAX];
-    const bool live = lane < nl;
-    // H is NLMAX x NLMAX with identity padding beyond nl (prepared by the caller); lanes >= NLMAX read slack
-#pragma unroll
-    for (int i = 0; i < NLMAX; ++i) a[i] = H[i * ldh + lane];
-    double b = (lane < NLMAX) ? x[lane] : 0.0;
+TRL_DEV double ldlt_regs_core(double (&a)[NLMAX], double b, int lane, int& bad) {
     double rdiag = 0.0;
-    int bad = 0;
 #pragma unroll
     for (int k = 0; k < NLMAX; ++k) {
         const double d = __shfl_sync(0xffffffffu, a[k], k);
@@ -156,7 +168,19 @@ TRL_DEV int ldlt_solve_regs(const double* H, int ldh, double* x, int nl, int lan
         const double ai = (lane < i) ? a[i] : 0.0;
         acc = fma(ai, xi, acc);
     }
-    if (live) x[lane] = fma(-rdiag, acc, z);
+    return fma(-rdiag, acc, z);
+}
+
+template <int NLMAX>
+TRL_DEV int ldlt_solve_regs(const double* H, int ldh, double* x, int nl, int lane) {
+    double a[NLMAX];
+    // H is NLMAX x NLMAX with identity padding beyond nl (prepared by the caller); lanes >= NLMAX read slack
+#pragma unroll
+    for (int i = 0; i < NLMAX; ++i) a[i] = H[i * ldh + lane];
+    const double b = (lane < NLMAX) ? x[lane] : 0.0;
+    int bad = 0;
+    const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
+    if (lane < nl) x[lane] = xv;
     return bad;
 }
 
@@ -216,9 +240,10 @@ TRL_DEV int ldlt_solve_smem(double* H, int ldh, double* x, int nl, int lane) {
 // ------------------------------------------------------------------------------------------------
 // G = lanes per env (32 / G envs share a warp; G >= N so one lane owns one joint in the per-joint phases).
 // NLMAX > 0: register-resident LDL^T for nl <= NLMAX <= 32; NLMAX == 0: shared-memory fallback (G = 32 only).
-template <int G, int NLMAX>
+// SPLIT: stop after assembling the system and write it to the global scratch (k_pd_solve finishes the step).
+template <int G, int NLMAX, bool SPLIT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TRL_PD_MIN_BLOCKS)
-k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
+k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
     extern __shared__ double smem[];
     constexpr int EPW = 32 / G;  // envs per warp
     const int wlane = threadIdx.x & 31;
@@ -231,7 +256,9 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
     const bool env_ok = e_raw < E;
     const int e = env_ok ? e_raw : E - 1;  // tail groups recompute the last env and store nothing
     const int N = M->N, n = M->n, nl = M->nl;
-    const PdLayout L = pd_layout(N, n, nl, NLMAX);
+    const PdLayout L = pd_layout(N, n, nl, NLMAX, SPLIT);
+    const PdScratch SC = pd_scratch(n, nl);
+    double* sc = SPLIT ? scratch + (size_t)e * SC.stride : nullptr;
     double* ws = smem + (size_t)(warp * EPW + sub) * L.total;
     double* q = ws + L.q;
     double* qd = ws + L.qd;
@@ -262,10 +289,16 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
         qd[i] = p.vel[(size_t)e * n + i];
     }
     const int hrows = NLMAX > 0 ? NLMAX : nl;
-    for (int i = lane; i < hrows * ldh; i += G) H[i] = 0.0;
-    for (int i = lane; i < hrows; i += G) x[i] = 0.0;
+    if (!SPLIT) {
+        for (int i = lane; i < hrows * ldh; i += G) H[i] = 0.0;
+        for (int i = lane; i < hrows; i += G) x[i] = 0.0;
+    } else if (p.out_mass && env_ok) {
+        double* om = p.out_mass + (size_t)e * n * n;
+        for (int idx = lane; idx < n * n; idx += G) om[idx] = 0.0;
+    }
     __syncwarp();
-    for (int r = nl + lane; r < hrows; r += G) H[r * ldh + r] = 1.0;  // identity padding (ordered by the next sync)
+    if (!SPLIT)
+        for (int r = nl + lane; r < hrows; r += G) H[r * ldh + r] = 1.0;  // identity padding (ordered by the next sync)
 
     // P1: joint-local transforms; the root lane also prepares R(q_root), gravity and c_root in the root frame
     if (lane < N) {
@@ -466,14 +499,32 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
         for (int a = c; a >= 0; a = M->col_parent[a]) {
             const double* sa = S + 6 * a;
             const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
-            H[c * ldh + a] = hv;
-            H[a * ldh + c] = hv;
+            if (SPLIT) {
+                if (a == c) x[c] = hv;  // diagonal stash: dt*Kd is added once the gains are known (P8)
+                else if (env_ok) sc[c * (c + 1) / 2 + a] = hv;
+            } else {
+                H[c * ldh + a] = hv;
+                H[a * ldh + c] = hv;
+            }
         }
     }
     __syncwarp();
 
     // optional outputs: cRBDModel::GetMassMat / GetBiasForce on the full n-dof layout (dead dofs are exact zeros)
-    if (p.out_mass && env_ok) {
+    if (SPLIT && p.out_mass && env_ok) {  // rare path (GetMassMat): re-walk the chains, scatter M symmetrically
+        double* om = p.out_mass + (size_t)e * n * n;
+        for (int c = lane; c < nl; c += G) {
+            const int di = M->col_dof[c];
+            om[di * n + di] = x[c];
+            for (int a = M->col_parent[c]; a >= 0; a = M->col_parent[a]) {
+                const int da = M->col_dof[a];
+                const double hv = sc[c * (c + 1) / 2 + a];
+                om[di * n + da] = hv;
+                om[da * n + di] = hv;
+            }
+        }
+    }
+    if (!SPLIT && p.out_mass && env_ok) {
         double* om = p.out_mass + (size_t)e * n * n;
         for (int idx = lane; idx < n * n; idx += G) {
             const int ci = M->dof_col[idx / n], ck = M->dof_col[idx % n];
@@ -534,6 +585,29 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
         }
     }
     __syncwarp();
+    if (SPLIT) {
+        // hand the assembled system to k_pd_solve: packed diagonal, rhs, and tau_i = t0_i - t1_i * qdd_col(i)
+        if (env_ok) {
+            for (int c = lane; c < nl; c += G) {
+                const int i = M->col_dof[c];
+                sc[SC.rhs + c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
+                sc[c * (c + 1) / 2 + c] = x[c] + dt * kdu[i];
+            }
+            for (int i = lane; i < n; i += G) {
+                double t0 = kpm[i] * ep[i] + kdm[i] * ev[i];
+                double t1 = kdm[i] * dt;
+                if (M->dof_col[i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
+                    const double dg = dt * kdu[i];
+                    const double acc = (fabs(dg) > DBL_MIN) ? t0 / dg : 0.0;
+                    t0 = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
+                    t1 = 0.0;
+                }
+                sc[SC.t0 + i] = t0;
+                sc[SC.t1 + i] = t1;
+            }
+        }
+        return;
+    }
     for (int c = lane; c < nl; c += G) {
         const int i = M->col_dof[c];
         x[c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
@@ -548,7 +622,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
 #pragma unroll 1
         for (int s2 = 0; s2 < EPW; ++s2) {
             double* wss = smem + (size_t)(warp * EPW + s2) * L.total;
-            const int b2 = ldlt_solve_regs<(NLMAX > 0 ? NLMAX : 1)>(wss + L.H, ldh, wss + L.x, nl, wlane);
+            const int b2 = SPLIT ? 0 : ldlt_solve_regs<(NLMAX > 0 ? NLMAX : 1)>(wss + L.H, ldh, wss + L.x, nl, wlane);
             if (s2 == sub) bad = b2;
         }
     } else {
@@ -579,6 +653,48 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
         if (lane == 0 && env_ok) p.status[e] = bad;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pd_solve: second half of the split stable-PD step -- one warp per env, no shared memory: loads the packed system
+// from the scratch straight into the register-resident LDL^T (lane <-> column), solves, forms tau.
+// ------------------------------------------------------------------------------------------------
+template <int NLMAX>
+__global__ void __launch_bounds__(128)
+k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
+           int tau_accumulate, int* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (e >= E) return;
+    const int n = M->n, nl = M->nl;
+    const PdScratch SC = pd_scratch(n, nl);
+    const double* sc = scratch + (size_t)e * SC.stride;
+    double a[NLMAX];
+    const int tl = lane * (lane + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < NLMAX; ++i) {
+        double v = (i == lane) ? 1.0 : 0.0;  // identity padding
+        if (lane < nl && i < nl) v = __ldg(sc + ((lane <= i) ? (i * (i + 1) / 2 + lane) : (tl + i)));
+        a[i] = v;
+    }
+    const double b = (lane < nl) ? __ldg(sc + SC.rhs + lane) : 0.0;
+    int bad = 0;
+    const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = (i < n) ? M->dof_col[i] : -1;
+        const double acc = __shfl_sync(0xffffffffu, xv, c < 0 ? 0 : c);
+        if (i < n) {
+            const double t = __ldg(sc + SC.t0 + i) - __ldg(sc + SC.t1 + i) * (c < 0 ? 0.0 : acc);
+            if (!isfinite(t)) bad |= 1;
+            double* out = tau + (size_t)e * n + i;
+            *out = tau_accumulate ? (*out + t) : t;
+        }
+    }
+    if (status) {
+        bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
+        if (lane == 0) status[e] = bad;
     }
 }
 
@@ -1054,9 +1170,7 @@ double trl_fp64_probe_tflops(void* stream) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-size_t trl_pd_smem_bytes(const DevModel& hm, int warps_per_block) {
-    return (size_t)pd_layout(hm.N, hm.n, hm.nl, hm.nl <= 32 ? 32 : 0).total * sizeof(double) * (size_t)warps_per_block;
-}
+
 
 static int ensure_smem(const void* func, size_t bytes) {
     // set once per (kernel, size): cudaFuncSetAttribute is kept out of graph captures
@@ -1073,10 +1187,15 @@ static int ensure_smem(const void* func, size_t bytes) {
     return 0;
 }
 
-template <int G, int NLMAX>
-static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int G, int NLMAX, bool SPLIT>
+static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
     constexpr int EPW = 32 / G;
-    const size_t per_warp = (size_t)pd_layout(hm.N, hm.n, hm.nl, NLMAX).total * sizeof(double) * EPW;
+    const size_t per_warp = (size_t)pd_layout(hm.N, hm.n, hm.nl, NLMAX, SPLIT).total * sizeof(double) * EPW;
     // warps per block: maximise resident warps per SM under the 227 KB shared-memory budget (1 KB reserved per block)
     int wpb = 1, best = 0;
     for (int w = kWarpsPerBlock; w >= 1; w >>= 1) {
@@ -1084,12 +1203,24 @@ static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const 
         const int resident = (int)((227 * 1024) / blk) * w;
         if (resident > best) { best = resident; wpb = w; }
     }
+    {
+        static const int wpb_env = env_int("TRL_PD_WPB", 0);  // tuning hook
+        if (wpb_env == 1 || wpb_env == 2 || wpb_env == 4) wpb = wpb_env;
+    }
     const size_t smem = per_warp * wpb;
-    int rc = ensure_smem((const void*)k_imp_pd<G, NLMAX>, smem);
+    int rc = ensure_smem((const void*)k_imp_pd<G, NLMAX, SPLIT>, smem);
     if (rc) return rc;
     const int envs_per_block = wpb * EPW;
     const int blocks = (E + envs_per_block - 1) / envs_per_block;
-    k_imp_pd<G, NLMAX><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
+    k_imp_pd<G, NLMAX, SPLIT><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p, scratch);
+    return (int)cudaGetLastError();
+}
+
+template <int NLMAX>
+static int launch_pd_solve_t(const DevModel* dm, int E, const StepPtrs& p, const double* scratch, void* stream) {
+    const int wpb = 4;
+    k_pd_solve<NLMAX><<<(E + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
+                                                                                 p.status);
     return (int)cudaGetLastError();
 }
 
@@ -1103,19 +1234,38 @@ static int pd_group_override() {
     return v;
 }
 
-int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+size_t trl_pd_scratch_doubles(const DevModel& hm) { return (size_t)pd_scratch(hm.n, hm.nl).stride; }
+
+// Returns the number of kernels launched (>0) or a negative cudaError.
+int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
     const int nl = hm.nl, N = hm.N;
-    int G = 32;  // measured on B200: with the shared-memory workspace limiting residency, one env per warp is fastest
-    (void)N;
+    if (nl > 32) {
+        int rc = launch_imp_pd_t<32, 0, false>(dm, hm, E, p, nullptr, stream);
+        return rc ? -rc : 1;
+    }
+    static const int split_env = env_int("TRL_PD_SPLIT", -1);  // tuning hooks (tests exercise both paths)
+    const bool split = (split_env >= 0) ? (split_env != 0) : true;
+    int G = split ? ((N <= 8) ? 8 : (N <= 16 ? 16 : 32)) : 32;
     const int ov = pd_group_override();
     if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
-    if (nl > 32) return launch_imp_pd_t<32, 0>(dm, hm, E, p, stream);
-#define TRL_PD_CASE(GG, NL) if (G == GG && nl <= NL) return launch_imp_pd_t<GG, NL>(dm, hm, E, p, stream);
+    int rc = -1;
+#define TRL_PD_CASE(GG, NL)                                                                       \
+    if (rc == -1 && G == GG && nl <= NL)                                                          \
+        rc = split ? launch_imp_pd_t<GG, NL, true>(dm, hm, E, p, scratch, stream)                 \
+                   : launch_imp_pd_t<GG, NL, false>(dm, hm, E, p, nullptr, stream);
     TRL_PD_CASE(8, 8) TRL_PD_CASE(8, 20) TRL_PD_CASE(8, 32)
-    TRL_PD_CASE(16, 8) TRL_PD_CASE(16, 18) TRL_PD_CASE(16, 20) TRL_PD_CASE(16, 32)
+    TRL_PD_CASE(16, 18) TRL_PD_CASE(16, 32)
     TRL_PD_CASE(32, 8) TRL_PD_CASE(32, 18) TRL_PD_CASE(32, 20) TRL_PD_CASE(32, 24) TRL_PD_CASE(32, 26) TRL_PD_CASE(32, 32)
 #undef TRL_PD_CASE
-    return launch_imp_pd_t<32, 0>(dm, hm, E, p, stream);
+    if (rc) return rc > 0 ? -rc : rc;
+    if (!split) return 1;
+    if (nl <= 8) rc = launch_pd_solve_t<8>(dm, E, p, scratch, stream);
+    else if (nl <= 18) rc = launch_pd_solve_t<18>(dm, E, p, scratch, stream);
+    else if (nl <= 20) rc = launch_pd_solve_t<20>(dm, E, p, scratch, stream);
+    else if (nl <= 24) rc = launch_pd_solve_t<24>(dm, E, p, scratch, stream);
+    else if (nl <= 26) rc = launch_pd_solve_t<26>(dm, E, p, scratch, stream);
+    else rc = launch_pd_solve_t<32>(dm, E, p, scratch, stream);
+    return rc ? -rc : 2;
 }
 
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
