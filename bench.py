@@ -72,41 +72,47 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (test infrastructure used here only as the measured CPU baseline)
 # ----------------------------------------------------------------------------------------------
-def cpu_oracle_run(name, sample_envs, passes, threads):
-    """Runs `passes` passes of the oracle's fused step over `sample_envs` envs split across `threads` threads
-    (one thread per env range, like cScenarioTrain::Run). Returns seconds."""
-    from oracle import oracle_py
-    from terrainrlsim_b200 import synth
-    om = oracle_py.Model(name)
-    cfg = oracle_py.obs_cfg(**synth.obs_config(name))
-    kind, fields = synth.make_grounds(name, min(sample_envs, 32))
-    grounds = [oracle_py.Ground(kind, p) for p in fields]
-    x = synth.make_inputs(name, sample_envs)
-    d = synth.load_model_dict(name)
-    dt = (1.0 / 30) / d["num_update_steps"]
-    arrays = dict(x)
-    oracle_py.step_range(om, cfg, arrays, grounds, dt, 0, min(8, sample_envs))  # allocate outputs, warm up
-    bounds = np.linspace(0, sample_envs, threads + 1).astype(int)
+class CpuArm:
+    """The CPU oracle's fused step over `sample_envs` envs, one thread per env range (like cScenarioTrain::Run)."""
 
-    def work(lo, hi):
-        for _ in range(passes):
-            oracle_py.step_range(om, cfg, arrays, grounds, dt, int(lo), int(hi))
+    def __init__(self, name, sample_envs, threads):
+        from oracle import oracle_py
+        from terrainrlsim_b200 import synth
+        self.oracle = oracle_py
+        self.threads = threads
+        self.sample = sample_envs
+        self.om = oracle_py.Model(name)
+        self.cfg = oracle_py.obs_cfg(**synth.obs_config(name))
+        kind, fields = synth.make_grounds(name, min(sample_envs, 32))
+        self.grounds = [oracle_py.Ground(kind, p) for p in fields]
+        d = synth.load_model_dict(name)
+        self.dt = (1.0 / 30) / d["num_update_steps"]
+        self.arrays = dict(synth.make_inputs(name, sample_envs))
+        oracle_py.step_range(self.om, self.cfg, self.arrays, self.grounds, self.dt, 0, min(8, sample_envs))  # allocate outputs
+        self.bounds = np.linspace(0, sample_envs, threads + 1).astype(int)
 
-    ts = [threading.Thread(target=work, args=(bounds[i], bounds[i + 1])) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    return time.perf_counter() - t0
+    def run(self, passes):
+        """`passes` passes over the sample; returns seconds."""
+        def work(lo, hi):
+            for _ in range(passes):
+                self.oracle.step_range(self.om, self.cfg, self.arrays, self.grounds, self.dt, int(lo), int(hi))
+
+        ts = [threading.Thread(target=work, args=(self.bounds[i], self.bounds[i + 1])) for i in range(self.threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
 
 
 def cpu_baseline(name, target_seconds=6.0):
     threads = os.cpu_count() or 1
     sample = 256 * threads
-    t = cpu_oracle_run(name, sample, 1, threads)
+    arm = CpuArm(name, sample, threads)
+    t = arm.run(1)
     passes = max(1, int(target_seconds / max(t, 1e-6)))
-    t = cpu_oracle_run(name, sample, passes, threads)
+    t = arm.run(passes)
     val = sample * passes / t
     return {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d envs x %d passes of the C oracle (faithful restatement; faster than the Eigen reference: "
@@ -114,17 +120,20 @@ def cpu_baseline(name, target_seconds=6.0):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port on all host cores."""
+    """--impl reference: the reference's CPU implementation of the path = the oracle port on all host cores
+    (the reference itself cannot be built here: Eigen / Bullet are not vendored). Each step is a bounded sample
+    of the workload; under torchrun only rank 0 works and prints."""
     if rank != 0:
         return
     name = args.config
     threads = os.cpu_count() or 1
-    sample = 128 * threads
+    sample = 512 * threads
+    arm = CpuArm(name, sample, threads)
     for _ in range(max(args.warmup, 1)):
-        cpu_oracle_run(name, sample, 1, threads)
+        arm.run(1)
     t = 0.0
     for _ in range(args.steps):
-        t += cpu_oracle_run(name, sample, 1, threads)
+        t += arm.run(1)
     val = sample * args.steps / t
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -299,7 +308,15 @@ class Workload:
                          (x["phase"], np.float64), (x["flip"], np.uint8), (o["state"], np.float64), (None, np.int32)])
             _capi.lib().trl_build_poli_state(b._h, *p)
 
-        for name, fn in (("imp_pd", f_pd), ("kin_char", f_kin), ("fk", f_fk), ("poli_state", f_obs)):
+        kin_args = [b.make_step_args(self.dt, self.inputs[s], {k: v for k, v in self.outputs[s].items() if k.startswith("kin")})
+                    for s in range(self.sets)]
+        idx = {id(self.inputs[s]): s for s in range(self.sets)}
+
+        def f_kin_fused(x, o):
+            b.step_fused_args(kin_args[idx[id(x)]])
+
+        for name, fn in (("imp_pd", f_pd), ("kin_char", f_kin), ("fk", f_fk), ("kin_fused", f_kin_fused),
+                         ("poli_state", f_obs)):
             for s in range(self.sets):
                 fn(self.inputs[s], self.outputs[s])
             torch.cuda.synchronize()

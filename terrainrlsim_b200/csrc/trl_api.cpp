@@ -499,12 +499,8 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
         }
     }
     if (!rc && d_kp) {
-        rc = trl_launch_kin_char(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, sB);
+        rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, d_kbp, sB);
         b->launches += 1;
-        if (!rc && d_kbp) {
-            rc = trl_launch_fk(b->d_model, b->model->dev, b->E, d_kp, nullptr, d_kbp, sB);
-            b->launches += 1;
-        }
     }
     if (!rc && d_state) {
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,

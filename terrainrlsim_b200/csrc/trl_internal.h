@@ -113,6 +113,9 @@ int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* p
 int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
                         const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
                         void* stream);
+int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
+                   const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
+                   double* out_body_pos, void* stream);
 int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,
                              unsigned char* out_valid, int* out_cell, void* stream);
 int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g, const trl_obs_cfg& cfg, int F,

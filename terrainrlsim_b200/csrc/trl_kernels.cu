@@ -38,29 +38,32 @@ struct PdLayout {
 };
 
 __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, bool split = false) {
+    // Lifetimes: Tl (P1-P2) | IF (P5-P7) share one region; sj, V, A (P3-P5) | ep, ev, kpm, kdm, kdu (P8-P10) share
+    // another; T0 lives P1-P7 (the joint-subspace columns are recomputed from it on the fly, never stored).
     PdLayout L;
     int o = 0;
     L.q = o; o += n;
     L.qd = o; o += n;
-    L.Tl = o; o += 12 * N;
     L.T0 = o; o += 12 * N;
-    {
-        int a = L.Tl;
-        L.ep = a; a += n;
-        L.ev = a; a += n;
-        L.kpm = a; a += n;
-        L.kdm = a; a += n;
-        L.kdu = a; a += n;
-        if (a > o) o = a;
-    }
     L.Rq = o; o += 9;
     L.g0 = o; o += 3;
     L.cj = o; o += 3;
-    L.sj = o; o += 6 * N;
-    L.V = o; o += 6 * N;
-    L.A = o; o += 6 * N;
+    {
+        int a = o;
+        L.sj = a; a += 6 * N;
+        L.V = a; a += 6 * N;
+        L.A = a; a += 6 * N;
+        int b = o;
+        L.ep = b; b += n;
+        L.ev = b; b += n;
+        L.kpm = b; b += n;
+        L.kdm = b; b += n;
+        L.kdu = b; b += n;
+        o = a > b ? a : b;
+    }
+    L.Tl = o;
     L.IF = o; o += 16 * N;
-    L.S = o; o += 6 * nl;
+    L.S = 0;  // unused
     L.C = o; o += nl;
     const int rows = nlmax > 0 ? nlmax : nl;
     L.ldh = rows | 1;  // odd row stride: conflict-free column loads / row-per-lane access
@@ -86,6 +89,23 @@ __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
     s.t1 = s.t0 + n;
     s.stride = (s.t1 + n + 1) & ~1;
     return s;
+}
+
+// Column c of the joint subspace S in the root frame (cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828),
+// recomputed from the joint's root-frame transform wherever it is needed instead of being stored.
+TRL_DEV void subspace_col(const DevModel* __restrict__ M, const double* T0, const double* Rq, int c, double* s) {
+    const int j = M->col_joint[c], kind = M->col_kind[c], a = M->col_axis[c];
+    const double* T = T0 + 12 * j;
+    if (kind == CK_ANG) {
+        s[0] = T[a]; s[1] = T[3 + a]; s[2] = T[6 + a];
+        cross3(T + 9, s, s + 3);
+    } else if (kind == CK_LIN) {
+        s[0] = s[1] = s[2] = 0.0;
+        s[3] = T[a]; s[4] = T[3 + a]; s[5] = T[6 + a];
+    } else {  // CK_ROOT_LIN: row a of R(q_root)
+        s[0] = s[1] = s[2] = 0.0;
+        s[3] = Rq[3 * a]; s[4] = Rq[3 * a + 1]; s[5] = Rq[3 * a + 2];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,7 +291,6 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     double* V = ws + L.V;
     double* A = ws + L.A;
     double* IF = ws + L.IF;
-    double* S = ws + L.S;
     double* C = ws + L.C;
     double* ep = ws + L.ep;
     double* ev = ws + L.ev;
@@ -349,31 +368,17 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     // P2: root-frame transforms
     compose_levels(M, Tl, T0, lane, 1, G);
 
-    // P3: subspace columns S_c (6) in the root frame; then s_j = S_j qd_j
-    for (int c = lane; c < nl; c += G) {
-        const int j = M->col_joint[c], kind = M->col_kind[c], a = M->col_axis[c];
-        const double* T = T0 + 12 * j;
-        double w[3] = {0, 0, 0}, v[3];
-        if (kind == CK_ANG) {
-            w[0] = T[a]; w[1] = T[3 + a]; w[2] = T[6 + a];
-            cross3(T + 9, w, v);
-        } else if (kind == CK_LIN) {
-            v[0] = T[a]; v[1] = T[3 + a]; v[2] = T[6 + a];
-        } else {  // CK_ROOT_LIN: row a of R(q_root)
-            v[0] = Rq[3 * a]; v[1] = Rq[3 * a + 1]; v[2] = Rq[3 * a + 2];
-        }
-        S[6 * c] = w[0]; S[6 * c + 1] = w[1]; S[6 * c + 2] = w[2];
-        S[6 * c + 3] = v[0]; S[6 * c + 4] = v[1]; S[6 * c + 5] = v[2];
-    }
-    __syncwarp();
+    // P3: s_j = S_j qd_j in the root frame (columns recomputed from T0)
     if (lane < N) {
         const int j = lane;
         double s[6] = {0, 0, 0, 0, 0, 0};
         const int c0 = M->first_col[j], nc = M->ncol[j];
         for (int c = c0; c < c0 + nc; ++c) {
             const double w = qd[M->col_dof[c]];
+            double sc6[6];
+            subspace_col(M, T0, Rq, c, sc6);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s[k] += S[6 * c + k] * w;
+            for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) sj[6 * j + k] = s[k];
@@ -481,7 +486,8 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     for (int c = lane; c < nl; c += G) {
         const int j = M->col_joint[c];
         const double* I = IF + 16 * j;
-        const double* s = S + 6 * c;
+        double s[6];
+        subspace_col(M, T0, Rq, c, s);
         const double m = I[0];
         const double* h = I + 1;
         double hxv[3], hxw[3];
@@ -497,7 +503,8 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         const double* f = I + 10;
         C[c] = s[0] * f[0] + s[1] * f[1] + s[2] * f[2] + s[3] * f[3] + s[4] * f[4] + s[5] * f[5];
         for (int a = c; a >= 0; a = M->col_parent[a]) {
-            const double* sa = S + 6 * a;
+            double sa[6];
+            subspace_col(M, T0, Rq, a, sa);
             const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
             if (SPLIT) {
                 if (a == c) x[c] = hv;  // diagonal stash: dt*Kd is added once the gains are known (P8)
@@ -843,6 +850,76 @@ k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, in
             for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
         }
         for (int i = 0; i < sz; ++i) out_vel[(size_t)e * n + o + i] = v[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_kin<G>: the fused step's kinematic chain in one kernel -- cKinCharacter::Pose(t) (pose + finite-difference vel)
+// and cKinTree::CalcBodyPartPos of that pose. G lanes per env (lane <-> joint), 32/G envs per warp.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(128)
+k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
+      const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
+      double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
+    extern __shared__ double smem[];
+    constexpr int EPW = 32 / G;
+    const int wlane = threadIdx.x & 31;
+    const int lane = wlane % G, sub = wlane / G;
+    const int warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int e_raw = (blockIdx.x * wpb + warp) * EPW + sub;
+    if ((blockIdx.x * wpb + warp) * EPW >= E) return;
+    const bool env_ok = e_raw < E;
+    const int e = env_ok ? e_raw : E - 1;
+    const int N = M->N, n = M->n, fs = n + 1;
+    double* Tl = smem + (size_t)(warp * EPW + sub) * 24 * N;
+    double* Tw = Tl + 12 * N;
+    const double t = time[e];
+    const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
+    double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
+    if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
+    if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
+    for (int j = lane; j < N; j += G) {
+        double p0[7], p1[7], v[7];
+        kin_joint_pose(M, frames, fs, j, t, opos, orot, p0);
+        const int o = M->offset[j], sz = M->size[j];
+        if (env_ok)
+            for (int i = 0; i < sz; ++i) out_pose[(size_t)e * n + o + i] = p0[i];
+        if (out_vel) {
+            kin_joint_pose(M, frames, fs, j, t + ddt, opos, orot, p1);
+            if (j == 0) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+                quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
+            } else if (M->type[j] == JT_SPHERICAL) {
+                quat_vel_rel(p0, p1, ddt, v);
+            } else {
+                for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+            }
+            if (env_ok)
+                for (int i = 0; i < sz; ++i) out_vel[(size_t)e * n + o + i] = v[i];
+        }
+        if (out_body_pos) {
+            double R[9], tt[3];
+            joint_local_trans(M, j, p0, R, tt);
+            double* dst = (j == 0) ? Tw : (Tl + 12 * j);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dst[i] = R[i];
+            dst[9] = tt[0]; dst[10] = tt[1]; dst[11] = tt[2];
+        }
+    }
+    if (!out_body_pos) return;
+    __syncwarp();
+    compose_levels(M, Tl, Tw, lane, 1, G);
+    if (env_ok) {
+        double* o = out_body_pos + (size_t)e * N * 3;
+        for (int idx = lane; idx < N * 3; idx += G) {
+            const int j = idx / 3, r = idx % 3;
+            const double* T = Tw + 12 * j;
+            const double* c = M->com[j];
+            o[idx] = M->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+        }
     }
 }
 
@@ -1283,6 +1360,28 @@ int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* fr
     const int blocks = (int)((total + 127) / 128);
     k_kin_char<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel);
     return (int)cudaGetLastError();
+}
+
+template <int G>
+static int launch_kin_t(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
+                        const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
+                        double* out_body_pos, void* stream) {
+    constexpr int EPW = 32 / G;
+    const int wpb = 4;
+    const size_t smem = (size_t)24 * hm.N * sizeof(double) * wpb * EPW;
+    const int epb = wpb * EPW;
+    k_kin<G><<<(E + epb - 1) / epb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot,
+                                                                        out_pose, out_vel, out_body_pos);
+    return (int)cudaGetLastError();
+}
+
+// cKinCharacter::Pose + body positions of the kin pose in one launch (used by trl_step_fused)
+int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
+                   const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
+                   double* out_body_pos, void* stream) {
+    if (hm.N <= 8) return launch_kin_t<8>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
+    if (hm.N <= 16) return launch_kin_t<16>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
+    return launch_kin_t<32>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
 }
 
 int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,
