@@ -10,6 +10,15 @@
 
 #define TRL_DEV __device__ __forceinline__
 
+// Cooperative copy of the model's integer tables into shared memory (call from every thread of the block, before
+// any early return; contains the __syncthreads()).
+TRL_DEV void stage_model_idx(ModelIdx* dst, const DevModel* __restrict__ M) {
+    const uint4* src = reinterpret_cast<const uint4*>(&M->ix);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelIdx) / 16); i += blockDim.x) d[i] = __ldg(src + i);
+    __syncthreads();
+}
+
 // ---- 3-vectors / 3x3 (row-major) ----
 TRL_DEV void cross3(const double* a, const double* b, double* o) {
     o[0] = a[1] * b[2] - a[2] * b[1];
@@ -126,11 +135,10 @@ TRL_DEV void quat_slerp_norm(const double* a, double t, const double* b, double*
 
 // ---- joint-local child->parent transform [R(9) | t(3)], cKinTree::ChildParentTrans* (anim/KinTree.cpp:1794-1866) ----
 // For the root pass world=true to get A*T(pos)*R(quat); otherwise callers treat the root frame as the origin.
-TRL_DEV void joint_local_trans(const DevModel* __restrict__ M, int j, const double* q /* joint params */, double* R,
-                               double* t) {
-    const double* A = M->attR[j];
-    const double* at = M->attT[j];
-    const int type = (M->parent[j] == -1) ? -1 : M->type[j];
+TRL_DEV void joint_local_trans(const ModelIdx* X, int j, const double* q /* joint params */,
+                               const double* A /* attach rotation, 9 */, const double* at /* attach point, 3 */,
+                               double* R, double* t) {
+    const int type = (X->parent[j] == -1) ? -1 : X->type[j];
     if (type == -1) {  // root: A * T * R
         double Rq[9];
         quat_to_mat(q[3], q[4], q[5], q[6], Rq);

@@ -16,7 +16,34 @@ enum { CK_ANG = 0,      // omega = R_j[:,axis], v = p_j x omega   (revolute z, s
        CK_ROOT_LIN = 2  // omega = 0, v = row `axis` of R(root quat) (root translation, RBDUtil.cpp:776-783)
 };
 
-// Flattened, immutable character model as the kernels read it (resident in HBM, ~7 KB).
+// Integer index tables of a model as signed bytes (every value is < 64 or -1): 848 B, staged in shared memory by
+// every kernel so the tree walks never wait on global / L2 loads (with ~200 KB of shared memory per SM carved out
+// for the per-env workspaces, L1 is too small to keep them resident).
+struct alignas(16) ModelIdx {
+    signed char parent[TRL_MAX_JOINTS];
+    signed char type[TRL_MAX_JOINTS];
+    signed char offset[TRL_MAX_JOINTS];
+    signed char size[TRL_MAX_JOINTS];
+    signed char valid_body[TRL_MAX_JOINTS];
+    signed char pd_valid[TRL_MAX_JOINTS];
+    signed char level[TRL_MAX_JOINTS];
+    signed char first_col[TRL_MAX_JOINTS];
+    signed char ncol[TRL_MAX_JOINTS];
+    signed char level_joint[TRL_MAX_JOINTS];
+    signed char slot_base[TRL_MAX_JOINTS];  // pose-feature slot of body j, cTerrainRLCharController packing (bodies 1..N-1)
+    signed char slot_ct[TRL_MAX_JOINTS];    // same for cCtController packing (bodies 0..N-1); -1 = invalid body
+    signed char level_start[TRL_MAX_JOINTS + 16];
+    signed char col_joint[TRL_MAX_DOF];
+    signed char col_kind[TRL_MAX_DOF];
+    signed char col_axis[TRL_MAX_DOF];
+    signed char col_dof[TRL_MAX_DOF];     // index into pose/vel vectors
+    signed char col_parent[TRL_MAX_DOF];  // Featherstone's lambda() expanded to dof columns, -1 at the top
+    signed char dof_col[TRL_MAX_DOF];     // dof -> live column or -1
+    signed char dof_joint[TRL_MAX_DOF];
+};
+static_assert(sizeof(ModelIdx) % 16 == 0, "ModelIdx is copied with 16-byte loads");
+
+// Flattened, immutable character model as the kernels read it (resident in HBM, ~5 KB).
 struct DevModel {
     int N;           // joints
     int n;           // dofs incl. dead slots (cKinTree::GetNumDof)
@@ -30,19 +57,7 @@ struct DevModel {
     double motion_duration;
     double cycle_delta[3];  // cKinCharacter::CalcCycleRootDelta, anim/KinCharacter.cpp:264-277
 
-    int parent[TRL_MAX_JOINTS];
-    int type[TRL_MAX_JOINTS];
-    int offset[TRL_MAX_JOINTS];
-    int size[TRL_MAX_JOINTS];
-    int valid_body[TRL_MAX_JOINTS];
-    int pd_valid[TRL_MAX_JOINTS];
-    int level[TRL_MAX_JOINTS];
-    int first_col[TRL_MAX_JOINTS];
-    int ncol[TRL_MAX_JOINTS];
-    int level_start[TRL_MAX_JOINTS + 1];
-    int level_joint[TRL_MAX_JOINTS];
-    int slot_base[TRL_MAX_JOINTS];  // pose-feature slot of body j, cTerrainRLCharController packing (bodies 1..N-1)
-    int slot_ct[TRL_MAX_JOINTS];    // same for cCtController packing (bodies 0..N-1); -1 = invalid body
+    ModelIdx ix;  // small integer tables; every kernel stages them in shared memory
     double attR[TRL_MAX_JOINTS][9];  // cKinTree::BuildAttachTrans rotation (Rz*Ry*Rx of AttachTheta), row-major
     double attT[TRL_MAX_JOINTS][3];  // attach point
     double mass[TRL_MAX_JOINTS];
@@ -51,13 +66,6 @@ struct DevModel {
     double kp[TRL_MAX_JOINTS];
     double kd[TRL_MAX_JOINTS];
 
-    int col_joint[TRL_MAX_DOF];
-    int col_kind[TRL_MAX_DOF];
-    int col_axis[TRL_MAX_DOF];
-    int col_dof[TRL_MAX_DOF];     // index into pose/vel vectors
-    int col_parent[TRL_MAX_DOF];  // Featherstone's lambda() expanded to dof columns, -1 at the top
-    int dof_col[TRL_MAX_DOF];     // dof -> live column or -1
-    int dof_joint[TRL_MAX_DOF];
 };
 
 struct trl_model {

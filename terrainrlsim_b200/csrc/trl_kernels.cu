@@ -31,6 +31,9 @@ constexpr int kWarpsPerBlock = 4;
 #define TRL_PD_MIN_BLOCKS 4
 #endif
 
+constexpr int kCst = 21;  // per-joint double constants staged per block by k_imp_pd
+__host__ __device__ inline int pd_cst_doubles(int N) { return (kCst * N + 1) & ~1; }
+
 // shared-memory workspace layout (in doubles) of k_imp_pd, per env. The PD vectors (ep, ev, kpm, kdm, kdu: 5n)
 // alias the transform arrays Tl/T0 (24N >= 5n), which are dead by the time the PD errors are formed.
 struct PdLayout {
@@ -93,8 +96,8 @@ __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
 
 // Column c of the joint subspace S in the root frame (cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828),
 // recomputed from the joint's root-frame transform wherever it is needed instead of being stored.
-TRL_DEV void subspace_col(const DevModel* __restrict__ M, const double* T0, const double* Rq, int c, double* s) {
-    const int j = M->col_joint[c], kind = M->col_kind[c], a = M->col_axis[c];
+TRL_DEV void subspace_col(const ModelIdx* X, const double* T0, const double* Rq, int c, double* s) {
+    const int j = X->col_joint[c], kind = X->col_kind[c], a = X->col_axis[c];
     const double* T = T0 + 12 * j;
     if (kind == CK_ANG) {
         s[0] = T[a]; s[1] = T[3 + a]; s[2] = T[6 + a];
@@ -111,16 +114,16 @@ TRL_DEV void subspace_col(const DevModel* __restrict__ M, const double* T0, cons
 // ------------------------------------------------------------------------------------------------
 // transforms in the root frame: Tl (local) -> T0 (root frame), level by level
 // ------------------------------------------------------------------------------------------------
-TRL_DEV void compose_levels(const DevModel* __restrict__ M, const double* Tl, double* T0, int lane, int first_level,
-                            int G = 32) {
+TRL_DEV void compose_levels(const DevModel* __restrict__ M, const ModelIdx* X, const double* Tl, double* T0, int lane,
+                            int first_level, int G = 32) {
     const int nlev = M->num_levels;
     for (int lv = first_level; lv < nlev; ++lv) {
-        const int beg = M->level_start[lv];
-        const int cnt = M->level_start[lv + 1] - beg;
+        const int beg = X->level_start[lv];
+        const int cnt = X->level_start[lv + 1] - beg;
         for (int it = lane; it < cnt * 12; it += G) {
-            const int j = M->level_joint[beg + it / 12];
+            const int j = X->level_joint[beg + it / 12];
             const int el = it % 12;
-            const int p = M->parent[j];
+            const int p = X->parent[j];
             const double* Rp = T0 + 12 * p;
             const double* L = Tl + 12 * j;
             double v;
@@ -265,6 +268,24 @@ template <int G, int NLMAX, bool SPLIT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TRL_PD_MIN_BLOCKS)
 k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
     extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
+        const int Nj = M->N;
+        for (int i = threadIdx.x; i < Nj * kCst; i += blockDim.x) {
+            const int j = i / kCst, k = i - j * kCst;
+            double v;
+            if (k < 9) v = M->attR[j][k];
+            else if (k < 12) v = M->attT[j][k - 9];
+            else if (k == 12) v = M->mass[j];
+            else if (k < 16) v = M->com[j][k - 13];
+            else if (k < 19) v = M->idiag[j][k - 16];
+            else if (k == 19) v = M->kp[j];
+            else v = M->kd[j];
+            smem[i] = v;
+        }
+    }
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     constexpr int EPW = 32 / G;  // envs per warp
     const int wlane = threadIdx.x & 31;
     const int lane = wlane % G;  // lane within the env's group
@@ -279,7 +300,8 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     const PdLayout L = pd_layout(N, n, nl, NLMAX, SPLIT);
     const PdScratch SC = pd_scratch(n, nl);
     double* sc = SPLIT ? scratch + (size_t)e * SC.stride : nullptr;
-    double* ws = smem + (size_t)(warp * EPW + sub) * L.total;
+    const double* cst = smem;  // per-joint constants (kCst doubles each), staged at kernel entry
+    double* ws = smem + pd_cst_doubles(N) + (size_t)(warp * EPW + sub) * L.total;
     double* q = ws + L.q;
     double* qd = ws + L.qd;
     double* Tl = ws + L.Tl;
@@ -302,10 +324,15 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     const int ldh = L.ldh;
     const double dt = p.dt;
 
-    // P0: stage pose / vel (coalesced); H = 0 with identity padding beyond nl
+    // P0: stage pose / vel (coalesced); H = 0 with identity padding beyond nl. The PD targets are only needed in P8:
+    // pull their cache lines towards L2 now so that the late loads do not pay a full HBM round trip.
     for (int i = lane; i < n; i += G) {
         q[i] = p.pose[(size_t)e * n + i];
         qd[i] = p.vel[(size_t)e * n + i];
+    }
+    for (int off = lane * 128; off < n * 8; off += G * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(p.tar_pose + (size_t)e * n) + off));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(p.tar_vel + (size_t)e * n) + off));
     }
     const int hrows = NLMAX > 0 ? NLMAX : nl;
     if (!SPLIT) {
@@ -325,7 +352,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         double R[9], t[3];
         if (j == 0) {
             double Rw[9], tw[3];
-            joint_local_trans(M, 0, q, Rw, tw);  // world <- root (A*T*R)
+            joint_local_trans(X, 0, q, cst, cst + 9, Rw, tw);  // world <- root (A*T*R)
             double rq[9];
             quat_to_mat(q[3], q[4], q[5], q[6], rq);
 #pragma unroll
@@ -357,7 +384,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             for (int i = 0; i < 9; ++i) T0[i] = R[i];
             T0[9] = T0[10] = T0[11] = 0.0;
         } else {
-            joint_local_trans(M, j, q + M->offset[j], R, t);
+            joint_local_trans(X, j, q + X->offset[j], cst + kCst * j, cst + kCst * j + 9, R, t);
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) Tl[12 * j + i] = R[i];
@@ -366,17 +393,17 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     __syncwarp();
 
     // P2: root-frame transforms
-    compose_levels(M, Tl, T0, lane, 1, G);
+    compose_levels(M, X, Tl, T0, lane, 1, G);
 
     // P3: s_j = S_j qd_j in the root frame (columns recomputed from T0)
     if (lane < N) {
         const int j = lane;
         double s[6] = {0, 0, 0, 0, 0, 0};
-        const int c0 = M->first_col[j], nc = M->ncol[j];
+        const int c0 = X->first_col[j], nc = X->ncol[j];
         for (int c = c0; c < c0 + nc; ++c) {
-            const double w = qd[M->col_dof[c]];
+            const double w = qd[X->col_dof[c]];
             double sc6[6];
-            subspace_col(M, T0, Rq, c, sc6);
+            subspace_col(X, T0, Rq, c, sc6);
 #pragma unroll
             for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
         }
@@ -393,12 +420,12 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 
     // P4: V_j = V_p + s_j ; a_j = a_p + V_p x s_j (motion cross product; V_j x s_j = V_p x s_j)
     for (int lv = 1; lv < M->num_levels; ++lv) {
-        const int beg = M->level_start[lv];
-        const int cnt = M->level_start[lv + 1] - beg;
+        const int beg = X->level_start[lv];
+        const int cnt = X->level_start[lv + 1] - beg;
         for (int it = lane; it < cnt * 6; it += G) {
-            const int j = M->level_joint[beg + it / 6];
+            const int j = X->level_joint[beg + it / 6];
             const int k = it % 6;
-            const int pj = M->parent[j];
+            const int pj = X->parent[j];
             const double* Vp = V + 6 * pj;
             const double* s = sj + 6 * j;
             const int i0 = k % 3, i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
@@ -419,13 +446,14 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         const int j = lane;
         double I[10];
         double f[6] = {0, 0, 0, 0, 0, 0};
-        if (M->valid_body[j]) {
+        if (X->valid_body[j]) {
             const double* T = T0 + 12 * j;
-            const double m = M->mass[j];
+            const double* cj_ = cst + kCst * j;
+            const double m = cj_[12];
             double c[3];
-            mat3_mulv(T, M->com[j], c);
+            mat3_mulv(T, cj_ + 13, c);
             c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
-            const double d0 = M->idiag[j][0], d1 = M->idiag[j][1], d2 = M->idiag[j][2];
+            const double d0 = cj_[16], d1 = cj_[17], d2 = cj_[18];
             // R diag R^T
             double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
             double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
@@ -478,16 +506,16 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 
     // P6: subtree sums, leaves -> root (joints are ordered parents-first, anim/KinTree.cpp:479-493)
     for (int j = N - 1; j >= 1; --j) {
-        for (int c = lane; c < 16; c += G) IF[16 * M->parent[j] + c] += IF[16 * j + c];
+        for (int c = lane; c < 16; c += G) IF[16 * X->parent[j] + c] += IF[16 * j + c];
         __syncwarp();
     }
 
     // P7: F_c = Ic_j S_c ; C_c = S_c . f_subtree ; H[c][c'] = F_c . S_c' along the ancestor chain
     for (int c = lane; c < nl; c += G) {
-        const int j = M->col_joint[c];
+        const int j = X->col_joint[c];
         const double* I = IF + 16 * j;
         double s[6];
-        subspace_col(M, T0, Rq, c, s);
+        subspace_col(X, T0, Rq, c, s);
         const double m = I[0];
         const double* h = I + 1;
         double hxv[3], hxw[3];
@@ -502,9 +530,9 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         Fc[5] = m * s[5] - hxw[2];
         const double* f = I + 10;
         C[c] = s[0] * f[0] + s[1] * f[1] + s[2] * f[2] + s[3] * f[3] + s[4] * f[4] + s[5] * f[5];
-        for (int a = c; a >= 0; a = M->col_parent[a]) {
+        for (int a = c; a >= 0; a = X->col_parent[a]) {
             double sa[6];
-            subspace_col(M, T0, Rq, a, sa);
+            subspace_col(X, T0, Rq, a, sa);
             const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
             if (SPLIT) {
                 if (a == c) x[c] = hv;  // diagonal stash: dt*Kd is added once the gains are known (P8)
@@ -521,10 +549,10 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     if (SPLIT && p.out_mass && env_ok) {  // rare path (GetMassMat): re-walk the chains, scatter M symmetrically
         double* om = p.out_mass + (size_t)e * n * n;
         for (int c = lane; c < nl; c += G) {
-            const int di = M->col_dof[c];
+            const int di = X->col_dof[c];
             om[di * n + di] = x[c];
-            for (int a = M->col_parent[c]; a >= 0; a = M->col_parent[a]) {
-                const int da = M->col_dof[a];
+            for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
+                const int da = X->col_dof[a];
                 const double hv = sc[c * (c + 1) / 2 + a];
                 om[di * n + da] = hv;
                 om[da * n + di] = hv;
@@ -534,14 +562,14 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     if (!SPLIT && p.out_mass && env_ok) {
         double* om = p.out_mass + (size_t)e * n * n;
         for (int idx = lane; idx < n * n; idx += G) {
-            const int ci = M->dof_col[idx / n], ck = M->dof_col[idx % n];
+            const int ci = X->dof_col[idx / n], ck = X->dof_col[idx % n];
             om[idx] = (ci >= 0 && ck >= 0) ? H[ci * ldh + ck] : 0.0;
         }
     }
     if (p.out_bias && env_ok) {
         double* ob = p.out_bias + (size_t)e * n;
         for (int i = lane; i < n; i += G) {
-            const int ci = M->dof_col[i];
+            const int ci = X->dof_col[i];
             ob[i] = (ci >= 0) ? C[ci] : 0.0;
         }
     }
@@ -549,13 +577,13 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     // P8: PD errors (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196)
     if (lane < N) {
         const int j = lane;
-        const int o = M->offset[j], sz = M->size[j];
-        const bool valid = M->pd_valid[j] != 0;
+        const int o = X->offset[j], sz = X->size[j];
+        const bool valid = X->pd_valid[j] != 0;
         const bool active = valid && (p.joint_active ? (p.joint_active[(size_t)e * N + j] != 0) : true);
         double kp = 0.0, kd = 0.0;
         if (valid) {
-            kp = p.kp ? p.kp[(size_t)e * N + j] : M->kp[j];
-            kd = p.kd ? p.kd[(size_t)e * N + j] : M->kd[j];
+            kp = p.kp ? p.kp[(size_t)e * N + j] : cst[kCst * j + 19];
+            kd = p.kd ? p.kd[(size_t)e * N + j] : cst[kCst * j + 20];
         }
         const double* tq = p.tar_pose + (size_t)e * n + o;
         const double* tqd = p.tar_vel + (size_t)e * n + o;
@@ -566,7 +594,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         }
         if (!valid) {
             for (int i = 0; i < sz; ++i) { ep[o + i] = 0.0; ev[o + i] = 0.0; }
-        } else if (M->type[j] == JT_SPHERICAL) {
+        } else if (X->type[j] == JT_SPHERICAL) {
             double dq[4], qi[4], tar[4];
             quat_diff_mul(q + o, qd + o, dq);
 #pragma unroll
@@ -596,14 +624,14 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         // hand the assembled system to k_pd_solve: packed diagonal, rhs, and tau_i = t0_i - t1_i * qdd_col(i)
         if (env_ok) {
             for (int c = lane; c < nl; c += G) {
-                const int i = M->col_dof[c];
+                const int i = X->col_dof[c];
                 sc[SC.rhs + c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
                 sc[c * (c + 1) / 2 + c] = x[c] + dt * kdu[i];
             }
             for (int i = lane; i < n; i += G) {
                 double t0 = kpm[i] * ep[i] + kdm[i] * ev[i];
                 double t1 = kdm[i] * dt;
-                if (M->dof_col[i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
+                if (X->dof_col[i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
                     const double dg = dt * kdu[i];
                     const double acc = (fabs(dg) > DBL_MIN) ? t0 / dg : 0.0;
                     t0 = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
@@ -616,7 +644,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         return;
     }
     for (int c = lane; c < nl; c += G) {
-        const int i = M->col_dof[c];
+        const int i = X->col_dof[c];
         x[c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
         H[c * ldh + c] += dt * kdu[i];
     }
@@ -628,7 +656,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     if (NLMAX > 0) {
 #pragma unroll 1
         for (int s2 = 0; s2 < EPW; ++s2) {
-            double* wss = smem + (size_t)(warp * EPW + s2) * L.total;
+            double* wss = smem + pd_cst_doubles(N) + (size_t)(warp * EPW + s2) * L.total;
             const int b2 = SPLIT ? 0 : ldlt_solve_regs<(NLMAX > 0 ? NLMAX : 1)>(wss + L.H, ldh, wss + L.x, nl, wlane);
             if (s2 == sub) bad = b2;
         }
@@ -639,7 +667,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 
     // P10: tau = Kp e_p + Kd (e_v - dt qdd)
     for (int i = lane; i < n; i += G) {
-        const int c = M->dof_col[i];
+        const int c = X->dof_col[i];
         double acc;
         if (c >= 0) {
             acc = x[c];
@@ -671,6 +699,9 @@ template <int NLMAX>
 __global__ void __launch_bounds__(128)
 k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
            int tau_accumulate, int* __restrict__ status) {
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     const int lane = threadIdx.x & 31;
     const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= E) return;
@@ -690,7 +721,7 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
     const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
-        const int c = (i < n) ? M->dof_col[i] : -1;
+        const int c = (i < n) ? X->dof_col[i] : -1;
         const double acc = __shfl_sync(0xffffffffu, xv, c < 0 ? 0 : c);
         if (i < n) {
             const double t = __ldg(sc + SC.t0 + i) - __ldg(sc + SC.t1 + i) * (c < 0 ? 0.0 : acc);
@@ -712,6 +743,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_fk(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, double* __restrict__ out_joint_world,
      double* __restrict__ out_body_pos) {
     extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int e = blockIdx.x * kWarpsPerBlock + warp;
@@ -725,14 +759,14 @@ k_fk(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, dou
     __syncwarp();
     if (lane < N) {
         double R[9], t[3];
-        joint_local_trans(M, lane, q + M->offset[lane], R, t);
+        joint_local_trans(X, lane, q + X->offset[lane], M->attR[lane], M->attT[lane], R, t);
         double* dst = (lane == 0) ? Tw : (Tl + 12 * lane);
 #pragma unroll
         for (int i = 0; i < 9; ++i) dst[i] = R[i];
         dst[9] = t[0]; dst[10] = t[1]; dst[11] = t[2];
     }
     __syncwarp();
-    compose_levels(M, Tl, Tw, lane, 1);
+    compose_levels(M, X, Tl, Tw, lane, 1);
     if (out_joint_world) {
         double* o = out_joint_world + (size_t)e * N * 12;
         for (int idx = lane; idx < N * 12; idx += 32) {
@@ -746,7 +780,7 @@ k_fk(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, dou
             const int j = idx / 3, r = idx % 3;
             const double* T = Tw + 12 * j;
             const double* c = M->com[j];
-            o[idx] = M->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+            o[idx] = X->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
         }
     }
 }
@@ -776,13 +810,14 @@ TRL_DEV void motion_index_phase(const DevModel* __restrict__ M, const double* __
 }
 
 // pose of one joint at `time` (root: with cycle offset and origin transform, anim/KinCharacter.cpp:280-315)
-TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const double* __restrict__ frames, int fs, int j, double time,
+TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const ModelIdx* X, const double* __restrict__ frames, int fs,
+                            int j, double time,
                             const double* opos, const double* orot, double* out /* size[j] */) {
     int idx;
     double ph;
     motion_index_phase(M, frames, fs, time, &idx, &ph);
     const double lerp = clampd(ph, 0.0, 1.0);
-    const int o = M->offset[j], sz = M->size[j];
+    const int o = X->offset[j], sz = X->size[j];
     const double* f0 = frames + (size_t)idx * fs + 1 + o;
     const double* f1 = frames + (size_t)(idx + 1) * fs + 1 + o;
     if (j == 0) {
@@ -807,7 +842,7 @@ TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const double* __rest
         for (int i = 0; i < 3; ++i) out[i] = rp[i] + (delta[i] + opos[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[3 + i] = rr[i];
-    } else if (M->type[j] == JT_SPHERICAL) {
+    } else if (X->type[j] == JT_SPHERICAL) {
         double qa[4], qb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + i); qb[i] = __ldg(f1 + i); }
@@ -821,6 +856,9 @@ __global__ void __launch_bounds__(128)
 k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
            const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
            double* __restrict__ out_vel) {
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     const int N = M->N, n = M->n;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)E * N) return;
@@ -833,18 +871,18 @@ k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, in
         if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
     }
     double p0[7], p1[7];
-    kin_joint_pose(M, frames, fs, j, t, opos, orot, p0);
-    const int o = M->offset[j], sz = M->size[j];
+    kin_joint_pose(M, X, frames, fs, j, t, opos, orot, p0);
+    const int o = X->offset[j], sz = X->size[j];
     for (int i = 0; i < sz; ++i) out_pose[(size_t)e * n + o + i] = p0[i];
     if (out_vel) {
         const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
-        kin_joint_pose(M, frames, fs, j, t + ddt, opos, orot, p1);
+        kin_joint_pose(M, X, frames, fs, j, t + ddt, opos, orot, p1);
         double v[7];
         if (j == 0) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
 #pragma unroll
             for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
             quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
-        } else if (M->type[j] == JT_SPHERICAL) {
+        } else if (X->type[j] == JT_SPHERICAL) {
             quat_vel_rel(p0, p1, ddt, v);
         } else {
             for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
@@ -863,6 +901,9 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
       const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
       double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
     extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     constexpr int EPW = 32 / G;
     const int wlane = threadIdx.x & 31;
     const int lane = wlane % G, sub = wlane / G;
@@ -882,17 +923,17 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
     if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
     for (int j = lane; j < N; j += G) {
         double p0[7], p1[7], v[7];
-        kin_joint_pose(M, frames, fs, j, t, opos, orot, p0);
-        const int o = M->offset[j], sz = M->size[j];
+        kin_joint_pose(M, X, frames, fs, j, t, opos, orot, p0);
+        const int o = X->offset[j], sz = X->size[j];
         if (env_ok)
             for (int i = 0; i < sz; ++i) out_pose[(size_t)e * n + o + i] = p0[i];
         if (out_vel) {
-            kin_joint_pose(M, frames, fs, j, t + ddt, opos, orot, p1);
+            kin_joint_pose(M, X, frames, fs, j, t + ddt, opos, orot, p1);
             if (j == 0) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
 #pragma unroll
                 for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
                 quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
-            } else if (M->type[j] == JT_SPHERICAL) {
+            } else if (X->type[j] == JT_SPHERICAL) {
                 quat_vel_rel(p0, p1, ddt, v);
             } else {
                 for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
@@ -902,7 +943,7 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
         }
         if (out_body_pos) {
             double R[9], tt[3];
-            joint_local_trans(M, j, p0, R, tt);
+            joint_local_trans(X, j, p0, M->attR[j], M->attT[j], R, tt);
             double* dst = (j == 0) ? Tw : (Tl + 12 * j);
 #pragma unroll
             for (int i = 0; i < 9; ++i) dst[i] = R[i];
@@ -911,14 +952,14 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
     }
     if (!out_body_pos) return;
     __syncwarp();
-    compose_levels(M, Tl, Tw, lane, 1, G);
+    compose_levels(M, X, Tl, Tw, lane, 1, G);
     if (env_ok) {
         double* o = out_body_pos + (size_t)e * N * 3;
         for (int idx = lane; idx < N * 3; idx += G) {
             const int j = idx / 3, r = idx % 3;
             const double* T = Tw + 12 * j;
             const double* c = M->com[j];
-            o[idx] = M->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+            o[idx] = X->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
         }
     }
 }
@@ -995,6 +1036,9 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
           const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
           const double* __restrict__ ground_vel, const double* __restrict__ phase,
           const unsigned char* __restrict__ flip_arr, ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = tid % kObsG;
     const int e_raw = tid / kObsG;
@@ -1070,7 +1114,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         return idx;
     };
     for (int i = first + lane; i < N; i += kObsG) {
-        const int slot = D.is_ct ? M->slot_ct[i] : M->slot_base[i];
+        const int slot = D.is_ct ? X->slot_ct[i] : X->slot_base[i];
         if (slot < 0) continue;
         const double* bp = body_pos + ((size_t)e * N + i) * 3;
         const double bx = bp[0], by = bp[1] - ground_h, bz = bp[2];
@@ -1274,9 +1318,10 @@ static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const 
     constexpr int EPW = 32 / G;
     const size_t per_warp = (size_t)pd_layout(hm.N, hm.n, hm.nl, NLMAX, SPLIT).total * sizeof(double) * EPW;
     // warps per block: maximise resident warps per SM under the 227 KB shared-memory budget (1 KB reserved per block)
+    const size_t cst_bytes = (size_t)pd_cst_doubles(hm.N) * sizeof(double);
     int wpb = 1, best = 0;
     for (int w = kWarpsPerBlock; w >= 1; w >>= 1) {
-        const size_t blk = per_warp * w + 1024;
+        const size_t blk = per_warp * w + cst_bytes + 2048;
         const int resident = (int)((227 * 1024) / blk) * w;
         if (resident > best) { best = resident; wpb = w; }
     }
@@ -1284,7 +1329,7 @@ static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const 
         static const int wpb_env = env_int("TRL_PD_WPB", 0);  // tuning hook
         if (wpb_env == 1 || wpb_env == 2 || wpb_env == 4) wpb = wpb_env;
     }
-    const size_t smem = per_warp * wpb;
+    const size_t smem = per_warp * wpb + cst_bytes;
     int rc = ensure_smem((const void*)k_imp_pd<G, NLMAX, SPLIT>, smem);
     if (rc) return rc;
     const int envs_per_block = wpb * EPW;

@@ -242,20 +242,20 @@ int trl_build_dev_model(trl_model* m) {
         }
         int size = (parent == -1) ? 7 : joint_param_size(type);  // root is always 7 (KinTree.cpp:789-795)
         if (size < 0) { trl_set_error("unsupported joint type"); return TRL_ERR_UNSUPPORTED; }
-        d.parent[j] = parent;
-        d.type[j] = type;
-        d.offset[j] = off;
-        d.size[j] = size;
+        d.ix.parent[j] = parent;
+        d.ix.type[j] = type;
+        d.ix.offset[j] = off;
+        d.ix.size[j] = size;
         off += size;
         int shape = (int)br[0];
-        d.valid_body[j] = shape < 2;  // cKinTree::IsValidBody, KinTree.cpp:390-398
-        d.pd_valid[j] = (parent != -1) && d.valid_body[j];
+        d.ix.valid_body[j] = shape < 2;  // cKinTree::IsValidBody, KinTree.cpp:390-398
+        d.ix.pd_valid[j] = (parent != -1) && d.ix.valid_body[j];
         euler_to_mat(jr + 5, d.attR[j]);
         d.attT[j][0] = jr[2]; d.attT[j][1] = jr[3]; d.attT[j][2] = jr[4];
         if (parent == -1) d.attT[j][0] = d.attT[j][1] = d.attT[j][2] = 0;  // PostProcessJointMat :1038-1040
-        d.level[j] = (parent == -1) ? 0 : d.level[parent] + 1;
+        d.ix.level[j] = (parent == -1) ? 0 : d.ix.level[parent] + 1;
         d.mass[j] = 0;
-        if (d.valid_body[j]) {
+        if (d.ix.valid_body[j]) {
             double mass = br[1];
             d.mass[j] = mass;
             d.com[j][0] = br[4]; d.com[j][1] = br[5]; d.com[j][2] = br[6];
@@ -278,8 +278,8 @@ int trl_build_dev_model(trl_model* m) {
                 d.idiag[j][2] = x;
             }
         }
-        d.kp[j] = d.pd_valid[j] ? pr[1] : 0.0;  // cImpPDController::InitGains, ImpPDController.cpp:100-121
-        d.kd[j] = d.pd_valid[j] ? pr[2] : 0.0;
+        d.kp[j] = d.ix.pd_valid[j] ? pr[1] : 0.0;  // cImpPDController::InitGains, ImpPDController.cpp:100-121
+        d.kd[j] = d.ix.pd_valid[j] ? pr[2] : 0.0;
         if (type == JT_SPHERICAL && parent != -1) d.has_spherical = 1;
     }
     d.n = off;
@@ -288,20 +288,20 @@ int trl_build_dev_model(trl_model* m) {
 
     // live dof columns
     int nl = 0;
-    for (int i = 0; i < TRL_MAX_DOF; ++i) d.dof_col[i] = -1;
+    for (int i = 0; i < TRL_MAX_DOF; ++i) d.ix.dof_col[i] = -1;
     for (int j = 0; j < N; ++j) {
-        d.first_col[j] = nl;
-        int o = d.offset[j];
+        d.ix.first_col[j] = nl;
+        int o = d.ix.offset[j];
         auto add = [&](int kind, int axis, int dof) {
-            d.col_joint[nl] = j; d.col_kind[nl] = kind; d.col_axis[nl] = axis; d.col_dof[nl] = dof;
-            d.dof_col[dof] = nl;
+            d.ix.col_joint[nl] = j; d.ix.col_kind[nl] = kind; d.ix.col_axis[nl] = axis; d.ix.col_dof[nl] = dof;
+            d.ix.dof_col[dof] = nl;
             ++nl;
         };
-        if (d.parent[j] == -1) {
+        if (d.ix.parent[j] == -1) {
             for (int k = 0; k < 3; ++k) add(CK_ROOT_LIN, k, o + k);
             for (int k = 0; k < 3; ++k) add(CK_ANG, k, o + 3 + k);
         } else {
-            switch (d.type[j]) {
+            switch (d.ix.type[j]) {
             case JT_REVOLUTE: add(CK_ANG, 2, o); break;
             case JT_PRISMATIC: add(CK_LIN, 0, o); break;
             case JT_PLANAR: add(CK_LIN, 0, o); add(CK_LIN, 1, o + 1); add(CK_ANG, 2, o + 2); break;
@@ -309,36 +309,36 @@ int trl_build_dev_model(trl_model* m) {
             default: break;
             }
         }
-        d.ncol[j] = nl - d.first_col[j];
-        for (int i = 0; i < d.size[j]; ++i) d.dof_joint[o + i] = j;
+        d.ix.ncol[j] = nl - d.ix.first_col[j];
+        for (int i = 0; i < d.ix.size[j]; ++i) d.ix.dof_joint[o + i] = j;
     }
     d.nl = nl;
     for (int c = 0; c < nl; ++c) {
-        int j = d.col_joint[c];
-        if (c > d.first_col[j]) {
-            d.col_parent[c] = c - 1;
+        int j = d.ix.col_joint[c];
+        if (c > d.ix.first_col[j]) {
+            d.ix.col_parent[c] = c - 1;
         } else {
-            int p = d.parent[j];
-            while (p != -1 && d.ncol[p] == 0) p = d.parent[p];
-            d.col_parent[c] = (p == -1) ? -1 : d.first_col[p] + d.ncol[p] - 1;
+            int p = d.ix.parent[j];
+            while (p != -1 && d.ix.ncol[p] == 0) p = d.ix.parent[p];
+            d.ix.col_parent[c] = (p == -1) ? -1 : d.ix.first_col[p] + d.ix.ncol[p] - 1;
         }
     }
     // levels
     int max_level = 0;
-    for (int j = 0; j < N; ++j) max_level = std::max(max_level, d.level[j]);
+    for (int j = 0; j < N; ++j) max_level = std::max(max_level, (int)d.ix.level[j]);
     d.num_levels = max_level + 1;
     int pos = 0;
     for (int l = 0; l <= max_level; ++l) {
-        d.level_start[l] = pos;
+        d.ix.level_start[l] = pos;
         for (int j = 0; j < N; ++j)
-            if (d.level[j] == l) d.level_joint[pos++] = j;
+            if (d.ix.level[j] == l) d.ix.level_joint[pos++] = j;
     }
-    d.level_start[max_level + 1] = pos;
+    d.ix.level_start[max_level + 1] = pos;
     {
         int sb = 0, sc = 0;
         for (int j = 0; j < N; ++j) {
-            d.slot_base[j] = (j >= 1 && d.valid_body[j]) ? sb++ : -1;
-            d.slot_ct[j] = d.valid_body[j] ? sc++ : -1;
+            d.ix.slot_base[j] = (j >= 1 && d.ix.valid_body[j]) ? sb++ : -1;
+            d.ix.slot_ct[j] = d.ix.valid_body[j] ? sc++ : -1;
         }
     }
 
