@@ -55,7 +55,7 @@ struct trl_batch {
     // fork/join plumbing of trl_step_fused: the three independent kernel chains of a step (stable PD | kin-char + FK |
     // observation) run concurrently on the main stream and two side streams (captured as parallel graph branches)
     cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_pv = nullptr;
     int overlap = 1;
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
@@ -73,12 +73,12 @@ struct trl_batch {
     std::vector<DevBuf> pool;
     size_t pool_next = 0;
 
-    void* stage_in(const void* host, size_t bytes) {
+    void* stage_in(const void* host, size_t bytes, cudaStream_t st = nullptr) {
         if (!host) return nullptr;
         if (pool_next >= pool.size()) pool.emplace_back();
         DevBuf& b = pool[pool_next++];
         if (!b.reserve(bytes)) return nullptr;
-        if (!cuda_ok(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, stream), "H2D")) return nullptr;
+        if (!cuda_ok(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, st ? st : stream), "H2D")) return nullptr;
         return b.p;
     }
     void* stage_out(size_t bytes) {
@@ -106,24 +106,25 @@ struct Guard {  // selects the batch's device for the duration of a call
 
 // Resolves an input array according to the pointer mode. Returns false on error.
 template <typename T>
-bool in_ptr(trl_batch* b, const T* user, size_t count, const T** out) {
+bool in_ptr(trl_batch* b, const T* user, size_t count, const T** out, cudaStream_t st = nullptr) {
     if (!user || count == 0) { *out = nullptr; return true; }
     if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
-    *out = static_cast<const T*>(b->stage_in(user, count * sizeof(T)));
+    *out = static_cast<const T*>(b->stage_in(user, count * sizeof(T), st));
     return *out != nullptr;
 }
 
-// Output array: device pointer to write to (+ remembers the host destination for the copy back).
-struct OutCopy { void* host; void* dev; size_t bytes; };
+// Output array: device pointer to write to (+ remembers the host destination and the stream for the copy back).
+struct OutCopy { void* host; void* dev; size_t bytes; cudaStream_t st; };
 
 template <typename T>
-bool out_ptr(trl_batch* b, T* user, size_t count, T** out, std::vector<OutCopy>& copies, bool preload = false) {
+bool out_ptr(trl_batch* b, T* user, size_t count, T** out, std::vector<OutCopy>& copies, bool preload = false,
+             cudaStream_t st = nullptr) {
     if (!user || count == 0) { *out = nullptr; return true; }
     if (b->ptr_mode == TRL_PTR_DEVICE) { *out = user; return true; }
-    void* d = preload ? b->stage_in(user, count * sizeof(T)) : b->stage_out(count * sizeof(T));
+    void* d = preload ? b->stage_in(user, count * sizeof(T), st) : b->stage_out(count * sizeof(T));
     if (!d) return false;
     *out = static_cast<T*>(d);
-    copies.push_back({user, d, count * sizeof(T)});
+    copies.push_back({user, d, count * sizeof(T), st});
     return true;
 }
 
@@ -134,7 +135,7 @@ int finish(trl_batch* b, std::vector<OutCopy>& copies, int launch_rc) {
     }
     if (b->ptr_mode == TRL_PTR_HOST) {
         for (auto& c : copies)
-            if (!cuda_ok(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, b->stream), "D2H")) return TRL_ERR_CUDA;
+            if (!cuda_ok(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, c.st ? c.st : b->stream), "D2H")) return TRL_ERR_CUDA;
         if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return TRL_ERR_CUDA;
     }
     return TRL_OK;
@@ -175,6 +176,7 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     }
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
         const char* ov = getenv("TRL_STEP_OVERLAP");  // tuning hook: 0 serialises the chains on one stream
         if (ov) b->overlap = atoi(ov) != 0;
@@ -239,6 +241,7 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
     }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_pv) cudaEventDestroy(b->ev_pv);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
@@ -457,55 +460,82 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (!b || !a || !a->pose || !a->vel) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);
     const size_t E = b->E, n = b->model->n, N = b->model->N;
+    const bool want_pd = a->out_tau != nullptr, want_kin = a->out_kin_pose != nullptr, want_obs = a->out_state != nullptr;
+    if (want_pd && (!a->tar_pose || !a->tar_vel)) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
+    if (want_kin && (b->model->num_frames < 2 || !a->kin_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
+    if (want_obs && (!a->body_pos || !a->body_vel)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
+    if (want_obs && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
     b->pool_next = 0;
     std::vector<OutCopy> copies;
     StepPtrs p{};
     p.dt = a->dt;
     p.tau_accumulate = 0;
     p.status = b->d_status;
-    const double *d_time, *d_op, *d_or, *d_bp, *d_bv, *d_ph;
-    const unsigned char* d_fl;
-    double *d_kp, *d_kv, *d_kbp, *d_state;
-    if (!in_ptr(b, a->pose, E * n, &p.pose) || !in_ptr(b, a->vel, E * n, &p.vel) ||
-        !in_ptr(b, a->tar_pose, E * n, &p.tar_pose) || !in_ptr(b, a->tar_vel, E * n, &p.tar_vel) ||
-        !in_ptr(b, a->joint_active, E * N, &p.joint_active) || !in_ptr(b, a->kin_time, E, &d_time) ||
-        !in_ptr(b, a->origin_pos, E * 3, &d_op) || !in_ptr(b, a->origin_rot, E * 4, &d_or) ||
-        !in_ptr(b, a->body_pos, E * N * 3, &d_bp) || !in_ptr(b, a->body_vel, E * N * 3, &d_bv) ||
-        !in_ptr(b, a->phase, E, &d_ph) || !in_ptr(b, a->flip, E, &d_fl) ||
-        !out_ptr(b, a->out_tau, E * n, &p.tau, copies) || !out_ptr(b, a->out_kin_pose, E * n, &d_kp, copies) ||
-        !out_ptr(b, a->out_kin_vel, E * n, &d_kv, copies) || !out_ptr(b, a->out_kin_body_pos, E * N * 3, &d_kbp, copies) ||
-        !out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies))
-        return TRL_ERR_CUDA;
-    int rc = 0;
-    if (p.tau && (!p.tar_pose || !p.tar_vel)) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
-    if (d_kp && (b->model->num_frames < 2 || !d_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
-    if (d_state && (!d_bp || !d_bv)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
-    if (d_state && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
+
     // Three independent chains: (A) stable PD on the main stream, (B) kin-char pose + FK, (C) observation. With
-    // overlap on, B and C fork onto side streams after the inputs are staged and join before the outputs are read.
-    const bool fork = b->overlap && ((p.tau ? 1 : 0) + (d_kp ? 1 : 0) + (d_state ? 1 : 0)) > 1;
+    // overlap on, B and C fork onto side streams and join before returning. In HOST pointer mode every chain also
+    // stages its own inputs and copies its own outputs back on its stream, so H2D, kernels and D2H of different
+    // chains overlap (the observation chain, whose [E][F] state is the largest transfer, goes first).
+    const bool fork = b->overlap && ((want_pd ? 1 : 0) + (want_kin ? 1 : 0) + (want_obs ? 1 : 0)) > 1;
     cudaStream_t sA = b->stream, sB = b->stream, sC = b->stream;
     if (fork) {
         if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
-        if (d_kp && p.tau) { sB = b->side[0]; cudaStreamWaitEvent(sB, b->ev_fork, 0); }
-        if (d_state && (p.tau || d_kp)) { sC = b->side[1]; cudaStreamWaitEvent(sC, b->ev_fork, 0); }
+        if (want_kin && (want_pd || want_obs)) { sB = b->side[0]; cudaStreamWaitEvent(sB, b->ev_fork, 0); }
+        if (want_obs && want_pd) { sC = b->side[1]; cudaStreamWaitEvent(sC, b->ev_fork, 0); }
     }
-    if (p.tau) {
+    const double *d_time = nullptr, *d_op = nullptr, *d_or = nullptr, *d_bp = nullptr, *d_bv = nullptr, *d_ph = nullptr;
+    const unsigned char* d_fl = nullptr;
+    double *d_kp = nullptr, *d_kv = nullptr, *d_kbp = nullptr, *d_state = nullptr;
+    bool ok = true;
+    // pose / vel are shared by chains A and C: stage them on C's stream (C starts first), A waits for them
+    const cudaStream_t s_pv = want_obs ? sC : sA;
+    ok = ok && in_ptr(b, a->pose, E * n, &p.pose, s_pv) && in_ptr(b, a->vel, E * n, &p.vel, s_pv);
+    if (ok && fork && s_pv != sA && b->ptr_mode == TRL_PTR_HOST) {
+        cudaEventRecord(b->ev_pv, s_pv);
+        cudaStreamWaitEvent(sA, b->ev_pv, 0);
+    }
+    if (want_obs)
+        ok = ok && in_ptr(b, a->body_pos, E * N * 3, &d_bp, sC) && in_ptr(b, a->body_vel, E * N * 3, &d_bv, sC) &&
+             in_ptr(b, a->phase, E, &d_ph, sC) && in_ptr(b, a->flip, E, &d_fl, sC) &&
+             out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies, false, sC);
+    if (want_kin)
+        ok = ok && in_ptr(b, a->kin_time, E, &d_time, sB) && in_ptr(b, a->origin_pos, E * 3, &d_op, sB) &&
+             in_ptr(b, a->origin_rot, E * 4, &d_or, sB) && out_ptr(b, a->out_kin_pose, E * n, &d_kp, copies, false, sB) &&
+             out_ptr(b, a->out_kin_vel, E * n, &d_kv, copies, false, sB) &&
+             out_ptr(b, a->out_kin_body_pos, E * N * 3, &d_kbp, copies, false, sB);
+    if (want_pd)
+        ok = ok && in_ptr(b, a->tar_pose, E * n, &p.tar_pose, sA) && in_ptr(b, a->tar_vel, E * n, &p.tar_vel, sA) &&
+             in_ptr(b, a->joint_active, E * N, &p.joint_active, sA) && out_ptr(b, a->out_tau, E * n, &p.tau, copies, false, sA);
+    int rc = ok ? 0 : (int)cudaErrorMemoryAllocation;
+    auto launch_obs = [&]() {
+        if (rc || !want_obs) return;
+        rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC);
+        b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+    };
+    auto launch_kin = [&]() {
+        if (rc || !want_kin) return;
+        rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, d_kbp, sB);
+        b->launches += 1;
+    };
+    auto launch_pd = [&]() {
+        if (rc || !want_pd) return;
         if (a->dt > 0) {
             rc = trl_launch_imp_pd(b->d_model, b->model->dev, b->E, p, b->d_pd_scratch, sA);
             if (rc > 0) { b->launches += rc; rc = 0; } else { rc = -rc; }
         } else {
             cudaMemsetAsync(p.tau, 0, sizeof(double) * E * n, sA);
         }
+    };
+    if (b->ptr_mode == TRL_PTR_HOST) {  // largest D2H (the state) first
+        launch_obs(); launch_kin(); launch_pd();
+    } else {                            // longest chain (stable PD) first
+        launch_pd(); launch_obs(); launch_kin();
     }
-    if (!rc && d_kp) {
-        rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, d_kbp, sB);
-        b->launches += 1;
-    }
-    if (!rc && d_state) {
-        rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
-                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC);
-        b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+    if (!rc && b->ptr_mode == TRL_PTR_HOST) {  // copy every chain's outputs back on its own stream
+        for (auto& c : copies)
+            if (!cuda_ok(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, c.st ? c.st : b->stream), "D2H")) rc = (int)cudaErrorUnknown;
+        copies.clear();
     }
     if (fork) {  // join (also on error, so the streams stay consistent / a capture stays closed)
         if (sB != b->stream) { cudaEventRecord(b->ev_join[0], sB); cudaStreamWaitEvent(b->stream, b->ev_join[0], 0); }

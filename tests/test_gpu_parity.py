@@ -304,3 +304,40 @@ def test_full_size_properties(trl, oracle, name, E):
     assert_close(out1["tau"][sub], ref["tau"], "full-size tau")
     assert_close(out1["state"][sub], ref["state"], "full-size state")
     assert_close(out1["kin_pose"][sub], ref["kin_pose"], "full-size kin pose")
+
+
+@pytest.mark.parametrize("name", ["biped3d", "dog", "biped2d"])
+def test_batched_sim_adapter(trl, oracle, name):
+    """cSimAdapter-shaped front end: shapes, a few frames with the kinematic stand-in world, and getState() parity."""
+    from terrainrlsim_b200.sim_adapter import BatchedSimAdapter
+    E = 48
+    sim = BatchedSimAdapter(name, E)
+    sim.setRandomSeed(3)
+    sim.init()
+    om = oracle.Model(name)
+    cfg = oracle_cfg(oracle, name)
+    assert sim.getActionSpaceSize() == om.n - 7
+    assert sim.getObservationSpaceSize() == oracle.poli_state_size(om, cfg)
+    rng = np.random.default_rng(1)
+    for frame in range(2):
+        if sim.needUpdatedAction():
+            pose, _, _, _ = sim.world.state()
+            sim.updateAction(pose[:, 7:] + 0.05 * rng.normal(size=(E, om.n - 7)))
+        sim.update()
+        assert np.all(np.isfinite(sim.tau)) and np.all(sim.tau[:, :7] == 0)
+        assert np.all(sim.batch.status() == 0)
+    ob = sim.getState()
+    assert ob.shape == (E, sim.getObservationSpaceSize())
+    pose, vel, body_pos, body_vel = sim.world.state()
+    kind, fields = synth.make_grounds(sim._terrain_meta, min(E, 64), seed=0xB200 + 3)
+    grounds = oracle_grounds(oracle, kind, fields)
+    phase = (sim._frame * (1.0 / 30)) % 1.0
+    for e in range(E):
+        ref = oracle.build_poli_state(om, grounds[e % len(grounds)], cfg, pose[e], vel[e], body_pos[e], body_vel[e],
+                                      phase=phase)
+        assert rel_err(ob[e], ref) <= 1e-9
+    # the torque of the last substep equals the oracle's stable PD on the world's state before that substep
+    assert sim.agentHasFallen().shape == (E,)
+    with pytest.raises(NotImplementedError):
+        sim.calcReward()
+    sim.finish()

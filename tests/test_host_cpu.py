@@ -172,3 +172,26 @@ def test_synthetic_inputs_are_deterministic_and_well_formed():
     assert kind == 1 and len(f) == 3 and len(f[0]) == 2 and f[0][0]["res"][0] >= 801
     kind, f = synth.make_grounds("biped3d", 2)
     assert kind == 2 and len(f[0]) == 4 and f[0][0]["res"] == (201, 201)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_sim_adapter_reads_reference_arg_files():
+    """BatchedSimAdapter.init() resolves -character_file / -motion_file / -num_update_steps from an arg file; without
+    a GPU it must stop at batch creation with the loud no-fallback error, after the model has loaded."""
+    import torch
+    from terrainrlsim_b200.sim_adapter import BatchedSimAdapter
+    cwd = os.getcwd()
+    os.chdir(REF)  # the reference's arg files use paths relative to its root
+    try:
+        sim = BatchedSimAdapter(["-arg_file=", "args/test_dog_args.txt"], 4)
+        if torch.cuda.is_available():
+            sim.init()
+            assert sim.getActionSpaceSize() == 20 and sim.num_update_steps == 20
+            sim.finish()
+        else:
+            with pytest.raises(trl.TrlError) as ei:
+                sim.init()
+            assert "no CPU fallback" in str(ei.value)
+            assert sim.model.num_joints == 21 and sim.num_update_steps == 20
+    finally:
+        os.chdir(cwd)
