@@ -696,7 +696,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 // from the scratch straight into the register-resident LDL^T (lane <-> column), solves, forms tau.
 // ------------------------------------------------------------------------------------------------
 template <int NLMAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
            int tau_accumulate, int* __restrict__ status) {
     __shared__ ModelIdx s_ix;
@@ -709,14 +709,20 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
     const PdScratch SC = pd_scratch(n, nl);
     const double* sc = scratch + (size_t)e * SC.stride;
     double a[NLMAX];
-    const int tl = lane * (lane + 1) / 2;
+    // column `lane` of the packed lower triangle: entry (i, lane) lives at tri(max) + min. Addresses are formed for a
+    // clamped lane so every load is unconditional; lanes / rows beyond nl are replaced by identity padding afterwards.
+    const bool live = lane < nl;
+    const int lc = live ? lane : 0;
+    const double* colp = sc + lc * (lc + 1) / 2;  // &P[lc][0]: entries (lc, i) for i <= lc
 #pragma unroll
     for (int i = 0; i < NLMAX; ++i) {
-        double v = (i == lane) ? 1.0 : 0.0;  // identity padding
-        if (lane < nl && i < nl) v = __ldg(sc + ((lane <= i) ? (i * (i + 1) / 2 + lane) : (tl + i)));
-        a[i] = v;
+        const double* rowp = sc + i * (i + 1) / 2 + lc;  // &P[i][lc]: valid when lc <= i
+        double v = 0.0;
+        if (i < nl) v = __ldg((lc <= i) ? rowp : (colp + i));
+        a[i] = live ? v : ((i == lane) ? 1.0 : 0.0);
+        if (live && i >= nl) a[i] = 0.0;
     }
-    const double b = (lane < nl) ? __ldg(sc + SC.rhs + lane) : 0.0;
+    const double b = live ? __ldg(sc + SC.rhs + lane) : 0.0;
     int bad = 0;
     const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
     for (int i0 = 0; i0 < n; i0 += 32) {
