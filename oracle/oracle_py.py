@@ -66,6 +66,7 @@ def lib():
         _lib = C.CDLL(build_lib())
         _lib.trlo_sample_height.restype = C.c_double
         _lib.trlo_calc_heading.restype = C.c_double
+        _lib.trlo_imitate_reward.restype = C.c_double
     return _lib
 
 
@@ -316,6 +317,21 @@ def build_poli_state(model, ground, cfg, pose, vel, body_pos, body_vel, body_qua
                                 _d(pose), _d(vel), _d(body_pos), _d(body_vel), _d(body_quat), _d(body_angvel),
                                 _d(ground_vel), C.c_double(phase), C.c_int(flip), _d(out))
     return out
+
+
+def calc_com(model, pose, vel):
+    pose, vel = _c(pose), _c(vel)
+    com, cv = np.zeros(3), np.zeros(3)
+    lib().trlo_calc_com(model.ref, _d(pose), _d(vel), _d(com), _d(cv))
+    return com, cv
+
+
+def imitate_reward(model, ground, pose0, vel0, pose1, vel1, body_vel, fallen=0):
+    pose0, vel0, pose1, vel1, body_vel = _c(pose0), _c(vel0), _c(pose1), _c(vel1), _c(body_vel)
+    terms = np.zeros(5)
+    r = lib().trlo_imitate_reward(model.ref, C.byref(ground.c) if ground is not None else None, _d(pose0), _d(vel0),
+                                  _d(pose1), _d(vel1), _d(body_vel), C.c_int(int(fallen)), _d(terms))
+    return r, terms
 
 
 def step_range(model, cfg, arrays, grounds, dt, env_begin=0, env_end=None, env_to_ground=None):

@@ -1544,6 +1544,219 @@ void trlo_build_poli_state(const trlo_model* m, const trlo_ground* g, const trlo
 }
 
 /* ------------------------------------------------------------------------------------------
+ * imitation reward: cScenarioExpImitate::CalcReward (scenarios/ScenarioExpImitate.cpp:13-159) with
+ * cKinTree::NormalizePoseHeading / CalcPoseErr / CalcVelErr (anim/KinTree.cpp:1319-1426,1647-1672),
+ * cRBDUtil::CalcCoM / CalcCoMVel (pose-only "hack" overload, sim/RBDUtil.cpp:499-505,557-598),
+ * cRBDUtil::BuildEndEffectorJacobian (:209-233), cSimCharacter::CalcCOMVel (sim/SimCharacter.cpp:359-377)
+ * ---------------------------------------------------------------------------------------- */
+static double quat_theta(quat dq) /* cMathUtil::QuatTheta, util/MathUtil.cpp:468-477 */
+{
+    if (fabs(dq.w) > 1) dq = quat_normalize(dq);
+    return 2 * acos(dq.w);
+}
+
+static sptrans build_trans_r(const double r[3]) /* cSpAlg::BuildTrans(r): identity rotation */
+{
+    sptrans X = identity_trans();
+    X.r[0] = r[0]; X.r[1] = r[1]; X.r[2] = r[2];
+    return X;
+}
+
+static spvec apply_inv_trans_m(const sptrans* X, const spvec* sv) /* SpAlg.cpp:285-297 */
+{
+    spvec out;
+    double eto[3], etv[3], c[3];
+    mat3T_mulv(X->E, sv->v, eto);
+    mat3T_mulv(X->E, sv->v + 3, etv);
+    cross3(X->r, eto, c);
+    for (int i = 0; i < 3; ++i) { out.v[i] = eto[i]; out.v[3 + i] = etv[i] + c[i]; }
+    return out;
+}
+
+/* cRBDUtil::CalcWorldVel(joint_mat, pose, vel, joint_id) = BuildEndEffectorJacobian(...) * vel (RBDUtil.cpp:209-233,474-480) */
+static spvec calc_world_vel(const trlo_model* m, const double* pose, const double* vel, int joint_id)
+{
+    int n = m->num_dof;
+    static const spvec zero_sv;
+    spvec J[TRLO_MAX_DOF];
+    for (int i = 0; i < n; ++i) J[i] = zero_sv;
+    rbd_cache c; /* only the subspace columns are used */
+    for (int j = 0; j < m->num_joints; ++j) build_joint_subspace(m, pose, j, &c);
+    int cur = joint_id;
+    sptrans cur_trans = identity_trans();
+    while (cur != -1) {
+        int off = trlo_param_offset(m, cur), size = trlo_param_size(m, cur);
+        for (int k = 0; k < size; ++k) {
+            spvec col;
+            for (int r = 0; r < 6; ++r) col.v[r] = c.S[r][off + k];
+            J[off + k] = apply_trans_m(&cur_trans, &col);
+        }
+        /* BuildParentChildTransform = InvTrans(MatToTrans(ChildParentTrans)) (RBDUtil.cpp:712-724) */
+        mat4 cp = child_parent_trans(m, pose, cur);
+        sptrans cpt = mat_to_trans(&cp);
+        sptrans pc = inv_trans(&cpt);
+        cur_trans = comp_trans(&cur_trans, &pc);
+        cur = trlo_parent(m, cur);
+    }
+    spvec sv = zero_sv;
+    for (int i = 0; i < n; ++i) {
+        spvec col = apply_inv_trans_m(&cur_trans, &J[i]);
+        for (int r = 0; r < 6; ++r) {
+            if (i == 0) sv.v[r] = col.v[r] * vel[0];
+            else sv.v[r] += col.v[r] * vel[i];
+        }
+    }
+    return sv;
+}
+
+/* cRBDUtil::CalcCoM(joint_mat, body_defs, pose, vel, com, com_vel), RBDUtil.cpp:557-598 */
+static void calc_com(const trlo_model* m, const double* pose, const double* vel, double com[3], double com_vel[3])
+{
+    double total = 0;
+    for (int i = 0; i < 3; ++i) { com[i] = 0; com_vel[i] = 0; }
+    for (int j = 0; j < m->num_joints; ++j) {
+        if (!trlo_valid_body(m, j)) continue;
+        mat4 jw = joint_world_trans(m, pose, j);
+        mat4 bj = body_joint_trans(m, j);
+        mat4 bw = mat4_mul(&jw, &bj);
+        vec4 lc = { { 0, 0, 0, 1 } };
+        vec4 wc = mat4_mulv(&bw, &lc);
+        double wcom[3] = { wc.v[0], wc.v[1], wc.v[2] };
+        sptrans ct = build_trans_r(wcom);
+        spvec sv = calc_world_vel(m, pose, vel, j);
+        sv = apply_trans_m(&ct, &sv);
+        double mass = brow(m, j)[BD_MASS];
+        for (int i = 0; i < 3; ++i) { com[i] += mass * wcom[i]; com_vel[i] += mass * sv.v[3 + i]; }
+        total += mass;
+    }
+    for (int i = 0; i < 3; ++i) { com[i] /= total; com_vel[i] /= total; }
+}
+
+void trlo_calc_com(const trlo_model* m, const double* pose, const double* vel, double com[3], double com_vel[3])
+{
+    calc_com(m, pose, vel, com, com_vel);
+}
+
+/* cKinTree::NormalizePoseHeading(joint_mat, pose, vel), KinTree.cpp:1647-1672 */
+static void normalize_pose_heading(double* pose, double* vel)
+{
+    double heading = trlo_calc_heading(pose);
+    const double yaxis[3] = { 0, 1, 0 };
+    quat hq = axis_angle_to_quat(yaxis, -heading);
+    quat rr = quat_mul(hq, pose_quat(pose + 3));
+    pose[0] = 0; pose[2] = 0;
+    pose[3] = rr.w; pose[4] = rr.x; pose[5] = rr.y; pose[6] = rr.z;
+    double rv[3], ra[3];
+    quat_rot_vec(hq, vel, rv);
+    quat_rot_vec(hq, vel + 3, ra);
+    for (int i = 0; i < 3; ++i) vel[i] = rv[i];
+    vel[3] = ra[0]; vel[4] = ra[1]; vel[5] = ra[2]; vel[6] = 0; /* SetRootAngVel writes the 4-segment of a w=0 vector */
+}
+
+double trlo_imitate_reward(const trlo_model* m, const trlo_ground* g, const double* pose0_in, const double* vel0_in,
+                           const double* pose1_in, const double* vel1_in, const double* body_vel, int fallen,
+                           double* out_terms /* [5] pose, vel, end_eff, root, com errors or NULL */)
+{
+    int N = m->num_joints, n = m->num_dof;
+    double pose_w = 0.5, vel_w = 0.05, end_eff_w = 0.15, root_w = 0.1, com_w = 0.2;
+    double total_w = pose_w + vel_w + end_eff_w + root_w + com_w;
+    pose_w /= total_w; vel_w /= total_w; end_eff_w /= total_w; root_w /= total_w; com_w /= total_w;
+    const double pose_scale = 2, vel_scale = 0.005, end_eff_scale = 40, root_scale = 10, com_scale = 10, err_scale = 1;
+    if (out_terms) for (int i = 0; i < 5; ++i) out_terms[i] = 0;
+    if (fallen) return 0;
+
+    double pose0[TRLO_MAX_DOF], vel0[TRLO_MAX_DOF], pose1[TRLO_MAX_DOF], vel1[TRLO_MAX_DOF];
+    memcpy(pose0, pose0_in, sizeof(double) * (size_t)n); memcpy(vel0, vel0_in, sizeof(double) * (size_t)n);
+    memcpy(pose1, pose1_in, sizeof(double) * (size_t)n); memcpy(vel1, vel1_in, sizeof(double) * (size_t)n);
+    mat4 origin_trans = build_origin_trans(pose0_in);
+
+    /* cSimCharacter::CalcCOMVel: mass-weighted body velocities */
+    double cv0w[3] = { 0, 0, 0 }, tm = 0;
+    for (int j = 0; j < N; ++j) {
+        if (!trlo_valid_body(m, j)) continue;
+        double mass = brow(m, j)[BD_MASS];
+        for (int i = 0; i < 3; ++i) cv0w[i] += mass * body_vel[3 * j + i];
+        tm += mass;
+    }
+    for (int i = 0; i < 3; ++i) cv0w[i] /= tm;
+    double tmp_com[3], cv1w[3];
+    calc_com(m, pose1, vel1, tmp_com, cv1w); /* cRBDUtil::CalcCoMVel(joint_mat, body_defs, pose1, vel1) */
+
+    normalize_pose_heading(pose0, vel0);
+    normalize_pose_heading(pose1, vel1);
+    double com0[3], com1[3], cvdummy[3];
+    calc_com(m, pose0, vel0, com0, cvdummy);
+    calc_com(m, pose1, vel1, com1, cvdummy);
+
+    /* joint weights: DiffWeight normalised by their 1-norm (ScenarioExpImitate.cpp:232-244) */
+    double wsum = 0;
+    for (int j = 0; j < N; ++j) wsum += fabs(jrow(m, j)[17]);
+    double pose_err = 0, vel_err = 0, end_eff_err = 0, root_err = 0, com_err = 0;
+    int num_end_effs = 0;
+    {
+        double w = jrow(m, 0)[17] / wsum;
+        quat d = quat_mul(pose_quat(pose1 + 3), quat_conj(pose_quat(pose0 + 3))); /* QuatDiff(q0,q1) = q1 * conj(q0) */
+        double th = quat_theta(d);
+        pose_err += w * (th * th);
+        double s = 0;
+        for (int i = 0; i < 4; ++i) { double dv = vel1[3 + i] - vel0[3 + i]; s += dv * dv; }
+        vel_err += w * s;
+    }
+    for (int j = 1; j < N; ++j) {
+        double w = jrow(m, j)[17] / wsum;
+        int off = trlo_param_offset(m, j), size = trlo_param_size(m, j);
+        double cpe = 0, cve = 0;
+        if (trlo_joint_type(m, j) == TRLO_JOINT_SPHERICAL) {
+            quat d = quat_mul(pose_quat(pose1 + off), quat_conj(pose_quat(pose0 + off)));
+            double th = quat_theta(d);
+            cpe = th * th;
+        } else {
+            for (int i = 0; i < size; ++i) { double dv = pose1[off + i] - pose0[off + i]; cpe += dv * dv; }
+        }
+        for (int i = 0; i < size; ++i) { double dv = vel1[off + i] - vel0[off + i]; cve += dv * dv; }
+        pose_err += w * cpe;
+        vel_err += w * cve;
+        if (jrow(m, j)[16] != 0) { /* IsEndEffector */
+            mat4 jw0 = joint_world_trans(m, pose0_in, j); /* mChar->CalcJointPos(j): world position in the sim pose */
+            double p0w[3] = { jw0.m[0][3], jw0.m[1][3], jw0.m[2][3] };
+            int v;
+            double gh0 = (g && g->kind != TRLO_GROUND_NONE) ? trlo_sample_height(g, p0w, &v, 0) : 0.0;
+            vec4 p0 = { { p0w[0], p0w[1], p0w[2], 1 } };
+            p0 = mat4_mulv(&origin_trans, &p0);
+            mat4 jw1 = joint_world_trans(m, pose1, j);
+            double p1[3] = { jw1.m[0][3], jw1.m[1][3], jw1.m[2][3] };
+            double r0[3] = { p0.v[0] - com0[0], p0.v[1] - gh0, p0.v[2] - com0[2] };
+            double r1[3] = { p1[0] - com1[0], p1[1] - 0.0, p1[2] - com1[2] };
+            double e2 = 0;
+            for (int i = 0; i < 3; ++i) { double dv = r1[i] - r0[i]; e2 += dv * dv; }
+            end_eff_err += e2;
+            ++num_end_effs;
+        }
+    }
+    if (num_end_effs > 0) end_eff_err /= num_end_effs;
+    {
+        int v;
+        double rgh0 = (g && g->kind != TRLO_GROUND_NONE) ? trlo_sample_height(g, pose0_in, &v, 0) : 0.0;
+        double h0 = pose0[1] - rgh0, h1 = pose1[1] - 0.0;
+        double dv2 = 0;
+        for (int i = 0; i < 3; ++i) { double dv = vel1[i] - vel0[i]; dv2 += dv * dv; }
+        root_err = (h1 - h0) * (h1 - h0) + 0 * 0.01 * dv2;
+    }
+    {
+        double s = 0;
+        for (int i = 0; i < 3; ++i) { double dv = cv1w[i] - cv0w[i]; s += dv * dv; }
+        com_err = 0.1 * s;
+    }
+    if (out_terms) { out_terms[0] = pose_err; out_terms[1] = vel_err; out_terms[2] = end_eff_err; out_terms[3] = root_err; out_terms[4] = com_err; }
+    double pose_reward = exp(-err_scale * pose_scale * pose_err);
+    double vel_reward = exp(-err_scale * vel_scale * vel_err);
+    double end_eff_reward = exp(-err_scale * end_eff_scale * end_eff_err);
+    double root_reward = exp(-err_scale * root_scale * root_err);
+    double com_reward = exp(-err_scale * com_scale * com_err);
+    return pose_w * pose_reward + vel_w * vel_reward + end_eff_w * end_eff_reward + root_w * root_reward + com_w * com_reward;
+}
+
+/* ------------------------------------------------------------------------------------------
  * batched driver: one env-step = stable-PD torque + kin-char pose/vel + FK + terrain + pack
  * 
  * ---------------------------------------------------------------------------------------- */

@@ -139,6 +139,15 @@ void trlo_build_poli_state(const trlo_model* m, const trlo_ground* g, const trlo
                            const double* body_quat, const double* body_angvel, const double* ground_vel,
                            double phase, int flip, double* out_state);
 
+/* ---- imitation reward (scenarios/ScenarioExpImitate.cpp:13-159); pose0/vel0 = simulated character, pose1/vel1 =
+ * kinematic reference, body_vel [N][3] = body linear velocities (for cSimCharacter::CalcCOMVel); end-effector world
+ * positions of the simulated character are the FK of pose0. out_terms [5] (pose, vel, end-eff, root, com errors). ---- */
+/* cRBDUtil::CalcCoM(joint_mat, body_defs, pose, vel, com, com_vel), sim/RBDUtil.cpp:557-598 */
+void trlo_calc_com(const trlo_model* m, const double* pose, const double* vel, double com[3], double com_vel[3]);
+double trlo_imitate_reward(const trlo_model* m, const trlo_ground* g, const double* pose0, const double* vel0,
+                           const double* pose1, const double* vel1, const double* body_vel, int fallen,
+                           double* out_terms);
+
 /* ---- batched drivers (loop over envs [env_begin, env_end); thread-safe on disjoint ranges) ---- */
 typedef struct trlo_step_io {
     int num_envs;

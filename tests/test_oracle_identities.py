@@ -177,3 +177,32 @@ def test_stable_pd_definition(oracle, name):
         assert np.all(tau[:7] == 0)
         assert np.allclose(tau, ref, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(ref).max()))
         assert zp >= 1  # root slot 6
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_com_velocity_is_time_derivative_of_com(oracle, name):
+    """cRBDUtil::CalcCoM's velocity (end-effector Jacobians) equals the finite-difference derivative of its position."""
+    m = oracle.Model(name)
+    x = _inputs(name, E=3)
+    eps = 1e-6
+    for e in range(3):
+        pose, vel = x["pose"][e], x["vel"][e]
+        _, cv = oracle.calc_com(m, pose, vel)
+        c1, _ = oracle.calc_com(m, _integrate(m, pose, vel, eps), vel)
+        c0, _ = oracle.calc_com(m, _integrate(m, pose, vel, -eps), vel)
+        assert np.allclose(cv, (c1 - c0) / (2 * eps), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["biped3d", "dog"])
+def test_imitation_reward_properties(oracle, name):
+    """Reward of a pose against itself is the maximum of every term that depends only on the poses; a fallen
+    character gets 0; the weights sum to 1."""
+    m = oracle.Model(name)
+    x = _inputs(name, E=3)
+    for e in range(3):
+        kp, kv = m.kin_char_pose(x["kin_time"][e])
+        r, t = oracle.imitate_reward(m, None, kp, kv, kp, kv, np.zeros((m.N, 3)))
+        assert t[0] < 1e-13 and t[1] == 0 and t[3] == 0 and t[2] < 1e-20  # 2*acos(w~1) amplifies rounding
+        r2, _ = oracle.imitate_reward(m, None, x["pose"][e], x["vel"][e], kp, kv, x["body_vel"][e])
+        assert 0 < r2 < r <= 1.0
+        assert oracle.imitate_reward(m, None, x["pose"][e], x["vel"][e], kp, kv, x["body_vel"][e], fallen=1)[0] == 0
