@@ -315,8 +315,17 @@ class Workload:
         def f_kin_fused(x, o):
             b.step_fused_args(kin_args[idx[id(x)]])
 
+        rew = [torch.empty((self.E,), dtype=torch.float64, device=self.inputs[0]["pose"].device) for _ in range(self.sets)]
+
+        def f_reward(x, o):  # SURVEY.md 8f rank-1 "next" row, measured beside the step's kernels
+            from terrainrlsim_b200 import _capi
+            p = b._prep([(x["pose"], np.float64), (x["vel"], np.float64), (o["kin_pose"], np.float64),
+                         (o["kin_vel"], np.float64), (x["body_vel"], np.float64), (None, np.uint8),
+                         (rew[idx[id(x)]], np.float64), (None, np.float64)])
+            _capi.lib().trl_imitate_calc_reward(b._h, *p)
+
         for name, fn in (("imp_pd", f_pd), ("kin_char", f_kin), ("fk", f_fk), ("kin_fused", f_kin_fused),
-                         ("poli_state", f_obs)):
+                         ("poli_state", f_obs), ("imitate_reward", f_reward)):
             for s in range(self.sets):
                 fn(self.inputs[s], self.outputs[s])
             torch.cuda.synchronize()

@@ -218,6 +218,19 @@ typedef struct trl_step_args {
 
 int trl_step_fused(trl_batch* b, const trl_step_args* args);
 
+/* ------------------------------------------------------------------------------------------
+ * imitation reward: cScenarioExpImitate::CalcReward (scenarios/ScenarioExpImitate.cpp:13-159)
+ *   with cKinTree::NormalizePoseHeading / CalcPoseErr / CalcVelErr (anim/KinTree.cpp:1319-1426,1647-1672),
+ *   cRBDUtil::CalcCoM / CalcCoMVel (sim/RBDUtil.cpp:499-598), cSimCharacter::CalcCOMVel (sim/SimCharacter.cpp:359-377).
+ *   pose / vel [E][n] = simulated character, kin_pose / kin_vel [E][n] = kinematic reference (trl_kin_char_pose),
+ *   body_vel [E][N][3] = body linear velocities, fallen [E] (NULL = none fallen; a fallen character scores 0).
+ *   End-effector positions of the simulated character are the FK of `pose` (the reference reads them from Bullet).
+ *   out_reward [E]; out_terms [E][5] = pose, vel, end-effector, root, com errors (optional).
+ * ---------------------------------------------------------------------------------------- */
+int trl_imitate_calc_reward(trl_batch* b, const double* pose, const double* vel, const double* kin_pose,
+                            const double* kin_vel, const double* body_vel, const unsigned char* fallen_or_null,
+                            double* out_reward, double* out_terms_or_null);
+
 /* per-env status word of the last stable-PD call: bit0 non-finite tau, bit1 non-positive pivot
  * (the reference would assert). out [E] ints, follows the pointer mode. */
 int trl_batch_get_status(trl_batch* b, int* out_status);

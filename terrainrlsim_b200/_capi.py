@@ -47,6 +47,7 @@ SYMBOLS = [
     ("trl_ground_sample_height", C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     ("trl_build_poli_state", C.c_int, [_VP] * 12),
     ("trl_step_fused", C.c_int, [_VP, C.POINTER(StepArgs)]),
+    ("trl_imitate_calc_reward", C.c_int, [_VP] * 9),
     ("trl_batch_get_status", C.c_int, [_VP, _VP]),
     ("trl_device_fp64_probe", C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     ("trl_last_error", C.c_char_p, []),

@@ -267,6 +267,16 @@ class Batch:
         check(_capi.lib().trl_build_poli_state(self._h, *p), "trl_build_poli_state")
         return (state, cells) if want_cells else state
 
+    # ---- imitation reward (cScenarioExpImitate::CalcReward) ----
+    def imitate_calc_reward(self, pose, vel, kin_pose, kin_vel, body_vel, fallen=None, want_terms=False):
+        reward = self._new((self.E,), pose)
+        terms = self._new((self.E, 5), pose) if want_terms else None
+        f8, u1 = np.float64, np.uint8
+        p = self._prep([(pose, f8), (vel, f8), (kin_pose, f8), (kin_vel, f8), (body_vel, f8), (fallen, u1), (reward, f8),
+                        (terms, f8)])
+        check(_capi.lib().trl_imitate_calc_reward(self._h, *p), "trl_imitate_calc_reward")
+        return (reward, terms) if want_terms else reward
+
     # ---- fused step ----
     def step_fused(self, dt, inp, out=None):
         """inp: dict with pose, vel, tar_pose, tar_vel, joint_active, kin_time, origin_pos, origin_rot, body_pos,

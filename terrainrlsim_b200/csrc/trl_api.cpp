@@ -544,6 +544,27 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     return finish(b, copies, rc);
 }
 
+extern "C" int trl_imitate_calc_reward(trl_batch* b, const double* pose, const double* vel, const double* kin_pose,
+                                       const double* kin_vel, const double* body_vel, const unsigned char* fallen,
+                                       double* out_reward, double* out_terms) {
+    if (!b || !pose || !vel || !kin_pose || !kin_vel || !body_vel || !out_reward) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double *d_p0, *d_v0, *d_p1, *d_v1, *d_bv;
+    const unsigned char* d_f;
+    double *d_r, *d_t;
+    if (!in_ptr(b, pose, E * n, &d_p0) || !in_ptr(b, vel, E * n, &d_v0) || !in_ptr(b, kin_pose, E * n, &d_p1) ||
+        !in_ptr(b, kin_vel, E * n, &d_v1) || !in_ptr(b, body_vel, E * N * 3, &d_bv) || !in_ptr(b, fallen, E, &d_f) ||
+        !out_ptr(b, out_reward, E, &d_r, copies) || !out_ptr(b, out_terms, E * 5, &d_t, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_imitate_reward(b->d_model, b->model->dev, b->ground, b->E, d_p0, d_v0, d_p1, d_v1, d_bv, d_f, d_r,
+                                       d_t, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
 extern "C" int trl_batch_get_status(trl_batch* b, int* out_status) {
     if (!b || !out_status) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);

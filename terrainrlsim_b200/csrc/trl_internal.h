@@ -32,6 +32,7 @@ struct alignas(16) ModelIdx {
     signed char level_joint[TRL_MAX_JOINTS];
     signed char slot_base[TRL_MAX_JOINTS];  // pose-feature slot of body j, cTerrainRLCharController packing (bodies 1..N-1)
     signed char slot_ct[TRL_MAX_JOINTS];    // same for cCtController packing (bodies 0..N-1); -1 = invalid body
+    signed char end_eff[TRL_MAX_JOINTS];    // cKinTree::IsEndEffector
     signed char level_start[TRL_MAX_JOINTS + 16];
     signed char col_joint[TRL_MAX_DOF];
     signed char col_kind[TRL_MAX_DOF];
@@ -65,6 +66,8 @@ struct DevModel {
     double idiag[TRL_MAX_JOINTS][3];  // BuildMomentInertia{Box,Capsule} diagonal (RBDUtil.cpp:623-673)
     double kp[TRL_MAX_JOINTS];
     double kd[TRL_MAX_JOINTS];
+    double joint_w[TRL_MAX_JOINTS];  // DiffWeight / sum|DiffWeight| (cScenarioExpImitate::CalcJointWeights)
+    double total_mass;
 
 };
 
@@ -124,6 +127,9 @@ int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* fr
 int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
                    const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
                    double* out_body_pos, void* stream);
+int trl_launch_imitate_reward(const DevModel* dm, const DevModel& hm, const DevGround& g, int E, const double* pose0,
+                              const double* vel0, const double* pose1, const double* vel1, const double* body_vel,
+                              const unsigned char* fallen, double* out_reward, double* out_terms, void* stream);
 int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,
                              unsigned char* out_valid, int* out_cell, void* stream);
 int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g, const trl_obs_cfg& cfg, int F,

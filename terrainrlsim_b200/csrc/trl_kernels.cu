@@ -971,6 +971,244 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_imitate_reward<G>: cScenarioExpImitate::CalcReward (scenarios/ScenarioExpImitate.cpp:13-159) -- G lanes per env.
+// pose0/vel0 = simulated character, pose1/vel1 = kinematic reference. One FK per character in world coordinates;
+// the heading-normalised frames of cKinTree::NormalizePoseHeading are applied to the FK results instead of
+// re-running FK on normalised pose vectors (same numbers to rounding).
+// ------------------------------------------------------------------------------------------------
+TRL_DEV double group_sum(double v, int G) {
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// heading frame of a root pose: R_h = R(y, -heading) as (c, s) with R_h * p = (c px + s pz, py, -s px + c pz),
+// and the heading quaternion hq = AxisAngleToQuaternion(y, -heading)
+struct HeadingFrame { double c, s, hq[4]; };
+TRL_DEV HeadingFrame heading_frame(const double* q) {
+    HeadingFrame h;
+    const double xdir[3] = {1, 0, 0};
+    double rd[3];
+    quat_rot_vec(q + 3, xdir, rd);
+    const double heading = atan2(-rd[2], rd[0]);
+    sincos(-heading, &h.s, &h.c);
+    double sh, ch;
+    sincos(-heading / 2, &sh, &ch);
+    h.hq[0] = ch; h.hq[1] = sh * 0.0; h.hq[2] = sh * 1.0; h.hq[3] = sh * 0.0;
+    return h;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128)
+k_imitate_reward(const DevModel* __restrict__ M, DevGround g, int E, const double* __restrict__ pose0,
+                 const double* __restrict__ vel0, const double* __restrict__ pose1, const double* __restrict__ vel1,
+                 const double* __restrict__ body_vel, const unsigned char* __restrict__ fallen,
+                 double* __restrict__ out_reward, double* __restrict__ out_terms) {
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    constexpr int EPW = 32 / G;
+    const int wlane = threadIdx.x & 31;
+    const int lane = wlane % G, sub = wlane / G;
+    const int warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int e_raw = (blockIdx.x * wpb + warp) * EPW + sub;
+    if ((blockIdx.x * wpb + warp) * EPW >= E) return;
+    const bool env_ok = e_raw < E;
+    const int e = env_ok ? e_raw : E - 1;
+    const int N = M->N, n = M->n;
+    double* ws = smem + (size_t)(warp * EPW + sub) * (42 * N);
+    double* Tl = ws;             // 12N scratch for the level composition
+    double* Tw0 = Tl + 12 * N;   // world transforms, simulated character
+    double* Tw1 = Tw0 + 12 * N;  // world transforms, kinematic character
+    double* V1 = Tw1 + 12 * N;   // world spatial velocities (at the world origin), kinematic character
+    const double* q0 = pose0 + (size_t)e * n;
+    const double* qd0 = vel0 + (size_t)e * n;
+    const double* q1 = pose1 + (size_t)e * n;
+    const double* qd1 = vel1 + (size_t)e * n;
+
+    // FK of both characters (world frame)
+    for (int pass = 0; pass < 2; ++pass) {
+        const double* q = pass ? q1 : q0;
+        double* Tw = pass ? Tw1 : Tw0;
+        for (int j = lane; j < N; j += G) {
+            double R[9], t[3];
+            double qq[7];
+            const int o = X->offset[j], sz = X->size[j];
+            for (int i = 0; i < sz; ++i) qq[i] = q[o + i];
+            joint_local_trans(X, j, qq, M->attR[j], M->attT[j], R, t);
+            double* dst = (j == 0) ? Tw : (Tl + 12 * j);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dst[i] = R[i];
+            dst[9] = t[0]; dst[10] = t[1]; dst[11] = t[2];
+        }
+        __syncwarp();
+        compose_levels(M, X, Tl, Tw, lane, 1, G);
+    }
+    // world spatial velocity of every joint of the kinematic character: V_j = V_p + S_j qd_j (motion vectors at the
+    // world origin: omega, v_O). Root: omega_l = qd[3:6], v_l = R(q)^T qd[0:3] in the joint frame (RBDUtil.cpp:770-784).
+    if (lane == 0) {
+        double Rq[9], vl[3], wl[3] = {qd1[3], qd1[4], qd1[5]}, lin[3] = {qd1[0], qd1[1], qd1[2]};
+        quat_to_mat(q1[3], q1[4], q1[5], q1[6], Rq);
+        mat3T_mulv(Rq, lin, vl);
+        double ww[3], vw[3], pxw[3];
+        mat3_mulv(Tw1, wl, ww);
+        mat3_mulv(Tw1, vl, vw);
+        cross3(Tw1 + 9, ww, pxw);
+        V1[0] = ww[0]; V1[1] = ww[1]; V1[2] = ww[2];
+        V1[3] = vw[0] + pxw[0]; V1[4] = vw[1] + pxw[1]; V1[5] = vw[2] + pxw[2];
+    }
+    __syncwarp();
+    for (int lv = 1; lv < M->num_levels; ++lv) {
+        const int beg = X->level_start[lv], cnt = X->level_start[lv + 1] - beg;
+        for (int it = lane; it < cnt; it += G) {
+            const int j = X->level_joint[beg + it];
+            double s[6] = {0, 0, 0, 0, 0, 0};
+            const int c0 = X->first_col[j], nc = X->ncol[j];
+            for (int c = c0; c < c0 + nc; ++c) {
+                double sc6[6];
+                subspace_col(X, Tw1, nullptr, c, sc6);  // non-root columns never read Rq
+                const double w = qd1[X->col_dof[c]];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
+            }
+            const int pj = X->parent[j];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) V1[6 * j + k] = V1[6 * pj + k] + s[k];
+        }
+        __syncwarp();
+    }
+
+    const HeadingFrame h0 = heading_frame(q0), h1 = heading_frame(q1);
+    // per-joint contributions
+    double s_m0[3] = {0, 0, 0}, s_m1[3] = {0, 0, 0}, s_v0[3] = {0, 0, 0}, s_v1[3] = {0, 0, 0};
+    double pose_err = 0, vel_err = 0, ee_err = 0, n_ee = 0;
+    const bool has_ground = g.kind != 0;
+    const DevPiece* pcs = nullptr;
+    if (g.kind == 1 || g.kind == 2) pcs = g.pieces + (long long)ground_field_of_env(g, e) * g.pieces_per_field;
+    for (int j = lane; j < N; j += G) {
+        const double w = M->joint_w[j];
+        const int o = X->offset[j], sz = X->size[j];
+        if (X->valid_body[j]) {
+            const double m = M->mass[j];
+            const double* cm = M->com[j];
+            // body CoM in the heading-normalised frames: R_h (c - root_xz) (y keeps the world height)
+            const double* T0 = Tw0 + 12 * j;
+            const double* T1 = Tw1 + 12 * j;
+            double c0w[3], c1w[3];
+            mat3_mulv(T0, cm, c0w); c0w[0] += T0[9]; c0w[1] += T0[10]; c0w[2] += T0[11];
+            mat3_mulv(T1, cm, c1w); c1w[0] += T1[9]; c1w[1] += T1[10]; c1w[2] += T1[11];
+            const double d0x = c0w[0] - q0[0], d0z = c0w[2] - q0[2];
+            const double d1x = c1w[0] - q1[0], d1z = c1w[2] - q1[2];
+            s_m0[0] += m * (h0.c * d0x + h0.s * d0z); s_m0[1] += m * c0w[1]; s_m0[2] += m * (-h0.s * d0x + h0.c * d0z);
+            s_m1[0] += m * (h1.c * d1x + h1.s * d1z); s_m1[1] += m * c1w[1]; s_m1[2] += m * (-h1.s * d1x + h1.c * d1z);
+            // CoM velocities (world): simulated = body velocities, kinematic = v_O + omega x c
+            const double* bv = body_vel + ((size_t)e * N + j) * 3;
+            s_v0[0] += m * bv[0]; s_v0[1] += m * bv[1]; s_v0[2] += m * bv[2];
+            const double* Vj = V1 + 6 * j;
+            double wxc[3];
+            cross3(Vj, c1w, wxc);
+            s_v1[0] += m * (Vj[3] + wxc[0]); s_v1[1] += m * (Vj[4] + wxc[1]); s_v1[2] += m * (Vj[5] + wxc[2]);
+        }
+        if (j == 0) {
+            // root: CalcRootRotErr / CalcRootAngVelErr on the heading-normalised poses (KinTree.cpp:1358-1363,1422-1426)
+            double a[4], b[4], bc[4], d[4];
+            quat_mul(h0.hq, q0 + 3, a);
+            quat_mul(h1.hq, q1 + 3, b);
+            bc[0] = a[0]; bc[1] = -a[1]; bc[2] = -a[2]; bc[3] = -a[3];
+            quat_mul(b, bc, d);  // QuatDiff(q0, q1) = q1 * conj(q0)
+            if (fabs(d[0]) > 1) quat_normalize(d);
+            const double th = 2 * acos(d[0]);
+            pose_err += w * (th * th);
+            double w0r[3], w1r[3];
+            quat_rot_vec(h0.hq, qd0 + 3, w0r);
+            quat_rot_vec(h1.hq, qd1 + 3, w1r);
+            double sv = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { const double dv = w1r[i] - w0r[i]; sv += dv * dv; }
+            vel_err += w * sv;
+        } else {
+            double cpe = 0, cve = 0;
+            if (X->type[j] == JT_SPHERICAL) {
+                double bc[4] = {q0[o], -q0[o + 1], -q0[o + 2], -q0[o + 3]}, d[4];
+                quat_mul(q1 + o, bc, d);
+                if (fabs(d[0]) > 1) quat_normalize(d);
+                const double th = 2 * acos(d[0]);
+                cpe = th * th;
+            } else {
+                for (int i = 0; i < sz; ++i) { const double dv = q1[o + i] - q0[o + i]; cpe += dv * dv; }
+            }
+            for (int i = 0; i < sz; ++i) { const double dv = qd1[o + i] - qd0[o + i]; cve += dv * dv; }
+            pose_err += w * cpe;
+            vel_err += w * cve;
+        }
+    }
+    // reduce the CoM sums over the env's lanes (every lane gets the totals)
+    const double inv_m = 1.0 / M->total_mass;
+    double com0[3], com1[3], cv0[3], cv1[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        com0[i] = group_sum(s_m0[i], G) * inv_m;
+        com1[i] = group_sum(s_m1[i], G) * inv_m;
+        cv0[i] = group_sum(s_v0[i], G) * inv_m;
+        cv1[i] = group_sum(s_v1[i], G) * inv_m;
+    }
+    // end effectors (ScenarioExpImitate.cpp:107-128)
+    for (int j = 1 + lane; j < N; j += G) {
+        if (!X->end_eff[j]) continue;
+        const double* T0 = Tw0 + 12 * j;
+        const double* T1 = Tw1 + 12 * j;
+        double gh0 = 0.0;
+        if (has_ground) {
+            int v, c3[3];
+            gh0 = ground_sample_pieces(g.kind, g.pieces_per_field, pcs, g.data, T0[9], T0[11], &v, c3);
+        }
+        const double d0x = T0[9] - q0[0], d0z = T0[11] - q0[2];
+        const double d1x = T1[9] - q1[0], d1z = T1[11] - q1[2];
+        const double r0x = (h0.c * d0x + h0.s * d0z) - com0[0], r0y = T0[10] - gh0, r0z = (-h0.s * d0x + h0.c * d0z) - com0[2];
+        const double r1x = (h1.c * d1x + h1.s * d1z) - com1[0], r1y = T1[10] - 0.0, r1z = (-h1.s * d1x + h1.c * d1z) - com1[2];
+        ee_err += (r1x - r0x) * (r1x - r0x) + (r1y - r0y) * (r1y - r0y) + (r1z - r0z) * (r1z - r0z);
+        n_ee += 1.0;
+    }
+    pose_err = group_sum(pose_err, G);
+    vel_err = group_sum(vel_err, G);
+    ee_err = group_sum(ee_err, G);
+    n_ee = group_sum(n_ee, G);
+    if (lane == 0 && env_ok) {
+        if (n_ee > 0) ee_err /= n_ee;
+        double rgh0 = 0.0;
+        if (has_ground) {
+            int v, c3[3];
+            rgh0 = ground_sample_pieces(g.kind, g.pieces_per_field, pcs, g.data, q0[0], q0[2], &v, c3);
+        }
+        // root velocities in the normalised frames (only through the 0-weighted term, kept for inf/NaN fidelity)
+        double rv0[3], rv1[3];
+        quat_rot_vec(h0.hq, qd0, rv0);
+        quat_rot_vec(h1.hq, qd1, rv1);
+        double dv2 = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double dv = rv1[i] - rv0[i]; dv2 += dv * dv; }
+        const double hh0 = q0[1] - rgh0, hh1 = q1[1] - 0.0;
+        const double root_err = (hh1 - hh0) * (hh1 - hh0) + 0 * 0.01 * dv2;
+        double cs = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double dv = cv1[i] - cv0[i]; cs += dv * dv; }
+        const double com_err = 0.1 * cs;
+        double pose_w = 0.5, vel_w = 0.05, end_eff_w = 0.15, root_w = 0.1, com_w = 0.2;
+        const double total_w = pose_w + vel_w + end_eff_w + root_w + com_w;
+        pose_w /= total_w; vel_w /= total_w; end_eff_w /= total_w; root_w /= total_w; com_w /= total_w;
+        double r = pose_w * exp(-1 * 2 * pose_err) + vel_w * exp(-1 * 0.005 * vel_err) + end_eff_w * exp(-1 * 40 * ee_err) +
+                   root_w * exp(-1 * 10 * root_err) + com_w * exp(-1 * 10 * com_err);
+        const bool fell = fallen ? (fallen[e] != 0) : false;
+        out_reward[e] = fell ? 0.0 : r;
+        if (out_terms) {
+            double* t = out_terms + (size_t)e * 5;
+            t[0] = fell ? 0.0 : pose_err; t[1] = fell ? 0.0 : vel_err; t[2] = fell ? 0.0 : ee_err;
+            t[3] = fell ? 0.0 : root_err; t[4] = fell ? 0.0 : com_err;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_sample_height: cGround::SampleHeight(MatrixXd, VectorXd&) with the scalar overload's numerics
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1433,6 +1671,29 @@ int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames,
     if (hm.N <= 8) return launch_kin_t<8>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
     if (hm.N <= 16) return launch_kin_t<16>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
     return launch_kin_t<32>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
+}
+
+template <int G>
+static int launch_reward_t(const DevModel* dm, const DevModel& hm, const DevGround& g, int E, const double* pose0,
+                           const double* vel0, const double* pose1, const double* vel1, const double* body_vel,
+                           const unsigned char* fallen, double* out_reward, double* out_terms, void* stream) {
+    constexpr int EPW = 32 / G;
+    const int wpb = 4;
+    const size_t smem = (size_t)42 * hm.N * sizeof(double) * wpb * EPW;
+    int rc = ensure_smem((const void*)k_imitate_reward<G>, smem);
+    if (rc) return rc;
+    const int epb = wpb * EPW;
+    k_imitate_reward<G><<<(E + epb - 1) / epb, wpb * 32, smem, (cudaStream_t)stream>>>(
+        dm, g, E, pose0, vel0, pose1, vel1, body_vel, fallen, out_reward, out_terms);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_imitate_reward(const DevModel* dm, const DevModel& hm, const DevGround& g, int E, const double* pose0,
+                              const double* vel0, const double* pose1, const double* vel1, const double* body_vel,
+                              const unsigned char* fallen, double* out_reward, double* out_terms, void* stream) {
+    if (hm.N <= 8) return launch_reward_t<8>(dm, hm, g, E, pose0, vel0, pose1, vel1, body_vel, fallen, out_reward, out_terms, stream);
+    if (hm.N <= 16) return launch_reward_t<16>(dm, hm, g, E, pose0, vel0, pose1, vel1, body_vel, fallen, out_reward, out_terms, stream);
+    return launch_reward_t<32>(dm, hm, g, E, pose0, vel0, pose1, vel1, body_vel, fallen, out_reward, out_terms, stream);
 }
 
 int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S, double* out_h,

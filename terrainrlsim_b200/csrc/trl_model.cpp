@@ -278,12 +278,22 @@ int trl_build_dev_model(trl_model* m) {
                 d.idiag[j][2] = x;
             }
         }
+        d.ix.end_eff[j] = jr[16] != 0;
         d.kp[j] = d.ix.pd_valid[j] ? pr[1] : 0.0;  // cImpPDController::InitGains, ImpPDController.cpp:100-121
         d.kd[j] = d.ix.pd_valid[j] ? pr[2] : 0.0;
         if (type == JT_SPHERICAL && parent != -1) d.has_spherical = 1;
     }
     d.n = off;
     m->n = off;
+    {
+        double wsum = 0;
+        d.total_mass = 0;
+        for (int j = 0; j < N; ++j) {
+            wsum += std::fabs(m->joint_mat[(size_t)j * TRL_JOINT_COLS + 17]);
+            if (d.ix.valid_body[j]) d.total_mass += d.mass[j];
+        }
+        for (int j = 0; j < N; ++j) d.joint_w[j] = m->joint_mat[(size_t)j * TRL_JOINT_COLS + 17] / wsum;
+    }
     if (off > TRL_MAX_DOF) { trl_set_error("model has too many dofs (max 64)"); return TRL_ERR_UNSUPPORTED; }
 
     // live dof columns

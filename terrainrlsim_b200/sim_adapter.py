@@ -20,7 +20,7 @@ Method map (reference -> here):
     update()               one animation frame = num_update_steps control substeps       :262-268, ScenarioSimChar.cpp:274-325
     updateAction(a)        PD targets of the actuated dofs (cCtPDController)             :441-456, CtPDController.cpp:70-100
     getState()             ParseGround + BuildPoliState                                  :493-508
-    calcReward()           imitation reward                                              SURVEY.md 8f rank 1 (not built yet)
+    calcReward()           imitation reward vs the kinematic reference                   ScenarioExpImitate.cpp:13-159
     agentHasFallen()       delegated to the world                                        :458-465
     needUpdatedAction()    true on the frames where the controller queries the policy    :467-475
     getActionSpaceSize() / getObservationSpaceSize()                                     :477-491
@@ -189,8 +189,16 @@ class BatchedSimAdapter:
                                            np.ascontiguousarray(body_vel), vel=np.ascontiguousarray(vel), phase=phase)
 
     def calcReward(self):
-        raise NotImplementedError("imitation reward (cScenarioExpImitate::CalcReward) is the SURVEY.md 8f rank-1 "
-                                  "'next' row and is not built in this round")
+        """cScenarioExpImitate::CalcReward against the kinematic reference character at the current time."""
+        if self.model.num_frames < 2:
+            raise TrlError("calcReward needs a motion (imitation scenarios)")
+        pose, vel, _, body_vel = self.world.state()
+        t = np.ascontiguousarray(getattr(self.world, "time", np.full(self.num_envs, self._frame * ANIM_STEP)), dtype=np.float64)
+        origin = getattr(self.world, "origin", None)
+        kin_pose, kin_vel = self.batch.kin_char_pose(t, origin, None)
+        fallen = np.ascontiguousarray(self.agentHasFallen(), dtype=np.uint8)
+        return self.batch.imitate_calc_reward(np.ascontiguousarray(pose), np.ascontiguousarray(vel), kin_pose, kin_vel,
+                                              np.ascontiguousarray(body_vel), fallen)
 
     def agentHasFallen(self):
         return np.asarray(self.world.has_fallen(), dtype=bool)

@@ -338,6 +338,36 @@ def test_batched_sim_adapter(trl, oracle, name):
         assert rel_err(ob[e], ref) <= 1e-9
     # the torque of the last substep equals the oracle's stable PD on the world's state before that substep
     assert sim.agentHasFallen().shape == (E,)
-    with pytest.raises(NotImplementedError):
-        sim.calcReward()
+    r = sim.calcReward()
+    assert r.shape == (E,) and np.all((r >= 0) & (r <= 1))
+    # the stand-in world tracks the reference exactly: pose / velocity terms are at their maximum
+    assert np.all(r[~sim.agentHasFallen()] > 0.5)
     sim.finish()
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_imitation_reward(trl, oracle, name):
+    """SURVEY.md 8f rank 1: cScenarioExpImitate::CalcReward, GPU vs oracle (reward and its five error terms)."""
+    E = 96
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=5)
+    kin_pose, kin_vel = batch.kin_char_pose(x["kin_time"], x["origin_pos"], x["origin_rot"])
+    # simulated character = perturbed reference (so every term is O(0.01 .. 1)), plus a few unrelated poses
+    rng = np.random.default_rng(9)
+    pose = kin_pose + 0.05 * rng.normal(size=kin_pose.shape)
+    for o in om.quat_slots():
+        pose[:, o:o + 4] /= np.linalg.norm(pose[:, o:o + 4], axis=1, keepdims=True)
+    vel = kin_vel + 0.3 * rng.normal(size=kin_vel.shape)
+    vel[:, 6] = 0
+    pose[:8], vel[:8] = x["pose"][:8], x["vel"][:8]
+    fallen = np.zeros(E, dtype=np.uint8)
+    fallen[5] = 1
+    reward, terms = batch.imitate_calc_reward(pose, vel, kin_pose, kin_vel, x["body_vel"], fallen, want_terms=True)
+    ref_r = np.zeros(E)
+    ref_t = np.zeros((E, 5))
+    for e in range(E):
+        ref_r[e], ref_t[e] = oracle.imitate_reward(om, grounds[e % len(grounds)], pose[e], vel[e], kin_pose[e], kin_vel[e],
+                                                   x["body_vel"][e], fallen[e])
+    assert reward[5] == 0 and np.all(terms[5] == 0)
+    assert_close(reward[:, None], ref_r[:, None], "imitation reward")
+    assert_close(terms, ref_t, "reward error terms")
+    assert np.all((reward >= 0) & (reward <= 1))
