@@ -20,6 +20,7 @@
 // and a 6-vector recurrence. Numbers agree with the reference's joint-local formulation to ~1e-13.
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 #include <math_constants.h>
 
 #include "trl_device.cuh"
@@ -147,6 +148,15 @@ TRL_DEV void compose_levels(const DevModel* __restrict__ M, const ModelIdx* X, c
 // (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot zeroes that solution component like
 // Eigen's pseudo-inverse of D does.
 // ------------------------------------------------------------------------------------------------
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, typename F>
+TRL_DEV void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
 TRL_DEV double fast_rcp(double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
@@ -739,6 +749,122 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
     if (status) {
         bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
         if (lane == 0) status[e] = bad;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pd_solve_w: same job as k_pd_solve with W (8 / 16) lanes per env, 32 / W envs per warp. Lane l of a group owns
+// columns l, l + W, ... (SLOTS = ceil(NLMAX / W) of them) of the symmetric system, so the rank-1 update of step k
+// costs one shuffle + SLOTS FMAs per row for 32 / W systems at once, instead of one shuffle + one FMA for one.
+// ------------------------------------------------------------------------------------------------
+template <int NLMAX, int W>
+struct SolveW {
+    static constexpr int SLOTS = (NLMAX + W - 1) / W;
+    static constexpr int MINB = (NLMAX * SLOTS * 2 + 44 <= 96) ? 5 : ((NLMAX * SLOTS * 2 + 48 <= 128) ? 4 : 3);
+};
+
+template <int NLMAX, int W>
+__global__ void __launch_bounds__(128, (SolveW<NLMAX, W>::MINB))
+k_pd_solve_w(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
+             int tau_accumulate, int* __restrict__ status) {
+    constexpr int SLOTS = SolveW<NLMAX, W>::SLOTS;
+    constexpr int EPW = 32 / W;
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int wl = threadIdx.x & 31;
+    const int l = wl & (W - 1);
+    const int e_raw = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * EPW + (wl / W);
+    const bool valid = e_raw < E;
+    const int e = valid ? e_raw : (E - 1);  // whole groups past the end redo the last env (no stores): shuffles stay full-warp
+    const int n = M->n, nl = M->nl;
+    const PdScratch SC = pd_scratch(n, nl);
+    const double* sc = scratch + (size_t)e * SC.stride;
+    double a[SLOTS * NLMAX], b[SLOTS], rdiag[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int col = l + s * W;
+        const bool live = col < nl;
+        const int lc = live ? col : 0;
+        const double* colp = sc + lc * (lc + 1) / 2;
+#pragma unroll
+        for (int i = 0; i < NLMAX; ++i) {
+            const double* rowp = sc + i * (i + 1) / 2 + lc;
+            double v = 0.0;
+            if (i < nl) v = __ldg((lc <= i) ? rowp : (colp + i));
+            a[s * NLMAX + i] = live ? v : ((i == col) ? 1.0 : 0.0);  // identity padding (columns >= NLMAX: never read)
+            if (live && i >= nl) a[s * NLMAX + i] = 0.0;
+        }
+        b[s] = live ? __ldg(sc + SC.rhs + lc) : 0.0;
+        rdiag[s] = 0.0;
+    }
+    int bad = 0;
+    // factorisation with the forward substitution folded in as one more row (b rides along as row NLMAX).
+    // static_for, not #pragma unroll: past a size budget nvcc silently keeps inner loops rolled, which would turn the
+    // register arrays into local memory.
+    static_for<0, NLMAX>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        constexpr int sk = k / W, lk = k % W;
+        const double d = __shfl_sync(0xffffffffu, a[sk * NLMAX + k], lk, W);
+        const bool ok = fabs(d) > DBL_MIN;
+        if (!(d > DBL_MIN)) bad |= 2;
+        const double r = ok ? fast_rcp(d) : 0.0;
+        if (l == lk) rdiag[sk] = r;
+        double c[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int col = l + s * W;
+            c[s] = (s >= sk && col > k && col < NLMAX) ? a[s * NLMAX + k] * r : 0.0;  // L[col][k]
+        }
+        static_for<k + 1, NLMAX>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const double t = __shfl_sync(0xffffffffu, a[sk * NLMAX + i], lk, W);  // A[i][k] = L[i][k] d_k
+#pragma unroll
+            for (int s = sk; s < SLOTS; ++s) a[s * NLMAX + i] = fma(-t, c[s], a[s * NLMAX + i]);
+        });
+        const double yk = __shfl_sync(0xffffffffu, b[sk], lk, W);  // y_k is final once steps < k are done
+#pragma unroll
+        for (int s = sk; s < SLOTS; ++s) b[s] = fma(-yk, c[s], b[s]);
+    });
+    double z[SLOTS], acc[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) { z[s] = b[s] * rdiag[s]; acc[s] = 0.0; }
+    static_for<0, NLMAX>([&](auto ic) {  // backward: L^T x = D^-1 y
+        constexpr int i = NLMAX - 1 - decltype(ic)::value;
+        constexpr int si = i / W, li = i % W;
+        const double xi = __shfl_sync(0xffffffffu, fma(-rdiag[si], acc[si], z[si]), li, W);
+#pragma unroll
+        for (int s = 0; s <= si; ++s) {
+            const double ai = (l + s * W < i) ? a[s * NLMAX + i] : 0.0;
+            acc[s] = fma(ai, xi, acc[s]);
+        }
+    });
+    double x[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) x[s] = fma(-rdiag[s], acc[s], z[s]);
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int i = i0 + l;
+        const int c = (i < n) ? X->dof_col[i] : -1;
+        const int cc = c < 0 ? 0 : c;
+        double qdd = 0.0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const double v = __shfl_sync(0xffffffffu, x[s], cc & (W - 1), W);
+            if ((cc / W) == s) qdd = v;
+        }
+        if (i < n) {
+            const double t = __ldg(sc + SC.t0 + i) - __ldg(sc + SC.t1 + i) * (c < 0 ? 0.0 : qdd);
+            if (!isfinite(t)) bad |= 1;
+            if (valid) {
+                double* out = tau + (size_t)e * n + i;
+                *out = tau_accumulate ? (*out + t) : t;
+            }
+        }
+    }
+    if (status) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o, W);
+        if (l == 0 && valid) status[e] = bad;
     }
 }
 
@@ -1590,6 +1716,14 @@ static int launch_pd_solve_t(const DevModel* dm, int E, const StepPtrs& p, const
     return (int)cudaGetLastError();
 }
 
+template <int NLMAX, int W>
+static int launch_pd_solve_w(const DevModel* dm, int E, const StepPtrs& p, const double* scratch, void* stream) {
+    const int wpb = 4, epb = wpb * (32 / W);
+    k_pd_solve_w<NLMAX, W><<<(E + epb - 1) / epb, wpb * 32, 0, (cudaStream_t)stream>>>(dm, E, scratch, p.tau,
+                                                                                      p.tau_accumulate, p.status);
+    return (int)cudaGetLastError();
+}
+
 // lanes per env: heuristic, or forced with the TRL_PD_GROUP environment variable (8 / 16 / 32; tuning and tests)
 static int pd_group_override() {
     static int v = -1;
@@ -1625,6 +1759,16 @@ int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepP
 #undef TRL_PD_CASE
     if (rc) return rc > 0 ? -rc : rc;
     if (!split) return 1;
+    static const int solve_w = env_int("TRL_PD_SOLVE_W", 1);  // tuning hook: 0 = one env per warp
+    if (solve_w) {
+        if (nl <= 8) rc = launch_pd_solve_w<8, 8>(dm, E, p, scratch, stream);
+        else if (nl <= 16) rc = launch_pd_solve_w<16, 16>(dm, E, p, scratch, stream);
+        else if (nl <= 20) rc = launch_pd_solve_w<20, 16>(dm, E, p, scratch, stream);
+        else if (nl <= 24) rc = launch_pd_solve_w<24, 16>(dm, E, p, scratch, stream);
+        else if (nl <= 28) rc = launch_pd_solve_w<28, 16>(dm, E, p, scratch, stream);
+        else rc = launch_pd_solve_w<32, 16>(dm, E, p, scratch, stream);
+        return rc ? -rc : 2;
+    }
     if (nl <= 8) rc = launch_pd_solve_t<8>(dm, E, p, scratch, stream);
     else if (nl <= 18) rc = launch_pd_solve_t<18>(dm, E, p, scratch, stream);
     else if (nl <= 20) rc = launch_pd_solve_t<20>(dm, E, p, scratch, stream);
