@@ -211,7 +211,8 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
     }
     {
-        const size_t bytes = trl_pd_scratch_doubles(m->dev) * sizeof(double) * (size_t)num_envs;
+        const size_t tile = (size_t)trl_pd_scratch_tile();
+        const size_t bytes = trl_pd_scratch_doubles(m->dev) * sizeof(double) * (((size_t)num_envs + tile - 1) / tile * tile);
         if (!cuda_ok(cudaMalloc((void**)&b->d_pd_scratch, bytes), "cudaMalloc(pd scratch)")) return nullptr;
         cudaMemset(b->d_pd_scratch, 0, bytes);  // structurally-zero entries of the packed matrix are never written
     }

@@ -34,6 +34,7 @@ struct alignas(16) ModelIdx {
     signed char slot_ct[TRL_MAX_JOINTS];    // same for cCtController packing (bodies 0..N-1); -1 = invalid body
     signed char end_eff[TRL_MAX_JOINTS];    // cKinTree::IsEndEffector
     signed char level_start[TRL_MAX_JOINTS + 16];
+    signed char dfs_event[2 * TRL_MAX_JOINTS];  // depth-first walk: j = enter joint j, -1 - j = leave joint j (2N events)
     signed char col_joint[TRL_MAX_DOF];
     signed char col_kind[TRL_MAX_DOF];
     signed char col_axis[TRL_MAX_DOF];
@@ -117,6 +118,7 @@ struct StepPtrs {
 };
 
 size_t trl_pd_scratch_doubles(const DevModel& hm);
+int trl_pd_scratch_tile();
 // returns the number of kernels launched (> 0) or a negative cudaError_t
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream);
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,

@@ -82,8 +82,11 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, b
     return L;
 }
 
-// global scratch handed from k_imp_pd<.., SPLIT> to k_pd_solve, per env (doubles):
-//   [Hp: nl(nl+1)/2 packed lower of M + dt*Kd][rhs: nl][t0: n][t1: n]     tau_i = t0_i - t1_i * qdd_col(i)
+// global scratch handed from k_imp_pd<.., SPLIT> to the solve kernel. Tiles of 32 envs, structure-of-arrays inside a
+// tile: element `idx` of env e lives at scratch[((e / 32) * stride + idx) * 32 + e % 32], so the solve kernel (one
+// thread per env) reads it with fully coalesced loads / one bulk copy per tile. Per env (doubles):
+//   [Hp: nl(nl+1)/2 column-packed lower triangle of M + dt*Kd][rhs: nl][t0: n][t1: n]   tau_i = t0_i - t1_i * qdd_col(i)
+constexpr int kTile = 32;
 struct PdScratch { int np, rhs, t0, t1, stride; };
 __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
     PdScratch s;
@@ -94,6 +97,8 @@ __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
     s.stride = (s.t1 + n + 1) & ~1;
     return s;
 }
+// entry (i, j), i >= j, of the column-packed lower triangle: column j is contiguous (rows j .. nl-1)
+__host__ __device__ constexpr int pd_tri(int i, int j, int nl) { return j * nl - j * (j - 1) / 2 + (i - j); }
 
 // Column c of the joint subspace S in the root frame (cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828),
 // recomputed from the joint's root-frame transform wherever it is needed instead of being stored.
@@ -309,7 +314,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     const int N = M->N, n = M->n, nl = M->nl;
     const PdLayout L = pd_layout(N, n, nl, NLMAX, SPLIT);
     const PdScratch SC = pd_scratch(n, nl);
-    double* sc = SPLIT ? scratch + (size_t)e * SC.stride : nullptr;
+    double* sc = SPLIT ? scratch + ((size_t)(e / kTile) * SC.stride * kTile + (e % kTile)) : nullptr;  // element idx: sc[idx * kTile]
     const double* cst = smem;  // per-joint constants (kCst doubles each), staged at kernel entry
     double* ws = smem + pd_cst_doubles(N) + (size_t)(warp * EPW + sub) * L.total;
     double* q = ws + L.q;
@@ -546,7 +551,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
             if (SPLIT) {
                 if (a == c) x[c] = hv;  // diagonal stash: dt*Kd is added once the gains are known (P8)
-                else if (env_ok) sc[c * (c + 1) / 2 + a] = hv;
+                else if (env_ok) sc[pd_tri(c, a, nl) * kTile] = hv;
             } else {
                 H[c * ldh + a] = hv;
                 H[a * ldh + c] = hv;
@@ -563,7 +568,7 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             om[di * n + di] = x[c];
             for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
                 const int da = X->col_dof[a];
-                const double hv = sc[c * (c + 1) / 2 + a];
+                const double hv = sc[pd_tri(c, a, nl) * kTile];
                 om[di * n + da] = hv;
                 om[da * n + di] = hv;
             }
@@ -635,8 +640,8 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         if (env_ok) {
             for (int c = lane; c < nl; c += G) {
                 const int i = X->col_dof[c];
-                sc[SC.rhs + c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
-                sc[c * (c + 1) / 2 + c] = x[c] + dt * kdu[i];
+                sc[(SC.rhs + c) * kTile] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
+                sc[pd_tri(c, c, nl) * kTile] = x[c] + dt * kdu[i];
             }
             for (int i = lane; i < n; i += G) {
                 double t0 = kpm[i] * ep[i] + kdm[i] * ev[i];
@@ -647,8 +652,8 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                     t0 = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
                     t1 = 0.0;
                 }
-                sc[SC.t0 + i] = t0;
-                sc[SC.t1 + i] = t1;
+                sc[(SC.t0 + i) * kTile] = t0;
+                sc[(SC.t1 + i) * kTile] = t1;
             }
         }
         return;
@@ -702,170 +707,543 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_pd_solve: second half of the split stable-PD step -- one warp per env, no shared memory: loads the packed system
-// from the scratch straight into the register-resident LDL^T (lane <-> column), solves, forms tau.
+// k_pd_tree: first half of the split stable-PD step -- ONE THREAD PER ENV, a warp = one scratch tile of 32 envs.
+// The articulated-body recursions run as a depth-first walk of the joint tree (ModelIdx::dfs_event): on entering a
+// joint the thread forms its PD terms, root-frame transform, velocity / acceleration, body inertia and force; on
+// leaving it the subtree inertia is complete, so the joint's columns of H = M + dt*Kd and of the bias force are
+// formed against the ancestors on the current root path and the subtree sums are folded into the parent. Only the
+// current root path is ever live, so the workspace is [depth][kSlot] doubles per env (shared memory, element k of
+// level l at ws[(l * kSlot + k) * 32 + lane]: conflict-free), not [joints][...]. Every branch depends on the model
+// only, never on the env: the 32 lanes run in lock step. Results go to the tiled scratch with coalesced stores.
+// Same formulation as k_imp_pd (root frame, 10-parameter inertias, H[c][a] = F_c . S_a on the ancestor chain).
 // ------------------------------------------------------------------------------------------------
-template <int NLMAX>
-__global__ void __launch_bounds__(128, 5)
-k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
-           int tau_accumulate, int* __restrict__ status) {
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (e >= E) return;
-    const int n = M->n, nl = M->nl;
-    const PdScratch SC = pd_scratch(n, nl);
-    const double* sc = scratch + (size_t)e * SC.stride;
-    double a[NLMAX];
-    // column `lane` of the packed lower triangle: entry (i, lane) lives at tri(max) + min. Addresses are formed for a
-    // clamped lane so every load is unconditional; lanes / rows beyond nl are replaced by identity padding afterwards.
-    const bool live = lane < nl;
-    const int lc = live ? lane : 0;
-    const double* colp = sc + lc * (lc + 1) / 2;  // &P[lc][0]: entries (lc, i) for i <= lc
-#pragma unroll
-    for (int i = 0; i < NLMAX; ++i) {
-        const double* rowp = sc + i * (i + 1) / 2 + lc;  // &P[i][lc]: valid when lc <= i
-        double v = 0.0;
-        if (i < nl) v = __ldg((lc <= i) ? rowp : (colp + i));
-        a[i] = live ? v : ((i == lane) ? 1.0 : 0.0);
-        if (live && i >= nl) a[i] = 0.0;
+constexpr int kSlotT = 0;    // root-frame transform of the joint [R(9) | t(3)]
+constexpr int kSlotV = 12;   // spatial velocity (6)
+constexpr int kSlotA = 18;   // spatial acceleration (6)
+constexpr int kSlotI = 24;   // inertia: m, h(3), Ixx Ixy Ixz Iyy Iyz Izz; summed over the subtree on the way up
+constexpr int kSlotF = 34;   // force (6), same
+constexpr int kSlotU = 40;   // Kp e_p + Kd e_v per joint dof (<= 7)
+constexpr int kSlotKd = 47;  // unmasked Kd of the joint
+constexpr int kSlot = 48;
+constexpr int kTreeHead = 9;  // per env, ahead of the levels: R(q_root), rows = directions of the root translation dofs
+
+TRL_DEV void tree_subspace(int kind, int a, const double* T /* [(k) * 32] strided */, const double* Rq, double* s) {
+    if (kind == CK_ANG) {
+        s[0] = T[a * kTile]; s[1] = T[(3 + a) * kTile]; s[2] = T[(6 + a) * kTile];
+        const double t0 = T[9 * kTile], t1 = T[10 * kTile], t2 = T[11 * kTile];
+        s[3] = t1 * s[2] - t2 * s[1];
+        s[4] = t2 * s[0] - t0 * s[2];
+        s[5] = t0 * s[1] - t1 * s[0];
+    } else if (kind == CK_LIN) {
+        s[0] = s[1] = s[2] = 0.0;
+        s[3] = T[a * kTile]; s[4] = T[(3 + a) * kTile]; s[5] = T[(6 + a) * kTile];
+    } else {  // CK_ROOT_LIN: row a of R(q_root)
+        s[0] = s[1] = s[2] = 0.0;
+        s[3] = Rq[(3 * a) * kTile]; s[4] = Rq[(3 * a + 1) * kTile]; s[5] = Rq[(3 * a + 2) * kTile];
     }
-    const double b = live ? __ldg(sc + SC.rhs + lane) : 0.0;
-    int bad = 0;
-    const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
-    for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const int c = (i < n) ? X->dof_col[i] : -1;
-        const double acc = __shfl_sync(0xffffffffu, xv, c < 0 ? 0 : c);
-        if (i < n) {
-            const double t = __ldg(sc + SC.t0 + i) - __ldg(sc + SC.t1 + i) * (c < 0 ? 0.0 : acc);
-            if (!isfinite(t)) bad |= 1;
-            double* out = tau + (size_t)e * n + i;
-            *out = tau_accumulate ? (*out + t) : t;
+}
+
+__global__ void __launch_bounds__(128)
+k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
+        const int Nj = M->N;
+        for (int i = threadIdx.x; i < Nj * kCst; i += blockDim.x) {
+            const int j = i / kCst, k = i - j * kCst;
+            double v;
+            if (k < 9) v = M->attR[j][k];
+            else if (k < 12) v = M->attT[j][k - 9];
+            else if (k == 12) v = M->mass[j];
+            else if (k < 16) v = M->com[j][k - 13];
+            else if (k < 19) v = M->idiag[j][k - 16];
+            else if (k == 19) v = M->kp[j];
+            else v = M->kd[j];
+            smem[i] = v;
         }
     }
-    if (status) {
-        bad = __reduce_or_sync(0xffffffffu, (unsigned)bad);
-        if (lane == 0) status[e] = bad;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int e0 = tile * kTile;
+    if (e0 >= E) return;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const int e = e0 + (env_ok ? lane : envs - 1);  // tail lanes redo the last env and store nothing
+    const int N = M->N, n = M->n, nl = M->nl;
+    const PdScratch SC = pd_scratch(n, nl);
+    const double* cst = smem;
+    double* ws = smem + pd_cst_doubles(N) + (size_t)warp * ((kTreeHead + M->num_levels * kSlot) * kTile) + lane;
+    double* Rq = ws;                       // Rq[k * 32]
+    double* lvl = ws + kTreeHead * kTile;  // level l, element k: lvl[(l * kSlot + k) * 32]
+    double* sc = scratch + (size_t)tile * SC.stride * kTile + lane;  // element idx: sc[idx * 32]
+    const double dt = p.dt;
+    const double* q = p.pose + (size_t)e * n;
+    const double* qd = p.vel + (size_t)e * n;
+    const double* tq = p.tar_pose + (size_t)e * n;
+    const double* tqd = p.tar_vel + (size_t)e * n;
+    {   // the four [32][n] input blocks of this tile are contiguous: pull their lines into L1 with coalesced prefetches
+        const size_t row0 = (size_t)e0 * n * sizeof(double);
+        const int bytes = envs * n * (int)sizeof(double);
+        for (int off = lane * 128; off < bytes; off += 32 * 128) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.pose + row0 + off));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.vel + row0 + off));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.tar_pose + row0 + off));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.tar_vel + row0 + off));
+        }
+    }
+    if (p.out_mass) {  // rare path (GetMassMat): zero the tile's [32][n][n] block, coalesced
+        double* om = p.out_mass + (size_t)e0 * n * n;
+        for (int idx = lane; idx < envs * n * n; idx += 32) om[idx] = 0.0;
+        __syncwarp();
+    }
+
+    const int nev = 2 * N;
+    for (int evi = 0; evi < nev; ++evi) {
+        const int code = X->dfs_event[evi];
+        if (code >= 0) {
+            // ---------------- enter joint j ----------------
+            const int j = code;
+            const int lv = X->level[j];
+            double* W = lvl + (size_t)lv * kSlot * kTile;
+            const double* Wp = W - kSlot * kTile;  // parent = previous level (valid when lv > 0)
+            const int o = X->offset[j], sz = X->size[j];
+            const int type = X->type[j];
+            const bool is_root = X->parent[j] == -1;
+            const double* cj_ = cst + kCst * j;
+
+            // PD terms (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196)
+            {
+                const bool valid = X->pd_valid[j] != 0;
+                const bool active = valid && (p.joint_active ? (p.joint_active[(size_t)e * N + j] != 0) : true);
+                double kp = 0.0, kd = 0.0;
+                if (valid) {
+                    kp = p.kp ? p.kp[(size_t)e * N + j] : cj_[19];
+                    kd = p.kd ? p.kd[(size_t)e * N + j] : cj_[20];
+                }
+                const double kpm = active ? kp : 0.0, kdm = active ? kd : 0.0;
+                W[kSlotKd * kTile] = kd;  // unmasked gains go on the diagonal
+                double ep[4] = {0, 0, 0, 0};
+                const bool sph = valid && !is_root && type == JT_SPHERICAL;
+                if (sph) {
+                    double qj[4], wj[4], dq[4], qi[4], tar[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { qj[i] = q[o + i]; wj[i] = qd[o + i]; tar[i] = tq[o + i]; }
+                    quat_diff_mul(qj, wj, dq);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) qi[i] = qj[i] + dt * dq[i];
+                    quat_normalize(qi);
+                    // cPDController::PostProcessTargetPose / PostProcessTargetVel (PDController.cpp:430-461)
+                    if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
+                    else quat_normalize(tar);
+                    quat_vel_rel(qi, tar, 1.0, ep);
+                }
+                for (int i = 0; i < sz; ++i) {
+                    const double qdi = qd[o + i];
+                    double epi = 0.0, evi_ = 0.0;
+                    if (valid) {
+                        if (sph) {
+                            epi = (i == 0) ? ep[0] : (i == 1) ? ep[1] : (i == 2) ? ep[2] : ep[3];
+                            evi_ = ((i < 3) ? tqd[o + i] : 0.0) - qdi;
+                        } else {
+                            epi = (tq[o + i] - (q[o + i] + dt * qdi)) / 1.0;
+                            evi_ = tqd[o + i] - qdi;
+                        }
+                    }
+                    const double u = kpm * epi + kdm * evi_;
+                    if (i < 7) W[(kSlotU + i) * kTile] = u;
+                    double t0 = u, t1 = kdm * dt;
+                    if (X->dof_col[o + i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
+                        const double dg = dt * kd;
+                        const double acc = (fabs(dg) > DBL_MIN) ? u / dg : 0.0;
+                        t0 = kpm * epi + kdm * (evi_ - dt * acc);
+                        t1 = 0.0;
+                    }
+                    if (env_ok) {
+                        sc[(SC.t0 + o + i) * kTile] = t0;
+                        sc[(SC.t1 + o + i) * kTile] = t1;
+                    }
+                }
+            }
+
+            // root-frame transform
+            double T[12], Vp[6], Ap[6];
+            if (is_root) {
+                double qr[7], wr[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { qr[i] = q[o + i]; wr[i] = qd[o + i]; }
+                double Rw[9];
+                {   // world <- root = A * T(pos) * R(quat); only its rotation is needed (gravity in the root frame)
+                    double rq9[9];
+                    quat_to_mat(qr[3], qr[4], qr[5], qr[6], rq9);
+                    mat3_mul(cj_, rq9, Rw);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rq[i * kTile] = rq9[i];
+                }
+                // a_0 = X_{world->root}(0, -g): E = Rw^T  (RBDUtil.cpp:17-18,59-60)
+                const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
+                double g0[3];
+                mat3T_mulv(Rw, ng, g0);
+                // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
+                double dq[4];
+                quat_diff_mul(qr + 3, wr + 3, dq);
+                const double qw = qr[3], qx = qr[4], qy = qr[5], qz = qr[6];
+                const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
+                const double m00 = 4 * (qw * dw + qx * dx), m11 = 4 * (qw * dw + qy * dy), m22 = 4 * (qw * dw + qz * dz);
+                const double m10 = 2 * (dx * qy + qx * dy - dw * qz - qw * dz);
+                const double m01 = 2 * (dx * qy + qx * dy + dw * qz + qw * dz);
+                const double m20 = 2 * (dx * qz + qx * dz + dw * qy + qw * dy);
+                const double m02 = 2 * (dx * qz + qx * dz - dw * qy - qw * dy);
+                const double m21 = 2 * (dy * qz + qy * dz - dw * qx - qw * dx);
+                const double m12 = 2 * (dy * qz + qy * dz + dw * qx + qw * dx);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) T[i] = (i % 4 == 0) ? 1.0 : 0.0;
+                T[9] = T[10] = T[11] = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { Vp[k] = 0.0; Ap[k] = 0.0; }
+                Ap[3] = g0[0] + (m00 * wr[0] + m01 * wr[1] + m02 * wr[2]);
+                Ap[4] = g0[1] + (m10 * wr[0] + m11 * wr[1] + m12 * wr[2]);
+                Ap[5] = g0[2] + (m20 * wr[0] + m21 * wr[1] + m22 * wr[2]);
+            } else {
+                double qj[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qj[i] = (i < sz) ? q[o + i] : 0.0;
+                double R[9], t[3];
+                joint_local_trans(X, j, qj, cj_, cj_ + 9, R, t);
+                double Tp[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Tp[i] = Wp[(kSlotT + i) * kTile];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
+                    T[9 + r] = Tp[9 + r] + (Tp[r * 3] * t[0] + Tp[r * 3 + 1] * t[1] + Tp[r * 3 + 2] * t[2]);
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { Vp[k] = Wp[(kSlotV + k) * kTile]; Ap[k] = Wp[(kSlotA + k) * kTile]; }
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) W[(kSlotT + i) * kTile] = T[i];
+
+            // s_j = S_j qd_j ; V_j = V_p + s_j ; a_j = a_p + V_p x s_j (motion cross product; V_j x s_j = V_p x s_j)
+            double s[6] = {0, 0, 0, 0, 0, 0};
+            {
+                const int c0 = X->first_col[j], nc = X->ncol[j];
+                for (int c = c0; c < c0 + nc; ++c) {
+                    const double w = qd[X->col_dof[c]];
+                    double sc6[6];
+                    tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sc6);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
+                }
+            }
+            double Vj[6], Aj[6];
+            {
+                double c0[3], c1[3], c2[3];
+                cross3(Vp, s, c0);
+                cross3(Vp + 3, s, c1);
+                cross3(Vp, s + 3, c2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    Vj[k] = Vp[k] + s[k];
+                    Vj[3 + k] = Vp[3 + k] + s[3 + k];
+                    Aj[k] = Ap[k] + c0[k];
+                    Aj[3 + k] = Ap[3 + k] + (c1[k] + c2[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { W[(kSlotV + k) * kTile] = Vj[k]; W[(kSlotA + k) * kTile] = Aj[k]; }
+
+            // body inertia in the root frame (m, h = m c, I about the frame origin) and f = I a + V x* (I V)
+            double I[10], f[6] = {0, 0, 0, 0, 0, 0};
+            if (X->valid_body[j]) {
+                const double m = cj_[12];
+                double c[3];
+                mat3_mulv(T, cj_ + 13, c);
+                c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
+                const double d0 = cj_[16], d1 = cj_[17], d2 = cj_[18];
+                double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
+                double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
+                double Ixz = T[0] * T[6] * d0 + T[1] * T[7] * d1 + T[2] * T[8] * d2;
+                double Iyy = T[3] * T[3] * d0 + T[4] * T[4] * d1 + T[5] * T[5] * d2;
+                double Iyz = T[3] * T[6] * d0 + T[4] * T[7] * d1 + T[5] * T[8] * d2;
+                double Izz = T[6] * T[6] * d0 + T[7] * T[7] * d1 + T[8] * T[8] * d2;
+                Ixx += m * (c[1] * c[1] + c[2] * c[2]);
+                Iyy += m * (c[0] * c[0] + c[2] * c[2]);
+                Izz += m * (c[0] * c[0] + c[1] * c[1]);
+                Ixy -= m * c[0] * c[1];
+                Ixz -= m * c[0] * c[2];
+                Iyz -= m * c[1] * c[2];
+                I[0] = m; I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
+                I[4] = Ixx; I[5] = Ixy; I[6] = Ixz; I[7] = Iyy; I[8] = Iyz; I[9] = Izz;
+                const double* h = I + 1;
+                double hxv[3], hxw[3];
+                cross3(h, Aj + 3, hxv);
+                cross3(h, Aj, hxw);
+                const double na[3] = {Ixx * Aj[0] + Ixy * Aj[1] + Ixz * Aj[2] + hxv[0],
+                                      Ixy * Aj[0] + Iyy * Aj[1] + Iyz * Aj[2] + hxv[1],
+                                      Ixz * Aj[0] + Iyz * Aj[1] + Izz * Aj[2] + hxv[2]};
+                const double fa[3] = {m * Aj[3] - hxw[0], m * Aj[4] - hxw[1], m * Aj[5] - hxw[2]};
+                cross3(h, Vj + 3, hxv);
+                cross3(h, Vj, hxw);
+                const double nv[3] = {Ixx * Vj[0] + Ixy * Vj[1] + Ixz * Vj[2] + hxv[0],
+                                      Ixy * Vj[0] + Iyy * Vj[1] + Iyz * Vj[2] + hxv[1],
+                                      Ixz * Vj[0] + Iyz * Vj[1] + Izz * Vj[2] + hxv[2]};
+                const double fv[3] = {m * Vj[3] - hxw[0], m * Vj[4] - hxw[1], m * Vj[5] - hxw[2]};
+                double wxn[3], vxf[3], wxf[3];
+                cross3(Vj, nv, wxn);
+                cross3(Vj + 3, fv, vxf);
+                cross3(Vj, fv, wxf);
+                f[0] = na[0] + wxn[0] + vxf[0]; f[1] = na[1] + wxn[1] + vxf[1]; f[2] = na[2] + wxn[2] + vxf[2];
+                f[3] = fa[0] + wxf[0]; f[4] = fa[1] + wxf[1]; f[5] = fa[2] + wxf[2];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 10; ++i) I[i] = 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 10; ++i) W[(kSlotI + i) * kTile] = I[i];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) W[(kSlotF + i) * kTile] = f[i];
+        } else {
+            // ---------------- leave joint j: subtree sums are complete ----------------
+            const int j = -1 - code;
+            const int lv = X->level[j];
+            double* W = lvl + (size_t)lv * kSlot * kTile;
+            const int o = X->offset[j];
+            double I[10], f[6];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) I[i] = W[(kSlotI + i) * kTile];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) f[i] = W[(kSlotF + i) * kTile];
+            const double kdu = W[kSlotKd * kTile];
+            const int c0 = X->first_col[j], nc = X->ncol[j];
+            for (int c = c0; c < c0 + nc; ++c) {
+                double sv[6];
+                tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv);
+                const double m = I[0];
+                const double* h = I + 1;
+                double hxv[3], hxw[3];
+                cross3(h, sv + 3, hxv);
+                cross3(h, sv, hxw);
+                double Fc[6];
+                Fc[0] = I[4] * sv[0] + I[5] * sv[1] + I[6] * sv[2] + hxv[0];
+                Fc[1] = I[5] * sv[0] + I[7] * sv[1] + I[8] * sv[2] + hxv[1];
+                Fc[2] = I[6] * sv[0] + I[8] * sv[1] + I[9] * sv[2] + hxv[2];
+                Fc[3] = m * sv[3] - hxw[0];
+                Fc[4] = m * sv[4] - hxw[1];
+                Fc[5] = m * sv[5] - hxw[2];
+                const double Cc = sv[0] * f[0] + sv[1] * f[1] + sv[2] * f[2] + sv[3] * f[3] + sv[4] * f[4] + sv[5] * f[5];
+                const int di = X->col_dof[c];
+                const double hd = Fc[0] * sv[0] + Fc[1] * sv[1] + Fc[2] * sv[2] + Fc[3] * sv[3] + Fc[4] * sv[4] + Fc[5] * sv[5];
+                const int ui = di - o;
+                const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
+                if (env_ok) {
+                    sc[(SC.rhs + c) * kTile] = u - Cc;
+                    sc[pd_tri(c, c, nl) * kTile] = hd + dt * kdu;
+                    if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
+                    if (p.out_mass) p.out_mass[((size_t)e * n + di) * n + di] = hd;
+                }
+                for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
+                    const int ja = X->col_joint[a];
+                    double sa[6];
+                    tree_subspace(X->col_kind[a], X->col_axis[a], lvl + ((size_t)X->level[ja] * kSlot + kSlotT) * kTile, Rq, sa);
+                    const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
+                    if (env_ok) {
+                        sc[pd_tri(c, a, nl) * kTile] = hv;
+                        if (p.out_mass) {
+                            const int da = X->col_dof[a];
+                            p.out_mass[((size_t)e * n + di) * n + da] = hv;
+                            p.out_mass[((size_t)e * n + da) * n + di] = hv;
+                        }
+                    }
+                }
+            }
+            if (lv > 0) {
+                double* Wp = W - kSlot * kTile;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Wp[(kSlotI + i) * kTile] += W[(kSlotI + i) * kTile];
+            }
+        }
+    }
+    if (p.out_bias && env_ok) {  // dead dofs are exact zeros
+        for (int i = 0; i < n; ++i)
+            if (X->dof_col[i] < 0) p.out_bias[(size_t)e * n + i] = 0.0;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_pd_solve_w: same job as k_pd_solve with W (8 / 16) lanes per env, 32 / W envs per warp. Lane l of a group owns
-// columns l, l + W, ... (SLOTS = ceil(NLMAX / W) of them) of the symmetric system, so the rank-1 update of step k
-// costs one shuffle + SLOTS FMAs per row for 32 / W systems at once, instead of one shuffle + one FMA for one.
+// k_pd_solve: second half of the split stable-PD step -- ONE THREAD PER ENV. A warp owns one scratch tile (32 envs,
+// structure-of-arrays): the packed triangle is pulled into shared memory with a single bulk async copy (TMA, completion
+// on an mbarrier), then every thread runs a scalar left-looking LDL^T on "its" column of the tile (element idx at
+// tri[idx * 32 + lane]: conflict-free). No shuffles, no masks, no symmetric double work: the 32 lanes do 32 systems.
+// NL > 0: exact size, fully unrolled with rhs / pivots in registers; NL == 0: any nl, runtime loops.
+// No pivoting: M + dt*Kd is SPD on the live dofs (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot
+// zeroes that solution component like Eigen's pseudo-inverse of D does.
 // ------------------------------------------------------------------------------------------------
-template <int NLMAX, int W>
-struct SolveW {
-    static constexpr int SLOTS = (NLMAX + W - 1) / W;
-    static constexpr int MINB = (NLMAX * SLOTS * 2 + 44 <= 96) ? 5 : ((NLMAX * SLOTS * 2 + 48 <= 128) ? 4 : 3);
-};
+TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int NLMAX, int W>
-__global__ void __launch_bounds__(128, (SolveW<NLMAX, W>::MINB))
-k_pd_solve_w(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
-             int tau_accumulate, int* __restrict__ status) {
-    constexpr int SLOTS = SolveW<NLMAX, W>::SLOTS;
-    constexpr int EPW = 32 / W;
+TRL_DEV void tile_bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar, int lane) {
+    const unsigned bar_a = smem_u32(bar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(dst)),
+                     "l"(src), "r"(bytes), "r"(bar_a)
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TRL_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra TRL_DONE_%=;\n"
+        "bra TRL_WAIT_%=;\n"
+        "TRL_DONE_%=:\n"
+        "}\n" ::"r"(bar_a)
+        : "memory");
+}
+
+template <int NL>
+__global__ void __launch_bounds__(128)
+k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
+           int tau_accumulate, int* __restrict__ status) {
+    extern __shared__ __align__(16) double smem[];
     __shared__ ModelIdx s_ix;
+    __shared__ unsigned long long s_bar[4];
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;
-    const int wl = threadIdx.x & 31;
-    const int l = wl & (W - 1);
-    const int e_raw = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * EPW + (wl / W);
-    const bool valid = e_raw < E;
-    const int e = valid ? e_raw : (E - 1);  // whole groups past the end redo the last env (no stores): shuffles stay full-warp
-    const int n = M->n, nl = M->nl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (tile * kTile >= E) return;
+    const int n = M->n, nl = (NL > 0) ? NL : M->nl;
     const PdScratch SC = pd_scratch(n, nl);
-    const double* sc = scratch + (size_t)e * SC.stride;
-    double a[SLOTS * NLMAX], b[SLOTS], rdiag[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int col = l + s * W;
-        const bool live = col < nl;
-        const int lc = live ? col : 0;
-        const double* colp = sc + lc * (lc + 1) / 2;
-#pragma unroll
-        for (int i = 0; i < NLMAX; ++i) {
-            const double* rowp = sc + i * (i + 1) / 2 + lc;
-            double v = 0.0;
-            if (i < nl) v = __ldg((lc <= i) ? rowp : (colp + i));
-            a[s * NLMAX + i] = live ? v : ((i == col) ? 1.0 : 0.0);  // identity padding (columns >= NLMAX: never read)
-            if (live && i >= nl) a[s * NLMAX + i] = 0.0;
-        }
-        b[s] = live ? __ldg(sc + SC.rhs + lc) : 0.0;
-        rdiag[s] = 0.0;
-    }
+    // per-warp shared memory: the triangle [np][32]; the generic path appends rhs / pivots / 1/pivots [3][nl][32]
+    const int per_warp = (SC.np + (NL > 0 ? 0 : 3 * nl)) * kTile;
+    double* tri = smem + (size_t)warp * per_warp + lane;  // element idx: tri[idx * kTile]
+    const double* g = scratch + (size_t)tile * SC.stride * kTile;
+    tile_bulk_load(tri - lane, g, (unsigned)(SC.np * kTile * sizeof(double)), &s_bar[warp], lane);
+    g += lane;
     int bad = 0;
-    // factorisation with the forward substitution folded in as one more row (b rides along as row NLMAX).
-    // static_for, not #pragma unroll: past a size budget nvcc silently keeps inner loops rolled, which would turn the
-    // register arrays into local memory.
-    static_for<0, NLMAX>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        constexpr int sk = k / W, lk = k % W;
-        const double d = __shfl_sync(0xffffffffu, a[sk * NLMAX + k], lk, W);
-        const bool ok = fabs(d) > DBL_MIN;
-        if (!(d > DBL_MIN)) bad |= 2;
-        const double r = ok ? fast_rcp(d) : 0.0;
-        if (l == lk) rdiag[sk] = r;
-        double c[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int col = l + s * W;
-            c[s] = (s >= sk && col > k && col < NLMAX) ? a[s * NLMAX + k] * r : 0.0;  // L[col][k]
-        }
-        static_for<k + 1, NLMAX>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const double t = __shfl_sync(0xffffffffu, a[sk * NLMAX + i], lk, W);  // A[i][k] = L[i][k] d_k
-#pragma unroll
-            for (int s = sk; s < SLOTS; ++s) a[s * NLMAX + i] = fma(-t, c[s], a[s * NLMAX + i]);
+    if constexpr (NL > 0) {
+        // b[] lives in registers (the column loop is a compile-time loop); the q loop stays a runtime loop so the
+        // code stays small: column q is addressed from one base register, its pivot d_q sits on the diagonal slot.
+        double b[NL];
+        static_for<0, NL>([&](auto ic) { b[decltype(ic)::value] = __ldg(g + (SC.rhs + decltype(ic)::value) * kTile); });
+        static_for<0, NL>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            double v[NL - j];
+            static_for<j, NL>([&](auto ic) { v[decltype(ic)::value - j] = tri[pd_tri(decltype(ic)::value, j, NL) * kTile]; });
+#pragma unroll 2
+            for (int q = 0; q < j; ++q) {
+                const double* cq = tri + (pd_tri(q, q, NL) - q) * kTile;  // cq[i * kTile] = entry (i, q)
+                const double w = cq[j * kTile] * cq[q * kTile];           // L[j][q] d_q
+                static_for<j, NL>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    v[i - j] = fma(-cq[i * kTile], w, v[i - j]);
+                });
+            }
+            const double dj = v[0];
+            const bool ok = fabs(dj) > DBL_MIN;
+            if (!(dj > DBL_MIN)) bad |= 2;
+            const double r = ok ? fast_rcp(dj) : 0.0;
+            tri[pd_tri(j, j, NL) * kTile] = ok ? dj : 0.0;
+            const double yj = b[j];
+            static_for<j + 1, NL>([&](auto ic) {  // L[i][j]; forward substitution rides along (y_j is final here)
+                constexpr int i = decltype(ic)::value;
+                const double lij = v[i - j] * r;
+                tri[pd_tri(i, j, NL) * kTile] = lij;
+                b[i] = fma(-lij, yj, b[i]);
+            });
+            b[j] = yj * r;  // z_j = y_j / d_j
         });
-        const double yk = __shfl_sync(0xffffffffu, b[sk], lk, W);  // y_k is final once steps < k are done
-#pragma unroll
-        for (int s = sk; s < SLOTS; ++s) b[s] = fma(-yk, c[s], b[s]);
-    });
-    double z[SLOTS], acc[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { z[s] = b[s] * rdiag[s]; acc[s] = 0.0; }
-    static_for<0, NLMAX>([&](auto ic) {  // backward: L^T x = D^-1 y
-        constexpr int i = NLMAX - 1 - decltype(ic)::value;
-        constexpr int si = i / W, li = i % W;
-        const double xi = __shfl_sync(0xffffffffu, fma(-rdiag[si], acc[si], z[si]), li, W);
-#pragma unroll
-        for (int s = 0; s <= si; ++s) {
-            const double ai = (l + s * W < i) ? a[s * NLMAX + i] : 0.0;
-            acc[s] = fma(ai, xi, acc[s]);
+        // backward: L^T x = D^-1 y, row by row (x_i is final when row i is reached; the updates of b[0..i) are
+        // independent). The rows are read through a pointer the compiler cannot prove equal to `tri`, otherwise it
+        // forwards every L[i][j] stored above through registers and spills the whole factor to local memory.
+        const double* trb = tri + ((E == -kTile) ? 1 : 0);
+        static_for<1, NL>([&](auto ic) {
+            constexpr int i = NL - decltype(ic)::value;
+            static_for<0, i>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                b[j] = fma(-trb[pd_tri(i, j, NL) * kTile], b[i], b[j]);
+            });
+        });
+        __syncwarp();
+        static_for<0, NL>([&](auto ic) { tri[decltype(ic)::value * kTile] = b[decltype(ic)::value]; });  // x -> smem (column 0 slots)
+    } else {
+        double* bs = tri + SC.np * kTile;
+        double* ds = bs + nl * kTile;
+        double* rs = ds + nl * kTile;
+        for (int i = 0; i < nl; ++i) bs[i * kTile] = __ldg(g + (SC.rhs + i) * kTile);
+        for (int j = 0; j < nl; ++j) {
+            for (int q = 0; q < j; ++q) {
+                const double w = tri[pd_tri(j, q, nl) * kTile] * ds[q * kTile];
+                for (int i = j; i < nl; ++i) tri[pd_tri(i, j, nl) * kTile] -= tri[pd_tri(i, q, nl) * kTile] * w;
+            }
+            const double dj = tri[pd_tri(j, j, nl) * kTile];
+            const bool ok = fabs(dj) > DBL_MIN;
+            if (!(dj > DBL_MIN)) bad |= 2;
+            const double r = ok ? fast_rcp(dj) : 0.0;
+            ds[j * kTile] = ok ? dj : 0.0;
+            rs[j * kTile] = r;
+            const double yj = bs[j * kTile];
+            for (int i = j + 1; i < nl; ++i) {
+                const double lij = tri[pd_tri(i, j, nl) * kTile] * r;
+                tri[pd_tri(i, j, nl) * kTile] = lij;
+                bs[i * kTile] -= lij * yj;
+            }
         }
-    });
-    double x[SLOTS];
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) x[s] = fma(-rdiag[s], acc[s], z[s]);
-    for (int i0 = 0; i0 < n; i0 += W) {
-        const int i = i0 + l;
-        const int c = (i < n) ? X->dof_col[i] : -1;
-        const int cc = c < 0 ? 0 : c;
-        double qdd = 0.0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const double v = __shfl_sync(0xffffffffu, x[s], cc & (W - 1), W);
-            if ((cc / W) == s) qdd = v;
+        for (int j = nl - 1; j >= 0; --j) {
+            double acc = bs[j * kTile] * rs[j * kTile];
+            for (int i = j + 1; i < nl; ++i) acc -= tri[pd_tri(i, j, nl) * kTile] * bs[i * kTile];
+            bs[j * kTile] = acc;
         }
-        if (i < n) {
-            const double t = __ldg(sc + SC.t0 + i) - __ldg(sc + SC.t1 + i) * (c < 0 ? 0.0 : qdd);
-            if (!isfinite(t)) bad |= 1;
-            if (valid) {
-                double* out = tau + (size_t)e * n + i;
-                *out = tau_accumulate ? (*out + t) : t;
+        __syncwarp();
+        for (int i = 0; i < nl; ++i) tri[i * kTile] = bs[i * kTile];
+    }
+    // tau_i = t0_i - t1_i * qdd_col(i), transposed through shared memory so the [E][n] output is written coalesced.
+    // The x vector sits in tri[0 .. nl) (rows of column 0); tau is staged behind it.
+    double* ts = tri - lane + nl * kTile;  // [32][n] env-major staging (np >= nl + n for every model with nl >= 3...)
+    const int e0 = tile * kTile;
+    const int envs = min(kTile, E - e0);
+    const bool stage = (SC.np - nl) >= n;  // room behind x inside the triangle region; else write directly
+    constexpr int kB = 8;  // tau terms are fetched kB dofs at a time so the global-load latency is paid n / kB times, not n
+    for (int i0 = 0; i0 < n; i0 += kB) {
+        double t0v[kB], t1v[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+            const int i = min(i0 + k, n - 1);
+            t0v[k] = __ldg(g + (SC.t0 + i) * kTile);
+            t1v[k] = __ldg(g + (SC.t1 + i) * kTile);
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+            const int i = i0 + k;
+            if (i < n) {
+                const int c = X->dof_col[i];
+                const double t = t0v[k] - t1v[k] * (c < 0 ? 0.0 : tri[c * kTile]);
+                if (!isfinite(t)) bad |= 1;
+                if (stage) {
+                    ts[lane * n + i] = t;
+                } else if (lane < envs) {
+                    double* out = tau + (size_t)(e0 + lane) * n + i;
+                    *out = tau_accumulate ? (*out + t) : t;
+                }
             }
         }
     }
-    if (status) {
-#pragma unroll
-        for (int o = W / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o, W);
-        if (l == 0 && valid) status[e] = bad;
+    if (stage) {
+        __syncwarp();
+        double* out = tau + (size_t)e0 * n;
+        for (int idx = lane; idx < envs * n; idx += 32) out[idx] = tau_accumulate ? (out[idx] + ts[idx]) : ts[idx];
     }
+    if (status && lane < envs) status[e0 + lane] = bad;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1708,19 +2086,32 @@ static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const 
     return (int)cudaGetLastError();
 }
 
-template <int NLMAX>
-static int launch_pd_solve_t(const DevModel* dm, int E, const StepPtrs& p, const double* scratch, void* stream) {
-    const int wpb = 4;
-    k_pd_solve<NLMAX><<<(E + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
-                                                                                 p.status);
+template <int NL>
+static int launch_pd_solve_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, const double* scratch, void* stream) {
+    const PdScratch SC = pd_scratch(hm.n, hm.nl);
+    const size_t per_warp = (size_t)(SC.np + (NL > 0 ? 0 : 3 * hm.nl)) * kTile * sizeof(double);
+    // one warp = one tile of 32 envs; blocks of one warp spread the tiles over the SMs as evenly as possible
+    const int wpb = 1;
+    const size_t smem = per_warp * wpb;
+    if (smem > 227 * 1024 - 2048) return (int)cudaErrorInvalidValue;
+    int rc = ensure_smem((const void*)k_pd_solve<NL>, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_pd_solve<NL><<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
+                                                                                    p.status);
     return (int)cudaGetLastError();
 }
 
-template <int NLMAX, int W>
-static int launch_pd_solve_w(const DevModel* dm, int E, const StepPtrs& p, const double* scratch, void* stream) {
-    const int wpb = 4, epb = wpb * (32 / W);
-    k_pd_solve_w<NLMAX, W><<<(E + epb - 1) / epb, wpb * 32, 0, (cudaStream_t)stream>>>(dm, E, scratch, p.tau,
-                                                                                      p.tau_accumulate, p.status);
+static int launch_pd_tree(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
+    const size_t per_warp = (size_t)(kTreeHead + hm.num_levels * kSlot) * kTile * sizeof(double);
+    const size_t cst_bytes = (size_t)pd_cst_doubles(hm.N) * sizeof(double);
+    const int wpb = 1;  // one warp = one tile of 32 envs; single-warp blocks spread the tiles evenly over the SMs
+    const size_t smem = per_warp * wpb + cst_bytes;
+    if (smem > 227 * 1024 - 2048) return (int)cudaErrorInvalidValue;
+    int rc = ensure_smem((const void*)k_pd_tree, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_pd_tree<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p, scratch);
     return (int)cudaGetLastError();
 }
 
@@ -1734,7 +2125,9 @@ static int pd_group_override() {
     return v;
 }
 
+// per env; the allocation is rounded up to whole tiles of kTile envs by the caller (trl_pd_scratch_tile())
 size_t trl_pd_scratch_doubles(const DevModel& hm) { return (size_t)pd_scratch(hm.n, hm.nl).stride; }
+int trl_pd_scratch_tile() { return kTile; }
 
 // Returns the number of kernels launched (>0) or a negative cudaError.
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
@@ -1749,6 +2142,8 @@ int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepP
     const int ov = pd_group_override();
     if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
     int rc = -1;
+    static const int tree_env = env_int("TRL_PD_TREE", 1);  // tuning / test hook: 0 = lane-per-joint k_imp_pd<.., SPLIT>
+    if (split && tree_env) rc = launch_pd_tree(dm, hm, E, p, scratch, stream);
 #define TRL_PD_CASE(GG, NL)                                                                       \
     if (rc == -1 && G == GG && nl <= NL)                                                          \
         rc = split ? launch_imp_pd_t<GG, NL, true>(dm, hm, E, p, scratch, stream)                 \
@@ -1759,22 +2154,15 @@ int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepP
 #undef TRL_PD_CASE
     if (rc) return rc > 0 ? -rc : rc;
     if (!split) return 1;
-    static const int solve_w = env_int("TRL_PD_SOLVE_W", 1);  // tuning hook: 0 = one env per warp
-    if (solve_w) {
-        if (nl <= 8) rc = launch_pd_solve_w<8, 8>(dm, E, p, scratch, stream);
-        else if (nl <= 16) rc = launch_pd_solve_w<16, 16>(dm, E, p, scratch, stream);
-        else if (nl <= 20) rc = launch_pd_solve_w<20, 16>(dm, E, p, scratch, stream);
-        else if (nl <= 24) rc = launch_pd_solve_w<24, 16>(dm, E, p, scratch, stream);
-        else if (nl <= 28) rc = launch_pd_solve_w<28, 16>(dm, E, p, scratch, stream);
-        else rc = launch_pd_solve_w<32, 16>(dm, E, p, scratch, stream);
-        return rc ? -rc : 2;
+    static const int generic_env = env_int("TRL_PD_SOLVE_GENERIC", 0);  // tuning / test hook: force the runtime-loop kernel
+    switch (generic_env ? -1 : nl) {  // exact sizes of the bundled characters are unrolled; anything else takes runtime loops
+        case 8: rc = launch_pd_solve_t<8>(dm, hm, E, p, scratch, stream); break;    // hopper
+        case 17: rc = launch_pd_solve_t<17>(dm, hm, E, p, scratch, stream); break;  // biped2d
+        case 20: rc = launch_pd_solve_t<20>(dm, hm, E, p, scratch, stream); break;  // biped3d
+        case 24: rc = launch_pd_solve_t<24>(dm, hm, E, p, scratch, stream); break;  // raptor
+        case 26: rc = launch_pd_solve_t<26>(dm, hm, E, p, scratch, stream); break;  // dog
+        default: rc = launch_pd_solve_t<0>(dm, hm, E, p, scratch, stream); break;
     }
-    if (nl <= 8) rc = launch_pd_solve_t<8>(dm, E, p, scratch, stream);
-    else if (nl <= 18) rc = launch_pd_solve_t<18>(dm, E, p, scratch, stream);
-    else if (nl <= 20) rc = launch_pd_solve_t<20>(dm, E, p, scratch, stream);
-    else if (nl <= 24) rc = launch_pd_solve_t<24>(dm, E, p, scratch, stream);
-    else if (nl <= 26) rc = launch_pd_solve_t<26>(dm, E, p, scratch, stream);
-    else rc = launch_pd_solve_t<32>(dm, E, p, scratch, stream);
     return rc ? -rc : 2;
 }
 

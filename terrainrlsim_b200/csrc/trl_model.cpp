@@ -344,6 +344,30 @@ int trl_build_dev_model(trl_model* m) {
             if (d.ix.level[j] == l) d.ix.level_joint[pos++] = j;
     }
     d.ix.level_start[max_level + 1] = pos;
+    {   // depth-first event list (enter / leave) for the thread-per-env tree walk of k_pd_tree
+        int ne = 0;
+        std::vector<int> stack;
+        std::vector<int> next_child(N, 0);
+        for (int r = 0; r < N; ++r) {
+            if (d.ix.parent[r] != -1) continue;
+            stack.push_back(r);
+            d.ix.dfs_event[ne++] = (signed char)r;
+            while (!stack.empty()) {
+                const int j = stack.back();
+                int c = next_child[j];
+                while (c < N && d.ix.parent[c] != j) ++c;
+                if (c < N) {
+                    next_child[j] = c + 1;
+                    stack.push_back(c);
+                    d.ix.dfs_event[ne++] = (signed char)c;
+                } else {
+                    next_child[j] = N;
+                    stack.pop_back();
+                    d.ix.dfs_event[ne++] = (signed char)(-1 - j);
+                }
+            }
+        }
+    }
     {
         int sb = 0, sc = 0;
         for (int j = 0; j < N; ++j) {

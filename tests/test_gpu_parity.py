@@ -371,3 +371,42 @@ def test_imitation_reward(trl, oracle, name):
     assert_close(reward[:, None], ref_r[:, None], "imitation reward")
     assert_close(terms, ref_t, "reward error terms")
     assert np.all((reward >= 0) & (reward <= 1))
+
+
+_VARIANT_SCRIPT = """
+import sys, numpy as np
+sys.path.insert(0, {tests!r}); sys.path.insert(0, {root!r})
+import terrainrlsim_b200 as trl
+from terrainrlsim_b200 import synth
+from oracle import oracle_py as oracle
+from helpers import rel_err, product_cfg
+for name in {names!r}:
+    E = 77  # not a multiple of the 32-env scratch tile
+    om = oracle.Model(name); pm = trl.CharModel.from_name(name)
+    batch = trl.Batch(pm, E, 0, product_cfg(trl, name))
+    x = synth.make_inputs(name, E)
+    tau, _, _ = batch.imp_pd_update_control_force(1.0 / 600, x["pose"], x["vel"], x["tar_pose"], x["tar_vel"],
+                                                  joint_active=x["joint_active"])
+    ref = np.stack([om.imp_pd(1.0 / 600, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e],
+                              x["joint_active"][e])[0] for e in range(E)])
+    err = rel_err(tau, ref)
+    assert err < 1e-9, (name, err)
+    assert np.all(batch.status() == 0)
+print("VARIANT_OK")
+"""
+
+
+@pytest.mark.parametrize("env", [{"TRL_PD_SPLIT": "0"}, {"TRL_PD_SOLVE_GENERIC": "1"}, {"TRL_PD_TREE": "0"},
+                                 {"TRL_PD_TREE": "0", "TRL_PD_GROUP": "32"},
+                                 {"TRL_PD_SPLIT": "0", "TRL_PD_GROUP": "16"}])
+def test_pd_kernel_variants(env):
+    """The launcher's tuning hooks select other kernel variants (monolithic warp-per-env PD, runtime-loop solve, wider
+    lane groups); each must meet the same 1e-9 bar. Hooks are read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    script = _VARIANT_SCRIPT.format(tests=here, root=os.path.dirname(here), names=["hopper", "biped2d", "dog", "biped3d"])
+    out = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
