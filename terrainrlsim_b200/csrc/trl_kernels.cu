@@ -85,7 +85,7 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, b
 // global scratch handed from k_imp_pd<.., SPLIT> to the solve kernel. Tiles of 32 envs, structure-of-arrays inside a
 // tile: element `idx` of env e lives at scratch[((e / 32) * stride + idx) * 32 + e % 32], so the solve kernel (one
 // thread per env) reads it with fully coalesced loads / one bulk copy per tile. Per env (doubles):
-//   [Hp: nl(nl+1)/2 column-packed lower triangle of M + dt*Kd][rhs: nl][t0: n][t1: n]   tau_i = t0_i - t1_i * qdd_col(i)
+//   [Hp: nl(nl+1)/2 row-packed lower triangle of M + dt*Kd][rhs: nl][t0: n][t1: n]   tau_i = t0_i - t1_i * qdd_col(i)
 constexpr int kTile = 32;
 struct PdScratch { int np, rhs, t0, t1, stride; };
 __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
@@ -97,8 +97,8 @@ __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
     s.stride = (s.t1 + n + 1) & ~1;
     return s;
 }
-// entry (i, j), i >= j, of the column-packed lower triangle: column j is contiguous (rows j .. nl-1)
-__host__ __device__ constexpr int pd_tri(int i, int j, int nl) { return j * nl - j * (j - 1) / 2 + (i - j); }
+// entry (i, j), i >= j, of the row-packed lower triangle
+__host__ __device__ constexpr int pd_tri(int i, int j, int /*nl*/ = 0) { return i * (i + 1) / 2 + j; }
 
 // Column c of the joint subspace S in the root frame (cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828),
 // recomputed from the joint's root-frame transform wherever it is needed instead of being stored.
@@ -1019,43 +1019,78 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
             for (int i = 0; i < 6; ++i) f[i] = W[(kSlotF + i) * kTile];
             const double kdu = W[kSlotKd * kTile];
             const int c0 = X->first_col[j], nc = X->ncol[j];
-            for (int c = c0; c < c0 + nc; ++c) {
-                double sv[6];
-                tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv);
-                const double m = I[0];
-                const double* h = I + 1;
-                double hxv[3], hxw[3];
-                cross3(h, sv + 3, hxv);
-                cross3(h, sv, hxw);
-                double Fc[6];
-                Fc[0] = I[4] * sv[0] + I[5] * sv[1] + I[6] * sv[2] + hxv[0];
-                Fc[1] = I[5] * sv[0] + I[7] * sv[1] + I[8] * sv[2] + hxv[1];
-                Fc[2] = I[6] * sv[0] + I[8] * sv[1] + I[9] * sv[2] + hxv[2];
-                Fc[3] = m * sv[3] - hxw[0];
-                Fc[4] = m * sv[4] - hxw[1];
-                Fc[5] = m * sv[5] - hxw[2];
-                const double Cc = sv[0] * f[0] + sv[1] * f[1] + sv[2] * f[2] + sv[3] * f[3] + sv[4] * f[4] + sv[5] * f[5];
-                const int di = X->col_dof[c];
-                const double hd = Fc[0] * sv[0] + Fc[1] * sv[1] + Fc[2] * sv[2] + Fc[3] * sv[3] + Fc[4] * sv[4] + Fc[5] * sv[5];
-                const int ui = di - o;
-                const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
-                if (env_ok) {
-                    sc[(SC.rhs + c) * kTile] = u - Cc;
-                    sc[pd_tri(c, c, nl) * kTile] = hd + dt * kdu;
-                    if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
-                    if (p.out_mass) p.out_mass[((size_t)e * n + di) * n + di] = hd;
+            // columns of the joint in groups of <= 3 (a joint has 1, 3 or, for the root, 6): the group's force columns
+            // F_c stay in registers while the ancestor chain is walked once, one subspace column S_a per step.
+            for (int cb = c0; cb < c0 + nc; cb += 3) {
+                const int cnt = min(3, c0 + nc - cb);
+                double sv[3][6], Fc[3][6];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = cb + (k < cnt ? k : 0);
+                    tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv[k]);
+                    const double m = I[0];
+                    const double* h = I + 1;
+                    double hxv[3], hxw[3];
+                    cross3(h, sv[k] + 3, hxv);
+                    cross3(h, sv[k], hxw);
+                    Fc[k][0] = I[4] * sv[k][0] + I[5] * sv[k][1] + I[6] * sv[k][2] + hxv[0];
+                    Fc[k][1] = I[5] * sv[k][0] + I[7] * sv[k][1] + I[8] * sv[k][2] + hxv[1];
+                    Fc[k][2] = I[6] * sv[k][0] + I[8] * sv[k][1] + I[9] * sv[k][2] + hxv[2];
+                    Fc[k][3] = m * sv[k][3] - hxw[0];
+                    Fc[k][4] = m * sv[k][4] - hxw[1];
+                    Fc[k][5] = m * sv[k][5] - hxw[2];
                 }
-                for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k < cnt) {
+                        const int c = cb + k;
+                        const double Cc = sv[k][0] * f[0] + sv[k][1] * f[1] + sv[k][2] * f[2] + sv[k][3] * f[3] +
+                                          sv[k][4] * f[4] + sv[k][5] * f[5];
+                        const int di = X->col_dof[c];
+                        const int ui = di - o;
+                        const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
+                        if (env_ok) {
+                            sc[(SC.rhs + c) * kTile] = u - Cc;
+                            if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
+                        }
+#pragma unroll
+                        for (int k2 = 0; k2 <= k; ++k2) {  // pairs inside the group (col_parent of a joint's column = previous one)
+                            double hv = (Fc[k][0] * sv[k2][0] + Fc[k][1] * sv[k2][1] + Fc[k][2] * sv[k2][2]) +
+                                        (Fc[k][3] * sv[k2][3] + Fc[k][4] * sv[k2][4] + Fc[k][5] * sv[k2][5]);
+                            if (env_ok) {
+                                if (p.out_mass) {
+                                    const int da = X->col_dof[cb + k2];
+                                    p.out_mass[((size_t)e * n + di) * n + da] = hv;
+                                    p.out_mass[((size_t)e * n + da) * n + di] = hv;
+                                }
+                                if (k2 == k) hv += dt * kdu;
+                                sc[pd_tri(c, cb + k2) * kTile] = hv;
+                            }
+                        }
+                    }
+                }
+                const int r0 = pd_tri(cb, 0), r1 = pd_tri(cb + 1, 0), r2 = pd_tri(cb + 2, 0);
+                for (int a = X->col_parent[cb]; a >= 0; a = X->col_parent[a]) {
                     const int ja = X->col_joint[a];
                     double sa[6];
                     tree_subspace(X->col_kind[a], X->col_axis[a], lvl + ((size_t)X->level[ja] * kSlot + kSlotT) * kTile, Rq, sa);
-                    const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
+                    double hv[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        hv[k] = (Fc[k][0] * sa[0] + Fc[k][1] * sa[1] + Fc[k][2] * sa[2]) +
+                                (Fc[k][3] * sa[3] + Fc[k][4] * sa[4] + Fc[k][5] * sa[5]);
                     if (env_ok) {
-                        sc[pd_tri(c, a, nl) * kTile] = hv;
+                        sc[(r0 + a) * kTile] = hv[0];
+                        if (cnt > 1) sc[(r1 + a) * kTile] = hv[1];
+                        if (cnt > 2) sc[(r2 + a) * kTile] = hv[2];
                         if (p.out_mass) {
                             const int da = X->col_dof[a];
-                            p.out_mass[((size_t)e * n + di) * n + da] = hv;
-                            p.out_mass[((size_t)e * n + da) * n + di] = hv;
+                            for (int k = 0; k < cnt; ++k) {
+                                const int di = X->col_dof[cb + k];
+                                const double h = (k == 0) ? hv[0] : (k == 1) ? hv[1] : hv[2];
+                                p.out_mass[((size_t)e * n + di) * n + da] = h;
+                                p.out_mass[((size_t)e * n + da) * n + di] = h;
+                            }
                         }
                     }
                 }
@@ -1133,7 +1168,8 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
     int bad = 0;
     if constexpr (NL > 0) {
         // b[] lives in registers (the column loop is a compile-time loop); the q loop stays a runtime loop so the
-        // code stays small: column q is addressed from one base register, its pivot d_q sits on the diagonal slot.
+        // code stays small: column q is addressed from one base register (row offsets are immediates), its pivot d_q
+        // sits on the diagonal slot.
         double b[NL];
         static_for<0, NL>([&](auto ic) { b[decltype(ic)::value] = __ldg(g + (SC.rhs + decltype(ic)::value) * kTile); });
         static_for<0, NL>([&](auto jc) {
@@ -1142,11 +1178,11 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
             static_for<j, NL>([&](auto ic) { v[decltype(ic)::value - j] = tri[pd_tri(decltype(ic)::value, j, NL) * kTile]; });
 #pragma unroll 2
             for (int q = 0; q < j; ++q) {
-                const double* cq = tri + (pd_tri(q, q, NL) - q) * kTile;  // cq[i * kTile] = entry (i, q)
-                const double w = cq[j * kTile] * cq[q * kTile];           // L[j][q] d_q
+                const double* cq = tri + q * kTile;  // cq[pd_tri(i, 0) * kTile] = entry (i, q)
+                const double w = cq[pd_tri(j, 0) * kTile] * cq[pd_tri(q, 0) * kTile];  // L[j][q] d_q
                 static_for<j, NL>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
-                    v[i - j] = fma(-cq[i * kTile], w, v[i - j]);
+                    v[i - j] = fma(-cq[pd_tri(i, 0) * kTile], w, v[i - j]);
                 });
             }
             const double dj = v[0];
@@ -1320,13 +1356,9 @@ TRL_DEV void motion_index_phase(const DevModel* __restrict__ M, const double* __
 }
 
 // pose of one joint at `time` (root: with cycle offset and origin transform, anim/KinCharacter.cpp:280-315)
-TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const ModelIdx* X, const double* __restrict__ frames, int fs,
-                            int j, double time,
-                            const double* opos, const double* orot, double* out /* size[j] */) {
-    int idx;
-    double ph;
-    motion_index_phase(M, frames, fs, time, &idx, &ph);
-    const double lerp = clampd(ph, 0.0, 1.0);
+TRL_DEV void kin_joint_pose_at(const DevModel* __restrict__ M, const ModelIdx* X, const double* __restrict__ frames,
+                               int fs, int j, double time, int idx, double lerp, const double* opos, const double* orot,
+                               double* out /* size[j] */) {
     const int o = X->offset[j], sz = X->size[j];
     const double* f0 = frames + (size_t)idx * fs + 1 + o;
     const double* f1 = frames + (size_t)(idx + 1) * fs + 1 + o;
@@ -1358,8 +1390,18 @@ TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const ModelIdx* X, c
         for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + i); qb[i] = __ldg(f1 + i); }
         quat_slerp_norm(qa, lerp, qb, out);
     } else {
-        for (int i = 0; i < sz; ++i) out[i] = (1 - lerp) * __ldg(f0 + i) + lerp * __ldg(f1 + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < sz) out[i] = (1 - lerp) * __ldg(f0 + i) + lerp * __ldg(f1 + i);
     }
+}
+
+TRL_DEV void kin_joint_pose(const DevModel* __restrict__ M, const ModelIdx* X, const double* __restrict__ frames, int fs,
+                            int j, double time, const double* opos, const double* orot, double* out /* size[j] */) {
+    int idx;
+    double ph;
+    motion_index_phase(M, frames, fs, time, &idx, &ph);
+    kin_joint_pose_at(M, X, frames, fs, j, time, idx, clampd(ph, 0.0, 1.0), opos, orot, out);
 }
 
 __global__ void __launch_bounds__(128)
@@ -1470,6 +1512,106 @@ k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, 
             const double* T = Tw + 12 * j;
             const double* c = M->com[j];
             o[idx] = X->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_kin_thread: same job as k_kin<G> with ONE THREAD PER ENV: the motion frame lookup is done once per env and time
+// (not once per joint), the joints are visited in the depth-first order of ModelIdx::dfs_event and the world
+// transforms of the current root path live in a per-level shared-memory workspace ([level][12][32 lanes]).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_kin_thread(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
+             const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
+             double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kTile;
+    if (e0 >= E) return;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const int e = e0 + (env_ok ? lane : envs - 1);
+    const int N = M->N, n = M->n, fs = n + 1;
+    double* lvl = smem + (size_t)warp * (M->num_levels * 12 * kTile) + lane;  // level l, element k: lvl[(l * 12 + k) * 32]
+    const double t = time[e];
+    const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
+    double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
+    if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
+    if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
+    int idx0, idx1 = 0;
+    double ph0, ph1 = 0.0;
+    motion_index_phase(M, frames, fs, t, &idx0, &ph0);
+    const double lerp0 = clampd(ph0, 0.0, 1.0);
+    if (out_vel) motion_index_phase(M, frames, fs, t + ddt, &idx1, &ph1);
+    const double lerp1 = clampd(ph1, 0.0, 1.0);
+    const int nev = 2 * N;
+    for (int evi = 0; evi < nev; ++evi) {
+        const int j = X->dfs_event[evi];
+        if (j < 0) continue;
+        const int o = X->offset[j], sz = X->size[j];
+        const bool is_root = X->parent[j] == -1;
+        const bool sph = !is_root && X->type[j] == JT_SPHERICAL;
+        double p0[7] = {0, 0, 0, 0, 0, 0, 0};
+        kin_joint_pose_at(M, X, frames, fs, j, t, idx0, lerp0, opos, orot, p0);
+        if (env_ok) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+                if (i < sz) out_pose[(size_t)e * n + o + i] = p0[i];
+        }
+        if (out_vel) {
+            double p1[7] = {0, 0, 0, 0, 0, 0, 0}, v[7] = {0, 0, 0, 0, 0, 0, 0};
+            kin_joint_pose_at(M, X, frames, fs, j, t + ddt, idx1, lerp1, opos, orot, p1);
+            if (is_root) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+                quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
+            } else if (sph) {
+                quat_vel_rel(p0, p1, ddt, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+            }
+            if (env_ok) {
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+                    if (i < sz) out_vel[(size_t)e * n + o + i] = v[i];
+            }
+        }
+        if (out_body_pos) {
+            double R[9], tt[3], T[12];
+            joint_local_trans(X, j, p0, M->attR[j], M->attT[j], R, tt);
+            double* W = lvl + (size_t)X->level[j] * 12 * kTile;
+            if (is_root) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) T[i] = R[i];
+                T[9] = tt[0]; T[10] = tt[1]; T[11] = tt[2];
+            } else {
+                const double* Wp = W - 12 * kTile;
+                double Tp[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Tp[i] = Wp[i * kTile];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
+                    T[9 + r] = Tp[9 + r] + (Tp[r * 3] * tt[0] + Tp[r * 3 + 1] * tt[1] + Tp[r * 3 + 2] * tt[2]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) W[i * kTile] = T[i];
+            if (env_ok) {
+                const double* c = M->com[j];
+                const bool vb = X->valid_body[j] != 0;
+                double* ob = out_body_pos + ((size_t)e * N + j) * 3;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+                    ob[r] = vb ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+            }
         }
     }
 }
@@ -2200,6 +2342,17 @@ static int launch_kin_t(const DevModel* dm, const DevModel& hm, const double* fr
 int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
                    const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
                    double* out_body_pos, void* stream) {
+    static const int thread_env = env_int("TRL_KIN_THREAD", 1);  // tuning / test hook: 0 = lane-per-joint k_kin<G>
+    if (thread_env) {
+        const int wpb = 1;
+        const size_t smem = (size_t)hm.num_levels * 12 * kTile * sizeof(double) * wpb;
+        int rc = ensure_smem((const void*)k_kin_thread, smem);
+        if (rc) return rc;
+        const int tiles = (E + kTile - 1) / kTile;
+        k_kin_thread<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos,
+                                                                                      origin_rot, out_pose, out_vel, out_body_pos);
+        return (int)cudaGetLastError();
+    }
     if (hm.N <= 8) return launch_kin_t<8>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
     if (hm.N <= 16) return launch_kin_t<16>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
     return launch_kin_t<32>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
