@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -192,7 +193,7 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         // CalcGroundSamplePos in the sampling frame, same expression order as the reference
         // (TerrainRLCharController.cpp:310-319; CtController.cpp:189-211 / BipedController3D.cpp:1932-1949)
         const int G = b->cfg.num_samples;
-        std::vector<double> loc((size_t)G * 2);
+        std::vector<double> loc((size_t)G * 2 + 4);  // + [min x, max x, min z, max z] of the local sample positions
         for (int s = 0; s < G; ++s) {
             if (b->cfg.sampler == TRL_SAMPLER_LINE) {
                 loc[2 * s] = ((b->cfg.view_max - b->cfg.view_min) * s) / (G - 1) + b->cfg.view_min;
@@ -206,6 +207,14 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
                 loc[2 * s] = ox + (u - 0.5) * w;
                 loc[2 * s + 1] = 0.0 + (v - 0.5) * w;
             }
+        }
+        loc[2 * G] = loc[2 * G + 1] = loc[0];
+        loc[2 * G + 2] = loc[2 * G + 3] = loc[1];
+        for (int s = 0; s < G; ++s) {
+            loc[2 * G] = std::min(loc[2 * G], loc[2 * s]);
+            loc[2 * G + 1] = std::max(loc[2 * G + 1], loc[2 * s]);
+            loc[2 * G + 2] = std::min(loc[2 * G + 2], loc[2 * s + 1]);
+            loc[2 * G + 3] = std::max(loc[2 * G + 3], loc[2 * s + 1]);
         }
         if (!cuda_ok(cudaMalloc((void**)&b->d_sample_local, sizeof(double) * loc.size()), "cudaMalloc(samples)")) return nullptr;
         if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
@@ -373,6 +382,8 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         for (int k = 0; k < 4; ++k) pc.bounds[k] = bounds[4 * i + k];
         pc.rscale[0] = 1.0 / pc.scale[0];
         pc.rscale[1] = 1.0 / pc.scale[2];
+        pc.half[0] = (double)(pc.res_x - 1) * 0.5;
+        pc.half[1] = (double)(pc.res_z - 1) * 0.5;
     }
     if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * (size_t)data_count), "cudaMalloc(heightfields)") ||
         !cuda_ok(cudaMemcpy(b->d_ground_data, data, sizeof(float) * (size_t)data_count, cudaMemcpyHostToDevice), "H2D(heightfields)") ||

@@ -202,10 +202,10 @@ TRL_DEV double div_by_const(double x, double d, double r) {
     return __fma_rn(e1, r, q1);
 }
 
-TRL_DEV double grid_coord(double pos, double origin, double scale, double rscale, int res) {
+TRL_DEV double grid_coord(double pos, double origin, double scale, double rscale, double half /* (res - 1) * 0.5 */) {
     double c = __dsub_rn(pos, origin);
     c = div_by_const(c, scale, rscale);
-    return __dadd_rn(c, __dmul_rn((double)(res - 1), 0.5));
+    return __dadd_rn(c, half);
 }
 
 // A height sample split in two halves so callers can batch the (dependent-address) heightfield loads of several
@@ -221,8 +221,8 @@ struct SamplePrep {
 TRL_DEV void sample_prep_2d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
     const double tol = 0.0001;
     const int w = pc.res_x, l = pc.res_z;
-    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], w);
-    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], l);
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], pc.half[0]);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], pc.half[1]);
     if (c0 > -tol && c0 < w - 1 + tol && c1 > -tol && c1 < l - 1 + tol) {
         c0 = clampd(c0, 0.0, w - 1.0);
         c1 = clampd(c1, 0.0, l - 1.0);
@@ -252,8 +252,8 @@ TRL_DEV double sample_finish_2d(const SamplePrep& sp, float f0, float f1) {
 TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
     const double tol = 0.0001;
     const int rx = pc.res_x, rz = pc.res_z;
-    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], rx);
-    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], rz);
+    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], pc.half[0]);
+    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], pc.half[1]);
     c0 = clampd(c0, 0.0, rx - 1.0 - tol);
     c1 = clampd(c1, 0.0, rz - 1.0 - tol);
     const int i = (int)c0, j = (int)c1;

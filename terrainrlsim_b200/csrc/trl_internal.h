@@ -90,6 +90,7 @@ struct DevPiece {
     double scale[3];
     double bounds[4];
     double rscale[2];  // correctly-rounded 1/scale_x, 1/scale_z (host IEEE division) for div_by_const
+    double half[2];    // (res_x - 1) * 0.5, (res_z - 1) * 0.5 (exact products)
 };
 
 struct DevGround {

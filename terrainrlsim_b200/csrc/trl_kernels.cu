@@ -1914,6 +1914,8 @@ struct ObsEnvRec {
     double i00, i02, i20, i22, it0, it1, it2;
     int flip;
     int pad;
+    int piece;  // >= 0: every ground sample of this env falls into this terrain piece (and into no earlier one)
+    int pad2;
 };
 
 // k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env.
@@ -1925,7 +1927,8 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
           const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
           const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
           const double* __restrict__ ground_vel, const double* __restrict__ phase,
-          const unsigned char* __restrict__ flip_arr, ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+          const unsigned char* __restrict__ flip_arr, const double* __restrict__ sample_local,
+          ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
     __shared__ ModelIdx s_ix;
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;
@@ -1978,6 +1981,45 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         ObsEnvRec r;
         r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
         r.flip = flip; r.pad = has_ground ? 1 : 0;
+        r.piece = -1;
+        r.pad2 = 0;
+        if ((gkind == 1 || gkind == 2) && cfg.num_samples > 0 && sample_local) {
+            // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
+            // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
+            // box is widened by a few ulps because the sample kernel may contract the same expression differently.
+            const double* bb = sample_local + 2 * cfg.num_samples;
+            const double lx[2] = {__ldg(bb), __ldg(bb + 1)};
+            double lz[2] = {__ldg(bb + 2), __ldg(bb + 3)};
+            if (flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D)) {
+                const double t = lz[0];
+                lz[0] = -lz[1];
+                lz[1] = -t;
+            }
+            double x0 = CUDART_INF, x1 = -CUDART_INF, z0 = CUDART_INF, z1 = -CUDART_INF;
+            bool finite = true;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double px = i00 * lx[a] + i02 * lz[b] + it0;
+                    const double pz = i20 * lx[a] + i22 * lz[b] + it2;
+                    finite = finite && isfinite(px) && isfinite(pz);
+                    x0 = fmin(x0, px); x1 = fmax(x1, px);
+                    z0 = fmin(z0, pz); z1 = fmax(z1, pz);
+                }
+            const double ex = 1e-12 * (fabs(x0) + fabs(x1) + 1.0), ez = 1e-12 * (fabs(z0) + fabs(z1) + 1.0);
+            x0 -= ex; x1 += ex; z0 -= ez; z1 += ez;
+            if (finite) {
+                const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
+                for (int s = 0; s < gP; ++s) {
+                    const double b0 = pcs[s].bounds[0], b1 = pcs[s].bounds[1], b2 = pcs[s].bounds[2], b3 = pcs[s].bounds[3];
+                    const bool inside = (gkind == 1) ? (x0 >= b0 && x1 <= b1) : (x0 >= b0 && x1 <= b1 && z0 >= b2 && z1 <= b3);
+                    const bool apart = (gkind == 1) ? (x1 < b0 || x0 > b1) : (x1 < b0 || x0 > b1 || z1 < b2 || z0 > b3);
+                    if (inside) { r.piece = s; break; }
+                    if (!apart) break;  // straddles this piece: per-sample search
+                }
+            }
+        }
         rec[e] = r;
     }
     if (!env_ok) return;
@@ -2083,7 +2125,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
 
 // k_obs_samples: ParseGround's sample loop -- one thread per (env, sample); block = one env, so the env's record and
 // terrain piece descriptors are staged once in shared memory and every thread is an independent load chain.
-template <int KIND>  // ground kind (1 = var2d, 2 = var3d, 0/3 = none/plane) as a compile-time constant
+template <int KIND, bool WANT_CELL>  // ground kind (1 = var2d, 2 = var3d, 0/3 = none/plane) as a compile-time constant
 __global__ void __launch_bounds__(256)
 k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
               const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
@@ -2119,10 +2161,16 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
             const double px = s_rec.i00 * lx + oz * 0.0 + s_rec.i02 * lz + s_rec.it0;
             const double pz = s_rec.i20 * lx + oz * 0.0 + s_rec.i22 * lz + s_rec.it2;
             int vs;
-            hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+            if (gkind == 1 || gkind == 2) {
+                const int up = s_rec.piece;  // block-uniform
+                const int pi = (up >= 0) ? up : ground_find_piece(gkind, gP, s_pieces, px, pz);
+                hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - s_rec.it1;
+            } else {
+                hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+            }
         }
         out[s] = hs;
-        if (out_cell) {
+        if (WANT_CELL && out_cell) {
             int* oc = out_cell + ((size_t)e * G + s) * 3;
             oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
         }
@@ -2398,17 +2446,21 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
     const long long threads = (long long)E * kObsG;
     const int blocks = (int)((threads + 127) / 128);
     k_obs_env<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel, body_quat,
-                                                        body_angvel, ground_vel, phase, flip, (ObsEnvRec*)env_rec,
-                                                        out_state);
+                                                        body_angvel, ground_vel, phase, flip, sample_local,
+                                                        (ObsEnvRec*)env_rec, out_state);
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
     const int tpb = cfg.num_samples >= 192 ? 256 : (cfg.num_samples >= 96 ? 128 : 64);
     const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g.kind == 1) k_obs_samples<1><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
-    else if (g.kind == 2) k_obs_samples<2><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
-    else if (g.kind == 3) k_obs_samples<3><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
-    else k_obs_samples<0><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+#define TRL_OBS_LAUNCH(K)                                                                                        \
+    if (out_cell) k_obs_samples<K, true><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);    \
+    else k_obs_samples<K, false><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+    if (g.kind == 1) { TRL_OBS_LAUNCH(1) }
+    else if (g.kind == 2) { TRL_OBS_LAUNCH(2) }
+    else if (g.kind == 3) { TRL_OBS_LAUNCH(3) }
+    else { TRL_OBS_LAUNCH(0) }
+#undef TRL_OBS_LAUNCH
     return (int)cudaGetLastError();
 }
 
