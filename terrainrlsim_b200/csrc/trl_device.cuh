@@ -181,10 +181,10 @@ TRL_DEV void joint_local_trans(const ModelIdx* X, int j, const double* q /* join
 // ---- heightfield sampling. Index arithmetic uses explicit round-to-nearest intrinsics so that nvcc never
 // contracts it into FMAs: cell indices must be bit-exact with the reference's double expression
 // (sim/GroundVar2D.cpp:652-681, GroundVar3D.cpp:602-621; SURVEY.md "Bit-exact terrain indices"). ----
-TRL_DEV double clampd(double v, double lo, double hi) {
-    double t = (v < hi) ? v : hi;
-    return (lo < t) ? t : lo;
-}
+// (v < hi ? v : hi) then (lo < t ? t : lo): NaN -> hi. fmin / fmax (one DMNMX each) give the same values: fmin(NaN, hi)
+// = hi, and the only other difference (which zero comes back when v = -0.0 and lo = +0.0) never changes a result
+// here: every caller converts the value to a cell index or subtracts an integer from it.
+TRL_DEV double clampd(double v, double lo, double hi) { return fmax(lo, fmin(v, hi)); }
 
 // Correctly-rounded x / d from the correctly-rounded reciprocal r = RN(1/d) (computed once per piece on the host):
 // Markstein's FMA sequence -- q0 = RN(x r) is within 2 ulp, one residual correction makes it faithful, and a second
@@ -193,8 +193,9 @@ TRL_DEV double clampd(double v, double lo, double hi) {
 // of the ~35 of a full IEEE division; bit-identical to `x / d` for normal-range operands, which is asserted over 1e7
 // random operands in tests/test_gpu_parity.py. Outside the safe range (inf, NaN, tiny, huge) it falls back to __ddiv_rn.
 TRL_DEV double div_by_const(double x, double d, double r) {
-    const double ax = fabs(x);
-    if (!(ax > 1e-200 && ax < 1e200)) return __ddiv_rn(x, d);
+    // safe range test on the exponent field (integer pipe, not FP64): 2^-600 < |x| < 2^600; zero, subnormal, inf, NaN fail
+    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu;
+    if (ex - 423u > 1200u) return __ddiv_rn(x, d);
     const double q0 = __dmul_rn(x, r);
     const double e0 = __fma_rn(-q0, d, x);
     const double q1 = __fma_rn(e0, r, q0);
@@ -259,13 +260,12 @@ TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, Sam
     const int i = (int)c0, j = (int)c1;
     const double lx = __dsub_rn(c0, (double)i), lz = __dsub_rn(c1, (double)j);
     const bool lower = (lz <= lx);
-    const int i0 = lower ? i : i + 1, j0 = lower ? j : j + 1;
-    const int i1 = lower ? i + 1 : i, j1 = lower ? j : j + 1;
-    const int i2 = lower ? i + 1 : i, j2 = lower ? j + 1 : j;
-    const unsigned int base = (unsigned int)pc.data_offset;  // < 2^32 floats (checked at registration)
-    sp.o0 = base + (unsigned int)(j0 * rx + i0);
-    sp.o1 = base + (unsigned int)(j1 * rx + i1);
-    sp.o2 = base + (unsigned int)(j2 * rx + i2);
+    // lower triangle: (i, j), (i+1, j), (i+1, j+1); upper: (i+1, j+1), (i, j+1), (i, j)
+    const unsigned int base = (unsigned int)pc.data_offset + (unsigned int)(j * rx + i);  // < 2^32 floats (checked at registration)
+    const unsigned int diag = base + (unsigned int)rx + 1u;
+    sp.o0 = lower ? base : diag;
+    sp.o1 = lower ? base + 1u : base + (unsigned int)rx;
+    sp.o2 = lower ? diag : base;
     // cMathUtil::CalcBarycentric (util/MathUtil.cpp:630-647) on the two unit triangles. With a = (0,0), b = (1,0),
     // c = (1,1) (lower) or a = (1,1), b = (0,1), c = (0,0) (upper) the general expression has d00 = d01 = 1,
     // d11 = 2, denom = 1 exactly, so every product by them and the division are exact and the reference's

@@ -18,6 +18,7 @@
 // Everything is expressed in the root-joint frame: there, parent->child transforms are pure additions
 // for composite inertias and forces, so the only level-serial work is the 3x4 transform composition
 // and a 6-vector recurrence. Numbers agree with the reference's joint-local formulation to ~1e-13.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -1915,7 +1916,7 @@ struct ObsEnvRec {
     int flip;
     int pad;
     int piece;  // >= 0: every ground sample of this env falls into this terrain piece (and into no earlier one)
-    int pad2;
+    int pad2, pad3, pad4;  // sizeof % 16 == 0 (staged with 16-byte copies)
 };
 
 // k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env.
@@ -1982,7 +1983,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
         r.flip = flip; r.pad = has_ground ? 1 : 0;
         r.piece = -1;
-        r.pad2 = 0;
+        r.pad2 = r.pad3 = r.pad4 = 0;
         if ((gkind == 1 || gkind == 2) && cfg.num_samples > 0 && sample_local) {
             // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
             // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
@@ -2123,56 +2124,63 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     }
 }
 
-// k_obs_samples: ParseGround's sample loop -- one thread per (env, sample); block = one env, so the env's record and
-// terrain piece descriptors are staged once in shared memory and every thread is an independent load chain.
+// k_obs_samples: ParseGround's sample loop -- block = one env, kObsSPT samples per thread (independent load chains the
+// compiler interleaves). The env's record and terrain piece descriptors are staged once in shared memory.
+constexpr int kObsSPT = 4;
 template <int KIND, bool WANT_CELL>  // ground kind (1 = var2d, 2 = var3d, 0/3 = none/plane) as a compile-time constant
 __global__ void __launch_bounds__(256)
 k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
               const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
-    __shared__ DevPiece s_pieces[4];
-    __shared__ ObsEnvRec s_rec;
+    static_assert(sizeof(DevPiece) % 16 == 0 && sizeof(ObsEnvRec) % 16 == 0, "staged with 16-byte copies");
+    __shared__ __align__(16) DevPiece s_pieces[4];
+    __shared__ __align__(16) ObsEnvRec s_rec;
     const int e = blockIdx.x;
     const int G = cfg.num_samples;
     constexpr int gkind = KIND;
     const int gP = g.pieces_per_field;
-    if (gkind == 1 || gkind == 2) {
-        const int words = gP * (int)(sizeof(DevPiece) / 8);
-        if ((int)threadIdx.x < words) {
-            const unsigned long long* src =
-                reinterpret_cast<const unsigned long long*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
-            reinterpret_cast<unsigned long long*>(s_pieces)[threadIdx.x] = __ldg(src + threadIdx.x);
+    {
+        constexpr int kRecW = (int)(sizeof(ObsEnvRec) / 16);
+        const int pw = (gkind == 1 || gkind == 2) ? gP * (int)(sizeof(DevPiece) / 16) : 0;
+        for (int t = threadIdx.x; t < pw + kRecW; t += blockDim.x) {
+            if (t < pw) {
+                const uint4* src = reinterpret_cast<const uint4*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
+                reinterpret_cast<uint4*>(s_pieces)[t] = __ldg(src + t);
+            } else {
+                reinterpret_cast<uint4*>(&s_rec)[t - pw] = __ldg(reinterpret_cast<const uint4*>(rec + e) + (t - pw));
+            }
         }
     }
-    if (threadIdx.x < (int)(sizeof(ObsEnvRec) / 8))
-        reinterpret_cast<unsigned long long*>(&s_rec)[threadIdx.x] =
-            __ldg(reinterpret_cast<const unsigned long long*>(rec + e) + threadIdx.x);
     __syncthreads();
-    const bool is_ct = (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
+    const bool flip_z = s_rec.flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
     const bool has_ground = gkind != 0;
     const double oz = 0.0;
     double* out = out_state + (size_t)e * F;
-    for (int s = threadIdx.x; s < G; s += blockDim.x) {
-        double hs = 0.0;
-        int cell[3] = {-1, 0, 0};
-        if (has_ground) {
-            const double lx = __ldg(sample_local + 2 * s);
-            double lz = __ldg(sample_local + 2 * s + 1);
-            if (s_rec.flip && is_ct) lz = -lz;
-            const double px = s_rec.i00 * lx + oz * 0.0 + s_rec.i02 * lz + s_rec.it0;
-            const double pz = s_rec.i20 * lx + oz * 0.0 + s_rec.i22 * lz + s_rec.it2;
-            int vs;
-            if (gkind == 1 || gkind == 2) {
-                const int up = s_rec.piece;  // block-uniform
-                const int pi = (up >= 0) ? up : ground_find_piece(gkind, gP, s_pieces, px, pz);
-                hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - s_rec.it1;
-            } else {
-                hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+    const int up = s_rec.piece;  // block-uniform: >= 0 when every sample of this env lies in that piece
+    for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
+#pragma unroll
+        for (int k = 0; k < kObsSPT; ++k) {
+            const int s = s0 + k * blockDim.x;
+            if (s >= G) break;
+            double hs = 0.0;
+            int cell[3] = {-1, 0, 0};
+            if (has_ground) {
+                const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
+                const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
+                const double px = s_rec.i00 * lx + oz * 0.0 + s_rec.i02 * lz + s_rec.it0;
+                const double pz = s_rec.i20 * lx + oz * 0.0 + s_rec.i22 * lz + s_rec.it2;
+                int vs;
+                if (gkind == 1 || gkind == 2) {
+                    const int pi = (up >= 0) ? up : ground_find_piece(gkind, gP, s_pieces, px, pz);
+                    hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - s_rec.it1;
+                } else {
+                    hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+                }
             }
-        }
-        out[s] = hs;
-        if (WANT_CELL && out_cell) {
-            int* oc = out_cell + ((size_t)e * G + s) * 3;
-            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+            out[s] = hs;
+            if (WANT_CELL && out_cell) {
+                int* oc = out_cell + ((size_t)e * G + s) * 3;
+                oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+            }
         }
     }
 }
@@ -2450,7 +2458,7 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                                                         (ObsEnvRec*)env_rec, out_state);
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
-    const int tpb = cfg.num_samples >= 192 ? 256 : (cfg.num_samples >= 96 ? 128 : 64);
+    const int tpb = std::min(256, std::max(32, ((cfg.num_samples + kObsSPT - 1) / kObsSPT + 31) / 32 * 32));
     const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
     cudaStream_t st = (cudaStream_t)stream;
 #define TRL_OBS_LAUNCH(K)                                                                                        \
