@@ -2155,32 +2155,47 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
     const bool has_ground = gkind != 0;
     const double oz = 0.0;
     double* out = out_state + (size_t)e * F;
-    const int up = s_rec.piece;  // block-uniform: >= 0 when every sample of this env lies in that piece
-    for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
+    const ObsEnvRec r = s_rec;   // registers
+    const int up = r.piece;      // block-uniform: >= 0 when every sample of this env lies in that piece
+    if ((gkind == 1 || gkind == 2) && up >= 0) {
+        // fast path: one piece for the whole env -- its descriptor is read once into registers, no per-sample search
+        const DevPiece pc = s_pieces[up];
+        for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
 #pragma unroll
-        for (int k = 0; k < kObsSPT; ++k) {
-            const int s = s0 + k * blockDim.x;
-            if (s >= G) break;
-            double hs = 0.0;
-            int cell[3] = {-1, 0, 0};
-            if (has_ground) {
+            for (int k = 0; k < kObsSPT; ++k) {
+                const int s = s0 + k * blockDim.x;
+                if (s >= G) break;
                 const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
                 const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
-                const double px = s_rec.i00 * lx + oz * 0.0 + s_rec.i02 * lz + s_rec.it0;
-                const double pz = s_rec.i20 * lx + oz * 0.0 + s_rec.i22 * lz + s_rec.it2;
-                int vs;
-                if (gkind == 1 || gkind == 2) {
-                    const int pi = (up >= 0) ? up : ground_find_piece(gkind, gP, s_pieces, px, pz);
-                    hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - s_rec.it1;
-                } else {
-                    hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - s_rec.it1;
+                const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
+                const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
+                int vs, cell[3];
+                const double hs = ((gkind == 1) ? sample_segment_2d(pc, g.data, up, px, pz, &vs, cell)
+                                                : sample_slab_3d(pc, g.data, up, px, pz, &vs, cell)) - r.it1;
+                out[s] = hs;
+                if (WANT_CELL && out_cell) {
+                    int* oc = out_cell + ((size_t)e * G + s) * 3;
+                    oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
                 }
             }
-            out[s] = hs;
-            if (WANT_CELL && out_cell) {
-                int* oc = out_cell + ((size_t)e * G + s) * 3;
-                oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
-            }
+        }
+        return;
+    }
+    for (int s = threadIdx.x; s < G; s += blockDim.x) {  // general path: the env straddles pieces (or has no heightfield)
+        double hs = 0.0;
+        int cell[3] = {-1, 0, 0};
+        if (has_ground) {
+            const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
+            const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
+            const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
+            const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
+            int vs;
+            hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - r.it1;
+        }
+        out[s] = hs;
+        if (WANT_CELL && out_cell) {
+            int* oc = out_cell + ((size_t)e * G + s) * 3;
+            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
         }
     }
 }
