@@ -125,6 +125,12 @@ int trl_batch_num_envs(const trl_batch* b);
 /* number of this library's kernel launches issued through this batch so far */
 long long trl_batch_launch_count(const trl_batch* b);
 
+/* Diagnostics: kernel timeline of everything launched while enabled (process-wide, current device). `out32` receives
+ * 16 pairs (first block start, last block end) in GPU-timer nanoseconds -- slot 0 k_imp_pd, 1 k_pd_tree, 2 k_pd_h,
+ * 3 k_pd_solve, 4 k_kin_thread, 5 k_obs_env, 6 k_obs_samples; untouched slots hold (2^64-1, 0). Reading re-arms it. */
+int trl_debug_trace_enable(int on);
+int trl_debug_trace_read(unsigned long long* out32);
+
 /* ------------------------------------------------------------------------------------------
  * (1) stable PD
  *   cRBDModel::Update(pose, vel)                         sim/RBDModel.cpp:39-55

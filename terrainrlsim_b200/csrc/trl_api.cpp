@@ -55,8 +55,8 @@ struct trl_batch {
     cudaStream_t stream = nullptr;
     // fork/join plumbing of trl_step_fused: the three independent kernel chains of a step (stable PD | kin-char + FK |
     // observation) run concurrently on the main stream and two side streams (captured as parallel graph branches)
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr}, ev_pv = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // kin chain, observation chain, stable-PD chain (highest priority)
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_pv = nullptr;
     int overlap = 1;
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
@@ -172,13 +172,20 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     Guard g(device);
     if (!cuda_ok(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
     b->stream = b->own_stream;
-    for (int i = 0; i < 2; ++i) {
-        if (!cuda_ok(cudaStreamCreateWithFlags(&b->side[i], cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
+    // Block-scheduling priorities: the stable-PD chain is the longest dependent chain of the fused step (three
+    // kernels back to back), so its kernels must not queue behind the thousands of blocks of the observation kernels.
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+    for (int i = 0; i < 3; ++i) {
+        const int prio = (i == 2) ? prio_hi : (i == 0 ? (prio_lo + prio_hi) / 2 : prio_lo);
+        if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     }
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
+        static const int carve = getenv("TRL_CARVEOUT") ? atoi(getenv("TRL_CARVEOUT")) : -1;  // tuning hook, see trl_set_carveout
+        if (carve >= 0 && trl_set_carveout(carve) != 0) { trl_set_error("cudaFuncSetAttribute(carveout) failed"); return nullptr; }
         const char* ov = getenv("TRL_STEP_OVERLAP");  // tuning hook: 0 serialises the chains on one stream
         if (ov) b->overlap = atoi(ov) != 0;
     }
@@ -246,7 +253,7 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     if (b->d_ground_data) cudaFree(b->d_ground_data);
     if (b->d_pieces) cudaFree(b->d_pieces);
     if (b->d_env_to_field) cudaFree(b->d_env_to_field);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (b->side[i]) { cudaStreamSynchronize(b->side[i]); cudaStreamDestroy(b->side[i]); }
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
     }
@@ -277,6 +284,8 @@ extern "C" int trl_batch_sync(trl_batch* b) {
 extern "C" int trl_poli_state_size(const trl_batch* b) { return b ? b->F : TRL_ERR_INVALID_ARG; }
 extern "C" int trl_batch_num_envs(const trl_batch* b) { return b ? b->E : TRL_ERR_INVALID_ARG; }
 extern "C" long long trl_batch_launch_count(const trl_batch* b) { return b ? b->launches : 0; }
+extern "C" int trl_debug_trace_enable(int on) { return trl_trace_enable(on) == 0 ? TRL_OK : TRL_ERR_CUDA; }
+extern "C" int trl_debug_trace_read(unsigned long long* out32) { return trl_trace_read(out32) == 0 ? TRL_OK : TRL_ERR_INVALID_ARG; }
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int trl_imp_pd_update_control_force(trl_batch* b, double dt, const double* pose, const double* vel,
@@ -484,8 +493,8 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     p.tau_accumulate = 0;
     p.status = b->d_status;
 
-    // Three independent chains: (A) stable PD on the main stream, (B) kin-char pose + FK, (C) observation. With
-    // overlap on, B and C fork onto side streams and join before returning. In HOST pointer mode every chain also
+    // Three independent chains: (A) stable PD, (B) kin-char pose + FK, (C) observation. With overlap on they fork
+    // onto the batch's side streams (A on the high-priority one) and join the caller's stream before returning. In HOST pointer mode every chain also
     // stages its own inputs and copies its own outputs back on its stream, so H2D, kernels and D2H of different
     // chains overlap (the observation chain, whose [E][F] state is the largest transfer, goes first).
     const bool fork = b->overlap && ((want_pd ? 1 : 0) + (want_kin ? 1 : 0) + (want_obs ? 1 : 0)) > 1;
@@ -494,6 +503,7 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
         if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
         if (want_kin && (want_pd || want_obs)) { sB = b->side[0]; cudaStreamWaitEvent(sB, b->ev_fork, 0); }
         if (want_obs && want_pd) { sC = b->side[1]; cudaStreamWaitEvent(sC, b->ev_fork, 0); }
+        if (want_pd) { sA = b->side[2]; cudaStreamWaitEvent(sA, b->ev_fork, 0); }
     }
     const double *d_time = nullptr, *d_op = nullptr, *d_or = nullptr, *d_bp = nullptr, *d_bv = nullptr, *d_ph = nullptr;
     const unsigned char* d_fl = nullptr;
@@ -552,6 +562,7 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (fork) {  // join (also on error, so the streams stay consistent / a capture stays closed)
         if (sB != b->stream) { cudaEventRecord(b->ev_join[0], sB); cudaStreamWaitEvent(b->stream, b->ev_join[0], 0); }
         if (sC != b->stream) { cudaEventRecord(b->ev_join[1], sC); cudaStreamWaitEvent(b->stream, b->ev_join[1], 0); }
+        if (sA != b->stream) { cudaEventRecord(b->ev_join[2], sA); cudaStreamWaitEvent(b->stream, b->ev_join[2], 0); }
     }
     return finish(b, copies, rc);
 }

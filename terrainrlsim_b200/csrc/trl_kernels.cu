@@ -28,6 +28,28 @@
 
 namespace {
 
+// ---- optional kernel timeline (trl_debug_trace_*): first block start / last block end per kernel, %globaltimer ns ----
+__device__ unsigned long long* g_trace = nullptr;  // [kTraceSlots][2] or null (tracing off: one uniform load per block)
+constexpr int kTraceSlots = 16;
+enum { TR_IMP_PD = 0, TR_PD_TREE, TR_PD_H, TR_PD_SOLVE, TR_KIN, TR_OBS_ENV, TR_OBS_SAMPLES, TR_FK, TR_KIN_CHAR, TR_REWARD };
+struct KTrace {
+    int id;
+    __device__ __forceinline__ explicit KTrace(int id_) : id(id_) {
+        if (threadIdx.x == 0 && g_trace) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMin(&g_trace[2 * id], t);
+        }
+    }
+    __device__ __forceinline__ ~KTrace() {
+        if (threadIdx.x == 0 && g_trace) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            atomicMax(&g_trace[2 * id + 1], t);
+        }
+    }
+};
+
 constexpr int kWarpsPerBlock = 4;
 #ifndef TRL_PD_MIN_BLOCKS
 #define TRL_PD_MIN_BLOCKS 4
@@ -88,14 +110,17 @@ __host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, b
 // thread per env) reads it with fully coalesced loads / one bulk copy per tile. Per env (doubles):
 //   [Hp: nl(nl+1)/2 row-packed lower triangle of M + dt*Kd][rhs: nl][t0: n][t1: n]   tau_i = t0_i - t1_i * qdd_col(i)
 constexpr int kTile = 32;
-struct PdScratch { int np, rhs, t0, t1, stride; };
+//   [S: 6 nl joint-subspace columns][F: 6 nl force columns F_c = Ic S_c]   (k_pd_tree -> k_pd_h: H[c][a] = F_c . S_a)
+struct PdScratch { int np, rhs, t0, t1, scol, fcol, stride; };
 __host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
     PdScratch s;
     s.np = nl * (nl + 1) / 2;
     s.rhs = s.np;
     s.t0 = s.rhs + nl;
     s.t1 = s.t0 + n;
-    s.stride = (s.t1 + n + 1) & ~1;
+    s.scol = s.t1 + n;
+    s.fcol = s.scol + 6 * nl;
+    s.stride = (s.fcol + 6 * nl + 1) & ~1;
     return s;
 }
 // entry (i, j), i >= j, of the row-packed lower triangle
@@ -283,6 +308,7 @@ TRL_DEV int ldlt_solve_smem(double* H, int ldh, double* x, int nl, int lane) {
 template <int G, int NLMAX, bool SPLIT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, TRL_PD_MIN_BLOCKS)
 k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
+    KTrace trace_(TR_IMP_PD);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
     {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
@@ -746,6 +772,7 @@ TRL_DEV void tree_subspace(int kind, int a, const double* T /* [(k) * 32] stride
 
 __global__ void __launch_bounds__(128)
 k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
+    KTrace trace_(TR_PD_TREE);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
     {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
@@ -1020,80 +1047,37 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
             for (int i = 0; i < 6; ++i) f[i] = W[(kSlotF + i) * kTile];
             const double kdu = W[kSlotKd * kTile];
             const int c0 = X->first_col[j], nc = X->ncol[j];
-            // columns of the joint in groups of <= 3 (a joint has 1, 3 or, for the root, 6): the group's force columns
-            // F_c stay in registers while the ancestor chain is walked once, one subspace column S_a per step.
-            for (int cb = c0; cb < c0 + nc; cb += 3) {
-                const int cnt = min(3, c0 + nc - cb);
-                double sv[3][6], Fc[3][6];
+            // per column: bias force, rhs, diagonal of H; S_c and F_c = Ic S_c go to the scratch -- the off-diagonal
+            // entries H[c][a] = F_c . S_a (a on the ancestor chain) are formed by k_pd_h with (env x column) parallelism
+            for (int c = c0; c < c0 + nc; ++c) {
+                double sv[6], Fc[6];
+                tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv);
+                const double m = I[0];
+                const double* h = I + 1;
+                double hxv[3], hxw[3];
+                cross3(h, sv + 3, hxv);
+                cross3(h, sv, hxw);
+                Fc[0] = I[4] * sv[0] + I[5] * sv[1] + I[6] * sv[2] + hxv[0];
+                Fc[1] = I[5] * sv[0] + I[7] * sv[1] + I[8] * sv[2] + hxv[1];
+                Fc[2] = I[6] * sv[0] + I[8] * sv[1] + I[9] * sv[2] + hxv[2];
+                Fc[3] = m * sv[3] - hxw[0];
+                Fc[4] = m * sv[4] - hxw[1];
+                Fc[5] = m * sv[5] - hxw[2];
+                const double Cc = (sv[0] * f[0] + sv[1] * f[1] + sv[2] * f[2]) + (sv[3] * f[3] + sv[4] * f[4] + sv[5] * f[5]);
+                const double hd = (Fc[0] * sv[0] + Fc[1] * sv[1] + Fc[2] * sv[2]) + (Fc[3] * sv[3] + Fc[4] * sv[4] + Fc[5] * sv[5]);
+                const int di = X->col_dof[c];
+                const int ui = di - o;
+                const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
+                if (env_ok) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int c = cb + (k < cnt ? k : 0);
-                    tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv[k]);
-                    const double m = I[0];
-                    const double* h = I + 1;
-                    double hxv[3], hxw[3];
-                    cross3(h, sv[k] + 3, hxv);
-                    cross3(h, sv[k], hxw);
-                    Fc[k][0] = I[4] * sv[k][0] + I[5] * sv[k][1] + I[6] * sv[k][2] + hxv[0];
-                    Fc[k][1] = I[5] * sv[k][0] + I[7] * sv[k][1] + I[8] * sv[k][2] + hxv[1];
-                    Fc[k][2] = I[6] * sv[k][0] + I[8] * sv[k][1] + I[9] * sv[k][2] + hxv[2];
-                    Fc[k][3] = m * sv[k][3] - hxw[0];
-                    Fc[k][4] = m * sv[k][4] - hxw[1];
-                    Fc[k][5] = m * sv[k][5] - hxw[2];
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k < cnt) {
-                        const int c = cb + k;
-                        const double Cc = sv[k][0] * f[0] + sv[k][1] * f[1] + sv[k][2] * f[2] + sv[k][3] * f[3] +
-                                          sv[k][4] * f[4] + sv[k][5] * f[5];
-                        const int di = X->col_dof[c];
-                        const int ui = di - o;
-                        const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
-                        if (env_ok) {
-                            sc[(SC.rhs + c) * kTile] = u - Cc;
-                            if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
-                        }
-#pragma unroll
-                        for (int k2 = 0; k2 <= k; ++k2) {  // pairs inside the group (col_parent of a joint's column = previous one)
-                            double hv = (Fc[k][0] * sv[k2][0] + Fc[k][1] * sv[k2][1] + Fc[k][2] * sv[k2][2]) +
-                                        (Fc[k][3] * sv[k2][3] + Fc[k][4] * sv[k2][4] + Fc[k][5] * sv[k2][5]);
-                            if (env_ok) {
-                                if (p.out_mass) {
-                                    const int da = X->col_dof[cb + k2];
-                                    p.out_mass[((size_t)e * n + di) * n + da] = hv;
-                                    p.out_mass[((size_t)e * n + da) * n + di] = hv;
-                                }
-                                if (k2 == k) hv += dt * kdu;
-                                sc[pd_tri(c, cb + k2) * kTile] = hv;
-                            }
-                        }
+                    for (int k = 0; k < 6; ++k) {
+                        sc[(SC.scol + 6 * c + k) * kTile] = sv[k];
+                        sc[(SC.fcol + 6 * c + k) * kTile] = Fc[k];
                     }
-                }
-                const int r0 = pd_tri(cb, 0), r1 = pd_tri(cb + 1, 0), r2 = pd_tri(cb + 2, 0);
-                for (int a = X->col_parent[cb]; a >= 0; a = X->col_parent[a]) {
-                    const int ja = X->col_joint[a];
-                    double sa[6];
-                    tree_subspace(X->col_kind[a], X->col_axis[a], lvl + ((size_t)X->level[ja] * kSlot + kSlotT) * kTile, Rq, sa);
-                    double hv[3];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        hv[k] = (Fc[k][0] * sa[0] + Fc[k][1] * sa[1] + Fc[k][2] * sa[2]) +
-                                (Fc[k][3] * sa[3] + Fc[k][4] * sa[4] + Fc[k][5] * sa[5]);
-                    if (env_ok) {
-                        sc[(r0 + a) * kTile] = hv[0];
-                        if (cnt > 1) sc[(r1 + a) * kTile] = hv[1];
-                        if (cnt > 2) sc[(r2 + a) * kTile] = hv[2];
-                        if (p.out_mass) {
-                            const int da = X->col_dof[a];
-                            for (int k = 0; k < cnt; ++k) {
-                                const int di = X->col_dof[cb + k];
-                                const double h = (k == 0) ? hv[0] : (k == 1) ? hv[1] : hv[2];
-                                p.out_mass[((size_t)e * n + di) * n + da] = h;
-                                p.out_mass[((size_t)e * n + da) * n + di] = h;
-                            }
-                        }
-                    }
+                    sc[(SC.rhs + c) * kTile] = u - Cc;
+                    sc[pd_tri(c, c) * kTile] = hd + dt * kdu;
+                    if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
+                    if (p.out_mass) p.out_mass[((size_t)e * n + di) * n + di] = hd;
                 }
             }
             if (lv > 0) {
@@ -1106,6 +1090,49 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
     if (p.out_bias && env_ok) {  // dead dofs are exact zeros
         for (int i = 0; i < n; ++i)
             if (X->dof_col[i] < 0) p.out_bias[(size_t)e * n + i] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pd_h: off-diagonal entries of H = M + dt*Kd from the columns k_pd_tree left in the scratch: H[c][a] = F_c . S_a
+// for every a on the ancestor chain of c (Featherstone's branch-induced sparsity; the other entries stay zero).
+// One warp per (tile of 32 envs, column c), lane = env: all loads / stores are 256-byte coalesced rows of the tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHWarps = 8;
+__global__ void __launch_bounds__(kHWarps * 32)
+k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, double* __restrict__ out_mass) {
+    KTrace trace_(TR_PD_H);
+    extern __shared__ double smem[];  // the tile's subspace columns S: [6 nl][32]
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = M->n, nl = M->nl;
+    const int tile = blockIdx.x;
+    const PdScratch SC = pd_scratch(n, nl);
+    double* g = scratch + (size_t)tile * SC.stride * kTile;
+    for (int i = threadIdx.x; i < 6 * nl * kTile; i += blockDim.x) smem[i] = g[SC.scol * kTile + i];
+    __syncthreads();
+    double* sc = g + lane;
+    const double* Ss = smem + lane;
+    const int e = tile * kTile + lane;
+    const bool env_ok = e < E;
+    for (int c = warp; c < nl; c += kHWarps) {
+        double F[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) F[k] = sc[(SC.fcol + 6 * c + k) * kTile];
+        const int row = pd_tri(c, 0);
+        for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
+            const double* S = Ss + 6 * a * kTile;
+            const double hv = (F[0] * S[0] + F[1] * S[kTile] + F[2] * S[2 * kTile]) +
+                              (F[3] * S[3 * kTile] + F[4] * S[4 * kTile] + F[5] * S[5 * kTile]);
+            sc[(row + a) * kTile] = hv;
+            if (out_mass && env_ok) {
+                const int di = X->col_dof[c], da = X->col_dof[a];
+                out_mass[((size_t)e * n + di) * n + da] = hv;
+                out_mass[((size_t)e * n + da) * n + di] = hv;
+            }
+        }
     }
 }
 
@@ -1150,6 +1177,7 @@ template <int NL>
 __global__ void __launch_bounds__(128)
 k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
            int tau_accumulate, int* __restrict__ status) {
+    KTrace trace_(TR_PD_SOLVE);
     extern __shared__ __align__(16) double smem[];
     __shared__ ModelIdx s_ix;
     __shared__ unsigned long long s_bar[4];
@@ -1363,13 +1391,20 @@ TRL_DEV void kin_joint_pose_at(const DevModel* __restrict__ M, const ModelIdx* X
     const int o = X->offset[j], sz = X->size[j];
     const double* f0 = frames + (size_t)idx * fs + 1 + o;
     const double* f1 = frames + (size_t)(idx + 1) * fs + 1 + o;
-    if (j == 0) {
-        double p[3], qa[4], qb[4], qr[4];
+    const bool is_root = (j == 0);
+    const bool has_quat = is_root || X->type[j] == JT_SPHERICAL;
+    const int qo = is_root ? 3 : 0;  // where the joint's quaternion sits in its parameter block
+    double qr[4] = {1, 0, 0, 0};
+    if (has_quat) {  // one slerp call site for the root and the spherical joints (keeps the code small)
+        double qa[4], qb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + qo + i); qb[i] = __ldg(f1 + qo + i); }
+        quat_slerp_norm(qa, lerp, qb, qr);
+    }
+    if (is_root) {
+        double p[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) p[i] = (1 - lerp) * __ldg(f0 + i) + lerp * __ldg(f1 + i);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + 3 + i); qb[i] = __ldg(f1 + 3 + i); }
-        quat_slerp_norm(qa, lerp, qb, qr);
         double delta[3] = {0, 0, 0};
         if (M->loop) {  // cMotion::CalcCycleCount, Motion.cpp:231-238
             const int cyc = (int)floor(time / M->motion_duration);
@@ -1385,11 +1420,9 @@ TRL_DEV void kin_joint_pose_at(const DevModel* __restrict__ M, const ModelIdx* X
         for (int i = 0; i < 3; ++i) out[i] = rp[i] + (delta[i] + opos[i]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) out[3 + i] = rr[i];
-    } else if (X->type[j] == JT_SPHERICAL) {
-        double qa[4], qb[4];
+    } else if (has_quat) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { qa[i] = __ldg(f0 + i); qb[i] = __ldg(f1 + i); }
-        quat_slerp_norm(qa, lerp, qb, out);
+        for (int i = 0; i < 4; ++i) out[i] = qr[i];
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -1526,6 +1559,7 @@ __global__ void __launch_bounds__(128)
 k_kin_thread(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
              const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
              double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
+    KTrace trace_(TR_KIN);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
     stage_model_idx(&s_ix, M);
@@ -1930,6 +1964,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
           const double* __restrict__ ground_vel, const double* __restrict__ phase,
           const unsigned char* __restrict__ flip_arr, const double* __restrict__ sample_local,
           ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+    KTrace trace_(TR_OBS_ENV);
     __shared__ ModelIdx s_ix;
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;
@@ -2131,6 +2166,7 @@ template <int KIND, bool WANT_CELL>  // ground kind (1 = var2d, 2 = var3d, 0/3 =
 __global__ void __launch_bounds__(256)
 k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
               const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
+    KTrace trace_(TR_OBS_SAMPLES);
     static_assert(sizeof(DevPiece) % 16 == 0 && sizeof(ObsEnvRec) % 16 == 0, "staged with 16-byte copies");
     __shared__ __align__(16) DevPiece s_pieces[4];
     __shared__ __align__(16) ObsEnvRec s_rec;
@@ -2217,6 +2253,50 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, doub
 }
 
 }  // namespace
+
+// Kernel timeline for diagnostics: enable allocates a [16][2] buffer of (first block start, last block end) in
+// %globaltimer nanoseconds; read copies it out and re-arms it. Slots: 0 k_imp_pd, 1 k_pd_tree, 2 k_pd_h, 3 k_pd_solve,
+// 4 k_kin_thread, 5 k_obs_env, 6 k_obs_samples.
+static unsigned long long* g_trace_host_ptr = nullptr;
+static void trace_rearm() {
+    unsigned long long init[2 * kTraceSlots];
+    for (int i = 0; i < kTraceSlots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+    cudaMemcpy(g_trace_host_ptr, init, sizeof(init), cudaMemcpyHostToDevice);
+}
+// Shared-memory carve-out preference for every kernel of the fused step (percent of the unified L1/shared array, or
+// < 0 to leave the driver default). Kernels with different carve-outs cannot share an SM without the SM draining to
+// be reconfigured, which would serialise the step's concurrent chains; one common value keeps them co-resident.
+int trl_set_carveout(int percent) {
+    if (percent < 0) return 0;
+    const void* funcs[] = {(const void*)k_pd_tree, (const void*)k_pd_h, (const void*)k_pd_solve<8>, (const void*)k_pd_solve<17>,
+                           (const void*)k_pd_solve<20>, (const void*)k_pd_solve<24>, (const void*)k_pd_solve<26>,
+                           (const void*)k_pd_solve<0>, (const void*)k_kin_thread, (const void*)k_obs_env,
+                           (const void*)k_obs_samples<0, false>, (const void*)k_obs_samples<1, false>,
+                           (const void*)k_obs_samples<2, false>, (const void*)k_obs_samples<3, false>,
+                           (const void*)k_obs_samples<1, true>, (const void*)k_obs_samples<2, true>};
+    for (const void* f : funcs) {
+        cudaError_t err = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+        if (err != cudaSuccess) return (int)err;
+    }
+    return 0;
+}
+
+int trl_trace_enable(int on) {
+    cudaDeviceSynchronize();
+    if (on && !g_trace_host_ptr) {
+        if (cudaMalloc((void**)&g_trace_host_ptr, sizeof(unsigned long long) * 2 * kTraceSlots) != cudaSuccess) return -1;
+        trace_rearm();
+    }
+    unsigned long long* v = on ? g_trace_host_ptr : nullptr;
+    return (int)cudaMemcpyToSymbol(g_trace, &v, sizeof(v));
+}
+int trl_trace_read(unsigned long long* out32) {
+    if (!g_trace_host_ptr) return -1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out32, g_trace_host_ptr, sizeof(unsigned long long) * 2 * kTraceSlots, cudaMemcpyDeviceToHost);
+    trace_rearm();
+    return 0;
+}
 
 // returns achieved FP64 TFLOP/s of a pure DFMA loop on the current device (<0: CUDA error)
 double trl_fp64_probe_tflops(void* stream) {
@@ -2325,6 +2405,12 @@ static int launch_pd_tree(const DevModel* dm, const DevModel& hm, int E, const S
     if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
     k_pd_tree<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p, scratch);
+    rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    const size_t hsmem = (size_t)6 * hm.nl * kTile * sizeof(double);
+    rc = ensure_smem((const void*)k_pd_h, hsmem);
+    if (rc) return rc;
+    k_pd_h<<<tiles, kHWarps * 32, hsmem, (cudaStream_t)stream>>>(dm, E, scratch, p.out_mass);
     return (int)cudaGetLastError();
 }
 
@@ -2356,7 +2442,8 @@ int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepP
     if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
     int rc = -1;
     static const int tree_env = env_int("TRL_PD_TREE", 1);  // tuning / test hook: 0 = lane-per-joint k_imp_pd<.., SPLIT>
-    if (split && tree_env) rc = launch_pd_tree(dm, hm, E, p, scratch, stream);
+    const bool use_tree = split && tree_env;
+    if (use_tree) rc = launch_pd_tree(dm, hm, E, p, scratch, stream);
 #define TRL_PD_CASE(GG, NL)                                                                       \
     if (rc == -1 && G == GG && nl <= NL)                                                          \
         rc = split ? launch_imp_pd_t<GG, NL, true>(dm, hm, E, p, scratch, stream)                 \
@@ -2376,7 +2463,7 @@ int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepP
         case 26: rc = launch_pd_solve_t<26>(dm, hm, E, p, scratch, stream); break;  // dog
         default: rc = launch_pd_solve_t<0>(dm, hm, E, p, scratch, stream); break;
     }
-    return rc ? -rc : 2;
+    return rc ? -rc : (use_tree ? 3 : 2);
 }
 
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
