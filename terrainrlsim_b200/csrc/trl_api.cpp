@@ -177,7 +177,10 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
     for (int i = 0; i < 3; ++i) {
-        const int prio = (i == 2) ? prio_hi : (i == 0 ? (prio_lo + prio_hi) / 2 : prio_lo);
+        static const int order = getenv("TRL_PRIO_ORDER") ? atoi(getenv("TRL_PRIO_ORDER")) : 1;  // tuning hook
+        const int mid = (prio_lo + prio_hi) / 2;
+        // side[0] = kin chain, side[1] = observation chain, side[2] = stable-PD chain
+        const int prio = (i == 2) ? prio_hi : (order == 1 ? (i == 1 ? mid : prio_lo) : (order == 0 ? (i == 0 ? mid : prio_lo) : prio_lo));
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     }

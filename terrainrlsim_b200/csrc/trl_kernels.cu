@@ -1652,6 +1652,110 @@ k_kin_thread(const DevModel* __restrict__ M, const double* __restrict__ frames, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_kin_tile: the kinematic chain with one WARP PER JOINT over a tile of 32 envs (lane = env, block = N warps). Every
+// branch depends on the joint only, so each warp runs one uniform code path; the joints' poses / velocities are
+// independent and run in parallel; FK then composes each joint's world transform up its (short) ancestor chain from
+// the local transforms left in shared memory ([joint][12][32 lanes]). N x the parallelism of k_kin_thread at the same
+// instruction count.
+// ------------------------------------------------------------------------------------------------
+constexpr int kKinWarps = 16;  // joints beyond this many are looped over
+__global__ void __launch_bounds__(kKinWarps * 32)
+k_kin_tile(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
+           const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
+           double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
+    KTrace trace_(TR_KIN);
+    extern __shared__ double smem[];  // local transforms [N][12][32]
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int e0 = blockIdx.x * kTile;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const int e = e0 + (env_ok ? lane : envs - 1);
+    const int N = M->N, n = M->n, fs = n + 1;
+    double* Tl = smem + lane;  // element k of joint a: Tl[(a * 12 + k) * 32]
+    const double t = time[e];
+    const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
+    int idx0, idx1 = 0;
+    double ph0, ph1 = 0.0;
+    motion_index_phase(M, frames, fs, t, &idx0, &ph0);
+    if (out_vel) motion_index_phase(M, frames, fs, t + ddt, &idx1, &ph1);
+    const double lerp0 = clampd(ph0, 0.0, 1.0), lerp1 = clampd(ph1, 0.0, 1.0);
+    for (int j = warp; j < N; j += nwarps) {  // warp <-> joint
+        const bool is_root = X->parent[j] == -1;
+        double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
+        if (is_root) {
+            if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
+            if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
+        }
+        const int o = X->offset[j], sz = X->size[j];
+        const bool sph = !is_root && X->type[j] == JT_SPHERICAL;
+        double p0[7] = {0, 0, 0, 0, 0, 0, 0};
+        kin_joint_pose_at(M, X, frames, fs, j, t, idx0, lerp0, opos, orot, p0);
+        if (env_ok) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+                if (i < sz) out_pose[(size_t)e * n + o + i] = p0[i];
+        }
+        if (out_vel) {
+            double p1[7] = {0, 0, 0, 0, 0, 0, 0}, v[7] = {0, 0, 0, 0, 0, 0, 0};
+            kin_joint_pose_at(M, X, frames, fs, j, t + ddt, idx1, lerp1, opos, orot, p1);
+            if (is_root) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+                quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
+            } else if (sph) {
+                quat_vel_rel(p0, p1, ddt, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+            }
+            if (env_ok) {
+#pragma unroll
+                for (int i = 0; i < 7; ++i)
+                    if (i < sz) out_vel[(size_t)e * n + o + i] = v[i];
+            }
+        }
+        if (out_body_pos) {
+            double R[9], tt[3];
+            joint_local_trans(X, j, p0, M->attR[j], M->attT[j], R, tt);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Tl[(j * 12 + i) * kTile] = R[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Tl[(j * 12 + 9 + i) * kTile] = tt[i];
+        }
+    }
+    if (!out_body_pos) return;
+    __syncthreads();
+    for (int j = warp; j < N; j += nwarps) {
+        double T[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) T[i] = Tl[(j * 12 + i) * kTile];
+        for (int a = X->parent[j]; a != -1; a = X->parent[a]) {  // T <- Tl[a] o T, up to the root
+            double P[12], Tn[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) P[i] = Tl[(a * 12 + i) * kTile];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Tn[r * 3 + c] = P[r * 3] * T[c] + P[r * 3 + 1] * T[3 + c] + P[r * 3 + 2] * T[6 + c];
+                Tn[9 + r] = P[9 + r] + (P[r * 3] * T[9] + P[r * 3 + 1] * T[10] + P[r * 3 + 2] * T[11]);
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) T[i] = Tn[i];
+        }
+        if (env_ok) {
+            const double* c = M->com[j];
+            const bool vb = X->valid_body[j] != 0;
+            double* ob = out_body_pos + ((size_t)e * N + j) * 3;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) ob[r] = vb ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_imitate_reward<G>: cScenarioExpImitate::CalcReward (scenarios/ScenarioExpImitate.cpp:13-159) -- G lanes per env.
 // pose0/vel0 = simulated character, pose1/vel1 = kinematic reference. One FK per character in world coordinates;
 // the heading-normalised frames of cKinTree::NormalizePoseHeading are applied to the FK results instead of
@@ -2500,7 +2604,17 @@ static int launch_kin_t(const DevModel* dm, const DevModel& hm, const double* fr
 int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
                    const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
                    double* out_body_pos, void* stream) {
-    static const int thread_env = env_int("TRL_KIN_THREAD", 1);  // tuning / test hook: 0 = lane-per-joint k_kin<G>
+    static const int thread_env = env_int("TRL_KIN_THREAD", 2);  // tuning / test hook: 2 = warp-per-joint tiles (default),
+                                                                 // 1 = thread-per-env, 0 = lane-per-joint k_kin<G>
+    if (thread_env == 2) {
+        const size_t smem = (size_t)hm.N * 12 * kTile * sizeof(double);
+        int rc = ensure_smem((const void*)k_kin_tile, smem);
+        if (rc) return rc;
+        const int tiles = (E + kTile - 1) / kTile;
+        k_kin_tile<<<tiles, std::min(hm.N, kKinWarps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
+                                                                    out_vel, out_body_pos);
+        return (int)cudaGetLastError();
+    }
     if (thread_env) {
         const int wpb = 1;
         const size_t smem = (size_t)hm.num_levels * 12 * kTile * sizeof(double) * wpb;
