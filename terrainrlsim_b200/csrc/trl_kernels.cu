@@ -1201,33 +1201,73 @@ k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scr
         // sits on the diagonal slot.
         double b[NL];
         static_for<0, NL>([&](auto ic) { b[decltype(ic)::value] = __ldg(g + (SC.rhs + decltype(ic)::value) * kTile); });
-        static_for<0, NL>([&](auto jc) {
-            constexpr int j = decltype(jc)::value;
-            double v[NL - j];
-            static_for<j, NL>([&](auto ic) { v[decltype(ic)::value - j] = tri[pd_tri(decltype(ic)::value, j, NL) * kTile]; });
+        // Two columns (j, j+1) per pass: every L[i][q] fetched from shared memory feeds two FMAs (the kernel is bound by
+        // shared-memory loads, one warp per SM sub-partition), and the two columns' chains interleave.
+        static_for<0, NL / 2>([&](auto pc) {
+            constexpr int j = 2 * decltype(pc)::value;
+            double v0[NL - j], v1[NL - j - 1];
+            static_for<j, NL>([&](auto ic) { v0[decltype(ic)::value - j] = tri[pd_tri(decltype(ic)::value, j) * kTile]; });
+            static_for<j + 1, NL>([&](auto ic) { v1[decltype(ic)::value - j - 1] = tri[pd_tri(decltype(ic)::value, j + 1) * kTile]; });
 #pragma unroll 2
             for (int q = 0; q < j; ++q) {
                 const double* cq = tri + q * kTile;  // cq[pd_tri(i, 0) * kTile] = entry (i, q)
-                const double w = cq[pd_tri(j, 0) * kTile] * cq[pd_tri(q, 0) * kTile];  // L[j][q] d_q
+                const double dq = cq[pd_tri(q, 0) * kTile];
+                const double w0 = cq[pd_tri(j, 0) * kTile] * dq;      // L[j][q] d_q
+                const double w1 = cq[pd_tri(j + 1, 0) * kTile] * dq;  // L[j+1][q] d_q
                 static_for<j, NL>([&](auto ic) {
                     constexpr int i = decltype(ic)::value;
-                    v[i - j] = fma(-cq[pd_tri(i, 0) * kTile], w, v[i - j]);
+                    const double l = cq[pd_tri(i, 0) * kTile];
+                    v0[i - j] = fma(-l, w0, v0[i - j]);
+                    if constexpr (i > j) v1[i - j - 1] = fma(-l, w1, v1[i - j - 1]);
                 });
             }
-            const double dj = v[0];
-            const bool ok = fabs(dj) > DBL_MIN;
-            if (!(dj > DBL_MIN)) bad |= 2;
-            const double r = ok ? fast_rcp(dj) : 0.0;
-            tri[pd_tri(j, j, NL) * kTile] = ok ? dj : 0.0;
-            const double yj = b[j];
-            static_for<j + 1, NL>([&](auto ic) {  // L[i][j]; forward substitution rides along (y_j is final here)
-                constexpr int i = decltype(ic)::value;
-                const double lij = v[i - j] * r;
-                tri[pd_tri(i, j, NL) * kTile] = lij;
-                b[i] = fma(-lij, yj, b[i]);
-            });
-            b[j] = yj * r;  // z_j = y_j / d_j
+            {   // finish column j; its contribution to column j+1 uses the unscaled v0[j+1] = L[j+1][j] d_j
+                const double dj = v0[0];
+                const bool ok = fabs(dj) > DBL_MIN;
+                if (!(dj > DBL_MIN)) bad |= 2;
+                const double r = ok ? fast_rcp(dj) : 0.0;
+                tri[pd_tri(j, j) * kTile] = ok ? dj : 0.0;
+                const double yj = b[j];
+                const double w = ok ? v0[1] : 0.0;
+                static_for<j + 1, NL>([&](auto ic) {  // L[i][j]; forward substitution rides along (y_j is final here)
+                    constexpr int i = decltype(ic)::value;
+                    const double lij = v0[i - j] * r;
+                    tri[pd_tri(i, j) * kTile] = lij;
+                    b[i] = fma(-lij, yj, b[i]);
+                    v1[i - j - 1] = fma(-lij, w, v1[i - j - 1]);
+                });
+                b[j] = yj * r;  // z_j = y_j / d_j
+            }
+            {   // finish column j + 1
+                const double dj = v1[0];
+                const bool ok = fabs(dj) > DBL_MIN;
+                if (!(dj > DBL_MIN)) bad |= 2;
+                const double r = ok ? fast_rcp(dj) : 0.0;
+                tri[pd_tri(j + 1, j + 1) * kTile] = ok ? dj : 0.0;
+                const double yj = b[j + 1];
+                static_for<j + 2, NL>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const double lij = v1[i - j - 1] * r;
+                    tri[pd_tri(i, j + 1) * kTile] = lij;
+                    b[i] = fma(-lij, yj, b[i]);
+                });
+                b[j + 1] = yj * r;
+            }
         });
+        if constexpr (NL % 2 == 1) {  // odd size: the last column on its own
+            constexpr int j = NL - 1;
+            double v = tri[pd_tri(j, j) * kTile];
+#pragma unroll 2
+            for (int q = 0; q < j; ++q) {
+                const double* cq = tri + q * kTile;
+                const double l = cq[pd_tri(j, 0) * kTile];
+                v = fma(-l, l * cq[pd_tri(q, 0) * kTile], v);
+            }
+            const bool ok = fabs(v) > DBL_MIN;
+            if (!(v > DBL_MIN)) bad |= 2;
+            tri[pd_tri(j, j) * kTile] = ok ? v : 0.0;
+            b[j] = b[j] * (ok ? fast_rcp(v) : 0.0);
+        }
         // backward: L^T x = D^-1 y, row by row (x_i is final when row i is reached; the updates of b[0..i) are
         // independent). The rows are read through a pointer the compiler cannot prove equal to `tri`, otherwise it
         // forwards every L[i][j] stored above through registers and spills the whole factor to local memory.
