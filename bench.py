@@ -13,8 +13,10 @@ value  : whole-job env-steps/s with every input already resident in HBM (DEVICE 
          max over ranks). L2 is defeated by rotating over R input/output sets whose total footprint is > 2.5x L2.
 e2e    : same metric through the public HOST-pointer API (pinned host buffers; H2D of every input and D2H of
          every output inside the timed region, each step).
-roofline: dominant kernel (k_imp_pd) -- algorithmic FP64 flops per launch (SURVEY.md 8d table x E) over its
-         CUDA-event time, against the FP64 DFMA peak measured in this run (MEASURED_PEAKS.json has no FP64 entry);
+roofline: dominant entry point (stable PD = k_pd_tree + k_pd_h + k_pd_solve, one CUDA-event-timed launch group) --
+         algorithmic FP64 flops per launch (SURVEY.md 8d table x E) over its time, against the FP64 DFMA peak measured
+         in this run (MEASURED_PEAKS.json has no FP64 entry); `traffic` = DRAM bytes of the three kernels from the
+         committed ncu captures (profiles/r01_pd_traffic.json);
          roofline_step_hbm does the same for the whole step's algorithmic bytes against the measured HBM copy peak.
 cpu_baseline / --impl reference: the CPU oracle (a faithful restatement of the reference's algorithms; the
          reference itself needs Eigen+Bullet and cannot be built here) on all host cores, bounded sample.
@@ -510,8 +512,16 @@ def run_ours(args, rank, local_rank, world):
         ach_tf = pd_flops * E / (ms_pd * 1e-3) / 1e12
         nominal = 37.2
         peak_tf = fp64_peak if fp64_peak else nominal
-        roof = {"bound": "fp64", "kernel": "k_imp_pd", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf, "traffic": None,
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pd_traffic.json")))
+            if tj.get("config") == name and tj.get("envs") == E:
+                traffic = tj["pd_entry_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            pass
+        roof = {"bound": "fp64", "kernel": "stable-PD entry: k_pd_tree + k_pd_h + k_pd_solve", "achieved": ach_tf,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
+                "traffic_note": "DRAM bytes per launch of the three kernels under ncu (cold L2; profiles/r01_pd_traffic.json)",
                 "peak_source": "DFMA probe measured in this run" if fp64_peak else "nominal 148 SM x 64 x 2 x 1.965 GHz",
                 "ms_per_launch": ms_pd, "algorithmic_flops_per_launch": pd_flops * E}
         ms_step = ms / args.steps
