@@ -57,6 +57,11 @@ struct trl_batch {
     // observation) run concurrently on the main stream and two side streams (captured as parallel graph branches)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // kin chain, observation chain, stable-PD chain (highest priority)
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_pv = nullptr;
+    // second lane of chain streams: the HOST-pointer step is pipelined over env slices, alternating between the two
+    // lanes so one slice's uploads overlap the previous slice's kernels and downloads
+    cudaStream_t side2[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join2[3] = {nullptr, nullptr, nullptr}, ev_pv2 = nullptr;
+    int host_slices = 2;  // measured on B200 + PCIe Gen5: 2 slices +6 %, 4 = no gain, 8 = host-launch bound
     int overlap = 1;
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
@@ -183,7 +188,11 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         const int prio = (i == 2) ? prio_hi : (order == 1 ? (i == 1 ? mid : prio_lo) : (order == 0 ? (i == 0 ? mid : prio_lo) : prio_lo));
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+        if (!cuda_ok(cudaStreamCreateWithPriority(&b->side2[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
+        if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join2[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     }
+    if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv2, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    if (const char* hs = getenv("TRL_HOST_SLICES")) b->host_slices = std::max(1, atoi(hs));  // tuning hook
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
@@ -259,7 +268,10 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     for (int i = 0; i < 3; ++i) {
         if (b->side[i]) { cudaStreamSynchronize(b->side[i]); cudaStreamDestroy(b->side[i]); }
         if (b->ev_join[i]) cudaEventDestroy(b->ev_join[i]);
+        if (b->side2[i]) { cudaStreamSynchronize(b->side2[i]); cudaStreamDestroy(b->side2[i]); }
+        if (b->ev_join2[i]) cudaEventDestroy(b->ev_join2[i]);
     }
+    if (b->ev_pv2) cudaEventDestroy(b->ev_pv2);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_pv) cudaEventDestroy(b->ev_pv);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -480,6 +492,133 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
     return finish(b, copies, rc);
 }
 
+// HOST-pointer step, pipelined over env slices. The step is bound by PCIe (biped3D x 16384 envs: 20 MB up, 50 MB down
+// per step against ~0.13 ms of kernels), so the batch is cut into `host_slices` ranges of whole 32-env tiles and the
+// ranges alternate between two lanes of chain streams: while one range's results are copied back, the next range's
+// inputs go up and its kernels run (the copy engines for the two directions are independent).
+static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool want_pd, bool want_kin, bool want_obs) {
+    const size_t E = b->E, n = b->model->n, N = b->model->N, F = (size_t)b->F;
+    b->pool_next = 0;
+    auto dev = [&](const void* host, size_t bytes_per_env) -> char* {
+        return host ? static_cast<char*>(b->stage_out(E * bytes_per_env)) : nullptr;
+    };
+    bool ok = true;
+    auto need = [&](const void* host, char* d) { if (host && !d) ok = false; };
+    char* d_pose = dev(a->pose, n * 8);            need(a->pose, d_pose);
+    char* d_vel = dev(a->vel, n * 8);              need(a->vel, d_vel);
+    char* d_tp = want_pd ? dev(a->tar_pose, n * 8) : nullptr;
+    char* d_tv = want_pd ? dev(a->tar_vel, n * 8) : nullptr;
+    char* d_ja = want_pd ? dev(a->joint_active, N) : nullptr;
+    char* d_tau = want_pd ? dev(a->out_tau, n * 8) : nullptr;
+    char* d_time = want_kin ? dev(a->kin_time, 8) : nullptr;
+    char* d_op = want_kin ? dev(a->origin_pos, 24) : nullptr;
+    char* d_or = want_kin ? dev(a->origin_rot, 32) : nullptr;
+    char* d_kp = want_kin ? dev(a->out_kin_pose, n * 8) : nullptr;
+    char* d_kv = want_kin ? dev(a->out_kin_vel, n * 8) : nullptr;
+    char* d_kbp = want_kin ? dev(a->out_kin_body_pos, N * 24) : nullptr;
+    char* d_bp = want_obs ? dev(a->body_pos, N * 24) : nullptr;
+    char* d_bv = want_obs ? dev(a->body_vel, N * 24) : nullptr;
+    char* d_ph = want_obs ? dev(a->phase, 8) : nullptr;
+    char* d_fl = want_obs ? dev(a->flip, 1) : nullptr;
+    char* d_st = want_obs ? dev(a->out_state, F * 8) : nullptr;
+    if (want_pd) { need(a->tar_pose, d_tp); need(a->tar_vel, d_tv); need(a->joint_active, d_ja); need(a->out_tau, d_tau); }
+    if (want_kin) { need(a->kin_time, d_time); need(a->origin_pos, d_op); need(a->origin_rot, d_or); need(a->out_kin_pose, d_kp); need(a->out_kin_vel, d_kv); need(a->out_kin_body_pos, d_kbp); }
+    if (want_obs) { need(a->body_pos, d_bp); need(a->body_vel, d_bv); need(a->phase, d_ph); need(a->flip, d_fl); need(a->out_state, d_st); }
+    if (!ok) { trl_set_error("trl_step_fused: device staging allocation failed"); return TRL_ERR_CUDA; }
+
+    const size_t tile = (size_t)trl_pd_scratch_tile();
+    const size_t S = (size_t)b->host_slices;
+    const size_t es = ((E + S - 1) / S + tile - 1) / tile * tile;  // envs per slice, whole tiles
+    if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
+    for (int lane = 0; lane < 2; ++lane)
+        for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(lane ? b->side2[i] : b->side[i], b->ev_fork, 0);
+    int rc = 0;
+    bool used[2] = {false, false};
+    auto up = [&](char* d, const void* h, size_t bpe, size_t e0, size_t ec, cudaStream_t st) {
+        if (d && !rc && cudaMemcpyAsync(d + e0 * bpe, static_cast<const char*>(h) + e0 * bpe, ec * bpe, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            rc = (int)cudaGetLastError();
+    };
+    auto down = [&](void* h, const char* d, size_t bpe, size_t e0, size_t ec, cudaStream_t st) {
+        if (d && !rc && cudaMemcpyAsync(static_cast<char*>(h) + e0 * bpe, d + e0 * bpe, ec * bpe, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = (int)cudaGetLastError();
+    };
+    const size_t rec_bytes = trl_obs_env_rec_bytes();
+    const size_t sc_stride = trl_pd_scratch_doubles(b->model->dev);
+    int slice = 0;
+    for (size_t e0 = 0; e0 < E && !rc; e0 += es, ++slice) {
+        const size_t ec = std::min(es, E - e0);
+        const int lane = slice & 1;
+        used[lane] = true;
+        cudaStream_t sB = lane ? b->side2[0] : b->side[0];  // kin chain
+        cudaStream_t sC = lane ? b->side2[1] : b->side[1];  // observation chain
+        cudaStream_t sA = lane ? b->side2[2] : b->side[2];  // stable-PD chain
+        cudaEvent_t ev_pv = lane ? b->ev_pv2 : b->ev_pv;
+        // pose / vel are shared by the PD and observation chains: upload on one, the other waits for it
+        cudaStream_t s_pv = want_obs ? sC : sA;
+        up(d_pose, a->pose, n * 8, e0, ec, s_pv);
+        up(d_vel, a->vel, n * 8, e0, ec, s_pv);
+        if (want_pd && s_pv != sA) { cudaEventRecord(ev_pv, s_pv); cudaStreamWaitEvent(sA, ev_pv, 0); }
+        if (want_obs) {
+            up(d_bp, a->body_pos, N * 24, e0, ec, sC); up(d_bv, a->body_vel, N * 24, e0, ec, sC);
+            up(d_ph, a->phase, 8, e0, ec, sC); up(d_fl, a->flip, 1, e0, ec, sC);
+        }
+        if (want_kin) { up(d_time, a->kin_time, 8, e0, ec, sB); up(d_op, a->origin_pos, 24, e0, ec, sB); up(d_or, a->origin_rot, 32, e0, ec, sB); }
+        if (want_pd) { up(d_tp, a->tar_pose, n * 8, e0, ec, sA); up(d_tv, a->tar_vel, n * 8, e0, ec, sA); up(d_ja, a->joint_active, N, e0, ec, sA); }
+        auto at = [&](char* d, size_t bpe) { return d ? d + e0 * bpe : nullptr; };
+        if (!rc && want_obs) {
+            DevGround g2 = b->ground;
+            if (g2.env_to_field) g2.env_to_field += e0;
+            rc = trl_launch_poli_state(b->d_model, b->model->dev, g2, b->cfg, b->F, (int)ec, (const double*)at(d_pose, n * 8),
+                                       (const double*)at(d_vel, n * 8), (const double*)at(d_bp, N * 24),
+                                       (const double*)at(d_bv, N * 24), nullptr, nullptr, nullptr, (const double*)at(d_ph, 8),
+                                       (const unsigned char*)at(d_fl, 1), b->d_sample_local,
+                                       static_cast<char*>(b->d_env_rec) + e0 * rec_bytes, (double*)at(d_st, F * 8), nullptr, sC);
+            b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+            down(a->out_state, d_st, F * 8, e0, ec, sC);
+        }
+        if (!rc && want_kin) {
+            rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, (int)ec, (const double*)at(d_time, 8),
+                                (const double*)at(d_op, 24), (const double*)at(d_or, 32), (double*)at(d_kp, n * 8),
+                                (double*)at(d_kv, n * 8), (double*)at(d_kbp, N * 24), sB);
+            b->launches += 1;
+            down(a->out_kin_pose, d_kp, n * 8, e0, ec, sB);
+            down(a->out_kin_vel, d_kv, n * 8, e0, ec, sB);
+            down(a->out_kin_body_pos, d_kbp, N * 24, e0, ec, sB);
+        }
+        if (!rc && want_pd) {
+            if (a->dt > 0) {
+                StepPtrs p{};
+                p.dt = a->dt;
+                p.pose = (const double*)at(d_pose, n * 8); p.vel = (const double*)at(d_vel, n * 8);
+                p.tar_pose = (const double*)at(d_tp, n * 8); p.tar_vel = (const double*)at(d_tv, n * 8);
+                p.joint_active = (const unsigned char*)at(d_ja, N);
+                p.tau = (double*)at(d_tau, n * 8);
+                p.tau_accumulate = 0;
+                p.status = b->d_status + e0;
+                int k = trl_launch_imp_pd(b->d_model, b->model->dev, (int)ec, p, b->d_pd_scratch + e0 * sc_stride, sA);
+                if (k > 0) b->launches += k; else rc = -k;
+            } else {
+                cudaMemsetAsync(at(d_tau, n * 8), 0, ec * n * 8, sA);
+            }
+            down(a->out_tau, d_tau, n * 8, e0, ec, sA);
+        }
+    }
+    for (int lane = 0; lane < 2; ++lane) {  // join (also on error, so the streams stay consistent)
+        if (!used[lane]) continue;
+        for (int i = 0; i < 3; ++i) {
+            cudaEvent_t ev = lane ? b->ev_join2[i] : b->ev_join[i];
+            cudaEventRecord(ev, lane ? b->side2[i] : b->side[i]);
+            cudaStreamWaitEvent(b->stream, ev, 0);
+        }
+    }
+    if (rc) {
+        cudaStreamSynchronize(b->stream);
+        trl_set_error(std::string("trl_step_fused: ") + cudaGetErrorString((cudaError_t)rc));
+        return TRL_ERR_CUDA;
+    }
+    return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? TRL_OK : TRL_ERR_CUDA;
+}
+
 extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (!b || !a || !a->pose || !a->vel) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);
@@ -489,6 +628,8 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (want_kin && (b->model->num_frames < 2 || !a->kin_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
     if (want_obs && (!a->body_pos || !a->body_vel)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
     if (want_obs && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
+    if (b->ptr_mode == TRL_PTR_HOST && b->overlap && b->host_slices > 1 && E >= 2048)
+        return step_fused_host_sliced(b, a, want_pd, want_kin, want_obs);
     b->pool_next = 0;
     std::vector<OutCopy> copies;
     StepPtrs p{};

@@ -277,6 +277,30 @@ def test_device_pointer_mode_equals_host_mode(trl, oracle):
     batch.set_stream(None)
 
 
+@pytest.mark.parametrize("name,E", [("biped3d", 2100), ("dog", 2049)])
+def test_host_pipeline_slices_equal_device_mode(trl, oracle, name, E):
+    """HOST pointer mode pipelines the step over env slices (whole 32-env tiles, ragged last slice) on two lanes of
+    streams; the result must be bit-identical to the single-pass DEVICE pointer mode and match the oracle."""
+    import torch
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=5)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    host = batch.step_fused(dt, x)
+    dev_in = {k: torch.from_numpy(v).cuda() for k, v in x.items()}
+    batch.use_torch_stream()
+    dev = batch.step_fused(dt, dev_in)
+    batch.sync()
+    torch.cuda.synchronize()
+    for k in host:
+        assert np.array_equal(host[k], dev[k].cpu().numpy(), equal_nan=True), k
+    batch.set_stream(None)
+    ref = oracle.step_range(om, oracle_cfg(oracle, name), dict(x), grounds, dt)
+    assert_close(host["tau"], ref["tau"], "sliced tau")
+    assert_close(host["state"], ref["state"], "sliced state")
+    assert_close(host["kin_pose"], ref["kin_pose"], "sliced kin pose")
+    assert np.all(batch.status() == 0)
+
+
 @pytest.mark.parametrize("name,E", [("hopper", 4096), ("dog", 4096), ("raptor", 8192), ("biped3d", 16384), ("biped2d", 4096)])
 def test_full_size_properties(trl, oracle, name, E):
     """BASELINE.json full sizes: determinism, env-permutation equivariance (bit-exact), and oracle parity on a
