@@ -185,7 +185,12 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         static const int order = getenv("TRL_PRIO_ORDER") ? atoi(getenv("TRL_PRIO_ORDER")) : 1;  // tuning hook
         const int mid = (prio_lo + prio_hi) / 2;
         // side[0] = kin chain, side[1] = observation chain, side[2] = stable-PD chain
-        const int prio = (i == 2) ? prio_hi : (order == 1 ? (i == 1 ? mid : prio_lo) : (order == 0 ? (i == 0 ? mid : prio_lo) : prio_lo));
+        int prio = prio_lo;
+        if (i == 2) prio = prio_hi;                                    // stable PD: always highest
+        else if (order == 0) prio = (i == 0) ? mid : prio_lo;          // kin > obs
+        else if (order == 1) prio = (i == 1) ? mid : prio_lo;          // obs > kin
+        else if (order == 3) prio = (i == 0) ? prio_hi : prio_lo;      // kin = PD > obs
+        else if (order == 4) prio = (i == 0) ? prio_hi : mid;          // kin = PD > obs (mid)
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side2[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
