@@ -326,8 +326,17 @@ class Workload:
                          (rew[idx[id(x)]], np.float64), (None, np.float64)])
             _capi.lib().trl_imitate_calc_reward(b._h, *p)
 
+        n_dof = self.model.num_dof
+        jac = [torch.empty((self.E, 6, n_dof), dtype=torch.float64, device=self.inputs[0]["pose"].device) for _ in range(2)]
+        gfo = torch.empty((self.E, n_dof), dtype=torch.float64, device=self.inputs[0]["pose"].device)
+
+        def f_extras(x, o):  # world Jacobian, CoM Jacobian, gravity force
+            from terrainrlsim_b200 import _capi
+            p = b._prep([(x["pose"], np.float64), (jac[0], np.float64), (jac[1], np.float64), (gfo, np.float64)])
+            _capi.lib().trl_rbd_extras(b._h, *p)
+
         for name, fn in (("imp_pd", f_pd), ("kin_char", f_kin), ("fk", f_fk), ("kin_fused", f_kin_fused),
-                         ("poli_state", f_obs), ("imitate_reward", f_reward)):
+                         ("poli_state", f_obs), ("imitate_reward", f_reward), ("rbd_extras", f_extras)):
             for s in range(self.sets):
                 fn(self.inputs[s], self.outputs[s])
             torch.cuda.synchronize()

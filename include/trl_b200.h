@@ -147,6 +147,12 @@ int trl_imp_pd_update_control_force(trl_batch* b, double dt, const double* pose,
                                     const double* kp_or_null, const double* kd_or_null, double* inout_tau,
                                     double* out_mass_or_null, double* out_bias_or_null);
 
+/* cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.cpp:256-275,294-345,937-982): the RBD
+ * quantities the FSM controllers read every substep next to M and C (BipedController3D.cpp:1065-1072,1301-1388,
+ * DogController.cpp:897,982). pose [E][n]; out_J, out_Jcom [E][6][n] row-major (rows = wx wy wz vx vy vz in world
+ * coordinates; columns of dead dof slots are zero); out_gravity_force [E][n]. Any output may be NULL. */
+int trl_rbd_extras(trl_batch* b, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force);
+
 /* ------------------------------------------------------------------------------------------
  * (2) kinematics
  *   cKinTree::JointWorldTrans for every joint (anim/KinTree.cpp:1099-1112) -> out_joint_world [E][N][12]

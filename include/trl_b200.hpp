@@ -6,6 +6,7 @@
 //   trl::cCharModel          <-> cCharacter::Init + cKinTree::Load + cPDController::LoadParams + cMotion::Load
 //   trl::cImpPDController    <-> cImpPDController (sim/ImpPDController.h:9-55) incl. its cRBDModel
 //                                (GetMassMat / GetBiasForce, sim/RBDModel.h:15-29), batched over E envs
+//   trl::cRBDUtil            <-> cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.h)
 //   trl::cKinCharacter       <-> cKinCharacter::Pose / SetOriginPos / SetOriginRot (anim/KinCharacter.h:15-45)
 //   trl::cGround             <-> cGround::SampleHeight (sim/Ground.h:93-97)
 //   trl::cTerrainRLCharController <-> ParseGround + BuildPoliState (sim/TerrainRLCharController.h:31-87)
@@ -140,6 +141,25 @@ private:
     cBatch* mBatch = nullptr;
     std::vector<double> mTarPose, mTarVel, mKp, mKd, mMass, mBias;
     std::vector<unsigned char> mActive;
+};
+
+// cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.h) for all E envs of a batch:
+// J, Jcom [E][6][n] row-major, tau_g [E][n]. cRBDUtil::ExtractEndEffJacobian(joint_mat, J, joint_id) is a column mask
+// of J (the blocks of the joints on the chain root..joint_id) and stays on the caller's side.
+class cRBDUtil {
+public:
+    static bool BuildJacobian(cBatch& batch, const std::vector<double>& pose, std::vector<double>& out_J) {
+        out_J.resize((size_t)batch.GetNumEnvs() * 6 * batch.GetNumDof());
+        return trl_rbd_extras(batch.Handle(), pose.data(), out_J.data(), nullptr, nullptr) == TRL_OK;
+    }
+    static bool BuildCOMJacobian(cBatch& batch, const std::vector<double>& pose, std::vector<double>& out_J) {
+        out_J.resize((size_t)batch.GetNumEnvs() * 6 * batch.GetNumDof());
+        return trl_rbd_extras(batch.Handle(), pose.data(), nullptr, out_J.data(), nullptr) == TRL_OK;
+    }
+    static bool CalcGravityForce(cBatch& batch, const std::vector<double>& pose, std::vector<double>& out_g_force) {
+        out_g_force.resize((size_t)batch.GetNumEnvs() * batch.GetNumDof());
+        return trl_rbd_extras(batch.Handle(), pose.data(), nullptr, nullptr, out_g_force.data()) == TRL_OK;
+    }
 };
 
 class cKinCharacter {

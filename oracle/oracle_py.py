@@ -159,6 +159,19 @@ class Model:
         lib().trlo_rbd_update(self.ref, _d(pose), _d(vel), _d(M), _d(Cb))
         return M, Cb
 
+    def rbd_extras(self, pose):
+        """cRBDUtil::BuildJacobian, BuildCOMJacobian, CalcGravityForce -> J [6][n], Jcom [6][n], tau_g [n]"""
+        pose = _c(pose)
+        J, Jc, g = np.zeros((6, self.n)), np.zeros((6, self.n)), np.zeros(self.n)
+        lib().trlo_rbd_extras(self.ref, _d(pose), _d(J), _d(Jc), _d(g))
+        return J, Jc, g
+
+    def end_eff_jacobian(self, pose, joint_id):
+        pose = _c(pose)
+        J = np.zeros((6, self.n))
+        lib().trlo_end_eff_jacobian(self.ref, _d(pose), C.c_int(joint_id), _d(J))
+        return J
+
     def inv_dyna(self, pose, vel, acc):
         pose, vel, acc = _c(pose), _c(vel), _c(acc)
         tau = np.zeros(self.n)

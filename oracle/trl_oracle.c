@@ -1017,6 +1017,158 @@ void trlo_solve_inv_dyna(const trlo_model* m, const double* pose, const double* 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * RBD extras used by the FSM controllers every substep
+ * ---------------------------------------------------------------------------------------- */
+static spvec apply_inv_trans_m(const sptrans* X, const spvec* sv) /* SpAlg.cpp:285-297 */
+{
+    double o1[3], v1[3], c[3];
+    mat3T_mulv(X->E, sv->v, o1);
+    mat3T_mulv(X->E, sv->v + 3, v1);
+    cross3(X->r, o1, c);
+    spvec out = { { o1[0], o1[1], o1[2], v1[0] + c[0], v1[1] + c[1], v1[2] + c[2] } };
+    return out;
+}
+
+/* cRBDUtil::BuildJacobian, RBDUtil.cpp:256-275: column block of joint j = ApplyInvTransM(world_joint_trans, S_j).
+ * out_J row-major [6][n]; the dead slots (root 6, spherical 3) stay zero columns. */
+static void build_jacobian(const trlo_model* m, const rbd_cache* c, double* J)
+{
+    int n = m->num_dof, N = m->num_joints;
+    for (int i = 0; i < 6 * n; ++i) J[i] = 0;
+    for (int j = 0; j < N; ++j) {
+        int off = trlo_param_offset(m, j), dim = trlo_param_size(m, j);
+        for (int k = 0; k < dim; ++k) {
+            spvec s, w;
+            for (int r = 0; r < 6; ++r) s.v[r] = c->S[r][off + k];
+            w = apply_inv_trans_m(&c->world_joint[j], &s);
+            for (int r = 0; r < 6; ++r) J[r * n + off + k] = w.v[r];
+        }
+    }
+}
+
+static mat4 trans_to_mat(const sptrans* X) /* SpAlg.cpp:164-172 */
+{
+    mat4 mt = mat4_identity();
+    double Er[3];
+    mat3_mulv(X->E, X->r, Er);
+    for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) mt.m[r][k] = X->E[r][k];
+        mt.m[r][3] = -Er[r];
+    }
+    return mt;
+}
+
+/* cRBDUtil::BuildCOMJacobian, RBDUtil.cpp:294-345 (the comment there says "origin at the com": each body's
+ * block is the world Jacobian shifted to that body's position, weighted by its mass fraction) */
+static void build_com_jacobian(const trlo_model* m, const rbd_cache* c, const double* J, double* Jc)
+{
+    int n = m->num_dof, N = m->num_joints;
+    for (int i = 0; i < 6 * n; ++i) Jc[i] = 0;
+    double total_mass = 0; /* cKinTree::CalcTotalMass, KinTree.cpp:376-388 */
+    for (int j = 0; j < N; ++j)
+        if (trlo_valid_body(m, j)) total_mass += brow(m, j)[BD_MASS];
+    for (int j = N - 1; j >= 0; --j) {
+        if (!trlo_valid_body(m, j)) continue;
+        double mass_frac = brow(m, j)[BD_MASS] / total_mass;
+        mat4 bj = body_joint_trans(m, j);
+        sptrans inv_w = inv_trans(&c->world_joint[j]);
+        sptrans bjt = mat_to_trans(&bj);
+        sptrans bw = comp_trans(&inv_w, &bjt);
+        mat4 bwm = trans_to_mat(&bw);
+        sptrans shift = identity_trans();
+        shift.r[0] = bwm.m[0][3]; shift.r[1] = bwm.m[1][3]; shift.r[2] = bwm.m[2][3];
+        for (int cur = j; cur != -1; cur = trlo_parent(m, cur)) {
+            int off = trlo_param_offset(m, cur), dim = trlo_param_size(m, cur);
+            for (int k = 0; k < dim; ++k) {
+                spvec col, t;
+                for (int r = 0; r < 6; ++r) col.v[r] = J[r * n + off + k];
+                t = apply_trans_m(&shift, &col);
+                for (int r = 0; r < 6; ++r) Jc[r * n + off + k] += mass_frac * t.v[r];
+            }
+        }
+    }
+}
+
+/* cRBDUtil::CalcGravityForce, RBDUtil.cpp:937-982. Note acc0 = (0, +gravity), and that an invalid body neither gets a
+ * torque nor hands its children's forces on to its parent. */
+static void calc_gravity_force(const trlo_model* m, const rbd_cache* c, double* out)
+{
+    int n = m->num_dof, N = m->num_joints;
+    spvec fs[TRLO_MAX_JOINTS];
+    memset(fs, 0, sizeof(fs)); /* the reference leaves the rows of invalid bodies uninitialised; they are never read */
+    spvec acc0 = { { 0, 0, 0, m->gravity[0], m->gravity[1], m->gravity[2] } };
+    for (int j = 0; j < N; ++j) {
+        if (!trlo_valid_body(m, j)) continue;
+        spmat I = build_inertia_spatial_mat(m, j);
+        spvec a = apply_trans_m(&c->world_joint[j], &acc0);
+        fs[j] = spmat_mulv(&I, &a);
+    }
+    for (int i = 0; i < n; ++i) out[i] = 0;
+    for (int j = N - 1; j >= 0; --j) {
+        if (!trlo_valid_body(m, j)) continue;
+        int off = trlo_param_offset(m, j), dim = trlo_param_size(m, j);
+        for (int k = 0; k < dim; ++k) { /* S^T f */
+            double sacc = 0;
+            for (int r = 0; r < 6; ++r) {
+                if (r == 0) sacc = c->S[0][off + k] * fs[j].v[0];
+                else sacc += c->S[r][off + k] * fs[j].v[r];
+            }
+            out[off + k] = sacc;
+        }
+        int p = trlo_parent(m, j);
+        if (p != -1) {
+            sptrans cp = sp_child_parent(c, j);
+            spvec t = apply_trans_f(&cp, &fs[j]);
+            for (int r = 0; r < 6; ++r) fs[p].v[r] += t.v[r];
+        }
+    }
+}
+
+/* cRBDUtil::BuildEndEffectorJacobian(model, joint_id), RBDUtil.cpp:181-206: blocks of the joints on the chain
+ * root .. joint_id, expressed in world coordinates (the other columns are zero). */
+static void build_end_eff_jacobian(const trlo_model* m, const rbd_cache* c, int joint_id, double* J)
+{
+    int n = m->num_dof;
+    for (int i = 0; i < 6 * n; ++i) J[i] = 0;
+    sptrans cur = identity_trans();
+    for (int id = joint_id; id != -1; id = trlo_parent(m, id)) {
+        int off = trlo_param_offset(m, id), dim = trlo_param_size(m, id);
+        for (int k = 0; k < dim; ++k) {
+            spvec s, t;
+            for (int r = 0; r < 6; ++r) s.v[r] = c->S[r][off + k];
+            t = apply_trans_m(&cur, &s);
+            for (int r = 0; r < 6; ++r) J[r * n + off + k] = t.v[r];
+        }
+        sptrans pc = sp_parent_child(c, id);
+        cur = comp_trans(&cur, &pc);
+    }
+    for (int col = 0; col < n; ++col) { /* out_J = ApplyInvTransM(curr_trans, out_J) */
+        spvec s, t;
+        for (int r = 0; r < 6; ++r) s.v[r] = J[r * n + col];
+        t = apply_inv_trans_m(&cur, &s);
+        for (int r = 0; r < 6; ++r) J[r * n + col] = t.v[r];
+    }
+}
+
+void trlo_rbd_extras(const trlo_model* m, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force)
+{
+    rbd_cache c;
+    double Jtmp[6 * TRLO_MAX_DOF];
+    rbd_build_cache(m, pose, &c);
+    double* J = out_J ? out_J : Jtmp;
+    if (out_J || out_Jcom) build_jacobian(m, &c, J);
+    if (out_Jcom) build_com_jacobian(m, &c, J, out_Jcom);
+    if (out_gravity_force) calc_gravity_force(m, &c, out_gravity_force);
+}
+
+void trlo_end_eff_jacobian(const trlo_model* m, const double* pose, int joint_id, double* out_J)
+{
+    rbd_cache c;
+    rbd_build_cache(m, pose, &c);
+    build_end_eff_jacobian(m, &c, joint_id, out_J);
+}
+
+/* ------------------------------------------------------------------------------------------
  * Eigen 3.3 LDLT restated (Eigen/src/Cholesky/LDLT.h: ldlt_inplace<Lower>::unblocked + _solve_impl).
  * Lower triangle, diagonal pivoting, zero pivot => solution component 0 (Q1).
  * ---------------------------------------------------------------------------------------- */
@@ -1560,17 +1712,6 @@ static sptrans build_trans_r(const double r[3]) /* cSpAlg::BuildTrans(r): identi
     sptrans X = identity_trans();
     X.r[0] = r[0]; X.r[1] = r[1]; X.r[2] = r[2];
     return X;
-}
-
-static spvec apply_inv_trans_m(const sptrans* X, const spvec* sv) /* SpAlg.cpp:285-297 */
-{
-    spvec out;
-    double eto[3], etv[3], c[3];
-    mat3T_mulv(X->E, sv->v, eto);
-    mat3T_mulv(X->E, sv->v + 3, etv);
-    cross3(X->r, eto, c);
-    for (int i = 0; i < 3; ++i) { out.v[i] = eto[i]; out.v[3 + i] = etv[i] + c[i]; }
-    return out;
 }
 
 /* cRBDUtil::CalcWorldVel(joint_mat, pose, vel, joint_id) = BuildEndEffectorJacobian(...) * vel (RBDUtil.cpp:209-233,474-480) */

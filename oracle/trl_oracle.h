@@ -100,6 +100,11 @@ void trlo_rbd_update(const trlo_model* m, const double* pose, const double* vel,
 void trlo_solve_inv_dyna(const trlo_model* m, const double* pose, const double* vel,
                          const double* acc, double* out_tau);
 void trlo_inertia_spatial(const trlo_model* m, int j, double out[36]);
+/* RBD extras: cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce
+ * (sim/RBDUtil.cpp:256-275,294-345,937-982); J, Jcom row-major [6][n]; any output may be NULL */
+void trlo_rbd_extras(const trlo_model* m, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force);
+/* cRBDUtil::BuildEndEffectorJacobian(model, joint_id), sim/RBDUtil.cpp:181-206; row-major [6][n] */
+void trlo_end_eff_jacobian(const trlo_model* m, const double* pose, int joint_id, double* out_J);
 
 /* Eigen 3.3 LDLT restated: A [n][n] row-major symmetric (only lower read), solves A x = b.
  * returns number of zero pivots. */

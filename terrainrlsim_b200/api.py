@@ -202,6 +202,17 @@ class Batch:
         check(_capi.lib().trl_kin_tree_fk(self._h, *p), "trl_kin_tree_fk")
         return jw, bp
 
+    def rbd_extras(self, pose, want_J=True, want_Jcom=True, want_gravity_force=True):
+        """cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce -> J [E][6][n], Jcom [E][6][n], tau_g [E][n]"""
+        n = self.model.num_dof
+        J = self._new((self.E, 6, n), pose) if want_J else None
+        Jc = self._new((self.E, 6, n), pose) if want_Jcom else None
+        g = self._new((self.E, n), pose) if want_gravity_force else None
+        f8 = np.float64
+        p = self._prep([(pose, f8), (J, f8), (Jc, f8), (g, f8)])
+        check(_capi.lib().trl_rbd_extras(self._h, *p), "trl_rbd_extras")
+        return J, Jc, g
+
     def kin_char_pose(self, time, origin_pos=None, origin_rot=None, want_vel=True):
         n = self.model.num_dof
         pose = self._new((self.E, n), time)

@@ -336,6 +336,22 @@ extern "C" int trl_imp_pd_update_control_force(trl_batch* b, double dt, const do
     return finish(b, copies, rc);
 }
 
+extern "C" int trl_rbd_extras(trl_batch* b, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force) {
+    if (!b || !pose) { trl_set_error("trl_rbd_extras: null argument"); return TRL_ERR_INVALID_ARG; }
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double* d_pose = nullptr;
+    double *d_J = nullptr, *d_Jc = nullptr, *d_g = nullptr;
+    if (!in_ptr(b, pose, E * n, &d_pose) || !out_ptr(b, out_J, E * 6 * n, &d_J, copies) ||
+        !out_ptr(b, out_Jcom, E * 6 * n, &d_Jc, copies) || !out_ptr(b, out_gravity_force, E * n, &d_g, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_rbd_extras(b->d_model, b->model->dev, b->E, d_pose, d_J, d_Jc, d_g, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
 extern "C" int trl_kin_tree_fk(trl_batch* b, const double* pose, double* out_joint_world, double* out_body_pos) {
     if (!b || !pose) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);

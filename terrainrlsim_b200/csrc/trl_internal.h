@@ -125,6 +125,8 @@ size_t trl_pd_scratch_doubles(const DevModel& hm);
 int trl_pd_scratch_tile();
 // returns the number of kernels launched (> 0) or a negative cudaError_t
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream);
+int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_J,
+                          double* out_Jcom, double* out_gforce, void* stream);
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
                   double* out_body_pos, void* stream);
 int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,

@@ -1094,6 +1094,162 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_rbd_extras: cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.cpp:256-275,294-345,
+// 937-982) -- thread per env, same depth-first walk and per-level workspace as k_pd_tree.
+// In the root frame every quantity is a by-product of the subtree sums (mass m, first moment h = sum m c):
+//   J column c (world)   = X_{world<-root} S_c = [Rw w ; Rw v + p_root x Rw w]
+//   Jcom column c        = [(m_sub / M) w_w ; (m_sub / M) v_w - ((Rw h_sub + m_sub p_root) / M) x w_w]
+//   tau_g[c]             = S_c . [h_g x g_r ; m_g g_r],  g_r = Rw^T g
+// where the Jcom sums run over every valid body below the joint, while the gravity sums follow the reference's
+// quirk: an invalid body gets no torque and does not hand its children's forces to its parent.
+// ------------------------------------------------------------------------------------------------
+constexpr int kXSlotT = 0;   // root-frame transform [R(9) | t(3)]
+constexpr int kXSlotC = 12;  // m, h(3) of the valid bodies of the subtree (Jcom)
+constexpr int kXSlotG = 16;  // m, h(3) along the reference's gravity recursion
+constexpr int kXSlot = 20;
+
+__global__ void __launch_bounds__(128)
+k_rbd_extras(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, double* __restrict__ out_J,
+             double* __restrict__ out_Jcom, double* __restrict__ out_gforce) {
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kTile;
+    if (e0 >= E) return;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const int e = e0 + (env_ok ? lane : envs - 1);
+    const int N = M->N, n = M->n;
+    double* ws = smem + (size_t)warp * ((kTreeHead + M->num_levels * kXSlot) * kTile) + lane;
+    double* Rq = ws;
+    double* lvl = ws + kTreeHead * kTile;
+    const double* q = pose + (size_t)e * n;
+    double* Jw = out_J ? out_J + (size_t)e * 6 * n : nullptr;
+    double* Jc = out_Jcom ? out_Jcom + (size_t)e * 6 * n : nullptr;
+    double* tg = out_gforce ? out_gforce + (size_t)e * n : nullptr;
+    if (env_ok) {  // dead dof slots and the columns of joints without dofs stay zero
+        for (int i = 0; i < 6 * n; ++i) {
+            if (Jw) Jw[i] = 0.0;
+            if (Jc) Jc[i] = 0.0;
+        }
+        if (tg) for (int i = 0; i < n; ++i) tg[i] = 0.0;
+    }
+    double Rw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pr[3] = {0, 0, 0}, gr[3] = {0, 0, 0};
+    const double inv_total = 1.0 / M->total_mass;
+    const int nev = 2 * N;
+    for (int evi = 0; evi < nev; ++evi) {
+        const int code = X->dfs_event[evi];
+        if (code >= 0) {
+            const int j = code;
+            const int lv = X->level[j];
+            double* W = lvl + (size_t)lv * kXSlot * kTile;
+            const int o = X->offset[j], sz = X->size[j];
+            double T[12];
+            if (X->parent[j] == -1) {
+                double qr[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) qr[i] = q[o + i];
+                double rq9[9];
+                quat_to_mat(qr[3], qr[4], qr[5], qr[6], rq9);
+                mat3_mul(M->attR[j], rq9, Rw);
+                mat3_mulv(M->attR[j], qr, pr);
+                pr[0] += M->attT[j][0]; pr[1] += M->attT[j][1]; pr[2] += M->attT[j][2];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rq[i * kTile] = rq9[i];
+                const double g[3] = {M->gravity[0], M->gravity[1], M->gravity[2]};
+                mat3T_mulv(Rw, g, gr);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) T[i] = (i % 4 == 0) ? 1.0 : 0.0;
+                T[9] = T[10] = T[11] = 0.0;
+            } else {
+                double qj[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) qj[i] = (i < sz) ? q[o + i] : 0.0;
+                double R[9], t[3];
+                joint_local_trans(X, j, qj, M->attR[j], M->attT[j], R, t);
+                const double* Wp = W - kXSlot * kTile;
+                double Tp[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Tp[i] = Wp[(kXSlotT + i) * kTile];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
+                    T[9 + r] = Tp[9 + r] + (Tp[r * 3] * t[0] + Tp[r * 3 + 1] * t[1] + Tp[r * 3 + 2] * t[2]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) W[(kXSlotT + i) * kTile] = T[i];
+            double m = 0.0, h[3] = {0, 0, 0};
+            if (X->valid_body[j]) {
+                m = M->mass[j];
+                double c[3];
+                mat3_mulv(T, M->com[j], c);
+                h[0] = m * (c[0] + T[9]); h[1] = m * (c[1] + T[10]); h[2] = m * (c[2] + T[11]);
+            }
+            W[kXSlotC * kTile] = m; W[kXSlotG * kTile] = m;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { W[(kXSlotC + 1 + i) * kTile] = h[i]; W[(kXSlotG + 1 + i) * kTile] = h[i]; }
+        } else {
+            const int j = -1 - code;
+            const int lv = X->level[j];
+            double* W = lvl + (size_t)lv * kXSlot * kTile;
+            const bool vb = X->valid_body[j] != 0;
+            const double mc = W[kXSlotC * kTile], mg = W[kXSlotG * kTile];
+            double hc[3], hg[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { hc[i] = W[(kXSlotC + 1 + i) * kTile]; hg[i] = W[(kXSlotG + 1 + i) * kTile]; }
+            // world first moment of the subtree about the world origin, over the total mass
+            double hw[3];
+            mat3_mulv(Rw, hc, hw);
+            const double mf = mc * inv_total;
+            const double pc[3] = {(hw[0] + mc * pr[0]) * inv_total, (hw[1] + mc * pr[1]) * inv_total, (hw[2] + mc * pr[2]) * inv_total};
+            // gravity wrench of the subtree in the root frame: [h x g ; m g]
+            double ng[3];
+            cross3(hg, gr, ng);
+            const int c0 = X->first_col[j], nc = X->ncol[j];
+            for (int c = c0; c < c0 + nc; ++c) {
+                double sv[6];
+                tree_subspace(X->col_kind[c], X->col_axis[c], W + kXSlotT * kTile, Rq, sv);
+                double ww[3], vr[3], vw[3], cx[3];
+                mat3_mulv(Rw, sv, ww);
+                mat3_mulv(Rw, sv + 3, vr);
+                cross3(pr, ww, cx);
+                vw[0] = vr[0] + cx[0]; vw[1] = vr[1] + cx[1]; vw[2] = vr[2] + cx[2];
+                const int di = X->col_dof[c];
+                if (env_ok) {
+                    if (Jw) {
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) { Jw[r * n + di] = ww[r]; Jw[(3 + r) * n + di] = vw[r]; }
+                    }
+                    if (Jc) {
+                        double px[3];
+                        cross3(pc, ww, px);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) { Jc[r * n + di] = mf * ww[r]; Jc[(3 + r) * n + di] = mf * vw[r] - px[r]; }
+                    }
+                    if (tg)
+                        tg[di] = vb ? ((sv[0] * ng[0] + sv[1] * ng[1] + sv[2] * ng[2]) +
+                                       mg * (sv[3] * gr[0] + sv[4] * gr[1] + sv[5] * gr[2])) : 0.0;
+                }
+            }
+            if (lv > 0) {
+                double* Wp = W - kXSlot * kTile;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Wp[(kXSlotC + i) * kTile] += W[(kXSlotC + i) * kTile];
+                if (vb) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) Wp[(kXSlotG + i) * kTile] += W[(kXSlotG + i) * kTile];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_pd_h: off-diagonal entries of H = M + dt*Kd from the columns k_pd_tree left in the scratch: H[c][a] = F_c . S_a
 // for every a on the ancestor chain of c (Featherstone's branch-induced sparsity; the other entries stay zero).
 // One warp per (tile of 32 envs, column c), lane = env: all loads / stores are 256-byte coalesced rows of the tile.
@@ -2536,6 +2692,17 @@ static int launch_pd_solve_t(const DevModel* dm, const DevModel& hm, int E, cons
     const int tiles = (E + kTile - 1) / kTile;
     k_pd_solve<NL><<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
                                                                                     p.status);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_J,
+                          double* out_Jcom, double* out_gforce, void* stream) {
+    const int wpb = 1;
+    const size_t smem = (size_t)(kTreeHead + hm.num_levels * kXSlot) * kTile * sizeof(double) * wpb;
+    int rc = ensure_smem((const void*)k_rbd_extras, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_rbd_extras<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, pose, out_J, out_Jcom, out_gforce);
     return (int)cudaGetLastError();
 }
 

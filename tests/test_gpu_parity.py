@@ -434,3 +434,21 @@ def test_pd_kernel_variants(env):
     out = subprocess.run([sys.executable, "-c", script], env=dict(os.environ, **env), capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_rbd_extras(trl, oracle, name):
+    """SURVEY 8f rank 2: world Jacobian, CoM Jacobian and gravity force vs the oracle (1e-9 per env matrix / vector);
+    E is not a multiple of the 32-env tile."""
+    E = 75
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    J, Jc, g = batch.rbd_extras(x["pose"])
+    rJ, rJc, rg = np.zeros_like(J), np.zeros_like(Jc), np.zeros_like(g)
+    for e in range(E):
+        rJ[e], rJc[e], rg[e] = om.rbd_extras(x["pose"][e])
+    assert_close(J.reshape(E, -1), rJ.reshape(E, -1), "world Jacobian")
+    assert_close(Jc.reshape(E, -1), rJc.reshape(E, -1), "CoM Jacobian")
+    assert_close(g, rg, "gravity force")
+    assert np.all(J[:, :, 6] == 0)  # dead root slot
+    J2, _, g2 = batch.rbd_extras(x["pose"], want_Jcom=False)
+    assert np.array_equal(J2, J) and np.array_equal(g2, g)

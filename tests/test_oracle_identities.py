@@ -206,3 +206,41 @@ def test_imitation_reward_properties(oracle, name):
         r2, _ = oracle.imitate_reward(m, None, x["pose"][e], x["vel"][e], kp, kv, x["body_vel"][e])
         assert 0 < r2 < r <= 1.0
         assert oracle.imitate_reward(m, None, x["pose"][e], x["vel"][e], kp, kv, x["body_vel"][e], fallen=1)[0] == 0
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_rbd_extras_identities(oracle, name):
+    """SURVEY 8f rank 2 (BuildJacobian / BuildCOMJacobian / CalcGravityForce / BuildEndEffectorJacobian), pinned by
+    identities that do not depend on the restatement: tau_g = -C(q, 0); the linear rows of Jcom times qdot equal the
+    CoM velocity of trlo_calc_com (computed through the end-effector-Jacobian path); J restricted to a joint's chain
+    equals that joint's end-effector Jacobian; the chain Jacobian times qdot is the finite-difference velocity of the
+    joint origin."""
+    m = oracle.Model(name)
+    x = synth.make_inputs(name, 6, seed=11)
+    for e in range(6):
+        q, qd = x["pose"][e], x["vel"][e]
+        J, Jc, g = m.rbd_extras(q)
+        _, C0 = m.rbd_update(q, np.zeros_like(qd))
+        assert np.allclose(g, -C0, rtol=1e-10, atol=1e-9 * max(1.0, np.abs(C0).max()))
+        com, com_vel = oracle.calc_com(m, q, qd)
+        assert np.allclose(Jc[3:] @ qd, com_vel, rtol=1e-9, atol=1e-9)
+        for j in range(m.N):
+            Je = m.end_eff_jacobian(q, j)
+            mask = np.zeros(m.n, dtype=bool)
+            k = j
+            while k != -1:
+                o, sz = int(m.offset[k]), int(m.size[k])
+                mask[o:o + sz] = True
+                k = int(m.parent[k])
+            assert np.allclose(Je[:, mask], J[:, mask], rtol=1e-10, atol=1e-11)
+            assert np.all(Je[:, ~mask] == 0)
+        # finite-difference velocity of the last joint's origin vs J qdot (linear part at the world origin:
+        # v_origin + omega x (-p) ... compare the point velocity v + omega x p)
+        j = m.N - 1
+        h = 1e-6
+        q1 = _integrate(m, q, qd, h)
+        p0 = m.joint_world_trans(q, j)[:3, 3]
+        p1 = m.joint_world_trans(q1, j)[:3, 3]
+        sv = m.end_eff_jacobian(q, j) @ qd
+        v_point = sv[3:] + np.cross(sv[:3], p0)
+        assert np.allclose((p1 - p0) / h, v_point, rtol=2e-4, atol=2e-5)
