@@ -147,6 +147,14 @@ int trl_imp_pd_update_control_force(trl_batch* b, double dt, const double* pose,
                                     const double* kp_or_null, const double* kd_or_null, double* inout_tau,
                                     double* out_mass_or_null, double* out_bias_or_null);
 
+/* cSimCharacter::ApplyControlForces + cJoint::ApplyTau (sim/SimCharacter.cpp:589-603; sim/Joint.cpp:162-221,300-318,
+ * 536-562): the step right after the torque computation -- per joint, the generalized torques become a (torque, force)
+ * pair, ClampTotalTorque / ClampTotalForce limit their norms (joint_mat TorqueLim / ForceLim), and the joint's world
+ * frame (FK of `pose`) maps them to equal-and-opposite world torques / forces on the child and parent bodies.
+ * pose, tau [E][n]; out_tau [E][n] = clamped generalized torques (in place allowed: out_tau may equal tau in DEVICE
+ * mode); out_body_wrench [E][N][6] = (torque xyz, force xyz) per body in world coordinates. Outputs may be NULL. */
+int trl_apply_control_forces(trl_batch* b, const double* pose, const double* tau, double* out_tau, double* out_body_wrench);
+
 /* cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.cpp:256-275,294-345,937-982): the RBD
  * quantities the FSM controllers read every substep next to M and C (BipedController3D.cpp:1065-1072,1301-1388,
  * DogController.cpp:897,982). pose [E][n]; out_J, out_Jcom [E][6][n] row-major (rows = wx wy wz vx vy vz in world

@@ -7,6 +7,7 @@
 //   trl::cImpPDController    <-> cImpPDController (sim/ImpPDController.h:9-55) incl. its cRBDModel
 //                                (GetMassMat / GetBiasForce, sim/RBDModel.h:15-29), batched over E envs
 //   trl::cRBDUtil            <-> cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.h)
+//   trl::cSimCharacter       <-> cSimCharacter::ApplyControlForces + cJoint::ApplyTau (sim/SimCharacter.cpp:589-603)
 //   trl::cKinCharacter       <-> cKinCharacter::Pose / SetOriginPos / SetOriginRot (anim/KinCharacter.h:15-45)
 //   trl::cGround             <-> cGround::SampleHeight (sim/Ground.h:93-97)
 //   trl::cTerrainRLCharController <-> ParseGround + BuildPoliState (sim/TerrainRLCharController.h:31-87)
@@ -159,6 +160,18 @@ public:
     static bool CalcGravityForce(cBatch& batch, const std::vector<double>& pose, std::vector<double>& out_g_force) {
         out_g_force.resize((size_t)batch.GetNumEnvs() * batch.GetNumDof());
         return trl_rbd_extras(batch.Handle(), pose.data(), nullptr, nullptr, out_g_force.data()) == TRL_OK;
+    }
+};
+
+// cSimCharacter::ApplyControlForces(tau) + cJoint::ApplyTau for all E envs: clamped generalized torques [E][n] and the
+// world-frame (torque, force) each body receives [E][N][6].
+class cSimCharacter {
+public:
+    static bool ApplyControlForces(cBatch& batch, const std::vector<double>& pose, const std::vector<double>& tau,
+                                   std::vector<double>& out_tau, std::vector<double>& out_body_wrench) {
+        out_tau.resize((size_t)batch.GetNumEnvs() * batch.GetNumDof());
+        out_body_wrench.resize((size_t)batch.GetNumEnvs() * batch.GetNumJoints() * 6);
+        return trl_apply_control_forces(batch.Handle(), pose.data(), tau.data(), out_tau.data(), out_body_wrench.data()) == TRL_OK;
     }
 };
 

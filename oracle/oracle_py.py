@@ -166,6 +166,13 @@ class Model:
         lib().trlo_rbd_extras(self.ref, _d(pose), _d(J), _d(Jc), _d(g))
         return J, Jc, g
 
+    def apply_control_forces(self, pose, tau):
+        """cSimCharacter::ApplyControlForces + cJoint::ApplyTau -> clamped tau [n], body wrenches [N][6] (world)"""
+        pose, tau = _c(pose), _c(tau)
+        out_tau, wr = np.zeros(self.n), np.zeros((self.N, 6))
+        lib().trlo_apply_control_forces(self.ref, _d(pose), _d(tau), _d(out_tau), _d(wr))
+        return out_tau, wr
+
     def end_eff_jacobian(self, pose, joint_id):
         pose = _c(pose)
         J = np.zeros((6, self.n))

@@ -1169,6 +1169,69 @@ void trlo_end_eff_jacobian(const trlo_model* m, const double* pose, int joint_id
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Torque post-processing: cSimCharacter::ApplyControlForces (sim/SimCharacter.cpp:589-603) ->
+ * cJoint::AddTau* (sim/Joint.cpp:536-562) -> cJoint::ApplyTau / ApplyTorque / ApplyForce with ClampTotalTorque /
+ * ClampTotalForce (sim/Joint.cpp:162-221,300-318): the generalized torques become clamped joint wrenches and then
+ * equal-and-opposite world-frame torques / forces on the parent and child bodies (what Bullet consumes).
+ * The joint's world rotation (cJoint::BuildWorldTrans = child body transform x joint-child transform) is taken from
+ * FK of `pose`, which is what it equals when the simulated bodies are consistent with the pose.
+ * out_tau [n]: the clamped generalized torques (same layout as tau; untouched slots are copied);
+ * out_body_wrench [N][6]: per body (torque xyz, force xyz) in world coordinates.
+ * ---------------------------------------------------------------------------------------- */
+enum { JD_TORQUE_LIM = 14, JD_FORCE_LIM = 15 };
+
+void trlo_apply_control_forces(const trlo_model* m, const double* pose, const double* tau, double* out_tau,
+                               double* out_body_wrench)
+{
+    int N = m->num_joints, n = m->num_dof;
+    if (out_tau) for (int i = 0; i < n; ++i) out_tau[i] = tau[i];
+    if (out_body_wrench) for (int i = 0; i < 6 * N; ++i) out_body_wrench[i] = 0;
+    for (int j = 0; j < N; ++j) {
+        int p = trlo_parent(m, j);
+        if (p == -1 || !trlo_valid_body(m, j)) continue; /* cJoint::IsValid: a constraint with a child body */
+        int off = trlo_param_offset(m, j), type = trlo_joint_type(m, j);
+        double tot[6] = { 0, 0, 0, 0, 0, 0 }; /* mTotalTau = [torque ; force] */
+        int has_torque = 0, has_force = 0;
+        switch (type) {
+        case TRLO_JOINT_REVOLUTE: tot[2] += tau[off]; has_torque = 1; break;
+        case TRLO_JOINT_PLANAR: /* note: the planar torque lands in slot 0 (Joint.cpp:541-546) */
+            tot[3] += tau[off]; tot[4] += tau[off + 1]; tot[0] += tau[off + 2]; has_torque = 1; has_force = 1; break;
+        case TRLO_JOINT_PRISMATIC: tot[3] += tau[off]; has_force = 1; break;
+        case TRLO_JOINT_SPHERICAL: tot[0] += tau[off]; tot[1] += tau[off + 1]; tot[2] += tau[off + 2]; has_torque = 1; break;
+        default: break; /* fixed */
+        }
+        mat4 W = joint_world_trans(m, pose, j);
+        if (has_torque) { /* ApplyTorque */
+            double mag = sqrt(tot[0] * tot[0] + tot[1] * tot[1] + tot[2] * tot[2]);
+            double lim = jrow(m, j)[JD_TORQUE_LIM];
+            if (mag > lim) { double sc = lim / mag; tot[0] *= sc; tot[1] *= sc; tot[2] *= sc; }
+            vec4 t = { { tot[0], tot[1], tot[2], 0 } };
+            vec4 w = mat4_mulv(&W, &t);
+            if (out_body_wrench)
+                for (int k = 0; k < 3; ++k) { out_body_wrench[6 * p + k] += -w.v[k]; out_body_wrench[6 * j + k] += w.v[k]; }
+        }
+        if (has_force) { /* ApplyForce */
+            double mag = sqrt(tot[3] * tot[3] + tot[4] * tot[4] + tot[5] * tot[5]);
+            double lim = jrow(m, j)[JD_FORCE_LIM];
+            if (mag > lim) { double sc = lim / mag; tot[3] *= sc; tot[4] *= sc; tot[5] *= sc; }
+            vec4 f = { { tot[3], tot[4], tot[5], 0 } };
+            vec4 w = mat4_mulv(&W, &f);
+            if (out_body_wrench)
+                for (int k = 0; k < 3; ++k) { out_body_wrench[6 * p + 3 + k] += -w.v[k]; out_body_wrench[6 * j + 3 + k] += w.v[k]; }
+        }
+        if (out_tau) { /* SetTotalTorque / SetTotalForce written back in the generalized layout */
+            switch (type) {
+            case TRLO_JOINT_REVOLUTE: out_tau[off] = tot[2]; break;
+            case TRLO_JOINT_PLANAR: out_tau[off] = tot[3]; out_tau[off + 1] = tot[4]; out_tau[off + 2] = tot[0]; break;
+            case TRLO_JOINT_PRISMATIC: out_tau[off] = tot[3]; break;
+            case TRLO_JOINT_SPHERICAL: out_tau[off] = tot[0]; out_tau[off + 1] = tot[1]; out_tau[off + 2] = tot[2]; break;
+            default: break;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Eigen 3.3 LDLT restated (Eigen/src/Cholesky/LDLT.h: ldlt_inplace<Lower>::unblocked + _solve_impl).
  * Lower triangle, diagonal pivoting, zero pivot => solution component 0 (Q1).
  * ---------------------------------------------------------------------------------------- */

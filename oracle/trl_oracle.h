@@ -103,6 +103,11 @@ void trlo_inertia_spatial(const trlo_model* m, int j, double out[36]);
 /* RBD extras: cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce
  * (sim/RBDUtil.cpp:256-275,294-345,937-982); J, Jcom row-major [6][n]; any output may be NULL */
 void trlo_rbd_extras(const trlo_model* m, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force);
+/* Torque post-processing: cSimCharacter::ApplyControlForces + cJoint::ApplyTau with
+ * ClampTotalTorque / ClampTotalForce (sim/SimCharacter.cpp:589-603, sim/Joint.cpp:162-221,300-318,536-562).
+ * out_tau [n] clamped generalized torques, out_body_wrench [N][6] world (torque, force) per body; either may be NULL */
+void trlo_apply_control_forces(const trlo_model* m, const double* pose, const double* tau, double* out_tau,
+                               double* out_body_wrench);
 /* cRBDUtil::BuildEndEffectorJacobian(model, joint_id), sim/RBDUtil.cpp:181-206; row-major [6][n] */
 void trlo_end_eff_jacobian(const trlo_model* m, const double* pose, int joint_id, double* out_J);
 

@@ -45,6 +45,7 @@ SYMBOLS = [
     ("trl_imp_pd_update_control_force", C.c_int, [_VP, C.c_double] + [_VP] * 10),
     ("trl_kin_tree_fk", C.c_int, [_VP, _VP, _VP, _VP]),
     ("trl_rbd_extras", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("trl_apply_control_forces", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     ("trl_kin_char_pose", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("trl_ground_set_heightfields", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, C.c_longlong, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("trl_ground_sample_height", C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),

@@ -202,6 +202,16 @@ class Batch:
         check(_capi.lib().trl_kin_tree_fk(self._h, *p), "trl_kin_tree_fk")
         return jw, bp
 
+    def apply_control_forces(self, pose, tau):
+        """cSimCharacter::ApplyControlForces + cJoint::ApplyTau -> clamped tau [E][n], body wrenches [E][N][6] (world)"""
+        n, N = self.model.num_dof, self.model.num_joints
+        out_tau = self._new((self.E, n), pose)
+        wr = self._new((self.E, N, 6), pose)
+        f8 = np.float64
+        p = self._prep([(pose, f8), (tau, f8), (out_tau, f8), (wr, f8)])
+        check(_capi.lib().trl_apply_control_forces(self._h, *p), "trl_apply_control_forces")
+        return out_tau, wr
+
     def rbd_extras(self, pose, want_J=True, want_Jcom=True, want_gravity_force=True):
         """cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce -> J [E][6][n], Jcom [E][6][n], tau_g [E][n]"""
         n = self.model.num_dof

@@ -336,6 +336,23 @@ extern "C" int trl_imp_pd_update_control_force(trl_batch* b, double dt, const do
     return finish(b, copies, rc);
 }
 
+extern "C" int trl_apply_control_forces(trl_batch* b, const double* pose, const double* tau, double* out_tau,
+                                        double* out_body_wrench) {
+    if (!b || !pose || !tau) { trl_set_error("trl_apply_control_forces: null argument"); return TRL_ERR_INVALID_ARG; }
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double *d_pose = nullptr, *d_tau = nullptr;
+    double *d_ot = nullptr, *d_w = nullptr;
+    if (!in_ptr(b, pose, E * n, &d_pose) || !in_ptr(b, tau, E * n, &d_tau) || !out_ptr(b, out_tau, E * n, &d_ot, copies) ||
+        !out_ptr(b, out_body_wrench, E * N * 6, &d_w, copies))
+        return TRL_ERR_CUDA;
+    int rc = trl_launch_apply_tau(b->d_model, b->model->dev, b->E, d_pose, d_tau, d_ot, d_w, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
 extern "C" int trl_rbd_extras(trl_batch* b, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force) {
     if (!b || !pose) { trl_set_error("trl_rbd_extras: null argument"); return TRL_ERR_INVALID_ARG; }
     Guard g(b->device);

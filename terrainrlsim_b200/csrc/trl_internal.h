@@ -68,6 +68,8 @@ struct DevModel {
     double kp[TRL_MAX_JOINTS];
     double kd[TRL_MAX_JOINTS];
     double joint_w[TRL_MAX_JOINTS];  // DiffWeight / sum|DiffWeight| (cScenarioExpImitate::CalcJointWeights)
+    double torque_lim[TRL_MAX_JOINTS];  // joint_mat TorqueLim / ForceLim (cJoint::ClampTotalTorque / ClampTotalForce)
+    double force_lim[TRL_MAX_JOINTS];
     double total_mass;
 
 };
@@ -127,6 +129,8 @@ int trl_pd_scratch_tile();
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream);
 int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_J,
                           double* out_Jcom, double* out_gforce, void* stream);
+int trl_launch_apply_tau(const DevModel* dm, const DevModel& hm, int E, const double* pose, const double* tau,
+                         double* out_tau, double* out_body_wrench, void* stream);
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
                   double* out_body_pos, void* stream);
 int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,

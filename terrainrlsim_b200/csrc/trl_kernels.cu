@@ -1250,6 +1250,107 @@ k_rbd_extras(const DevModel* __restrict__ M, int E, const double* __restrict__ p
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_apply_tau: cSimCharacter::ApplyControlForces + cJoint::ApplyTau (sim/SimCharacter.cpp:589-603, sim/Joint.cpp:
+// 162-221,300-318,536-562) -- thread per env, depth-first walk with the world transforms of the
+// current root path in shared memory. Generalized torques -> per-joint (torque, force), clamped by TorqueLim /
+// ForceLim, rotated to world coordinates by the joint's world frame and applied +/- to the child / parent body.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_apply_tau(const DevModel* __restrict__ M, int E, const double* __restrict__ pose, const double* __restrict__ tau,
+            double* __restrict__ out_tau, double* __restrict__ out_wrench) {
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kTile;
+    if (e0 >= E) return;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const int e = e0 + (env_ok ? lane : envs - 1);
+    const int N = M->N, n = M->n;
+    double* lvl = smem + (size_t)warp * (M->num_levels * 12 * kTile) + lane;
+    const double* q = pose + (size_t)e * n;
+    const double* te = tau + (size_t)e * n;
+    double* ot = out_tau ? out_tau + (size_t)e * n : nullptr;
+    double* ow = out_wrench ? out_wrench + (size_t)e * N * 6 : nullptr;
+    if (env_ok) {
+        if (ot) for (int i = 0; i < n; ++i) ot[i] = te[i];
+        if (ow) for (int i = 0; i < 6 * N; ++i) ow[i] = 0.0;
+    }
+    const int nev = 2 * N;
+    for (int evi = 0; evi < nev; ++evi) {
+        const int j = X->dfs_event[evi];
+        if (j < 0) continue;
+        const int o = X->offset[j], sz = X->size[j], p = X->parent[j];
+        double* W = lvl + (size_t)X->level[j] * 12 * kTile;
+        double qj[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) qj[i] = (i < sz) ? q[o + i] : 0.0;
+        double R[9], t[3], T[12];
+        joint_local_trans(X, j, qj, M->attR[j], M->attT[j], R, t);
+        if (p == -1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) T[i] = R[i];
+            T[9] = t[0]; T[10] = t[1]; T[11] = t[2];
+        } else {
+            const double* Wp = W - 12 * kTile;
+            double Tp[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) Tp[i] = Wp[i * kTile];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
+                T[9 + r] = Tp[9 + r] + (Tp[r * 3] * t[0] + Tp[r * 3 + 1] * t[1] + Tp[r * 3 + 2] * t[2]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) W[i * kTile] = T[i];
+        if (p == -1 || !X->valid_body[j]) continue;  // cJoint::IsValid: a constraint with a child body
+        const int type = X->type[j];
+        double tot[6] = {0, 0, 0, 0, 0, 0};  // mTotalTau = [torque ; force]
+        bool has_torque = false, has_force = false;
+        if (type == JT_REVOLUTE) { tot[2] = te[o]; has_torque = true; }
+        else if (type == JT_PLANAR) { tot[3] = te[o]; tot[4] = te[o + 1]; tot[0] = te[o + 2]; has_torque = has_force = true; }  // Joint.cpp:541-546
+        else if (type == JT_PRISMATIC) { tot[3] = te[o]; has_force = true; }
+        else if (type == JT_SPHERICAL) { tot[0] = te[o]; tot[1] = te[o + 1]; tot[2] = te[o + 2]; has_torque = true; }
+        if (has_torque) {
+            const double mag = sqrt(tot[0] * tot[0] + tot[1] * tot[1] + tot[2] * tot[2]);
+            const double lim = M->torque_lim[j];
+            if (mag > lim) { const double sc = lim / mag; tot[0] *= sc; tot[1] *= sc; tot[2] *= sc; }
+            if (ow && env_ok) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double w = T[r * 3] * tot[0] + T[r * 3 + 1] * tot[1] + T[r * 3 + 2] * tot[2];
+                    ow[6 * p + r] += -w;
+                    ow[6 * j + r] += w;
+                }
+            }
+        }
+        if (has_force) {
+            const double mag = sqrt(tot[3] * tot[3] + tot[4] * tot[4] + tot[5] * tot[5]);
+            const double lim = M->force_lim[j];
+            if (mag > lim) { const double sc = lim / mag; tot[3] *= sc; tot[4] *= sc; tot[5] *= sc; }
+            if (ow && env_ok) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double w = T[r * 3] * tot[3] + T[r * 3 + 1] * tot[4] + T[r * 3 + 2] * tot[5];
+                    ow[6 * p + 3 + r] += -w;
+                    ow[6 * j + 3 + r] += w;
+                }
+            }
+        }
+        if (ot && env_ok) {
+            if (type == JT_REVOLUTE) ot[o] = tot[2];
+            else if (type == JT_PLANAR) { ot[o] = tot[3]; ot[o + 1] = tot[4]; ot[o + 2] = tot[0]; }
+            else if (type == JT_PRISMATIC) ot[o] = tot[3];
+            else if (type == JT_SPHERICAL) { ot[o] = tot[0]; ot[o + 1] = tot[1]; ot[o + 2] = tot[2]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_pd_h: off-diagonal entries of H = M + dt*Kd from the columns k_pd_tree left in the scratch: H[c][a] = F_c . S_a
 // for every a on the ancestor chain of c (Featherstone's branch-induced sparsity; the other entries stay zero).
 // One warp per (tile of 32 envs, column c), lane = env: all loads / stores are 256-byte coalesced rows of the tile.
@@ -2692,6 +2793,16 @@ static int launch_pd_solve_t(const DevModel* dm, const DevModel& hm, int E, cons
     const int tiles = (E + kTile - 1) / kTile;
     k_pd_solve<NL><<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
                                                                                     p.status);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_apply_tau(const DevModel* dm, const DevModel& hm, int E, const double* pose, const double* tau,
+                         double* out_tau, double* out_body_wrench, void* stream) {
+    const size_t smem = (size_t)hm.num_levels * 12 * kTile * sizeof(double);
+    int rc = ensure_smem((const void*)k_apply_tau, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_apply_tau<<<tiles, 32, smem, (cudaStream_t)stream>>>(dm, E, pose, tau, out_tau, out_body_wrench);
     return (int)cudaGetLastError();
 }
 

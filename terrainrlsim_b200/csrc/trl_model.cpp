@@ -254,6 +254,8 @@ int trl_build_dev_model(trl_model* m) {
         d.attT[j][0] = jr[2]; d.attT[j][1] = jr[3]; d.attT[j][2] = jr[4];
         if (parent == -1) d.attT[j][0] = d.attT[j][1] = d.attT[j][2] = 0;  // PostProcessJointMat :1038-1040
         d.ix.level[j] = (parent == -1) ? 0 : d.ix.level[parent] + 1;
+        d.torque_lim[j] = jr[14];
+        d.force_lim[j] = jr[15];
         d.mass[j] = 0;
         if (d.ix.valid_body[j]) {
             double mass = br[1];

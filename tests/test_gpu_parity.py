@@ -452,3 +452,20 @@ def test_rbd_extras(trl, oracle, name):
     assert np.all(J[:, :, 6] == 0)  # dead root slot
     J2, _, g2 = batch.rbd_extras(x["pose"], want_Jcom=False)
     assert np.array_equal(J2, J) and np.array_equal(g2, g)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_apply_control_forces(trl, oracle, name):
+    """clamped joint torques and world-frame body wrenches vs the oracle; torques scaled so that about
+    half of the joints hit their limits."""
+    E = 70
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    rng = np.random.default_rng(21)
+    tau = rng.normal(size=(E, om.n)) * 150.0
+    ct, wr = batch.apply_control_forces(x["pose"], tau)
+    rct, rwr = np.zeros_like(ct), np.zeros_like(wr)
+    for e in range(E):
+        rct[e], rwr[e] = om.apply_control_forces(x["pose"][e], tau[e])
+    assert_close(ct, rct, "clamped tau")
+    assert_close(wr.reshape(E, -1), rwr.reshape(E, -1), "body wrenches")
+    assert (np.abs(ct - tau) > 0).any() and (ct == tau).any()  # some joints clamped, some not

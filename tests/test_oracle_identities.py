@@ -244,3 +244,44 @@ def test_rbd_extras_identities(oracle, name):
         sv = m.end_eff_jacobian(q, j) @ qd
         v_point = sv[3:] + np.cross(sv[:3], p0)
         assert np.allclose((p1 - p0) / h, v_point, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_apply_control_forces_identities(oracle, name):
+    """SURVEY 8f rank 3, pinned by: action = reaction (body wrenches sum to zero), clamping (norm <= limit, direction
+    kept, small torques untouched), and power balance for the rotational joints: sum_b T_b . omega_b = tau . qdot with
+    the body angular velocities taken from the end-effector Jacobians."""
+    m = oracle.Model(name)
+    x = synth.make_inputs(name, 5, seed=3)
+    rng = np.random.default_rng(9)
+    lim = m.joint_mat[:, 14]
+    for e in range(5):
+        q, qd = x["pose"][e], x["vel"][e]
+        tau = rng.normal(size=m.n) * 20.0
+        tau[:7] = 0
+        ct, wr = m.apply_control_forces(q, tau)
+        assert np.allclose(wr.sum(axis=0), 0, atol=1e-9)
+        small = tau * 1e-3
+        ct_s, wr_s = m.apply_control_forces(q, small)
+        assert np.array_equal(ct_s, small)
+        big = tau * 1e3
+        ct_b, _ = m.apply_control_forces(q, big)
+        for j in range(1, m.N):
+            o, sz, ty = int(m.offset[j]), int(m.size[j]), int(m.jtype[j])
+            if ty in (0, 4):  # revolute / spherical: pure torque
+                k = 1 if ty == 0 else 3
+                nb = np.linalg.norm(ct_b[o:o + k])
+                assert nb <= lim[j] * (1 + 1e-12)
+                if nb > 0:
+                    assert np.allclose(ct_b[o:o + k] / nb, big[o:o + k] / np.linalg.norm(big[o:o + k]), atol=1e-12)
+        if all(int(t) in (0, 3, 4) for t in m.jtype[1:]):
+            power = 0.0
+            for j in range(m.N):
+                om = (m.end_eff_jacobian(q, j) @ qd)[:3]
+                power += wr_s[j, :3] @ om
+            ref = 0.0
+            for j in range(1, m.N):
+                o, ty = int(m.offset[j]), int(m.jtype[j])
+                k = 1 if ty == 0 else (3 if ty == 4 else 0)
+                ref += small[o:o + k] @ qd[o:o + k]
+            assert np.isclose(power, ref, rtol=1e-9, atol=1e-12)
