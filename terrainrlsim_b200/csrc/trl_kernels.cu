@@ -1974,11 +1974,20 @@ k_kin_tile(const DevModel* __restrict__ M, const double* __restrict__ frames, in
     double* Tl = smem + lane;  // element k of joint a: Tl[(a * 12 + k) * 32]
     const double t = time[e];
     const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
-    int idx0, idx1 = 0;
-    double ph0, ph1 = 0.0;
-    motion_index_phase(M, frames, fs, t, &idx0, &ph0);
-    if (out_vel) motion_index_phase(M, frames, fs, t + ddt, &idx1, &ph1);
-    const double lerp0 = clampd(ph0, 0.0, 1.0), lerp1 = clampd(ph1, 0.0, 1.0);
+    // frame lookup (an exact fmod + a binary search) once per env and time, by the first two warps, shared through
+    // shared memory -- not once per joint
+    __shared__ double s_lerp[2][kTile];
+    __shared__ int s_idx[2][kTile];
+    for (int k = warp; k < (out_vel ? 2 : 1); k += nwarps) {
+        int idx;
+        double ph;
+        motion_index_phase(M, frames, fs, k ? t + ddt : t, &idx, &ph);
+        s_idx[k][lane] = idx;
+        s_lerp[k][lane] = clampd(ph, 0.0, 1.0);
+    }
+    __syncthreads();
+    const int idx0 = s_idx[0][lane], idx1 = out_vel ? s_idx[1][lane] : 0;
+    const double lerp0 = s_lerp[0][lane], lerp1 = out_vel ? s_lerp[1][lane] : 0.0;
     for (int j = warp; j < N; j += nwarps) {  // warp <-> joint
         const bool is_root = X->parent[j] == -1;
         double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
