@@ -1355,11 +1355,13 @@ k_apply_tau(const DevModel* __restrict__ M, int E, const double* __restrict__ po
 // for every a on the ancestor chain of c (Featherstone's branch-induced sparsity; the other entries stay zero).
 // One warp per (tile of 32 envs, column c), lane = env: all loads / stores are 256-byte coalesced rows of the tile.
 // ------------------------------------------------------------------------------------------------
+TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 constexpr int kHWarps = 8;
 __global__ void __launch_bounds__(kHWarps * 32)
 k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, double* __restrict__ out_mass) {
     KTrace trace_(TR_PD_H);
-    extern __shared__ double smem[];  // the tile's subspace columns S: [6 nl][32]
+    extern __shared__ __align__(16) double smem[];  // the tile's subspace columns S: [6 nl][32]
     __shared__ ModelIdx s_ix;
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;
@@ -1368,8 +1370,33 @@ k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, doub
     const int tile = blockIdx.x;
     const PdScratch SC = pd_scratch(n, nl);
     double* g = scratch + (size_t)tile * SC.stride * kTile;
-    for (int i = threadIdx.x; i < 6 * nl * kTile; i += blockDim.x) smem[i] = g[SC.scol * kTile + i];
-    __syncthreads();
+    {   // the tile's S block is contiguous in the scratch: one bulk async copy (TMA) for the whole block
+        __shared__ unsigned long long s_bar;
+        const unsigned bar_a = smem_u32(&s_bar);
+        const unsigned bytes = (unsigned)(6 * nl * kTile * sizeof(double));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem)),
+                         "l"(g + SC.scol * kTile), "r"(bytes), "r"(bar_a)
+                         : "memory");
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "TRL_HWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra TRL_HDONE_%=;\n"
+            "bra TRL_HWAIT_%=;\n"
+            "TRL_HDONE_%=:\n"
+            "}\n" ::"r"(bar_a)
+            : "memory");
+    }
     double* sc = g + lane;
     const double* Ss = smem + lane;
     const int e = tile * kTile + lane;
@@ -1402,7 +1429,6 @@ k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, doub
 // No pivoting: M + dt*Kd is SPD on the live dofs (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot
 // zeroes that solution component like Eigen's pseudo-inverse of D does.
 // ------------------------------------------------------------------------------------------------
-TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 TRL_DEV void tile_bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar, int lane) {
     const unsigned bar_a = smem_u32(bar);
