@@ -311,20 +311,9 @@ k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     KTrace trace_(TR_IMP_PD);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
-    {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
-        const int Nj = M->N;
-        for (int i = threadIdx.x; i < Nj * kCst; i += blockDim.x) {
-            const int j = i / kCst, k = i - j * kCst;
-            double v;
-            if (k < 9) v = M->attR[j][k];
-            else if (k < 12) v = M->attT[j][k - 9];
-            else if (k == 12) v = M->mass[j];
-            else if (k < 16) v = M->com[j][k - 13];
-            else if (k < 19) v = M->idiag[j][k - 16];
-            else if (k == 19) v = M->kp[j];
-            else v = M->kd[j];
-            smem[i] = v;
-        }
+    {   // per-joint double constants (DevModel::pd_cst, packed on the host): one coalesced copy
+        const int cnt = M->N * kCst;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
     }
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;
@@ -775,20 +764,9 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
     KTrace trace_(TR_PD_TREE);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
-    {   // per-joint double constants: attach rotation (9) + point (3), mass, CoM (3), inertia diagonal (3), Kp, Kd
-        const int Nj = M->N;
-        for (int i = threadIdx.x; i < Nj * kCst; i += blockDim.x) {
-            const int j = i / kCst, k = i - j * kCst;
-            double v;
-            if (k < 9) v = M->attR[j][k];
-            else if (k < 12) v = M->attT[j][k - 9];
-            else if (k == 12) v = M->mass[j];
-            else if (k < 16) v = M->com[j][k - 13];
-            else if (k < 19) v = M->idiag[j][k - 16];
-            else if (k == 19) v = M->kp[j];
-            else v = M->kd[j];
-            smem[i] = v;
-        }
+    {   // per-joint double constants (DevModel::pd_cst, packed on the host): one coalesced copy
+        const int cnt = M->N * kCst;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
     }
     stage_model_idx(&s_ix, M);
     const ModelIdx* X = &s_ix;

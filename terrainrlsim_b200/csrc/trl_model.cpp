@@ -325,6 +325,14 @@ int trl_build_dev_model(trl_model* m) {
         for (int i = 0; i < d.ix.size[j]; ++i) d.ix.dof_joint[o + i] = j;
     }
     d.nl = nl;
+    for (int j = 0; j < N; ++j) {
+        double* c = d.pd_cst + 21 * j;
+        for (int k = 0; k < 9; ++k) c[k] = d.attR[j][k];
+        for (int k = 0; k < 3; ++k) { c[9 + k] = d.attT[j][k]; c[13 + k] = d.com[j][k]; c[16 + k] = d.idiag[j][k]; }
+        c[12] = d.mass[j];
+        c[19] = d.kp[j];
+        c[20] = d.kd[j];
+    }
     for (int c = 0; c < nl; ++c) {
         int j = d.ix.col_joint[c];
         if (c > d.ix.first_col[j]) {
