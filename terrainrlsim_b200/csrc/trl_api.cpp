@@ -446,6 +446,8 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         pc.rscale[1] = 1.0 / pc.scale[2];
         pc.half[0] = (double)(pc.res_x - 1) * 0.5;
         pc.half[1] = (double)(pc.res_z - 1) * 0.5;
+        pc.cmax3[0] = pc.res_x - 1.0 - 0.0001;
+        pc.cmax3[1] = pc.res_z - 1.0 - 0.0001;
     }
     if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * (size_t)data_count), "cudaMalloc(heightfields)") ||
         !cuda_ok(cudaMemcpy(b->d_ground_data, data, sizeof(float) * (size_t)data_count, cudaMemcpyHostToDevice), "H2D(heightfields)") ||

@@ -215,6 +215,27 @@ TRL_DEV double grid_coord(double pos, double origin, double scale, double rscale
     return __dadd_rn(c, half);
 }
 
+// both grid coordinates of a sample with ONE range guard (the common case is two in-range operands)
+TRL_DEV void grid_coord2(double px, double pz, const DevPiece& pc, double& c0, double& c1) {
+    const double x = __dsub_rn(px, pc.origin[0]), z = __dsub_rn(pz, pc.origin[2]);
+    const unsigned ex = ((unsigned)__double2hiint(x) >> 20) & 0x7ffu, ez = ((unsigned)__double2hiint(z) >> 20) & 0x7ffu;
+    double qx, qz;
+    if ((ex - 423u) > 1200u || (ez - 423u) > 1200u) {  // zero, subnormal, huge, inf, NaN: IEEE division
+        qx = __ddiv_rn(x, pc.scale[0]);
+        qz = __ddiv_rn(z, pc.scale[2]);
+    } else {  // Markstein division by the per-piece constant spacing, see div_by_const
+        const double rx = pc.rscale[0], rz = pc.rscale[1], dx = pc.scale[0], dz = pc.scale[2];
+        const double ax = __dmul_rn(x, rx), az = __dmul_rn(z, rz);
+        const double e0x = __fma_rn(-ax, dx, x), e0z = __fma_rn(-az, dz, z);
+        const double bx = __fma_rn(e0x, rx, ax), bz = __fma_rn(e0z, rz, az);
+        const double e1x = __fma_rn(-bx, dx, x), e1z = __fma_rn(-bz, dz, z);
+        qx = __fma_rn(e1x, rx, bx);
+        qz = __fma_rn(e1z, rz, bz);
+    }
+    c0 = __dadd_rn(qx, pc.half[0]);
+    c1 = __dadd_rn(qz, pc.half[1]);
+}
+
 // A height sample split in two halves so callers can batch the (dependent-address) heightfield loads of several
 // samples before combining them: prep computes cell indices / weights, finish applies the reference's interpolation.
 struct SamplePrep {
@@ -257,12 +278,11 @@ TRL_DEV double sample_finish_2d(const SamplePrep& sp, float f0, float f1) {
 }
 
 TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
-    const double tol = 0.0001;
-    const int rx = pc.res_x, rz = pc.res_z;
-    double c0 = grid_coord(px, pc.origin[0], pc.scale[0], pc.rscale[0], pc.half[0]);
-    double c1 = grid_coord(pz, pc.origin[2], pc.scale[2], pc.rscale[1], pc.half[1]);
-    c0 = clampd(c0, 0.0, rx - 1.0 - tol);
-    c1 = clampd(c1, 0.0, rz - 1.0 - tol);
+    const int rx = pc.res_x;
+    double c0, c1;
+    grid_coord2(px, pz, pc, c0, c1);
+    c0 = clampd(c0, 0.0, pc.cmax3[0]);  // rx - 1.0 - tol, evaluated once per piece on the host
+    c1 = clampd(c1, 0.0, pc.cmax3[1]);
     const int i = (int)c0, j = (int)c1;
     const double lx = __dsub_rn(c0, (double)i), lz = __dsub_rn(c1, (double)j);
     const bool lower = (lz <= lx);

@@ -96,6 +96,7 @@ struct DevPiece {
     double bounds[4];
     double rscale[2];  // correctly-rounded 1/scale_x, 1/scale_z (host IEEE division) for div_by_const
     double half[2];    // (res_x - 1) * 0.5, (res_z - 1) * 0.5 (exact products)
+    double cmax3[2];   // 3-D clamp bounds res_x - 1.0 - tol, res_z - 1.0 - tol (GroundVar3D.cpp:602-621), host-evaluated
 };
 
 struct DevGround {
