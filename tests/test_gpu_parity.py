@@ -416,12 +416,25 @@ for name in {names!r}:
     err = rel_err(tau, ref)
     assert err < 1e-9, (name, err)
     assert np.all(batch.status() == 0)
+    # the fused step (all three chains) under the same hooks
+    from helpers import oracle_cfg, oracle_grounds
+    kind, fields = synth.make_grounds(name, 5)
+    batch.ground_set_heightfields(kind, fields)
+    grounds = oracle_grounds(oracle, kind, fields)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    out = batch.step_fused(dt, x)
+    ref = oracle.step_range(om, oracle_cfg(oracle, name), dict(x), grounds, dt)
+    for k, tol in (("tau", 1e-9), ("state", 1e-9), ("kin_pose", 1e-9), ("kin_vel", 1e-8), ("kin_body_pos", 1e-9)):
+        err = rel_err(out[k].reshape(E, -1), ref[k].reshape(E, -1))
+        assert err < tol, (name, k, err)
 print("VARIANT_OK")
 """
 
 
 @pytest.mark.parametrize("env", [{"TRL_PD_SPLIT": "0"}, {"TRL_PD_SOLVE_GENERIC": "1"}, {"TRL_PD_TREE": "0"},
-                                 {"TRL_PD_TREE": "0", "TRL_PD_GROUP": "32"},
+                                 {"TRL_PD_TREE": "0", "TRL_PD_GROUP": "32"}, {"TRL_KIN_THREAD": "0"}, {"TRL_KIN_THREAD": "1"},
+                                 {"TRL_STEP_OVERLAP": "0"}, {"TRL_HOST_SLICES": "1"},
                                  {"TRL_PD_SPLIT": "0", "TRL_PD_GROUP": "16"}])
 def test_pd_kernel_variants(env):
     """The launcher's tuning hooks select other kernel variants (monolithic warp-per-env PD, runtime-loop solve, wider

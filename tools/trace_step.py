@@ -22,7 +22,7 @@ def main():
     torch.cuda.set_device(0)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
-        wl = bench.Workload(name, E, 0, 0, sets=2 if use_graph else None)
+        wl = bench.Workload(name, E, 0, 0, sets=1 if use_graph else None)
         for d in drop:
             keys = {"pd": ["tau"], "kin": ["kin_pose", "kin_vel", "kin_body_pos"], "obs": ["state"]}[d]
             for i in range(wl.sets):
