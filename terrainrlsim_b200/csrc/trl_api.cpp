@@ -61,7 +61,10 @@ struct trl_batch {
     // lanes so one slice's uploads overlap the previous slice's kernels and downloads
     cudaStream_t side2[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_join2[3] = {nullptr, nullptr, nullptr}, ev_pv2 = nullptr;
-    int host_slices = 2;  // measured on B200 + PCIe Gen5: 2 slices +6 %, 4 = no gain, 8 = host-launch bound
+    int host_slices = 2;  // measured: 2 slices best (13.2 M env-steps/s); 4 and 8 lose to per-copy overheads
+    static constexpr int kMaxSlices = 16;
+    cudaEvent_t ev_up[kMaxSlices][3] = {}, ev_cmp[kMaxSlices][3] = {};  // per slice: inputs uploaded (per upload stream) / chain finished
+    cudaStream_t up_streams[3] = {nullptr, nullptr, nullptr};  // one H2D stream moves ~20 GB/s on this platform, three reach PCIe speed
     int overlap = 1;
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
@@ -197,7 +200,15 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join2[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     }
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv2, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
-    if (const char* hs = getenv("TRL_HOST_SLICES")) b->host_slices = std::max(1, atoi(hs));  // tuning hook
+    if (const char* hs = getenv("TRL_HOST_SLICES")) b->host_slices = std::min((int)trl_batch::kMaxSlices, std::max(1, atoi(hs)));  // tuning hook
+    for (int i = 0; i < trl_batch::kMaxSlices; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_up[i][k], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+            if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_cmp[i][k], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+        }
+    }
+    for (int k = 0; k < 3; ++k)
+        if (!cuda_ok(cudaStreamCreateWithFlags(&b->up_streams[k], cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
@@ -277,6 +288,14 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
         if (b->ev_join2[i]) cudaEventDestroy(b->ev_join2[i]);
     }
     if (b->ev_pv2) cudaEventDestroy(b->ev_pv2);
+    for (int i = 0; i < trl_batch::kMaxSlices; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            if (b->ev_up[i][k]) cudaEventDestroy(b->ev_up[i][k]);
+            if (b->ev_cmp[i][k]) cudaEventDestroy(b->ev_cmp[i][k]);
+        }
+    }
+    for (int k = 0; k < 3; ++k)
+        if (b->up_streams[k]) { cudaStreamSynchronize(b->up_streams[k]); cudaStreamDestroy(b->up_streams[k]); }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_pv) cudaEventDestroy(b->ev_pv);
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -533,9 +552,11 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
 }
 
 // HOST-pointer step, pipelined over env slices. The step is bound by PCIe (biped3D x 16384 envs: 20 MB up, 50 MB down
-// per step against ~0.13 ms of kernels), so the batch is cut into `host_slices` ranges of whole 32-env tiles and the
-// ranges alternate between two lanes of chain streams: while one range's results are copied back, the next range's
-// inputs go up and its kernels run (the copy engines for the two directions are independent).
+// per step against ~0.1 ms of kernels), so the batch is cut into `host_slices` ranges of whole 32-env tiles and run as
+// a three-stage pipeline: one upload stream copies slice after slice, the three chain streams compute a slice as soon
+// as its inputs have landed, and one download stream copies results back as each chain of a slice finishes. The copy
+// engines of the two directions and the SMs all work on different slices at the same time; the critical path is one
+// slice's upload + kernels plus the whole download.
 static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool want_pd, bool want_kin, bool want_obs) {
     const size_t E = b->E, n = b->model->n, N = b->model->N, F = (size_t)b->F;
     b->pool_next = 0;
@@ -567,45 +588,52 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
     if (!ok) { trl_set_error("trl_step_fused: device staging allocation failed"); return TRL_ERR_CUDA; }
 
     const size_t tile = (size_t)trl_pd_scratch_tile();
-    const size_t S = (size_t)b->host_slices;
+    const size_t S = (size_t)std::min(b->host_slices, (int)trl_batch::kMaxSlices);
     const size_t es = ((E + S - 1) / S + tile - 1) / tile * tile;  // envs per slice, whole tiles
+    cudaStream_t sB = b->side[0], sC = b->side[1], sA = b->side[2];  // kin, observation, stable-PD chains
+    // uploads: stream 0 = pose / vel (+ the small arrays), 1 = PD targets, 2 = body states; download: one stream
+    cudaStream_t s_up0 = b->up_streams[0], s_up1 = b->up_streams[1], s_up2 = b->up_streams[2], s_dn = b->side2[1];
     if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
-    for (int lane = 0; lane < 2; ++lane)
-        for (int i = 0; i < 3; ++i) cudaStreamWaitEvent(lane ? b->side2[i] : b->side[i], b->ev_fork, 0);
+    for (cudaStream_t st : {sA, sB, sC, s_up0, s_up1, s_up2, s_dn}) cudaStreamWaitEvent(st, b->ev_fork, 0);
     int rc = 0;
-    bool used[2] = {false, false};
-    auto up = [&](char* d, const void* h, size_t bpe, size_t e0, size_t ec, cudaStream_t st) {
-        if (d && !rc && cudaMemcpyAsync(d + e0 * bpe, static_cast<const char*>(h) + e0 * bpe, ec * bpe, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    cudaStream_t s_up = s_up0;
+    auto up = [&](char* d, const void* h, size_t bpe, size_t e0, size_t ec) {
+        if (d && !rc && cudaMemcpyAsync(d + e0 * bpe, static_cast<const char*>(h) + e0 * bpe, ec * bpe, cudaMemcpyHostToDevice, s_up) != cudaSuccess)
             rc = (int)cudaGetLastError();
     };
-    auto down = [&](void* h, const char* d, size_t bpe, size_t e0, size_t ec, cudaStream_t st) {
-        if (d && !rc && cudaMemcpyAsync(static_cast<char*>(h) + e0 * bpe, d + e0 * bpe, ec * bpe, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    auto down = [&](void* h, const char* d, size_t bpe, size_t e0, size_t ec) {
+        if (d && !rc && cudaMemcpyAsync(static_cast<char*>(h) + e0 * bpe, d + e0 * bpe, ec * bpe, cudaMemcpyDeviceToHost, s_dn) != cudaSuccess)
             rc = (int)cudaGetLastError();
     };
+    // the small per-env arrays go up once, whole (1.3 MB for 16384 envs): fewer copies per slice
+    if (want_obs) { up(d_ph, a->phase, 8, 0, E); up(d_fl, a->flip, 1, 0, E); }
+    if (want_kin) { up(d_time, a->kin_time, 8, 0, E); up(d_op, a->origin_pos, 24, 0, E); up(d_or, a->origin_rot, 32, 0, E); }
+    if (want_pd) up(d_ja, a->joint_active, N, 0, E);
     const size_t rec_bytes = trl_obs_env_rec_bytes();
     const size_t sc_stride = trl_pd_scratch_doubles(b->model->dev);
     int slice = 0;
     for (size_t e0 = 0; e0 < E && !rc; e0 += es, ++slice) {
         const size_t ec = std::min(es, E - e0);
-        const int lane = slice & 1;
-        used[lane] = true;
-        cudaStream_t sB = lane ? b->side2[0] : b->side[0];  // kin chain
-        cudaStream_t sC = lane ? b->side2[1] : b->side[1];  // observation chain
-        cudaStream_t sA = lane ? b->side2[2] : b->side[2];  // stable-PD chain
-        cudaEvent_t ev_pv = lane ? b->ev_pv2 : b->ev_pv;
-        // pose / vel are shared by the PD and observation chains: upload on one, the other waits for it
-        cudaStream_t s_pv = want_obs ? sC : sA;
-        up(d_pose, a->pose, n * 8, e0, ec, s_pv);
-        up(d_vel, a->vel, n * 8, e0, ec, s_pv);
-        if (want_pd && s_pv != sA) { cudaEventRecord(ev_pv, s_pv); cudaStreamWaitEvent(sA, ev_pv, 0); }
+        s_up = s_up0;
+        up(d_pose, a->pose, n * 8, e0, ec);
+        up(d_vel, a->vel, n * 8, e0, ec);
+        cudaEventRecord(b->ev_up[slice][0], s_up0);
+        // submission order = service order on the copy engines: the observation chain's inputs go first (its [E][F]
+        // state is 3/4 of the download, which is the long pole), the PD targets after them
         if (want_obs) {
-            up(d_bp, a->body_pos, N * 24, e0, ec, sC); up(d_bv, a->body_vel, N * 24, e0, ec, sC);
-            up(d_ph, a->phase, 8, e0, ec, sC); up(d_fl, a->flip, 1, e0, ec, sC);
+            s_up = s_up2;
+            up(d_bp, a->body_pos, N * 24, e0, ec); up(d_bv, a->body_vel, N * 24, e0, ec);
+            cudaEventRecord(b->ev_up[slice][2], s_up2);
         }
-        if (want_kin) { up(d_time, a->kin_time, 8, e0, ec, sB); up(d_op, a->origin_pos, 24, e0, ec, sB); up(d_or, a->origin_rot, 32, e0, ec, sB); }
-        if (want_pd) { up(d_tp, a->tar_pose, n * 8, e0, ec, sA); up(d_tv, a->tar_vel, n * 8, e0, ec, sA); up(d_ja, a->joint_active, N, e0, ec, sA); }
+        if (want_pd) {
+            s_up = s_up1;
+            up(d_tp, a->tar_pose, n * 8, e0, ec); up(d_tv, a->tar_vel, n * 8, e0, ec);
+            cudaEventRecord(b->ev_up[slice][1], s_up1);
+        }
         auto at = [&](char* d, size_t bpe) { return d ? d + e0 * bpe : nullptr; };
         if (!rc && want_obs) {
+            cudaStreamWaitEvent(sC, b->ev_up[slice][0], 0);
+            cudaStreamWaitEvent(sC, b->ev_up[slice][2], 0);
             DevGround g2 = b->ground;
             if (g2.env_to_field) g2.env_to_field += e0;
             rc = trl_launch_poli_state(b->d_model, b->model->dev, g2, b->cfg, b->F, (int)ec, (const double*)at(d_pose, n * 8),
@@ -614,18 +642,19 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
                                        (const unsigned char*)at(d_fl, 1), b->d_sample_local,
                                        static_cast<char*>(b->d_env_rec) + e0 * rec_bytes, (double*)at(d_st, F * 8), nullptr, sC);
             b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
-            down(a->out_state, d_st, F * 8, e0, ec, sC);
+            cudaEventRecord(b->ev_cmp[slice][1], sC);
         }
         if (!rc && want_kin) {
+            cudaStreamWaitEvent(sB, b->ev_up[slice][0], 0);  // the small arrays went up ahead of slice 0 on stream 0
             rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, (int)ec, (const double*)at(d_time, 8),
                                 (const double*)at(d_op, 24), (const double*)at(d_or, 32), (double*)at(d_kp, n * 8),
                                 (double*)at(d_kv, n * 8), (double*)at(d_kbp, N * 24), sB);
             b->launches += 1;
-            down(a->out_kin_pose, d_kp, n * 8, e0, ec, sB);
-            down(a->out_kin_vel, d_kv, n * 8, e0, ec, sB);
-            down(a->out_kin_body_pos, d_kbp, N * 24, e0, ec, sB);
+            cudaEventRecord(b->ev_cmp[slice][0], sB);
         }
         if (!rc && want_pd) {
+            cudaStreamWaitEvent(sA, b->ev_up[slice][0], 0);
+            cudaStreamWaitEvent(sA, b->ev_up[slice][1], 0);
             if (a->dt > 0) {
                 StepPtrs p{};
                 p.dt = a->dt;
@@ -640,16 +669,39 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
             } else {
                 cudaMemsetAsync(at(d_tau, n * 8), 0, ec * n * 8, sA);
             }
-            down(a->out_tau, d_tau, n * 8, e0, ec, sA);
+            cudaEventRecord(b->ev_cmp[slice][2], sA);
+        }
+        // downloads of this slice, in the order the chains finish
+        if (!rc && want_kin) {
+            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][0], 0);
+            down(a->out_kin_pose, d_kp, n * 8, e0, ec);
+            down(a->out_kin_vel, d_kv, n * 8, e0, ec);
+            down(a->out_kin_body_pos, d_kbp, N * 24, e0, ec);
+        }
+        if (!rc && want_obs) {
+            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][1], 0);
+            down(a->out_state, d_st, F * 8, e0, ec);
+        }
+        if (!rc && want_pd) {
+            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][2], 0);
+            down(a->out_tau, d_tau, n * 8, e0, ec);
         }
     }
-    for (int lane = 0; lane < 2; ++lane) {  // join (also on error, so the streams stay consistent)
-        if (!used[lane]) continue;
-        for (int i = 0; i < 3; ++i) {
-            cudaEvent_t ev = lane ? b->ev_join2[i] : b->ev_join[i];
-            cudaEventRecord(ev, lane ? b->side2[i] : b->side[i]);
-            cudaStreamWaitEvent(b->stream, ev, 0);
+    {   // join everything back into the caller's stream (also on error, so the streams stay consistent)
+        int k = 0;
+        for (cudaStream_t st : {sB, sC, sA}) {
+            cudaEventRecord(b->ev_join[k], st);
+            cudaStreamWaitEvent(b->stream, b->ev_join[k], 0);
+            ++k;
         }
+        cudaEventRecord(b->ev_join2[0], s_up0);
+        cudaStreamWaitEvent(b->stream, b->ev_join2[0], 0);
+        cudaEventRecord(b->ev_join2[1], s_dn);
+        cudaStreamWaitEvent(b->stream, b->ev_join2[1], 0);
+        cudaEventRecord(b->ev_join2[2], s_up1);
+        cudaStreamWaitEvent(b->stream, b->ev_join2[2], 0);
+        cudaEventRecord(b->ev_pv2, s_up2);
+        cudaStreamWaitEvent(b->stream, b->ev_pv2, 0);
     }
     if (rc) {
         cudaStreamSynchronize(b->stream);

@@ -36,8 +36,26 @@ def main():
         lib = _capi.lib()
         assert lib.trl_debug_trace_enable(1) == 0
         buf = (C.c_ulonglong * 32)()
+        host = "--host" in sys.argv  # HOST pointer mode: pinned host buffers, sliced pipeline; spans cover all slices
+        if host:
+            import time
+            hin = {k: torch.from_numpy(v).pin_memory() for k, v in wl.host_inputs.items()}
+            n, N, F = wl.model.num_dof, wl.model.num_joints, wl.batch.F
+            hout = {"tau": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                    "kin_pose": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                    "kin_vel": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+                    "kin_body_pos": torch.empty((E, N, 3), dtype=torch.float64).pin_memory(),
+                    "state": torch.empty((E, F), dtype=torch.float64).pin_memory()}
+            hargs = wl.batch.make_step_args(wl.dt, {k: t.numpy() for k, t in hin.items()}, {k: t.numpy() for k, t in hout.items()})
+            wl.batch.set_stream(None)
+            for _ in range(3):
+                wl.batch.step_fused_args(hargs)
         for rep in range(4):
-            if use_graph:
+            if host:
+                t0w = time.perf_counter()
+                wl.batch.step_fused_args(hargs)
+                print("host-mode step wall time %.1f us" % ((time.perf_counter() - t0w) * 1e6))
+            elif use_graph:
                 wl.graph.replay()
             else:
                 wl.step()
