@@ -2364,7 +2364,8 @@ struct ObsEnvRec {
     int flip;
     int pad;
     int piece;  // >= 0: every ground sample of this env falls into this terrain piece (and into no earlier one)
-    int pad2, pad3, pad4;  // sizeof % 16 == 0 (staged with 16-byte copies)
+    int pad2;  // bitmask of the terrain pieces the env's sample bounding box touches (candidates of the per-sample search)
+    int pad3, pad4;  // sizeof % 16 == 0 (staged with 16-byte copies)
 };
 
 // k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env (the per-env prologue is redundant across the lanes, so few lanes win).
@@ -2432,7 +2433,8 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
         r.flip = flip; r.pad = has_ground ? 1 : 0;
         r.piece = -1;
-        r.pad2 = r.pad3 = r.pad4 = 0;
+        r.pad2 = 0xf;  // candidate pieces of the per-sample search (all, unless the bounding-box test below narrows it)
+        r.pad3 = r.pad4 = 0;
         if ((gkind == 1 || gkind == 2) && cfg.num_samples > 0 && sample_local) {
             // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
             // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
@@ -2461,13 +2463,17 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
             x0 -= ex; x1 += ex; z0 -= ez; z1 += ez;
             if (finite) {
                 const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
+                bool open_scan = true;  // no earlier piece touches the box so far
+                int cand = 0;           // pieces the box touches: the only ones a sample of this env can fall into
                 for (int s = 0; s < gP; ++s) {
                     const double b0 = pcs[s].bounds[0], b1 = pcs[s].bounds[1], b2 = pcs[s].bounds[2], b3 = pcs[s].bounds[3];
                     const bool inside = (gkind == 1) ? (x0 >= b0 && x1 <= b1) : (x0 >= b0 && x1 <= b1 && z0 >= b2 && z1 <= b3);
                     const bool apart = (gkind == 1) ? (x1 < b0 || x0 > b1) : (x1 < b0 || x0 > b1 || z1 < b2 || z0 > b3);
-                    if (inside) { r.piece = s; break; }
-                    if (!apart) break;  // straddles this piece: per-sample search
+                    if (!apart) cand |= 1 << s;
+                    if (open_scan && inside) r.piece = s;
+                    if (!apart) open_scan = false;  // a later piece can only be "first containing" for some samples
                 }
+                r.pad2 = cand;
             }
         }
         rec[e] = r;
@@ -2631,7 +2637,35 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
         }
         return;
     }
-    for (int s = threadIdx.x; s < G; s += blockDim.x) {  // general path: the env straddles pieces (or has no heightfield)
+    if (gkind == 1 || gkind == 2) {
+        // general path: the env's samples straddle pieces. The search runs over the pieces its bounding box touches only
+        // (block-uniform mask from k_obs_env), lowest index first like the reference's scan; 4 samples per thread.
+        const int cand = r.pad2;
+        for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
+#pragma unroll
+            for (int k = 0; k < kObsSPT; ++k) {
+                const int s = s0 + k * blockDim.x;
+                if (s >= G) break;
+                const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
+                const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
+                const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
+                const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
+                int pi = -1;
+#pragma unroll
+                for (int t = 3; t >= 0; --t)
+                    if (t < gP && ((cand >> t) & 1) && piece_contains(gkind, s_pieces[t], px, pz)) pi = t;
+                int vs, cell[3];
+                const double hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - r.it1;
+                out[s] = hs;
+                if (WANT_CELL && out_cell) {
+                    int* oc = out_cell + ((size_t)e * G + s) * 3;
+                    oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+                }
+            }
+        }
+        return;
+    }
+    for (int s = threadIdx.x; s < G; s += blockDim.x) {  // no heightfield (flat ground / none)
         double hs = 0.0;
         int cell[3] = {-1, 0, 0};
         if (has_ground) {
