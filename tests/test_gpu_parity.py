@@ -482,3 +482,29 @@ def test_apply_control_forces(trl, oracle, name):
     assert_close(ct, rct, "clamped tau")
     assert_close(wr.reshape(E, -1), rwr.reshape(E, -1), "body wrenches")
     assert (np.abs(ct - tau) > 0).any() and (ct == tau).any()  # some joints clamped, some not
+
+
+def test_widened_rows_device_pointer_mode(trl, oracle):
+    """trl_rbd_extras / trl_apply_control_forces / trl_imitate_calc_reward with device pointers (torch CUDA tensors,
+    asynchronous on the batch's stream) give bit-identical results to the host-pointer calls."""
+    import torch
+    name, E = "biped3d", 100
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=True, num_fields=3)
+    rng = np.random.default_rng(4)
+    tau = rng.normal(size=(E, om.n)) * 120.0
+    hJ, hJc, hg = batch.rbd_extras(x["pose"])
+    hct, hwr = batch.apply_control_forces(x["pose"], tau)
+    kin_pose, kin_vel = batch.kin_char_pose(x["kin_time"], x["origin_pos"], x["origin_rot"])
+    hr = batch.imitate_calc_reward(x["pose"], x["vel"], kin_pose, kin_vel, x["body_vel"], None)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in
+         dict(pose=x["pose"], vel=x["vel"], tau=tau, kin_pose=kin_pose, kin_vel=kin_vel, body_vel=x["body_vel"]).items()}
+    batch.use_torch_stream()
+    dJ, dJc, dg = batch.rbd_extras(d["pose"])
+    dct, dwr = batch.apply_control_forces(d["pose"], d["tau"])
+    dr = batch.imitate_calc_reward(d["pose"], d["vel"], d["kin_pose"], d["kin_vel"], d["body_vel"], None)
+    batch.sync()
+    torch.cuda.synchronize()
+    for a, b_ in ((hJ, dJ), (hJc, dJc), (hg, dg), (hct, dct), (hwr, dwr)):
+        assert np.array_equal(a, b_.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(hr, dr.cpu().numpy(), equal_nan=True)
+    batch.set_stream(None)
