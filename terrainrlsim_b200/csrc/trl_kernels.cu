@@ -1104,16 +1104,19 @@ k_rbd_extras(const DevModel* __restrict__ M, int E, const double* __restrict__ p
     double* Rq = ws;
     double* lvl = ws + kTreeHead * kTile;
     const double* q = pose + (size_t)e * n;
-    double* Jw = out_J ? out_J + (size_t)e * 6 * n : nullptr;
-    double* Jc = out_Jcom ? out_Jcom + (size_t)e * 6 * n : nullptr;
+    // J / Jcom rows are assembled in shared memory ([lane][6n], odd row stride: conflict-free) and written out coalesced
+    // at the end: a thread-per-env kernel writing its own 1.2 KB row directly would touch 32 sectors per store.
+    const int jstride = (6 * n) | 1;
+    double* jbuf = smem + (size_t)(blockDim.x >> 5) * ((kTreeHead + M->num_levels * kXSlot) * kTile) +
+                   (size_t)warp * 2 * kTile * jstride;
+    double* Jw = out_J ? jbuf + lane * jstride : nullptr;
+    double* Jc = out_Jcom ? jbuf + (kTile + lane) * jstride : nullptr;
     double* tg = out_gforce ? out_gforce + (size_t)e * n : nullptr;
-    if (env_ok) {  // dead dof slots and the columns of joints without dofs stay zero
-        for (int i = 0; i < 6 * n; ++i) {
-            if (Jw) Jw[i] = 0.0;
-            if (Jc) Jc[i] = 0.0;
-        }
-        if (tg) for (int i = 0; i < n; ++i) tg[i] = 0.0;
+    for (int i = 0; i < 6 * n; ++i) {  // dead dof slots and the columns of joints without dofs stay zero
+        if (Jw) Jw[i] = 0.0;
+        if (Jc) Jc[i] = 0.0;
     }
+    if (env_ok && tg) for (int i = 0; i < n; ++i) tg[i] = 0.0;
     double Rw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pr[3] = {0, 0, 0}, gr[3] = {0, 0, 0};
     const double inv_total = 1.0 / M->total_mass;
     const int nev = 2 * N;
@@ -1198,21 +1201,19 @@ k_rbd_extras(const DevModel* __restrict__ M, int E, const double* __restrict__ p
                 cross3(pr, ww, cx);
                 vw[0] = vr[0] + cx[0]; vw[1] = vr[1] + cx[1]; vw[2] = vr[2] + cx[2];
                 const int di = X->col_dof[c];
-                if (env_ok) {
-                    if (Jw) {
+                if (Jw) {
 #pragma unroll
-                        for (int r = 0; r < 3; ++r) { Jw[r * n + di] = ww[r]; Jw[(3 + r) * n + di] = vw[r]; }
-                    }
-                    if (Jc) {
-                        double px[3];
-                        cross3(pc, ww, px);
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) { Jc[r * n + di] = mf * ww[r]; Jc[(3 + r) * n + di] = mf * vw[r] - px[r]; }
-                    }
-                    if (tg)
-                        tg[di] = vb ? ((sv[0] * ng[0] + sv[1] * ng[1] + sv[2] * ng[2]) +
-                                       mg * (sv[3] * gr[0] + sv[4] * gr[1] + sv[5] * gr[2])) : 0.0;
+                    for (int r = 0; r < 3; ++r) { Jw[r * n + di] = ww[r]; Jw[(3 + r) * n + di] = vw[r]; }
                 }
+                if (Jc) {
+                    double px[3];
+                    cross3(pc, ww, px);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) { Jc[r * n + di] = mf * ww[r]; Jc[(3 + r) * n + di] = mf * vw[r] - px[r]; }
+                }
+                if (tg && env_ok)
+                    tg[di] = vb ? ((sv[0] * ng[0] + sv[1] * ng[1] + sv[2] * ng[2]) +
+                                   mg * (sv[3] * gr[0] + sv[4] * gr[1] + sv[5] * gr[2])) : 0.0;
             }
             if (lv > 0) {
                 double* Wp = W - kXSlot * kTile;
@@ -1223,6 +1224,19 @@ k_rbd_extras(const DevModel* __restrict__ M, int E, const double* __restrict__ p
                     for (int i = 0; i < 4; ++i) Wp[(kXSlotG + i) * kTile] += W[(kXSlotG + i) * kTile];
                 }
             }
+        }
+    }
+    __syncwarp();
+    for (int r = 0; r < envs; ++r) {  // coalesced copy-out, one env row at a time
+        if (out_J) {
+            double* o = out_J + (size_t)(e0 + r) * 6 * n;
+            const double* src = jbuf + r * jstride;
+            for (int i = lane; i < 6 * n; i += 32) o[i] = src[i];
+        }
+        if (out_Jcom) {
+            double* o = out_Jcom + (size_t)(e0 + r) * 6 * n;
+            const double* src = jbuf + (kTile + r) * jstride;
+            for (int i = lane; i < 6 * n; i += 32) o[i] = src[i];
         }
     }
 }
@@ -2856,7 +2870,8 @@ int trl_launch_apply_tau(const DevModel* dm, const DevModel& hm, int E, const do
 int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_J,
                           double* out_Jcom, double* out_gforce, void* stream) {
     const int wpb = 1;
-    const size_t smem = (size_t)(kTreeHead + hm.num_levels * kXSlot) * kTile * sizeof(double) * wpb;
+    const size_t smem = ((size_t)(kTreeHead + hm.num_levels * kXSlot) * kTile + (size_t)2 * kTile * ((6 * hm.n) | 1)) * sizeof(double) * wpb;
+    if (smem > 227 * 1024 - 2048) return (int)cudaErrorInvalidValue;
     int rc = ensure_smem((const void*)k_rbd_extras, smem);
     if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
