@@ -2798,13 +2798,14 @@ double trl_fp64_probe_tflops(void* stream) {
 
 static int ensure_smem(const void* func, size_t bytes) {
     // set once per (kernel, size): cudaFuncSetAttribute is kept out of graph captures
-    static const void* seen_func[16];
-    static size_t seen_bytes[16];
+    constexpr int kSeen = 128;
+    static const void* seen_func[kSeen];
+    static size_t seen_bytes[kSeen];
     static int nseen = 0;
     if (bytes > 48 * 1024) {
         for (int i = 0; i < nseen; ++i)
             if (seen_func[i] == func && seen_bytes[i] >= bytes) return 0;
-        if (nseen < 16) { seen_func[nseen] = func; seen_bytes[nseen] = bytes; ++nseen; }
+        if (nseen < kSeen) { seen_func[nseen] = func; seen_bytes[nseen] = bytes; ++nseen; }
         cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (err != cudaSuccess) return (int)err;
     }
