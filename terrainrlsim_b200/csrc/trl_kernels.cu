@@ -20,6 +20,7 @@
 // and a 6-vector recurrence. Numbers agree with the reference's joint-local formulation to ~1e-13.
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
 #include <cstdlib>
 #include <type_traits>
 #include <math_constants.h>
@@ -2802,6 +2803,8 @@ static int ensure_smem(const void* func, size_t bytes) {
     static const void* seen_func[kSeen];
     static size_t seen_bytes[kSeen];
     static int nseen = 0;
+    static std::mutex mu;  // batches on different host threads share this cache
+    std::lock_guard<std::mutex> lock(mu);
     if (bytes > 48 * 1024) {
         for (int i = 0; i < nseen; ++i)
             if (seen_func[i] == func && seen_bytes[i] >= bytes) return 0;
