@@ -119,6 +119,11 @@ int trl_batch_set_pointer_mode(trl_batch* b, int mode);
 #define TRL_STREAM_OWN ((void*)(~(unsigned long long)0))
 int trl_batch_set_stream(trl_batch* b, void* cuda_stream);
 int trl_batch_sync(trl_batch* b);
+/* HOST pointer mode only: with `on`, trl_step_fused returns as soon as the step's uploads, kernels and downloads are
+ * enqueued; the outputs are valid after trl_batch_sync(). The input and output arrays must be page-locked and must not
+ * be touched, and no other call may be made on this batch, until then. Two batches driven alternately this way overlap
+ * one's download with the other's upload and kernels (the synchronous call is PCIe-bound). */
+int trl_batch_set_host_async(trl_batch* b, int on);
 /* GetPoliStateSize() (sim/TerrainRLCharController.cpp:438-493, CtController.cpp:482-504) */
 int trl_poli_state_size(const trl_batch* b);
 int trl_batch_num_envs(const trl_batch* b);

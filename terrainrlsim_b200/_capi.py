@@ -40,6 +40,7 @@ SYMBOLS = [
     ("trl_poli_state_size", C.c_int, [_VP]),
     ("trl_batch_num_envs", C.c_int, [_VP]),
     ("trl_batch_launch_count", C.c_longlong, [_VP]),
+    ("trl_batch_set_host_async", C.c_int, [_VP, C.c_int]),
     ("trl_debug_trace_enable", C.c_int, [C.c_int]),
     ("trl_debug_trace_read", C.c_int, [C.POINTER(C.c_ulonglong)]),
     ("trl_imp_pd_update_control_force", C.c_int, [_VP, C.c_double] + [_VP] * 10),

@@ -339,5 +339,9 @@ class Batch:
             setattr(a, "out_" + k, ptr)
         return a
 
+    def set_host_async(self, on):
+        """HOST pointer mode: step_fused_args returns after enqueueing; sync() completes the step (pinned buffers only)."""
+        check(_capi.lib().trl_batch_set_host_async(self._h, 1 if on else 0), "trl_batch_set_host_async")
+
     def step_fused_args(self, args):
         return _capi.lib().trl_step_fused(self._h, C.byref(args))

@@ -66,6 +66,7 @@ struct trl_batch {
     cudaEvent_t ev_up[kMaxSlices][3] = {}, ev_cmp[kMaxSlices][3] = {};  // per slice: inputs uploaded (per upload stream) / chain finished
     cudaStream_t up_streams[3] = {nullptr, nullptr, nullptr};  // one H2D stream moves ~20 GB/s on this platform, three reach PCIe speed
     int overlap = 1;
+    int host_async = 0;  // HOST-pointer trl_step_fused returns after enqueueing; trl_batch_sync() completes it
     DevModel* d_model = nullptr;
     double* d_frames = nullptr;
     int* d_status = nullptr;
@@ -708,7 +709,14 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
         trl_set_error(std::string("trl_step_fused: ") + cudaGetErrorString((cudaError_t)rc));
         return TRL_ERR_CUDA;
     }
+    if (b->host_async) return TRL_OK;  // the caller completes the step with trl_batch_sync()
     return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? TRL_OK : TRL_ERR_CUDA;
+}
+
+extern "C" int trl_batch_set_host_async(trl_batch* b, int on) {
+    if (!b) return TRL_ERR_INVALID_ARG;
+    b->host_async = on ? 1 : 0;
+    return TRL_OK;
 }
 
 extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
@@ -720,7 +728,7 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
     if (want_kin && (b->model->num_frames < 2 || !a->kin_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
     if (want_obs && (!a->body_pos || !a->body_vel)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
     if (want_obs && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
-    if (b->ptr_mode == TRL_PTR_HOST && b->overlap && b->host_slices > 1 && E >= 2048)
+    if (b->ptr_mode == TRL_PTR_HOST && b->overlap && (b->host_async || (b->host_slices > 1 && E >= 2048)))
         return step_fused_host_sliced(b, a, want_pd, want_kin, want_obs);
     b->pool_next = 0;
     std::vector<OutCopy> copies;

@@ -508,3 +508,34 @@ def test_widened_rows_device_pointer_mode(trl, oracle):
         assert np.array_equal(a, b_.cpu().numpy(), equal_nan=True)
     assert np.array_equal(hr, dr.cpu().numpy(), equal_nan=True)
     batch.set_stream(None)
+
+
+def test_host_async_mode_matches_synchronous(trl, oracle):
+    """trl_batch_set_host_async: the HOST-pointer step returns after enqueueing and trl_batch_sync completes it; two
+    batches driven alternately give the same bits as the synchronous call (pinned buffers)."""
+    import torch
+    name, E = "biped3d", 2304
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    batches, args, outs, refs = [], [], [], []
+    for k in range(2):
+        om, pm, batch, x, _ = _setup(trl, oracle, name, E, num_fields=3)
+        x = synth.make_inputs(name, E, seed=100 + k)
+        refs.append(batch.step_fused(dt, x))
+        hin = {kk: torch.from_numpy(v).pin_memory() for kk, v in x.items()}
+        hout = {kk: torch.empty(v.shape, dtype=torch.float64).pin_memory() for kk, v in refs[-1].items()}
+        batch.set_stream(None)
+        args.append((hin, hout, batch.make_step_args(dt, {kk: t.numpy() for kk, t in hin.items()},
+                                                      {kk: t.numpy() for kk, t in hout.items()})))
+        batch.set_host_async(True)
+        batches.append(batch)
+        outs.append(hout)
+    for rep in range(3):
+        for b, a in zip(batches, args):
+            assert b.step_fused_args(a[2]) == 0
+        for b in batches:
+            b.sync()
+    for k in range(2):
+        for kk, ref in refs[k].items():
+            assert np.array_equal(outs[k][kk].numpy(), ref, equal_nan=True), (k, kk)
+        batches[k].set_host_async(False)
