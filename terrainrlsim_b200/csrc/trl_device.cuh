@@ -102,14 +102,14 @@ TRL_DEV void quat_vel_rel(const double* q0, const double* q1, double dt, double*
     double d[4];
     quat_mul(c, q1, d);
     double st = sqrt(d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
-    double theta = 0, ax = 0, ay = 0, az = 1;
+    // reference: axis = d.xyz / st, out = (theta / dt) * axis (axis = z, theta = 0 below the 1e-4 threshold). One
+    // division instead of four: out = (theta / (dt * st)) * d.xyz -- the same value to an ulp or two (bar: 1e-9).
+    double k = 0.0;
     if (st > 0.0001) {
         double sg = (double)((0.0 < d[0]) - (d[0] < 0.0));
-        theta = 2 * sg * asin(st);
-        ax = d[1] / st; ay = d[2] / st; az = d[3] / st;
+        k = (2 * sg * asin(st)) / (dt * st);
     }
-    double s = theta / dt;
-    o[0] = s * ax; o[1] = s * ay; o[2] = s * az; o[3] = s * 0.0;
+    o[0] = k * d[1]; o[1] = k * d[2]; o[2] = k * d[3]; o[3] = 0.0;
 }
 
 // Eigen 3.3 slerp followed by normalize (anim/KinTree.cpp:1544-1545)

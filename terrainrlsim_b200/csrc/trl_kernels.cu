@@ -1993,6 +1993,7 @@ k_kin_tile(const DevModel* __restrict__ M, const double* __restrict__ frames, in
     double* Tl = smem + lane;  // element k of joint a: Tl[(a * 12 + k) * 32]
     const double t = time[e];
     const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
+    const double inv_ddt = 1.0 / ddt;  // the reference divides by ddt; one reciprocal + products agree to an ulp
     // frame lookup (an exact fmod + a binary search) once per env and time, by the first two warps, shared through
     // shared memory -- not once per joint
     __shared__ double s_lerp[2][kTile];
@@ -2028,13 +2029,13 @@ k_kin_tile(const DevModel* __restrict__ M, const double* __restrict__ frames, in
             kin_joint_pose_at(M, X, frames, fs, j, t + ddt, idx1, lerp1, opos, orot, p1);
             if (is_root) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
 #pragma unroll
-                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) * inv_ddt;
                 quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
             } else if (sph) {
                 quat_vel_rel(p0, p1, ddt, v);
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = (p1[i] - p0[i]) / ddt;
+                for (int i = 0; i < 4; ++i) v[i] = (p1[i] - p0[i]) * inv_ddt;
             }
             if (env_ok) {
 #pragma unroll
