@@ -1048,10 +1048,12 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
                 const int ui = di - o;
                 const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
                 if (env_ok) {
+                    double* ps = sc + (SC.scol + 6 * c) * kTile;  // one address per column, immediate offsets below
+                    double* pf = sc + (SC.fcol + 6 * c) * kTile;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
-                        sc[(SC.scol + 6 * c + k) * kTile] = sv[k];
-                        sc[(SC.fcol + 6 * c + k) * kTile] = Fc[k];
+                        ps[k * kTile] = sv[k];
+                        pf[k * kTile] = Fc[k];
                     }
                     sc[(SC.rhs + c) * kTile] = u - Cc;
                     sc[pd_tri(c, c) * kTile] = hd + dt * kdu;
