@@ -1352,7 +1352,7 @@ k_apply_tau(const DevModel* __restrict__ M, int E, const double* __restrict__ po
 // ------------------------------------------------------------------------------------------------
 TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-constexpr int kHWarps = 8;
+constexpr int kHWarps = 4;
 __global__ void __launch_bounds__(kHWarps * 32)
 k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, double* __restrict__ out_mass) {
     KTrace trace_(TR_PD_H);
