@@ -52,7 +52,8 @@ class CStepIO(C.Structure):
 
 def build_lib(force=False):
     if force or not os.path.exists(_LIB_PATH) or \
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "trl_oracle.c")):
+            any(os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, f))
+                for f in ("trl_oracle.c", "trl_oracle_terrain.c", "trl_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -195,6 +196,16 @@ class Model:
         zp = lib().trlo_imp_pd_control_force(self.ref, C.c_double(dt), _d(pose), _d(vel), _d(tar_pose), _d(tar_vel),
                                              _u(active), _d(kp), _d(kd), _d(tau), _d(M), _d(Cb))
         return tau, M, Cb, zp
+
+    def exp_pd(self, dt, pose, vel, tar_pose, tar_vel, active=None, kp=None, kd=None, tau0=None):
+        """cExpPDController::UpdateControlForce(dt, tau) -> tau"""
+        pose, vel, tar_pose, tar_vel = _c(pose), _c(vel), _c(tar_pose), _c(tar_vel)
+        active = _c(active, np.uint8)
+        kp, kd = _c(kp), _c(kd)
+        tau = np.zeros(self.n) if tau0 is None else np.array(tau0, dtype=np.float64)
+        lib().trlo_exp_pd_control_force(self.ref, C.c_double(dt), _d(pose), _d(vel), _d(tar_pose), _d(tar_vel),
+                                        _u(active), _d(kp), _d(kd), _d(tau))
+        return tau
 
     def joint_world_trans(self, pose, j):
         pose = _c(pose)
@@ -398,3 +409,137 @@ def step_range(model, cfg, arrays, grounds, dt, env_begin=0, env_end=None, env_t
         env_end = E
     lib().trlo_step_range(model.ref, C.byref(cfg), C.byref(io), C.c_int(env_begin), C.c_int(env_end))
     return arrays
+
+
+# ----------------------------------------------------------------------------------------------
+# terrain generation and scrolling (oracle/trl_oracle_terrain.c)
+# ----------------------------------------------------------------------------------------------
+GROUND_TYPE_NAMES = ["plane", "var2d_flat", "var2d_gaps", "var2d_steps", "var2d_walls", "var2d_bumps", "var2d_mixed",
+                     "var2d_narrow_gaps", "var2d_slopes", "var2d_slopes_gaps", "var2d_slopes_walls",
+                     "var2d_slopes_steps", "var2d_slopes_mixed", "var2d_slopes_narrow_gaps", "var2d_cliffs",
+                     "var3d_flat"]  # cGround::eType order, sim/Ground.cpp:4-33
+TERRAIN2D_PARAM_NAMES = [  # cTerrainGen2D::gParamDefs, sim/TerrainGen2D.cpp:12-63
+    "GapSpacingMin", "GapSpacingMax", "GapWMin", "GapWMax", "GapHMin", "GapHMax",
+    "WallSpacingMin", "WallSpacingMax", "WallWMin", "WallWMax", "WallHMin", "WallHMax",
+    "StepSpacingMin", "StepSpacingMax", "StepH0Min", "StepH0Max", "StepH1Min", "StepH1Max",
+    "BumpHMin", "BumpHMax",
+    "NarrowGapSpacingMin", "NarrowGapSpacingMax", "NarrowGapDistMin", "NarrowGapDistMax", "NarrowGapWMin",
+    "NarrowGapWMax", "NarrowGapDepthMin", "NarrowGapDepthMax", "NarrowGapCountMin", "NarrowGapCountMax",
+    "CliffSpacingMin", "CliffSpacingMax", "CliffH0Min", "CliffH0Max", "CliffH1Min", "CliffH1Max", "CliffMiniCountMax",
+    "SlopeDeltaRange", "SlopeDeltaMin", "SlopeDeltaMax"]
+PIECE_CAP = 49152
+
+
+class CRand(C.Structure):
+    _fields_ = [("x", C.c_ulonglong)]
+
+
+class CTerrainPiece(C.Structure):
+    _fields_ = [("data", C.c_float * PIECE_CAP), ("count", C.c_int), ("res", C.c_int * 2), ("origin", C.c_double * 3),
+                ("scale", C.c_double * 3), ("aabb", C.c_double * 4), ("min", C.c_double * 3), ("max", C.c_double * 3)]
+
+
+class CGroundVar2D(C.Structure):
+    _fields_ = [("type", C.c_int), ("params", C.c_double * 40), ("ground_width", C.c_double),
+                ("world_scale", C.c_double), ("rand", CRand), ("flip_seg", C.c_int), ("piece", CTerrainPiece * 2)]
+
+
+class CGroundVar3D(C.Structure):
+    _fields_ = [("ground_width", C.c_double), ("spacing_x", C.c_double), ("spacing_z", C.c_double),
+                ("world_scale", C.c_double), ("slab_order", C.c_int * 4), ("piece", CTerrainPiece * 4)]
+
+
+def terrain2d_default_params():
+    out = np.zeros(lib().trlo_terrain2d_num_params())
+    lib().trlo_terrain2d_default_params(_d(out))
+    return out
+
+
+def load_terrain_file(path):
+    """cGroundFactory::ParseParamsJson (sim/GroundFactory.cpp:11-61) + cTerrainGen2D::LoadParams: returns
+    {type (int), type_name, ground_width, spacing_x, spacing_z, params [num_sets][40] (2-D) }"""
+    with open(path) as f:
+        d = json.load(f)
+    name = d.get("Type", "var2d_flat")
+    out = {"type_name": name, "type": GROUND_TYPE_NAMES.index(name), "ground_width": float(d.get("GroundWidth", 20)),
+           "spacing_x": float(d.get("VertSpacingX", 0.2)), "spacing_z": float(d.get("VertSpacingZ", 0.2)), "params": None}
+    if name.startswith("var2d") and d.get("Params"):
+        rows = []
+        for entry in d["Params"]:
+            p = terrain2d_default_params()
+            for i, key in enumerate(TERRAIN2D_PARAM_NAMES):
+                if key in entry and entry[key] is not None:
+                    p[i] = float(entry[key])
+            rows.append(p)
+        out["params"] = np.array(rows)
+    return out
+
+
+def terrain_gen_2d(type_id, width, params=None, seed=0, cap=1 << 16):
+    """cTerrainGen2D::Build*(width, params, cRand(seed), out_data) -> float32 heights"""
+    rnd = CRand()
+    lib().trlo_rand_seed(C.byref(rnd), C.c_ulong(seed))
+    params = _c(params)
+    out = np.zeros(cap, dtype=np.float32)
+    count = C.c_int(0)
+    lib().trlo_terrain_gen_2d.restype = C.c_double
+    lib().trlo_terrain_gen_2d(C.c_int(type_id), C.c_double(width), _d(params), C.byref(rnd), out.ctypes.data_as(_fp),
+                              C.byref(count), C.c_int(cap))
+    return out[:count.value].copy()
+
+
+def _pieces_from_view(view, n):
+    out = []
+    for s in range(n):
+        rx, rz = view.res[s][0], view.res[s][1]
+        data = np.ctypeslib.as_array(view.data[s], shape=(rz * rx,)).copy().reshape(rz, rx)
+        out.append({"data": data, "res": (rx, rz), "origin": np.array(view.origin[s][:]),
+                    "scale": np.array(view.scale[s][:]), "bounds": np.array(view.bounds[s][:])})
+    return out
+
+
+class GroundVar2D:
+    """cGroundVar2D restated: two scrolling segments generated by cTerrainGen2D"""
+
+    def __init__(self, type_id, params=None, ground_width=20.0, world_scale=1.0, seed=0, blend=0.0):
+        self.c = CGroundVar2D()
+        if params is not None:
+            params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+            # cGround::CalcBlendParams (sim/Ground.cpp:255-278): lerp of two consecutive parameter sets
+            b = min(max(blend, 0.0), params.shape[0] - 1.0)
+            i0 = int(b)
+            i1 = min(i0 + 1, params.shape[0] - 1)
+            b -= i0
+            params = np.ascontiguousarray((1 - b) * params[i0] + b * params[i1])
+        half = ground_width / 2
+        lib().trlo_ground2d_init(C.byref(self.c), C.c_int(type_id), _d(params), C.c_double(ground_width),
+                                 C.c_double(world_scale), C.c_ulong(seed), C.c_double(-half - 1.0), C.c_double(half - 1.0))
+
+    def update(self, bound_min_x, bound_max_x):
+        lib().trlo_ground2d_update(C.byref(self.c), C.c_double(bound_min_x), C.c_double(bound_max_x))
+
+    def pieces(self):
+        view = CGround()
+        lib().trlo_ground2d_view(C.byref(self.c), C.byref(view))
+        return _pieces_from_view(view, 2)
+
+
+class GroundVar3D:
+    """cGroundVar3D restated with cTerrainGen3D::BuildFlat: four scrolling slabs"""
+
+    def __init__(self, spacing_x=0.2, spacing_z=0.2, world_scale=1.0, ground_width=20.0):
+        self.c = CGroundVar3D()
+        half = ground_width / 2  # cGroundFactory::BuildGroundVar3D bounds use the *file's* width (default 20)
+        bmin = np.array([-half, 0.0, -half])
+        bmax = np.array([half, 0.0, half])
+        lib().trlo_ground3d_init(C.byref(self.c), C.c_double(spacing_x), C.c_double(spacing_z), C.c_double(world_scale),
+                                 _d(bmin), _d(bmax))
+
+    def update(self, bound_min, bound_max):
+        bmin, bmax = _c(bound_min), _c(bound_max)
+        lib().trlo_ground3d_update(C.byref(self.c), _d(bmin), _d(bmax))
+
+    def pieces(self):
+        view = CGround()
+        lib().trlo_ground3d_view(C.byref(self.c), C.byref(view))
+        return _pieces_from_view(view, 4)

@@ -320,3 +320,19 @@ def terrain_params_2d(param_file, idx=0):
     if rc < 0:
         raise RuntimeError("reference failed to parse " + param_file)
     return out
+
+
+def terrain_params_2d_default():
+    """cTerrainGen2D::GetDefaultParams through a terrain file without a Params block"""
+    return _default_2d()
+
+
+def _default_2d():
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write('{"Type": "var2d_flat", "Params": [{}]}')
+        path = f.name
+    try:
+        return terrain_params_2d(path)
+    finally:
+        os.unlink(path)

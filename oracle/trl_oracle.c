@@ -376,7 +376,7 @@ static void calc_barycentric(const double p[2], const double a[2], const double 
  * ---------------------------------------------------------------------------------------- */
 enum { JD_TYPE = 0, JD_PARENT = 1, JD_ATTACH_X = 2, JD_ATTACH_THETA_X = 5, JD_PARAM_OFFSET = 18 };
 enum { BD_SHAPE = 0, BD_MASS = 1, BD_ATTACH_X = 4, BD_ATTACH_THETA_X = 7, BD_PARAM0 = 10 };
-enum { PD_KP = 1, PD_KD = 2 };
+enum { PD_KP = 1, PD_KD = 2, PD_USE_WORLD = 17 }; /* sim/PDController.h:12-32 */
 
 static const double* jrow(const trlo_model* m, int j) { return m->joint_mat + (size_t)j * TRLO_JOINT_COLS; }
 static const double* brow(const trlo_model* m, int j) { return m->body_defs + (size_t)j * TRLO_BODY_COLS; }
@@ -1305,6 +1305,114 @@ int trlo_ldlt_solve(int n, const double* A, const double* b, double* x)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * PD targets as the controllers see them: cPDController::SetTargetTheta / SetTargetVel post-processing
+ * (sim/PDController.cpp:191-211,430-461: spherical targets normalised, zero quaternion -> identity, vel slot 3 = 0)
+ * followed by GetTargetTheta (:223-273), which converts WORLD-coordinate targets (pd_params UseWorldCoord != 0)
+ * of revolute and spherical joints into joint coordinates from the current joint rotations. The joint's world
+ * transform (cJoint::BuildWorldTrans, sim/Joint.cpp:126-131: child body transform x joint-in-body) equals
+ * cKinTree::JointWorldTrans of the pose; CalcRotation (sim/Joint.cpp:70-93,565-569,624-628) is the joint's own
+ * coordinate. Used by cImpPDController::BuildTargetPose / BuildTargetVel (sim/ImpPDController.cpp:198-243) and by
+ * cPDController::CalcJointTau* (sim/PDController.cpp:302-428). Invalid controllers (root, null bodies) get zeros.
+ * ---------------------------------------------------------------------------------------- */
+static void pd_build_targets(const trlo_model* m, const double* pose, const double* tar_pose_in,
+                             const double* tar_vel_in, double* tar_pose, double* tar_vel)
+{
+    int N = m->num_joints, n = m->num_dof;
+    for (int i = 0; i < n; ++i) tar_pose[i] = tar_vel[i] = 0;
+    for (int j = 0; j < N; ++j) {
+        if (!trlo_pd_valid(m, j)) continue;
+        int off = trlo_param_offset(m, j), size = trlo_param_size(m, j);
+        int type = trlo_joint_type(m, j);
+        int world = m->pd_params[(size_t)j * TRLO_PD_COLS + PD_USE_WORLD] != 0;
+        for (int i = 0; i < size; ++i) {
+            tar_pose[off + i] = tar_pose_in[off + i];
+            tar_vel[off + i] = tar_vel_in[off + i];
+        }
+        if (type == TRLO_JOINT_SPHERICAL) {
+            double* t = tar_pose + off;
+            if (t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3] == 0) t[0] = 1;
+            else normalize4(t);
+            tar_vel[off + size - 1] = 0;
+        }
+        if (world && type == TRLO_JOINT_REVOLUTE) {      /* PDController.cpp:238-252 */
+            double W[16];
+            trlo_joint_world_trans(m, pose, j, W);
+            mat4 Wm;
+            memcpy(Wm.m, W, sizeof(W));
+            double axis_world[3], theta_world;
+            rot_mat_to_axis_angle(&Wm, axis_world, &theta_world);
+            double axis_rel[3] = { 0, 0, 1 }, theta_rel = pose[off];
+            /* CalcAxisWorld: trans * (0,0,1,0), Joint.cpp:46-53 */
+            double axis_ref[3] = { Wm.m[0][2], Wm.m[1][2], Wm.m[2][2] };
+            double dw = axis_world[0] * axis_ref[0] + axis_world[1] * axis_ref[1] + axis_world[2] * axis_ref[2] + 0.0;
+            double dr = axis_rel[0] * axis_ref[0] + axis_rel[1] * axis_ref[1] + axis_rel[2] * axis_ref[2] + 0.0;
+            double theta_offset = dw * theta_world - dr * theta_rel;
+            tar_pose[off] -= theta_offset;
+        }
+        if (world && type == TRLO_JOINT_SPHERICAL) {     /* PDController.cpp:254-267 */
+            double W[16];
+            trlo_joint_world_trans(m, pose, j, W);
+            mat4 Wm;
+            memcpy(Wm.m, W, sizeof(W));
+            double axis_rel[3], theta_rel;
+            quat_to_axis_angle(pose_quat(pose + off), axis_rel, &theta_rel);
+            quat world_rot = rot_mat_to_quat(&Wm);
+            quat rel_rot = axis_angle_to_quat(axis_rel, theta_rel);
+            quat tar_q = pose_quat(tar_pose + off);
+            quat diff = quat_mul(quat_conj(world_rot), tar_q);
+            tar_q = quat_mul(rel_rot, diff);
+            tar_pose[off] = tar_q.w; tar_pose[off + 1] = tar_q.x; tar_pose[off + 2] = tar_q.y; tar_pose[off + 3] = tar_q.z;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * cExpPDController::UpdateControlForce -> cPDController::UpdateControlForce / CalcJointTau*
+ * (sim/ExpPDController.cpp:59-66,148-159; sim/PDController.cpp:134-149,302-428): explicit PD per joint.
+ * Joint coordinates / rates are the pose / vel entries (cJoint::CalcRotation, BuildPose, BuildVel,
+ * CalcDisplacementPrismatic: the data contract of sim/Joint.cpp:353-417,565-628).
+ * ---------------------------------------------------------------------------------------- */
+void trlo_exp_pd_control_force(const trlo_model* m, double dt, const double* pose, const double* vel,
+                               const double* tar_pose_in, const double* tar_vel_in,
+                               const unsigned char* joint_active, const double* kp_joint, const double* kd_joint,
+                               double* inout_tau)
+{
+    int N = m->num_joints;
+    double tar_pose[TRLO_MAX_DOF], tar_vel[TRLO_MAX_DOF];
+    if (!(dt > 0)) return; /* ExpPDController.cpp:62 */
+    pd_build_targets(m, pose, tar_pose_in, tar_vel_in, tar_pose, tar_vel);
+    for (int j = 0; j < N; ++j) {
+        if (!trlo_pd_valid(m, j)) continue;
+        if (joint_active && !joint_active[j]) continue; /* PDController.cpp:137 */
+        int off = trlo_param_offset(m, j);
+        double kp = kp_joint ? kp_joint[j] : m->pd_params[(size_t)j * TRLO_PD_COLS + PD_KP];
+        double kd = kd_joint ? kd_joint[j] : m->pd_params[(size_t)j * TRLO_PD_COLS + PD_KD];
+        switch (trlo_joint_type(m, j)) {
+        case TRLO_JOINT_REVOLUTE:   /* :329-356 */
+        case TRLO_JOINT_PRISMATIC: { /* :366-389 */
+            double theta_err = tar_pose[off] - pose[off];
+            double vel_err = tar_vel[off] - vel[off];
+            inout_tau[off] += kp * theta_err + kd * vel_err;
+            break;
+        }
+        case TRLO_JOINT_SPHERICAL: { /* :397-428 */
+            quat tar_q = pose_quat(tar_pose + off);
+            quat q = pose_quat(pose + off);
+            quat q_err = quat_mul(quat_conj(q), tar_q);
+            double axis[3], theta;
+            quat_to_axis_angle(q_err, axis, &theta);
+            double torque[4] = { (kp * theta) * axis[0], (kp * theta) * axis[1], (kp * theta) * axis[2], (kp * theta) * 0.0 };
+            for (int i = 0; i < 3; ++i) torque[i] += kd * (tar_vel[off + i] - vel[off + i]);
+            for (int i = 0; i < 4; ++i) inout_tau[off + i] += torque[i];
+            break;
+        }
+        default: /* planar (unsupported: zero, :358-364), fixed (:391-395) */
+            break;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * cImpPDController::CalcControlForces, sim/ImpPDController.cpp:137-196
  * ---------------------------------------------------------------------------------------- */
 int trlo_imp_pd_control_force(const trlo_model* m, double dt, const double* pose, const double* vel,
@@ -1324,26 +1432,15 @@ int trlo_imp_pd_control_force(const trlo_model* m, double dt, const double* pose
     if (out_bias) memcpy(out_bias, C, sizeof(double) * (size_t)n);
 
     /* InitGains :100-121, BuildTargetPose/Vel :198-243: zero for invalid controllers (root) */
-    for (int i = 0; i < n; ++i) { mKp[i] = mKd[i] = 0; tar_pose[i] = tar_vel[i] = 0; }
+    for (int i = 0; i < n; ++i) { mKp[i] = mKd[i] = 0; }
     for (int j = 0; j < N; ++j) {
         if (!trlo_pd_valid(m, j)) continue;
         int off = trlo_param_offset(m, j), size = trlo_param_size(m, j);
         double kp = kp_joint ? kp_joint[j] : m->pd_params[(size_t)j * TRLO_PD_COLS + PD_KP];
         double kd = kd_joint ? kd_joint[j] : m->pd_params[(size_t)j * TRLO_PD_COLS + PD_KD];
-        for (int i = 0; i < size; ++i) {
-            mKp[off + i] = 1.0 * kp; mKd[off + i] = 1.0 * kd;
-            tar_pose[off + i] = tar_pose_in[off + i];
-            tar_vel[off + i] = tar_vel_in[off + i];
-        }
-        if (trlo_joint_type(m, j) == TRLO_JOINT_SPHERICAL) {
-            /* targets enter through SetTargetTheta / SetTargetVel, which post-process spherical joints
-             * (sim/PDController.cpp:191-211,430-461): zero quaternion -> identity, else normalise; vel slot 3 = 0 */
-            double* t = tar_pose + off;
-            if (t[0] * t[0] + t[1] * t[1] + t[2] * t[2] + t[3] * t[3] == 0) t[0] = 1;
-            else normalize4(t);
-            tar_vel[off + size - 1] = 0;
-        }
+        for (int i = 0; i < size; ++i) { mKp[off + i] = 1.0 * kp; mKd[off + i] = 1.0 * kd; }
     }
+    pd_build_targets(m, pose, tar_pose_in, tar_vel_in, tar_pose, tar_vel);
     /* mask gains of invalid / inactive controllers :151-161 */
     for (int i = 0; i < n; ++i) { Kp[i] = mKp[i]; Kd[i] = mKd[i]; }
     for (int j = 0; j < N; ++j) {

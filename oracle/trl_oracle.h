@@ -6,10 +6,10 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library; the product (terrainrlsim_b200/, include/) never does.
  *
- * PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for this
- * path and cannot be compiled here (Eigen, Bullet absent), so
- * this oracle is validated by mathematical identities and an independent numpy
- * cross-check (tests/test_oracle_*.py), not against reference outputs.
+ * PARITY PINNED TO THE REFERENCE ITSELF: the reference ships no golden vectors, but its own
+ * translation units compile unmodified against stand-in Eigen / Bullet headers into
+ * oracle/_ref (oracle/Makefile `ref`); tests/test_ref_pin.py compares this oracle with it at
+ * 1e-13 (most results to the last bit) and tests/golden/ freezes the reference outputs.
  *
  * Every function cites the reference file:line it follows (paths relative to the
  * reference tree). Third-party arithmetic restated from its published algorithm:
@@ -117,12 +117,21 @@ int trlo_ldlt_solve(int n, const double* A, const double* b, double* x);
 
 /* ---- stable PD (sim/ImpPDController.cpp:137-196) ---- */
 /* kp_joint/kd_joint: [N] per-joint gains or NULL (use pd_params); joint_active [N] or NULL (all active);
- * tar_pose/tar_vel [n]; inout_tau [n] accumulated (+=); out_mass/out_bias optional. returns #zero pivots */
+ * tar_pose/tar_vel [n]; inout_tau [n] accumulated (+=); out_mass/out_bias optional. returns #zero pivots.
+ * Targets of joints whose pd_params row has UseWorldCoord != 0 are WORLD-coordinate targets and are converted with
+ * the current joint rotations like cPDController::GetTargetTheta does (sim/PDController.cpp:223-273). */
 int trlo_imp_pd_control_force(const trlo_model* m, double dt, const double* pose, const double* vel,
                               const double* tar_pose, const double* tar_vel,
                               const unsigned char* joint_active,
                               const double* kp_joint, const double* kd_joint,
                               double* inout_tau, double* out_mass, double* out_bias);
+
+/* explicit PD: cExpPDController::UpdateControlForce -> cPDController::CalcJointTau* (sim/ExpPDController.cpp:59-66,
+ * 148-159; sim/PDController.cpp:134-149,302-428). Same argument meaning as the stable-PD call. */
+void trlo_exp_pd_control_force(const trlo_model* m, double dt, const double* pose, const double* vel,
+                               const double* tar_pose, const double* tar_vel,
+                               const unsigned char* joint_active,
+                               const double* kp_joint, const double* kd_joint, double* inout_tau);
 
 /* ---- motion / kinematic character (anim/Motion.cpp, anim/KinCharacter.cpp) ---- */
 void trlo_motion_index_phase(const trlo_model* m, double time, int* out_idx, double* out_phase);
@@ -157,6 +166,55 @@ void trlo_calc_com(const trlo_model* m, const double* pose, const double* vel, d
 double trlo_imitate_reward(const trlo_model* m, const trlo_ground* g, const double* pose0, const double* vel0,
                            const double* pose1, const double* vel1, const double* body_vel, int fallen,
                            double* out_terms);
+
+/* ---- terrain generation and scrolling (oracle/trl_oracle_terrain.c) ---- */
+/* cRand (util/Rand.cpp) on std::default_random_engine = minstd_rand0 */
+typedef struct trlo_rand { unsigned long long x; } trlo_rand;
+void trlo_rand_seed(trlo_rand* r, unsigned long seed);
+double trlo_rand_double(trlo_rand* r);
+double trlo_rand_double_range(trlo_rand* r, double mn, double mx);
+int trlo_rand_int(trlo_rand* r);
+int trlo_rand_int_range(trlo_rand* r, int mn, int mx);
+int trlo_rand_flip_coin(trlo_rand* r, double p);
+/* cTerrainGen2D: type = cGround::eType (sim/Ground.h:26-55: 1 flat, 2 gaps, 3 steps, 4 walls, 5 bumps, 6 mixed,
+ * 7 narrow gaps, 8..13 slopes variants, 14 cliffs); params [trlo_terrain2d_num_params()] or NULL for the defaults;
+ * appends to data[*inout_count ...]; returns the width added */
+int trlo_terrain2d_num_params(void);
+void trlo_terrain2d_default_params(double* out);
+double trlo_terrain_gen_2d(int type, double width, const double* params, trlo_rand* rand, float* data,
+                           int* inout_count, int cap);
+/* one terrain piece (2-D segment / 3-D slab) with its Bullet-side placement */
+#define TRLO_TERRAIN_PIECE_CAP 49152
+typedef struct trlo_terrain_piece {
+    float data[TRLO_TERRAIN_PIECE_CAP];
+    int count;          /* floats in data (2-D: 3 rows of res[0]) */
+    int res[2];
+    double origin[3];   /* cSimObj::GetPos() */
+    double scale[3];    /* GetScaling() */
+    double aabb[4];     /* rigid-body AABB min_x, max_x, min_z, max_z (/ world scale) */
+    double min[3], max[3]; /* 3-D: tSlab::mMin / mMax */
+} trlo_terrain_piece;
+typedef struct trlo_ground_var2d {
+    int type;
+    double params[40];
+    double ground_width, world_scale;
+    trlo_rand rand;
+    int flip_seg;
+    trlo_terrain_piece piece[2];
+} trlo_ground_var2d;
+void trlo_ground2d_init(trlo_ground_var2d* g, int type, const double* params, double ground_width, double world_scale,
+                        unsigned long seed, double bound_min_x, double bound_max_x);
+void trlo_ground2d_update(trlo_ground_var2d* g, double bound_min_x, double bound_max_x);
+void trlo_ground2d_view(const trlo_ground_var2d* g, trlo_ground* out);
+typedef struct trlo_ground_var3d {
+    double ground_width, spacing_x, spacing_z, world_scale;
+    int slab_order[4];
+    trlo_terrain_piece piece[4];
+} trlo_ground_var3d;
+void trlo_ground3d_init(trlo_ground_var3d* g, double spacing_x, double spacing_z, double world_scale,
+                        const double bound_min[3], const double bound_max[3]);
+void trlo_ground3d_update(trlo_ground_var3d* g, const double bound_min[3], const double bound_max[3]);
+void trlo_ground3d_view(const trlo_ground_var3d* g, trlo_ground* out);
 
 /* ---- batched drivers (loop over envs [env_begin, env_end); thread-safe on disjoint ranges) ---- */
 typedef struct trlo_step_io {

@@ -119,6 +119,44 @@ def test_oracle_sample_height_against_reference_outputs(oracle, tag):
         assert np.array_equal(h, fx["s%d_h" % step])
 
 
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_oracle_world_targets_and_explicit_pd_against_reference_outputs(oracle, name):
+    fx = load("ref_" + name)
+    mw = oracle_model(oracle, fx, world=True, frames=False)
+    ml = oracle_model(oracle, fx, world=False, frames=False)
+    for e in range(fx["pose"].shape[0]):
+        args = (fx["dt"][e], fx["pose"][e], fx["vel"][e], fx["tar_pose"][e], fx["tar_vel"][e], fx["joint_active"][e])
+        assert rel(mw.imp_pd(*args)[0], fx["tau_world_targets"][e]) <= TOL
+        assert rel(ml.exp_pd(*args), fx["exp_tau"][e]) <= TOL
+
+
+@pytest.mark.parametrize("tag", GROUNDS)
+def test_oracle_terrain_generation_against_reference_outputs(oracle, tag):
+    """the terrain pieces in the fixtures were GENERATED by the reference (seeded cRand + cTerrainGen2D / 3D, then one
+    scroll step): the oracle's generator must reproduce heights, placement and bounds bit for bit"""
+    fx = load("ref_ground_" + tag)
+    scale, seed = float(fx["world_scale"]), int(fx["seed"])
+    if int(fx["kind"]) == 1:
+        type_id = oracle.GROUND_TYPE_NAMES.index(str(fx["type_name"]))
+        og = oracle.GroundVar2D(type_id, fx["params"], float(fx["ground_width"]), scale, seed)
+    else:
+        og = oracle.GroundVar3D(0.2, 0.2, scale, float(fx["ground_width"]))
+    for step in range(2):
+        _, want = ground_from_fixture(oracle, fx, step)
+        got = og.pieces()
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert tuple(a["res"]) == tuple(b["res"])
+            for k in ("origin", "scale", "bounds"):
+                assert np.array_equal(a[k], b[k]), k
+            assert np.array_equal(np.asarray(a["data"]).ravel(), np.asarray(b["data"]).ravel())
+        lo, hi = fx["s%d_update_min" % step], fx["s%d_update_max" % step]
+        if int(fx["kind"]) == 1:
+            og.update(float(lo[0]), float(hi[0]))
+        else:
+            og.update(lo, hi)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # GPU: the product through the C-ABI against the reference's outputs
 # ------------------------------------------------------------------------------------------------------------------

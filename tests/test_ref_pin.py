@@ -309,3 +309,101 @@ def test_synthetic_character_with_planar_and_fixed_joints(oracle, null_body):
         t0, _, _, _ = m.imp_pd(1.0 / 600, pose[e], vel[e], tar[e], tar_vel[e])
         t1, _, _ = r.imp_pd(1.0 / 600, pose[e], vel[e], tar[e], tar_vel[e])
         assert rel(t0, t1) <= TOL
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_world_coordinate_targets_and_explicit_pd(oracle, name):
+    """UseWorldCoord targets (cPDController::GetTargetTheta, sim/PDController.cpp:223-273) through stable PD, and
+    explicit PD (cExpPDController / cPDController::CalcJointTau*, sim/PDController.cpp:302-428), with the characters'
+    own UseWorldCoord flags (hopper, dog, raptor, biped3D have world-coordinate joints)"""
+    m, r = models(oracle, name, world_coord=True)
+    E = 8
+    x = synth.make_inputs(name, E)
+    rng = np.random.default_rng(2)
+    for e in range(E):
+        act = x["joint_active"][e]
+        kp = kd = None
+        if e % 3 == 2:
+            kp, kd = rng.uniform(10, 500, m.N), rng.uniform(1, 50, m.N)
+        t0, _, _, _ = m.imp_pd(1.0 / 600, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e], act, kp, kd)
+        t1, _, _ = r.imp_pd(1.0 / 600, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e], act, kp, kd)
+        assert rel(t0, t1) <= TOL
+        tau0 = rng.normal(size=m.n)
+        e0 = m.exp_pd(1.0 / 600, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e], act, kp, kd, tau0)
+        e1 = r.exp_pd(1.0 / 600, x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e], act, kp, kd, tau0)
+        assert rel(e0, e1) <= TOL
+    assert np.array_equal(m.exp_pd(0.0, x["pose"][0], x["vel"][0], x["tar_pose"][0], x["tar_vel"][0]), np.zeros(m.n))
+
+
+def _same_pieces(pa, pb):
+    assert len(pa) == len(pb)
+    for a, b in zip(pa, pb):
+        assert tuple(a["res"]) == tuple(b["res"])
+        for k in ("origin", "scale", "bounds"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(np.asarray(a["data"]).ravel(), np.asarray(b["data"]).ravel())
+
+
+TERRAIN_FILES = ["flat.txt", "gaps.txt", "steps.txt", "walls.txt", "bumps.txt", "mixed.txt", "mixed_hopper.txt",
+                 "narrow_gaps.txt", "slopes.txt", "slopes_mixed.txt", "cliffs_rugged.txt"]
+
+
+@needs_tree
+@pytest.mark.parametrize("terrain", TERRAIN_FILES)
+def test_terrain_generator_and_rng_bit_exact(oracle, terrain):
+    """cTerrainGen2D::Build* with cRand on std::default_random_engine (sim/TerrainGen2D.cpp:127-653, util/Rand.cpp):
+    float heights bit-identical; parameter files through cTerrainGen2D::LoadParams"""
+    path = os.path.join(REF, "data", "terrain", terrain)
+    if not os.path.exists(path):
+        pytest.skip("no such terrain file")
+    tf = oracle.load_terrain_file(path)
+    p = None
+    if tf["params"] is not None:
+        assert np.array_equal(ref_py.terrain_params_2d(path, 0), tf["params"][0])
+        p = tf["params"][0]
+    for seed in (0, 1, 12345, 2147483647, 2 ** 40 + 17):
+        for width in (20.0, 3.3):
+            a = oracle.terrain_gen_2d(tf["type"], width, p, seed)
+            b = ref_py.terrain_gen_2d(tf["type_name"], width, p, seed)
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+@needs_tree
+@pytest.mark.parametrize("terrain,scale", [("mixed.txt", 1.0), ("mixed_hopper.txt", 4.0), ("flat.txt", 1.0),
+                                           ("slopes_mixed.txt", 1.0), ("gaps.txt", 4.0)])
+def test_ground_var2d_segments_and_scrolling(oracle, terrain, scale):
+    """cGroundVar2D::Init / Update / BuildSegment / AddPadding + tSegment::Init (sim/GroundVar2D.cpp:33-96,261-520):
+    heights, origin, scaling and AABB bounds identical through forward / backward scrolling and re-initialisation"""
+    path = os.path.join(REF, "data", "terrain", terrain)
+    tf = oracle.load_terrain_file(path)
+    for seed in (3, 77):
+        rg = ref_py.RefGround(path, world_scale=scale, seed=seed)
+        og = oracle.GroundVar2D(tf["type"], tf["params"], tf["ground_width"], scale, seed)
+        _same_pieces(og.pieces(), rg.pieces())
+        for step in range(6):
+            pcs = rg.pieces()
+            hi = max(p["bounds"][1] for p in pcs)
+            lo = min(p["bounds"][0] for p in pcs)
+            if step in (0, 1, 2, 4):
+                bmin, bmax = hi - 1.0, hi + 1.0
+            elif step == 3:
+                bmin, bmax = lo - 1.0, lo + 1.0
+            else:
+                bmin, bmax = hi + 100, hi + 102
+            rg.update([bmin, 0, -1], [bmax, 0, 1])
+            og.update(bmin, bmax)
+            _same_pieces(og.pieces(), rg.pieces())
+
+
+@needs_tree
+@pytest.mark.parametrize("scale", [1.0, 4.0])
+def test_ground_var3d_slabs_and_scrolling(oracle, scale):
+    """cGroundVar3D::Init / Update / BuildSlab with cTerrainGen3D::BuildFlat (sim/GroundVar3D.cpp:24-141,350-420,511-550)"""
+    rg = ref_py.RefGround(os.path.join(REF, "data", "terrain", "flat3d.txt"), world_scale=scale, seed=1)
+    og = oracle.GroundVar3D(0.2, 0.2, scale)
+    _same_pieces(og.pieces(), rg.pieces())
+    for bmin, bmax in [([19, 0, -1], [21, 0, 1]), ([39, 0, -1], [41, 0, 1]), ([30, 0, 19], [32, 0, 21]),
+                       ([-5, 0, 30], [-3, 0, 32]), ([500, 0, 500], [501, 0, 501]), ([480, 0, 470], [481, 0, 471])]:
+        rg.update(bmin, bmax)
+        og.update(bmin, bmax)
+        _same_pieces(og.pieces(), rg.pieces())

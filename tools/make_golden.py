@@ -134,6 +134,18 @@ def make_ground(terrain, scale, seed, tag):
     rg = ref_py.RefGround(os.path.join(REF, "data", "terrain", terrain), world_scale=scale, seed=seed)
     rng = np.random.default_rng(seed)
     fx = {"kind": np.array(rg.kind), "world_scale": np.array(scale), "seed": np.array(seed)}
+    # generator inputs, parsed by the reference's own loader (cGroundFactory::ParseParamsJson as restated in
+    # oracle/ref_wrap.cpp + cTerrainGen2D::LoadParams), so the oracle / product generators can be run on them
+    import json
+    with open(os.path.join(REF, "data", "terrain", terrain)) as f:
+        meta = json.load(f)
+    fx["type_name"] = np.array(meta["Type"])
+    fx["ground_width"] = np.array(float(meta.get("GroundWidth", 20)))
+    if rg.kind == 1:
+        try:
+            fx["params"] = ref_py.terrain_params_2d(os.path.join(REF, "data", "terrain", terrain), 0)
+        except RuntimeError:
+            fx["params"] = ref_py.terrain_params_2d_default()
     for step in range(2):
         pieces = rg.pieces()
         lo = min(p["bounds"][0] for p in pieces) - 1.0
@@ -163,6 +175,8 @@ def make_ground(terrain, scale, seed, tag):
             fx["s%d_p%d_res" % (step, s)] = np.array(p["res"])
         fx["s%d_pos" % step], fx["s%d_h" % step], fx["s%d_valid" % step] = pos, h, valid
         xs = max(p["bounds"][1] for p in pieces)
+        fx["s%d_update_min" % step] = np.array([xs - 1.0, 0, -1.0])
+        fx["s%d_update_max" % step] = np.array([xs + 1.0, 0, 1.0])
         rg.update([xs - 1.0, 0, -1.0], [xs + 1.0, 0, 1.0])
     np.savez_compressed(os.path.join(OUT, "ref_ground_%s.npz" % tag), **fx)
 
