@@ -143,8 +143,12 @@ def test_ldlt_restatement(oracle):
 def test_stable_pd_definition(oracle, name):
     """tau = Kp e_p + Kd (e_v - dt qdd), (M + dt Kd) qdd = Kp e_p + Kd e_v - C, evaluated independently in numpy
     from the oracle's own M, C and error vectors; root torque entries are 0; inactive joints use masked gains on
-    the right-hand side but the unmasked Kd on the diagonal (Q2)."""
-    m = oracle.Model(name)
+    the right-hand side but the unmasked Kd on the diagonal (Q2). Targets here are joint-local (UseWorldCoord cleared;
+    the world-target conversion is pinned against the reference in test_ref_pin.py / test_golden.py)."""
+    m0 = oracle.Model(name)
+    pd = m0.pd_params.copy()
+    pd[:, 17] = 0
+    m = oracle.Model(joint_mat=m0.joint_mat, body_defs=m0.body_defs, pd_params=pd)
     x = _inputs(name, E=4)
     dt = 1.0 / 600
     for e in range(4):
