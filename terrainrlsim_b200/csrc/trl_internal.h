@@ -45,6 +45,36 @@ struct alignas(16) ModelIdx {
 };
 static_assert(sizeof(ModelIdx) % 16 == 0, "ModelIdx is copied with 16-byte loads");
 
+// Index tables of the block-cooperative stable-PD kernel (k_pd_block): the branch-sparse storage of H = M + dt*Kd.
+// Column c only couples with the columns on its own ancestor chain (Featherstone's branch-induced sparsity), so row c
+// is stored as [H(c,c), H(c,lambda c), H(c,lambda^2 c), ...] starting at rowbase[c]; the entry for an ancestor a of c
+// sits at rowbase[c] + cdepth[c] - cdepth[a].
+struct alignas(16) PdBlkIdx {
+    short rowbase[TRL_MAX_DOF];
+    signed char cdepth[TRL_MAX_DOF];         // number of column-ancestors of c
+    signed char cd_order[TRL_MAX_DOF];       // columns sorted by cdepth (back substitution runs depth by depth)
+    signed char cd_start[TRL_MAX_DOF + 16];  // start of each depth in cd_order, [max_cdepth + 2] entries
+    signed char use_world[TRL_MAX_JOINTS];   // pd_params UseWorldCoord of the joint (sim/PDController.h:31)
+    short aba_off[TRL_MAX_JOINTS];           // k_pd_aba: first scratch slot of joint j (1 + 14 k doubles for k live dofs)
+    signed char preorder[TRL_MAX_JOINTS];    // joints in depth-first pre-order (the order ModelIdx::dfs_event enters them)
+    // k_pd_aba works branch by branch (a branch = the subtree of one child of the root), one warp per branch:
+    signed char nchild[TRL_MAX_JOINTS];      // number of children of joint j
+    signed char b_ev0[TRL_MAX_JOINTS];       // branch b: first event in ModelIdx::dfs_event (its events are contiguous)
+    signed char b_ev1[TRL_MAX_JOINTS];       //           one past its last event
+    signed char b_pre0[TRL_MAX_JOINTS];      //           first joint in `preorder`
+    signed char b_pre1[TRL_MAX_JOINTS];      //           one past its last joint
+    short xoff[TRL_MAX_JOINTS];              // joints with >= 2 children: offset (elements, within the branch's area) of
+                                             // their [V6 A6 IA21 P6] block; -1 otherwise
+    int num_branches;
+    int branch_area;                         // elements per branch area: 22 per level below the root + the blocks above
+    int pad_[2];
+    int hcount;                              // entries of the sparse H
+    int max_cdepth;
+    int aba_slots;                           // scratch doubles per env of k_pd_aba
+    int all_valid;                           // every body valid (k_pd_aba's precondition)
+};
+static_assert(sizeof(PdBlkIdx) % 16 == 0, "PdBlkIdx is copied with 16-byte loads");
+
 // Flattened, immutable character model as the kernels read it (resident in HBM, ~5 KB).
 struct DevModel {
     int N;           // joints
@@ -60,6 +90,7 @@ struct DevModel {
     double cycle_delta[3];  // cKinCharacter::CalcCycleRootDelta, anim/KinCharacter.cpp:264-277
 
     ModelIdx ix;  // small integer tables; every kernel stages them in shared memory
+    PdBlkIdx bx;  // sparse-H index tables of k_pd_block
     double attR[TRL_MAX_JOINTS][9];  // cKinTree::BuildAttachTrans rotation (Rz*Ry*Rx of AttachTheta), row-major
     double attT[TRL_MAX_JOINTS][3];  // attach point
     double mass[TRL_MAX_JOINTS];

@@ -1074,6 +1074,9 @@ k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict_
     }
 }
 
+#include "trl_pd_block.cuh"
+#include "trl_pd_aba.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // k_rbd_extras: cRBDUtil::BuildJacobian / BuildCOMJacobian / CalcGravityForce (sim/RBDUtil.cpp:256-275,294-345,
 // 937-982) -- thread per env, same depth-first walk and per-level workspace as k_pd_tree.
@@ -2916,12 +2919,88 @@ static int pd_group_override() {
 }
 
 // per env; the allocation is rounded up to whole tiles of kTile envs by the caller (trl_pd_scratch_tile())
-size_t trl_pd_scratch_doubles(const DevModel& hm) { return (size_t)pd_scratch(hm.n, hm.nl).stride; }
+size_t trl_pd_scratch_doubles(const DevModel& hm) {
+    return std::max((size_t)pd_scratch(hm.n, hm.nl).stride, (size_t)hm.bx.aba_slots);
+}
 int trl_pd_scratch_tile() { return kTile; }
+
+// k_pd_block: one block per tile of TE envs. TE = 32 unless the tile's state does not fit in shared memory; the number
+// of warps per block keeps about 16 warps per SM (4 per sub-partition) across however many tiles share an SM.
+// Returns 0, a cudaError_t, or -1 when the model does not fit (the caller falls back to the three-kernel chain).
+static int launch_pd_block(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+    const PdBlkLayout L = pd_blk_layout(hm.N, hm.n, hm.nl, hm.bx.hcount);
+    const size_t cst_bytes = (size_t)pd_cst_doubles(hm.N) * sizeof(double);
+    const size_t kStatic = 2048, kBudget = 227 * 1024;
+    int te = 0;
+    size_t smem = 0;
+    for (int cand = 32; cand >= 16 && !te; cand >>= 1) {
+        smem = cst_bytes + (size_t)L.total * cand * sizeof(double);
+        if (smem + kStatic <= kBudget) te = cand;
+    }
+    if (!te) return -1;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const int tiles = (E + te - 1) / te;
+    const int per_sm_fit = (int)(kBudget / (smem + kStatic + 1024));
+    const int per_sm = std::max(1, std::min(per_sm_fit, (tiles + num_sms - 1) / num_sms));
+    int W = 16 / per_sm;
+    W = std::max(4, std::min(16, W));
+    static const int w_env = env_int("TRL_PD_BLOCK_WARPS", 0);  // tuning hook
+    if (w_env >= 1 && w_env <= 16) W = w_env;
+    int rc;
+    if (te == 32) {
+        rc = ensure_smem((const void*)k_pd_block<32>, smem);
+        if (rc) return rc;
+        k_pd_block<32><<<tiles, W * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
+    } else {
+        rc = ensure_smem((const void*)k_pd_block<16>, smem);
+        if (rc) return rc;
+        k_pd_block<16><<<tiles, W * 32, smem, (cudaStream_t)stream>>>(dm, E, p);
+    }
+    return (int)cudaGetLastError();
+}
+
+// k_pd_aba: lane = env, one warp per branch of the tree, one 32-env tile per block. Returns 0, a cudaError_t, or -1
+// when the kernel does not apply (M / C requested, a shape-less body, or a tree too deep for the workspace).
+static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
+    if (p.out_mass || p.out_bias || !hm.bx.all_valid || !scratch || hm.N < 2) return -1;
+    const int nb = hm.bx.num_branches;
+    int W = std::min(nb, 8);  // one warp per branch
+    static const int w_env = env_int("TRL_PD_ABA_WARPS", 0);  // tuning hook
+    if (w_env >= 1 && w_env <= 8) W = std::min(w_env, nb);
+    const size_t smem = (size_t)pd_cst_doubles(hm.N) * sizeof(double) +
+                        (size_t)aba_ws_elems(nb, hm.bx.branch_area, W) * kTile * sizeof(double);
+    if (smem > 227 * 1024 - 3072) return -1;
+    int rc = ensure_smem((const void*)k_pd_aba, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_pd_aba<<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(dm, E, p, scratch, (int)trl_pd_scratch_doubles(hm));
+    return (int)cudaGetLastError();
+}
 
 // Returns the number of kernels launched (>0) or a negative cudaError.
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
     const int nl = hm.nl, N = hm.N;
+    {
+        static const int aba_env = env_int("TRL_PD_ABA", 1);  // A/B hook: 0 = CRBA + LDLT kernels only
+        if (aba_env) {
+            const int rc = launch_pd_aba(dm, hm, E, p, scratch, stream);
+            if (rc == 0) return 1;
+            if (rc > 0) return -rc;
+        }
+    }
+    {
+        static const int block_env = env_int("TRL_PD_BLOCK", 1);  // A/B hook: 0 = the thread-per-env three-kernel chain
+        if (block_env) {
+            const int rc = launch_pd_block(dm, hm, E, p, stream);
+            if (rc == 0) return 1;
+            if (rc > 0) return -rc;
+        }
+    }
     if (nl > 32) {
         int rc = launch_imp_pd_t<32, 0, false>(dm, hm, E, p, nullptr, stream);
         return rc ? -rc : 1;

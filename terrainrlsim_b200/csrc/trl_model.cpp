@@ -343,6 +343,36 @@ int trl_build_dev_model(trl_model* m) {
             d.ix.col_parent[c] = (p == -1) ? -1 : d.ix.first_col[p] + d.ix.ncol[p] - 1;
         }
     }
+    {   // branch-sparse H layout of k_pd_block
+        PdBlkIdx& b = d.bx;
+        std::memset(&b, 0, sizeof(b));
+        int total = 0, maxd = 0;
+        for (int c = 0; c < nl; ++c) {
+            const int pc = d.ix.col_parent[c];
+            b.cdepth[c] = (pc == -1) ? 0 : (signed char)(b.cdepth[pc] + 1);
+            b.rowbase[c] = (short)total;
+            total += b.cdepth[c] + 1;
+            maxd = std::max(maxd, (int)b.cdepth[c]);
+        }
+        b.hcount = total;
+        b.max_cdepth = maxd;
+        int pos2 = 0;
+        for (int dep = 0; dep <= maxd; ++dep) {
+            b.cd_start[dep] = (signed char)pos2;
+            for (int c = 0; c < nl; ++c)
+                if (b.cdepth[c] == dep) b.cd_order[pos2++] = (signed char)c;
+        }
+        b.cd_start[maxd + 1] = (signed char)pos2;
+        int slots = 0;
+        b.all_valid = 1;
+        for (int j = 0; j < N; ++j) {
+            b.use_world[j] = (d.ix.pd_valid[j] && m->pd_params[(size_t)j * TRL_PD_COLS + 17] != 0) ? 1 : 0;
+            b.aba_off[j] = (short)slots;
+            if (d.ix.parent[j] != -1) slots += 1 + 14 * d.ix.ncol[j] + (d.ix.size[j] - d.ix.ncol[j]);  // + dead slots
+            if (!d.ix.valid_body[j]) b.all_valid = 0;
+        }
+        b.aba_slots = slots;
+    }
     // levels
     int max_level = 0;
     for (int j = 0; j < N; ++j) max_level = std::max(max_level, (int)d.ix.level[j]);
@@ -377,6 +407,42 @@ int trl_build_dev_model(trl_model* m) {
                 }
             }
         }
+    }
+    {   // pre-order list, branches (subtrees of the root's children) and their workspace layout for k_pd_aba
+        PdBlkIdx& b = d.bx;
+        int np = 0;
+        for (int k = 0; k < 2 * N; ++k)
+            if (d.ix.dfs_event[k] >= 0) b.preorder[np++] = d.ix.dfs_event[k];
+        for (int j = 0; j < N; ++j) { b.nchild[j] = 0; b.xoff[j] = -1; }
+        for (int j = 1; j < N; ++j) b.nchild[d.ix.parent[j]]++;
+        int nb = 0, area = 0;
+        for (int k = 1; k < 2 * N - 1;) {  // events between "enter root" and "leave root"
+            const int r = d.ix.dfs_event[k];  // enters a child of the root
+            int k1 = k;
+            while (d.ix.dfs_event[k1] != -1 - r) ++k1;
+            b.b_ev0[nb] = (signed char)k;
+            b.b_ev1[nb] = (signed char)(k1 + 1);
+            int depth = 0, extra = 0, first = -1, cnt = 0;
+            for (int q = k; q <= k1; ++q) {
+                const int jj = d.ix.dfs_event[q];
+                if (jj < 0) continue;
+                depth = std::max(depth, (int)d.ix.level[jj]);
+                ++cnt;
+            }
+            for (int q = 0; q < N; ++q)
+                if (b.preorder[q] == r) first = q;
+            b.b_pre0[nb] = (signed char)first;
+            b.b_pre1[nb] = (signed char)(first + cnt);
+            for (int q = k; q <= k1; ++q) {
+                const int jj = d.ix.dfs_event[q];
+                if (jj >= 0 && b.nchild[jj] >= 2) { b.xoff[jj] = (short)(22 * depth + 39 * extra); ++extra; }
+            }
+            area = std::max(area, 22 * depth + 39 * extra);
+            ++nb;
+            k = k1 + 1;
+        }
+        b.num_branches = nb;
+        b.branch_area = area;
     }
     {
         int sb = 0, sc = 0;

@@ -1,0 +1,715 @@
+// k_pd_aba: stable-PD torque WITHOUT materialising M -- thread per env, two depth-first walks. Included by
+// trl_kernels.cu (inside its anonymous namespace).
+//
+// The reference builds M (CRBA) and C (RNEA), adds dt*Kd to the diagonal and solves (M + dt Kd) qdd = u - C with a
+// dense LDLT (sim/ImpPDController.cpp:137-196). The same qdd follows from eliminating the system joint by joint from
+// the leaves of the kinematic tree, which is what Featherstone's branch-sparse L^T D L factorisation does to M -- and
+// carried out on 6x6 articulated quantities instead of on columns of M it is the articulated-body recursion with the
+// diagonal dt*Kd acting as a joint-space ("rotor") inertia. In the root-joint frame used by all kernels here (every
+// transform, velocity, inertia and force expressed in one frame, so parents accumulate children by plain addition):
+//
+//   down   : T_j, V_j, A_j (bias acceleration with qdd = 0, gravity included), body inertia I_j, f_j = I_j A_j + V_j x* I_j V_j
+//            (identical to the RNEA pass of k_pd_block); u_j = Kp e_p + Kd e_v
+//   up     : I^A_j = I_j + sum_c I^a_c ,  p^A_j = f_j + sum_c p^a_c                       (children c of j)
+//            U = I^A S_j ,  D = S_j^T U + dt Kd_j(unmasked) ,  uh = u_j - S_j^T p^A
+//            I^a_j = I^A - U D^-1 U^T ,  p^a_j = p^A + U D^-1 uh                           (handed to the parent)
+//   root   : 6x6 solve  (S^T I^A S) qdd_root = -S^T p^A ,  delta_root = S qdd_root
+//   down 2 : qdd_j = D^-1 (uh - U^T delta_parent) ,  delta_j = delta_parent + S_j qdd_j ,  tau_j = u_j - dt Kd_j(masked) qdd_j
+//
+// where delta_j is the part of the body's spatial acceleration caused by the joint accelerations. This is exactly
+// (M + dt Kd) qdd = u - C: S^T(I^A delta + p^A) is row j of M qdd + C restricted to the subtree. The result agrees with the
+// LDLT path (k_pd_block, and the reference through the oracle) to ~1e-13; 1e-9 is the bar.
+//
+// Cost: O(N) 6x6 work -- about 3.3 kFLOP per biped3D env instead of 8.2 kFLOP (16.3 k by SURVEY.md's count) for
+// CRBA + RNEA + LDLT, and no n x n matrix.
+//
+// Mapping: lane = env (32-env tile per block), ONE WARP PER BRANCH (a branch = the subtree of one child of the root):
+// the branches are independent between the root's "down" step and its solve, so a biped's two legs, a raptor's four
+// limbs, ... are walked concurrently by different warps -- this is what lifts the chain off the single-warp latency
+// floor (16384 envs are only 512 tiles on 592 SM sub-partitions). Warp 0 also does the root. Three block barriers.
+//
+// State: a walker keeps 22 doubles per tree LEVEL of its branch in shared memory (T12, f6, u3, Kd1); the articulated
+// inertia / bias force travel up a chain in REGISTERS (a joint's "leave" is followed by its parent's when it is an only
+// child) and velocities / accelerations travel down in registers (a joint's "enter" is followed by its first child's);
+// only joints with two or more children own a [V6 A6 IA21 P6] block. biped3D: 12 + 2 x 27 + 2 x 66 = 198 doubles per env =
+// 51 KB per tile, so all 512 tiles of 16384 envs are resident at once. What the second walk needs (U D^-1, D^-1 uh, S, u,
+// Kd: 14k+1 doubles per joint with k dofs, plus the finished tau of dead slots) goes through a tile-major global
+// scratch (1.6 KB per env, written and read back by the same warp: L2-resident).
+//
+// Restrictions (callers fall back to k_pd_block): every body valid (the reference's handling of shape-less bodies
+// leaves M structurally inconsistent: SURVEY.md, k_rbd_extras note), no M / C output requested.
+#pragma once
+
+// symmetric 6x6 in 21 doubles, upper triangle row by row: (r, c), r <= c
+__host__ __device__ constexpr int sym6(int r, int c) { return r <= c ? r * 6 - r * (r - 1) / 2 + (c - r) : c * 6 - c * (c - 1) / 2 + (r - c); }
+
+// y = A x for symmetric A (21)
+TRL_DEV void sym6_mulv(const double* A, const double* x, double* y) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s += A[sym6(r, c)] * x[c];
+        y[r] = s;
+    }
+}
+
+TRL_DEV double dot6(const double* a, const double* b) {
+    return (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (a[3] * b[3] + a[4] * b[4] + a[5] * b[5]);
+}
+
+
+// body inertia of joint j in the root frame from its transform T: I = (m, h = m c, Ixx Ixy Ixz Iyy Iyz Izz about the origin)
+TRL_DEV void aba_inertia(const double* T, const double* cj_, double* I) {
+    const double m = cj_[12];
+    double c[3];
+    mat3_mulv(T, cj_ + 13, c);
+    c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
+    const double d0 = cj_[16], d1 = cj_[17], d2 = cj_[18];
+    double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
+    double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
+    double Ixz = T[0] * T[6] * d0 + T[1] * T[7] * d1 + T[2] * T[8] * d2;
+    double Iyy = T[3] * T[3] * d0 + T[4] * T[4] * d1 + T[5] * T[5] * d2;
+    double Iyz = T[3] * T[6] * d0 + T[4] * T[7] * d1 + T[5] * T[8] * d2;
+    double Izz = T[6] * T[6] * d0 + T[7] * T[7] * d1 + T[8] * T[8] * d2;
+    Ixx += m * (c[1] * c[1] + c[2] * c[2]);
+    Iyy += m * (c[0] * c[0] + c[2] * c[2]);
+    Izz += m * (c[0] * c[0] + c[1] * c[1]);
+    Ixy -= m * c[0] * c[1];
+    Ixz -= m * c[0] * c[2];
+    Iyz -= m * c[1] * c[2];
+    I[0] = m; I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
+    I[4] = Ixx; I[5] = Ixy; I[6] = Ixz; I[7] = Iyy; I[8] = Iyz; I[9] = Izz;
+}
+
+// body inertia and f = I a + V x* (I V)
+TRL_DEV void aba_body(const double* T, const double* cj_, const double* Vj, const double* Aj, double* I, double* f) {
+    aba_inertia(T, cj_, I);
+    const double m = I[0];
+    const double* h = I + 1;
+    const double Ixx = I[4], Ixy = I[5], Ixz = I[6], Iyy = I[7], Iyz = I[8], Izz = I[9];
+    double hxv[3], hxw[3];
+    cross3(h, Aj + 3, hxv);
+    cross3(h, Aj, hxw);
+    const double na[3] = {Ixx * Aj[0] + Ixy * Aj[1] + Ixz * Aj[2] + hxv[0],
+                          Ixy * Aj[0] + Iyy * Aj[1] + Iyz * Aj[2] + hxv[1],
+                          Ixz * Aj[0] + Iyz * Aj[1] + Izz * Aj[2] + hxv[2]};
+    const double fa[3] = {m * Aj[3] - hxw[0], m * Aj[4] - hxw[1], m * Aj[5] - hxw[2]};
+    cross3(h, Vj + 3, hxv);
+    cross3(h, Vj, hxw);
+    const double nv[3] = {Ixx * Vj[0] + Ixy * Vj[1] + Ixz * Vj[2] + hxv[0],
+                          Ixy * Vj[0] + Iyy * Vj[1] + Iyz * Vj[2] + hxv[1],
+                          Ixz * Vj[0] + Iyz * Vj[1] + Izz * Vj[2] + hxv[2]};
+    const double fv[3] = {m * Vj[3] - hxw[0], m * Vj[4] - hxw[1], m * Vj[5] - hxw[2]};
+    double wxn[3], vxf[3], wxf[3];
+    cross3(Vj, nv, wxn);
+    cross3(Vj + 3, fv, vxf);
+    cross3(Vj, fv, wxf);
+    f[0] = na[0] + wxn[0] + vxf[0]; f[1] = na[1] + wxn[1] + vxf[1]; f[2] = na[2] + wxn[2] + vxf[2];
+    f[3] = fa[0] + wxf[0]; f[4] = fa[1] + wxf[1]; f[5] = fa[2] + wxf[2];
+}
+
+// joint-subspace column in the root frame from the joint's transform T (registers): angular about / linear along axis `ax`
+TRL_DEV void aba_column(int kind, int ax, const double* T, double* S) {
+    const double a0 = (ax == 0) ? T[0] : (ax == 1) ? T[1] : T[2];
+    const double a1 = (ax == 0) ? T[3] : (ax == 1) ? T[4] : T[5];
+    const double a2 = (ax == 0) ? T[6] : (ax == 1) ? T[7] : T[8];
+    if (kind == CK_ANG) {
+        S[0] = a0; S[1] = a1; S[2] = a2;
+        S[3] = T[10] * a2 - T[11] * a1; S[4] = T[11] * a0 - T[9] * a2; S[5] = T[9] * a1 - T[10] * a0;
+    } else {
+        S[0] = S[1] = S[2] = 0.0;
+        S[3] = a0; S[4] = a1; S[5] = a2;
+    }
+}
+
+// workspace layout, in elements of 32 doubles ([element][lane]):
+//   [0, 12)                       root V, A (second walk: delta of the root in [0, 6))
+//   [12, 12 + 27 nb)              per branch: I^a (21), p^a (6) handed to the root; afterwards the tau staging rows
+//   [.., + W x branch_area)       one area per WARP: 22 per level below the root (T12 f6 u3 Kd1; second walk: delta in
+//                                 [0, 6)), then the [V6 A6 IA21 P6] blocks of joints with several children
+__host__ __device__ inline int aba_ws_elems(int nb, int branch_area, int warps) { return 12 + 27 * nb + warps * branch_area; }
+
+__global__ void __launch_bounds__(256)
+k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch, int scratch_stride) {
+    KTrace trace_(TR_PD_TREE);
+    extern __shared__ double smem[];
+    __shared__ ModelIdx s_ix;
+    __shared__ PdBlkIdx s_bx;
+    __shared__ int s_status[32];
+    {
+        const int cnt = M->N * kCst;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
+        const uint4* src = reinterpret_cast<const uint4*>(&M->bx);
+        uint4* d = reinterpret_cast<uint4*>(&s_bx);
+        for (int i = threadIdx.x; i < (int)(sizeof(PdBlkIdx) / 16); i += blockDim.x) d[i] = __ldg(src + i);
+        if (threadIdx.x < 32) s_status[threadIdx.x] = 0;
+    }
+    stage_model_idx(&s_ix, M);  // contains the barrier
+    const ModelIdx* X = &s_ix;
+    const PdBlkIdx* B = &s_bx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int tile = blockIdx.x;
+    const int e0 = tile * kTile;
+    const int envs = min(kTile, E - e0);
+    const bool env_ok = lane < envs;
+    const size_t e = (size_t)(e0 + (env_ok ? lane : envs - 1));  // tail lanes redo the last env and store nothing
+    const int N = M->N, n = M->n, nb = B->num_branches;
+    const double* cst = smem;
+    double* ws0 = smem + pd_cst_doubles(N);  // workspace base (no lane offset)
+    double* ws = ws0 + lane;                 // element k of this env: ws[k * 32]
+    double* sc = scratch + (size_t)tile * scratch_stride * kTile + lane;
+    const double dt = p.dt;
+    const double* q = p.pose + e * n;
+    const double* qd = p.vel + e * n;
+    const double* tq = p.tar_pose + e * n;
+    const double* tqd = p.tar_vel + e * n;
+    const int kOut = 12;
+    double* area = ws + (size_t)(kOut + 27 * nb + warp * B->branch_area) * kTile;  // this warp's branch area
+    int status = 0;
+    double rq9[9], Rw[9];  // R(q_root) and the world <- root rotation
+    quat_to_mat(q[3], q[4], q[5], q[6], rq9);
+    mat3_mul(cst, rq9, Rw);
+
+    // ======================= root, down: V_0 = S qd, A_0 = gravity + c_root (warp 0) =======================
+    double fr[6];  // f of the root body (warp 0)
+    double Ir[10];
+    if (warp == 0) {
+        double wr[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) wr[i] = qd[i];
+        const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
+        double g0[3];
+        mat3T_mulv(Rw, ng, g0);  // a_0 = X_{world->root}(0, -g)  (RBDUtil.cpp:17-18,59-60)
+        double dq[4];
+        const double qr4[4] = {q[3], q[4], q[5], q[6]};
+        quat_diff_mul(qr4, wr + 3, dq);  // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
+        const double qw = qr4[0], qx = qr4[1], qy = qr4[2], qz = qr4[3];
+        const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
+        const double m00 = 4 * (qw * dw + qx * dx), m11 = 4 * (qw * dw + qy * dy), m22 = 4 * (qw * dw + qz * dz);
+        const double m10 = 2 * (dx * qy + qx * dy - dw * qz - qw * dz);
+        const double m01 = 2 * (dx * qy + qx * dy + dw * qz + qw * dz);
+        const double m20 = 2 * (dx * qz + qx * dz + dw * qy + qw * dy);
+        const double m02 = 2 * (dx * qz + qx * dz - dw * qy - qw * dy);
+        const double m21 = 2 * (dy * qz + qy * dz - dw * qx - qw * dx);
+        const double m12 = 2 * (dy * qz + qy * dz + dw * qx + qw * dx);
+        double V[6], A[6];
+        V[0] = wr[3]; V[1] = wr[4]; V[2] = wr[5];
+        V[3] = rq9[0] * wr[0] + rq9[3] * wr[1] + rq9[6] * wr[2];
+        V[4] = rq9[1] * wr[0] + rq9[4] * wr[1] + rq9[7] * wr[2];
+        V[5] = rq9[2] * wr[0] + rq9[5] * wr[1] + rq9[8] * wr[2];
+        A[0] = A[1] = A[2] = 0.0;
+        A[3] = g0[0] + (m00 * wr[0] + m01 * wr[1] + m02 * wr[2]);
+        A[4] = g0[1] + (m10 * wr[0] + m11 * wr[1] + m12 * wr[2]);
+        A[5] = g0[2] + (m20 * wr[0] + m21 * wr[1] + m22 * wr[2]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { ws[k * kTile] = V[k]; ws[(6 + k) * kTile] = A[k]; }
+        const double Tid[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+        aba_body(Tid, cst, V, A, Ir, fr);
+    }
+    __syncthreads();
+
+    // ======================= branches: first walk (down: T V A f u ; up: articulated elimination) =======================
+    const int nev_all = 2 * N;
+    (void)nev_all;
+    for (int b = warp; b < nb; b += W) {
+        double Vc[6], Ac[6];      // V, A of the joint entered last (handed to its first child in registers)
+        double IAc[21], Pc[6];    // articulated inertia / bias force of the joint left last (handed to its parent)
+#pragma unroll
+        for (int i = 0; i < 21; ++i) IAc[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { Pc[i] = 0.0; Vc[i] = 0.0; Ac[i] = 0.0; }
+        int last_entered = -1;
+        const int ev0 = B->b_ev0[b], ev1 = B->b_ev1[b];
+        for (int evi = ev0; evi < ev1; ++evi) {
+            const int code = X->dfs_event[evi];
+            if (code >= 0) {
+                // ---------------- enter joint j ----------------
+                const int j = code;
+                const int lv = X->level[j];
+                const int pj = X->parent[j];
+                double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;  // T12 f6 u3 kd1
+                const int o = X->offset[j], sz = X->size[j], type = X->type[j];
+                const double* cj_ = cst + kCst * j;
+                double qj[4], wj[4], tar[4], tarv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool in = i < sz;
+                    qj[i] = in ? q[o + i] : 0.0;
+                    wj[i] = in ? qd[o + i] : 0.0;
+                    tar[i] = in ? tq[o + i] : 0.0;
+                    tarv[i] = in ? tqd[o + i] : 0.0;
+                }
+                double R[9], t[3], T[12];
+                joint_local_trans(X, j, qj, cj_, cj_ + 9, R, t);
+                double Vp[6], Ap[6];
+                if (lv == 1) {  // parent = root: identity transform, V / A from the root block
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) T[i] = R[i];
+                    T[9] = t[0]; T[10] = t[1]; T[11] = t[2];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { Vp[k] = ws[k * kTile]; Ap[k] = ws[(6 + k) * kTile]; }
+                } else {
+                    const double* Wp = area + (size_t)(22 * (lv - 2)) * kTile;
+                    double Tp[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) Tp[i] = Wp[i * kTile];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
+                        T[9 + r] = Tp[9 + r] + (Tp[r * 3] * t[0] + Tp[r * 3 + 1] * t[1] + Tp[r * 3 + 2] * t[2]);
+                    }
+                    if (last_entered == pj) {  // first child: the parent's V / A are still in registers
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) { Vp[k] = Vc[k]; Ap[k] = Ac[k]; }
+                    } else {                   // later child: the parent owns a block
+                        const double* Xp = area + (size_t)B->xoff[pj] * kTile;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) { Vp[k] = Xp[k * kTile]; Ap[k] = Xp[(6 + k) * kTile]; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i) Wl[i * kTile] = T[i];
+                // s_j = S_j qd_j ; V_j = V_p + s_j ; A_j = A_p + V_p x s_j
+                double s[6] = {0, 0, 0, 0, 0, 0};
+                const int c0 = X->first_col[j], nc = X->ncol[j];
+                for (int c = c0; c < c0 + nc; ++c) {
+                    const int di = X->col_dof[c] - o;
+                    const double w = (di == 0) ? wj[0] : (di == 1) ? wj[1] : (di == 2) ? wj[2] : wj[3];
+                    const int kind = X->col_kind[c], ax = X->col_axis[c];
+                    const double a0 = (ax == 0) ? T[0] : (ax == 1) ? T[1] : T[2];
+                    const double a1 = (ax == 0) ? T[3] : (ax == 1) ? T[4] : T[5];
+                    const double a2 = (ax == 0) ? T[6] : (ax == 1) ? T[7] : T[8];
+                    if (kind == CK_ANG) {
+                        s[0] += a0 * w; s[1] += a1 * w; s[2] += a2 * w;
+                        s[3] += (T[10] * a2 - T[11] * a1) * w;
+                        s[4] += (T[11] * a0 - T[9] * a2) * w;
+                        s[5] += (T[9] * a1 - T[10] * a0) * w;
+                    } else {
+                        s[3] += a0 * w; s[4] += a1 * w; s[5] += a2 * w;
+                    }
+                }
+                double x0[3], x1[3], x2[3];
+                cross3(Vp, s, x0);
+                cross3(Vp + 3, s, x1);
+                cross3(Vp, s + 3, x2);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    Vc[k] = Vp[k] + s[k];
+                    Vc[3 + k] = Vp[3 + k] + s[3 + k];
+                    Ac[k] = Ap[k] + x0[k];
+                    Ac[3 + k] = Ap[3 + k] + (x1[k] + x2[k]);
+                }
+                last_entered = j;
+                if (B->xoff[j] >= 0) {  // several children: V / A for the later ones, zeroed accumulators
+                    double* Xj = area + (size_t)B->xoff[j] * kTile;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { Xj[k * kTile] = Vc[k]; Xj[(6 + k) * kTile] = Ac[k]; }
+#pragma unroll
+                    for (int k = 12; k < 39; ++k) Xj[k * kTile] = 0.0;
+                }
+                // body force f_j = I_j A_j + V_j x* I_j V_j (the inertia itself is rebuilt from T_j on the way up)
+                {
+                    double Ib[10], f[6];
+                    aba_body(T, cj_, Vc, Ac, Ib, f);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) Wl[(12 + k) * kTile] = f[k];
+                }
+                // PD terms (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196; targets through
+                // cPDController::SetTargetTheta / GetTargetTheta, PDController.cpp:191-273)
+                const bool valid = X->pd_valid[j] != 0;
+                const bool active = valid && (p.joint_active ? (p.joint_active[e * N + j] != 0) : true);
+                double kp = 0.0, kd = 0.0;
+                if (valid) {
+                    kp = p.kp ? p.kp[e * N + j] : cj_[19];
+                    kd = p.kd ? p.kd[e * N + j] : cj_[20];
+                }
+                const double kpm = active ? kp : 0.0, kdm = active ? kd : 0.0;
+                Wl[21 * kTile] = kd;  // unmasked gains go on the diagonal
+                const bool world = B->use_world[j] != 0;
+                double Wm[9];
+                if (world) mat3_mul(Rw, T, Wm);
+                double ep[4] = {0, 0, 0, 0};
+                const bool sph = valid && type == JT_SPHERICAL;
+                double tar0 = 0.0;
+                if (valid && !sph && sz > 0) tar0 = tar[0];
+                if (sph) {
+                    double dq[4], qi[4];
+                    quat_diff_mul(qj, wj, dq);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) qi[i] = qj[i] + dt * dq[i];
+                    quat_normalize(qi);
+                    if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
+                    else quat_normalize(tar);
+                    if (world) {  // tar = rel_rot * (world_rot^-1 * tar), PDController.cpp:254-267
+                        const double st = sqrt(qj[1] * qj[1] + qj[2] * qj[2] + qj[3] * qj[3]);
+                        double ax3[3] = {0, 0, 1}, th = 0.0;
+                        if (st > 0.0001) {
+                            const double sg = (double)((0.0 < qj[0]) - (qj[0] < 0.0));
+                            th = 2 * sg * asin(st);
+                            ax3[0] = qj[1] / st; ax3[1] = qj[2] / st; ax3[2] = qj[3] / st;
+                        }
+                        double sh, ch;
+                        sincos(th / 2, &sh, &ch);
+                        const double rel[4] = {ch, sh * ax3[0], sh * ax3[1], sh * ax3[2]};
+                        double wq[4];
+                        pb_rot_to_quat(Wm, wq);
+                        const double wc[4] = {wq[0], -wq[1], -wq[2], -wq[3]};
+                        double diff[4], t2[4];
+                        quat_mul(wc, tar, diff);
+                        quat_mul(rel, diff, t2);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tar[i] = t2[i];
+                    }
+                    quat_vel_rel(qi, tar, 1.0, ep);
+                } else if (world && valid && type == JT_REVOLUTE) {  // PDController.cpp:238-252
+                    double axis_world[3], theta_world;
+                    pb_rot_to_axis_angle(Wm, axis_world, theta_world);
+                    const double dwv = axis_world[0] * Wm[2] + axis_world[1] * Wm[5] + axis_world[2] * Wm[8];
+                    tar0 -= dwv * theta_world - Wm[8] * qj[0];
+                }
+                // per dof: u = Kp e_p + Kd e_v. Live dofs keep u (<= 3 per joint) for the way up; dead slots
+                // (spherical slot 3) are decoupled 1x1 systems and are finished here.
+                int lc = 0, nd = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i >= sz) break;
+                    const double qdi = wj[i];
+                    double epi = 0.0, evi_ = 0.0;
+                    if (valid) {
+                        if (sph) {
+                            epi = ep[i];
+                            evi_ = ((i < 3) ? tarv[i] : 0.0) - qdi;
+                        } else {
+                            const double ti = (i == 0) ? tar0 : tar[i];
+                            epi = (ti - (qj[i] + dt * qdi)) / 1.0;
+                            evi_ = tarv[i] - qdi;
+                        }
+                    }
+                    const double u = kpm * epi + kdm * evi_;
+                    if (X->dof_col[o + i] < 0) {
+                        const double dg = dt * kd;
+                        const double acc = (fabs(dg) > DBL_MIN) ? u / dg : 0.0;
+                        const double t0 = kpm * epi + kdm * (evi_ - dt * acc);
+                        if (!isfinite(t0)) status |= 1;
+                        sc[(size_t)(B->aba_off[j] + 1 + 14 * nc + nd) * kTile] = t0;  // after the joint's live data
+                        ++nd;
+                    } else {
+                        if (lc < 3) Wl[(18 + lc) * kTile] = u;
+                        ++lc;
+                    }
+                }
+                sc[(size_t)B->aba_off[j] * kTile] = kdm * dt;  // masked Kd dt, first scratch slot of the joint
+            } else {
+                // ---------------- leave joint j: its subtree is complete ----------------
+                const int j = -1 - code;
+                const int lv = X->level[j];
+                const int pj = X->parent[j];
+                double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;
+                const double* cj_ = cst + kCst * j;
+                double T[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) T[i] = Wl[i * kTile];
+                // I^A = I_j + children, p^A = f_j + children
+                double IA[21], P[6];
+                {
+                    double Ib[10];
+                    aba_inertia(T, cj_, Ib);
+                    const double m = Ib[0], h0 = Ib[1], h1 = Ib[2], h2 = Ib[3];
+                    IA[sym6(0, 0)] = Ib[4]; IA[sym6(0, 1)] = Ib[5]; IA[sym6(0, 2)] = Ib[6];
+                    IA[sym6(1, 1)] = Ib[7]; IA[sym6(1, 2)] = Ib[8]; IA[sym6(2, 2)] = Ib[9];
+                    IA[sym6(0, 3)] = 0.0; IA[sym6(0, 4)] = -h2; IA[sym6(0, 5)] = h1;
+                    IA[sym6(1, 3)] = h2;  IA[sym6(1, 4)] = 0.0; IA[sym6(1, 5)] = -h0;
+                    IA[sym6(2, 3)] = -h1; IA[sym6(2, 4)] = h0;  IA[sym6(2, 5)] = 0.0;
+                    IA[sym6(3, 3)] = m; IA[sym6(3, 4)] = 0.0; IA[sym6(3, 5)] = 0.0;
+                    IA[sym6(4, 4)] = m; IA[sym6(4, 5)] = 0.0;
+                    IA[sym6(5, 5)] = m;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) P[i] = Wl[(12 + i) * kTile];
+                const int nch = B->nchild[j];
+                if (nch == 1) {  // only child: its result is still in registers
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) IA[i] += IAc[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) P[i] += Pc[i];
+                } else if (nch > 1) {
+                    const double* Xj = area + (size_t)B->xoff[j] * kTile;
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) IA[i] += Xj[(12 + i) * kTile];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) P[i] += Xj[(33 + i) * kTile];
+                }
+                const int c0 = X->first_col[j], nc = X->ncol[j];
+                double* sj = sc + (size_t)B->aba_off[j] * kTile;  // [kdm dt][u k][uh' k][S 6k][U' 6k][dead tau]
+                const double kdd = dt * Wl[21 * kTile];
+                if (nc == 1) {
+                    const int kind = X->col_kind[c0], ax = X->col_axis[c0];
+                    double S[6];
+                    aba_column(kind, ax, T, S);
+                    double U[6];
+                    sym6_mulv(IA, S, U);
+                    const double D = dot6(S, U) + kdd;
+                    if (!(D > 0.0)) status |= 2;
+                    const double u = Wl[18 * kTile];
+                    const double uh = u - dot6(S, P);
+                    const double inv = fast_rcp(D);
+                    const double uhs = uh * inv;
+                    double Us[6];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) Us[r] = U[r] * inv;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c) IA[sym6(r, c)] -= Us[r] * U[c];
+                        P[r] += U[r] * uhs;
+                    }
+                    sj[1 * kTile] = u;
+                    sj[2 * kTile] = uhs;
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) { sj[(3 + r) * kTile] = S[r]; sj[(9 + r) * kTile] = Us[r]; }
+                } else if (nc > 1) {  // 2 or 3 columns (planar, spherical): padded to 3 with an identity row
+                    double S[3][6], U[3][6], uh[3], u3[3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        const bool on = a < nc;
+                        aba_column(on ? X->col_kind[c0 + a] : CK_LIN, on ? X->col_axis[c0 + a] : 0, T, S[a]);
+                        if (!on) {
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) S[a][r] = 0.0;
+                        }
+                        sym6_mulv(IA, S[a], U[a]);
+                        u3[a] = on ? Wl[(18 + a) * kTile] : 0.0;
+                        uh[a] = u3[a] - dot6(S[a], P);
+                    }
+                    const double D00 = dot6(S[0], U[0]) + kdd, D11 = dot6(S[1], U[1]) + kdd;
+                    const double D22 = (nc > 2) ? dot6(S[2], U[2]) + kdd : 1.0;
+                    const double D10 = dot6(S[1], U[0]), D20 = dot6(S[2], U[0]), D21 = dot6(S[2], U[1]);
+                    const double i0 = fast_rcp(D00);
+                    const double l10 = D10 * i0, l20 = D20 * i0;
+                    const double e1 = D11 - l10 * D10;
+                    const double i1 = fast_rcp(e1);
+                    const double l21 = (D21 - l20 * D10) * i1;
+                    const double e2 = D22 - l20 * D20 - l21 * (D21 - l20 * D10);
+                    const double i2 = fast_rcp(e2);
+                    if (!(D00 > 0.0) || !(e1 > 0.0) || !(e2 > 0.0)) status |= 2;
+                    auto solve3 = [&](double y0, double y1, double y2, double& r0, double& r1, double& r2) {
+                        const double z1 = y1 - l10 * y0;
+                        const double z2 = y2 - l20 * y0 - l21 * z1;
+                        r2 = z2 * i2;
+                        r1 = z1 * i1 - l21 * r2;
+                        r0 = y0 * i0 - l10 * r1 - l20 * r2;
+                    };
+                    double uhs[3];
+                    solve3(uh[0], uh[1], uh[2], uhs[0], uhs[1], uhs[2]);
+                    double Us[3][6];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) solve3(U[0][r], U[1][r], U[2][r], Us[0][r], Us[1][r], Us[2][r]);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+                        for (int c = r; c < 6; ++c)
+                            IA[sym6(r, c)] -= Us[0][r] * U[0][c] + Us[1][r] * U[1][c] + Us[2][r] * U[2][c];
+                        P[r] += U[0][r] * uhs[0] + U[1][r] * uhs[1] + U[2][r] * uhs[2];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+                        if (a < nc) {
+                            sj[(1 + a) * kTile] = u3[a];
+                            sj[(1 + nc + a) * kTile] = uhs[a];
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) {
+                                sj[(1 + 2 * nc + 6 * a + r) * kTile] = S[a][r];
+                                sj[(1 + 8 * nc + 6 * a + r) * kTile] = Us[a][r];
+                            }
+                        }
+                }
+                // hand I^a, p^a to the parent: registers (only child), its block (several children) or the root's slot
+                if (lv == 1) {
+                    double* O = ws + (size_t)(kOut + 27 * b) * kTile;
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) O[i * kTile] = IA[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) O[(21 + i) * kTile] = P[i];
+                } else if (B->nchild[pj] == 1) {
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) IAc[i] = IA[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Pc[i] = P[i];
+                } else {
+                    double* Xp = area + (size_t)B->xoff[pj] * kTile;
+#pragma unroll
+                    for (int i = 0; i < 21; ++i) Xp[(12 + i) * kTile] += IA[i];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) Xp[(33 + i) * kTile] += P[i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ======================= root: (S^T I^A S) qdd = -S^T p^A, S = [rows of R(q_root) | e_x e_y e_z] (warp 0) =======================
+    const int np = n | 1;
+    const bool staged = np <= 27 * nb;
+    if (warp == 0) {
+        double IA[21], P[6];
+        {
+            const double m = Ir[0], h0 = Ir[1], h1 = Ir[2], h2 = Ir[3];
+            IA[sym6(0, 0)] = Ir[4]; IA[sym6(0, 1)] = Ir[5]; IA[sym6(0, 2)] = Ir[6];
+            IA[sym6(1, 1)] = Ir[7]; IA[sym6(1, 2)] = Ir[8]; IA[sym6(2, 2)] = Ir[9];
+            IA[sym6(0, 3)] = 0.0; IA[sym6(0, 4)] = -h2; IA[sym6(0, 5)] = h1;
+            IA[sym6(1, 3)] = h2;  IA[sym6(1, 4)] = 0.0; IA[sym6(1, 5)] = -h0;
+            IA[sym6(2, 3)] = -h1; IA[sym6(2, 4)] = h0;  IA[sym6(2, 5)] = 0.0;
+            IA[sym6(3, 3)] = m; IA[sym6(3, 4)] = 0.0; IA[sym6(3, 5)] = 0.0;
+            IA[sym6(4, 4)] = m; IA[sym6(4, 5)] = 0.0;
+            IA[sym6(5, 5)] = m;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) P[i] = fr[i];
+        for (int b = 0; b < nb; ++b) {
+            const double* O = ws + (size_t)(kOut + 27 * b) * kTile;
+#pragma unroll
+            for (int i = 0; i < 21; ++i) IA[i] += O[i * kTile];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) P[i] += O[(21 + i) * kTile];
+        }
+        double S[6][6];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            S[c][0] = S[c][1] = S[c][2] = 0.0;
+            S[c][3] = rq9[3 * c]; S[c][4] = rq9[3 * c + 1]; S[c][5] = rq9[3 * c + 2];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) S[3 + c][r] = (r == c) ? 1.0 : 0.0;
+        }
+        double A[6][6], bb[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double U[6];
+            sym6_mulv(IA, S[c], U);
+            bb[c] = -dot6(S[c], P);
+#pragma unroll
+            for (int r = 0; r <= c; ++r) A[c][r] = dot6(S[r], U);  // lower triangle
+        }
+        // unpivoted LDL^T (S^T I^A S is symmetric positive definite), forward / back substitution
+        double Lm[6][6], dd[6], dinv[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double d = A[k][k];
+#pragma unroll
+            for (int s = 0; s < k; ++s) d -= Lm[k][s] * Lm[k][s] * dd[s];
+            dd[k] = d;
+            if (!(d > 0.0)) status |= 2;
+            dinv[k] = fast_rcp(d);
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) {
+                double v = A[i][k];
+#pragma unroll
+                for (int s = 0; s < k; ++s) v -= Lm[i][s] * Lm[k][s] * dd[s];
+                Lm[i][k] = v * dinv[k];
+            }
+        }
+        double y[6], x[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double v = bb[k];
+#pragma unroll
+            for (int s = 0; s < k; ++s) v -= Lm[k][s] * y[s];
+            y[k] = v;
+        }
+#pragma unroll
+        for (int k = 5; k >= 0; --k) {
+            double v = y[k] * dinv[k];
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) v -= Lm[i][k] * x[i];
+            x[k] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s += S[c][r] * x[c];
+            ws[r * kTile] = s;  // delta of the root (V is dead)
+        }
+    }
+    __syncthreads();
+
+    // ======================= second walk: qdd_j = D^-1 (uh - U^T delta_p), delta_j = delta_p + S_j qdd_j, tau =======================
+    // tau is staged as [32][n | 1] rows (conflict-free for the per-env writes here and for the coalesced write below) in the
+    // region that carried the branch results; delta of a level reuses the first 6 elements of its slot (T is dead).
+    double* stage = ws0 + (size_t)kOut * kTile + (size_t)lane * np;
+    auto put_tau = [&](int dof, double v) {
+        if (staged) stage[dof] = v;
+        else if (env_ok) {
+            double* dst = p.tau + e * n + dof;
+            *dst = p.tau_accumulate ? *dst + v : v;
+        }
+    };
+    if (warp == 0)
+        for (int i = 0; i < 7; ++i) put_tau(i, 0.0);  // root dofs: no controller
+    for (int b = warp; b < nb; b += W) {
+        const int p0 = B->b_pre0[b], p1 = B->b_pre1[b];
+        for (int pi = p0; pi < p1; ++pi) {
+            const int j = B->preorder[pi];
+            const int lv = X->level[j];
+            double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;
+            const double* Dp = (lv == 1) ? ws : area + (size_t)(22 * (lv - 2)) * kTile;
+            if (pi + 1 < p1) {  // the next joint's scratch rows (contiguous, 256 B each): one cooperative L1 prefetch
+                const int jn = B->preorder[pi + 1];
+                const char* base = (const char*)(scratch + ((size_t)tile * scratch_stride + B->aba_off[jn]) * kTile);
+                const int lines = (1 + 14 * X->ncol[jn]) * 2;
+                for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)l * 128));
+            }
+            double dp[6], dl[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { dp[r] = Dp[r * kTile]; dl[r] = dp[r]; }
+            const int c0 = X->first_col[j], nc = X->ncol[j];
+            const double* sj = sc + (size_t)B->aba_off[j] * kTile;
+            const double kdmdt = sj[0];
+            double u[3], qdd[3], S[3][6], Us[3][6];  // every load of the joint first (one L2 round trip), arithmetic after
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const bool on = a < nc;
+                u[a] = on ? sj[(1 + a) * kTile] : 0.0;
+                qdd[a] = on ? sj[(1 + nc + a) * kTile] : 0.0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    S[a][r] = on ? sj[(1 + 2 * nc + 6 * a + r) * kTile] : 0.0;
+                    Us[a][r] = on ? sj[(1 + 8 * nc + 6 * a + r) * kTile] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                if (a >= nc) break;
+                qdd[a] -= dot6(Us[a], dp);
+#pragma unroll
+                for (int r = 0; r < 6; ++r) dl[r] += S[a][r] * qdd[a];
+                const double tv = u[a] - kdmdt * qdd[a];
+                if (!isfinite(tv)) status |= 1;
+                put_tau(X->col_dof[c0 + a], tv);
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) Wl[r * kTile] = dl[r];
+            const int o = X->offset[j], sz = X->size[j];
+            for (int i = 0, nd = 0; i < sz; ++i)
+                if (X->dof_col[o + i] < 0) {
+                    put_tau(o + i, sj[(1 + 14 * nc + nd) * kTile]);
+                    ++nd;
+                }
+        }
+    }
+    if (status) atomicOr(&s_status[lane], status);
+    __syncthreads();
+    if (staged) {
+        const double* st = ws0 + (size_t)kOut * kTile;
+        double* out = p.tau + (size_t)e0 * n;
+        const int total = envs * n;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int r = idx / n, c = idx - r * n;
+            const double v = st[r * np + c];
+            out[idx] = p.tau_accumulate ? out[idx] + v : v;
+        }
+    }
+    if (p.status && threadIdx.x < envs) p.status[e0 + threadIdx.x] = s_status[threadIdx.x];
+}
