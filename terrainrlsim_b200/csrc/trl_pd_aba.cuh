@@ -167,14 +167,14 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     const int kOut = 12;
     double* area = ws + (size_t)(kOut + 27 * nb + warp * B->branch_area) * kTile;  // this warp's branch area
     int status = 0;
-    double rq9[9], Rw[9];  // R(q_root) and the world <- root rotation
-    quat_to_mat(q[3], q[4], q[5], q[6], rq9);
-    mat3_mul(cst, rq9, Rw);
 
     // ======================= root, down: V_0 = S qd, A_0 = gravity + c_root (warp 0) =======================
     double fr[6];  // f of the root body (warp 0)
     double Ir[10];
     if (warp == 0) {
+        double rq9[9], Rw[9];  // R(q_root) and the world <- root rotation
+        quat_to_mat(q[3], q[4], q[5], q[6], rq9);
+        mat3_mul(cst, rq9, Rw);
         double wr[7];
 #pragma unroll
         for (int i = 0; i < 7; ++i) wr[i] = qd[i];
@@ -330,7 +330,12 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                 Wl[21 * kTile] = kd;  // unmasked gains go on the diagonal
                 const bool world = B->use_world[j] != 0;
                 double Wm[9];
-                if (world) mat3_mul(Rw, T, Wm);
+                if (world) {  // joint world rotation = (attach_root R(q_root)) R_j
+                    double rq9[9], Rw[9];
+                    quat_to_mat(q[3], q[4], q[5], q[6], rq9);
+                    mat3_mul(cst, rq9, Rw);
+                    mat3_mul(Rw, T, Wm);
+                }
                 double ep[4] = {0, 0, 0, 0};
                 const bool sph = valid && type == JT_SPHERICAL;
                 double tar0 = 0.0;
@@ -445,18 +450,17 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                 const int c0 = X->first_col[j], nc = X->ncol[j];
                 double* sj = sc + (size_t)B->aba_off[j] * kTile;  // [kdm dt][u k][uh' k][S 6k][U' 6k][dead tau]
                 const double kdd = dt * Wl[21 * kTile];
-                if (nc == 1) {
-                    const int kind = X->col_kind[c0], ax = X->col_axis[c0];
-                    double S[6];
-                    aba_column(kind, ax, T, S);
-                    double U[6];
+                // The joint's columns are eliminated one after the other (a k-dof joint = k stacked 1-dof joints: the same
+                // arithmetic as an LDL^T of its k x k block, with a third of the registers). dt*Kd sits on every diagonal.
+                for (int a = 0; a < nc; ++a) {
+                    double S[6], U[6];
+                    aba_column(X->col_kind[c0 + a], X->col_axis[c0 + a], T, S);
                     sym6_mulv(IA, S, U);
                     const double D = dot6(S, U) + kdd;
                     if (!(D > 0.0)) status |= 2;
-                    const double u = Wl[18 * kTile];
-                    const double uh = u - dot6(S, P);
+                    const double u = Wl[(18 + a) * kTile];
                     const double inv = fast_rcp(D);
-                    const double uhs = uh * inv;
+                    const double uhs = (u - dot6(S, P)) * inv;
                     double Us[6];
 #pragma unroll
                     for (int r = 0; r < 6; ++r) Us[r] = U[r] * inv;
@@ -466,65 +470,13 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                         for (int c = r; c < 6; ++c) IA[sym6(r, c)] -= Us[r] * U[c];
                         P[r] += U[r] * uhs;
                     }
-                    sj[1 * kTile] = u;
-                    sj[2 * kTile] = uhs;
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) { sj[(3 + r) * kTile] = S[r]; sj[(9 + r) * kTile] = Us[r]; }
-                } else if (nc > 1) {  // 2 or 3 columns (planar, spherical): padded to 3 with an identity row
-                    double S[3][6], U[3][6], uh[3], u3[3];
-#pragma unroll
-                    for (int a = 0; a < 3; ++a) {
-                        const bool on = a < nc;
-                        aba_column(on ? X->col_kind[c0 + a] : CK_LIN, on ? X->col_axis[c0 + a] : 0, T, S[a]);
-                        if (!on) {
-#pragma unroll
-                            for (int r = 0; r < 6; ++r) S[a][r] = 0.0;
-                        }
-                        sym6_mulv(IA, S[a], U[a]);
-                        u3[a] = on ? Wl[(18 + a) * kTile] : 0.0;
-                        uh[a] = u3[a] - dot6(S[a], P);
-                    }
-                    const double D00 = dot6(S[0], U[0]) + kdd, D11 = dot6(S[1], U[1]) + kdd;
-                    const double D22 = (nc > 2) ? dot6(S[2], U[2]) + kdd : 1.0;
-                    const double D10 = dot6(S[1], U[0]), D20 = dot6(S[2], U[0]), D21 = dot6(S[2], U[1]);
-                    const double i0 = fast_rcp(D00);
-                    const double l10 = D10 * i0, l20 = D20 * i0;
-                    const double e1 = D11 - l10 * D10;
-                    const double i1 = fast_rcp(e1);
-                    const double l21 = (D21 - l20 * D10) * i1;
-                    const double e2 = D22 - l20 * D20 - l21 * (D21 - l20 * D10);
-                    const double i2 = fast_rcp(e2);
-                    if (!(D00 > 0.0) || !(e1 > 0.0) || !(e2 > 0.0)) status |= 2;
-                    auto solve3 = [&](double y0, double y1, double y2, double& r0, double& r1, double& r2) {
-                        const double z1 = y1 - l10 * y0;
-                        const double z2 = y2 - l20 * y0 - l21 * z1;
-                        r2 = z2 * i2;
-                        r1 = z1 * i1 - l21 * r2;
-                        r0 = y0 * i0 - l10 * r1 - l20 * r2;
-                    };
-                    double uhs[3];
-                    solve3(uh[0], uh[1], uh[2], uhs[0], uhs[1], uhs[2]);
-                    double Us[3][6];
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) solve3(U[0][r], U[1][r], U[2][r], Us[0][r], Us[1][r], Us[2][r]);
+                    sj[(1 + a) * kTile] = u;
+                    sj[(1 + nc + a) * kTile] = uhs;
 #pragma unroll
                     for (int r = 0; r < 6; ++r) {
-#pragma unroll
-                        for (int c = r; c < 6; ++c)
-                            IA[sym6(r, c)] -= Us[0][r] * U[0][c] + Us[1][r] * U[1][c] + Us[2][r] * U[2][c];
-                        P[r] += U[0][r] * uhs[0] + U[1][r] * uhs[1] + U[2][r] * uhs[2];
+                        sj[(1 + 2 * nc + 6 * a + r) * kTile] = S[r];
+                        sj[(1 + 8 * nc + 6 * a + r) * kTile] = Us[r];
                     }
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-                        if (a < nc) {
-                            sj[(1 + a) * kTile] = u3[a];
-                            sj[(1 + nc + a) * kTile] = uhs[a];
-#pragma unroll
-                            for (int r = 0; r < 6; ++r) {
-                                sj[(1 + 2 * nc + 6 * a + r) * kTile] = S[a][r];
-                                sj[(1 + 8 * nc + 6 * a + r) * kTile] = Us[a][r];
-                            }
-                        }
                 }
                 // hand I^a, p^a to the parent: registers (only child), its block (several children) or the root's slot
                 if (lv == 1) {
@@ -575,6 +527,8 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 #pragma unroll
             for (int i = 0; i < 6; ++i) P[i] += O[(21 + i) * kTile];
         }
+        double rq9[9];
+        quat_to_mat(q[3], q[4], q[5], q[6], rq9);
         double S[6][6];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -661,31 +615,25 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                 const int lines = (1 + 14 * X->ncol[jn]) * 2;
                 for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)l * 128));
             }
-            double dp[6], dl[6];
+            double dl[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { dp[r] = Dp[r * kTile]; dl[r] = dp[r]; }
+            for (int r = 0; r < 6; ++r) dl[r] = Dp[r * kTile];
             const int c0 = X->first_col[j], nc = X->ncol[j];
             const double* sj = sc + (size_t)B->aba_off[j] * kTile;
             const double kdmdt = sj[0];
-            double u[3], qdd[3], S[3][6], Us[3][6];  // every load of the joint first (one L2 round trip), arithmetic after
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const bool on = a < nc;
-                u[a] = on ? sj[(1 + a) * kTile] : 0.0;
-                qdd[a] = on ? sj[(1 + nc + a) * kTile] : 0.0;
+            for (int a = nc - 1; a >= 0; --a) {  // reverse order of the elimination
+                double S[6], Us[6];
+                const double u = sj[(1 + a) * kTile];
+                double qdd = sj[(1 + nc + a) * kTile];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
-                    S[a][r] = on ? sj[(1 + 2 * nc + 6 * a + r) * kTile] : 0.0;
-                    Us[a][r] = on ? sj[(1 + 8 * nc + 6 * a + r) * kTile] : 0.0;
+                    S[r] = sj[(1 + 2 * nc + 6 * a + r) * kTile];
+                    Us[r] = sj[(1 + 8 * nc + 6 * a + r) * kTile];
                 }
-            }
+                qdd -= dot6(Us, dl);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                if (a >= nc) break;
-                qdd[a] -= dot6(Us[a], dp);
-#pragma unroll
-                for (int r = 0; r < 6; ++r) dl[r] += S[a][r] * qdd[a];
-                const double tv = u[a] - kdmdt * qdd[a];
+                for (int r = 0; r < 6; ++r) dl[r] += S[r] * qdd;
+                const double tv = u - kdmdt * qdd;
                 if (!isfinite(tv)) status |= 1;
                 put_tau(X->col_dof[c0 + a], tv);
             }
