@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtrl_b200.so")
 SOURCES = ["trl_model.cpp", "trl_api.cpp", "trl_kernels.cu"]
-HEADERS = ["trl_internal.h", "trl_device.cuh", os.path.join("..", "..", "include", "trl_b200.h")]
+HEADERS = ["trl_internal.h", "trl_device.cuh", "trl_pd_aba.cuh", "trl_pd_block.cuh", os.path.join("..", "..", "include", "trl_b200.h")]
 
 
 def nvcc_path():

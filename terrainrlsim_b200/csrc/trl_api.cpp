@@ -1,6 +1,7 @@
 // C ABI: batch lifetime, pointer-mode staging and kernel sequencing. No torch types, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -71,6 +72,8 @@ struct trl_batch {
     double* d_frames = nullptr;
     int* d_status = nullptr;
     double* d_sample_local = nullptr;  // [G][2] local (x, z) of every ground sample
+    double sample_diag = 0.0;          // diagonal of the local bounding box of the ground samples (bounds the staged cell rectangle)
+    int sample_table_ok = 0;           // every local sample coordinate is 0 or in [2^-300, 2^300]
     void* d_env_rec = nullptr;         // [E] per-env sampling transform handed from k_obs_env to k_obs_samples
     double* d_pd_scratch = nullptr;    // [E][stride] assembled (M + dt Kd, rhs, tau terms) between the two PD kernels
     // ground
@@ -251,6 +254,12 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
             loc[2 * G + 1] = std::max(loc[2 * G + 1], loc[2 * s]);
             loc[2 * G + 2] = std::min(loc[2 * G + 2], loc[2 * s + 1]);
             loc[2 * G + 3] = std::max(loc[2 * G + 3], loc[2 * s + 1]);
+        }
+        b->sample_diag = std::hypot(loc[2 * G + 1] - loc[2 * G], loc[2 * G + 3] - loc[2 * G + 2]);
+        b->sample_table_ok = 1;
+        for (int s = 0; s < 2 * G; ++s) {
+            const double a = std::fabs(loc[s]);
+            if (!(a == 0.0 || (a >= 0x1p-300 && a <= 0x1p300))) b->sample_table_ok = 0;
         }
         if (!cuda_ok(cudaMalloc((void**)&b->d_sample_local, sizeof(double) * loc.size()), "cudaMalloc(samples)")) return nullptr;
         if (!cuda_ok(cudaMemcpy(b->d_sample_local, loc.data(), sizeof(double) * loc.size(), cudaMemcpyHostToDevice), "H2D(samples)")) return nullptr;
@@ -454,13 +463,20 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         pc.data_offset = data_offset[i];
         pc.res_x = res[2 * i];
         pc.res_z = res[2 * i + 1];
-        if (pc.res_x < 2 || pc.res_z < 1 || pc.data_offset < 0 ||
+        // var2d reads row 0 only; var3d reads rows j and j + 1, so it needs at least two
+        if (pc.res_x < 2 || pc.res_z < (kind == 2 ? 2 : 1) || pc.data_offset < 0 ||
             pc.data_offset + (long long)pc.res_x * pc.res_z > data_count) {
-            trl_set_error("trl_ground_set_heightfields: piece outside the data array");
+            trl_set_error("trl_ground_set_heightfields: piece outside the data array (or fewer than 2 x 2 / 2 x 1 vertices)");
             b->ground.kind = 0;
             return TRL_ERR_INVALID_ARG;
         }
         for (int k = 0; k < 3; ++k) { pc.origin[k] = origin[3 * i + k]; pc.scale[k] = scale[3 * i + k]; }
+        if (!std::isfinite(pc.scale[0]) || pc.scale[0] == 0.0 || !std::isfinite(pc.scale[1]) ||
+            !std::isfinite(pc.scale[2]) || pc.scale[2] == 0.0) {
+            trl_set_error("trl_ground_set_heightfields: grid spacing must be finite and non-zero");
+            b->ground.kind = 0;
+            return TRL_ERR_INVALID_ARG;
+        }
         for (int k = 0; k < 4; ++k) pc.bounds[k] = bounds[4 * i + k];
         pc.rscale[0] = 1.0 / pc.scale[0];
         pc.rscale[1] = 1.0 / pc.scale[2];
@@ -469,8 +485,37 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         pc.cmax3[0] = pc.res_x - 1.0 - 0.0001;
         pc.cmax3[1] = pc.res_z - 1.0 - 0.0001;
     }
-    if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * (size_t)data_count), "cudaMalloc(heightfields)") ||
-        !cuda_ok(cudaMemcpy(b->d_ground_data, data, sizeof(float) * (size_t)data_count, cudaMemcpyHostToDevice), "H2D(heightfields)") ||
+    // Device layout: pieces on 16-byte boundaries, rows `pitch` floats apart, and a tail pad so that a fixed-size row
+    // segment read near the end of the last piece stays inside the allocation (see DevPiece).
+    std::vector<float> packed;
+    {
+        size_t total = 0;
+        for (size_t i = 0; i < np; ++i) {
+            DevPiece& pc = pieces[i];
+            pc.pitch = (kind == 2) ? ((pc.res_x + 3) & ~3) : pc.res_x;  // var2d reads row 0 only: rows stay packed
+            total = (total + 3) & ~(size_t)3;
+            total += (size_t)pc.pitch * pc.res_z;
+        }
+        const size_t tail = 4096;
+        if (total + tail >= ((size_t)1 << 32)) {
+            trl_set_error("trl_ground_set_heightfields: more than 2^32 height values");
+            b->ground.kind = 0;
+            return TRL_ERR_UNSUPPORTED;
+        }
+        packed.assign(total + tail, 0.0f);
+        size_t at = 0;
+        for (size_t i = 0; i < np; ++i) {
+            DevPiece& pc = pieces[i];
+            at = (at + 3) & ~(size_t)3;
+            const float* src = data + pc.data_offset;
+            for (int j = 0; j < pc.res_z; ++j)
+                std::memcpy(packed.data() + at + (size_t)j * pc.pitch, src + (size_t)j * pc.res_x, sizeof(float) * pc.res_x);
+            pc.data_offset = (long long)at;
+            at += (size_t)pc.pitch * pc.res_z;
+        }
+    }
+    if (!cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * packed.size()), "cudaMalloc(heightfields)") ||
+        !cuda_ok(cudaMemcpy(b->d_ground_data, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice), "H2D(heightfields)") ||
         !cuda_ok(cudaMalloc((void**)&b->d_pieces, sizeof(DevPiece) * np), "cudaMalloc(pieces)") ||
         !cuda_ok(cudaMemcpy(b->d_pieces, pieces.data(), sizeof(DevPiece) * np, cudaMemcpyHostToDevice), "H2D(pieces)")) {
         b->ground.kind = 0;
@@ -490,6 +535,24 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
             !cuda_ok(cudaMemcpy(b->d_env_to_field, e2f.data(), sizeof(int) * (size_t)b->E, cudaMemcpyHostToDevice), "H2D(env_to_field)")) {
             b->ground.kind = 0;
             return TRL_ERR_CUDA;
+        }
+    }
+    {
+        // Shared memory per env for the cell rectangles k_obs_samples stages: the sample window (diagonal D in any
+        // heading) covers at most D / spacing + 5 cells per axis, + 3 because a staged row starts at a column multiple of 4.
+        double min_sx = HUGE_VAL, min_sz = HUGE_VAL;
+        for (size_t i = 0; i < np; ++i) {
+            min_sx = std::min(min_sx, std::fabs(pieces[i].scale[0]));
+            min_sz = std::min(min_sz, std::fabs(pieces[i].scale[2]));
+        }
+        const double cx = std::floor(b->sample_diag / min_sx) + 8.0;
+        const double cz = (kind == 2) ? std::floor(b->sample_diag / min_sz) + 5.0 : 1.0;
+        b->ground.patch_w = b->ground.patch_h = b->ground.patch_nbuf = 0;
+        b->ground.table_ok = b->sample_table_ok;
+        if (b->cfg.num_samples > 0 && cx <= 1024.0 && cz <= 64.0) {
+            const int w = ((int)cx + 3) & ~3, h = (int)cz;
+            const int nbuf = std::min(pieces_per_field, (int)(8192 / ((size_t)w * h * sizeof(float))));  // <= 8 KB per env
+            if (nbuf >= 1) { b->ground.patch_w = w; b->ground.patch_h = h; b->ground.patch_nbuf = nbuf; }
         }
     }
     b->ground.num_fields = num_fields;

@@ -280,7 +280,7 @@ TRL_DEV double sample_finish_2d(const SamplePrep& sp, float f0, float f1) {
 }
 
 TRL_DEV void sample_prep_3d(const DevPiece& pc, int s, double px, double pz, SamplePrep& sp) {
-    const int rx = pc.res_x;
+    const int rx = pc.pitch;  // device row pitch (>= res_x)
     double c0, c1;
     grid_coord2(px, pz, pc, c0, c1);
     c0 = clampd(c0, 0.0, pc.cmax3[0]);  // rx - 1.0 - tol, evaluated once per piece on the host

@@ -118,10 +118,14 @@ struct trl_model {
     DevModel dev;
 };
 
-// per-piece terrain descriptor in HBM
+// per-piece terrain descriptor in HBM (160 bytes). The device copy of a heightfield is re-pitched at registration: every
+// piece starts on a 16-byte boundary and its rows are `pitch` floats apart (res_x rounded up to a multiple of 4), so a
+// row segment that starts at a column multiple of 4 can be moved with one bulk asynchronous copy (k_obs_samples).
 struct DevPiece {
-    long long data_offset;
+    long long data_offset;  // first float of the piece in the device array (multiple of 4)
     int res_x, res_z;
+    int pitch;              // floats between consecutive rows on the device
+    int pad_[3];
     double origin[3];
     double scale[3];
     double bounds[4];
@@ -129,12 +133,17 @@ struct DevPiece {
     double half[2];    // (res_x - 1) * 0.5, (res_z - 1) * 0.5 (exact products)
     double cmax3[2];   // 3-D clamp bounds res_x - 1.0 - tol, res_z - 1.0 - tol (GroundVar3D.cpp:602-621), host-evaluated
 };
+static_assert(sizeof(DevPiece) == 160, "DevPiece is copied with 16-byte loads");
 
 struct DevGround {
     int kind;  // 0 none, 1 var2d, 2 var3d, 3 plane
     int num_fields;
     int pieces_per_field;
-    int pad;
+    // k_obs_samples stages the cell rectangle an env's sample window covers in shared memory: up to patch_nbuf rectangles
+    // (one per terrain piece the window touches) of patch_h rows x patch_w floats each; patch_nbuf = 0: never stage
+    int patch_w, patch_h, patch_nbuf;
+    int table_ok;  // every entry of the batch's local sample table is 0 or in [2^-300, 2^300] (see k_obs_env)
+    int pad_;
     const float* data;
     const DevPiece* pieces;   // [F][P]
     const int* env_to_field;  // [E] or nullptr

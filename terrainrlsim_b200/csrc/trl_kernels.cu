@@ -2379,15 +2379,22 @@ TRL_DEV void roty_to_quat(double c, double s, double m11, double* q) {
 }
 
 // Per-env record handed from k_obs_env to k_obs_samples: the ground-sample transform (InvRigid(origin_trans) with
-// y += ground height under the root) and the stance flip.
+// y += ground height under the root), the stance flip and how the env's sample window maps onto its terrain pieces.
 struct ObsEnvRec {
     double i00, i02, i20, i22, it0, it1, it2;
     int flip;
-    int pad;
-    int piece;  // >= 0: every ground sample of this env falls into this terrain piece (and into no earlier one)
-    int pad2;  // bitmask of the terrain pieces the env's sample bounding box touches (candidates of the per-sample search)
-    int pad3, pad4;  // sizeof % 16 == 0 (staged with 16-byte copies)
+    int has_ground;
+    long long src_off[4];  // per piece: first float (device array) of the cell rectangle the window covers, a multiple of 4
+    int pitch[4];          //            floats between its rows
+    int ph[4];             //            rows
+    int shift[4];          //            cell (i, j) of the piece sits at patch[shift + j * patch_w + i]
+    int cand;      // bit mask of the pieces a sample can fall into (all of them when the window's box is unknown)
+    int up;        // >= 0: every sample lies in this piece and in no earlier one (the reference's scan stops there)
+    int interior;  // bit 0 (`up` only): the window keeps a cell of distance from the grid's edge, the clamps cannot fire;
+                   // bit 1: operands in the range where the division-by-spacing sequence needs no guard
+    int staged;    // bit 1 of `interior` holds and the rectangles (of `up`, or of all candidates) fit the patch buffers
 };
+static_assert(sizeof(ObsEnvRec) == 160, "read with 16-byte loads");
 
 // k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env (the per-env prologue is redundant across the lanes, so few lanes win).
 // Everything that is per-env (heading, origin transform, ground height under the root) is computed once here.
@@ -2452,10 +2459,13 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     if (lane == 0 && env_ok) {
         ObsEnvRec r;
         r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
-        r.flip = flip; r.pad = has_ground ? 1 : 0;
-        r.piece = -1;
-        r.pad2 = 0xf;  // candidate pieces of the per-sample search (all, unless the bounding-box test below narrows it)
-        r.pad3 = r.pad4 = 0;
+        r.flip = flip; r.has_ground = has_ground ? 1 : 0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { r.src_off[s] = 0; r.pitch[s] = r.ph[s] = r.shift[s] = 0; }
+        r.cand = 0xf;  // candidate pieces of the per-sample search (all, unless the bounding-box test below narrows it)
+        r.up = -1;
+        r.interior = 0;
+        r.staged = 0;
         if ((gkind == 1 || gkind == 2) && cfg.num_samples > 0 && sample_local) {
             // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
             // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
@@ -2477,24 +2487,76 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
                     const double px = i00 * lx[a] + i02 * lz[b] + it0;
                     const double pz = i20 * lx[a] + i22 * lz[b] + it2;
                     finite = finite && isfinite(px) && isfinite(pz);
-                    x0 = fmin(x0, px); x1 = fmax(x1, px);
-                    z0 = fmin(z0, pz); z1 = fmax(z1, pz);
+                    x0 = (px < x0) ? px : x0; x1 = (px > x1) ? px : x1;
+                    z0 = (pz < z0) ? pz : z0; z1 = (pz > z1) ? pz : z1;
                 }
             const double ex = 1e-12 * (fabs(x0) + fabs(x1) + 1.0), ez = 1e-12 * (fabs(z0) + fabs(z1) + 1.0);
             x0 -= ex; x1 += ex; z0 -= ez; z1 += ez;
             if (finite) {
+                // The staged sample code divides by the grid spacing with the unguarded correction sequence of
+                // div_by_const, exact for operands x = pos - origin with x == 0 or 2^-900 < |x| < 2^900. Every quantity x
+                // is built from being zero or in [2^-300, 2^300] guarantees that (the sample table is checked on the host).
+                auto okmag = [](double v) { const double a = fabs(v); return a == 0.0 || (a >= 0x1p-300 && a <= 0x1p300); };
+                bool safe = g.table_ok != 0 && okmag(i00) && okmag(i02) && okmag(i20) && okmag(i22) && okmag(it0) && okmag(it2) &&
+                            fabs(x0) < 0x1p300 && fabs(x1) < 0x1p300 && fabs(z0) < 0x1p300 && fabs(z1) < 0x1p300;
                 const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
                 bool open_scan = true;  // no earlier piece touches the box so far
                 int cand = 0;           // pieces the box touches: the only ones a sample of this env can fall into
-                for (int s = 0; s < gP; ++s) {
-                    const double b0 = pcs[s].bounds[0], b1 = pcs[s].bounds[1], b2 = pcs[s].bounds[2], b3 = pcs[s].bounds[3];
+                int inner = 0;          // pieces whose rectangle stays clear of the grid's edge
+                int fits = 0;           // pieces whose rectangle fits a patch buffer
+                int pi0[4], pj0[4];
+                // Cell range of the box in a piece's grid. The estimate (plain arithmetic) is within a tiny fraction of a
+                // cell of the exact coordinate sequence used per sample; one cell of slack on either side absorbs it, one
+                // more on the high side holds the i + 1 / j + 1 vertices.
+                auto range = [](double lo_w, double hi_w, double o, double rs, double half, int res, int& first, int& count, bool& clear) {
+                    const double ca = (lo_w - o) * rs + half, cb = (hi_w - o) * rs + half;
+                    double lo = (ca < cb) ? ca : cb, hi = (ca < cb) ? cb : ca;
+                    lo = clampd(lo, -4.0, 1.0e9);
+                    hi = clampd(hi, -4.0, 1.0e9);
+                    const int ilo = (int)floor(lo) - 1, ihi = (int)floor(hi) + 2;
+                    clear = ilo >= 0 && ihi <= res - 1;
+                    first = max(ilo, 0);
+                    count = max(min(ihi, res - 1) - first + 1, 0);
+                };
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    pi0[s] = pj0[s] = 0;
+                    if (s >= gP) continue;
+                    const DevPiece& pc = pcs[s];
+                    const double b0 = pc.bounds[0], b1 = pc.bounds[1], b2 = pc.bounds[2], b3 = pc.bounds[3];
                     const bool inside = (gkind == 1) ? (x0 >= b0 && x1 <= b1) : (x0 >= b0 && x1 <= b1 && z0 >= b2 && z1 <= b3);
                     const bool apart = (gkind == 1) ? (x1 < b0 || x0 > b1) : (x1 < b0 || x0 > b1 || z1 < b2 || z0 > b3);
-                    if (!apart) cand |= 1 << s;
-                    if (open_scan && inside) r.piece = s;
-                    if (!apart) open_scan = false;  // a later piece can only be "first containing" for some samples
+                    if (open_scan && inside) r.up = s;
+                    if (!apart) {
+                        cand |= 1 << s;
+                        open_scan = false;  // a later piece can only be "first containing" for some samples
+                        safe = safe && okmag(pc.origin[0]) && okmag(pc.origin[2]);
+                    }
+                    if (!apart && g.patch_nbuf > 0) {  // cell rectangle, only when k_obs_samples stages
+                        bool cx, cz = true;
+                        int first_x, count_x, count_z = 1;
+                        range(x0, x1, pc.origin[0], pc.rscale[0], pc.half[0], pc.res_x, first_x, count_x, cx);
+                        if (gkind == 2) range(z0, z1, pc.origin[2], pc.rscale[1], pc.half[1], pc.res_z, pj0[s], count_z, cz);
+                        pi0[s] = first_x & ~3;  // staged rows start at a column multiple of 4 (16-byte aligned bulk copies)
+                        const int pw = first_x + count_x - pi0[s];
+                        r.ph[s] = count_z;
+                        r.pitch[s] = pc.pitch;
+                        r.src_off[s] = pc.data_offset + (long long)pj0[s] * pc.pitch + pi0[s];
+                        if (cx && cz) inner |= 1 << s;
+                        if (count_x >= 1 && pw <= g.patch_w && count_z >= 1 && count_z <= g.patch_h) fits |= 1 << s;
+                    }
                 }
-                r.pad2 = cand;
+                r.cand = cand;
+                const int smask = (r.up >= 0) ? (1 << r.up) : cand;
+                int nb = 0;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    if ((smask >> s) & 1) {
+                        r.shift[s] = nb * g.patch_w * g.patch_h - pj0[s] * g.patch_w - pi0[s];
+                        ++nb;
+                    }
+                r.staged = (safe && smask != 0 && (fits & smask) == smask && nb <= g.patch_nbuf) ? 1 : 0;
+                r.interior = ((r.up >= 0 && ((inner >> r.up) & 1)) ? 1 : 0) | (safe ? 2 : 0);
             }
         }
         rec[e] = r;
@@ -2600,107 +2662,365 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     }
 }
 
-// k_obs_samples: ParseGround's sample loop -- block = one env, kObsSPT samples per thread (independent load chains the
-// compiler interleaves). The env's record and terrain piece descriptors are staged once in shared memory.
-constexpr int kObsSPT = 4;
+// k_obs_samples: ParseGround's sample loop -- ONE WARP PER ENV, lane = sample (s = lane, lane + 32, ...).
+//
+// The cells an env's samples can touch are known before any sample is evaluated: k_obs_env maps the world-space box of
+// the sample positions onto the (<= 4) terrain pieces of the env's terrain -- which pieces the box touches, and the cell
+// rectangle it covers in each of them -- and this kernel STAGES those rectangles in shared memory with bulk asynchronous
+// copies (cp.async.bulk + mbarrier, the TMA path): lane r moves row r of a rectangle, so ONE warp instruction puts up to
+// 32 rows in flight, lane 0 moves the env's piece descriptors, and the warp waits once on the mbarrier. (The device copy
+// of a heightfield is re-pitched at registration so that row segments starting at a column multiple of 4 are 16-byte
+// aligned.) A 16 x 16 window of biped3D covers <= 26 x 26 cells; its buffer is 27 rows x 32 floats = 3.4 KB. Per sample
+// there is then no dependent global gather: the 3 (2-D: 2) vertices come from shared memory.
+// ncu A/B against the gather version: profiles/README.md.
+//
+//   * box inside one piece, no earlier piece touching it ("uniform", ~60 % of the envs when pieces meet at the origin):
+//     the piece's constants live in registers. If the box also keeps a cell of distance from the grid's edge
+//     ("interior") the reference's clamps cannot fire and are skipped.
+//   * box touching several pieces: every touched piece's rectangle is staged (one buffer each); per sample the first
+//     containing piece (the reference's scan order) selects the constants from the descriptors in shared memory.
+//   * no finite box, more touched pieces than buffers, rectangles larger than a buffer, operands outside the guard-free
+//     range: per-sample search and global gathers (the general code).
+//
+// Grid coordinates keep the reference's rounding sequence exactly (sub, IEEE-equal division by the spacing, add);
+// (int)c and c - (double)(int)c are taken with one round-down add of 2^52 (exact for 0 <= c < 2^31) instead of two
+// conversion instructions.
+constexpr int kObsWarps = 2;       // envs per block (small blocks: a finished env's shared memory is reusable at once)
+constexpr int kObsUnroll = 4;      // samples in flight per lane
+constexpr double kTwo52 = 4503599627370496.0;
+constexpr int kObsHead = 16 + 4 * (int)sizeof(DevPiece);  // per warp: mbarrier (16 bytes), 4 piece descriptors
+
+__host__ __device__ inline size_t obs_warp_bytes(const DevGround& g) {
+    return (size_t)kObsHead + (size_t)g.patch_nbuf * g.patch_w * g.patch_h * sizeof(float);
+}
+
+// floor and fraction of a grid coordinate 0 <= c < 2^31
+TRL_DEV void floor_frac(double c, int& i, double& frac) {
+    const double t = __dadd_rd(c, kTwo52);  // 2^52 + floor(c), exactly
+    i = __double2loint(t);
+    frac = __dsub_rn(c, __dsub_rn(t, kTwo52));
+}
+
+// cMathUtil::Clamp(c, 0, hi) for a finite c (the staged paths): c < 0 is the sign bit (-0 -> +0 like the comparison)
+TRL_DEV double clamp0(double c, double hi) {
+    c = (c < hi) ? c : hi;
+    return (__double2hiint(c) < 0) ? 0.0 : c;
+}
+
+// x / d by Markstein's correction sequence from r = RN(1 / d) (see div_by_const), without its range guard: k_obs_env
+// admits an env to the staged paths only if its operands are in the range where the sequence is exact
+TRL_DEV double div_by_const_unguarded(double x, double d, double r) {
+    const double q0 = __dmul_rn(x, r);
+    const double e0 = __fma_rn(-q0, d, x);
+    const double q1 = __fma_rn(e0, r, q0);
+    const double e1 = __fma_rn(-q1, d, x);
+    return __fma_rn(e1, r, q1);
+}
+
+// one height sample out of the staged patch: cell (i, j) of the piece sits at patch[shift + j * pw + i]; `c` is the piece
+// descriptor in registers (uniform piece) or in shared memory (per-sample piece)
+template <int KIND, bool INTERIOR>
+TRL_DEV double patch_sample(const DevPiece& c, const float* __restrict__ patch, int shift, int pw, double px, double pz,
+                            int& ci, int& cj) {
+    const double sy = c.scale[1];
+    if (KIND == 1) {
+        double c0 = __dadd_rn(div_by_const_unguarded(__dsub_rn(px, c.origin[0]), c.scale[0], c.rscale[0]), c.half[0]);
+        if (!INTERIOR) c0 = clamp0(c0, c.res_x - 1.0);
+        int i;
+        double lerp;
+        floor_frac(c0, i, lerp);
+        const int j = INTERIOR ? i + 1 : min(c.res_x - 1, i + 1);
+        const double a = __dmul_rn((double)patch[shift + i], sy), b = __dmul_rn((double)patch[shift + j], sy);
+        ci = i; cj = j;
+        return __dadd_rn(__dmul_rn(__dsub_rn(1.0, lerp), a), __dmul_rn(lerp, b));
+    } else {
+        const double qx = div_by_const_unguarded(__dsub_rn(px, c.origin[0]), c.scale[0], c.rscale[0]);
+        const double qz = div_by_const_unguarded(__dsub_rn(pz, c.origin[2]), c.scale[2], c.rscale[1]);
+        double c0 = __dadd_rn(qx, c.half[0]), c1 = __dadd_rn(qz, c.half[1]);
+        if (!INTERIOR) {
+            c0 = clamp0(c0, c.cmax3[0]);
+            c1 = clamp0(c1, c.cmax3[1]);
+        }
+        int i, j;
+        double lx, lz;
+        floor_frac(c0, i, lx);
+        floor_frac(c1, j, lz);
+        // cMathUtil::CalcBarycentric on the unit triangles, see sample_prep_3d: with (a, b) = (lx, lz) in the lower and
+        // (1 - lx, 1 - lz) in the upper triangle both cases are d20 = a, d21 = a + b (-RN(lx - 1) == RN(1 - lx)).
+        const bool lower = (lz <= lx);
+        const double a = lower ? lx : __dsub_rn(1.0, lx);
+        const double b = lower ? lz : __dsub_rn(1.0, lz);
+        const double d21 = __dadd_rn(a, b);
+        const double bv = __fma_rn(2.0, a, -d21);  // RN(RN(2 a) - d21): 2 a is exact
+        const double bw = __dsub_rn(d21, a);
+        const double w0 = __dsub_rn(__dsub_rn(1.0, bv), bw);
+        const int idx = shift + j * pw + i;
+        const int diag = idx + pw + 1;
+        const double v0 = __dmul_rn((double)patch[lower ? idx : diag], sy);
+        const double v1 = __dmul_rn((double)patch[lower ? idx + 1 : idx + pw], sy);
+        const double v2 = __dmul_rn((double)patch[lower ? diag : idx], sy);
+        ci = i; cj = j;
+        return __dadd_rn(__dadd_rn(__dmul_rn(w0, v0), __dmul_rn(bv, v1)), __dmul_rn(bw, v2));
+    }
+}
+
 template <int KIND, bool WANT_CELL>  // ground kind (1 = var2d, 2 = var3d, 0/3 = none/plane) as a compile-time constant
-__global__ void __launch_bounds__(256, 5)  // 48 registers: measured better than the natural 60 (occupancy) and than 40 (spills)
+__global__ void __launch_bounds__(kObsWarps * 32, 14)
 k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
               const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
     KTrace trace_(TR_OBS_SAMPLES);
-    static_assert(sizeof(DevPiece) % 16 == 0 && sizeof(ObsEnvRec) % 16 == 0, "staged with 16-byte copies");
+    extern __shared__ __align__(128) unsigned char s_obs_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kObsWarps + warp;
+    if (e >= E) return;  // warp-uniform; the kernel has no block barrier
+    const int G = cfg.num_samples;
+    ObsEnvRec r;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + e);
+        uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int k = 0; k < (int)(sizeof(ObsEnvRec) / 16); ++k) dst[k] = __ldg(src + k);
+    }
+    const bool flip_z = r.flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
+    const double i02 = flip_z ? -r.i02 : r.i02, i22 = flip_z ? -r.i22 : r.i22;  // local z -> -z folded into the map
+    double* out = out_state + (size_t)e * F;
+    int* oc = (WANT_CELL && out_cell) ? out_cell + (size_t)e * G * 3 : nullptr;
+    const double2* sl2 = reinterpret_cast<const double2*>(sample_local);
+
+    if (KIND != 1 && KIND != 2) {  // no heightfield: cGround::SampleHeight = 0 (sim/Ground.cpp:176-186)
+        const double hs = r.has_ground ? (0.0 - r.it1) : 0.0;
+        for (int s = lane; s < G; s += 32) {
+            out[s] = hs;
+            if (oc) { oc[3 * s] = -1; oc[3 * s + 1] = 0; oc[3 * s + 2] = 0; }
+        }
+        return;
+    }
+
+    const int gP = g.pieces_per_field;
+    const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
+    const unsigned cand = (unsigned)r.cand;
+    const int up = r.up;
+    const int pw = g.patch_w;
+
+    if (r.staged) {
+        unsigned char* wbase = s_obs_raw + (size_t)warp * obs_warp_bytes(g);
+        const unsigned bar_a = smem_u32(wbase);
+        DevPiece* spc = reinterpret_cast<DevPiece*>(wbase + 16);
+        float* patch = reinterpret_cast<float*>(wbase + kObsHead);
+        // ---- stage: the env's piece descriptors (lane 0) and one row of a rectangle per lane, all on one mbarrier ----
+        const unsigned smask = (up >= 0) ? (1u << up) : cand;
+        const unsigned row_bytes = (unsigned)pw * 4u, desc_bytes = (unsigned)gP * (unsigned)sizeof(DevPiece);
+        if (lane == 0) {
+            unsigned total = desc_bytes;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if ((smask >> t) & 1u) total += (unsigned)r.ph[t] * row_bytes;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(spc)), "l"(pcs), "r"(desc_bytes), "r"(bar_a) : "memory");
+        }
+        __syncwarp();
+        {
+            int buf = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                if (!((smask >> t) & 1u)) continue;
+                const float* src = g.data + r.src_off[t];
+                float* dst = patch + (size_t)buf * pw * g.patch_h;
+                for (int row = lane; row < r.ph[t]; row += 32)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(dst + row * pw)), "l"(src + (long long)row * r.pitch[t]), "r"(row_bytes), "r"(bar_a) : "memory");
+                ++buf;
+            }
+        }
+        double2 nxt[kObsUnroll];  // the first group's entries of the sample table: loaded while the copies are in flight
+#pragma unroll
+        for (int k = 0; k < kObsUnroll; ++k) {
+            const int s = lane + 32 * k;
+            nxt[k] = __ldg(sl2 + (s < G ? s : 0));
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "TRL_OWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@p bra TRL_ODONE_%=;\n"
+            "bra TRL_OWAIT_%=;\n"
+            "TRL_ODONE_%=:\n"
+            "}\n" ::"r"(bar_a)
+            : "memory");
+
+        if (up >= 0) {
+            // ---- uniform piece: constants in registers ----
+            const DevPiece c = spc[up];
+            const int sh = (up == 0) ? r.shift[0] : (up == 1) ? r.shift[1] : (up == 2) ? r.shift[2] : r.shift[3];
+            auto run = [&](auto inner_tag) {
+                constexpr bool INNER = decltype(inner_tag)::value;
+                for (int s0 = lane; s0 < G; s0 += 32 * kObsUnroll) {
+                    double2 cur[kObsUnroll];
+#pragma unroll
+                    for (int k = 0; k < kObsUnroll; ++k) cur[k] = nxt[k];
+                    if (s0 + 32 * kObsUnroll < G) {  // the next group's table entries load while this group computes
+#pragma unroll
+                        for (int k = 0; k < kObsUnroll; ++k) {
+                            const int s = s0 + 32 * (kObsUnroll + k);
+                            nxt[k] = __ldg(sl2 + (s < G ? s : 0));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kObsUnroll; ++k) {
+                        const int s = s0 + 32 * k;
+                        if (s >= G) break;
+                        const double px = fma(r.i00, cur[k].x, fma(i02, cur[k].y, r.it0));
+                        const double pz = fma(r.i20, cur[k].x, fma(i22, cur[k].y, r.it2));
+                        int ci, cj;
+                        out[s] = patch_sample<KIND, INNER>(c, patch, sh, pw, px, pz, ci, cj) - r.it1;
+                        if (WANT_CELL && oc) { oc[3 * s] = up; oc[3 * s + 1] = ci; oc[3 * s + 2] = cj; }
+                    }
+                }
+            };
+            if (r.interior & 1) run(std::true_type{});
+            else run(std::false_type{});
+            return;
+        }
+        // ---- several pieces staged: first containing candidate per sample selects the descriptor (shared memory) ----
+        for (int s0 = lane; s0 < G; s0 += 32 * kObsUnroll) {
+            double2 cur[kObsUnroll];
+#pragma unroll
+            for (int k = 0; k < kObsUnroll; ++k) cur[k] = nxt[k];
+            if (s0 + 32 * kObsUnroll < G) {
+#pragma unroll
+                for (int k = 0; k < kObsUnroll; ++k) {
+                    const int s = s0 + 32 * (kObsUnroll + k);
+                    nxt[k] = __ldg(sl2 + (s < G ? s : 0));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kObsUnroll; ++k) {
+                const int s = s0 + 32 * k;
+                if (s >= G) break;
+                const double px = fma(r.i00, cur[k].x, fma(i02, cur[k].y, r.it0));
+                const double pz = fma(r.i20, cur[k].x, fma(i22, cur[k].y, r.it2));
+                int pi = -1;
+#pragma unroll
+                for (int t = 3; t >= 0; --t)
+                    if (((cand >> t) & 1u) && piece_contains(KIND, spc[t], px, pz)) pi = t;
+                int ci = 0, cj = 0;
+                double hs = -CUDART_INF;
+                if (pi >= 0) {
+                    const int sh = (pi == 0) ? r.shift[0] : (pi == 1) ? r.shift[1] : (pi == 2) ? r.shift[2] : r.shift[3];
+                    hs = patch_sample<KIND, false>(spc[pi], patch, sh, pw, px, pz, ci, cj);
+                }
+                out[s] = hs - r.it1;
+                if (WANT_CELL && oc) { oc[3 * s] = pi; oc[3 * s + 1] = ci; oc[3 * s + 2] = cj; }
+            }
+        }
+        return;
+    }
+    // ---- general code: per-sample search over the candidate pieces, vertices gathered from global memory ----
+    for (int s = lane; s < G; s += 32) {
+        const double2 l2 = __ldg(sl2 + s);
+        const double px = fma(r.i00, l2.x, fma(i02, l2.y, r.it0));
+        const double pz = fma(r.i20, l2.x, fma(i22, l2.y, r.it2));
+        int pi = -1;
+#pragma unroll
+        for (int t = 3; t >= 0; --t)
+            if (t < gP && ((cand >> t) & 1u) && piece_contains(KIND, pcs[t], px, pz)) pi = t;
+        int vs, cell[3];
+        out[s] = ground_sample_piece(KIND, pcs, pi, g.data, px, pz, &vs, cell) - r.it1;
+        if (WANT_CELL && oc) { oc[3 * s] = cell[0]; oc[3 * s + 1] = cell[1]; oc[3 * s + 2] = cell[2]; }
+    }
+}
+
+// k_obs_gather: the same sample loop with the vertices gathered straight from global memory -- block = one env,
+// kObsSPT samples per thread (independent load chains the compiler interleaves), the env's record and piece descriptors
+// staged once in shared memory. Many small independent blocks keep ~35 warps per SM resident; on the 3-D heightfields
+// (3 scattered vertices per sample, a rectangle of ~26 rows to stage per env) this beats the staged kernel, which wins on
+// the 2-D ones (one contiguous row per env): see the ncu A/B in profiles/README.md. Same arithmetic (patch_sample reads
+// "patch" = the piece's device array with its row pitch).
+constexpr int kObsSPT = 4;
+template <int KIND, bool WANT_CELL>
+__global__ void __launch_bounds__(256, 5)
+k_obs_gather(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
+             const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
+    KTrace trace_(TR_OBS_SAMPLES);
     __shared__ __align__(16) DevPiece s_pieces[4];
     __shared__ __align__(16) ObsEnvRec s_rec;
     const int e = blockIdx.x;
     const int G = cfg.num_samples;
-    constexpr int gkind = KIND;
     const int gP = g.pieces_per_field;
+    const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
     {
         constexpr int kRecW = (int)(sizeof(ObsEnvRec) / 16);
-        const int pw = (gkind == 1 || gkind == 2) ? gP * (int)(sizeof(DevPiece) / 16) : 0;
+        const int pw = gP * (int)(sizeof(DevPiece) / 16);
         for (int t = threadIdx.x; t < pw + kRecW; t += blockDim.x) {
-            if (t < pw) {
-                const uint4* src = reinterpret_cast<const uint4*>(g.pieces + (long long)ground_field_of_env(g, e) * gP);
-                reinterpret_cast<uint4*>(s_pieces)[t] = __ldg(src + t);
-            } else {
-                reinterpret_cast<uint4*>(&s_rec)[t - pw] = __ldg(reinterpret_cast<const uint4*>(rec + e) + (t - pw));
-            }
+            if (t < pw) reinterpret_cast<uint4*>(s_pieces)[t] = __ldg(reinterpret_cast<const uint4*>(pcs) + t);
+            else reinterpret_cast<uint4*>(&s_rec)[t - pw] = __ldg(reinterpret_cast<const uint4*>(rec + e) + (t - pw));
         }
     }
     __syncthreads();
-    const bool flip_z = s_rec.flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
-    const bool has_ground = gkind != 0;
-    const double oz = 0.0;
+    const ObsEnvRec r = s_rec;  // registers
+    const bool flip_z = r.flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
+    const double i02 = flip_z ? -r.i02 : r.i02, i22 = flip_z ? -r.i22 : r.i22;
     double* out = out_state + (size_t)e * F;
-    const ObsEnvRec r = s_rec;   // registers
-    const int up = r.piece;      // block-uniform: >= 0 when every sample of this env lies in that piece
-    if ((gkind == 1 || gkind == 2) && up >= 0) {
-        // fast path: one piece for the whole env -- its descriptor is read once into registers, no per-sample search
-        const DevPiece pc = s_pieces[up];
-        for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
+    int* oc = (WANT_CELL && out_cell) ? out_cell + (size_t)e * G * 3 : nullptr;
+    const double2* sl2 = reinterpret_cast<const double2*>(sample_local);
+    const int up = r.up;
+    const unsigned cand = (unsigned)r.cand;
+    const bool safe = (r.interior & 2) != 0;
+    if (safe && up >= 0) {
+        // every sample in one piece, operands in the guard-free range: the piece's descriptor in registers
+        const DevPiece c = s_pieces[up];
+        const float* base = g.data + c.data_offset;
+        auto run = [&](auto inner_tag) {
+            constexpr bool INNER = decltype(inner_tag)::value;
+            for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
 #pragma unroll
-            for (int k = 0; k < kObsSPT; ++k) {
-                const int s = s0 + k * blockDim.x;
-                if (s >= G) break;
-                const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
-                const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
-                const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
-                const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
-                int vs, cell[3];
-                const double hs = ((gkind == 1) ? sample_segment_2d(pc, g.data, up, px, pz, &vs, cell)
-                                                : sample_slab_3d(pc, g.data, up, px, pz, &vs, cell)) - r.it1;
-                out[s] = hs;
-                if (WANT_CELL && out_cell) {
-                    int* oc = out_cell + ((size_t)e * G + s) * 3;
-                    oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+                for (int k = 0; k < kObsSPT; ++k) {
+                    const int s = s0 + k * blockDim.x;
+                    if (s >= G) break;
+                    const double2 l2 = __ldg(sl2 + s);
+                    const double px = fma(r.i00, l2.x, fma(i02, l2.y, r.it0));
+                    const double pz = fma(r.i20, l2.x, fma(i22, l2.y, r.it2));
+                    int ci, cj;
+                    out[s] = patch_sample<KIND, INNER>(c, base, 0, c.pitch, px, pz, ci, cj) - r.it1;
+                    if (WANT_CELL && oc) { oc[3 * s] = up; oc[3 * s + 1] = ci; oc[3 * s + 2] = cj; }
                 }
             }
-        }
+        };
+        if (r.interior & 1) run(std::true_type{});
+        else run(std::false_type{});
         return;
     }
-    if (gkind == 1 || gkind == 2) {
-        // general path: the env's samples straddle pieces. The search runs over the pieces its bounding box touches only
-        // (block-uniform mask from k_obs_env), lowest index first like the reference's scan; 4 samples per thread.
-        const int cand = r.pad2;
-        for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
+    // general code: per-sample search over the candidate pieces (lowest index first like the reference's scan)
+    for (int s0 = threadIdx.x; s0 < G; s0 += blockDim.x * kObsSPT) {
 #pragma unroll
-            for (int k = 0; k < kObsSPT; ++k) {
-                const int s = s0 + k * blockDim.x;
-                if (s >= G) break;
-                const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
-                const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
-                const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
-                const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
-                int pi = -1;
+        for (int k = 0; k < kObsSPT; ++k) {
+            const int s = s0 + k * blockDim.x;
+            if (s >= G) break;
+            const double2 l2 = __ldg(sl2 + s);
+            const double px = fma(r.i00, l2.x, fma(i02, l2.y, r.it0));
+            const double pz = fma(r.i20, l2.x, fma(i22, l2.y, r.it2));
+            int pi = -1;
 #pragma unroll
-                for (int t = 3; t >= 0; --t)
-                    if (t < gP && ((cand >> t) & 1) && piece_contains(gkind, s_pieces[t], px, pz)) pi = t;
-                int vs, cell[3];
-                const double hs = ground_sample_piece(gkind, s_pieces, pi, g.data, px, pz, &vs, cell) - r.it1;
-                out[s] = hs;
-                if (WANT_CELL && out_cell) {
-                    int* oc = out_cell + ((size_t)e * G + s) * 3;
-                    oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+            for (int t = 3; t >= 0; --t)
+                if (t < gP && ((cand >> t) & 1u) && piece_contains(KIND, s_pieces[t], px, pz)) pi = t;
+            int ci = 0, cj = 0;
+            double hs = -CUDART_INF;
+            if (pi >= 0) {
+                if (safe) {
+                    const DevPiece& c = s_pieces[pi];
+                    hs = patch_sample<KIND, false>(c, g.data + c.data_offset, 0, c.pitch, px, pz, ci, cj);
+                } else {
+                    int vs, cell[3];
+                    hs = ground_sample_piece(KIND, s_pieces, pi, g.data, px, pz, &vs, cell);
+                    ci = cell[1]; cj = cell[2];
                 }
             }
-        }
-        return;
-    }
-    for (int s = threadIdx.x; s < G; s += blockDim.x) {  // no heightfield (flat ground / none)
-        double hs = 0.0;
-        int cell[3] = {-1, 0, 0};
-        if (has_ground) {
-            const double2 l2 = __ldg(reinterpret_cast<const double2*>(sample_local) + s);
-            const double lx = l2.x, lz = flip_z ? -l2.y : l2.y;
-            const double px = r.i00 * lx + oz * 0.0 + r.i02 * lz + r.it0;
-            const double pz = r.i20 * lx + oz * 0.0 + r.i22 * lz + r.it2;
-            int vs;
-            hs = ground_sample_pieces(gkind, gP, s_pieces, g.data, px, pz, &vs, cell) - r.it1;
-        }
-        out[s] = hs;
-        if (WANT_CELL && out_cell) {
-            int* oc = out_cell + ((size_t)e * G + s) * 3;
-            oc[0] = cell[0]; oc[1] = cell[1]; oc[2] = cell[2];
+            out[s] = hs - r.it1;
+            if (WANT_CELL && oc) { oc[3 * s] = pi; oc[3 * s + 1] = ci; oc[3 * s + 2] = cj; }
         }
     }
 }
@@ -2804,20 +3124,23 @@ double trl_fp64_probe_tflops(void* stream) {
 
 
 static int ensure_smem(const void* func, size_t bytes) {
-    // set once per (kernel, size): cudaFuncSetAttribute is kept out of graph captures
-    constexpr int kSeen = 128;
+    // set once per (device, kernel, size): cudaFuncSetAttribute is kept out of graph captures. The attribute is per
+    // device, so the cache is keyed on the current device as well (batches on several GPUs in one process).
+    constexpr int kSeen = 256;
     static const void* seen_func[kSeen];
     static size_t seen_bytes[kSeen];
+    static int seen_dev[kSeen];
     static int nseen = 0;
     static std::mutex mu;  // batches on different host threads share this cache
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return (int)cudaGetLastError();
     std::lock_guard<std::mutex> lock(mu);
-    if (bytes > 48 * 1024) {
-        for (int i = 0; i < nseen; ++i)
-            if (seen_func[i] == func && seen_bytes[i] >= bytes) return 0;
-        if (nseen < kSeen) { seen_func[nseen] = func; seen_bytes[nseen] = bytes; ++nseen; }
-        cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (err != cudaSuccess) return (int)err;
-    }
+    for (int i = 0; i < nseen; ++i)
+        if (seen_func[i] == func && seen_dev[i] == dev && seen_bytes[i] >= bytes) return 0;
+    cudaError_t err = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err != cudaSuccess) return (int)err;
+    if (nseen < kSeen) { seen_func[nseen] = func; seen_bytes[nseen] = bytes; seen_dev[nseen] = dev; ++nseen; }
     return 0;
 }
 
@@ -3127,12 +3450,17 @@ int trl_launch_sample_height(const DevGround& g, int E, const double* pos, int S
     return (int)cudaGetLastError();
 }
 
-int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g, const trl_obs_cfg& cfg, int F,
+int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGround& g_in, const trl_obs_cfg& cfg, int F,
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
                           const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream) {
     (void)hm;
+    // staged rows (one contiguous row per env) win on the 2-D heightfields, direct gathers on the 3-D ones (profiles/README.md)
+    static const int staged_env = env_int("TRL_OBS_STAGED", -1);  // A/B hook: 0 = always gather, 1 = always stage
+    const bool use_staged = g_in.patch_nbuf > 0 && (staged_env >= 0 ? staged_env != 0 : g_in.kind == 1);
+    DevGround g = g_in;
+    if (!use_staged) g.patch_nbuf = 0;  // k_obs_env skips the cell-rectangle mapping
     const long long threads = (long long)E * kObsG;
     const int blocks = (int)((threads + 127) / 128);
     k_obs_env<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel, body_quat,
@@ -3140,16 +3468,29 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                                                         (ObsEnvRec*)env_rec, out_state);
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
-    const int tpb = std::min(256, std::max(32, ((cfg.num_samples + kObsSPT - 1) / kObsSPT + 31) / 32 * 32));
     const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
     cudaStream_t st = (cudaStream_t)stream;
-#define TRL_OBS_LAUNCH(K)                                                                                        \
-    if (out_cell) k_obs_samples<K, true><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);    \
-    else k_obs_samples<K, false><<<E, tpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
-    if (g.kind == 1) { TRL_OBS_LAUNCH(1) }
-    else if (g.kind == 2) { TRL_OBS_LAUNCH(2) }
+    const size_t smem = (g.kind == 1 || g.kind == 2) ? (size_t)kObsWarps * obs_warp_bytes(g) : 0;
+    const int grid = (E + kObsWarps - 1) / kObsWarps;
+#define TRL_OBS_LAUNCH(K)                                                                                          \
+    if (out_cell) {                                                                                                \
+        rc = ensure_smem((const void*)k_obs_samples<K, true>, smem);                                               \
+        if (rc) return rc;                                                                                         \
+        k_obs_samples<K, true><<<grid, kObsWarps * 32, smem, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);  \
+    } else {                                                                                                       \
+        rc = ensure_smem((const void*)k_obs_samples<K, false>, smem);                                              \
+        if (rc) return rc;                                                                                         \
+        k_obs_samples<K, false><<<grid, kObsWarps * 32, smem, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell); \
+    }
+#define TRL_OBS_GATHER(K)                                                                                          \
+    if (out_cell) k_obs_gather<K, true><<<E, gtpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);   \
+    else k_obs_gather<K, false><<<E, gtpb, 0, st>>>(g, cfg, F, E, er, sample_local, out_state, out_cell);
+    const int gtpb = std::min(256, std::max(32, ((cfg.num_samples + kObsSPT - 1) / kObsSPT + 31) / 32 * 32));
+    if (g.kind == 1) { if (use_staged) { TRL_OBS_LAUNCH(1) } else { TRL_OBS_GATHER(1) } }
+    else if (g.kind == 2) { if (use_staged) { TRL_OBS_LAUNCH(2) } else { TRL_OBS_GATHER(2) } }
     else if (g.kind == 3) { TRL_OBS_LAUNCH(3) }
     else { TRL_OBS_LAUNCH(0) }
+#undef TRL_OBS_GATHER
 #undef TRL_OBS_LAUNCH
     return (int)cudaGetLastError();
 }
