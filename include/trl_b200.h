@@ -243,6 +243,24 @@ typedef struct trl_step_args {
 
 int trl_step_fused(trl_batch* b, const trl_step_args* args);
 
+/* Extended fused step: fewer bytes across PCIe for host-coupled callers. All members optional (NULL).
+ *   out_reward [E]      imitation reward epilogue (trl_imitate_calc_reward on the step's own kin pose / vel, which then
+ *                       need not be requested: out_kin_* may be NULL and stay on the device). Needs a motion, kin_time
+ *                       and body_vel. cScenarioExpImitate::CalcReward, scenarios/ScenarioExpImitate.cpp:13-159.
+ *   fallen [E]          per-env "has fallen" flag for the reward (NULL = none).
+ *   out_state_f32 [E][F] single-precision copy of the policy state (the reference feeds the state to Caffe as floats);
+ *                       args->out_state may then be NULL.
+ * In trl_step_args, tar_vel == NULL means zero target velocities (the reference's default), and out_state == NULL skips
+ * the observation: a caller that queries the policy every k-th substep (cCtController::UpdateCalcTau,
+ * sim/CtController.cpp:300-325: 1 in 20) passes out_state only on those. */
+typedef struct trl_step_opts {
+    double* out_reward;
+    const unsigned char* fallen;
+    float* out_state_f32;
+} trl_step_opts;
+
+int trl_step_fused_ex(trl_batch* b, const trl_step_args* args, const trl_step_opts* opts_or_null);
+
 /* ------------------------------------------------------------------------------------------
  * imitation reward: cScenarioExpImitate::CalcReward (scenarios/ScenarioExpImitate.cpp:13-159)
  *   with cKinTree::NormalizePoseHeading / CalcPoseErr / CalcVelErr (anim/KinTree.cpp:1319-1426,1647-1672),

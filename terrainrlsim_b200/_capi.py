@@ -22,6 +22,11 @@ class StepArgs(C.Structure):
                 ("out_kin_body_pos", C.c_void_p), ("out_state", C.c_void_p)]
 
 
+class StepOpts(C.Structure):
+    """trl_step_opts (include/trl_b200.h)."""
+    _fields_ = [("out_reward", C.c_void_p), ("fallen", C.c_void_p), ("out_state_f32", C.c_void_p)]
+
+
 # every symbol include/trl_b200.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = [
@@ -52,6 +57,7 @@ SYMBOLS = [
     ("trl_ground_sample_height", C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
     ("trl_build_poli_state", C.c_int, [_VP] * 12),
     ("trl_step_fused", C.c_int, [_VP, C.POINTER(StepArgs)]),
+    ("trl_step_fused_ex", C.c_int, [_VP, C.POINTER(StepArgs), C.POINTER(StepOpts)]),
     ("trl_imitate_calc_reward", C.c_int, [_VP] * 9),
     ("trl_batch_get_status", C.c_int, [_VP, _VP]),
     ("trl_device_fp64_probe", C.c_int, [C.c_int, C.POINTER(C.c_double)]),

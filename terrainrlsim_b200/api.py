@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import ObsCfg, StepArgs, TrlError, check
+from ._capi import ObsCfg, StepArgs, StepOpts, TrlError, check
 from . import synth
 
 PTR_HOST, PTR_DEVICE = 0, 1
@@ -343,5 +343,26 @@ class Batch:
         """HOST pointer mode: step_fused_args returns after enqueueing; sync() completes the step (pinned buffers only)."""
         check(_capi.lib().trl_batch_set_host_async(self._h, 1 if on else 0), "trl_batch_set_host_async")
 
-    def step_fused_args(self, args):
-        return _capi.lib().trl_step_fused(self._h, C.byref(args))
+    def step_fused_args(self, args, opts=None):
+        if opts is None:
+            return _capi.lib().trl_step_fused(self._h, C.byref(args))
+        return _capi.lib().trl_step_fused_ex(self._h, C.byref(args), C.byref(opts))
+
+    def make_step_opts(self, reward=None, fallen=None, state_f32=None):
+        """trl_step_opts for step_fused_args: imitation-reward epilogue [E], fallen flags [E], fp32 state [E][F]."""
+        arrs = [(reward, np.float64), (fallen, np.uint8), (state_f32, np.float32)]
+        o = StepOpts()
+        if all(a is None for a, _ in arrs):
+            return o
+        keep = self._keep
+        o.out_reward, o.fallen, o.out_state_f32 = self._prep(arrs)
+        self._keep = keep + self._keep
+        return o
+
+    def step_fused_ex(self, dt, inp, out, reward=None, fallen=None, state_f32=None):
+        """trl_step_fused_ex: `out` holds only the outputs the caller wants back (missing keys = NULL); reward [E] and
+        state_f32 [E][F] are preallocated arrays / tensors or None."""
+        a = self.make_step_args(dt, inp, out)
+        o = self.make_step_opts(reward, fallen, state_f32)
+        check(self.step_fused_args(a, o), "trl_step_fused_ex")
+        return out

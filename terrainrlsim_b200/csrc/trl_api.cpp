@@ -82,6 +82,11 @@ struct trl_batch {
     DevPiece* d_pieces = nullptr;
     int* d_env_to_field = nullptr;
     long long launches = 0;
+    // trl_step_fused_ex: internal device-resident intermediates
+    double* d_zero_nvec = nullptr;  // [E][n] zeros: tar_vel == NULL (the reference's default target velocity)
+    DevBuf kin_tmp;                 // [E][2n + 3N] kin pose / vel / body positions the caller did not ask for (reward epilogue)
+    DevBuf state_tmp;               // [E][F] double state behind an fp32-only state output
+    cudaEvent_t ev_bv = nullptr;    // body states staged (reward epilogue on the kin stream)
     // staging (host pointer mode): a small pool of grow-only device buffers handed out per call
     std::vector<DevBuf> pool;
     size_t pool_next = 0;
@@ -215,6 +220,7 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         if (!cuda_ok(cudaStreamCreateWithFlags(&b->up_streams[k], cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_bv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
         static const int carve = getenv("TRL_CARVEOUT") ? atoi(getenv("TRL_CARVEOUT")) : -1;  // tuning hook, see trl_set_carveout
         if (carve >= 0 && trl_set_carveout(carve) != 0) { trl_set_error("cudaFuncSetAttribute(carveout) failed"); return nullptr; }
@@ -271,6 +277,11 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
         cudaMemset(b->d_pd_scratch, 0, bytes);  // structurally-zero entries of the packed matrix are never written
     }
     if (!cuda_ok(cudaMalloc(&b->d_env_rec, trl_obs_env_rec_bytes() * (size_t)num_envs), "cudaMalloc(env_rec)")) return nullptr;
+    {
+        const size_t bytes = sizeof(double) * (size_t)num_envs * m->n;
+        if (!cuda_ok(cudaMalloc((void**)&b->d_zero_nvec, bytes), "cudaMalloc(zeros)")) return nullptr;
+        cudaMemset(b->d_zero_nvec, 0, bytes);
+    }
     if (!cuda_ok(cudaMalloc((void**)&b->d_status, sizeof(int) * (size_t)num_envs), "cudaMalloc(status)")) return nullptr;
     cudaMemset(b->d_status, 0, sizeof(int) * (size_t)num_envs);
     std::memset(&b->ground, 0, sizeof(b->ground));
@@ -308,6 +319,10 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
         if (b->up_streams[k]) { cudaStreamSynchronize(b->up_streams[k]); cudaStreamDestroy(b->up_streams[k]); }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_pv) cudaEventDestroy(b->ev_pv);
+    if (b->ev_bv) cudaEventDestroy(b->ev_bv);
+    if (b->d_zero_nvec) cudaFree(b->d_zero_nvec);
+    b->kin_tmp.release();
+    b->state_tmp.release();
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
@@ -621,7 +636,8 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
 // as its inputs have landed, and one download stream copies results back as each chain of a slice finishes. The copy
 // engines of the two directions and the SMs all work on different slices at the same time; the critical path is one
 // slice's upload + kernels plus the whole download.
-static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool want_pd, bool want_kin, bool want_obs) {
+static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const trl_step_opts* o, bool want_pd, bool want_kin,
+                                  bool want_obs) {
     const size_t E = b->E, n = b->model->n, N = b->model->N, F = (size_t)b->F;
     b->pool_next = 0;
     auto dev = [&](const void* host, size_t bytes_per_env) -> char* {
@@ -632,23 +648,33 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
     char* d_pose = dev(a->pose, n * 8);            need(a->pose, d_pose);
     char* d_vel = dev(a->vel, n * 8);              need(a->vel, d_vel);
     char* d_tp = want_pd ? dev(a->tar_pose, n * 8) : nullptr;
-    char* d_tv = want_pd ? dev(a->tar_vel, n * 8) : nullptr;
+    char* d_tv = want_pd ? (a->tar_vel ? dev(a->tar_vel, n * 8) : reinterpret_cast<char*>(b->d_zero_nvec)) : nullptr;
+    const bool want_reward = o && o->out_reward, want_f32 = o && o->out_state_f32;
+    auto scratch = [&](bool wanted, size_t bytes_per_env) -> char* {
+        return wanted ? static_cast<char*>(b->stage_out(E * bytes_per_env)) : nullptr;
+    };
     char* d_ja = want_pd ? dev(a->joint_active, N) : nullptr;
     char* d_tau = want_pd ? dev(a->out_tau, n * 8) : nullptr;
     char* d_time = want_kin ? dev(a->kin_time, 8) : nullptr;
     char* d_op = want_kin ? dev(a->origin_pos, 24) : nullptr;
     char* d_or = want_kin ? dev(a->origin_rot, 32) : nullptr;
-    char* d_kp = want_kin ? dev(a->out_kin_pose, n * 8) : nullptr;
-    char* d_kv = want_kin ? dev(a->out_kin_vel, n * 8) : nullptr;
-    char* d_kbp = want_kin ? dev(a->out_kin_body_pos, N * 24) : nullptr;
+    // kin outputs the caller did not ask for stay on the device (the reward epilogue reads them there)
+    char* d_kp = scratch(want_kin && (a->out_kin_pose || want_reward), n * 8);
+    char* d_kv = scratch(want_kin && (a->out_kin_vel || want_reward), n * 8);
+    char* d_kbp = scratch(want_kin && a->out_kin_body_pos, N * 24);
     char* d_bp = want_obs ? dev(a->body_pos, N * 24) : nullptr;
-    char* d_bv = want_obs ? dev(a->body_vel, N * 24) : nullptr;
+    char* d_bv = (want_obs || want_reward) ? dev(a->body_vel, N * 24) : nullptr;
     char* d_ph = want_obs ? dev(a->phase, 8) : nullptr;
     char* d_fl = want_obs ? dev(a->flip, 1) : nullptr;
-    char* d_st = want_obs ? dev(a->out_state, F * 8) : nullptr;
+    char* d_st = scratch(want_obs, F * 8);
+    char* d_st32 = scratch(want_f32, F * 4);
+    char* d_rw = scratch(want_reward, 8);
+    char* d_fallen = want_reward ? dev(o->fallen, 1) : nullptr;
     if (want_pd) { need(a->tar_pose, d_tp); need(a->tar_vel, d_tv); need(a->joint_active, d_ja); need(a->out_tau, d_tau); }
     if (want_kin) { need(a->kin_time, d_time); need(a->origin_pos, d_op); need(a->origin_rot, d_or); need(a->out_kin_pose, d_kp); need(a->out_kin_vel, d_kv); need(a->out_kin_body_pos, d_kbp); }
-    if (want_obs) { need(a->body_pos, d_bp); need(a->body_vel, d_bv); need(a->phase, d_ph); need(a->flip, d_fl); need(a->out_state, d_st); }
+    if (want_obs) { need(a->body_pos, d_bp); need(a->body_vel, d_bv); need(a->phase, d_ph); need(a->flip, d_fl); need(a->body_pos, d_st); }
+    if (want_reward) { need(a->body_vel, d_bv); need(o->out_reward, d_rw); need(o->out_reward, d_kp); need(o->out_reward, d_kv); need(o->fallen, d_fallen); }
+    if (want_f32) need(o->out_state_f32, d_st32);
     if (!ok) { trl_set_error("trl_step_fused: device staging allocation failed"); return TRL_ERR_CUDA; }
 
     const size_t tile = (size_t)trl_pd_scratch_tile();
@@ -666,13 +692,14 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
             rc = (int)cudaGetLastError();
     };
     auto down = [&](void* h, const char* d, size_t bpe, size_t e0, size_t ec) {
-        if (d && !rc && cudaMemcpyAsync(static_cast<char*>(h) + e0 * bpe, d + e0 * bpe, ec * bpe, cudaMemcpyDeviceToHost, s_dn) != cudaSuccess)
+        if (h && d && !rc && cudaMemcpyAsync(static_cast<char*>(h) + e0 * bpe, d + e0 * bpe, ec * bpe, cudaMemcpyDeviceToHost, s_dn) != cudaSuccess)
             rc = (int)cudaGetLastError();
     };
     // the small per-env arrays go up once, whole (1.3 MB for 16384 envs): fewer copies per slice
     if (want_obs) { up(d_ph, a->phase, 8, 0, E); up(d_fl, a->flip, 1, 0, E); }
     if (want_kin) { up(d_time, a->kin_time, 8, 0, E); up(d_op, a->origin_pos, 24, 0, E); up(d_or, a->origin_rot, 32, 0, E); }
     if (want_pd) up(d_ja, a->joint_active, N, 0, E);
+    if (want_reward) up(d_fallen, o->fallen, 1, 0, E);
     const size_t rec_bytes = trl_obs_env_rec_bytes();
     const size_t sc_stride = trl_pd_scratch_doubles(b->model->dev);
     int slice = 0;
@@ -684,14 +711,16 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
         cudaEventRecord(b->ev_up[slice][0], s_up0);
         // submission order = service order on the copy engines: the observation chain's inputs go first (its [E][F]
         // state is 3/4 of the download, which is the long pole), the PD targets after them
-        if (want_obs) {
+        if (want_obs || want_reward) {
             s_up = s_up2;
-            up(d_bp, a->body_pos, N * 24, e0, ec); up(d_bv, a->body_vel, N * 24, e0, ec);
+            if (want_obs) up(d_bp, a->body_pos, N * 24, e0, ec);
+            up(d_bv, a->body_vel, N * 24, e0, ec);
             cudaEventRecord(b->ev_up[slice][2], s_up2);
         }
         if (want_pd) {
             s_up = s_up1;
-            up(d_tp, a->tar_pose, n * 8, e0, ec); up(d_tv, a->tar_vel, n * 8, e0, ec);
+            up(d_tp, a->tar_pose, n * 8, e0, ec);
+            if (a->tar_vel) up(d_tv, a->tar_vel, n * 8, e0, ec);
             cudaEventRecord(b->ev_up[slice][1], s_up1);
         }
         auto at = [&](char* d, size_t bpe) { return d ? d + e0 * bpe : nullptr; };
@@ -706,6 +735,10 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
                                        (const unsigned char*)at(d_fl, 1), b->d_sample_local,
                                        static_cast<char*>(b->d_env_rec) + e0 * rec_bytes, (double*)at(d_st, F * 8), nullptr, sC);
             b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+            if (!rc && want_f32) {
+                rc = trl_launch_f64_to_f32((const double*)at(d_st, F * 8), (float*)at(d_st32, F * 4), ec * F, sC);
+                b->launches += 1;
+            }
             cudaEventRecord(b->ev_cmp[slice][1], sC);
         }
         if (!rc && want_kin) {
@@ -714,6 +747,16 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
                                 (const double*)at(d_op, 24), (const double*)at(d_or, 32), (double*)at(d_kp, n * 8),
                                 (double*)at(d_kv, n * 8), (double*)at(d_kbp, N * 24), sB);
             b->launches += 1;
+            if (!rc && want_reward) {  // cScenarioExpImitate::CalcReward on the kin chain's stream: kin pose / vel never leave the device
+                cudaStreamWaitEvent(sB, b->ev_up[slice][2], 0);
+                DevGround g2 = b->ground;
+                if (g2.env_to_field) g2.env_to_field += e0;
+                rc = trl_launch_imitate_reward(b->d_model, b->model->dev, g2, (int)ec, (const double*)at(d_pose, n * 8),
+                                               (const double*)at(d_vel, n * 8), (const double*)at(d_kp, n * 8),
+                                               (const double*)at(d_kv, n * 8), (const double*)at(d_bv, N * 24),
+                                               (const unsigned char*)at(d_fallen, 1), (double*)at(d_rw, 8), nullptr, sB);
+                b->launches += 1;
+            }
             cudaEventRecord(b->ev_cmp[slice][0], sB);
         }
         if (!rc && want_pd) {
@@ -741,10 +784,12 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, bool wan
             down(a->out_kin_pose, d_kp, n * 8, e0, ec);
             down(a->out_kin_vel, d_kv, n * 8, e0, ec);
             down(a->out_kin_body_pos, d_kbp, N * 24, e0, ec);
+            if (want_reward) down(o->out_reward, d_rw, 8, e0, ec);
         }
         if (!rc && want_obs) {
             cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][1], 0);
             down(a->out_state, d_st, F * 8, e0, ec);
+            if (want_f32) down(o->out_state_f32, d_st32, F * 4, e0, ec);
         }
         if (!rc && want_pd) {
             cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][2], 0);
@@ -782,17 +827,22 @@ extern "C" int trl_batch_set_host_async(trl_batch* b, int on) {
     return TRL_OK;
 }
 
-extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
+extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) { return trl_step_fused_ex(b, a, nullptr); }
+
+extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl_step_opts* o) {
     if (!b || !a || !a->pose || !a->vel) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);
     const size_t E = b->E, n = b->model->n, N = b->model->N;
-    const bool want_pd = a->out_tau != nullptr, want_kin = a->out_kin_pose != nullptr, want_obs = a->out_state != nullptr;
-    if (want_pd && (!a->tar_pose || !a->tar_vel)) { trl_set_error("trl_step_fused: out_tau needs tar_pose and tar_vel"); return TRL_ERR_INVALID_ARG; }
+    const bool want_reward = o && o->out_reward, want_f32 = o && o->out_state_f32;
+    const bool want_pd = a->out_tau != nullptr, want_kin = a->out_kin_pose != nullptr || want_reward;
+    const bool want_obs = a->out_state != nullptr || want_f32;
+    if (want_pd && !a->tar_pose) { trl_set_error("trl_step_fused: out_tau needs tar_pose"); return TRL_ERR_INVALID_ARG; }
+    if (want_reward && !a->body_vel) { trl_set_error("trl_step_fused: out_reward needs body_vel"); return TRL_ERR_INVALID_ARG; }
     if (want_kin && (b->model->num_frames < 2 || !a->kin_time)) { trl_set_error("trl_step_fused: kin pose needs a motion and kin_time"); return TRL_ERR_NO_MOTION; }
     if (want_obs && (!a->body_pos || !a->body_vel)) { trl_set_error("trl_step_fused: out_state needs body_pos and body_vel"); return TRL_ERR_INVALID_ARG; }
     if (want_obs && b->cfg.obs_kind == TRL_OBS_CT_3D) { trl_set_error("trl_step_fused: TRL_OBS_CT_3D needs body_quat / body_angvel: use trl_build_poli_state"); return TRL_ERR_INVALID_ARG; }
     if (b->ptr_mode == TRL_PTR_HOST && b->overlap && (b->host_async || (b->host_slices > 1 && E >= 2048)))
-        return step_fused_host_sliced(b, a, want_pd, want_kin, want_obs);
+        return step_fused_host_sliced(b, a, o, want_pd, want_kin, want_obs);
     b->pool_next = 0;
     std::vector<OutCopy> copies;
     StepPtrs p{};
@@ -813,9 +863,12 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
         if (want_pd) { sA = b->side[2]; cudaStreamWaitEvent(sA, b->ev_fork, 0); }
     }
     const double *d_time = nullptr, *d_op = nullptr, *d_or = nullptr, *d_bp = nullptr, *d_bv = nullptr, *d_ph = nullptr;
-    const unsigned char* d_fl = nullptr;
-    double *d_kp = nullptr, *d_kv = nullptr, *d_kbp = nullptr, *d_state = nullptr;
+    const unsigned char *d_fl = nullptr, *d_fallen = nullptr;
+    double *d_kp = nullptr, *d_kv = nullptr, *d_kbp = nullptr, *d_state = nullptr, *d_reward = nullptr;
+    float* d_state32 = nullptr;
     bool ok = true;
+    if (want_reward && (!a->out_kin_pose || !a->out_kin_vel)) ok = ok && b->kin_tmp.reserve(sizeof(double) * E * 2 * n);
+    if (want_f32 && !a->out_state) ok = ok && b->state_tmp.reserve(sizeof(double) * E * (size_t)b->F);
     // pose / vel are shared by chains A and C: stage them on C's stream (C starts first), A waits for them
     const cudaStream_t s_pv = want_obs ? sC : sA;
     ok = ok && in_ptr(b, a->pose, E * n, &p.pose, s_pv) && in_ptr(b, a->vel, E * n, &p.vel, s_pv);
@@ -823,29 +876,55 @@ extern "C" int trl_step_fused(trl_batch* b, const trl_step_args* a) {
         cudaEventRecord(b->ev_pv, s_pv);
         cudaStreamWaitEvent(sA, b->ev_pv, 0);
     }
-    if (want_obs)
+    if (want_obs) {
         ok = ok && in_ptr(b, a->body_pos, E * N * 3, &d_bp, sC) && in_ptr(b, a->body_vel, E * N * 3, &d_bv, sC) &&
              in_ptr(b, a->phase, E, &d_ph, sC) && in_ptr(b, a->flip, E, &d_fl, sC) &&
-             out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies, false, sC);
-    if (want_kin)
+             out_ptr(b, a->out_state, E * (size_t)b->F, &d_state, copies, false, sC) &&
+             out_ptr(b, o ? o->out_state_f32 : nullptr, E * (size_t)b->F, &d_state32, copies, false, sC);
+        if (!d_state) d_state = static_cast<double*>(b->state_tmp.p);
+    } else if (want_reward) {
+        ok = ok && in_ptr(b, a->body_vel, E * N * 3, &d_bv, sB);
+    }
+    if (want_kin) {
         ok = ok && in_ptr(b, a->kin_time, E, &d_time, sB) && in_ptr(b, a->origin_pos, E * 3, &d_op, sB) &&
              in_ptr(b, a->origin_rot, E * 4, &d_or, sB) && out_ptr(b, a->out_kin_pose, E * n, &d_kp, copies, false, sB) &&
              out_ptr(b, a->out_kin_vel, E * n, &d_kv, copies, false, sB) &&
              out_ptr(b, a->out_kin_body_pos, E * N * 3, &d_kbp, copies, false, sB);
-    if (want_pd)
+        if (want_reward) {  // kin pose / vel the caller did not ask for stay on the device
+            if (!d_kp) d_kp = static_cast<double*>(b->kin_tmp.p);
+            if (!d_kv) d_kv = static_cast<double*>(b->kin_tmp.p) + E * n;
+            ok = ok && in_ptr(b, o->fallen, E, &d_fallen, sB) && out_ptr(b, o->out_reward, E, &d_reward, copies, false, sB);
+        }
+    }
+    if (want_pd) {
         ok = ok && in_ptr(b, a->tar_pose, E * n, &p.tar_pose, sA) && in_ptr(b, a->tar_vel, E * n, &p.tar_vel, sA) &&
              in_ptr(b, a->joint_active, E * N, &p.joint_active, sA) && out_ptr(b, a->out_tau, E * n, &p.tau, copies, false, sA);
+        if (!a->tar_vel) p.tar_vel = b->d_zero_nvec;  // the reference's default target velocity
+    }
+    if (ok && want_reward && fork && b->ptr_mode == TRL_PTR_HOST) {  // the reward reads pose / vel / body_vel staged on other streams
+        if (s_pv != sB) { cudaEventRecord(b->ev_pv2, s_pv); cudaStreamWaitEvent(sB, b->ev_pv2, 0); }
+        if (want_obs && sC != sB) { cudaEventRecord(b->ev_bv, sC); cudaStreamWaitEvent(sB, b->ev_bv, 0); }
+    }
     int rc = ok ? 0 : (int)cudaErrorMemoryAllocation;
     auto launch_obs = [&]() {
         if (rc || !want_obs) return;
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
                                    nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC);
         b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+        if (!rc && d_state32) {
+            rc = trl_launch_f64_to_f32(d_state, d_state32, E * (size_t)b->F, sC);
+            b->launches += 1;
+        }
     };
     auto launch_kin = [&]() {
         if (rc || !want_kin) return;
         rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, b->E, d_time, d_op, d_or, d_kp, d_kv, d_kbp, sB);
         b->launches += 1;
+        if (!rc && want_reward) {
+            rc = trl_launch_imitate_reward(b->d_model, b->model->dev, b->ground, b->E, p.pose, p.vel, d_kp, d_kv, d_bv, d_fallen,
+                                           d_reward, nullptr, sB);
+            b->launches += 1;
+        }
     };
     auto launch_pd = [&]() {
         if (rc || !want_pd) return;

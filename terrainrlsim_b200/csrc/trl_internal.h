@@ -194,3 +194,4 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           const double* ground_vel, const double* phase, const unsigned char* flip,
                           const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream);
 size_t trl_obs_env_rec_bytes();
+int trl_launch_f64_to_f32(const double* src, float* dst, size_t count, void* stream);

@@ -3025,6 +3025,21 @@ k_obs_gather(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __rest
     }
 }
 
+// k_f64_to_f32: single-precision copy of the policy state (the reference hands the state to Caffe as floats,
+// learning/NeuralNet.cpp); round to nearest like the C++ double -> float conversion. Two elements per thread, grid-stride.
+__global__ void __launch_bounds__(256) k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, size_t count) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 2;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < count; i += stride) {
+        if (i + 1 < count && ((reinterpret_cast<size_t>(src + i) & 15) == 0) && ((reinterpret_cast<size_t>(dst + i) & 7) == 0)) {
+            const double2 v = *reinterpret_cast<const double2*>(src + i);
+            *reinterpret_cast<float2*>(dst + i) = make_float2((float)v.x, (float)v.y);
+        } else {
+            dst[i] = (float)src[i];
+            if (i + 1 < count) dst[i + 1] = (float)src[i + 1];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_fp64_probe: register-resident DFMA chains, the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
 // ------------------------------------------------------------------------------------------------
@@ -3496,5 +3511,12 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
 }
 
 size_t trl_obs_env_rec_bytes() { return sizeof(ObsEnvRec); }
+
+int trl_launch_f64_to_f32(const double* src, float* dst, size_t count, void* stream) {
+    if (count == 0) return 0;
+    const int blocks = (int)std::min<size_t>((count / 2 + 255) / 256, (size_t)148 * 16);
+    k_f64_to_f32<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, count);
+    return (int)cudaGetLastError();
+}
 
 int trl_obs_state_size(int N, const trl_obs_cfg& cfg) { return obs_dims(N, cfg).F; }

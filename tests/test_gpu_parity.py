@@ -539,3 +539,59 @@ def test_host_async_mode_matches_synchronous(trl, oracle):
         for kk, ref in refs[k].items():
             assert np.array_equal(outs[k][kk].numpy(), ref, equal_nan=True), (k, kk)
         batches[k].set_host_async(False)
+
+
+@pytest.mark.parametrize("name,E", [("biped3d", 2100), ("dog", 96), ("biped2d", 2049)])
+def test_step_fused_ex_reward_epilogue_f32_state_default_tar_vel(trl, oracle, name, E):
+    """trl_step_fused_ex: the imitation-reward epilogue on the step's own kin pose / vel (which then stay on the device),
+    the single-precision state copy and tar_vel == NULL (zero target velocity), in HOST pointer mode (sliced pipeline for
+    E >= 2048, single pass below) and in DEVICE pointer mode. Bit-identical to the separate entry points."""
+    import torch
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=5)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    assert np.all(x["tar_vel"] == 0)
+    base = batch.step_fused(dt, x)  # every output, tar_vel given
+    fallen = np.zeros(E, dtype=np.uint8)
+    fallen[3] = 1
+    ref_reward = batch.imitate_calc_reward(x["pose"], x["vel"], base["kin_pose"], base["kin_vel"], x["body_vel"], fallen)
+    x0 = {k: v for k, v in x.items() if k != "tar_vel"}
+    n, F = pm.num_dof, batch.F
+
+    # HOST pointers: only tau, the fp32 state and the reward come back
+    out = {"tau": np.empty((E, n))}
+    reward = np.empty(E)
+    s32 = np.empty((E, F), dtype=np.float32)
+    batch.step_fused_ex(dt, x0, out, reward=reward, fallen=fallen, state_f32=s32)
+    assert np.array_equal(out["tau"], base["tau"])
+    assert np.array_equal(reward, ref_reward)
+    assert np.array_equal(s32, base["state"].astype(np.float32), equal_nan=True)
+    assert reward[3] == 0
+
+    # HOST pointers, f64 state + kin pose requested next to the reward
+    out = {"tau": np.empty((E, n)), "state": np.empty((E, F)), "kin_pose": np.empty((E, n))}
+    reward2 = np.empty(E)
+    batch.step_fused_ex(dt, x0, out, reward=reward2, fallen=fallen)
+    assert np.array_equal(out["state"], base["state"], equal_nan=True)
+    assert np.array_equal(out["kin_pose"], base["kin_pose"])
+    assert np.array_equal(reward2, ref_reward)
+
+    # observation skipped (a substep between two policy queries): tau + reward only
+    out = {"tau": np.empty((E, n))}
+    reward3 = np.empty(E)
+    batch.step_fused_ex(dt, x0, out, reward=reward3, fallen=fallen)
+    assert np.array_equal(out["tau"], base["tau"]) and np.array_equal(reward3, ref_reward)
+
+    # DEVICE pointers
+    dev_in = {k: torch.from_numpy(v).cuda() for k, v in x0.items()}
+    dout = {"tau": torch.empty((E, n), dtype=torch.float64, device="cuda")}
+    drew = torch.empty(E, dtype=torch.float64, device="cuda")
+    ds32 = torch.empty((E, F), dtype=torch.float32, device="cuda")
+    batch.use_torch_stream()
+    batch.step_fused_ex(dt, dev_in, dout, reward=drew, fallen=torch.from_numpy(fallen).cuda(), state_f32=ds32)
+    batch.sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(dout["tau"].cpu().numpy(), base["tau"])
+    assert np.array_equal(drew.cpu().numpy(), ref_reward)
+    assert np.array_equal(ds32.cpu().numpy(), base["state"].astype(np.float32), equal_nan=True)
+    batch.set_stream(None)
