@@ -71,13 +71,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def default_fields(name, E, override=0):
+    """Distinct terrains per GPU (one per env up to 4096, env % 4096 above)."""
+    if override:
+        return min(E, override)
+    return min(E, 4096)
+
+
 # ----------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (test infrastructure used here only as the measured CPU baseline)
 # ----------------------------------------------------------------------------------------------
 class CpuArm:
     """The CPU oracle's fused step over `sample_envs` envs, one thread per env range (like cScenarioTrain::Run)."""
 
-    def __init__(self, name, sample_envs, threads):
+    def __init__(self, name, sample_envs, threads, fields=None):
         from oracle import oracle_py
         from terrainrlsim_b200 import synth
         self.oracle = oracle_py
@@ -85,11 +92,12 @@ class CpuArm:
         self.sample = sample_envs
         self.om = oracle_py.Model(name)
         self.cfg = oracle_py.obs_cfg(**synth.obs_config(name))
-        kind, fields = synth.make_grounds(name, min(sample_envs, 32))
-        self.grounds = [oracle_py.Ground(kind, p) for p in fields]
+        self.num_fields = min(sample_envs, fields if fields else 32)
+        kind, fl = synth.make_grounds(name, self.num_fields)
+        self.grounds = [oracle_py.Ground(kind, p) for p in fl]
         d = synth.load_model_dict(name)
         self.dt = (1.0 / 30) / d["num_update_steps"]
-        self.arrays = dict(synth.make_inputs(name, sample_envs))
+        self.arrays = dict(synth.derive_body_state(name, synth.make_inputs(name, sample_envs)))
         oracle_py.step_range(self.om, self.cfg, self.arrays, self.grounds, self.dt, 0, min(8, sample_envs))  # allocate outputs
         self.bounds = np.linspace(0, sample_envs, threads + 1).astype(int)
 
@@ -108,17 +116,17 @@ class CpuArm:
         return time.perf_counter() - t0
 
 
-def cpu_baseline(name, target_seconds=6.0):
+def cpu_baseline(name, E, fields, target_seconds=8.0):
+    """The oracle on all host cores over the GPU arm's own workload (E envs, the same number of terrains), ~10 s."""
     threads = os.cpu_count() or 1
-    sample = 256 * threads
-    arm = CpuArm(name, sample, threads)
+    arm = CpuArm(name, E, threads, fields=fields)
     t = arm.run(1)
     passes = max(1, int(target_seconds / max(t, 1e-6)))
     t = arm.run(passes)
-    val = sample * passes / t
+    val = E * passes / t
     return {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d envs x %d passes of the C oracle (faithful restatement; faster than the Eigen reference: "
-                      "no heap temporaries), one thread per env range, %d threads" % (sample, passes, threads)}
+            "sample": "%d envs on %d terrains x %d passes of the C oracle (faithful restatement; faster than the Eigen "
+                      "reference: no heap temporaries), one thread per env range, %d threads" % (E, arm.num_fields, passes, threads)}
 
 
 def run_reference(args, rank, world):
@@ -127,10 +135,12 @@ def run_reference(args, rank, world):
     of the workload; under torchrun only rank 0 works and prints."""
     if rank != 0:
         return
+    from terrainrlsim_b200 import synth
     name = args.config
     threads = os.cpu_count() or 1
-    sample = 512 * threads
-    arm = CpuArm(name, sample, threads)
+    # the same workload as the GPU arm: one step = one pass over a GPU's worth of envs on the same number of terrains
+    sample = args.envs or synth.load_model_dict(name)["envs_per_gpu"]
+    arm = CpuArm(name, sample, threads, fields=default_fields(name, sample, args.terrains))
     for _ in range(max(args.warmup, 1)):
         arm.run(1)
     t = 0.0
@@ -140,7 +150,8 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD_NAMES[name], "envs_per_step_sample": sample},
+            "config": {"workload": WORKLOAD_NAMES[name], "envs_per_gpu": sample, "terrains_per_gpu": arm.num_fields,
+                       "sample": "one GPU's worth of envs per step on the host cores"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "each step = one oracle pass over %d envs (bounded sample of the workload), "
                                        "%d threads" % (sample, threads)},
@@ -207,9 +218,8 @@ class Workload:
         self.dt = (1.0 / 30) / self.d["num_update_steps"]
         self.model = trl.CharModel.from_name(name)
         self.batch = trl.Batch(self.model, E, device, trl.make_obs_cfg(**synth.obs_config(name)))
-        is3d = self.d["terrain"].startswith("var3d")
         if fields is None:
-            fields = min(E, 1024 if is3d else 4096)
+            fields = default_fields(name, E)
         self.num_fields = fields
         kind, fl = synth.make_grounds(name, fields, rank=rank)
         self.batch.ground_set_heightfields(kind, fl)
@@ -221,11 +231,11 @@ class Workload:
             sets = max(2, int(np.ceil(2.5 * L2_BYTES / (self.in_bytes + self.out_bytes))))
         self.sets = sets
         dev = torch.device("cuda", device)
-        self.host_inputs = synth.make_inputs(name, E, rank=rank)
+        self.host_inputs = synth.derive_body_state(name, synth.make_inputs(name, E, rank=rank))
         self.inputs, self.outputs, self.args = [], [], []
         self.batch.use_torch_stream()
         for s in range(sets):
-            x = self.host_inputs if s == 0 else synth.make_inputs(name, E, seed=0xB200 + 7919 * s + rank)
+            x = self.host_inputs if s == 0 else synth.derive_body_state(name, synth.make_inputs(name, E, seed=0xB200 + 7919 * s + rank))
             xin = {k: torch.from_numpy(v).to(dev) for k, v in x.items()}
             out = {"tau": torch.empty((E, n), dtype=torch.float64, device=dev),
                    "kin_pose": torch.empty((E, n), dtype=torch.float64, device=dev),
@@ -377,6 +387,164 @@ def timed_loop(fn, steps, barrier=None):
     return e0.elapsed_time(e1)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Restrict this rank's threads to the CPUs of the NUMA node its GPU hangs off, so pinned staging buffers (first touch)
+    land in that node's memory: with 8 ranks the host-coupled path is bound by the host's PCIe / DRAM fabric."""
+    info = {"node": None}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        info["all_cpus"] = sorted(os.sched_getaffinity(0))
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(info["all_cpus"])
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update({"node": node, "cpus": len(cpus)})
+    except Exception as exc:  # not fatal: the bench runs unbound
+        info["error"] = str(exc)[:120]
+    return info
+
+
+def measure_e2e(w, name, E, world, rank, local_rank, args, barrier, max_over_ranks):
+    """env-steps/s through the C ABI in HOST pointer mode: pinned host buffers, every step's H2D and D2H inside the timed
+    region, synchronous calls (the call returns when the results are in host memory).
+
+    What crosses PCIe is what SURVEY.md section 8d counts as the step's algorithmic bytes: pose, vel, tar_pose, the kin
+    clock and the body states up (tar_vel is the reference's default zero: NULL); tau and the [E][F] double state down.
+    The kinematic reference pose / vel are computed every step as well and consumed on the device by the imitation-reward
+    epilogue (trl_step_fused_ex), whose [E] reward comes down too -- extra work the CPU arm does not do.
+    Variants reported beside it: the previous round's contract (every kin output downloaded), the state as fp32, the
+    state every 20th substep only (the reference's own policy-query rate, sim/CtController.cpp:300-325), and the headline
+    contract double-buffered over two batches."""
+    import torch
+    from terrainrlsim_b200 import _capi
+    n, N, F = w.model.num_dof, w.model.num_joints, w.batch.F
+    pin = []
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        pin.append(t)
+        return t.numpy()
+
+    def empty(shape, dtype=torch.float64):
+        t = torch.empty(shape, dtype=dtype).pin_memory()
+        pin.append(t)
+        return t.numpy()
+
+    def host_io(wl):
+        hin = {k: pinned(v) for k, v in wl.host_inputs.items() if k != "tar_vel"}
+        full = dict(hin)
+        full["tar_vel"] = pinned(wl.host_inputs["tar_vel"])
+        return hin, full
+
+    hin, hin_full = host_io(w)
+    tau, state, reward = empty((E, n)), empty((E, F)), empty((E,))
+    state32 = empty((E, F), torch.float32)
+    kin = {"kin_pose": empty((E, n)), "kin_vel": empty((E, n)), "kin_body_pos": empty((E, N, 3))}
+    b = w.batch
+    b.set_stream(None)
+    nb = lambda d: int(sum(v.nbytes for v in d.values()))  # noqa: E731
+
+    # (args, opts, host->device bytes, device->host bytes) per contract; pointers resolved once, like a C++ caller
+    a_head = b.make_step_args(w.dt, hin, {"tau": tau, "state": state})
+    o_head = b.make_step_opts(reward=reward)
+    a_r01 = b.make_step_args(w.dt, hin_full, dict(kin, tau=tau, state=state))
+    a_f32 = b.make_step_args(w.dt, hin, {"tau": tau})
+    o_f32 = b.make_step_opts(reward=reward, state_f32=state32)
+    a_sub = b.make_step_args(w.dt, hin, {"tau": tau})
+    o_sub = b.make_step_opts(reward=reward)
+    h2d = nb(hin)
+    steps = max(5, min(args.steps, 50))
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn(0)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(k):
+            rc = fn(i)
+            if rc != 0:
+                raise RuntimeError("trl_step_fused_ex (host mode) failed: " + _capi.last_error())
+        t1 = time.perf_counter()
+        barrier()
+        return max_over_ranks((t1 - t0) * 1e3)
+
+    def rate(ms, k):
+        return world * E * k / (ms * 1e-3)
+
+    ms = timed(lambda i: b.step_fused_args(a_head, o_head), steps)
+    d2h = tau.nbytes + state.nbytes + reward.nbytes
+    e2e = {"value": rate(ms, steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h), "steps": steps,
+           "ms_per_step": ms / steps, "pcie_gbs_per_rank": (h2d + d2h) * steps / (ms * 1e-3) / 1e9,
+           "timer": "host perf_counter around synchronous calls",
+           "contract": "up: pose, vel, tar_pose, joint_active, kin clock / origin, body pos / vel, phase, flip; down: tau, "
+                       "[E][F] f64 state, [E] imitation reward (kin pose / vel / FK computed every step, consumed on the device)"}
+    variants = {}
+    ms = timed(lambda i: b.step_fused_args(a_r01), steps)
+    variants["all_outputs_r01"] = {"value": rate(ms, steps), "h2d_bytes_per_step": nb(hin_full),
+                                   "d2h_bytes_per_step": int(tau.nbytes + state.nbytes + nb(kin)),
+                                   "note": "round-1 contract: tar_vel uploaded, kin pose / vel / body positions downloaded"}
+    ms = timed(lambda i: b.step_fused_args(a_f32, o_f32), steps)
+    variants["state_f32"] = {"value": rate(ms, steps), "h2d_bytes_per_step": h2d,
+                             "d2h_bytes_per_step": int(tau.nbytes + state32.nbytes + reward.nbytes),
+                             "note": "state downloaded as float (what the reference feeds Caffe); f64 on the device"}
+    k20 = 20 * max(1, steps // 20)
+    ms = timed(lambda i: b.step_fused_args(a_head, o_head) if i % 20 == 0 else b.step_fused_args(a_sub, o_sub), k20)
+    variants["state_every_20th_substep"] = {
+        "value": rate(ms, k20), "steps": k20, "h2d_bytes_per_step": h2d,
+        "d2h_bytes_per_step": int(tau.nbytes + reward.nbytes + state.nbytes / 20),
+        "note": "observation computed and downloaded on 1 substep in 20 (cCtController::UpdateCalcTau's policy-query rate); "
+                "torque, kin pose and reward every substep"}
+    # the headline contract, double-buffered: two batches (each E envs, own pinned buffers) driven alternately through the
+    # asynchronous HOST-pointer mode, so one batch's download overlaps the other's upload and kernels
+    try:
+        w2 = Workload(name, E, local_rank, rank + 1000, sets=1, fields=min(w.num_fields, 256))
+        hin2, _ = host_io(w2)
+        tau2, state2, reward2 = empty((E, n)), empty((E, F)), empty((E,))
+        w2.batch.set_stream(None)
+        a2 = w2.batch.make_step_args(w2.dt, hin2, {"tau": tau2, "state": state2})
+        o2 = w2.batch.make_step_opts(reward=reward2)
+        pair = [(b, a_head, o_head), (w2.batch, a2, o2)]
+        for bt, aa, oo in pair:
+            bt.step_fused_args(aa, oo)  # warm-up (synchronous)
+            bt.set_host_async(True)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for bt, aa, oo in pair:
+            bt.step_fused_args(aa, oo)
+        for _ in range(steps // 2):
+            for bt, aa, oo in pair:
+                bt.sync()
+                bt.step_fused_args(aa, oo)
+        for bt, aa, oo in pair:
+            bt.sync()
+        t1 = time.perf_counter()
+        barrier()
+        nsteps = 2 + 2 * (steps // 2)
+        pms = max_over_ranks((t1 - t0) * 1e3)
+        e2e["pipelined"] = {"value": rate(pms, nsteps), "unit": UNIT, "steps": nsteps,
+                            "mode": "two batches of E envs in flight (trl_batch_set_host_async), every step's H2D and D2H "
+                                    "inside the timed region"}
+        for bt, aa, oo in pair:
+            bt.set_host_async(False)
+        del w2
+    except Exception as exc:  # the synchronous number above stands on its own
+        e2e["pipelined"] = {"error": str(exc)[:200]}
+    e2e["variants"] = variants
+    return e2e
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -386,6 +554,7 @@ def run_ours(args, rank, local_rank, world):
     import ctypes as C
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # pinned host buffers are allocated on the GPU's own NUMA node
     use_dist = world > 1
     if use_dist:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -406,7 +575,7 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     side = torch.cuda.Stream(device=local_rank)  # a real (non-legacy) stream: events and kernels share it
     torch.cuda.set_stream(side)
-    w = Workload(name, E, local_rank, rank)
+    w = Workload(name, E, local_rank, rank, fields=default_fields(name, E, args.terrains))
     for _ in range(3):
         w.step()
     if not args.no_graph:
@@ -444,74 +613,7 @@ def run_ours(args, rank, local_rank, world):
     # end-to-end through the public HOST-pointer API with pinned host buffers
     e2e = None
     if not args.no_e2e:
-        hin = {}
-        for kname, v in w.host_inputs.items():
-            t = torch.from_numpy(v).pin_memory()
-            hin[kname] = t.numpy()
-            hin["_keep_" + kname] = t
-        n, N, F = w.model.num_dof, w.model.num_joints, w.batch.F
-        hout_t = {"tau": torch.empty((E, n), dtype=torch.float64).pin_memory(),
-                  "kin_pose": torch.empty((E, n), dtype=torch.float64).pin_memory(),
-                  "kin_vel": torch.empty((E, n), dtype=torch.float64).pin_memory(),
-                  "kin_body_pos": torch.empty((E, N, 3), dtype=torch.float64).pin_memory(),
-                  "state": torch.empty((E, F), dtype=torch.float64).pin_memory()}
-        hout = {kname: t.numpy() for kname, t in hout_t.items()}
-        hin_clean = {kname: v for kname, v in hin.items() if not kname.startswith("_keep_")}
-        w.batch.set_stream(None)
-        # pointers resolved once (the buffers are fixed), then the C entry point is called directly, like a C++ caller
-        hargs = w.batch.make_step_args(w.dt, hin_clean, hout)
-        for _ in range(3):
-            w.batch.step_fused_args(hargs)
-        e2e_steps = max(5, min(args.steps, 50))
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            rc_e2e = w.batch.step_fused_args(hargs)  # synchronous: returns when outputs are in host memory
-        t1 = time.perf_counter()
-        if rc_e2e != 0:
-            raise RuntimeError("trl_step_fused (host mode) failed: " + _capi.last_error())
-        barrier()
-        e2e_ms = max_over_ranks((t1 - t0) * 1e3)
-        h2d = sum(v.nbytes for v in hin_clean.values())
-        d2h = sum(v.nbytes for v in hout.values())
-        e2e = {"value": world * E * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "timer": "host perf_counter around synchronous calls"}
-        # Same copies and kernels per step, but double-buffered: two batches (each E envs, own pinned buffers) driven
-        # alternately through the asynchronous HOST-pointer mode, so one batch's download overlaps the other's upload and
-        # kernels. Reported beside the synchronous number, not instead of it.
-        try:
-            w2 = Workload(name, E, local_rank, rank + 1000, sets=1)
-            hin2 = {kname: torch.from_numpy(v).pin_memory() for kname, v in w2.host_inputs.items()}
-            hout2 = {kname: torch.empty_like(t).pin_memory() for kname, t in hout_t.items()}
-            w2.batch.set_stream(None)
-            hargs2 = w2.batch.make_step_args(w2.dt, {k_: t.numpy() for k_, t in hin2.items()}, {k_: t.numpy() for k_, t in hout2.items()})
-            pair = [(w.batch, hargs), (w2.batch, hargs2)]
-            for bt, ha in pair:
-                bt.step_fused_args(ha)  # warm-up (synchronous)
-                bt.set_host_async(True)
-            barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for bt, ha in pair:
-                bt.step_fused_args(ha)
-            for _ in range(e2e_steps // 2):
-                for bt, ha in pair:
-                    bt.sync()
-                    bt.step_fused_args(ha)
-            for bt, ha in pair:
-                bt.sync()
-            t1 = time.perf_counter()
-            barrier()
-            nsteps = 2 + 2 * (e2e_steps // 2)
-            pms = max_over_ranks((t1 - t0) * 1e3)
-            e2e["pipelined"] = {"value": world * E * nsteps / (pms * 1e-3), "unit": UNIT, "steps": nsteps,
-                                "mode": "two batches of E envs in flight (trl_batch_set_host_async), every step's H2D and D2H inside the timed region"}
-            for bt, ha in pair:
-                bt.set_host_async(False)
-            del w2
-        except Exception as exc:  # the synchronous number above stands on its own
-            e2e["pipelined"] = {"error": str(exc)[:200]}
+        e2e = measure_e2e(w, name, E, world, rank, local_rank, args, barrier, max_over_ranks)
         w.batch.use_torch_stream()
 
     kernel_ms = w.breakdown() if not args.no_graph else None
@@ -534,8 +636,9 @@ def run_ours(args, rank, local_rank, world):
         dist.all_gather(lst, stats)
         gathered = [x.cpu().tolist() for x in lst]
 
+    # the other BASELINE.json configs at their stated envs per GPU, on every rank (weak scaling, max over ranks)
     others = {}
-    if rank == 0 and not args.no_others and world == 1:
+    if not args.no_others:
         del w.inputs[1:], w.outputs[1:], w.args[1:]
         for oname in ROOFLINE_MODEL:
             if oname == name:
@@ -548,10 +651,13 @@ def run_ours(args, rank, local_rank, world):
                 ow.capture()
             ok = 20 * ow.sets
             ow.run_steps(ok)
-            oms = timed_loop(ow.run_steps, ok)
-            opd = timed_loop(ow.run_pd, ok) / ok if ow.pd_graph is not None else None
-            others[oname] = {"envs_per_gpu": oE, "value": oE * ok / (oms * 1e-3), "unit": UNIT,
-                             "ms_per_step": oms / ok, "ms_per_pd_launch": opd}
+            oms = max_over_ranks(timed_loop(ow.run_steps, ok, barrier))
+            opd = max_over_ranks(timed_loop(ow.run_pd, ok) / ok) if ow.pd_graph is not None else None
+            pdf, totf, byt = ROOFLINE_MODEL[oname]
+            others[oname] = {"envs_per_gpu": oE, "n_gpus": world, "value": world * oE * ok / (oms * 1e-3), "unit": UNIT,
+                             "ms_per_step": oms / ok, "ms_per_pd_launch": opd,
+                             "fp64_tflops_per_gpu": totf * oE * ok / (oms * 1e-3) / 1e12,
+                             "hbm_gbs_per_gpu": byt * oE * ok / (oms * 1e-3) / 1e9}
             del ow
 
     if rank == 0:
@@ -578,7 +684,9 @@ def run_ours(args, rank, local_rank, world):
                     "peak_source": hbm_src, "whole_step_fp64_tflops": total_flops * E / (ms_step * 1e-3) / 1e12}
         cpu = None
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline(name)
+            if numa.get("all_cpus"):
+                os.sched_setaffinity(0, numa["all_cpus"])  # the CPU baseline uses every host core
+            cpu = cpu_baseline(name, E, w.num_fields)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -592,7 +700,8 @@ def run_ours(args, rank, local_rank, world):
                 "CUDA graph of %d fused steps (%d kernels each) replayed" % (w.sets, w.launches_per_step),
                 "clocks": clocks, "roofline": roof,
                 "kernel_ms": kernel_ms, "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
-                "host_cores": os.cpu_count(), "other_workloads": others,
+                "host_cores": os.cpu_count(), "numa": {k: v for k, v in numa.items() if k != "all_cpus"},
+                "other_workloads": others,
                 "episode_stats_allgather": gathered}
         print(json.dumps(line))
     if use_dist:
@@ -607,6 +716,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="biped3d", choices=sorted(ROOFLINE_MODEL))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's BASELINE.json size)")
+    ap.add_argument("--terrains", type=int, default=0, help="distinct terrains per GPU (default: min(envs, 4096))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true")

@@ -170,6 +170,98 @@ def make_inputs(name_or_dict, E, seed=None, rank=0):
 
 
 # ----------------------------------------------------------------------------------------------
+# body states derived from the pose (SURVEY.md section 8d: "FK of pose and Jacobian-free finite difference")
+# ----------------------------------------------------------------------------------------------
+def _quat_rot(q):
+    """[E][4] (w, x, y, z) unit quaternions -> [E][3][3] rotation matrices."""
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((q.shape[0], 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def _euler_zyx(t):
+    """Rz * Ry * Rx of the attach angles (x, y, z), the reference's attach convention (util/MathUtil.cpp:128-155)."""
+    cx, sx, cy, sy, cz, sz = np.cos(t[0]), np.sin(t[0]), np.cos(t[1]), np.sin(t[1]), np.cos(t[2]), np.sin(t[2])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def fk_body_pos(name_or_dict, pose):
+    """World positions [E][N][3] of the body parts for poses [E][n]: plain numpy forward kinematics in the conventions of
+    cKinTree::CalcBodyPartPos (anim/KinTree.cpp:299-308,1055-1139). Input preparation only (not a checker, not timed)."""
+    d = load_model_dict(name_or_dict) if isinstance(name_or_dict, str) else name_or_dict
+    mi = ModelInfo(d)
+    jm, bd = mi.joint_mat, np.array(d["body_defs"], dtype=np.float64)
+    E = pose.shape[0]
+    Rw = [None] * mi.N
+    tw = [None] * mi.N
+    out = np.empty((E, mi.N, 3))
+    for j in range(mi.N):
+        o = mi.offset[j]
+        if mi.parent[j] < 0:
+            q = pose[:, 3:7] / np.linalg.norm(pose[:, 3:7], axis=1, keepdims=True)
+            Rw[j], tw[j] = _quat_rot(q), pose[:, 0:3].copy()
+        else:
+            A = _euler_zyx(jm[j, 5:8])
+            a = jm[j, 2:5]
+            t = mi.jtype[j]
+            Rl = np.tile(A, (E, 1, 1))
+            tl = np.tile(a, (E, 1))
+            if t == JOINT_REVOLUTE:
+                th = pose[:, o]
+                Rz = np.zeros((E, 3, 3))
+                Rz[:, 0, 0] = np.cos(th); Rz[:, 0, 1] = -np.sin(th); Rz[:, 1, 0] = np.sin(th); Rz[:, 1, 1] = np.cos(th); Rz[:, 2, 2] = 1
+                Rl = A @ Rz
+            elif t == JOINT_PRISMATIC:
+                tl = tl + pose[:, o:o + 1] * A[:, 0]
+            elif t == JOINT_PLANAR:
+                th = pose[:, o + 2]
+                Rz = np.zeros((E, 3, 3))
+                Rz[:, 0, 0] = np.cos(th); Rz[:, 0, 1] = -np.sin(th); Rz[:, 1, 0] = np.sin(th); Rz[:, 1, 1] = np.cos(th); Rz[:, 2, 2] = 1
+                Rl = A @ Rz
+                loc = np.zeros((E, 3))
+                loc[:, 0:2] = pose[:, o:o + 2]
+                tl = tl + np.einsum("eij,ej->ei", Rl, loc)
+            elif t == JOINT_SPHERICAL:
+                q = pose[:, o:o + 4] / np.linalg.norm(pose[:, o:o + 4], axis=1, keepdims=True)
+                Rl = A @ _quat_rot(q)
+            pj = mi.parent[j]
+            Rw[j] = Rw[pj] @ Rl
+            tw[j] = tw[pj] + np.einsum("eij,ej->ei", Rw[pj], tl)
+        out[:, j] = tw[j] + np.einsum("eij,j->ei", Rw[j], bd[j, 4:7])
+    return out
+
+
+def derive_body_state(name_or_dict, x, h=1e-5):
+    """Replaces x['body_pos'] / x['body_vel'] by the FK of x['pose'] and its finite difference along x['vel'] (root
+    angular velocity in the world frame, spherical joint velocities in the joint frame), so the observation features
+    are consistent with the pose. Returns x."""
+    d = load_model_dict(name_or_dict) if isinstance(name_or_dict, str) else name_or_dict
+    mi = ModelInfo(d)
+    pose, vel = x["pose"], x["vel"]
+    E = pose.shape[0]
+    p2 = pose + h * vel
+    zeros = np.zeros((E, 1))
+    w = np.concatenate([zeros, vel[:, 3:6]], axis=1)
+    p2[:, 3:7] = pose[:, 3:7] + 0.5 * h * quat_mul(w, pose[:, 3:7])
+    for j in range(1, mi.N):
+        if mi.jtype[j] == JOINT_SPHERICAL:
+            o = mi.offset[j]
+            w = np.concatenate([zeros, vel[:, o:o + 3]], axis=1)
+            p2[:, o:o + 4] = pose[:, o:o + 4] + 0.5 * h * quat_mul(pose[:, o:o + 4], w)
+    b0 = fk_body_pos(d, pose)
+    b1 = fk_body_pos(d, p2)
+    x["body_pos"] = np.ascontiguousarray(b0)
+    x["body_vel"] = np.ascontiguousarray((b1 - b0) / h)
+    return x
+
+
+# ----------------------------------------------------------------------------------------------
 # terrain
 # ----------------------------------------------------------------------------------------------
 def _f32(x):
