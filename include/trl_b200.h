@@ -152,6 +152,18 @@ int trl_imp_pd_update_control_force(trl_batch* b, double dt, const double* pose,
                                     const double* kp_or_null, const double* kd_or_null, double* inout_tau,
                                     double* out_mass_or_null, double* out_bias_or_null);
 
+/* Explicit PD: cExpPDController::UpdateControlForce -> cPDController::UpdateControlForce / CalcJointTau{Revolute,
+ * Prismatic, Spherical} (sim/ExpPDController.cpp:59-66,148-159; sim/PDController.cpp:134-149,302-428), with the same target
+ * post-processing as the stable-PD entry (normalised spherical targets, world-coordinate targets of UseWorldCoord joints,
+ * sim/PDController.cpp:191-273). Per active valid joint: revolute / prismatic tau += kp (tar - theta) + kd (tar_vel - vel);
+ * spherical tau += kp * axis-angle(q^-1 * tar) + kd (tar_vel - vel) on slots 0..2; planar and fixed joints add nothing.
+ * Same arguments as trl_imp_pd_update_control_force (no M / C outputs); inout_tau [E][n] is ACCUMULATED; dt <= 0 is a
+ * no-op like the reference (ExpPDController.cpp:62). */
+int trl_exp_pd_update_control_force(trl_batch* b, double dt, const double* pose, const double* vel,
+                                    const double* tar_pose, const double* tar_vel,
+                                    const unsigned char* joint_active_or_null,
+                                    const double* kp_or_null, const double* kd_or_null, double* inout_tau);
+
 /* cSimCharacter::ApplyControlForces + cJoint::ApplyTau (sim/SimCharacter.cpp:589-603; sim/Joint.cpp:162-221,300-318,
  * 536-562): the step right after the torque computation -- per joint, the generalized torques become a (torque, force)
  * pair, ClampTotalTorque / ClampTotalForce limit their norms (joint_mat TorqueLim / ForceLim), and the joint's world
@@ -165,6 +177,15 @@ int trl_apply_control_forces(trl_batch* b, const double* pose, const double* tau
  * DogController.cpp:897,982). pose [E][n]; out_J, out_Jcom [E][6][n] row-major (rows = wx wy wz vx vy vz in world
  * coordinates; columns of dead dof slots are zero); out_gravity_force [E][n]. Any output may be NULL. */
 int trl_rbd_extras(trl_batch* b, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force);
+
+/* cRBDUtil::BuildEndEffectorJacobian (sim/RBDUtil.cpp:181-233), read every substep by the FSM controllers for the stance /
+ * swing foot (sim/BipedController3D.cpp:1301-1388, sim/DogController.cpp:972-1060): the world-coordinate Jacobian of joint
+ * `joint_id`'s frame -- the columns of the joints on the chain root .. joint_id, zero elsewhere.
+ * joint_ids [E] (one joint per env: the stance leg differs between envs), or NULL to use `joint_id_all` for every env.
+ * pose [E][n]; out_J [E][6][n] row-major like trl_rbd_extras. A joint id outside [0, N) is TRL_ERR_INVALID_ARG (checked for
+ * joint_id_all; out-of-range entries of joint_ids give an all-zero Jacobian for that env). */
+int trl_rbd_end_effector_jacobian(trl_batch* b, const double* pose, const int* joint_ids_or_null, int joint_id_all,
+                                  double* out_J);
 
 /* ------------------------------------------------------------------------------------------
  * (2) kinematics

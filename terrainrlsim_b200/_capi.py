@@ -49,8 +49,10 @@ SYMBOLS = [
     ("trl_debug_trace_enable", C.c_int, [C.c_int]),
     ("trl_debug_trace_read", C.c_int, [C.POINTER(C.c_ulonglong)]),
     ("trl_imp_pd_update_control_force", C.c_int, [_VP, C.c_double] + [_VP] * 10),
+    ("trl_exp_pd_update_control_force", C.c_int, [_VP, C.c_double] + [_VP] * 8),
     ("trl_kin_tree_fk", C.c_int, [_VP, _VP, _VP, _VP]),
     ("trl_rbd_extras", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    ("trl_rbd_end_effector_jacobian", C.c_int, [_VP, _VP, _VP, C.c_int, _VP]),
     ("trl_apply_control_forces", C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     ("trl_kin_char_pose", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("trl_ground_set_heightfields", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, C.c_longlong, _VP, _VP, _VP, _VP, _VP, _VP]),

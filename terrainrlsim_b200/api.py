@@ -186,6 +186,21 @@ class Batch:
         check(_capi.lib().trl_imp_pd_update_control_force(self._h, float(dt), *p), "trl_imp_pd_update_control_force")
         return tau, mass, bias
 
+    def exp_pd_update_control_force(self, dt, pose, vel, tar_pose, tar_vel=None, joint_active=None, kp=None, kd=None,
+                                    tau=None):
+        """cExpPDController::UpdateControlForce: explicit PD torques, accumulated into tau [E][n]."""
+        n = self.model.num_dof
+        if tau is None:
+            tau = self._new((self.E, n), pose)
+            if _is_torch(tau):
+                tau.zero_()
+            else:
+                tau[...] = 0
+        f8, u1 = np.float64, np.uint8
+        p = self._prep([(pose, f8), (vel, f8), (tar_pose, f8), (tar_vel, f8), (joint_active, u1), (kp, f8), (kd, f8), (tau, f8)])
+        check(_capi.lib().trl_exp_pd_update_control_force(self._h, float(dt), *p), "trl_exp_pd_update_control_force")
+        return tau
+
     def status(self):
         out = np.zeros(self.E, dtype=np.int32)
         self._set_mode(PTR_HOST)
@@ -222,6 +237,19 @@ class Batch:
         p = self._prep([(pose, f8), (J, f8), (Jc, f8), (g, f8)])
         check(_capi.lib().trl_rbd_extras(self._h, *p), "trl_rbd_extras")
         return J, Jc, g
+
+    def rbd_end_effector_jacobian(self, pose, joint_id):
+        """cRBDUtil::BuildEndEffectorJacobian -> [E][6][n]; joint_id: an int (every env) or an int32 array / tensor [E]."""
+        n = self.model.num_dof
+        J = self._new((self.E, 6, n), pose)
+        if isinstance(joint_id, (int, np.integer)):
+            p = self._prep([(pose, np.float64), (J, np.float64)])
+            check(_capi.lib().trl_rbd_end_effector_jacobian(self._h, p[0], None, int(joint_id), p[1]),
+                  "trl_rbd_end_effector_jacobian")
+        else:
+            p = self._prep([(pose, np.float64), (joint_id, np.int32), (J, np.float64)])
+            check(_capi.lib().trl_rbd_end_effector_jacobian(self._h, p[0], p[1], -1, p[2]), "trl_rbd_end_effector_jacobian")
+        return J
 
     def kin_char_pose(self, time, origin_pos=None, origin_rot=None, want_vel=True):
         n = self.model.num_dof

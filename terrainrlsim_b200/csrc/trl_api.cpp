@@ -397,6 +397,55 @@ extern "C" int trl_apply_control_forces(trl_batch* b, const double* pose, const 
     return finish(b, copies, rc);
 }
 
+extern "C" int trl_exp_pd_update_control_force(trl_batch* b, double dt, const double* pose, const double* vel,
+                                               const double* tar_pose, const double* tar_vel,
+                                               const unsigned char* joint_active, const double* kp, const double* kd,
+                                               double* inout_tau) {
+    if (!b || !pose || !vel || !tar_pose || !inout_tau) {
+        trl_set_error("trl_exp_pd_update_control_force: null argument");
+        return TRL_ERR_INVALID_ARG;
+    }
+    if (!(dt > 0)) return TRL_OK;  // cExpPDController::UpdateControlForce, ExpPDController.cpp:62
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n, N = b->model->N;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    StepPtrs p{};
+    p.dt = dt;
+    if (!in_ptr(b, pose, E * n, &p.pose) || !in_ptr(b, vel, E * n, &p.vel) || !in_ptr(b, tar_pose, E * n, &p.tar_pose) ||
+        !in_ptr(b, tar_vel, E * n, &p.tar_vel) || !in_ptr(b, joint_active, E * N, &p.joint_active) ||
+        !in_ptr(b, kp, E * N, &p.kp) || !in_ptr(b, kd, E * N, &p.kd) ||
+        !out_ptr(b, inout_tau, E * n, &p.tau, copies, /*preload=*/true))
+        return TRL_ERR_CUDA;
+    if (!tar_vel) p.tar_vel = b->d_zero_nvec;
+    int rc = trl_launch_exp_pd(b->d_model, b->model->dev, b->E, p, b->stream);
+    b->launches += 1;
+    return finish(b, copies, rc);
+}
+
+extern "C" int trl_rbd_end_effector_jacobian(trl_batch* b, const double* pose, const int* joint_ids, int joint_id_all,
+                                             double* out_J) {
+    if (!b || !pose || !out_J) { trl_set_error("trl_rbd_end_effector_jacobian: null argument"); return TRL_ERR_INVALID_ARG; }
+    if (!joint_ids && (joint_id_all < 0 || joint_id_all >= b->model->N)) {
+        trl_set_error("trl_rbd_end_effector_jacobian: joint id out of range");
+        return TRL_ERR_INVALID_ARG;
+    }
+    Guard g(b->device);
+    const size_t E = b->E, n = b->model->n;
+    b->pool_next = 0;
+    std::vector<OutCopy> copies;
+    const double* d_pose = nullptr;
+    const int* d_ids = nullptr;
+    double* d_J = nullptr;
+    if (!in_ptr(b, pose, E * n, &d_pose) || !in_ptr(b, joint_ids, E, &d_ids) || !out_ptr(b, out_J, E * 6 * n, &d_J, copies))
+        return TRL_ERR_CUDA;
+    // the chain's columns of the world Jacobian (k_rbd_extras), everything off the chain zeroed
+    int rc = trl_launch_rbd_extras(b->d_model, b->model->dev, b->E, d_pose, d_J, nullptr, nullptr, b->stream);
+    if (!rc) rc = trl_launch_ee_mask(b->d_model, b->E, (int)n, d_ids, joint_id_all, d_J, b->stream);
+    b->launches += 2;
+    return finish(b, copies, rc);
+}
+
 extern "C" int trl_rbd_extras(trl_batch* b, const double* pose, double* out_J, double* out_Jcom, double* out_gravity_force) {
     if (!b || !pose) { trl_set_error("trl_rbd_extras: null argument"); return TRL_ERR_INVALID_ARG; }
     Guard g(b->device);

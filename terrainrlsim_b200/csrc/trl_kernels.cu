@@ -3040,6 +3040,117 @@ __global__ void __launch_bounds__(256) k_f64_to_f32(const double* __restrict__ s
     }
 }
 
+// k_ee_mask: cRBDUtil::BuildEndEffectorJacobian (sim/RBDUtil.cpp:181-233) from the world Jacobian -- one thread per
+// (env, dof): a column survives iff its joint lies on the chain root .. joint_id of that env.
+__global__ void __launch_bounds__(256) k_ee_mask(const DevModel* __restrict__ M, int E, int n, const int* __restrict__ joint_ids,
+                                                 int joint_id_all, double* __restrict__ J) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)E * n) return;
+    const int e = (int)(tid / n), dof = (int)(tid - (long long)e * n);
+    const int target = joint_ids ? joint_ids[e] : joint_id_all;
+    const int jd = M->ix.dof_joint[dof];
+    bool on_chain = false;
+    if (target >= 0 && target < M->N)
+        for (int j = target; j >= 0; j = M->ix.parent[j])
+            if (j == jd) { on_chain = true; break; }
+    if (!on_chain) {
+        double* col = J + (size_t)e * 6 * n + dof;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) col[(size_t)r * n] = 0.0;
+    }
+}
+
+// k_exp_pd: explicit PD (cExpPDController::UpdateControlForce, sim/ExpPDController.cpp:59-66 -> cPDController::
+// CalcJointTau*, sim/PDController.cpp:302-428) -- one thread per (env, joint); the joints are independent. A joint with a
+// world-coordinate target (UseWorldCoord) composes its world rotation up its ancestor chain first.
+__global__ void __launch_bounds__(128) k_exp_pd(const DevModel* __restrict__ M, int E, StepPtrs p) {
+    __shared__ ModelIdx s_ix;
+    stage_model_idx(&s_ix, M);
+    const ModelIdx* X = &s_ix;
+    const int N = M->N, n = M->n;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)E * N) return;
+    const size_t e = (size_t)(tid / N);
+    const int j = (int)(tid - (long long)e * N);
+    if (!X->pd_valid[j]) return;
+    if (p.joint_active && !p.joint_active[e * N + j]) return;  // PDController.cpp:137
+    const int type = X->type[j], o = X->offset[j], sz = X->size[j];
+    if (type != JT_REVOLUTE && type != JT_PRISMATIC && type != JT_SPHERICAL) return;  // planar (:358-364), fixed (:391-395)
+    const double* q = p.pose + e * n;
+    const double* qd = p.vel + e * n;
+    const double* tq = p.tar_pose + e * n;
+    const double* tqd = p.tar_vel + e * n;
+    const double kp = p.kp ? p.kp[e * N + j] : M->kp[j];
+    const double kd = p.kd ? p.kd[e * N + j] : M->kd[j];
+    double* tau = p.tau + e * n;
+    double Wm[9];
+    const bool world = M->bx.use_world[j] != 0;
+    if (world) {  // joint world rotation = product of the child -> parent rotations from the joint to the root
+        double qj[7];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) qj[i] = (i < sz) ? q[o + i] : 0.0;
+        double t3[3];
+        joint_local_trans(X, j, qj, M->attR[j], M->attT[j], Wm, t3);
+        for (int a = X->parent[j]; a >= 0; a = X->parent[a]) {
+            const int oa = X->offset[a], sa = (X->parent[a] == -1) ? 7 : X->size[a];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) qj[i] = (i < sa) ? q[oa + i] : 0.0;
+            double Ra[9], Rn[9];
+            joint_local_trans(X, a, qj, M->attR[a], M->attT[a], Ra, t3);
+            mat3_mul(Ra, Wm, Rn);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Wm[i] = Rn[i];
+        }
+    }
+    if (type == JT_SPHERICAL) {
+        double tar[4] = {tq[o], tq[o + 1], tq[o + 2], tq[o + 3]};
+        const double qq[4] = {q[o], q[o + 1], q[o + 2], q[o + 3]};
+        if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;  // SetTargetTheta, :191-211
+        else quat_normalize(tar);
+        auto axis_angle = [](const double* v, double* axis, double& theta) {  // cMathUtil::QuaternionToAxisAngle (MathUtil.cpp:399-416)
+            const double st = sqrt(v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+            axis[0] = 0; axis[1] = 0; axis[2] = 1;
+            theta = 0.0;
+            if (st > 0.0001) {
+                const double sg = (double)((0.0 < v[0]) - (v[0] < 0.0));
+                theta = 2 * sg * asin(st);
+                axis[0] = v[1] / st; axis[1] = v[2] / st; axis[2] = v[3] / st;
+            }
+        };
+        if (world) {  // tar = rel_rot * (world_rot^-1 * tar), PDController.cpp:254-267
+            double ax3[3], th;
+            axis_angle(qq, ax3, th);
+            double sh, ch;
+            sincos(th / 2, &sh, &ch);
+            const double rel[4] = {ch, sh * ax3[0], sh * ax3[1], sh * ax3[2]};
+            double wq[4];
+            pb_rot_to_quat(Wm, wq);
+            const double wc[4] = {wq[0], -wq[1], -wq[2], -wq[3]};
+            double diff[4], t2[4];
+            quat_mul(wc, tar, diff);
+            quat_mul(rel, diff, t2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tar[i] = t2[i];
+        }
+        const double qc[4] = {qq[0], -qq[1], -qq[2], -qq[3]};
+        double qerr[4], axis[3], theta;
+        quat_mul(qc, tar, qerr);  // q^-1 * tar, PDController.cpp:404-409
+        axis_angle(qerr, axis, theta);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) tau[o + i] += (kp * theta) * axis[i] + kd * (tqd[o + i] - qd[o + i]);
+        tau[o + 3] += (kp * theta) * 0.0;
+    } else {
+        double tar0 = tq[o];
+        if (world && type == JT_REVOLUTE) {  // PDController.cpp:238-252
+            double axis_world[3], theta_world;
+            pb_rot_to_axis_angle(Wm, axis_world, theta_world);
+            const double dw = axis_world[0] * Wm[2] + axis_world[1] * Wm[5] + axis_world[2] * Wm[8];
+            tar0 -= dw * theta_world - Wm[8] * q[o];
+        }
+        tau[o] += kp * (tar0 - q[o]) + kd * (tqd[o] - qd[o]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_fp64_probe: register-resident DFMA chains, the FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
 // ------------------------------------------------------------------------------------------------
@@ -3507,6 +3618,18 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
     else { TRL_OBS_LAUNCH(0) }
 #undef TRL_OBS_GATHER
 #undef TRL_OBS_LAUNCH
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_exp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {
+    const long long total = (long long)E * hm.N;
+    k_exp_pd<<<(int)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dm, E, p);
+    return (int)cudaGetLastError();
+}
+
+int trl_launch_ee_mask(const DevModel* dm, int E, int n, const int* joint_ids, int joint_id_all, double* J, void* stream) {
+    const long long total = (long long)E * n;
+    k_ee_mask<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dm, E, n, joint_ids, joint_id_all, J);
     return (int)cudaGetLastError();
 }
 

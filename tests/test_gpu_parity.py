@@ -595,3 +595,50 @@ def test_step_fused_ex_reward_epilogue_f32_state_default_tar_vel(trl, oracle, na
     assert np.array_equal(drew.cpu().numpy(), ref_reward)
     assert np.array_equal(ds32.cpu().numpy(), base["state"].astype(np.float32), equal_nan=True)
     batch.set_stream(None)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_exp_pd_control_force(trl, oracle, name):
+    """SURVEY.md 8f rank 3: cExpPDController::UpdateControlForce (explicit PD incl. world-coordinate targets, inactive
+    joints, gain overrides, accumulation into tau) vs the oracle; dt <= 0 is a no-op."""
+    E = 77
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    dt = 1.0 / 600
+    rng = np.random.default_rng(11)
+    tau0 = rng.normal(size=(E, om.n))
+    tar_vel = rng.normal(size=(E, om.n))
+    kp = rng.uniform(50, 500, size=(E, om.N))
+    kd = rng.uniform(5, 50, size=(E, om.N))
+    for gains in (False, True):
+        tau = batch.exp_pd_update_control_force(dt, x["pose"], x["vel"], x["tar_pose"], tar_vel,
+                                                joint_active=x["joint_active"], kp=kp if gains else None,
+                                                kd=kd if gains else None, tau=tau0.copy())
+        ref = np.zeros_like(tau)
+        for e in range(E):
+            ref[e] = om.exp_pd(dt, x["pose"][e], x["vel"][e], x["tar_pose"][e], tar_vel[e], x["joint_active"][e],
+                               kp=kp[e] if gains else None, kd=kd[e] if gains else None, tau0=tau0[e])
+        assert_close(tau, ref, "explicit PD torque")
+        assert np.array_equal(tau[:, :7], tau0[:, :7])  # no controller on the root
+    same = batch.exp_pd_update_control_force(0.0, x["pose"], x["vel"], x["tar_pose"], tar_vel, tau=tau0.copy())
+    assert np.array_equal(same, tau0)
+    # tar_vel == NULL is the reference's default zero target velocity
+    a = batch.exp_pd_update_control_force(dt, x["pose"], x["vel"], x["tar_pose"], None, tau=tau0.copy())
+    b = batch.exp_pd_update_control_force(dt, x["pose"], x["vel"], x["tar_pose"], np.zeros_like(tar_vel), tau=tau0.copy())
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_rbd_end_effector_jacobian(trl, oracle, name):
+    """SURVEY.md 8f rank 2 remainder: cRBDUtil::BuildEndEffectorJacobian, one joint for every env and one joint per env."""
+    E = 70
+    om, pm, batch, x, _ = _setup(trl, oracle, name, E, with_ground=False)
+    for jid in sorted({om.N - 1, 1, om.N // 2}):
+        J = batch.rbd_end_effector_jacobian(x["pose"], int(jid))
+        ref = np.stack([om.end_eff_jacobian(x["pose"][e], jid) for e in range(E)])
+        assert_close(J.reshape(E, -1), ref.reshape(E, -1), "end-effector Jacobian (joint %d)" % jid)
+    ids = (np.arange(E) % om.N).astype(np.int32)
+    J = batch.rbd_end_effector_jacobian(x["pose"], ids)
+    ref = np.stack([om.end_eff_jacobian(x["pose"][e], int(ids[e])) for e in range(E)])
+    assert_close(J.reshape(E, -1), ref.reshape(E, -1), "end-effector Jacobian (joint per env)")
+    with pytest.raises(trl.TrlError):
+        batch.rbd_end_effector_jacobian(x["pose"], om.N)
