@@ -221,6 +221,53 @@ int trl_ground_sample_height(trl_batch* b, const double* pos, int samples_per_en
                              unsigned char* out_valid_or_null, int* out_cell_or_null);
 
 /* ------------------------------------------------------------------------------------------
+ * (3b) procedural terrain on the device: the terrains are generated and scrolled where the
+ *   sampling kernels read them, one per field, with the reference's random stream (std::default_random_engine order).
+ *   cGroundVar2D::Init / Update / BuildSegment   sim/GroundVar2D.cpp:33-96,261-450   (two segments, cTerrainGen2D::Build*
+ *                                                sim/TerrainGen2D.cpp:127-653)
+ *   cGroundVar3D::Init / Update / BuildSlab      sim/GroundVar3D.cpp:24-141,350-420  (four slabs, cTerrainGen3D::BuildFlat)
+ *   cGroundFactory::ParseParamsJson              sim/GroundFactory.cpp:11-60 + cTerrainGen2D::LoadParams (data/terrain/ *.txt)
+ * ---------------------------------------------------------------------------------------- */
+#define TRL_TERRAIN_NUM_PARAMS 40 /* cTerrainGen2D::eParamsMax, in the order of sim/TerrainGen2D.h:13-66 */
+typedef enum trl_terrain_type { /* cGround::eType, sim/Ground.h:26-55 */
+    TRL_TERRAIN_PLANE = 0, TRL_TERRAIN_VAR2D_FLAT = 1, TRL_TERRAIN_VAR2D_GAPS = 2, TRL_TERRAIN_VAR2D_STEPS = 3,
+    TRL_TERRAIN_VAR2D_WALLS = 4, TRL_TERRAIN_VAR2D_BUMPS = 5, TRL_TERRAIN_VAR2D_MIXED = 6, TRL_TERRAIN_VAR2D_NARROW_GAPS = 7,
+    TRL_TERRAIN_VAR2D_SLOPES = 8, TRL_TERRAIN_VAR2D_SLOPES_GAPS = 9, TRL_TERRAIN_VAR2D_SLOPES_WALLS = 10,
+    TRL_TERRAIN_VAR2D_SLOPES_STEPS = 11, TRL_TERRAIN_VAR2D_SLOPES_MIXED = 12, TRL_TERRAIN_VAR2D_SLOPES_NARROW_GAPS = 13,
+    TRL_TERRAIN_VAR2D_CLIFFS = 14, TRL_TERRAIN_VAR3D_FLAT = 15
+} trl_terrain_type;
+
+typedef struct trl_terrain_cfg {
+    int type;                               /* trl_terrain_type */
+    int pad;
+    double params[TRL_TERRAIN_NUM_PARAMS];  /* blended parameter set (cGround::CalcBlendParams) */
+    double ground_width;                    /* GroundWidth (20); var3d uses 40 like cGroundVar3D::Init */
+    double world_scale;                     /* -world_scale= (4): heights are stored multiplied by it */
+    double spacing_x, spacing_z;            /* VertSpacingX / Z (0.2): var3d vertex spacing */
+} trl_terrain_cfg;
+
+/* Defaults of cGround::tParams and cTerrainGen2D::gParamDefs (type var2d_flat, width 20, spacing 0.2, world scale 4). */
+int trl_terrain_default_cfg(trl_terrain_cfg* out);
+/* Parses a data/terrain/ *.txt file ("Type", "GroundWidth", "VertSpacingX/Z", "Params": [ {..}, .. ]); `blend` selects /
+ * interpolates between the parameter sets like cGround::SetParamBlend. Types other than plane / var2d_* / var3d_flat are
+ * TRL_ERR_UNSUPPORTED. world_scale is left at its default (it comes from the arg file). */
+int trl_terrain_load(const char* terrain_file, double blend, trl_terrain_cfg* out);
+/* Generates `num_fields` terrains on the device and registers them like trl_ground_set_heightfields (which this call
+ * replaces). seeds [F] = cGround::tParams::mRandSeed per terrain; bound_min / bound_max [F][3] = the view bounds passed to
+ * cGround::Init (var2d reads x only). Plane terrains register the flat ground. HOST pointers regardless of the mode. */
+int trl_ground_generate(trl_batch* b, const trl_terrain_cfg* cfg, int num_fields, const unsigned long long* seeds,
+                        const double* bound_min, const double* bound_max, const int* env_to_field_or_null);
+/* cGround::Update(dt, bound_min, bound_max) for every terrain: a segment / slab the view bounds have reached is rebuilt
+ * (continuing the terrain's random stream), the others are kept. bound_min / bound_max [F][3] and out_changed_or_null [F]
+ * (1 = rebuilt, 2 = a rebuilt piece did not fit its slot: TRL_ERR_UNSUPPORTED in HOST mode) follow the pointer mode; in DEVICE mode the call only enqueues the kernel. */
+int trl_ground_update(trl_batch* b, const double* bound_min, const double* bound_max, int* out_changed_or_null);
+/* Reads terrain `field` back in the layout of trl_ground_set_heightfields (pieces in the reference's scan order; var2d
+ * rows are replicated to the reference's 3): out_data holds the pieces back to back (capacity in floats), res [P][2],
+ * origin / scale [P][3], bounds [P][4], data_offset [P]. Returns the number of floats written or a negative status. */
+long long trl_ground_read_field(trl_batch* b, int field, float* out_data, long long capacity, long long* data_offset,
+                                int* res, double* origin, double* scale, double* bounds);
+
+/* ------------------------------------------------------------------------------------------
  * (4) observation
  *   cTerrainRLCharController::ParseGround + BuildPoliState (sim/TerrainRLCharController.cpp:281-436) and the
  *   cCtController / cCtPhaseController / hopper / biped3D variants selected by trl_obs_cfg.

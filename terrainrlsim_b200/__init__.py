@@ -4,8 +4,8 @@ Only what the hot path needs: csrc/ (CUDA kernels + C ABI, built in-tree into li
 api.py (host mirror of the reference interface over the C ABI), synth.py (deterministic synthetic inputs)
 and data/ (flat model matrices of the five BASELINE.json configs).
 """
-from .api import (Batch, CharModel, TrlError, make_obs_cfg, GROUND_NONE, GROUND_PLANE, GROUND_VAR2D, GROUND_VAR3D,
+from .api import (Batch, CharModel, TrlError, make_obs_cfg, terrain_cfg, terrain_load, GROUND_NONE, GROUND_PLANE, GROUND_VAR2D, GROUND_VAR3D,
                   PTR_DEVICE, PTR_HOST)
 
-__all__ = ["Batch", "CharModel", "TrlError", "make_obs_cfg", "GROUND_NONE", "GROUND_PLANE", "GROUND_VAR2D",
+__all__ = ["Batch", "CharModel", "TrlError", "make_obs_cfg", "terrain_cfg", "terrain_load", "GROUND_NONE", "GROUND_PLANE", "GROUND_VAR2D",
            "GROUND_VAR3D", "PTR_DEVICE", "PTR_HOST"]

@@ -27,6 +27,16 @@ class StepOpts(C.Structure):
     _fields_ = [("out_reward", C.c_void_p), ("fallen", C.c_void_p), ("out_state_f32", C.c_void_p)]
 
 
+TERRAIN_NUM_PARAMS = 40
+
+
+class TerrainCfg(C.Structure):
+    """trl_terrain_cfg (include/trl_b200.h)."""
+    _fields_ = [("type", C.c_int), ("pad", C.c_int), ("params", C.c_double * TERRAIN_NUM_PARAMS),
+                ("ground_width", C.c_double), ("world_scale", C.c_double), ("spacing_x", C.c_double),
+                ("spacing_z", C.c_double)]
+
+
 # every symbol include/trl_b200.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 SYMBOLS = [
@@ -57,6 +67,11 @@ SYMBOLS = [
     ("trl_kin_char_pose", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     ("trl_ground_set_heightfields", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, _VP, C.c_longlong, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("trl_ground_sample_height", C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _VP]),
+    ("trl_terrain_default_cfg", C.c_int, [C.POINTER(TerrainCfg)]),
+    ("trl_terrain_load", C.c_int, [C.c_char_p, C.c_double, C.POINTER(TerrainCfg)]),
+    ("trl_ground_generate", C.c_int, [_VP, C.POINTER(TerrainCfg), C.c_int, _VP, _VP, _VP, _VP]),
+    ("trl_ground_update", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("trl_ground_read_field", C.c_longlong, [_VP, C.c_int, _VP, C.c_longlong, _VP, _VP, _VP, _VP, _VP]),
     ("trl_build_poli_state", C.c_int, [_VP] * 12),
     ("trl_step_fused", C.c_int, [_VP, C.POINTER(StepArgs)]),
     ("trl_step_fused_ex", C.c_int, [_VP, C.POINTER(StepArgs), C.POINTER(StepOpts)]),

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from ._capi import ObsCfg, StepArgs, StepOpts, TrlError, check
+from ._capi import ObsCfg, StepArgs, StepOpts, TerrainCfg, TrlError, check
 from . import synth
 
 PTR_HOST, PTR_DEVICE = 0, 1
@@ -296,6 +296,58 @@ class Batch:
             scale.ctypes.data, bounds.ctypes.data, e2f.ctypes.data if e2f is not None else None),
             "trl_ground_set_heightfields")
 
+    # ---- (3b) procedural terrain on the device ----
+    def ground_generate(self, cfg, num_fields, seeds=None, bound_min=None, bound_max=None, env_to_field=None):
+        """cGround::Init for `num_fields` terrains, generated on the device. cfg: TerrainCfg (terrain_cfg / terrain_load);
+        seeds [F] uint64; bound_min / bound_max [F][3] view bounds (default: the reference's +-GroundWidth/2 around x = -1
+        for var2d, +-10 for var3d, like cGroundFactory)."""
+        F = int(num_fields)
+        seeds = np.ascontiguousarray(seeds if seeds is not None else np.zeros(F), dtype=np.uint64)
+        if bound_min is None or bound_max is None:
+            half = 0.5 * (20.0 if cfg.type == 15 else cfg.ground_width)
+            shift = 0.0 if cfg.type == 15 else -1.0
+            bound_min = np.tile(np.array([-half + shift, 0.0, -half if cfg.type == 15 else 0.0]), (F, 1))
+            bound_max = np.tile(np.array([half + shift, 0.0, half if cfg.type == 15 else 0.0]), (F, 1))
+        bmin = np.ascontiguousarray(bound_min, dtype=np.float64).reshape(F, 3)
+        bmax = np.ascontiguousarray(bound_max, dtype=np.float64).reshape(F, 3)
+        e2f = np.ascontiguousarray(env_to_field, dtype=np.int32) if env_to_field is not None else None
+        check(_capi.lib().trl_ground_generate(self._h, C.byref(cfg), F, seeds.ctypes.data, bmin.ctypes.data, bmax.ctypes.data,
+                                              e2f.ctypes.data if e2f is not None else None), "trl_ground_generate")
+        self.num_fields = F
+
+    def ground_update(self, bound_min, bound_max, want_changed=True):
+        """cGround::Update for every terrain; returns the per-terrain "rebuilt" flags [F] (numpy or torch like the bounds)."""
+        F = self.num_fields
+        changed = self._new((F,), bound_min, np.int32) if want_changed else None
+        p = self._prep([(bound_min, np.float64), (bound_max, np.float64), (changed, np.int32)])
+        check(_capi.lib().trl_ground_update(self._h, *p), "trl_ground_update")
+        return changed
+
+    def ground_read_field(self, field):
+        """Terrain `field` as a list of pieces {data [res_z][res_x] float32, res, origin, scale, bounds} in scan order."""
+        P = 4
+        offs = np.zeros(P, dtype=np.int64)
+        res = np.zeros((P, 2), dtype=np.int32)
+        origin, scale, bounds = np.zeros((P, 3)), np.zeros((P, 3)), np.zeros((P, 4))
+        lib = _capi.lib()
+        total = lib.trl_ground_read_field(self._h, int(field), None, 0, offs.ctypes.data, res.ctypes.data, origin.ctypes.data,
+                                          scale.ctypes.data, bounds.ctypes.data)
+        if total < 0:
+            check(int(total), "trl_ground_read_field")
+        data = np.zeros(int(total), dtype=np.float32)
+        total = lib.trl_ground_read_field(self._h, int(field), data.ctypes.data, int(total), offs.ctypes.data, res.ctypes.data,
+                                          origin.ctypes.data, scale.ctypes.data, bounds.ctypes.data)
+        if total < 0:
+            check(int(total), "trl_ground_read_field")
+        out = []
+        for s in range(P):
+            rx, rz = int(res[s, 0]), int(res[s, 1])
+            if rx == 0:
+                break
+            out.append({"data": data[offs[s]:offs[s] + rx * rz].reshape(rz, rx).copy(), "res": (rx, rz),
+                        "origin": origin[s].copy(), "scale": scale[s].copy(), "bounds": bounds[s].copy()})
+        return out
+
     def ground_sample_height(self, pos):
         S = pos.shape[1]
         h = self._new((self.E, S), pos)
@@ -394,3 +446,23 @@ class Batch:
         o = self.make_step_opts(reward, fallen, state_f32)
         check(self.step_fused_args(a, o), "trl_step_fused_ex")
         return out
+
+
+def terrain_cfg(type_id=1, params=None, ground_width=20.0, world_scale=4.0, spacing_x=0.2, spacing_z=0.2):
+    """trl_terrain_cfg with the reference's defaults (cGround::tParams, cTerrainGen2D::gParamDefs)."""
+    cfg = TerrainCfg()
+    check(_capi.lib().trl_terrain_default_cfg(C.byref(cfg)), "trl_terrain_default_cfg")
+    cfg.type = int(type_id)
+    if params is not None:
+        for i, v in enumerate(params):
+            cfg.params[i] = float(v)
+    cfg.ground_width, cfg.world_scale, cfg.spacing_x, cfg.spacing_z = ground_width, world_scale, spacing_x, spacing_z
+    return cfg
+
+
+def terrain_load(path, blend=0.0, world_scale=4.0):
+    """A data/terrain/*.txt parameter file -> TerrainCfg (cGroundFactory::ParseParamsJson + cGround::SetParamBlend)."""
+    cfg = TerrainCfg()
+    check(_capi.lib().trl_terrain_load(str(path).encode(), float(blend), C.byref(cfg)), "trl_terrain_load")
+    cfg.world_scale = world_scale
+    return cfg

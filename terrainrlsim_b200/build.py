@@ -8,6 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtrl_b200.so")
 SOURCES = ["trl_model.cpp", "trl_api.cpp", "trl_kernels.cu"]
+STRICT_SOURCES = ["trl_terrain.cu"]  # compiled with -fmad=false: bit-exact float / double expression sequences
 HEADERS = ["trl_internal.h", "trl_device.cuh", "trl_pd_aba.cuh", "trl_pd_block.cuh", os.path.join("..", "..", "include", "trl_b200.h")]
 
 
@@ -23,7 +24,7 @@ def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
+    for f in SOURCES + STRICT_SOURCES + HEADERS:
         if os.path.getmtime(os.path.join(CSRC, f)) > t:
             return True
     return False
@@ -37,10 +38,17 @@ def build(force=False, verbose=False):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libtrl_b200.so (there is no CPU fallback)")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177,128", "-o", LIB_PATH] + SOURCES
+    common = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "177,128"]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+        common[1:1] = ["-Xptxas", "-v"]
+    objs = []
+    for src in STRICT_SOURCES:
+        obj = os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o")
+        subprocess.check_call(common + ["-fmad=false", "-c", src, "-o", obj], cwd=CSRC)
+        objs.append(obj)
+    # build to a temporary name and rename: ranks that import concurrently never see a half-written library
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    subprocess.check_call(common + ["-shared", "-o", tmp] + SOURCES + objs, cwd=CSRC)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH

@@ -81,6 +81,11 @@ struct trl_batch {
     float* d_ground_data = nullptr;
     DevPiece* d_pieces = nullptr;
     int* d_env_to_field = nullptr;
+    // procedural terrain (trl_ground_generate): generator config and the per-terrain state on the device
+    TerrainGenCfg tgen{};
+    TerrainState* d_tstate = nullptr;
+    int* d_tchanged = nullptr;
+    double* d_tbounds = nullptr;  // [2][F][3] staging of the view bounds
     long long launches = 0;
     // trl_step_fused_ex: internal device-resident intermediates
     double* d_zero_nvec = nullptr;  // [E][n] zeros: tar_vel == NULL (the reference's default target velocity)
@@ -298,6 +303,9 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     if (b->d_status) cudaFree(b->d_status);
     if (b->d_sample_local) cudaFree(b->d_sample_local);
     if (b->d_env_rec) cudaFree(b->d_env_rec);
+    if (b->d_tstate) cudaFree(b->d_tstate);
+    if (b->d_tchanged) cudaFree(b->d_tchanged);
+    if (b->d_tbounds) cudaFree(b->d_tbounds);
     if (b->d_pd_scratch) cudaFree(b->d_pd_scratch);
     if (b->d_ground_data) cudaFree(b->d_ground_data);
     if (b->d_pieces) cudaFree(b->d_pieces);
@@ -496,6 +504,30 @@ extern "C" int trl_kin_char_pose(trl_batch* b, const double* time, const double*
     return finish(b, copies, rc);
 }
 
+// Shared memory per env for the cell rectangles k_obs_samples stages: the sample window (diagonal D in any heading)
+// covers at most D / spacing + 5 cells per axis, + 3 because a staged row starts at a column multiple of 4.
+static void set_patch_dims(trl_batch* b, int kind, double min_sx, double min_sz, int pieces_per_field) {
+    const double cx = std::floor(b->sample_diag / min_sx) + 8.0;
+    const double cz = (kind == 2) ? std::floor(b->sample_diag / min_sz) + 5.0 : 1.0;
+    b->ground.patch_w = b->ground.patch_h = b->ground.patch_nbuf = 0;
+    b->ground.table_ok = b->sample_table_ok;
+    if (b->cfg.num_samples > 0 && cx <= 1024.0 && cz <= 64.0) {
+        const int w = ((int)cx + 3) & ~3, h = (int)cz;
+        const int nbuf = std::min(pieces_per_field, (int)(8192 / ((size_t)w * h * sizeof(float))));  // <= 8 KB per env
+        if (nbuf >= 1) { b->ground.patch_w = w; b->ground.patch_h = h; b->ground.patch_nbuf = nbuf; }
+    }
+}
+
+static void release_ground(trl_batch* b) {
+    if (b->d_ground_data) { cudaFree(b->d_ground_data); b->d_ground_data = nullptr; }
+    if (b->d_pieces) { cudaFree(b->d_pieces); b->d_pieces = nullptr; }
+    if (b->d_env_to_field) { cudaFree(b->d_env_to_field); b->d_env_to_field = nullptr; }
+    if (b->d_tstate) { cudaFree(b->d_tstate); b->d_tstate = nullptr; }
+    if (b->d_tchanged) { cudaFree(b->d_tchanged); b->d_tchanged = nullptr; }
+    if (b->d_tbounds) { cudaFree(b->d_tbounds); b->d_tbounds = nullptr; }
+    std::memset(&b->ground, 0, sizeof(b->ground));
+}
+
 extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_fields, int pieces_per_field,
                                            const float* data, long long data_count, const long long* data_offset,
                                            const int* res, const double* origin, const double* scale,
@@ -503,10 +535,7 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
     if (!b) return TRL_ERR_INVALID_ARG;
     Guard g(b->device);
     cudaStreamSynchronize(b->stream);
-    if (b->d_ground_data) { cudaFree(b->d_ground_data); b->d_ground_data = nullptr; }
-    if (b->d_pieces) { cudaFree(b->d_pieces); b->d_pieces = nullptr; }
-    if (b->d_env_to_field) { cudaFree(b->d_env_to_field); b->d_env_to_field = nullptr; }
-    std::memset(&b->ground, 0, sizeof(b->ground));
+    release_ground(b);
     b->ground.kind = kind;
     if (kind == 0 || kind == 3) return TRL_OK;
     if (data_count >= (1LL << 32)) {
@@ -602,22 +631,12 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
         }
     }
     {
-        // Shared memory per env for the cell rectangles k_obs_samples stages: the sample window (diagonal D in any
-        // heading) covers at most D / spacing + 5 cells per axis, + 3 because a staged row starts at a column multiple of 4.
         double min_sx = HUGE_VAL, min_sz = HUGE_VAL;
         for (size_t i = 0; i < np; ++i) {
             min_sx = std::min(min_sx, std::fabs(pieces[i].scale[0]));
             min_sz = std::min(min_sz, std::fabs(pieces[i].scale[2]));
         }
-        const double cx = std::floor(b->sample_diag / min_sx) + 8.0;
-        const double cz = (kind == 2) ? std::floor(b->sample_diag / min_sz) + 5.0 : 1.0;
-        b->ground.patch_w = b->ground.patch_h = b->ground.patch_nbuf = 0;
-        b->ground.table_ok = b->sample_table_ok;
-        if (b->cfg.num_samples > 0 && cx <= 1024.0 && cz <= 64.0) {
-            const int w = ((int)cx + 3) & ~3, h = (int)cz;
-            const int nbuf = std::min(pieces_per_field, (int)(8192 / ((size_t)w * h * sizeof(float))));  // <= 8 KB per env
-            if (nbuf >= 1) { b->ground.patch_w = w; b->ground.patch_h = h; b->ground.patch_nbuf = nbuf; }
-        }
+        set_patch_dims(b, kind, min_sx, min_sz, pieces_per_field);
     }
     b->ground.num_fields = num_fields;
     b->ground.pieces_per_field = pieces_per_field;
@@ -625,6 +644,184 @@ extern "C" int trl_ground_set_heightfields(trl_batch* b, int kind, int num_field
     b->ground.pieces = b->d_pieces;
     b->ground.env_to_field = b->d_env_to_field;
     return TRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// procedural terrain on the device (kernels: trl_terrain.cu)
+// ------------------------------------------------------------------------------------------------
+static int upload_env_to_field(trl_batch* b, int num_fields, const int* env_to_field, const char* who) {
+    std::vector<int> e2f((size_t)b->E);
+    for (int e = 0; e < b->E; ++e) {
+        e2f[e] = env_to_field ? env_to_field[e] : (e % num_fields);
+        if (e2f[e] < 0 || e2f[e] >= num_fields) {
+            trl_set_error(std::string(who) + ": env_to_field out of range");
+            return TRL_ERR_INVALID_ARG;
+        }
+    }
+    if (!cuda_ok(cudaMalloc((void**)&b->d_env_to_field, sizeof(int) * (size_t)b->E), "cudaMalloc(env_to_field)") ||
+        !cuda_ok(cudaMemcpy(b->d_env_to_field, e2f.data(), sizeof(int) * (size_t)b->E, cudaMemcpyHostToDevice), "H2D(env_to_field)"))
+        return TRL_ERR_CUDA;
+    return TRL_OK;
+}
+
+extern "C" int trl_ground_generate(trl_batch* b, const trl_terrain_cfg* cfg, int num_fields, const unsigned long long* seeds,
+                                   const double* bound_min, const double* bound_max, const int* env_to_field) {
+    if (!b || !cfg) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    cudaStreamSynchronize(b->stream);
+    release_ground(b);
+    if (cfg->type == TRL_TERRAIN_PLANE) { b->ground.kind = 3; return TRL_OK; }
+    const bool is3d = cfg->type == TRL_TERRAIN_VAR3D_FLAT;
+    if (cfg->type < TRL_TERRAIN_VAR2D_FLAT || cfg->type > TRL_TERRAIN_VAR3D_FLAT) {
+        trl_set_error("trl_ground_generate: unsupported terrain type");
+        return TRL_ERR_UNSUPPORTED;
+    }
+    if (num_fields < 1 || !bound_min || !bound_max || (!is3d && !seeds) || !(cfg->world_scale > 0) ||
+        !(cfg->ground_width > 0) || (is3d && (!(cfg->spacing_x > 0) || !(cfg->spacing_z > 0)))) {
+        trl_set_error("trl_ground_generate: invalid argument");
+        return TRL_ERR_INVALID_ARG;
+    }
+    TerrainGenCfg& t = b->tgen;
+    t.type = cfg->type;
+    t.pieces = is3d ? 4 : 2;
+    for (int i = 0; i < TRL_TERRAIN_NUM_PARAMS; ++i) t.params[i] = cfg->params[i];
+    t.world_scale = cfg->world_scale;
+    t.spacing_x = cfg->spacing_x;
+    t.spacing_z = cfg->spacing_z;
+    if (is3d) {
+        t.ground_width = 40;  // cGroundVar3D::Init forces mGroundWidth (sim/GroundVar3D.cpp:24-36)
+        const long long rx = (long long)std::ceil(t.ground_width / t.spacing_x - 0.000001) + 1;
+        const long long rz = (long long)std::ceil(t.ground_width / t.spacing_z - 0.000001) + 1;
+        t.slot_floats = ((rx + 3) & ~3LL) * rz;
+    } else {
+        // a builder appends whole features until the width is reached, after a flat lead-in of up to the whole width when
+        // the segment spans the origin (AddPadding): room for twice the width and the longest single feature
+        t.ground_width = cfg->ground_width;
+        const double* p = t.params;
+        const double feature = std::max({p[1] + p[3], p[7] + p[9], p[13], p[21] + std::max(1.0, p[29]) * (p[23] + p[25]),
+                                         p[31] + std::max(0.0, p[36]) * 0.1 + 0.5, 1.0});
+        const double verts = std::ceil((2.0 * t.ground_width + 1.0 + feature) / 0.025) + 8.0 * (std::max(1.0, p[29]) + std::max(0.0, p[36])) + 64.0;
+        if (!(verts < 1.0e6)) { trl_set_error("trl_ground_generate: terrain parameters out of range"); return TRL_ERR_INVALID_ARG; }
+        t.slot_floats = ((long long)verts + 3) & ~3LL;
+    }
+    const size_t F = (size_t)num_fields, P = (size_t)t.pieces;
+    const size_t floats = F * P * (size_t)t.slot_floats + 4096;
+    if (floats >= ((size_t)1 << 32)) { trl_set_error("trl_ground_generate: more than 2^32 height values"); return TRL_ERR_UNSUPPORTED; }
+    std::vector<unsigned long long> zero_seeds;
+    if (!seeds) { zero_seeds.assign(F, 0ULL); seeds = zero_seeds.data(); }
+    unsigned long long* d_seeds = nullptr;
+    bool ok = cuda_ok(cudaMalloc((void**)&b->d_ground_data, sizeof(float) * floats), "cudaMalloc(heightfields)") &&
+              cuda_ok(cudaMemset(b->d_ground_data, 0, sizeof(float) * floats), "cudaMemset(heightfields)") &&
+              cuda_ok(cudaMalloc((void**)&b->d_pieces, sizeof(DevPiece) * F * P), "cudaMalloc(pieces)") &&
+              cuda_ok(cudaMalloc((void**)&b->d_tstate, sizeof(TerrainState) * F), "cudaMalloc(terrain state)") &&
+              cuda_ok(cudaMemset(b->d_tstate, 0, sizeof(TerrainState) * F), "cudaMemset(terrain state)") &&
+              cuda_ok(cudaMalloc((void**)&b->d_tchanged, sizeof(int) * F), "cudaMalloc(terrain flags)") &&
+              cuda_ok(cudaMalloc((void**)&b->d_tbounds, sizeof(double) * 6 * F), "cudaMalloc(terrain bounds)") &&
+              cuda_ok(cudaMalloc((void**)&d_seeds, sizeof(unsigned long long) * F), "cudaMalloc(seeds)") &&
+              cuda_ok(cudaMemcpy(d_seeds, seeds, sizeof(unsigned long long) * F, cudaMemcpyHostToDevice), "H2D(seeds)") &&
+              cuda_ok(cudaMemcpy(b->d_tbounds, bound_min, sizeof(double) * 3 * F, cudaMemcpyHostToDevice), "H2D(bounds)") &&
+              cuda_ok(cudaMemcpy(b->d_tbounds + 3 * F, bound_max, sizeof(double) * 3 * F, cudaMemcpyHostToDevice), "H2D(bounds)");
+    int rc = TRL_OK;
+    if (ok) {
+        const int lrc = trl_launch_terrain(t, num_fields, d_seeds, b->d_tbounds, b->d_tbounds + 3 * F, b->d_tstate, b->d_ground_data,
+                                           b->d_pieces, b->d_tchanged, 1, b->stream);
+        b->launches += 1;
+        ok = lrc == 0 && cuda_ok(cudaStreamSynchronize(b->stream), "terrain generation");
+        if (lrc) trl_set_error(std::string("trl_ground_generate: ") + cudaGetErrorString((cudaError_t)lrc));
+    }
+    if (d_seeds) cudaFree(d_seeds);
+    if (ok) {  // a piece that did not fit its slot is an error, like an out-of-memory in the reference
+        std::vector<TerrainState> st(F);
+        ok = cuda_ok(cudaMemcpy(st.data(), b->d_tstate, sizeof(TerrainState) * F, cudaMemcpyDeviceToHost), "D2H(terrain state)");
+        for (size_t f = 0; ok && f < F; ++f)
+            if (st[f].overflow) { trl_set_error("trl_ground_generate: a terrain piece exceeds its slot"); rc = TRL_ERR_UNSUPPORTED; ok = false; }
+    }
+    if (ok) rc = upload_env_to_field(b, num_fields, env_to_field, "trl_ground_generate");
+    if (!ok || rc != TRL_OK) {
+        release_ground(b);
+        return rc != TRL_OK ? rc : TRL_ERR_CUDA;
+    }
+    b->ground.kind = is3d ? 2 : 1;
+    const double sx = is3d ? (double)(float)(t.spacing_x * t.world_scale) / t.world_scale : (double)(0.025f * (float)1.0) * 1.0;
+    const double sz = is3d ? (double)(float)(t.spacing_z * t.world_scale) / t.world_scale : 1.0;
+    set_patch_dims(b, b->ground.kind, std::fabs(sx) * 0.999, std::fabs(sz) * 0.999, t.pieces);
+    b->ground.num_fields = num_fields;
+    b->ground.pieces_per_field = t.pieces;
+    b->ground.data = b->d_ground_data;
+    b->ground.pieces = b->d_pieces;
+    b->ground.env_to_field = b->d_env_to_field;
+    return TRL_OK;
+}
+
+extern "C" int trl_ground_update(trl_batch* b, const double* bound_min, const double* bound_max, int* out_changed) {
+    if (!b || !bound_min || !bound_max) return TRL_ERR_INVALID_ARG;
+    if (!b->d_tstate) { trl_set_error("trl_ground_update: no generated terrain (trl_ground_generate)"); return TRL_ERR_INVALID_ARG; }
+    Guard g(b->device);
+    const size_t F = (size_t)b->ground.num_fields;
+    const double *d_min = bound_min, *d_max = bound_max;
+    int* d_changed = out_changed;
+    if (b->ptr_mode == TRL_PTR_HOST) {
+        if (!cuda_ok(cudaMemcpyAsync(b->d_tbounds, bound_min, sizeof(double) * 3 * F, cudaMemcpyHostToDevice, b->stream), "H2D(bounds)") ||
+            !cuda_ok(cudaMemcpyAsync(b->d_tbounds + 3 * F, bound_max, sizeof(double) * 3 * F, cudaMemcpyHostToDevice, b->stream), "H2D(bounds)"))
+            return TRL_ERR_CUDA;
+        d_min = b->d_tbounds;
+        d_max = b->d_tbounds + 3 * F;
+        d_changed = b->d_tchanged;
+    }
+    const int lrc = trl_launch_terrain(b->tgen, (int)F, nullptr, d_min, d_max, b->d_tstate, b->d_ground_data, b->d_pieces, d_changed,
+                                       0, b->stream);
+    b->launches += 1;
+    if (lrc) { trl_set_error(std::string("trl_ground_update: ") + cudaGetErrorString((cudaError_t)lrc)); return TRL_ERR_CUDA; }
+    if (b->ptr_mode == TRL_PTR_HOST) {
+        std::vector<int> flags(F);
+        if (!cuda_ok(cudaMemcpyAsync(flags.data(), b->d_tchanged, sizeof(int) * F, cudaMemcpyDeviceToHost, b->stream), "D2H(flags)") ||
+            !cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize"))
+            return TRL_ERR_CUDA;
+        bool overflow = false;
+        for (size_t f = 0; f < F; ++f) {
+            overflow = overflow || flags[f] == 2;
+            if (out_changed) out_changed[f] = flags[f];
+        }
+        if (overflow) { trl_set_error("trl_ground_update: a terrain piece exceeds its slot"); return TRL_ERR_UNSUPPORTED; }
+    }
+    return TRL_OK;
+}
+
+extern "C" long long trl_ground_read_field(trl_batch* b, int field, float* out_data, long long capacity, long long* data_offset,
+                                           int* res, double* origin, double* scale, double* bounds) {
+    if (!b || field < 0 || field >= b->ground.num_fields || (b->ground.kind != 1 && b->ground.kind != 2)) return TRL_ERR_INVALID_ARG;
+    Guard g(b->device);
+    if (!cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize")) return TRL_ERR_CUDA;
+    const int P = b->ground.pieces_per_field;
+    std::vector<DevPiece> pcs((size_t)P);
+    if (!cuda_ok(cudaMemcpy(pcs.data(), b->d_pieces + (size_t)field * P, sizeof(DevPiece) * P, cudaMemcpyDeviceToHost), "D2H(pieces)"))
+        return TRL_ERR_CUDA;
+    long long at = 0;
+    std::vector<float> row;
+    for (int s = 0; s < P; ++s) {
+        const DevPiece& pc = pcs[s];
+        const long long count = (long long)pc.res_x * pc.res_z;
+        if (data_offset) data_offset[s] = at;
+        if (res) { res[2 * s] = pc.res_x; res[2 * s + 1] = pc.res_z; }
+        for (int k = 0; k < 3; ++k) {
+            if (origin) origin[3 * s + k] = pc.origin[k];
+            if (scale) scale[3 * s + k] = pc.scale[k];
+        }
+        for (int k = 0; k < 4; ++k)
+            if (bounds) bounds[4 * s + k] = pc.bounds[k];
+        if (out_data) {
+            if (at + count > capacity) { trl_set_error("trl_ground_read_field: capacity too small"); return TRL_ERR_INVALID_ARG; }
+            // device rows are `pitch` floats apart; a var2d segment keeps one row on the device (the reference's 3 are identical)
+            const int dev_rows = (b->ground.kind == 1) ? 1 : pc.res_z;
+            row.resize((size_t)pc.pitch * dev_rows);
+            if (!cuda_ok(cudaMemcpy(row.data(), b->d_ground_data + pc.data_offset, sizeof(float) * row.size(), cudaMemcpyDeviceToHost), "D2H(heights)"))
+                return TRL_ERR_CUDA;
+            for (int j = 0; j < pc.res_z; ++j)
+                std::memcpy(out_data + at + (long long)j * pc.res_x, row.data() + (size_t)(dev_rows == 1 ? 0 : j) * pc.pitch, sizeof(float) * pc.res_x);
+        }
+        at += count;
+    }
+    return at;
 }
 
 extern "C" int trl_ground_sample_height(trl_batch* b, const double* pos, int S, double* out_h,

@@ -149,6 +149,29 @@ struct DevGround {
     const int* env_to_field;  // [E] or nullptr
 };
 
+// procedural terrain (trl_terrain.cu)
+struct TerrainGenCfg {
+    int type;
+    int pieces;             // 2 (var2d segments) or 4 (var3d slabs)
+    double params[TRL_TERRAIN_NUM_PARAMS];
+    double ground_width, world_scale, spacing_x, spacing_z;
+    long long slot_floats;  // capacity of one piece's slot in the device heightfield array (multiple of 4)
+};
+struct TerrainState {       // per terrain, device-resident
+    unsigned long long rand_x;  // position in the terrain's minstd_rand0 stream
+    int flip;                   // cGroundVar2D::mFlipSeg
+    int order[4];               // cGroundVar3D::mSlabOrder
+    int count[4];               // vertices of piece id (0 = empty)
+    int overflow;               // a piece did not fit its slot
+    int pad_[2];
+    double aabb[4][4];          // rigid-body AABB of piece id: min x, max x, min z, max z
+    double mn[4][3], mx[4][3];  // tSlab::mMin / mMax
+    DevPiece piece[4];          // descriptors by piece id (the registered array holds them in scan order)
+};
+int trl_launch_terrain(const TerrainGenCfg& cfg, int F, const unsigned long long* d_seeds, const double* d_bound_min,
+                       const double* d_bound_max, TerrainState* d_states, float* d_data, DevPiece* d_pieces, int* d_changed,
+                       int init, void* stream);
+
 void trl_set_error(const std::string& msg);
 int trl_build_dev_model(trl_model* m);  // fills m->dev; returns status
 

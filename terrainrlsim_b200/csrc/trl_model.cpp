@@ -686,3 +686,75 @@ extern "C" int trl_arg_file_get(const char* path, const char* key, char* out_val
     std::snprintf(out_value, (size_t)out_capacity, "%s", found.c_str());
     return TRL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// terrain parameter files (data/terrain/*.txt): cGroundFactory::ParseParamsJson (sim/GroundFactory.cpp:11-60),
+// cTerrainGen2D::LoadParams (sim/TerrainGen2D.cpp:72-84), cGround::CalcBlendParams (sim/Ground.cpp:255-277)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct TerrainParamDef { const char* name; double dflt; };
+const TerrainParamDef kTerrainParams[TRL_TERRAIN_NUM_PARAMS] = {  // cTerrainGen2D::gParamDefs, sim/TerrainGen2D.cpp:12-63
+    {"GapSpacingMin", 4}, {"GapSpacingMax", 7}, {"GapWMin", 0.5}, {"GapWMax", 2}, {"GapHMin", -2}, {"GapHMax", -2},
+    {"WallSpacingMin", 6}, {"WallSpacingMax", 8}, {"WallWMin", 0.2}, {"WallWMax", 0.2}, {"WallHMin", 0.25}, {"WallHMax", 0.5},
+    {"StepSpacingMin", 5}, {"StepSpacingMax", 7}, {"StepH0Min", 0.1}, {"StepH0Max", 0.4}, {"StepH1Min", -0.4}, {"StepH1Max", -0.1},
+    {"BumpHMin", 0}, {"BumpHMax", 0.03},
+    {"NarrowGapSpacingMin", 3}, {"NarrowGapSpacingMax", 6}, {"NarrowGapDistMin", 0.1}, {"NarrowGapDistMax", 0.4},
+    {"NarrowGapWMin", 0.15}, {"NarrowGapWMax", 0.5}, {"NarrowGapDepthMin", -2}, {"NarrowGapDepthMax", -2},
+    {"NarrowGapCountMin", 1}, {"NarrowGapCountMax", 4},
+    {"CliffSpacingMin", 5}, {"CliffSpacingMax", 7}, {"CliffH0Min", 0.1}, {"CliffH0Max", 0.4}, {"CliffH1Min", -0.4},
+    {"CliffH1Max", -0.1}, {"CliffMiniCountMax", 0}, {"SlopeDeltaRange", 0.25}, {"SlopeDeltaMin", -0.35}, {"SlopeDeltaMax", 0.35}};
+const char* const kTerrainTypeNames[] = {  // cGround::gGroundTypeNames (sim/Ground.cpp:5-33), the types this library builds
+    "plane", "var2d_flat", "var2d_gaps", "var2d_steps", "var2d_walls", "var2d_bumps", "var2d_mixed", "var2d_narrow_gaps",
+    "var2d_slopes", "var2d_slopes_gaps", "var2d_slopes_walls", "var2d_slopes_steps", "var2d_slopes_mixed",
+    "var2d_slopes_narrow_gaps", "var2d_cliffs", "var3d_flat"};
+}  // namespace
+
+extern "C" int trl_terrain_default_cfg(trl_terrain_cfg* out) {
+    if (!out) return TRL_ERR_INVALID_ARG;
+    out->type = TRL_TERRAIN_VAR2D_FLAT;  // cGround::tParams::tParams, sim/Ground.cpp:41-54
+    out->pad = 0;
+    for (int i = 0; i < TRL_TERRAIN_NUM_PARAMS; ++i) out->params[i] = kTerrainParams[i].dflt;
+    out->ground_width = 20;
+    out->world_scale = 4;
+    out->spacing_x = out->spacing_z = 0.2;
+    return TRL_OK;
+}
+
+extern "C" int trl_terrain_load(const char* terrain_file, double blend, trl_terrain_cfg* out) {
+    if (!terrain_file || !out) return TRL_ERR_INVALID_ARG;
+    trl_terrain_default_cfg(out);
+    std::string text, err;
+    if (!read_file(terrain_file, text)) { trl_set_error(std::string("Failed to open ") + terrain_file); return TRL_ERR_IO; }
+    JVal root;
+    JParser parser(text);
+    if (!parser.parse(root, err)) { trl_set_error(std::string("Failed to parse ") + terrain_file + ": " + err); return TRL_ERR_PARSE; }
+    if (const JVal* t = root.get("Type")) {
+        int found = -1;
+        for (int i = 0; i < (int)(sizeof(kTerrainTypeNames) / sizeof(kTerrainTypeNames[0])); ++i)
+            if (t->str == kTerrainTypeNames[i]) found = i;
+        if (found < 0) {
+            trl_set_error("trl_terrain_load: ground type '" + t->str + "' is not built by this library");
+            return TRL_ERR_UNSUPPORTED;
+        }
+        out->type = found;
+    }
+    if (const JVal* v = root.get("GroundWidth")) out->ground_width = v->as_double();
+    if (const JVal* v = root.get("VertSpacingX")) out->spacing_x = v->as_double();
+    if (const JVal* v = root.get("VertSpacingZ")) out->spacing_z = v->as_double();
+    const JVal* arr = root.get("Params");
+    if (arr && arr->kind == JVal::ARR && !arr->arr.empty() && out->type != TRL_TERRAIN_PLANE && out->type != TRL_TERRAIN_VAR3D_FLAT) {
+        const int num = (int)arr->arr.size();
+        std::vector<double> rows((size_t)num * TRL_TERRAIN_NUM_PARAMS);
+        for (int r = 0; r < num; ++r)
+            for (int i = 0; i < TRL_TERRAIN_NUM_PARAMS; ++i) {
+                const JVal* v = arr->arr[r].get(kTerrainParams[i].name);
+                rows[(size_t)r * TRL_TERRAIN_NUM_PARAMS + i] = (v && !v->is_null()) ? v->as_double() : kTerrainParams[i].dflt;
+            }
+        double bl = std::max(0.0, std::min(blend, num - 1.0));  // cMathUtil::Clamp
+        const int idx0 = (int)bl, idx1 = std::min(idx0 + 1, num - 1);
+        bl -= idx0;
+        for (int i = 0; i < TRL_TERRAIN_NUM_PARAMS; ++i)
+            out->params[i] = (1 - bl) * rows[(size_t)idx0 * TRL_TERRAIN_NUM_PARAMS + i] + bl * rows[(size_t)idx1 * TRL_TERRAIN_NUM_PARAMS + i];
+    }
+    return TRL_OK;
+}
