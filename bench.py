@@ -93,8 +93,15 @@ class CpuArm:
         self.om = oracle_py.Model(name)
         self.cfg = oracle_py.obs_cfg(**synth.obs_config(name))
         self.num_fields = min(sample_envs, fields if fields else 32)
-        kind, fl = synth.make_grounds(name, self.num_fields)
-        self.grounds = [oracle_py.Ground(kind, p) for p in fl]
+        # the config's own terrain file and generator seeds, as on the GPU arm (the oracle's generator and the device one
+        # build bit-identical terrains: tests/test_terrain.py)
+        t = synth.terrain_setup(name, self.num_fields)
+        if t["type"] == 15:
+            self.grounds = [oracle_py.Ground(2, oracle_py.GroundVar3D(t["spacing_x"], t["spacing_z"], t["world_scale"],
+                                                                      t["ground_width"]).pieces()) for _ in t["seeds"]]
+        else:
+            self.grounds = [oracle_py.Ground(1, oracle_py.GroundVar2D(t["type"], t["params"], t["ground_width"], t["world_scale"],
+                                                                      int(sd)).pieces()) for sd in t["seeds"]]
         d = synth.load_model_dict(name)
         self.dt = (1.0 / 30) / d["num_update_steps"]
         self.arrays = dict(synth.derive_body_state(name, synth.make_inputs(name, sample_envs)))
@@ -221,9 +228,10 @@ class Workload:
         if fields is None:
             fields = default_fields(name, E)
         self.num_fields = fields
-        kind, fl = synth.make_grounds(name, fields, rank=rank)
-        self.batch.ground_set_heightfields(kind, fl)
-        del fl
+        # one procedural terrain per field, generated on the device from the config's terrain parameter file
+        t = synth.terrain_setup(name, fields)
+        self.batch.ground_generate(trl.terrain_cfg(t["type"], t["params"], t["ground_width"], t["world_scale"], t["spacing_x"],
+                                                   t["spacing_z"]), fields, seeds=t["seeds"])
         n, N, F = self.model.num_dof, self.model.num_joints, self.batch.F
         self.in_bytes = E * (4 * n * 8 + N + 8 + 3 * 8 + 4 * 8 + 2 * N * 3 * 8 + 8 + 1)
         self.out_bytes = E * (3 * n * 8 + N * 3 * 8 + F * 8)
@@ -693,6 +701,7 @@ def run_ours(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD_NAMES[name], "envs_per_gpu": E, "joints": w.model.num_joints,
                            "dofs": w.model.num_dof, "ground_samples": w.batch.cfg.num_samples, "features": w.batch.F,
                            "dt": w.dt, "terrains_per_gpu": w.num_fields,
+                           "terrain": "%s generated on the device (trl_ground_generate)" % w.d.get("terrain_file", w.d["terrain"]),
                            "l2": "rotating %d device-resident input/output sets, %.0f MB total > L2 (126 MB)" %
                                  (w.sets, w.sets * (w.in_bytes + w.out_bytes) / 1e6),
                            "sharding": "envs partitioned by rank, no hot-path collective"},

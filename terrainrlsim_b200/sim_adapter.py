@@ -27,6 +27,7 @@ Method map (reference -> here):
     setRandomSeed(s)                                                                     :510-515
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -91,6 +92,17 @@ class BatchedSimAdapter:
         self.seed = 0
         self._frame = 0
 
+    @staticmethod
+    def _data_root(arg_file):
+        """The reference resolves data/... paths against its working directory (the repository root): the first ancestor
+        of the arg file that has a data/ directory."""
+        d = os.path.dirname(os.path.abspath(arg_file))
+        while d and d != os.path.dirname(d):
+            if os.path.isdir(os.path.join(d, "data")):
+                return d
+            d = os.path.dirname(d)
+        return os.getcwd()
+
     # ---- construction ----
     def init(self):
         cfg_name = None
@@ -101,6 +113,7 @@ class BatchedSimAdapter:
             self.num_update_steps = int(meta["num_update_steps"])
             self.obs_cfg = make_obs_cfg(**synth.obs_config(meta))
             self._terrain_meta = meta
+            self._terrain_file = None
         else:
             arg_file = None
             a = list(self.args)
@@ -123,8 +136,9 @@ class BatchedSimAdapter:
             else:
                 self.obs_cfg = make_obs_cfg(obs_kind=1 if "hopper" in ctrl else 0)
             terrain = _arg(arg_file, "terrain_file", "") or ""
-            self._terrain_meta = {"name": ctrl, "terrain": "var3d_flat" if "3d" in terrain else
-                                  ("var2d_mixed" if "mixed" in terrain else "var2d_flat")}
+            self._terrain_meta = None
+            self._terrain_file = terrain if os.path.isabs(terrain) else os.path.join(self._data_root(arg_file), terrain)
+            self._world_scale = float(_arg(arg_file, "world_scale", "1"))
         self.batch = Batch(self.model, self.num_envs, self.device, self.obs_cfg)
         self.n = self.model.num_dof
         self.N = self.model.num_joints
@@ -137,9 +151,27 @@ class BatchedSimAdapter:
         self.initEpoch()
 
     def _build_ground(self):
-        # terrain generation (cTerrainGen2D/3D) is a SURVEY.md 8f "next" row: use the synthetic generator
-        kind, fields = synth.make_grounds(self._terrain_meta, min(self.num_envs, 64), seed=0xB200 + self.seed)
-        self.batch.ground_set_heightfields(kind, fields)
+        """cScenarioSimChar::BuildGround: one procedural terrain per env (up to 4096), generated on the device from the
+        config's terrain parameter file with the reference's generator (trl_ground_generate)."""
+        from .api import terrain_cfg, terrain_load
+        F = min(self.num_envs, 4096)
+        if self._terrain_file is not None:
+            cfg = terrain_load(self._terrain_file, world_scale=self._world_scale)
+            seeds = (np.arange(F, dtype=np.uint64) * np.uint64(104729) + np.uint64(self.seed) + np.uint64(1)) % np.uint64(2147483647)
+        else:
+            t = synth.terrain_setup(self._terrain_meta, F, seed=0xB200 + self.seed)
+            cfg = terrain_cfg(t["type"], t["params"], t["ground_width"], t["world_scale"], t["spacing_x"], t["spacing_z"])
+            seeds = t["seeds"]
+        self.batch.ground_generate(cfg, F, seeds=seeds)
+        self._ground_fields = F
+
+    def updateGround(self, root_pos, view_half=10.0):
+        """cScenarioSimChar::UpdateGround -> cGround::Update: scroll the terrains under the characters. root_pos [E][3];
+        terrain f follows env f (envs beyond the terrain count share terrains and do not move them)."""
+        F = self._ground_fields
+        p = np.asarray(root_pos, dtype=np.float64)[:F]
+        return self.batch.ground_update(np.ascontiguousarray(p - [view_half, 0, view_half]),
+                                        np.ascontiguousarray(p + [view_half, 0, view_half]))
 
     # ---- cSimAdapter methods ----
     def setRandomSeed(self, seed):

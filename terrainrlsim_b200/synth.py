@@ -370,6 +370,21 @@ def make_grounds(name_or_dict, num, seed=None, rank=0, stress=True):
     return 1, out
 
 
+def terrain_setup(name_or_dict, num, seed=None, rank=0):
+    """The config's own terrain (its arg file's -terrain_file=, stored in data/<config>.json as `terrain_cfg`) for `num`
+    distinct terrains: (type, params [40], ground_width, world_scale, spacing_x, spacing_z, seeds [num] uint64).
+    The same tuple drives trl_ground_generate on the device and the oracle's GroundVar2D / 3D on the host, which build
+    bit-identical terrains (tests/test_terrain.py)."""
+    d = load_model_dict(name_or_dict) if isinstance(name_or_dict, str) else name_or_dict
+    if seed is None:
+        seed = 0xB200 + 1000 * CONFIG_IDS.get(d.get("name", ""), 9) + rank
+    tc = d["terrain_cfg"]
+    seeds = (np.uint64(seed) * np.uint64(7919) + np.arange(num, dtype=np.uint64) * np.uint64(104729) + np.uint64(1)) % np.uint64(2147483647)
+    return {"type": int(tc["type"]), "params": np.array(tc["params"], dtype=np.float64), "ground_width": float(tc["ground_width"]),
+            "world_scale": WORLD_SCALE, "spacing_x": float(tc["spacing_x"]), "spacing_z": float(tc["spacing_z"]),
+            "seeds": seeds.astype(np.uint64)}
+
+
 def obs_config(name_or_dict):
     """Observation layout of a config."""
     d = load_model_dict(name_or_dict) if isinstance(name_or_dict, str) else name_or_dict

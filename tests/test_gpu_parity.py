@@ -353,8 +353,11 @@ def test_batched_sim_adapter(trl, oracle, name):
     ob = sim.getState()
     assert ob.shape == (E, sim.getObservationSpaceSize())
     pose, vel, body_pos, body_vel = sim.world.state()
-    kind, fields = synth.make_grounds(sim._terrain_meta, min(E, 64), seed=0xB200 + 3)
-    grounds = oracle_grounds(oracle, kind, fields)
+    # the adapter's terrains are generated on the device from the config's terrain file: read them back for the oracle
+    kind = 2 if name == "biped3d" else 1
+    grounds = oracle_grounds(oracle, kind, [sim.batch.ground_read_field(f) for f in range(sim._ground_fields)])
+    changed = sim.updateGround(pose[:, :3])  # cScenarioSimChar::UpdateGround: nothing has walked off its terrain yet
+    assert changed.shape == (sim._ground_fields,)
     phase = (sim._frame * (1.0 / 30)) % 1.0
     for e in range(E):
         ref = oracle.build_poli_state(om, grounds[e % len(grounds)], cfg, pose[e], vel[e], body_pos[e], body_vel[e],

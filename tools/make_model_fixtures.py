@@ -108,6 +108,13 @@ def build(name, char_file, motion_file, state_file, extra):
         out["state"] = {"pose": s["Pose"], "vel": s["Vel"]}
         assert len(s["Pose"]) == off
     out.update(extra)
+    if extra.get("terrain_file"):
+        # the terrain parameter file as the product's own loader reads it (cGroundFactory::ParseParamsJson), blend 0
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+        import terrainrlsim_b200 as trl
+        tc = trl.terrain_load(os.path.join(REF, extra["terrain_file"]))
+        out["terrain_cfg"] = {"type": int(tc.type), "ground_width": tc.ground_width, "spacing_x": tc.spacing_x,
+                              "spacing_z": tc.spacing_z, "params": [float(v) for v in tc.params]}
 
     def enc(o):
         if isinstance(o, float) and math.isinf(o):
@@ -126,21 +133,23 @@ CONFIGS = [
     # name, character, motion, state, extras (observation config per SURVEY.md section 8 table)
     ("biped2d", "data/characters/biped2D_full.txt", "data/motions/biped2D_full_walk.txt",
      "data/states/biped2D_full_walk_state.txt",
-     {"ctrl": "ct_pd_phase", "obs": "ct", "ground_samples": 0, "terrain": "var2d_flat",
+     {"ctrl": "ct_pd_phase", "obs": "ct", "ground_samples": 0, "terrain": "var2d_flat", "terrain_file": "data/terrain/flat.txt",
       "num_update_steps": 20, "envs_per_gpu": 4096}),
     ("hopper", "data/characters/monoped_hopper0.txt", "data/motions/monoped_hopper.txt",
      "data/states/monoped_hopper.txt",
      {"ctrl": "monoped_hopper", "obs": "terrain_rl_hopper", "ground_samples": 200, "terrain": "var2d_mixed",
+      "terrain_file": "data/terrain/mixed_hopper.txt",
       "num_update_steps": 80, "envs_per_gpu": 4096}),
     ("dog", "data/characters/dog.txt", "data/motions/dog_bound.txt", "data/states/dog_bound_state3.txt",
-     {"ctrl": "dog", "obs": "terrain_rl", "ground_samples": 200, "terrain": "var2d_mixed",
+     {"ctrl": "dog", "obs": "terrain_rl", "ground_samples": 200, "terrain": "var2d_mixed", "terrain_file": "data/terrain/mixed.txt",
       "num_update_steps": 20, "envs_per_gpu": 4096}),
     ("raptor", "data/characters/raptor.txt", "data/motions/raptor_run.txt", "data/states/raptor_run_state.txt",
-     {"ctrl": "raptor", "obs": "terrain_rl", "ground_samples": 200, "terrain": "var2d_flat",
+     {"ctrl": "raptor", "obs": "terrain_rl", "ground_samples": 200, "terrain": "var2d_flat", "terrain_file": "data/terrain/flat.txt",
       "num_update_steps": 20, "envs_per_gpu": 8192}),
     ("biped3d", "data/characters/biped_3D.txt", "data/motions/biped_3D_walk.txt",
      "data/states/biped3D/biped3d_stand_state.txt",
      {"ctrl": "biped3D_cacla", "obs": "terrain_rl_grid", "ground_samples": 256, "terrain": "var3d_flat",
+      "terrain_file": "data/terrain/flat3d.txt",
       "num_update_steps": 20, "envs_per_gpu": 16384}),
 ]
 
