@@ -83,6 +83,13 @@ void trl_model_free(trl_model* m);
  * copies the value string, or TRL_ERR_INVALID_ARG when the key is absent. */
 int trl_arg_file_get(const char* arg_file_path, const char* key, char* out_value, int out_capacity);
 
+/* Character state files (data/states/ *.txt, {"Pose": [n], "Vel": [n]}): cCharacter::ReadState / WriteState
+ * (anim/Character.cpp:277-342,370-379). Reading normalises the root's and the spherical joints' quaternions
+ * (cKinTree::PoseProcessPose); a key the file does not hold leaves the caller's array untouched. Writing uses the
+ * reference's number format (std::to_string). pose / vel [n]. */
+int trl_state_read(const trl_model* m, const char* state_file, double* inout_pose, double* inout_vel);
+int trl_state_write(const trl_model* m, const char* state_file, const double* pose, const double* vel);
+
 /* ------------------------------------------------------------------------------------------
  * batch
  * ---------------------------------------------------------------------------------------- */

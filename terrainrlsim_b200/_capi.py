@@ -47,6 +47,8 @@ SYMBOLS = [
     ("trl_model_get_motion", C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     ("trl_model_free", None, [_VP]),
     ("trl_arg_file_get", C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
+    ("trl_state_read", C.c_int, [_VP, C.c_char_p, _VP, _VP]),
+    ("trl_state_write", C.c_int, [_VP, C.c_char_p, _VP, _VP]),
     ("trl_batch_create", _VP, [_VP, C.c_int, C.c_int, C.POINTER(ObsCfg)]),
     ("trl_batch_destroy", None, [_VP]),
     ("trl_batch_set_pointer_mode", C.c_int, [_VP, C.c_int]),

@@ -79,6 +79,18 @@ class CharModel:
         check(_capi.lib().trl_model_get_motion(self._h, fr.ctypes.data, C.byref(loop)), "get_motion")
         return fr, bool(loop.value)
 
+    def read_state(self, state_file, pose=None, vel=None):
+        """cCharacter::ReadState: (pose [n], vel [n]); keys the file lacks keep the given defaults (zeros if none)."""
+        pose = np.zeros(self.num_dof) if pose is None else np.array(pose, dtype=np.float64)
+        vel = np.zeros(self.num_dof) if vel is None else np.array(vel, dtype=np.float64)
+        check(_capi.lib().trl_state_read(self._h, str(state_file).encode(), pose.ctypes.data, vel.ctypes.data), "trl_state_read")
+        return pose, vel
+
+    def write_state(self, state_file, pose, vel):
+        """cCharacter::WriteState (identity root transform)."""
+        pose, vel = np.ascontiguousarray(pose, dtype=np.float64), np.ascontiguousarray(vel, dtype=np.float64)
+        check(_capi.lib().trl_state_write(self._h, str(state_file).encode(), pose.ctypes.data, vel.ctypes.data), "trl_state_write")
+
     def close(self):
         if self._h:
             _capi.lib().trl_model_free(self._h)

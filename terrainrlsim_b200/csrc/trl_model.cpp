@@ -758,3 +758,58 @@ extern "C" int trl_terrain_load(const char* terrain_file, double blend, trl_terr
     }
     return TRL_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// character state files (data/states/*.txt): cCharacter::ReadState / WriteState / BuildStateJson
+// (anim/Character.cpp:277-342,362-379), cJsonUtil::BuildVectorJson (util/JsonUtil.cpp:40-59: std::to_string, "%f")
+// ------------------------------------------------------------------------------------------------
+extern "C" int trl_state_read(const trl_model* m, const char* state_file, double* inout_pose, double* inout_vel) {
+    if (!m || !state_file) return TRL_ERR_INVALID_ARG;
+    std::string text, err;
+    if (!read_file(state_file, text)) { trl_set_error(std::string("Failed to open ") + state_file); return TRL_ERR_IO; }
+    JVal root;
+    JParser parser(text);
+    if (!parser.parse(root, err)) { trl_set_error(std::string("Failed to parse ") + state_file + ": " + err); return TRL_ERR_PARSE; }
+    const int n = m->n, N = m->N;
+    auto read_vec = [&](const char* key, double* out) -> int {
+        const JVal* v = root.get(key);
+        if (!v || v->is_null() || !out) return TRL_OK;  // a missing key keeps the caller's values (ReadState :326,334)
+        if (v->kind != JVal::ARR || (int)v->arr.size() != n) {
+            trl_set_error(std::string(state_file) + ": \"" + key + "\" must hold " + std::to_string(n) + " numbers");
+            return TRL_ERR_PARSE;
+        }
+        for (int i = 0; i < n; ++i) out[i] = v->arr[i].as_double();
+        return TRL_OK;
+    };
+    int rc = read_vec("Pose", inout_pose);
+    if (rc == TRL_OK && inout_pose && root.get("Pose") && !root.get("Pose")->is_null()) {
+        // cKinTree::PoseProcessPose (anim/KinTree.cpp:1510-1527): normalise the root and the spherical joints' quaternions
+        auto normalize4 = [](double* q) {
+            const double nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+            if (nrm > 0) for (int k = 0; k < 4; ++k) q[k] /= nrm;
+        };
+        normalize4(inout_pose + 3);
+        for (int j = 1; j < N; ++j)
+            if ((int)m->joint_mat[(size_t)j * 19] == JT_SPHERICAL) normalize4(inout_pose + (int)m->joint_mat[(size_t)j * 19 + 18]);
+    }
+    if (rc == TRL_OK) rc = read_vec("Vel", inout_vel);
+    return rc;
+}
+
+extern "C" int trl_state_write(const trl_model* m, const char* state_file, const double* pose, const double* vel) {
+    if (!m || !state_file || !pose || !vel) return TRL_ERR_INVALID_ARG;
+    auto vec_json = [&](const double* v) {
+        std::string out = "[";
+        for (int i = 0; i < m->n; ++i) {
+            if (i) out += ", ";
+            out += std::to_string(v[i]);
+        }
+        return out + "]";
+    };
+    const std::string json = "{\n\"Pose\":" + vec_json(pose) + ",\n\"Vel\":" + vec_json(vel) + "\n}";
+    FILE* f = std::fopen(state_file, "w");
+    if (!f) { trl_set_error(std::string("Failed to open ") + state_file); return TRL_ERR_IO; }
+    std::fprintf(f, "%s", json.c_str());
+    std::fclose(f);
+    return TRL_OK;
+}

@@ -115,18 +115,28 @@ class BatchedSimAdapter:
             self._terrain_meta = meta
             self._terrain_file = None
         else:
-            arg_file = None
+            arg_file = rel = None
             a = list(self.args)
             for i, tok in enumerate(a):
                 if tok.startswith("-arg_file=") and i + 1 < len(a):
                     arg_file = a[i + 1]
+                if tok.startswith("-relative_file_path=") and i + 1 < len(a):
+                    rel = a[i + 1]  # prefix of every data path (SimAdapter.cpp:104-118, cCharacter::setRelativeFilePath)
             if arg_file is None:
                 raise TrlError("BatchedSimAdapter.init: no -arg_file= given")
-            char_file = _arg(arg_file, "character_file")
-            motion_file = _arg(arg_file, "motion_file")
+            root = rel if rel is not None else (self._data_root(arg_file) + "/")
+
+            def path(p):
+                if not p or os.path.isabs(p) or os.path.exists(p):
+                    return p
+                return os.path.join(root, p)
+
+            char_file = path(_arg(arg_file, "character_file"))
+            motion_file = path(_arg(arg_file, "motion_file"))
             if char_file is None:
                 raise TrlError("arg file has no -character_file=")
             self.model = CharModel.load(char_file, motion_file)
+            self.state_file = path(_arg(arg_file, "state_file"))
             self.num_update_steps = int(_arg(arg_file, "num_update_steps", "20"))
             ctrl = _arg(arg_file, "char_ctrl", "")
             if ctrl.startswith("ct"):
@@ -137,7 +147,10 @@ class BatchedSimAdapter:
                 self.obs_cfg = make_obs_cfg(obs_kind=1 if "hopper" in ctrl else 0)
             terrain = _arg(arg_file, "terrain_file", "") or ""
             self._terrain_meta = None
-            self._terrain_file = terrain if os.path.isabs(terrain) else os.path.join(self._data_root(arg_file), terrain)
+            self._terrain_file = path(terrain) if terrain else None
+            if self._terrain_file is None:  # no -terrain_file=: cGround::tParams defaults (flat 2-D ground)
+                self._terrain_meta = {"name": ctrl, "terrain_cfg": {"type": 1, "ground_width": 20.0, "spacing_x": 0.2,
+                                                                     "spacing_z": 0.2, "params": None}}
             self._world_scale = float(_arg(arg_file, "world_scale", "1"))
         self.batch = Batch(self.model, self.num_envs, self.device, self.obs_cfg)
         self.n = self.model.num_dof
@@ -201,6 +214,10 @@ class BatchedSimAdapter:
         if action.shape != (self.num_envs, self.n - 7):
             raise TrlError("updateAction: expected shape %s" % ((self.num_envs, self.n - 7),))
         self.tar_pose[:, 7:] = action
+
+    def handleUpdatedAction(self):
+        """cSimAdapter::handleUpdatedAction: the new action has been consumed by updateAction; nothing is pending."""
+        return None
 
     def update(self):
         """One animation frame: num_update_steps x (read state, stable-PD torques, hand them to the world)."""

@@ -380,7 +380,8 @@ def terrain_setup(name_or_dict, num, seed=None, rank=0):
         seed = 0xB200 + 1000 * CONFIG_IDS.get(d.get("name", ""), 9) + rank
     tc = d["terrain_cfg"]
     seeds = (np.uint64(seed) * np.uint64(7919) + np.arange(num, dtype=np.uint64) * np.uint64(104729) + np.uint64(1)) % np.uint64(2147483647)
-    return {"type": int(tc["type"]), "params": np.array(tc["params"], dtype=np.float64), "ground_width": float(tc["ground_width"]),
+    return {"type": int(tc["type"]), "params": None if tc["params"] is None else np.array(tc["params"], dtype=np.float64),
+            "ground_width": float(tc["ground_width"]),
             "world_scale": WORLD_SCALE, "spacing_x": float(tc["spacing_x"]), "spacing_z": float(tc["spacing_z"]),
             "seeds": seeds.astype(np.uint64)}
 

@@ -645,3 +645,23 @@ def test_rbd_end_effector_jacobian(trl, oracle, name):
     assert_close(J.reshape(E, -1), ref.reshape(E, -1), "end-effector Jacobian (joint per env)")
     with pytest.raises(trl.TrlError):
         batch.rbd_end_effector_jacobian(x["pose"], om.N)
+
+
+def test_terrainrl_sim_wrapper_batched(trl, oracle):
+    """simAdapter/terrainRLSim.py's TerrainRLSimWrapper over the batched adapter: reset / step / spaces, [E]-shaped."""
+    from terrainrlsim_b200.envs import TerrainRLSimWrapper
+    from terrainrlsim_b200.sim_adapter import BatchedSimAdapter
+    E = 40
+    sim = BatchedSimAdapter("dog", E)
+    sim.init()
+    env = TerrainRLSimWrapper(sim, config={"time_limit": 256})
+    ob = env.reset()
+    A = env.getActionSpace().getMinimum().shape[0]
+    assert ob.shape == (E, sim.getObservationSpaceSize()) and A == sim.getActionSpaceSize()
+    assert env.observation_space.low.shape == (ob.shape[1],)
+    pose, _, _, _ = sim.world.state()
+    ob2, reward, done, info = env.step(pose[:, 7:])
+    assert ob2.shape == ob.shape and reward.shape == (E,) and done.shape == (E,) and done.dtype == bool and info is None
+    assert np.all(np.isfinite(ob2)) and np.all((reward >= 0) & (reward <= 1))
+    assert env.endOfEpoch() is done
+    env.finish()

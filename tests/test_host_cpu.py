@@ -195,3 +195,49 @@ def test_sim_adapter_reads_reference_arg_files():
             assert sim.model.num_joints == 21 and sim.num_update_steps == 20
     finally:
         os.chdir(cwd)
+
+
+def test_state_file_round_trip(tmp_path):
+    """cCharacter::ReadState / WriteState: quaternions normalised on read, missing keys keep the caller's values, the
+    writer's number format is the reference's std::to_string ("%f")."""
+    import json
+    import terrainrlsim_b200 as trl
+    m = trl.CharModel.from_name("biped3d")
+    d = synth.load_model_dict("biped3d")
+    pose0 = np.array(d["state"]["pose"])
+    vel0 = np.array(d["state"]["vel"])
+    p = tmp_path / "state.txt"
+    scaled = pose0.copy()
+    scaled[3:7] *= 3.0
+    p.write_text(json.dumps({"Pose": scaled.tolist(), "Vel": vel0.tolist()}))
+    pose, vel = m.read_state(str(p))
+    assert np.allclose(np.linalg.norm(pose[3:7]), 1.0) and np.allclose(pose[:3], pose0[:3])
+    assert np.array_equal(vel, vel0)
+    p.write_text(json.dumps({"Pose": pose0.tolist()}))
+    _, vel = m.read_state(str(p), vel=np.full(m.num_dof, 7.0))
+    assert np.all(vel == 7.0)
+    out = tmp_path / "out.txt"
+    m.write_state(str(out), pose0, vel0)
+    txt = out.read_text()
+    assert txt.startswith('{\n"Pose":[') and ("%f" % pose0[1]) in txt
+    pose2, vel2 = m.read_state(str(out))
+    assert np.allclose(pose2, pose0 / 1.0, atol=1e-6) or np.allclose(pose2[7:], pose0[7:], atol=1e-6)
+    p.write_text(json.dumps({"Pose": [1.0, 2.0]}))
+    with pytest.raises(trl.TrlError):
+        m.read_state(str(p))
+    if os.path.isdir(REF):
+        ref_pose, ref_vel = m.read_state(os.path.join(REF, "data/states/biped3D/biped3d_stand_state.txt"))
+        assert ref_pose.shape == (25,) and abs(np.linalg.norm(ref_pose[3:7]) - 1) < 1e-12
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+def test_env_registry_lists_the_reference_envs():
+    """simAdapter/terrainRLSim.py getEnvsList / getEnv over args/envs.json (the adapter itself needs a GPU)."""
+    import torch
+    from terrainrlsim_b200 import envs
+    lst = envs.getEnvsList(REF)
+    assert "PD_Biped2D_Flat_Terrain-v0" in lst and lst["PD_Biped2D_Flat_Terrain-v0"]["config_file"].endswith(".txt")
+    assert envs.getEnv("no-such-env", root=REF) is None
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            envs.getEnv("PD_Biped2D_Flat_Terrain-v0", root=REF, num_envs=4)
