@@ -11,9 +11,14 @@
 //   trl::cKinCharacter       <-> cKinCharacter::Pose / SetOriginPos / SetOriginRot (anim/KinCharacter.h:15-45)
 //   trl::cGround             <-> cGround::SampleHeight (sim/Ground.h:93-97)
 //   trl::cTerrainRLCharController <-> ParseGround + BuildPoliState (sim/TerrainRLCharController.h:31-87)
+//   trl::cExpPDController    <-> cExpPDController::UpdateControlForce (sim/ExpPDController.h:15-35)
+//   trl::cGroundVar          <-> cGroundVar2D / cGroundVar3D Init + Update on generated terrain (sim/GroundVar2D.h, GroundVar3D.h)
+//   trl::cBatchedSimAdapter  <-> cSimAdapter (simAdapter/SimAdapter.h:29-81, terrainRLAdapter.swig) for E characters,
+//                                over a caller-supplied rigid-body world (trl::cWorldHook; Bullet in the reference)
 // Errors: the reference returns bool + printf / asserts; here every call returns bool and LastError() has the text.
 #pragma once
 
+#include <cmath>
 #include <cstddef>
 #include <string>
 #include <vector>
@@ -239,6 +244,195 @@ public:
 
 private:
     cBatch* mBatch = nullptr;
+};
+
+// cExpPDController-shaped explicit PD (sim/ExpPDController.h:15-35): same targets / gains as cImpPDController above.
+class cExpPDController {
+public:
+    void Init(cBatch* batch) { mBatch = batch; }
+    // UpdateControlForce(time_step, out_tau): tau [E][n] is accumulated like the reference's out_tau
+    bool UpdateControlForce(double time_step, const std::vector<double>& pose, const std::vector<double>& vel,
+                            const std::vector<double>& tar_pose, const std::vector<double>* tar_vel,
+                            std::vector<double>& inout_tau, const std::vector<unsigned char>* active = nullptr) {
+        inout_tau.resize((size_t)mBatch->GetNumEnvs() * mBatch->GetNumDof(), 0.0);
+        return trl_exp_pd_update_control_force(mBatch->Handle(), time_step, pose.data(), vel.data(), tar_pose.data(),
+                                               tar_vel ? tar_vel->data() : nullptr, active ? active->data() : nullptr, nullptr,
+                                               nullptr, inout_tau.data()) == TRL_OK;
+    }
+
+private:
+    cBatch* mBatch = nullptr;
+};
+
+// cGroundVar2D / cGroundVar3D-shaped procedural ground (sim/GroundVar2D.h, sim/GroundVar3D.h): Init builds one terrain per
+// field from a terrain parameter file, Update scrolls them under the characters (cGround::Update).
+class cGroundVar {
+public:
+    void Init(cBatch* batch) { mBatch = batch; }
+    bool LoadParams(const std::string& terrain_file, double blend = 0.0, double world_scale = 4.0) {
+        if (trl_terrain_load(terrain_file.c_str(), blend, &mCfg) != TRL_OK) return false;
+        mCfg.world_scale = world_scale;
+        return true;
+    }
+    trl_terrain_cfg& Params() { return mCfg; }
+    bool Build(int num_fields, const std::vector<unsigned long long>& seeds, const std::vector<double>& bound_min,
+               const std::vector<double>& bound_max) {
+        mFields = num_fields;
+        return trl_ground_generate(mBatch->Handle(), &mCfg, num_fields, seeds.data(), bound_min.data(), bound_max.data(), nullptr) == TRL_OK;
+    }
+    bool Update(const std::vector<double>& bound_min, const std::vector<double>& bound_max, std::vector<int>* out_changed = nullptr) {
+        if (out_changed) out_changed->resize((size_t)mFields);
+        return trl_ground_update(mBatch->Handle(), bound_min.data(), bound_max.data(), out_changed ? out_changed->data() : nullptr) == TRL_OK;
+    }
+
+private:
+    cBatch* mBatch = nullptr;
+    trl_terrain_cfg mCfg{};
+    int mFields = 0;
+};
+
+// The rigid-body world behind the adapter (Bullet in the reference: cWorld + cSimCharacter's bodies). It stays the caller's:
+// the adapter reads the generalized state and the body states from it and hands it the torques.
+class cWorldHook {
+public:
+    virtual ~cWorldHook() = default;
+    virtual void Reset(int num_envs) = 0;                                              // cScenarioSimChar::Reset
+    // cSimCharacter::BuildPose / BuildVel [E][n], cSimObj::GetPos / GetLinearVelocity [E][N][3]
+    virtual void GetState(std::vector<double>& pose, std::vector<double>& vel, std::vector<double>& body_pos,
+                          std::vector<double>& body_vel) = 0;
+    virtual void ApplyTau(const std::vector<double>& tau, double dt) = 0;              // ApplyControlForces + cWorld::Update(dt)
+    virtual void HasFallen(std::vector<unsigned char>& out_fallen) = 0;                // cSimCharacter::HasFallen
+    virtual double KinTime(int env) const { (void)env; return 0.0; }                   // clock of the kinematic reference
+};
+
+// cSimAdapter (simAdapter/SimAdapter.h:29-81, terrainRLAdapter.swig:1-44) for E characters at once: the same method names;
+// every std::vector<double> of the reference is the env-major concatenation over the E envs.
+class cBatchedSimAdapter {
+public:
+    // args: the reference's argv ("-arg_file=", "<file>", "-relative_file_path=", "<dir>/")
+    cBatchedSimAdapter(const std::vector<std::string>& args, int num_envs, cWorldHook* world, int device = 0)
+        : mArgs(args), mNumEnvs(num_envs), mDevice(device), mWorld(world) {}
+
+    bool init() {  // SimAdapter.cpp:40-253
+        std::string arg_file, rel;
+        for (size_t i = 0; i + 1 < mArgs.size(); ++i) {
+            if (mArgs[i].rfind("-arg_file=", 0) == 0) arg_file = mArgs[i + 1];
+            if (mArgs[i].rfind("-relative_file_path=", 0) == 0) rel = mArgs[i + 1];
+        }
+        if (arg_file.empty()) return false;
+        auto arg = [&](const char* key, const std::string& dflt) {
+            char buf[1024];
+            return trl_arg_file_get(arg_file.c_str(), key, buf, (int)sizeof(buf)) == TRL_OK ? std::string(buf) : dflt;
+        };
+        auto path = [&](const std::string& p) { return (p.empty() || p[0] == '/') ? p : rel + p; };
+        const std::string char_file = path(arg("character_file", "")), motion_file = path(arg("motion_file", ""));
+        if (char_file.empty() || !mModel.Init(char_file, motion_file)) return false;
+        mNumUpdateSteps = std::stoi(arg("num_update_steps", "20"));
+        const std::string ctrl = arg("char_ctrl", "");
+        trl_obs_cfg cfg{TRL_OBS_TERRAIN_RL, TRL_SAMPLER_LINE, 200, 0, -0.5, 10.0, -1};
+        if (ctrl.rfind("ct", 0) == 0) cfg = trl_obs_cfg{TRL_OBS_CT, TRL_SAMPLER_LINE, 0, 0, -0.5, 10.0, ctrl.find("phase") != std::string::npos ? 4 : -1};
+        else if (ctrl.rfind("biped3D", 0) == 0) cfg = trl_obs_cfg{TRL_OBS_TERRAIN_RL, TRL_SAMPLER_GRID, 256, 16, -1.0, 2.0, -1};
+        else if (ctrl.find("hopper") != std::string::npos) cfg.obs_kind = TRL_OBS_TERRAIN_RL_HOPPER;
+        mHasPhase = cfg.num_phase_bins >= 0;
+        if (!mBatch.Init(mModel, mNumEnvs, mDevice, &cfg)) return false;
+        mGround.Init(&mBatch);
+        const std::string terrain = path(arg("terrain_file", ""));
+        if (terrain.empty()) trl_terrain_default_cfg(&mGround.Params());
+        else if (!mGround.LoadParams(terrain, 0.0, std::stod(arg("world_scale", "1")))) return false;
+        const int F = mNumEnvs < 4096 ? mNumEnvs : 4096;
+        const bool is3d = mGround.Params().type == TRL_TERRAIN_VAR3D_FLAT;
+        const double half = is3d ? 10.0 : 0.5 * mGround.Params().ground_width, shift = is3d ? 0.0 : -1.0;
+        std::vector<unsigned long long> seeds((size_t)F);
+        std::vector<double> bmin((size_t)F * 3, 0.0), bmax((size_t)F * 3, 0.0);
+        for (int f = 0; f < F; ++f) {
+            seeds[f] = (unsigned long long)mSeed + 104729ULL * (unsigned long long)f + 1ULL;
+            bmin[3 * f] = -half + shift; bmax[3 * f] = half + shift;
+            if (is3d) { bmin[3 * f + 2] = -half; bmax[3 * f + 2] = half; }
+        }
+        if (!mGround.Build(F, seeds, bmin, bmax)) return false;
+        mPD.Init(&mBatch);
+        mCtrl.Init(&mBatch);
+        const size_t En = (size_t)mNumEnvs * mModel.GetNumDof();
+        mTarPose.assign(En, 0.0);
+        mTarVel.assign(En, 0.0);
+        initEpoch();
+        return true;
+    }
+    void initEpoch() {  // :255-260
+        mWorld->Reset(mNumEnvs);
+        mFrame = 0;
+        Pull();
+        mTarPose = mPose;  // default action: hold the current pose
+        const int n = mModel.GetNumDof();
+        for (int e = 0; e < mNumEnvs; ++e)
+            for (int i = 0; i < 7; ++i) mTarPose[(size_t)e * n + i] = 0.0;
+    }
+    bool update() {  // :262-268 + cScenarioSimChar::Update: num_update_steps control substeps per animation frame
+        const double dt = (1.0 / 30.0) / mNumUpdateSteps;
+        for (int s = 0; s < mNumUpdateSteps; ++s) {
+            Pull();
+            mTau.assign(mPose.size(), 0.0);  // cSimCharacter::ClearJointTorques
+            if (trl_imp_pd_update_control_force(mBatch.Handle(), dt, mPose.data(), mVel.data(), mTarPose.data(), mTarVel.data(),
+                                                nullptr, nullptr, nullptr, mTau.data(), nullptr, nullptr) != TRL_OK)
+                return false;
+            mWorld->ApplyTau(mTau, dt);
+        }
+        ++mFrame;
+        return true;
+    }
+    bool updateAction(const std::vector<double>& action) {  // :441-456: PD targets of the actuated dofs, [E][n - 7]
+        const int n = mModel.GetNumDof(), a = n - 7;
+        if (action.size() != (size_t)mNumEnvs * a) return false;
+        for (int e = 0; e < mNumEnvs; ++e)
+            for (int i = 0; i < a; ++i) mTarPose[(size_t)e * n + 7 + i] = action[(size_t)e * a + i];
+        return true;
+    }
+    void handleUpdatedAction() {}
+    std::vector<double> getState() {  // :493-508: ParseGround + BuildPoliState, [E][F]
+        Pull();
+        std::vector<double> state, phase;
+        const std::vector<double>* ph = nullptr;
+        if (mHasPhase) { phase.assign((size_t)mNumEnvs, std::fmod(mFrame * (1.0 / 30.0), 1.0)); ph = &phase; }
+        mCtrl.BuildPoliState(mPose, mVel, mBodyPos, mBodyVel, state, ph);
+        return state;
+    }
+    std::vector<double> calcReward() {  // cScenarioExpImitate::CalcReward vs the kinematic reference, [E]
+        Pull();
+        const int n = mModel.GetNumDof();
+        std::vector<double> t((size_t)mNumEnvs), kin_pose((size_t)mNumEnvs * n), kin_vel((size_t)mNumEnvs * n), reward((size_t)mNumEnvs, 0.0);
+        for (int e = 0; e < mNumEnvs; ++e) t[e] = mWorld->KinTime(e);
+        std::vector<unsigned char> fallen;
+        mWorld->HasFallen(fallen);
+        if (trl_kin_char_pose(mBatch.Handle(), t.data(), nullptr, nullptr, kin_pose.data(), kin_vel.data()) != TRL_OK) return reward;
+        trl_imitate_calc_reward(mBatch.Handle(), mPose.data(), mVel.data(), kin_pose.data(), kin_vel.data(), mBodyVel.data(),
+                                fallen.data(), reward.data(), nullptr);
+        return reward;
+    }
+    std::vector<unsigned char> agentHasFallen() {  // :458-465, [E]
+        std::vector<unsigned char> f;
+        mWorld->HasFallen(f);
+        return f;
+    }
+    bool needUpdatedAction() const { return true; }                       // :467-475 (policy query rate = 30 Hz)
+    size_t getActionSpaceSize() const { return (size_t)mModel.GetNumDof() - 7; }   // :477-483
+    size_t getObservationSpaceSize() const { return (size_t)trl_poli_state_size(mBatch.Handle()); }  // :485-491
+    void setRandomSeed(int seed) { mSeed = seed; }                         // :510-515
+    void finish() { mBatch.Clear(); mModel.Clear(); }
+    const std::vector<double>& tau() const { return mTau; }
+    cBatch& batch() { return mBatch; }
+
+private:
+    void Pull() { mWorld->GetState(mPose, mVel, mBodyPos, mBodyVel); }
+    std::vector<std::string> mArgs;
+    int mNumEnvs, mDevice, mNumUpdateSteps = 20, mFrame = 0, mSeed = 0;
+    bool mHasPhase = false;
+    cWorldHook* mWorld;
+    cCharModel mModel;
+    cBatch mBatch;
+    cGroundVar mGround;
+    cImpPDController mPD;
+    cTerrainRLCharController mCtrl;
+    std::vector<double> mPose, mVel, mBodyPos, mBodyVel, mTarPose, mTarVel, mTau;
 };
 
 }  // namespace trl

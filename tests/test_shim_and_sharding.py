@@ -49,6 +49,38 @@ def test_cpp_shim_runs_on_gpu(tmp_path):
     assert "ok sum|tau|" in r.stdout
 
 
+def _adapter_files(tmp_path):
+    """a two-joint character, a flat terrain file and the arg file that points at them (paths relative to tmp_path)"""
+    exe = str(tmp_path / "adapter_smoke")
+    build.build()
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "adapter_smoke.cpp"), "-o", exe,
+                           "-L", build.LIB_DIR, "-ltrl_b200", "-Wl,-rpath," + build.LIB_DIR])
+    os.makedirs(tmp_path / "data", exist_ok=True)
+    (tmp_path / "data" / "char.txt").write_text(json.dumps(CHAR))
+    (tmp_path / "data" / "terrain.txt").write_text(json.dumps({"Type": "var2d_gaps", "Params": [{"GapWMax": 1.0}]}))
+    (tmp_path / "args.txt").write_text("-character_file= data/char.txt\n-terrain_file= data/terrain.txt\n"
+                                       "-char_ctrl= dog\n-num_update_steps= 20\n-world_scale= 4\n")
+    return exe, str(tmp_path / "args.txt"), str(tmp_path) + "/"
+
+
+def test_cpp_batched_sim_adapter_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe, args, rel = _adapter_files(tmp_path)
+    r = subprocess.run([exe, args, rel, "8", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_batched_sim_adapter_runs_on_gpu(tmp_path):
+    exe, args, rel = _adapter_files(tmp_path)
+    r = subprocess.run([exe, args, rel, "8", "2", "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok obs=207" in r.stdout  # 200 ground samples + pose (2 N - 1 = 3) + vel (2 N = 4) for N = 2
+
+
 WORKER = r"""
 import os, sys, json
 import numpy as np
