@@ -289,3 +289,50 @@ def test_apply_control_forces_identities(oracle, name):
                 k = 1 if ty == 0 else (3 if ty == 4 else 0)
                 ref += small[o:o + k] @ qd[o:o + k]
             assert np.isclose(power, ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_stable_pd_solve_against_50_digit_arithmetic(oracle, name):
+    """an independent high-precision evaluation bounds the oracle's own rounding. Given the oracle's M, C and
+    error vectors (doubles), the solve (M + dt Kd) qdd = Kp e_p + Kd e_v - C and tau = Kp e_p + Kd (e_v - dt qdd) are
+    redone with mpmath at 50 digits for three poses per character; the oracle's pivoted LDLT in double must agree to 1e-11
+    relative (condition numbers of the bundled characters are ~1e3..1e5)."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    m0 = oracle.Model(name)
+    pd = m0.pd_params.copy()
+    pd[:, 17] = 0
+    m = oracle.Model(joint_mat=m0.joint_mat, body_defs=m0.body_defs, pd_params=pd)
+    x = _inputs(name, E=3)
+    dt = 1.0 / 600
+    for e in range(3):
+        pose, vel, tp, tv = x["pose"][e], x["vel"][e], x["tar_pose"][e], x["tar_vel"][e]
+        tau, M, C, _ = m.imp_pd(dt, pose, vel, tp, tv, x["joint_active"][e])
+        kp, kd, kd_diag = np.zeros(m.n), np.zeros(m.n), np.zeros(m.n)
+        for j in range(1, m.N):
+            o, s = int(m.offset[j]), int(m.size[j])
+            kd_diag[o:o + s] = m.pd_params[j, 2]
+            if x["joint_active"][e][j]:
+                kp[o:o + s], kd[o:o + s] = m.pd_params[j, 1], m.pd_params[j, 2]
+        pose_inc = m.post_process_pose(pose + dt * m.vel_to_pose_diff(pose, vel))
+        tpe = tp.copy()
+        tpe[:7] = 0
+        e_p = m.calc_vel(pose_inc, tpe, 1.0)
+        e_v = tv - vel
+        e_v[:7] = -vel[:7]
+        live = [i for i in range(m.n) if M[i, i] + dt * kd_diag[i] != 0]
+        A = mp.matrix(len(live), len(live))
+        b = mp.matrix(len(live), 1)
+        for r, i in enumerate(live):
+            b[r] = mp.mpf(kp[i]) * mp.mpf(e_p[i]) + mp.mpf(kd[i]) * mp.mpf(e_v[i]) - mp.mpf(C[i])
+            for c, k in enumerate(live):
+                A[r, c] = mp.mpf(M[i, k]) + (mp.mpf(dt) * mp.mpf(kd_diag[i]) if i == k else 0)
+        qdd = mp.lu_solve(A, b)
+        ref = np.zeros(m.n)
+        for r, i in enumerate(live):
+            ref[i] = float(mp.mpf(kp[i]) * mp.mpf(e_p[i]) + mp.mpf(kd[i]) * (mp.mpf(e_v[i]) - mp.mpf(dt) * qdd[r]))
+        for i in range(m.n):
+            if i not in live:
+                ref[i] = kp[i] * e_p[i] + kd[i] * e_v[i]
+        scale = max(1.0, np.abs(ref).max())
+        assert np.abs(tau - ref).max() <= 1e-11 * scale, (name, e, np.abs(tau - ref).max() / scale)
