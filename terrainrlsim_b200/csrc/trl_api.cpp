@@ -199,15 +199,9 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
     for (int i = 0; i < 3; ++i) {
-        static const int order = getenv("TRL_PRIO_ORDER") ? atoi(getenv("TRL_PRIO_ORDER")) : 1;  // tuning hook
-        const int mid = (prio_lo + prio_hi) / 2;
-        // side[0] = kin chain, side[1] = observation chain, side[2] = stable-PD chain
-        int prio = prio_lo;
-        if (i == 2) prio = prio_hi;                                    // stable PD: always highest
-        else if (order == 0) prio = (i == 0) ? mid : prio_lo;          // kin > obs
-        else if (order == 1) prio = (i == 1) ? mid : prio_lo;          // obs > kin
-        else if (order == 3) prio = (i == 0) ? prio_hi : prio_lo;      // kin = PD > obs
-        else if (order == 4) prio = (i == 0) ? prio_hi : mid;          // kin = PD > obs (mid)
+        // side[0] = kin chain (lowest), side[1] = observation chain (middle), side[2] = stable-PD chain (highest): the
+        // measured best of the orderings tried (profiles/README.md, round 1)
+        const int prio = (i == 2) ? prio_hi : (i == 1) ? (prio_lo + prio_hi) / 2 : prio_lo;
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side2[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
@@ -227,8 +221,6 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_bv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
-        static const int carve = getenv("TRL_CARVEOUT") ? atoi(getenv("TRL_CARVEOUT")) : -1;  // tuning hook, see trl_set_carveout
-        if (carve >= 0 && trl_set_carveout(carve) != 0) { trl_set_error("cudaFuncSetAttribute(carveout) failed"); return nullptr; }
         const char* ov = getenv("TRL_STEP_OVERLAP");  // tuning hook: 0 serialises the chains on one stream
         if (ov) b->overlap = atoi(ov) != 0;
     }
@@ -930,8 +922,18 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
     // uploads: stream 0 = pose / vel (+ the small arrays), 1 = PD targets, 2 = body states; download: one stream
     cudaStream_t s_up0 = b->up_streams[0], s_up1 = b->up_streams[1], s_up2 = b->up_streams[2], s_dn = b->side2[1];
     if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
-    for (cudaStream_t st : {sA, sB, sC, s_up0, s_up1, s_up2, s_dn}) cudaStreamWaitEvent(st, b->ev_fork, 0);
+    for (cudaStream_t st : {sA, sB, sC, s_up0, s_up1, s_up2, s_dn})
+        if (!cuda_ok(cudaStreamWaitEvent(st, b->ev_fork, 0), "cudaStreamWaitEvent")) return TRL_ERR_CUDA;
     int rc = 0;
+    // every event / dependency call is checked: the first failure is kept in rc and reported after the join
+    auto ev_rec = [&](cudaEvent_t ev, cudaStream_t st) {
+        const cudaError_t err = cudaEventRecord(ev, st);
+        if (err != cudaSuccess && !rc) rc = (int)err;
+    };
+    auto st_wait = [&](cudaStream_t st, cudaEvent_t ev) {
+        const cudaError_t err = cudaStreamWaitEvent(st, ev, 0);
+        if (err != cudaSuccess && !rc) rc = (int)err;
+    };
     cudaStream_t s_up = s_up0;
     auto up = [&](char* d, const void* h, size_t bpe, size_t e0, size_t ec) {
         if (d && !rc && cudaMemcpyAsync(d + e0 * bpe, static_cast<const char*>(h) + e0 * bpe, ec * bpe, cudaMemcpyHostToDevice, s_up) != cudaSuccess)
@@ -954,25 +956,25 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
         s_up = s_up0;
         up(d_pose, a->pose, n * 8, e0, ec);
         up(d_vel, a->vel, n * 8, e0, ec);
-        cudaEventRecord(b->ev_up[slice][0], s_up0);
+        ev_rec(b->ev_up[slice][0], s_up0);
         // submission order = service order on the copy engines: the observation chain's inputs go first (its [E][F]
         // state is 3/4 of the download, which is the long pole), the PD targets after them
         if (want_obs || want_reward) {
             s_up = s_up2;
             if (want_obs) up(d_bp, a->body_pos, N * 24, e0, ec);
             up(d_bv, a->body_vel, N * 24, e0, ec);
-            cudaEventRecord(b->ev_up[slice][2], s_up2);
+            ev_rec(b->ev_up[slice][2], s_up2);
         }
         if (want_pd) {
             s_up = s_up1;
             up(d_tp, a->tar_pose, n * 8, e0, ec);
             if (a->tar_vel) up(d_tv, a->tar_vel, n * 8, e0, ec);
-            cudaEventRecord(b->ev_up[slice][1], s_up1);
+            ev_rec(b->ev_up[slice][1], s_up1);
         }
         auto at = [&](char* d, size_t bpe) { return d ? d + e0 * bpe : nullptr; };
         if (!rc && want_obs) {
-            cudaStreamWaitEvent(sC, b->ev_up[slice][0], 0);
-            cudaStreamWaitEvent(sC, b->ev_up[slice][2], 0);
+            st_wait(sC, b->ev_up[slice][0]);
+            st_wait(sC, b->ev_up[slice][2]);
             DevGround g2 = b->ground;
             if (g2.env_to_field) g2.env_to_field += e0;
             rc = trl_launch_poli_state(b->d_model, b->model->dev, g2, b->cfg, b->F, (int)ec, (const double*)at(d_pose, n * 8),
@@ -985,16 +987,16 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
                 rc = trl_launch_f64_to_f32((const double*)at(d_st, F * 8), (float*)at(d_st32, F * 4), ec * F, sC);
                 b->launches += 1;
             }
-            cudaEventRecord(b->ev_cmp[slice][1], sC);
+            ev_rec(b->ev_cmp[slice][1], sC);
         }
         if (!rc && want_kin) {
-            cudaStreamWaitEvent(sB, b->ev_up[slice][0], 0);  // the small arrays went up ahead of slice 0 on stream 0
+            st_wait(sB, b->ev_up[slice][0]);  // the small arrays went up ahead of slice 0 on stream 0
             rc = trl_launch_kin(b->d_model, b->model->dev, b->d_frames, (int)ec, (const double*)at(d_time, 8),
                                 (const double*)at(d_op, 24), (const double*)at(d_or, 32), (double*)at(d_kp, n * 8),
                                 (double*)at(d_kv, n * 8), (double*)at(d_kbp, N * 24), sB);
             b->launches += 1;
             if (!rc && want_reward) {  // cScenarioExpImitate::CalcReward on the kin chain's stream: kin pose / vel never leave the device
-                cudaStreamWaitEvent(sB, b->ev_up[slice][2], 0);
+                st_wait(sB, b->ev_up[slice][2]);
                 DevGround g2 = b->ground;
                 if (g2.env_to_field) g2.env_to_field += e0;
                 rc = trl_launch_imitate_reward(b->d_model, b->model->dev, g2, (int)ec, (const double*)at(d_pose, n * 8),
@@ -1003,11 +1005,11 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
                                                (const unsigned char*)at(d_fallen, 1), (double*)at(d_rw, 8), nullptr, sB);
                 b->launches += 1;
             }
-            cudaEventRecord(b->ev_cmp[slice][0], sB);
+            ev_rec(b->ev_cmp[slice][0], sB);
         }
         if (!rc && want_pd) {
-            cudaStreamWaitEvent(sA, b->ev_up[slice][0], 0);
-            cudaStreamWaitEvent(sA, b->ev_up[slice][1], 0);
+            st_wait(sA, b->ev_up[slice][0]);
+            st_wait(sA, b->ev_up[slice][1]);
             if (a->dt > 0) {
                 StepPtrs p{};
                 p.dt = a->dt;
@@ -1022,41 +1024,41 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
             } else {
                 cudaMemsetAsync(at(d_tau, n * 8), 0, ec * n * 8, sA);
             }
-            cudaEventRecord(b->ev_cmp[slice][2], sA);
+            ev_rec(b->ev_cmp[slice][2], sA);
         }
         // downloads of this slice, in the order the chains finish
         if (!rc && want_kin) {
-            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][0], 0);
+            st_wait(s_dn, b->ev_cmp[slice][0]);
             down(a->out_kin_pose, d_kp, n * 8, e0, ec);
             down(a->out_kin_vel, d_kv, n * 8, e0, ec);
             down(a->out_kin_body_pos, d_kbp, N * 24, e0, ec);
             if (want_reward) down(o->out_reward, d_rw, 8, e0, ec);
         }
         if (!rc && want_obs) {
-            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][1], 0);
+            st_wait(s_dn, b->ev_cmp[slice][1]);
             down(a->out_state, d_st, F * 8, e0, ec);
             if (want_f32) down(o->out_state_f32, d_st32, F * 4, e0, ec);
         }
         if (!rc && want_pd) {
-            cudaStreamWaitEvent(s_dn, b->ev_cmp[slice][2], 0);
+            st_wait(s_dn, b->ev_cmp[slice][2]);
             down(a->out_tau, d_tau, n * 8, e0, ec);
         }
     }
     {   // join everything back into the caller's stream (also on error, so the streams stay consistent)
         int k = 0;
         for (cudaStream_t st : {sB, sC, sA}) {
-            cudaEventRecord(b->ev_join[k], st);
-            cudaStreamWaitEvent(b->stream, b->ev_join[k], 0);
+            ev_rec(b->ev_join[k], st);
+            st_wait(b->stream, b->ev_join[k]);
             ++k;
         }
-        cudaEventRecord(b->ev_join2[0], s_up0);
-        cudaStreamWaitEvent(b->stream, b->ev_join2[0], 0);
-        cudaEventRecord(b->ev_join2[1], s_dn);
-        cudaStreamWaitEvent(b->stream, b->ev_join2[1], 0);
-        cudaEventRecord(b->ev_join2[2], s_up1);
-        cudaStreamWaitEvent(b->stream, b->ev_join2[2], 0);
-        cudaEventRecord(b->ev_pv2, s_up2);
-        cudaStreamWaitEvent(b->stream, b->ev_pv2, 0);
+        ev_rec(b->ev_join2[0], s_up0);
+        st_wait(b->stream, b->ev_join2[0]);
+        ev_rec(b->ev_join2[1], s_dn);
+        st_wait(b->stream, b->ev_join2[1]);
+        ev_rec(b->ev_join2[2], s_up1);
+        st_wait(b->stream, b->ev_join2[2]);
+        ev_rec(b->ev_pv2, s_up2);
+        st_wait(b->stream, b->ev_pv2);
     }
     if (rc) {
         cudaStreamSynchronize(b->stream);
@@ -1100,13 +1102,22 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
     // onto the batch's side streams (A on the high-priority one) and join the caller's stream before returning. In HOST pointer mode every chain also
     // stages its own inputs and copies its own outputs back on its stream, so H2D, kernels and D2H of different
     // chains overlap (the observation chain, whose [E][F] state is the largest transfer, goes first).
+    int dep_rc = 0;  // first failure of an event / dependency call (reported with the launch status)
+    auto ev_rec = [&](cudaEvent_t ev, cudaStream_t st) {
+        const cudaError_t err = cudaEventRecord(ev, st);
+        if (err != cudaSuccess && !dep_rc) dep_rc = (int)err;
+    };
+    auto st_wait = [&](cudaStream_t st, cudaEvent_t ev) {
+        const cudaError_t err = cudaStreamWaitEvent(st, ev, 0);
+        if (err != cudaSuccess && !dep_rc) dep_rc = (int)err;
+    };
     const bool fork = b->overlap && ((want_pd ? 1 : 0) + (want_kin ? 1 : 0) + (want_obs ? 1 : 0)) > 1;
     cudaStream_t sA = b->stream, sB = b->stream, sC = b->stream;
     if (fork) {
         if (!cuda_ok(cudaEventRecord(b->ev_fork, b->stream), "cudaEventRecord")) return TRL_ERR_CUDA;
-        if (want_kin && (want_pd || want_obs)) { sB = b->side[0]; cudaStreamWaitEvent(sB, b->ev_fork, 0); }
-        if (want_obs && want_pd) { sC = b->side[1]; cudaStreamWaitEvent(sC, b->ev_fork, 0); }
-        if (want_pd) { sA = b->side[2]; cudaStreamWaitEvent(sA, b->ev_fork, 0); }
+        if (want_kin && (want_pd || want_obs)) { sB = b->side[0]; st_wait(sB, b->ev_fork); }
+        if (want_obs && want_pd) { sC = b->side[1]; st_wait(sC, b->ev_fork); }
+        if (want_pd) { sA = b->side[2]; st_wait(sA, b->ev_fork); }
     }
     const double *d_time = nullptr, *d_op = nullptr, *d_or = nullptr, *d_bp = nullptr, *d_bv = nullptr, *d_ph = nullptr;
     const unsigned char *d_fl = nullptr, *d_fallen = nullptr;
@@ -1119,8 +1130,8 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
     const cudaStream_t s_pv = want_obs ? sC : sA;
     ok = ok && in_ptr(b, a->pose, E * n, &p.pose, s_pv) && in_ptr(b, a->vel, E * n, &p.vel, s_pv);
     if (ok && fork && s_pv != sA && b->ptr_mode == TRL_PTR_HOST) {
-        cudaEventRecord(b->ev_pv, s_pv);
-        cudaStreamWaitEvent(sA, b->ev_pv, 0);
+        ev_rec(b->ev_pv, s_pv);
+        st_wait(sA, b->ev_pv);
     }
     if (want_obs) {
         ok = ok && in_ptr(b, a->body_pos, E * N * 3, &d_bp, sC) && in_ptr(b, a->body_vel, E * N * 3, &d_bv, sC) &&
@@ -1148,8 +1159,8 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
         if (!a->tar_vel) p.tar_vel = b->d_zero_nvec;  // the reference's default target velocity
     }
     if (ok && want_reward && fork && b->ptr_mode == TRL_PTR_HOST) {  // the reward reads pose / vel / body_vel staged on other streams
-        if (s_pv != sB) { cudaEventRecord(b->ev_pv2, s_pv); cudaStreamWaitEvent(sB, b->ev_pv2, 0); }
-        if (want_obs && sC != sB) { cudaEventRecord(b->ev_bv, sC); cudaStreamWaitEvent(sB, b->ev_bv, 0); }
+        if (s_pv != sB) { ev_rec(b->ev_pv2, s_pv); st_wait(sB, b->ev_pv2); }
+        if (want_obs && sC != sB) { ev_rec(b->ev_bv, sC); st_wait(sB, b->ev_bv); }
     }
     int rc = ok ? 0 : (int)cudaErrorMemoryAllocation;
     auto launch_obs = [&]() {
@@ -1187,11 +1198,7 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
         // Submission order of the three chains (block-scheduling priority is per stream, see trl_batch_create). The
         // observation chain goes first: its first kernel gates the step's widest one (k_obs_samples). Measured per step:
         // obs-pd-kin 0.1027 ms, pd-obs-kin 0.1051, obs-kin-pd 0.1045, kin-obs-pd 0.1047.
-        static const int lo = getenv("TRL_LAUNCH_ORDER") ? atoi(getenv("TRL_LAUNCH_ORDER")) : 1;  // tuning hook
-        if (lo == 0) { launch_pd(); launch_obs(); launch_kin(); }
-        else if (lo == 2) { launch_obs(); launch_kin(); launch_pd(); }
-        else if (lo == 3) { launch_kin(); launch_obs(); launch_pd(); }
-        else { launch_obs(); launch_pd(); launch_kin(); }
+        launch_obs(); launch_pd(); launch_kin();
     }
     if (!rc && b->ptr_mode == TRL_PTR_HOST) {  // copy every chain's outputs back on its own stream
         for (auto& c : copies)
@@ -1199,11 +1206,11 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
         copies.clear();
     }
     if (fork) {  // join (also on error, so the streams stay consistent / a capture stays closed)
-        if (sB != b->stream) { cudaEventRecord(b->ev_join[0], sB); cudaStreamWaitEvent(b->stream, b->ev_join[0], 0); }
-        if (sC != b->stream) { cudaEventRecord(b->ev_join[1], sC); cudaStreamWaitEvent(b->stream, b->ev_join[1], 0); }
-        if (sA != b->stream) { cudaEventRecord(b->ev_join[2], sA); cudaStreamWaitEvent(b->stream, b->ev_join[2], 0); }
+        if (sB != b->stream) { ev_rec(b->ev_join[0], sB); st_wait(b->stream, b->ev_join[0]); }
+        if (sC != b->stream) { ev_rec(b->ev_join[1], sC); st_wait(b->stream, b->ev_join[1]); }
+        if (sA != b->stream) { ev_rec(b->ev_join[2], sA); st_wait(b->stream, b->ev_join[2]); }
     }
-    return finish(b, copies, rc);
+    return finish(b, copies, rc ? rc : dep_rc);
 }
 
 extern "C" int trl_imitate_calc_reward(trl_batch* b, const double* pose, const double* vel, const double* kin_pose,

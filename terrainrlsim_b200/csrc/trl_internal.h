@@ -187,7 +187,6 @@ struct StepPtrs {
     int* status;
 };
 
-int trl_set_carveout(int percent);
 int trl_trace_enable(int on);
 int trl_trace_read(unsigned long long* out32);
 size_t trl_pd_scratch_doubles(const DevModel& hm);

@@ -59,74 +59,7 @@ constexpr int kWarpsPerBlock = 4;
 constexpr int kCst = 21;  // per-joint double constants staged per block by k_imp_pd
 __host__ __device__ inline int pd_cst_doubles(int N) { return (kCst * N + 1) & ~1; }
 
-// shared-memory workspace layout (in doubles) of k_imp_pd, per env. The PD vectors (ep, ev, kpm, kdm, kdu: 5n)
-// alias the transform arrays Tl/T0 (24N >= 5n), which are dead by the time the PD errors are formed.
-struct PdLayout {
-    int q, qd, Tl, T0, Rq, g0, cj, sj, V, A, IF, S, C, ep, ev, kpm, kdm, kdu, x, H, ldh, total;
-};
-
-__host__ __device__ inline PdLayout pd_layout(int N, int n, int nl, int nlmax, bool split = false) {
-    // Lifetimes: Tl (P1-P2) | IF (P5-P7) share one region; sj, V, A (P3-P5) | ep, ev, kpm, kdm, kdu (P8-P10) share
-    // another; T0 lives P1-P7 (the joint-subspace columns are recomputed from it on the fly, never stored).
-    PdLayout L;
-    int o = 0;
-    L.q = o; o += n;
-    L.qd = o; o += n;
-    L.T0 = o; o += 12 * N;
-    L.Rq = o; o += 9;
-    L.g0 = o; o += 3;
-    L.cj = o; o += 3;
-    {
-        int a = o;
-        L.sj = a; a += 6 * N;
-        L.V = a; a += 6 * N;
-        L.A = a; a += 6 * N;
-        int b = o;
-        L.ep = b; b += n;
-        L.ev = b; b += n;
-        L.kpm = b; b += n;
-        L.kdm = b; b += n;
-        L.kdu = b; b += n;
-        o = a > b ? a : b;
-    }
-    L.Tl = o;
-    L.IF = o; o += 16 * N;
-    L.S = 0;  // unused
-    L.C = o; o += nl;
-    const int rows = nlmax > 0 ? nlmax : nl;
-    L.ldh = rows | 1;  // odd row stride: conflict-free column loads / row-per-lane access
-    if (split) {  // H / rhs go to the global scratch; only the diagonal is stashed (x = Hd)
-        L.x = o; o += nl;
-        L.H = o;
-    } else {
-        L.x = o; o += rows;
-        L.H = o; o += rows * L.ldh + (nlmax > 0 ? 32 : 0);  // + slack: lanes >= NLMAX read (and ignore) past the last row
-    }
-    L.total = (o + 1) & ~1;
-    return L;
-}
-
-// global scratch handed from k_imp_pd<.., SPLIT> to the solve kernel. Tiles of 32 envs, structure-of-arrays inside a
-// tile: element `idx` of env e lives at scratch[((e / 32) * stride + idx) * 32 + e % 32], so the solve kernel (one
-// thread per env) reads it with fully coalesced loads / one bulk copy per tile. Per env (doubles):
-//   [Hp: nl(nl+1)/2 row-packed lower triangle of M + dt*Kd][rhs: nl][t0: n][t1: n]   tau_i = t0_i - t1_i * qdd_col(i)
 constexpr int kTile = 32;
-//   [S: 6 nl joint-subspace columns][F: 6 nl force columns F_c = Ic S_c]   (k_pd_tree -> k_pd_h: H[c][a] = F_c . S_a)
-struct PdScratch { int np, rhs, t0, t1, scol, fcol, stride; };
-__host__ __device__ inline PdScratch pd_scratch(int n, int nl) {
-    PdScratch s;
-    s.np = nl * (nl + 1) / 2;
-    s.rhs = s.np;
-    s.t0 = s.rhs + nl;
-    s.t1 = s.t0 + n;
-    s.scol = s.t1 + n;
-    s.fcol = s.scol + 6 * nl;
-    s.stride = (s.fcol + 6 * nl + 1) & ~1;
-    return s;
-}
-// entry (i, j), i >= j, of the row-packed lower triangle
-__host__ __device__ constexpr int pd_tri(int i, int j, int /*nl*/ = 0) { return i * (i + 1) / 2 + j; }
-
 // Column c of the joint subspace S in the root frame (cRBDUtil::BuildJointSubspace*, sim/RBDUtil.cpp:733-828),
 // recomputed from the joint's root-frame transform wherever it is needed instead of being stored.
 TRL_DEV void subspace_col(const ModelIdx* X, const double* T0, const double* Rq, int c, double* s) {
@@ -173,21 +106,7 @@ TRL_DEV void compose_levels(const DevModel* __restrict__ M, const ModelIdx* X, c
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// LDL^T + solve, register-resident: lane j owns column j (= row j, the matrix is kept fully symmetric) of the
-// n x n system in NLMAX registers; step k broadcasts column k with shuffles. Rows/columns >= nl are identity
-// padding, so the fully unrolled code needs no bounds checks. No pivoting: M + dt*Kd is SPD on the live dofs
-// (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot zeroes that solution component like
-// Eigen's pseudo-inverse of D does.
-// ------------------------------------------------------------------------------------------------
-// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
-template <int I, int N, typename F>
-TRL_DEV void static_for(F&& f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
+TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 TRL_DEV double fast_rcp(double d) {
     double r;
@@ -199,549 +118,6 @@ TRL_DEV double fast_rcp(double d) {
     return r;
 }
 
-// Core: a[] = column `lane` of the symmetric system (identity-padded to NLMAX), b = rhs[lane]. Returns x[lane].
-template <int NLMAX>
-TRL_DEV double ldlt_regs_core(double (&a)[NLMAX], double b, int lane, int& bad) {
-    double rdiag = 0.0;
-#pragma unroll
-    for (int k = 0; k < NLMAX; ++k) {
-        const double d = __shfl_sync(0xffffffffu, a[k], k);
-        const bool ok = fabs(d) > DBL_MIN;
-        if (!(d > DBL_MIN)) bad |= 2;
-        const double r = ok ? fast_rcp(d) : 0.0;
-        if (lane == k) rdiag = r;
-        const double c = (lane > k && lane < NLMAX) ? a[k] * r : 0.0;  // L[lane][k]; 0 keeps columns <= k untouched
-#pragma unroll
-        for (int i = k + 1; i < NLMAX; ++i) {
-            const double t = __shfl_sync(0xffffffffu, a[i], k);  // A[i][k] = L[i][k] d_k
-            a[i] = fma(-t, c, a[i]);
-        }
-    }
-    // forward: L y = b  (lane i: b -= (L[i][k] d_k) * (y_k / d_k))
-#pragma unroll
-    for (int k = 0; k < NLMAX; ++k) {
-        const double zk = __shfl_sync(0xffffffffu, b * rdiag, k);
-        const double ak = (lane > k) ? a[k] : 0.0;
-        b = fma(-ak, zk, b);
-    }
-    // backward: L^T x = D^-1 y  (lane k: x_k = z_k - (1/d_k) sum_{i>k} (L[i][k] d_k) x_i)
-    const double z = b * rdiag;
-    double acc = 0.0;
-#pragma unroll
-    for (int i = NLMAX - 1; i >= 0; --i) {
-        const double xi = __shfl_sync(0xffffffffu, fma(-rdiag, acc, z), i);
-        const double ai = (lane < i) ? a[i] : 0.0;
-        acc = fma(ai, xi, acc);
-    }
-    return fma(-rdiag, acc, z);
-}
-
-template <int NLMAX>
-TRL_DEV int ldlt_solve_regs(const double* H, int ldh, double* x, int nl, int lane) {
-    double a[NLMAX];
-    // H is NLMAX x NLMAX with identity padding beyond nl (prepared by the caller); lanes >= NLMAX read slack
-#pragma unroll
-    for (int i = 0; i < NLMAX; ++i) a[i] = H[i * ldh + lane];
-    const double b = (lane < NLMAX) ? x[lane] : 0.0;
-    int bad = 0;
-    const double xv = ldlt_regs_core<NLMAX>(a, b, lane, bad);
-    if (lane < nl) x[lane] = xv;
-    return bad;
-}
-
-// generic shared-memory fallback (any nl <= 64): left-looking; lower = L, upper = L*D, diagonal = D
-TRL_DEV int ldlt_solve_smem(double* H, int ldh, double* x, int nl, int lane) {
-    int bad = 0;
-    for (int k = 0; k < nl; ++k) {
-        double v0 = 0.0, v1 = 0.0;
-        const int i0 = k + lane, i1 = k + lane + 32;
-        if (i0 < nl) {
-            v0 = H[i0 * ldh + k];
-            for (int qq = 0; qq < k; ++qq) v0 -= H[i0 * ldh + qq] * H[qq * ldh + k];
-        }
-        if (i1 < nl) {
-            v1 = H[i1 * ldh + k];
-            for (int qq = 0; qq < k; ++qq) v1 -= H[i1 * ldh + qq] * H[qq * ldh + k];
-        }
-        const double d = __shfl_sync(0xffffffffu, v0, 0);
-        const bool ok = fabs(d) > DBL_MIN;
-        if (!(d > DBL_MIN)) bad |= 2;
-        const double rd = ok ? 1.0 / d : 0.0;
-        __syncwarp();
-        if (i0 < nl) {
-            if (lane == 0) {
-                H[k * ldh + k] = d;
-            } else {
-                H[k * ldh + i0] = ok ? v0 : 0.0;
-                H[i0 * ldh + k] = v0 * rd;
-            }
-        }
-        if (i1 < nl) {
-            H[k * ldh + i1] = ok ? v1 : 0.0;
-            H[i1 * ldh + k] = v1 * rd;
-        }
-        __syncwarp();
-    }
-    for (int k = 0; k < nl; ++k) {  // forward substitution L y = b
-        const double yk = x[k];
-        for (int i = k + 1 + lane; i < nl; i += 32) x[i] -= H[i * ldh + k] * yk;
-        __syncwarp();
-    }
-    for (int i = lane; i < nl; i += 32) {  // D^-1 (zero pivot => 0, Eigen's pseudo-inverse of D)
-        const double d = H[i * ldh + i];
-        x[i] = (fabs(d) > DBL_MIN) ? x[i] / d : 0.0;
-    }
-    __syncwarp();
-    for (int k = nl - 1; k >= 0; --k) {  // backward substitution L^T x = z
-        const double xk = x[k];
-        for (int i = lane; i < k; i += 32) x[i] -= H[k * ldh + i] * xk;
-        __syncwarp();
-    }
-    return bad;
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_imp_pd: stable-PD torques (and optionally M, C) -- one warp per env
-// ------------------------------------------------------------------------------------------------
-// G = lanes per env (32 / G envs share a warp; G >= N so one lane owns one joint in the per-joint phases).
-// NLMAX > 0: register-resident LDL^T for nl <= NLMAX <= 32; NLMAX == 0: shared-memory fallback (G = 32 only).
-// SPLIT: stop after assembling the system and write it to the global scratch (k_pd_solve finishes the step).
-template <int G, int NLMAX, bool SPLIT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, TRL_PD_MIN_BLOCKS)
-k_imp_pd(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
-    KTrace trace_(TR_IMP_PD);
-    extern __shared__ double smem[];
-    __shared__ ModelIdx s_ix;
-    {   // per-joint double constants (DevModel::pd_cst, packed on the host): one coalesced copy
-        const int cnt = M->N * kCst;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
-    }
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    constexpr int EPW = 32 / G;  // envs per warp
-    const int wlane = threadIdx.x & 31;
-    const int lane = wlane % G;  // lane within the env's group
-    const int sub = wlane / G;
-    const int warp = threadIdx.x >> 5;
-    const int wpb = blockDim.x >> 5;  // warps per block: chosen by the launcher to maximise resident warps
-    const int e_raw = (blockIdx.x * wpb + warp) * EPW + sub;
-    if ((blockIdx.x * wpb + warp) * EPW >= E) return;  // whole warp idle
-    const bool env_ok = e_raw < E;
-    const int e = env_ok ? e_raw : E - 1;  // tail groups recompute the last env and store nothing
-    const int N = M->N, n = M->n, nl = M->nl;
-    const PdLayout L = pd_layout(N, n, nl, NLMAX, SPLIT);
-    const PdScratch SC = pd_scratch(n, nl);
-    double* sc = SPLIT ? scratch + ((size_t)(e / kTile) * SC.stride * kTile + (e % kTile)) : nullptr;  // element idx: sc[idx * kTile]
-    const double* cst = smem;  // per-joint constants (kCst doubles each), staged at kernel entry
-    double* ws = smem + pd_cst_doubles(N) + (size_t)(warp * EPW + sub) * L.total;
-    double* q = ws + L.q;
-    double* qd = ws + L.qd;
-    double* Tl = ws + L.Tl;
-    double* T0 = ws + L.T0;
-    double* Rq = ws + L.Rq;
-    double* g0 = ws + L.g0;
-    double* cj = ws + L.cj;
-    double* sj = ws + L.sj;
-    double* V = ws + L.V;
-    double* A = ws + L.A;
-    double* IF = ws + L.IF;
-    double* C = ws + L.C;
-    double* ep = ws + L.ep;
-    double* ev = ws + L.ev;
-    double* kpm = ws + L.kpm;
-    double* kdm = ws + L.kdm;
-    double* kdu = ws + L.kdu;
-    double* x = ws + L.x;
-    double* H = ws + L.H;
-    const int ldh = L.ldh;
-    const double dt = p.dt;
-
-    // P0: stage pose / vel (coalesced); H = 0 with identity padding beyond nl. The PD targets are only needed in P8:
-    // pull their cache lines towards L2 now so that the late loads do not pay a full HBM round trip.
-    for (int i = lane; i < n; i += G) {
-        q[i] = p.pose[(size_t)e * n + i];
-        qd[i] = p.vel[(size_t)e * n + i];
-    }
-    for (int off = lane * 128; off < n * 8; off += G * 128) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(p.tar_pose + (size_t)e * n) + off));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(p.tar_vel + (size_t)e * n) + off));
-    }
-    const int hrows = NLMAX > 0 ? NLMAX : nl;
-    if (!SPLIT) {
-        for (int i = lane; i < hrows * ldh; i += G) H[i] = 0.0;
-        for (int i = lane; i < hrows; i += G) x[i] = 0.0;
-    } else if (p.out_mass && env_ok) {
-        double* om = p.out_mass + (size_t)e * n * n;
-        for (int idx = lane; idx < n * n; idx += G) om[idx] = 0.0;
-    }
-    __syncwarp();
-    if (!SPLIT)
-        for (int r = nl + lane; r < hrows; r += G) H[r * ldh + r] = 1.0;  // identity padding (ordered by the next sync)
-
-    // P1: joint-local transforms; the root lane also prepares R(q_root), gravity and c_root in the root frame
-    if (lane < N) {
-        const int j = lane;
-        double R[9], t[3];
-        if (j == 0) {
-            double Rw[9], tw[3];
-            joint_local_trans(X, 0, q, cst, cst + 9, Rw, tw);  // world <- root (A*T*R)
-            double rq[9];
-            quat_to_mat(q[3], q[4], q[5], q[6], rq);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rq[i] = rq[i];
-            // a_0 = X_{world->root}(0, -g): E = Rw^T  (RBDUtil.cpp:17-18,59-60)
-            const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
-            double gg[3];
-            mat3T_mulv(Rw, ng, gg);
-            g0[0] = gg[0]; g0[1] = gg[1]; g0[2] = gg[2];
-            // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
-            double dq[4];
-            quat_diff_mul(q + 3, qd + 3, dq);
-            const double qw = q[3], qx = q[4], qy = q[5], qz = q[6];
-            const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
-            double m00 = 4 * (qw * dw + qx * dx), m11 = 4 * (qw * dw + qy * dy), m22 = 4 * (qw * dw + qz * dz);
-            double m10 = 2 * (dx * qy + qx * dy - dw * qz - qw * dz);
-            double m01 = 2 * (dx * qy + qx * dy + dw * qz + qw * dz);
-            double m20 = 2 * (dx * qz + qx * dz + dw * qy + qw * dy);
-            double m02 = 2 * (dx * qz + qx * dz - dw * qy - qw * dy);
-            double m21 = 2 * (dy * qz + qy * dz - dw * qx - qw * dx);
-            double m12 = 2 * (dy * qz + qy * dz + dw * qx + qw * dx);
-            cj[0] = m00 * qd[0] + m01 * qd[1] + m02 * qd[2];
-            cj[1] = m10 * qd[0] + m11 * qd[1] + m12 * qd[2];
-            cj[2] = m20 * qd[0] + m21 * qd[1] + m22 * qd[2];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-            t[0] = t[1] = t[2] = 0.0;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) T0[i] = R[i];
-            T0[9] = T0[10] = T0[11] = 0.0;
-        } else {
-            joint_local_trans(X, j, q + X->offset[j], cst + kCst * j, cst + kCst * j + 9, R, t);
-        }
-#pragma unroll
-        for (int i = 0; i < 9; ++i) Tl[12 * j + i] = R[i];
-        Tl[12 * j + 9] = t[0]; Tl[12 * j + 10] = t[1]; Tl[12 * j + 11] = t[2];
-    }
-    __syncwarp();
-
-    // P2: root-frame transforms
-    compose_levels(M, X, Tl, T0, lane, 1, G);
-
-    // P3: s_j = S_j qd_j in the root frame (columns recomputed from T0)
-    if (lane < N) {
-        const int j = lane;
-        double s[6] = {0, 0, 0, 0, 0, 0};
-        const int c0 = X->first_col[j], nc = X->ncol[j];
-        for (int c = c0; c < c0 + nc; ++c) {
-            const double w = qd[X->col_dof[c]];
-            double sc6[6];
-            subspace_col(X, T0, Rq, c, sc6);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
-        }
-#pragma unroll
-        for (int k = 0; k < 6; ++k) sj[6 * j + k] = s[k];
-        if (j == 0) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) V[k] = s[k];
-            A[0] = A[1] = A[2] = 0.0;
-            A[3] = g0[0] + cj[0]; A[4] = g0[1] + cj[1]; A[5] = g0[2] + cj[2];
-        }
-    }
-    __syncwarp();
-
-    // P4: V_j = V_p + s_j ; a_j = a_p + V_p x s_j (motion cross product; V_j x s_j = V_p x s_j)
-    for (int lv = 1; lv < M->num_levels; ++lv) {
-        const int beg = X->level_start[lv];
-        const int cnt = X->level_start[lv + 1] - beg;
-        for (int it = lane; it < cnt * 6; it += G) {
-            const int j = X->level_joint[beg + it / 6];
-            const int k = it % 6;
-            const int pj = X->parent[j];
-            const double* Vp = V + 6 * pj;
-            const double* s = sj + 6 * j;
-            const int i0 = k % 3, i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
-            double cr;
-            if (k < 3) {
-                cr = Vp[i1] * s[i2] - Vp[i2] * s[i1];
-            } else {
-                cr = (Vp[3 + i1] * s[i2] - Vp[3 + i2] * s[i1]) + (Vp[i1] * s[3 + i2] - Vp[i2] * s[3 + i1]);
-            }
-            V[6 * j + k] = Vp[k] + s[k];
-            A[6 * j + k] = A[6 * pj + k] + cr;
-        }
-        __syncwarp();
-    }
-
-    // P5: body inertia in the root frame (m, h = m c, I about the frame origin) and f = I a + V x* (I V)
-    if (lane < N) {
-        const int j = lane;
-        double I[10];
-        double f[6] = {0, 0, 0, 0, 0, 0};
-        if (X->valid_body[j]) {
-            const double* T = T0 + 12 * j;
-            const double* cj_ = cst + kCst * j;
-            const double m = cj_[12];
-            double c[3];
-            mat3_mulv(T, cj_ + 13, c);
-            c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
-            const double d0 = cj_[16], d1 = cj_[17], d2 = cj_[18];
-            // R diag R^T
-            double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
-            double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
-            double Ixz = T[0] * T[6] * d0 + T[1] * T[7] * d1 + T[2] * T[8] * d2;
-            double Iyy = T[3] * T[3] * d0 + T[4] * T[4] * d1 + T[5] * T[5] * d2;
-            double Iyz = T[3] * T[6] * d0 + T[4] * T[7] * d1 + T[5] * T[8] * d2;
-            double Izz = T[6] * T[6] * d0 + T[7] * T[7] * d1 + T[8] * T[8] * d2;
-            // parallel axis: + m (|c|^2 1 - c c^T)
-            Ixx += m * (c[1] * c[1] + c[2] * c[2]);
-            Iyy += m * (c[0] * c[0] + c[2] * c[2]);
-            Izz += m * (c[0] * c[0] + c[1] * c[1]);
-            Ixy -= m * c[0] * c[1];
-            Ixz -= m * c[0] * c[2];
-            Iyz -= m * c[1] * c[2];
-            I[0] = m; I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
-            I[4] = Ixx; I[5] = Ixy; I[6] = Ixz; I[7] = Iyy; I[8] = Iyz; I[9] = Izz;
-            const double* Vj = V + 6 * j;
-            const double* Aj = A + 6 * j;
-            const double* h = I + 1;
-            // I * a
-            double hxv[3], hxw[3];
-            cross3(h, Aj + 3, hxv);
-            cross3(h, Aj, hxw);
-            double na[3] = {Ixx * Aj[0] + Ixy * Aj[1] + Ixz * Aj[2] + hxv[0], Ixy * Aj[0] + Iyy * Aj[1] + Iyz * Aj[2] + hxv[1],
-                            Ixz * Aj[0] + Iyz * Aj[1] + Izz * Aj[2] + hxv[2]};
-            double fa[3] = {m * Aj[3] - hxw[0], m * Aj[4] - hxw[1], m * Aj[5] - hxw[2]};
-            // I * V
-            cross3(h, Vj + 3, hxv);
-            cross3(h, Vj, hxw);
-            double nv[3] = {Ixx * Vj[0] + Ixy * Vj[1] + Ixz * Vj[2] + hxv[0], Ixy * Vj[0] + Iyy * Vj[1] + Iyz * Vj[2] + hxv[1],
-                            Ixz * Vj[0] + Iyz * Vj[1] + Izz * Vj[2] + hxv[2]};
-            double fv[3] = {m * Vj[3] - hxw[0], m * Vj[4] - hxw[1], m * Vj[5] - hxw[2]};
-            // V x* (I V) = (w x n + v x f ; w x f)
-            double wxn[3], vxf[3], wxf[3];
-            cross3(Vj, nv, wxn);
-            cross3(Vj + 3, fv, vxf);
-            cross3(Vj, fv, wxf);
-            f[0] = na[0] + wxn[0] + vxf[0]; f[1] = na[1] + wxn[1] + vxf[1]; f[2] = na[2] + wxn[2] + vxf[2];
-            f[3] = fa[0] + wxf[0]; f[4] = fa[1] + wxf[1]; f[5] = fa[2] + wxf[2];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 10; ++i) I[i] = 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < 10; ++i) IF[16 * j + i] = I[i];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) IF[16 * j + 10 + i] = f[i];
-    }
-    __syncwarp();
-
-    // P6: subtree sums, leaves -> root (joints are ordered parents-first, anim/KinTree.cpp:479-493)
-    for (int j = N - 1; j >= 1; --j) {
-        for (int c = lane; c < 16; c += G) IF[16 * X->parent[j] + c] += IF[16 * j + c];
-        __syncwarp();
-    }
-
-    // P7: F_c = Ic_j S_c ; C_c = S_c . f_subtree ; H[c][c'] = F_c . S_c' along the ancestor chain
-    for (int c = lane; c < nl; c += G) {
-        const int j = X->col_joint[c];
-        const double* I = IF + 16 * j;
-        double s[6];
-        subspace_col(X, T0, Rq, c, s);
-        const double m = I[0];
-        const double* h = I + 1;
-        double hxv[3], hxw[3];
-        cross3(h, s + 3, hxv);
-        cross3(h, s, hxw);
-        double Fc[6];
-        Fc[0] = I[4] * s[0] + I[5] * s[1] + I[6] * s[2] + hxv[0];
-        Fc[1] = I[5] * s[0] + I[7] * s[1] + I[8] * s[2] + hxv[1];
-        Fc[2] = I[6] * s[0] + I[8] * s[1] + I[9] * s[2] + hxv[2];
-        Fc[3] = m * s[3] - hxw[0];
-        Fc[4] = m * s[4] - hxw[1];
-        Fc[5] = m * s[5] - hxw[2];
-        const double* f = I + 10;
-        C[c] = s[0] * f[0] + s[1] * f[1] + s[2] * f[2] + s[3] * f[3] + s[4] * f[4] + s[5] * f[5];
-        for (int a = c; a >= 0; a = X->col_parent[a]) {
-            double sa[6];
-            subspace_col(X, T0, Rq, a, sa);
-            const double hv = Fc[0] * sa[0] + Fc[1] * sa[1] + Fc[2] * sa[2] + Fc[3] * sa[3] + Fc[4] * sa[4] + Fc[5] * sa[5];
-            if (SPLIT) {
-                if (a == c) x[c] = hv;  // diagonal stash: dt*Kd is added once the gains are known (P8)
-                else if (env_ok) sc[pd_tri(c, a, nl) * kTile] = hv;
-            } else {
-                H[c * ldh + a] = hv;
-                H[a * ldh + c] = hv;
-            }
-        }
-    }
-    __syncwarp();
-
-    // optional outputs: cRBDModel::GetMassMat / GetBiasForce on the full n-dof layout (dead dofs are exact zeros)
-    if (SPLIT && p.out_mass && env_ok) {  // rare path (GetMassMat): re-walk the chains, scatter M symmetrically
-        double* om = p.out_mass + (size_t)e * n * n;
-        for (int c = lane; c < nl; c += G) {
-            const int di = X->col_dof[c];
-            om[di * n + di] = x[c];
-            for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
-                const int da = X->col_dof[a];
-                const double hv = sc[pd_tri(c, a, nl) * kTile];
-                om[di * n + da] = hv;
-                om[da * n + di] = hv;
-            }
-        }
-    }
-    if (!SPLIT && p.out_mass && env_ok) {
-        double* om = p.out_mass + (size_t)e * n * n;
-        for (int idx = lane; idx < n * n; idx += G) {
-            const int ci = X->dof_col[idx / n], ck = X->dof_col[idx % n];
-            om[idx] = (ci >= 0 && ck >= 0) ? H[ci * ldh + ck] : 0.0;
-        }
-    }
-    if (p.out_bias && env_ok) {
-        double* ob = p.out_bias + (size_t)e * n;
-        for (int i = lane; i < n; i += G) {
-            const int ci = X->dof_col[i];
-            ob[i] = (ci >= 0) ? C[ci] : 0.0;
-        }
-    }
-
-    // P8: PD errors (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196)
-    if (lane < N) {
-        const int j = lane;
-        const int o = X->offset[j], sz = X->size[j];
-        const bool valid = X->pd_valid[j] != 0;
-        const bool active = valid && (p.joint_active ? (p.joint_active[(size_t)e * N + j] != 0) : true);
-        double kp = 0.0, kd = 0.0;
-        if (valid) {
-            kp = p.kp ? p.kp[(size_t)e * N + j] : cst[kCst * j + 19];
-            kd = p.kd ? p.kd[(size_t)e * N + j] : cst[kCst * j + 20];
-        }
-        const double* tq = p.tar_pose + (size_t)e * n + o;
-        const double* tqd = p.tar_vel + (size_t)e * n + o;
-        for (int i = 0; i < sz; ++i) {
-            kpm[o + i] = active ? kp : 0.0;
-            kdm[o + i] = active ? kd : 0.0;
-            kdu[o + i] = kd;  // unmasked gains go on the diagonal
-        }
-        if (!valid) {
-            for (int i = 0; i < sz; ++i) { ep[o + i] = 0.0; ev[o + i] = 0.0; }
-        } else if (X->type[j] == JT_SPHERICAL) {
-            double dq[4], qi[4], tar[4];
-            quat_diff_mul(q + o, qd + o, dq);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) qi[i] = q[o + i] + dt * dq[i];
-            quat_normalize(qi);
-            // cPDController::PostProcessTargetPose / PostProcessTargetVel (PDController.cpp:430-461)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) tar[i] = tq[i];
-            if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
-            else quat_normalize(tar);
-            double er[4];
-            quat_vel_rel(qi, tar, 1.0, er);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ep[o + i] = er[i];
-            ev[o] = tqd[0] - qd[o]; ev[o + 1] = tqd[1] - qd[o + 1]; ev[o + 2] = tqd[2] - qd[o + 2];
-            ev[o + 3] = 0.0 - qd[o + 3];
-        } else {
-            for (int i = 0; i < sz; ++i) {
-                const double pinc = q[o + i] + dt * qd[o + i];
-                ep[o + i] = (tq[i] - pinc) / 1.0;
-                ev[o + i] = tqd[i] - qd[o + i];
-            }
-        }
-    }
-    __syncwarp();
-    if (SPLIT) {
-        // hand the assembled system to k_pd_solve: packed diagonal, rhs, and tau_i = t0_i - t1_i * qdd_col(i)
-        if (env_ok) {
-            for (int c = lane; c < nl; c += G) {
-                const int i = X->col_dof[c];
-                sc[(SC.rhs + c) * kTile] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
-                sc[pd_tri(c, c, nl) * kTile] = x[c] + dt * kdu[i];
-            }
-            for (int i = lane; i < n; i += G) {
-                double t0 = kpm[i] * ep[i] + kdm[i] * ev[i];
-                double t1 = kdm[i] * dt;
-                if (X->dof_col[i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
-                    const double dg = dt * kdu[i];
-                    const double acc = (fabs(dg) > DBL_MIN) ? t0 / dg : 0.0;
-                    t0 = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
-                    t1 = 0.0;
-                }
-                sc[(SC.t0 + i) * kTile] = t0;
-                sc[(SC.t1 + i) * kTile] = t1;
-            }
-        }
-        return;
-    }
-    for (int c = lane; c < nl; c += G) {
-        const int i = X->col_dof[c];
-        x[c] = (kpm[i] * ep[i] + kdm[i] * ev[i]) - C[c];
-        H[c * ldh + c] += dt * kdu[i];
-    }
-    __syncwarp();
-
-    // P9: LDL^T factorisation + solve of (M + dt Kd) qdd = rhs on the live dofs; x <- qdd.
-    // The envs sharing this warp are factorised one after the other, each by all 32 lanes (lane <-> column).
-    int bad = 0;
-    if (NLMAX > 0) {
-#pragma unroll 1
-        for (int s2 = 0; s2 < EPW; ++s2) {
-            double* wss = smem + pd_cst_doubles(N) + (size_t)(warp * EPW + s2) * L.total;
-            const int b2 = SPLIT ? 0 : ldlt_solve_regs<(NLMAX > 0 ? NLMAX : 1)>(wss + L.H, ldh, wss + L.x, nl, wlane);
-            if (s2 == sub) bad = b2;
-        }
-    } else {
-        bad = ldlt_solve_smem(H, ldh, x, nl, wlane);
-    }
-    __syncwarp();
-
-    // P10: tau = Kp e_p + Kd (e_v - dt qdd)
-    for (int i = lane; i < n; i += G) {
-        const int c = X->dof_col[i];
-        double acc;
-        if (c >= 0) {
-            acc = x[c];
-        } else {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
-            const double dg = dt * kdu[i];
-            const double rhs = kpm[i] * ep[i] + kdm[i] * ev[i];
-            acc = (fabs(dg) > DBL_MIN) ? rhs / dg : 0.0;
-        }
-        const double t = kpm[i] * ep[i] + kdm[i] * (ev[i] - dt * acc);
-        if (!isfinite(t)) bad |= 1;
-        if (env_ok) {
-            double* out = p.tau + (size_t)e * n + i;
-            *out = p.tau_accumulate ? (*out + t) : t;
-        }
-    }
-    if (p.status) {
-        // OR-reduce `bad` over the env's G lanes
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
-        if (lane == 0 && env_ok) p.status[e] = bad;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_pd_tree: first half of the split stable-PD step -- ONE THREAD PER ENV, a warp = one scratch tile of 32 envs.
-// The articulated-body recursions run as a depth-first walk of the joint tree (ModelIdx::dfs_event): on entering a
-// joint the thread forms its PD terms, root-frame transform, velocity / acceleration, body inertia and force; on
-// leaving it the subtree inertia is complete, so the joint's columns of H = M + dt*Kd and of the bias force are
-// formed against the ancestors on the current root path and the subtree sums are folded into the parent. Only the
-// current root path is ever live, so the workspace is [depth][kSlot] doubles per env (shared memory, element k of
-// level l at ws[(l * kSlot + k) * 32 + lane]: conflict-free), not [joints][...]. Every branch depends on the model
-// only, never on the env: the 32 lanes run in lock step. Results go to the tiled scratch with coalesced stores.
-// Same formulation as k_imp_pd (root frame, 10-parameter inertias, H[c][a] = F_c . S_a on the ancestor chain).
-// ------------------------------------------------------------------------------------------------
-constexpr int kSlotT = 0;    // root-frame transform of the joint [R(9) | t(3)]
-constexpr int kSlotV = 12;   // spatial velocity (6)
-constexpr int kSlotA = 18;   // spatial acceleration (6)
-constexpr int kSlotI = 24;   // inertia: m, h(3), Ixx Ixy Ixz Iyy Iyz Izz; summed over the subtree on the way up
-constexpr int kSlotF = 34;   // force (6), same
-constexpr int kSlotU = 40;   // Kp e_p + Kd e_v per joint dof (<= 7)
-constexpr int kSlotKd = 47;  // unmasked Kd of the joint
-constexpr int kSlot = 48;
 constexpr int kTreeHead = 9;  // per env, ahead of the levels: R(q_root), rows = directions of the root translation dofs
 
 TRL_DEV void tree_subspace(int kind, int a, const double* T /* [(k) * 32] strided */, const double* Rq, double* s) {
@@ -759,321 +135,6 @@ TRL_DEV void tree_subspace(int kind, int a, const double* T /* [(k) * 32] stride
         s[3] = Rq[(3 * a) * kTile]; s[4] = Rq[(3 * a + 1) * kTile]; s[5] = Rq[(3 * a + 2) * kTile];
     }
 }
-
-__global__ void __launch_bounds__(128)
-k_pd_tree(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch) {
-    KTrace trace_(TR_PD_TREE);
-    extern __shared__ double smem[];
-    __shared__ ModelIdx s_ix;
-    {   // per-joint double constants (DevModel::pd_cst, packed on the host): one coalesced copy
-        const int cnt = M->N * kCst;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
-    }
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
-    const int e0 = tile * kTile;
-    if (e0 >= E) return;
-    const int envs = min(kTile, E - e0);
-    const bool env_ok = lane < envs;
-    const int e = e0 + (env_ok ? lane : envs - 1);  // tail lanes redo the last env and store nothing
-    const int N = M->N, n = M->n, nl = M->nl;
-    const PdScratch SC = pd_scratch(n, nl);
-    const double* cst = smem;
-    double* ws = smem + pd_cst_doubles(N) + (size_t)warp * ((kTreeHead + M->num_levels * kSlot) * kTile) + lane;
-    double* Rq = ws;                       // Rq[k * 32]
-    double* lvl = ws + kTreeHead * kTile;  // level l, element k: lvl[(l * kSlot + k) * 32]
-    double* sc = scratch + (size_t)tile * SC.stride * kTile + lane;  // element idx: sc[idx * 32]
-    const double dt = p.dt;
-    const double* q = p.pose + (size_t)e * n;
-    const double* qd = p.vel + (size_t)e * n;
-    const double* tq = p.tar_pose + (size_t)e * n;
-    const double* tqd = p.tar_vel + (size_t)e * n;
-    {   // the four [32][n] input blocks of this tile are contiguous: pull their lines into L1 with coalesced prefetches
-        const size_t row0 = (size_t)e0 * n * sizeof(double);
-        const int bytes = envs * n * (int)sizeof(double);
-        for (int off = lane * 128; off < bytes; off += 32 * 128) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.pose + row0 + off));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.vel + row0 + off));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.tar_pose + row0 + off));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)p.tar_vel + row0 + off));
-        }
-    }
-    if (p.out_mass) {  // rare path (GetMassMat): zero the tile's [32][n][n] block, coalesced
-        double* om = p.out_mass + (size_t)e0 * n * n;
-        for (int idx = lane; idx < envs * n * n; idx += 32) om[idx] = 0.0;
-        __syncwarp();
-    }
-
-    const int nev = 2 * N;
-    for (int evi = 0; evi < nev; ++evi) {
-        const int code = X->dfs_event[evi];
-        if (code >= 0) {
-            // ---------------- enter joint j ----------------
-            const int j = code;
-            const int lv = X->level[j];
-            double* W = lvl + (size_t)lv * kSlot * kTile;
-            const double* Wp = W - kSlot * kTile;  // parent = previous level (valid when lv > 0)
-            const int o = X->offset[j], sz = X->size[j];
-            const int type = X->type[j];
-            const bool is_root = X->parent[j] == -1;
-            const double* cj_ = cst + kCst * j;
-
-            // PD terms (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196)
-            {
-                const bool valid = X->pd_valid[j] != 0;
-                const bool active = valid && (p.joint_active ? (p.joint_active[(size_t)e * N + j] != 0) : true);
-                double kp = 0.0, kd = 0.0;
-                if (valid) {
-                    kp = p.kp ? p.kp[(size_t)e * N + j] : cj_[19];
-                    kd = p.kd ? p.kd[(size_t)e * N + j] : cj_[20];
-                }
-                const double kpm = active ? kp : 0.0, kdm = active ? kd : 0.0;
-                W[kSlotKd * kTile] = kd;  // unmasked gains go on the diagonal
-                double ep[4] = {0, 0, 0, 0};
-                const bool sph = valid && !is_root && type == JT_SPHERICAL;
-                if (sph) {
-                    double qj[4], wj[4], dq[4], qi[4], tar[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { qj[i] = q[o + i]; wj[i] = qd[o + i]; tar[i] = tq[o + i]; }
-                    quat_diff_mul(qj, wj, dq);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) qi[i] = qj[i] + dt * dq[i];
-                    quat_normalize(qi);
-                    // cPDController::PostProcessTargetPose / PostProcessTargetVel (PDController.cpp:430-461)
-                    if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
-                    else quat_normalize(tar);
-                    quat_vel_rel(qi, tar, 1.0, ep);
-                }
-                for (int i = 0; i < sz; ++i) {
-                    const double qdi = qd[o + i];
-                    double epi = 0.0, evi_ = 0.0;
-                    if (valid) {
-                        if (sph) {
-                            epi = (i == 0) ? ep[0] : (i == 1) ? ep[1] : (i == 2) ? ep[2] : ep[3];
-                            evi_ = ((i < 3) ? tqd[o + i] : 0.0) - qdi;
-                        } else {
-                            epi = (tq[o + i] - (q[o + i] + dt * qdi)) / 1.0;
-                            evi_ = tqd[o + i] - qdi;
-                        }
-                    }
-                    const double u = kpm * epi + kdm * evi_;
-                    if (i < 7) W[(kSlotU + i) * kTile] = u;
-                    double t0 = u, t1 = kdm * dt;
-                    if (X->dof_col[o + i] < 0) {  // dead slot: decoupled 1x1 system (0 + dt*Kd) qdd = rhs, zero pivot => 0
-                        const double dg = dt * kd;
-                        const double acc = (fabs(dg) > DBL_MIN) ? u / dg : 0.0;
-                        t0 = kpm * epi + kdm * (evi_ - dt * acc);
-                        t1 = 0.0;
-                    }
-                    if (env_ok) {
-                        sc[(SC.t0 + o + i) * kTile] = t0;
-                        sc[(SC.t1 + o + i) * kTile] = t1;
-                    }
-                }
-            }
-
-            // root-frame transform
-            double T[12], Vp[6], Ap[6];
-            if (is_root) {
-                double qr[7], wr[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) { qr[i] = q[o + i]; wr[i] = qd[o + i]; }
-                double Rw[9];
-                {   // world <- root = A * T(pos) * R(quat); only its rotation is needed (gravity in the root frame)
-                    double rq9[9];
-                    quat_to_mat(qr[3], qr[4], qr[5], qr[6], rq9);
-                    mat3_mul(cj_, rq9, Rw);
-#pragma unroll
-                    for (int i = 0; i < 9; ++i) Rq[i * kTile] = rq9[i];
-                }
-                // a_0 = X_{world->root}(0, -g): E = Rw^T  (RBDUtil.cpp:17-18,59-60)
-                const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
-                double g0[3];
-                mat3T_mulv(Rw, ng, g0);
-                // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
-                double dq[4];
-                quat_diff_mul(qr + 3, wr + 3, dq);
-                const double qw = qr[3], qx = qr[4], qy = qr[5], qz = qr[6];
-                const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
-                const double m00 = 4 * (qw * dw + qx * dx), m11 = 4 * (qw * dw + qy * dy), m22 = 4 * (qw * dw + qz * dz);
-                const double m10 = 2 * (dx * qy + qx * dy - dw * qz - qw * dz);
-                const double m01 = 2 * (dx * qy + qx * dy + dw * qz + qw * dz);
-                const double m20 = 2 * (dx * qz + qx * dz + dw * qy + qw * dy);
-                const double m02 = 2 * (dx * qz + qx * dz - dw * qy - qw * dy);
-                const double m21 = 2 * (dy * qz + qy * dz - dw * qx - qw * dx);
-                const double m12 = 2 * (dy * qz + qy * dz + dw * qx + qw * dx);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) T[i] = (i % 4 == 0) ? 1.0 : 0.0;
-                T[9] = T[10] = T[11] = 0.0;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { Vp[k] = 0.0; Ap[k] = 0.0; }
-                Ap[3] = g0[0] + (m00 * wr[0] + m01 * wr[1] + m02 * wr[2]);
-                Ap[4] = g0[1] + (m10 * wr[0] + m11 * wr[1] + m12 * wr[2]);
-                Ap[5] = g0[2] + (m20 * wr[0] + m21 * wr[1] + m22 * wr[2]);
-            } else {
-                double qj[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) qj[i] = (i < sz) ? q[o + i] : 0.0;
-                double R[9], t[3];
-                joint_local_trans(X, j, qj, cj_, cj_ + 9, R, t);
-                double Tp[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) Tp[i] = Wp[(kSlotT + i) * kTile];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
-                    T[9 + r] = Tp[9 + r] + (Tp[r * 3] * t[0] + Tp[r * 3 + 1] * t[1] + Tp[r * 3 + 2] * t[2]);
-                }
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { Vp[k] = Wp[(kSlotV + k) * kTile]; Ap[k] = Wp[(kSlotA + k) * kTile]; }
-            }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) W[(kSlotT + i) * kTile] = T[i];
-
-            // s_j = S_j qd_j ; V_j = V_p + s_j ; a_j = a_p + V_p x s_j (motion cross product; V_j x s_j = V_p x s_j)
-            double s[6] = {0, 0, 0, 0, 0, 0};
-            {
-                const int c0 = X->first_col[j], nc = X->ncol[j];
-                for (int c = c0; c < c0 + nc; ++c) {
-                    const double w = qd[X->col_dof[c]];
-                    double sc6[6];
-                    tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sc6);
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) s[k] += sc6[k] * w;
-                }
-            }
-            double Vj[6], Aj[6];
-            {
-                double c0[3], c1[3], c2[3];
-                cross3(Vp, s, c0);
-                cross3(Vp + 3, s, c1);
-                cross3(Vp, s + 3, c2);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    Vj[k] = Vp[k] + s[k];
-                    Vj[3 + k] = Vp[3 + k] + s[3 + k];
-                    Aj[k] = Ap[k] + c0[k];
-                    Aj[3 + k] = Ap[3 + k] + (c1[k] + c2[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { W[(kSlotV + k) * kTile] = Vj[k]; W[(kSlotA + k) * kTile] = Aj[k]; }
-
-            // body inertia in the root frame (m, h = m c, I about the frame origin) and f = I a + V x* (I V)
-            double I[10], f[6] = {0, 0, 0, 0, 0, 0};
-            if (X->valid_body[j]) {
-                const double m = cj_[12];
-                double c[3];
-                mat3_mulv(T, cj_ + 13, c);
-                c[0] += T[9]; c[1] += T[10]; c[2] += T[11];
-                const double d0 = cj_[16], d1 = cj_[17], d2 = cj_[18];
-                double Ixx = T[0] * T[0] * d0 + T[1] * T[1] * d1 + T[2] * T[2] * d2;
-                double Ixy = T[0] * T[3] * d0 + T[1] * T[4] * d1 + T[2] * T[5] * d2;
-                double Ixz = T[0] * T[6] * d0 + T[1] * T[7] * d1 + T[2] * T[8] * d2;
-                double Iyy = T[3] * T[3] * d0 + T[4] * T[4] * d1 + T[5] * T[5] * d2;
-                double Iyz = T[3] * T[6] * d0 + T[4] * T[7] * d1 + T[5] * T[8] * d2;
-                double Izz = T[6] * T[6] * d0 + T[7] * T[7] * d1 + T[8] * T[8] * d2;
-                Ixx += m * (c[1] * c[1] + c[2] * c[2]);
-                Iyy += m * (c[0] * c[0] + c[2] * c[2]);
-                Izz += m * (c[0] * c[0] + c[1] * c[1]);
-                Ixy -= m * c[0] * c[1];
-                Ixz -= m * c[0] * c[2];
-                Iyz -= m * c[1] * c[2];
-                I[0] = m; I[1] = m * c[0]; I[2] = m * c[1]; I[3] = m * c[2];
-                I[4] = Ixx; I[5] = Ixy; I[6] = Ixz; I[7] = Iyy; I[8] = Iyz; I[9] = Izz;
-                const double* h = I + 1;
-                double hxv[3], hxw[3];
-                cross3(h, Aj + 3, hxv);
-                cross3(h, Aj, hxw);
-                const double na[3] = {Ixx * Aj[0] + Ixy * Aj[1] + Ixz * Aj[2] + hxv[0],
-                                      Ixy * Aj[0] + Iyy * Aj[1] + Iyz * Aj[2] + hxv[1],
-                                      Ixz * Aj[0] + Iyz * Aj[1] + Izz * Aj[2] + hxv[2]};
-                const double fa[3] = {m * Aj[3] - hxw[0], m * Aj[4] - hxw[1], m * Aj[5] - hxw[2]};
-                cross3(h, Vj + 3, hxv);
-                cross3(h, Vj, hxw);
-                const double nv[3] = {Ixx * Vj[0] + Ixy * Vj[1] + Ixz * Vj[2] + hxv[0],
-                                      Ixy * Vj[0] + Iyy * Vj[1] + Iyz * Vj[2] + hxv[1],
-                                      Ixz * Vj[0] + Iyz * Vj[1] + Izz * Vj[2] + hxv[2]};
-                const double fv[3] = {m * Vj[3] - hxw[0], m * Vj[4] - hxw[1], m * Vj[5] - hxw[2]};
-                double wxn[3], vxf[3], wxf[3];
-                cross3(Vj, nv, wxn);
-                cross3(Vj + 3, fv, vxf);
-                cross3(Vj, fv, wxf);
-                f[0] = na[0] + wxn[0] + vxf[0]; f[1] = na[1] + wxn[1] + vxf[1]; f[2] = na[2] + wxn[2] + vxf[2];
-                f[3] = fa[0] + wxf[0]; f[4] = fa[1] + wxf[1]; f[5] = fa[2] + wxf[2];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 10; ++i) I[i] = 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < 10; ++i) W[(kSlotI + i) * kTile] = I[i];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) W[(kSlotF + i) * kTile] = f[i];
-        } else {
-            // ---------------- leave joint j: subtree sums are complete ----------------
-            const int j = -1 - code;
-            const int lv = X->level[j];
-            double* W = lvl + (size_t)lv * kSlot * kTile;
-            const int o = X->offset[j];
-            double I[10], f[6];
-#pragma unroll
-            for (int i = 0; i < 10; ++i) I[i] = W[(kSlotI + i) * kTile];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) f[i] = W[(kSlotF + i) * kTile];
-            const double kdu = W[kSlotKd * kTile];
-            const int c0 = X->first_col[j], nc = X->ncol[j];
-            // per column: bias force, rhs, diagonal of H; S_c and F_c = Ic S_c go to the scratch -- the off-diagonal
-            // entries H[c][a] = F_c . S_a (a on the ancestor chain) are formed by k_pd_h with (env x column) parallelism
-            for (int c = c0; c < c0 + nc; ++c) {
-                double sv[6], Fc[6];
-                tree_subspace(X->col_kind[c], X->col_axis[c], W + kSlotT * kTile, Rq, sv);
-                const double m = I[0];
-                const double* h = I + 1;
-                double hxv[3], hxw[3];
-                cross3(h, sv + 3, hxv);
-                cross3(h, sv, hxw);
-                Fc[0] = I[4] * sv[0] + I[5] * sv[1] + I[6] * sv[2] + hxv[0];
-                Fc[1] = I[5] * sv[0] + I[7] * sv[1] + I[8] * sv[2] + hxv[1];
-                Fc[2] = I[6] * sv[0] + I[8] * sv[1] + I[9] * sv[2] + hxv[2];
-                Fc[3] = m * sv[3] - hxw[0];
-                Fc[4] = m * sv[4] - hxw[1];
-                Fc[5] = m * sv[5] - hxw[2];
-                const double Cc = (sv[0] * f[0] + sv[1] * f[1] + sv[2] * f[2]) + (sv[3] * f[3] + sv[4] * f[4] + sv[5] * f[5]);
-                const double hd = (Fc[0] * sv[0] + Fc[1] * sv[1] + Fc[2] * sv[2]) + (Fc[3] * sv[3] + Fc[4] * sv[4] + Fc[5] * sv[5]);
-                const int di = X->col_dof[c];
-                const int ui = di - o;
-                const double u = W[(kSlotU + (ui < 7 ? ui : 6)) * kTile];
-                if (env_ok) {
-                    double* ps = sc + (SC.scol + 6 * c) * kTile;  // one address per column, immediate offsets below
-                    double* pf = sc + (SC.fcol + 6 * c) * kTile;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        ps[k * kTile] = sv[k];
-                        pf[k * kTile] = Fc[k];
-                    }
-                    sc[(SC.rhs + c) * kTile] = u - Cc;
-                    sc[pd_tri(c, c) * kTile] = hd + dt * kdu;
-                    if (p.out_bias) p.out_bias[(size_t)e * n + di] = Cc;
-                    if (p.out_mass) p.out_mass[((size_t)e * n + di) * n + di] = hd;
-                }
-            }
-            if (lv > 0) {
-                double* Wp = W - kSlot * kTile;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) Wp[(kSlotI + i) * kTile] += W[(kSlotI + i) * kTile];
-            }
-        }
-    }
-    if (p.out_bias && env_ok) {  // dead dofs are exact zeros
-        for (int i = 0; i < n; ++i)
-            if (X->dof_col[i] < 0) p.out_bias[(size_t)e * n + i] = 0.0;
-    }
-}
-
 #include "trl_pd_block.cuh"
 #include "trl_pd_aba.cuh"
 
@@ -1349,290 +410,6 @@ k_apply_tau(const DevModel* __restrict__ M, int E, const double* __restrict__ po
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_pd_h: off-diagonal entries of H = M + dt*Kd from the columns k_pd_tree left in the scratch: H[c][a] = F_c . S_a
-// for every a on the ancestor chain of c (Featherstone's branch-induced sparsity; the other entries stay zero).
-// One warp per (tile of 32 envs, column c), lane = env: all loads / stores are 256-byte coalesced rows of the tile.
-// ------------------------------------------------------------------------------------------------
-TRL_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-constexpr int kHWarps = 4;
-__global__ void __launch_bounds__(kHWarps * 32)
-k_pd_h(const DevModel* __restrict__ M, int E, double* __restrict__ scratch, double* __restrict__ out_mass) {
-    KTrace trace_(TR_PD_H);
-    extern __shared__ __align__(16) double smem[];  // the tile's subspace columns S: [6 nl][32]
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = M->n, nl = M->nl;
-    const int tile = blockIdx.x;
-    const PdScratch SC = pd_scratch(n, nl);
-    double* g = scratch + (size_t)tile * SC.stride * kTile;
-    {   // the tile's S block is contiguous in the scratch: one bulk async copy (TMA) for the whole block
-        __shared__ unsigned long long s_bar;
-        const unsigned bar_a = smem_u32(&s_bar);
-        const unsigned bytes = (unsigned)(6 * nl * kTile * sizeof(double));
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(smem)),
-                         "l"(g + SC.scol * kTile), "r"(bytes), "r"(bar_a)
-                         : "memory");
-        }
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "TRL_HWAIT_%=:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-            "@p bra TRL_HDONE_%=;\n"
-            "bra TRL_HWAIT_%=;\n"
-            "TRL_HDONE_%=:\n"
-            "}\n" ::"r"(bar_a)
-            : "memory");
-    }
-    double* sc = g + lane;
-    const double* Ss = smem + lane;
-    const int e = tile * kTile + lane;
-    const bool env_ok = e < E;
-    for (int c = warp; c < nl; c += kHWarps) {
-        double F[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) F[k] = sc[(SC.fcol + 6 * c + k) * kTile];
-        const int row = pd_tri(c, 0);
-        for (int a = X->col_parent[c]; a >= 0; a = X->col_parent[a]) {
-            const double* S = Ss + 6 * a * kTile;
-            const double hv = (F[0] * S[0] + F[1] * S[kTile] + F[2] * S[2 * kTile]) +
-                              (F[3] * S[3 * kTile] + F[4] * S[4 * kTile] + F[5] * S[5 * kTile]);
-            sc[(row + a) * kTile] = hv;
-            if (out_mass && env_ok) {
-                const int di = X->col_dof[c], da = X->col_dof[a];
-                out_mass[((size_t)e * n + di) * n + da] = hv;
-                out_mass[((size_t)e * n + da) * n + di] = hv;
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_pd_solve: second half of the split stable-PD step -- ONE THREAD PER ENV. A warp owns one scratch tile (32 envs,
-// structure-of-arrays): the packed triangle is pulled into shared memory with a single bulk async copy (TMA, completion
-// on an mbarrier), then every thread runs a scalar left-looking LDL^T on "its" column of the tile (element idx at
-// tri[idx * 32 + lane]: conflict-free). No shuffles, no masks, no symmetric double work: the 32 lanes do 32 systems.
-// NL > 0: exact size, fully unrolled with rhs / pivots in registers; NL == 0: any nl, runtime loops.
-// No pivoting: M + dt*Kd is SPD on the live dofs (the reference's pivoted Eigen LDLT agrees to rounding); a zero pivot
-// zeroes that solution component like Eigen's pseudo-inverse of D does.
-// ------------------------------------------------------------------------------------------------
-
-TRL_DEV void tile_bulk_load(double* dst, const double* src, unsigned bytes, unsigned long long* bar, int lane) {
-    const unsigned bar_a = smem_u32(bar);
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (lane == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         smem_u32(dst)),
-                     "l"(src), "r"(bytes), "r"(bar_a)
-                     : "memory");
-    }
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TRL_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-        "@p bra TRL_DONE_%=;\n"
-        "bra TRL_WAIT_%=;\n"
-        "TRL_DONE_%=:\n"
-        "}\n" ::"r"(bar_a)
-        : "memory");
-}
-
-template <int NL>
-__global__ void __launch_bounds__(128)
-k_pd_solve(const DevModel* __restrict__ M, int E, const double* __restrict__ scratch, double* __restrict__ tau,
-           int tau_accumulate, int* __restrict__ status) {
-    KTrace trace_(TR_PD_SOLVE);
-    extern __shared__ __align__(16) double smem[];
-    __shared__ ModelIdx s_ix;
-    __shared__ unsigned long long s_bar[4];
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (tile * kTile >= E) return;
-    const int n = M->n, nl = (NL > 0) ? NL : M->nl;
-    const PdScratch SC = pd_scratch(n, nl);
-    // per-warp shared memory: the triangle [np][32]; the generic path appends rhs / pivots / 1/pivots [3][nl][32]
-    const int per_warp = (SC.np + (NL > 0 ? 0 : 3 * nl)) * kTile;
-    double* tri = smem + (size_t)warp * per_warp + lane;  // element idx: tri[idx * kTile]
-    const double* g = scratch + (size_t)tile * SC.stride * kTile;
-    tile_bulk_load(tri - lane, g, (unsigned)(SC.np * kTile * sizeof(double)), &s_bar[warp], lane);
-    g += lane;
-    int bad = 0;
-    if constexpr (NL > 0) {
-        // b[] lives in registers (the column loop is a compile-time loop); the q loop stays a runtime loop so the
-        // code stays small: column q is addressed from one base register (row offsets are immediates), its pivot d_q
-        // sits on the diagonal slot.
-        double b[NL];
-        static_for<0, NL>([&](auto ic) { b[decltype(ic)::value] = __ldg(g + (SC.rhs + decltype(ic)::value) * kTile); });
-        // Two columns (j, j+1) per pass: every L[i][q] fetched from shared memory feeds two FMAs (the kernel is bound by
-        // shared-memory loads, one warp per SM sub-partition), and the two columns' chains interleave.
-        static_for<0, NL / 2>([&](auto pc) {
-            constexpr int j = 2 * decltype(pc)::value;
-            double v0[NL - j], v1[NL - j - 1];
-            static_for<j, NL>([&](auto ic) { v0[decltype(ic)::value - j] = tri[pd_tri(decltype(ic)::value, j) * kTile]; });
-            static_for<j + 1, NL>([&](auto ic) { v1[decltype(ic)::value - j - 1] = tri[pd_tri(decltype(ic)::value, j + 1) * kTile]; });
-#pragma unroll 2
-            for (int q = 0; q < j; ++q) {
-                const double* cq = tri + q * kTile;  // cq[pd_tri(i, 0) * kTile] = entry (i, q)
-                const double dq = cq[pd_tri(q, 0) * kTile];
-                const double w0 = cq[pd_tri(j, 0) * kTile] * dq;      // L[j][q] d_q
-                const double w1 = cq[pd_tri(j + 1, 0) * kTile] * dq;  // L[j+1][q] d_q
-                static_for<j, NL>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    const double l = cq[pd_tri(i, 0) * kTile];
-                    v0[i - j] = fma(-l, w0, v0[i - j]);
-                    if constexpr (i > j) v1[i - j - 1] = fma(-l, w1, v1[i - j - 1]);
-                });
-            }
-            {   // finish column j; its contribution to column j+1 uses the unscaled v0[j+1] = L[j+1][j] d_j
-                const double dj = v0[0];
-                const bool ok = fabs(dj) > DBL_MIN;
-                if (!(dj > DBL_MIN)) bad |= 2;
-                const double r = ok ? fast_rcp(dj) : 0.0;
-                tri[pd_tri(j, j) * kTile] = ok ? dj : 0.0;
-                const double yj = b[j];
-                const double w = ok ? v0[1] : 0.0;
-                static_for<j + 1, NL>([&](auto ic) {  // L[i][j]; forward substitution rides along (y_j is final here)
-                    constexpr int i = decltype(ic)::value;
-                    const double lij = v0[i - j] * r;
-                    tri[pd_tri(i, j) * kTile] = lij;
-                    b[i] = fma(-lij, yj, b[i]);
-                    v1[i - j - 1] = fma(-lij, w, v1[i - j - 1]);
-                });
-                b[j] = yj * r;  // z_j = y_j / d_j
-            }
-            {   // finish column j + 1
-                const double dj = v1[0];
-                const bool ok = fabs(dj) > DBL_MIN;
-                if (!(dj > DBL_MIN)) bad |= 2;
-                const double r = ok ? fast_rcp(dj) : 0.0;
-                tri[pd_tri(j + 1, j + 1) * kTile] = ok ? dj : 0.0;
-                const double yj = b[j + 1];
-                static_for<j + 2, NL>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    const double lij = v1[i - j - 1] * r;
-                    tri[pd_tri(i, j + 1) * kTile] = lij;
-                    b[i] = fma(-lij, yj, b[i]);
-                });
-                b[j + 1] = yj * r;
-            }
-        });
-        if constexpr (NL % 2 == 1) {  // odd size: the last column on its own
-            constexpr int j = NL - 1;
-            double v = tri[pd_tri(j, j) * kTile];
-#pragma unroll 2
-            for (int q = 0; q < j; ++q) {
-                const double* cq = tri + q * kTile;
-                const double l = cq[pd_tri(j, 0) * kTile];
-                v = fma(-l, l * cq[pd_tri(q, 0) * kTile], v);
-            }
-            const bool ok = fabs(v) > DBL_MIN;
-            if (!(v > DBL_MIN)) bad |= 2;
-            tri[pd_tri(j, j) * kTile] = ok ? v : 0.0;
-            b[j] = b[j] * (ok ? fast_rcp(v) : 0.0);
-        }
-        // backward: L^T x = D^-1 y, row by row (x_i is final when row i is reached; the updates of b[0..i) are
-        // independent). The rows are read through a pointer the compiler cannot prove equal to `tri`, otherwise it
-        // forwards every L[i][j] stored above through registers and spills the whole factor to local memory.
-        const double* trb = tri + ((E == -kTile) ? 1 : 0);
-        static_for<1, NL>([&](auto ic) {
-            constexpr int i = NL - decltype(ic)::value;
-            static_for<0, i>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                b[j] = fma(-trb[pd_tri(i, j, NL) * kTile], b[i], b[j]);
-            });
-        });
-        __syncwarp();
-        static_for<0, NL>([&](auto ic) { tri[decltype(ic)::value * kTile] = b[decltype(ic)::value]; });  // x -> smem (column 0 slots)
-    } else {
-        double* bs = tri + SC.np * kTile;
-        double* ds = bs + nl * kTile;
-        double* rs = ds + nl * kTile;
-        for (int i = 0; i < nl; ++i) bs[i * kTile] = __ldg(g + (SC.rhs + i) * kTile);
-        for (int j = 0; j < nl; ++j) {
-            for (int q = 0; q < j; ++q) {
-                const double w = tri[pd_tri(j, q, nl) * kTile] * ds[q * kTile];
-                for (int i = j; i < nl; ++i) tri[pd_tri(i, j, nl) * kTile] -= tri[pd_tri(i, q, nl) * kTile] * w;
-            }
-            const double dj = tri[pd_tri(j, j, nl) * kTile];
-            const bool ok = fabs(dj) > DBL_MIN;
-            if (!(dj > DBL_MIN)) bad |= 2;
-            const double r = ok ? fast_rcp(dj) : 0.0;
-            ds[j * kTile] = ok ? dj : 0.0;
-            rs[j * kTile] = r;
-            const double yj = bs[j * kTile];
-            for (int i = j + 1; i < nl; ++i) {
-                const double lij = tri[pd_tri(i, j, nl) * kTile] * r;
-                tri[pd_tri(i, j, nl) * kTile] = lij;
-                bs[i * kTile] -= lij * yj;
-            }
-        }
-        for (int j = nl - 1; j >= 0; --j) {
-            double acc = bs[j * kTile] * rs[j * kTile];
-            for (int i = j + 1; i < nl; ++i) acc -= tri[pd_tri(i, j, nl) * kTile] * bs[i * kTile];
-            bs[j * kTile] = acc;
-        }
-        __syncwarp();
-        for (int i = 0; i < nl; ++i) tri[i * kTile] = bs[i * kTile];
-    }
-    // tau_i = t0_i - t1_i * qdd_col(i), transposed through shared memory so the [E][n] output is written coalesced.
-    // The x vector sits in tri[0 .. nl) (rows of column 0); tau is staged behind it.
-    double* ts = tri - lane + nl * kTile;  // [32][n] env-major staging (np >= nl + n for every model with nl >= 3...)
-    const int e0 = tile * kTile;
-    const int envs = min(kTile, E - e0);
-    const bool stage = (SC.np - nl) >= n;  // room behind x inside the triangle region; else write directly
-    constexpr int kB = 8;  // tau terms are fetched kB dofs at a time so the global-load latency is paid n / kB times, not n
-    for (int i0 = 0; i0 < n; i0 += kB) {
-        double t0v[kB], t1v[kB];
-#pragma unroll
-        for (int k = 0; k < kB; ++k) {
-            const int i = min(i0 + k, n - 1);
-            t0v[k] = __ldg(g + (SC.t0 + i) * kTile);
-            t1v[k] = __ldg(g + (SC.t1 + i) * kTile);
-        }
-#pragma unroll
-        for (int k = 0; k < kB; ++k) {
-            const int i = i0 + k;
-            if (i < n) {
-                const int c = X->dof_col[i];
-                const double t = t0v[k] - t1v[k] * (c < 0 ? 0.0 : tri[c * kTile]);
-                if (!isfinite(t)) bad |= 1;
-                if (stage) {
-                    ts[lane * n + i] = t;
-                } else if (lane < envs) {
-                    double* out = tau + (size_t)(e0 + lane) * n + i;
-                    *out = tau_accumulate ? (*out + t) : t;
-                }
-            }
-        }
-    }
-    if (stage) {
-        __syncwarp();
-        double* out = tau + (size_t)e0 * n;
-        for (int idx = lane; idx < envs * n; idx += 32) out[idx] = tau_accumulate ? (out[idx] + ts[idx]) : ts[idx];
-    }
-    if (status && lane < envs) status[e0 + lane] = bad;
-}
-
-// ------------------------------------------------------------------------------------------------
 // k_fk: cKinTree::JointWorldTrans for all joints + CalcBodyPartPos -- one warp per env
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -1795,180 +572,6 @@ k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, in
             for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
         }
         for (int i = 0; i < sz; ++i) out_vel[(size_t)e * n + o + i] = v[i];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_kin<G>: the fused step's kinematic chain in one kernel -- cKinCharacter::Pose(t) (pose + finite-difference vel)
-// and cKinTree::CalcBodyPartPos of that pose. G lanes per env (lane <-> joint), 32/G envs per warp.
-// ------------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(128)
-k_kin(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
-      const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
-      double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
-    extern __shared__ double smem[];
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    constexpr int EPW = 32 / G;
-    const int wlane = threadIdx.x & 31;
-    const int lane = wlane % G, sub = wlane / G;
-    const int warp = threadIdx.x >> 5;
-    const int wpb = blockDim.x >> 5;
-    const int e_raw = (blockIdx.x * wpb + warp) * EPW + sub;
-    if ((blockIdx.x * wpb + warp) * EPW >= E) return;
-    const bool env_ok = e_raw < E;
-    const int e = env_ok ? e_raw : E - 1;
-    const int N = M->N, n = M->n, fs = n + 1;
-    double* Tl = smem + (size_t)(warp * EPW + sub) * 24 * N;
-    double* Tw = Tl + 12 * N;
-    const double t = time[e];
-    const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
-    double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
-    if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
-    if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
-    for (int j = lane; j < N; j += G) {
-        double p0[7], p1[7], v[7];
-        kin_joint_pose(M, X, frames, fs, j, t, opos, orot, p0);
-        const int o = X->offset[j], sz = X->size[j];
-        if (env_ok)
-            for (int i = 0; i < sz; ++i) out_pose[(size_t)e * n + o + i] = p0[i];
-        if (out_vel) {
-            kin_joint_pose(M, X, frames, fs, j, t + ddt, opos, orot, p1);
-            if (j == 0) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
-#pragma unroll
-                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
-                quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
-            } else if (X->type[j] == JT_SPHERICAL) {
-                quat_vel_rel(p0, p1, ddt, v);
-            } else {
-                for (int i = 0; i < sz; ++i) v[i] = (p1[i] - p0[i]) / ddt;
-            }
-            if (env_ok)
-                for (int i = 0; i < sz; ++i) out_vel[(size_t)e * n + o + i] = v[i];
-        }
-        if (out_body_pos) {
-            double R[9], tt[3];
-            joint_local_trans(X, j, p0, M->attR[j], M->attT[j], R, tt);
-            double* dst = (j == 0) ? Tw : (Tl + 12 * j);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) dst[i] = R[i];
-            dst[9] = tt[0]; dst[10] = tt[1]; dst[11] = tt[2];
-        }
-    }
-    if (!out_body_pos) return;
-    __syncwarp();
-    compose_levels(M, X, Tl, Tw, lane, 1, G);
-    if (env_ok) {
-        double* o = out_body_pos + (size_t)e * N * 3;
-        for (int idx = lane; idx < N * 3; idx += G) {
-            const int j = idx / 3, r = idx % 3;
-            const double* T = Tw + 12 * j;
-            const double* c = M->com[j];
-            o[idx] = X->valid_body[j] ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_kin_thread: same job as k_kin<G> with ONE THREAD PER ENV: the motion frame lookup is done once per env and time
-// (not once per joint), the joints are visited in the depth-first order of ModelIdx::dfs_event and the world
-// transforms of the current root path live in a per-level shared-memory workspace ([level][12][32 lanes]).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_kin_thread(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
-             const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
-             double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
-    KTrace trace_(TR_KIN);
-    extern __shared__ double smem[];
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int e0 = (blockIdx.x * (blockDim.x >> 5) + warp) * kTile;
-    if (e0 >= E) return;
-    const int envs = min(kTile, E - e0);
-    const bool env_ok = lane < envs;
-    const int e = e0 + (env_ok ? lane : envs - 1);
-    const int N = M->N, n = M->n, fs = n + 1;
-    double* lvl = smem + (size_t)warp * (M->num_levels * 12 * kTile) + lane;  // level l, element k: lvl[(l * 12 + k) * 32]
-    const double t = time[e];
-    const double ddt = 1 / 60.0;  // gDiffTimeStep, anim/KinCharacter.cpp:5
-    double opos[3] = {0, 0, 0}, orot[4] = {1, 0, 0, 0};
-    if (origin_pos) { opos[0] = origin_pos[3 * (size_t)e]; opos[1] = origin_pos[3 * (size_t)e + 1]; opos[2] = origin_pos[3 * (size_t)e + 2]; }
-    if (origin_rot) { orot[0] = origin_rot[4 * (size_t)e]; orot[1] = origin_rot[4 * (size_t)e + 1]; orot[2] = origin_rot[4 * (size_t)e + 2]; orot[3] = origin_rot[4 * (size_t)e + 3]; }
-    int idx0, idx1 = 0;
-    double ph0, ph1 = 0.0;
-    motion_index_phase(M, frames, fs, t, &idx0, &ph0);
-    const double lerp0 = clampd(ph0, 0.0, 1.0);
-    if (out_vel) motion_index_phase(M, frames, fs, t + ddt, &idx1, &ph1);
-    const double lerp1 = clampd(ph1, 0.0, 1.0);
-    const int nev = 2 * N;
-    for (int evi = 0; evi < nev; ++evi) {
-        const int j = X->dfs_event[evi];
-        if (j < 0) continue;
-        const int o = X->offset[j], sz = X->size[j];
-        const bool is_root = X->parent[j] == -1;
-        const bool sph = !is_root && X->type[j] == JT_SPHERICAL;
-        double p0[7] = {0, 0, 0, 0, 0, 0, 0};
-        kin_joint_pose_at(M, X, frames, fs, j, t, idx0, lerp0, opos, orot, p0);
-        if (env_ok) {
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-                if (i < sz) out_pose[(size_t)e * n + o + i] = p0[i];
-        }
-        if (out_vel) {
-            double p1[7] = {0, 0, 0, 0, 0, 0, 0}, v[7] = {0, 0, 0, 0, 0, 0, 0};
-            kin_joint_pose_at(M, X, frames, fs, j, t + ddt, idx1, lerp1, opos, orot, p1);
-            if (is_root) {  // cKinTree::CalcVel, anim/KinTree.cpp:1470-1508
-#pragma unroll
-                for (int i = 0; i < 3; ++i) v[i] = (p1[i] - p0[i]) / ddt;
-                quat_vel_rel(p0 + 3, p1 + 3, ddt, v + 3);
-            } else if (sph) {
-                quat_vel_rel(p0, p1, ddt, v);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = (p1[i] - p0[i]) / ddt;
-            }
-            if (env_ok) {
-#pragma unroll
-                for (int i = 0; i < 7; ++i)
-                    if (i < sz) out_vel[(size_t)e * n + o + i] = v[i];
-            }
-        }
-        if (out_body_pos) {
-            double R[9], tt[3], T[12];
-            joint_local_trans(X, j, p0, M->attR[j], M->attT[j], R, tt);
-            double* W = lvl + (size_t)X->level[j] * 12 * kTile;
-            if (is_root) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) T[i] = R[i];
-                T[9] = tt[0]; T[10] = tt[1]; T[11] = tt[2];
-            } else {
-                const double* Wp = W - 12 * kTile;
-                double Tp[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) Tp[i] = Wp[i * kTile];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        T[r * 3 + c] = Tp[r * 3] * R[c] + Tp[r * 3 + 1] * R[3 + c] + Tp[r * 3 + 2] * R[6 + c];
-                    T[9 + r] = Tp[9 + r] + (Tp[r * 3] * tt[0] + Tp[r * 3 + 1] * tt[1] + Tp[r * 3 + 2] * tt[2]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) W[i * kTile] = T[i];
-            if (env_ok) {
-                const double* c = M->com[j];
-                const bool vb = X->valid_body[j] != 0;
-                double* ob = out_body_pos + ((size_t)e * N + j) * 3;
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-                    ob[r] = vb ? (T[r * 3] * c[0] + T[r * 3 + 1] * c[1] + T[r * 3 + 2] * c[2] + T[9 + r]) : 0.0;
-            }
-        }
     }
 }
 
@@ -2584,6 +1187,10 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         if (a < 2 * nlp) return idx + nlp;      // first leg block -> second
         return idx;
     };
+    if (!M->bx.all_valid) {  // the reference starts from VectorXd::Zero(psize): slots of shape-less bodies stay zero
+        for (int i = 1 + lane; i < D.psize; i += kObsG) opose[i] = 0.0;
+        __syncwarp();  // the lanes of an env zero each other's slots: order them before the body writes below
+    }
     for (int i = first + lane; i < N; i += kObsG) {
         const int slot = D.is_ct ? X->slot_ct[i] : X->slot_base[i];
         if (slot < 0) continue;
@@ -3170,32 +1777,14 @@ __global__ void __launch_bounds__(256) k_fp64_probe(double* out, int iters, doub
 }  // namespace
 
 // Kernel timeline for diagnostics: enable allocates a [16][2] buffer of (first block start, last block end) in
-// %globaltimer nanoseconds; read copies it out and re-arms it. Slots: 0 k_imp_pd, 1 k_pd_tree, 2 k_pd_h, 3 k_pd_solve,
-// 4 k_kin_thread, 5 k_obs_env, 6 k_obs_samples.
+// %globaltimer nanoseconds; read copies it out and re-arms it. Slots: 1 stable PD (k_pd_aba / k_pd_block), 4 k_kin_tile,
+// 5 k_obs_env, 6 k_obs_samples / k_obs_gather. The buffer belongs to the device that was current at enable time.
 static unsigned long long* g_trace_host_ptr = nullptr;
 static void trace_rearm() {
     unsigned long long init[2 * kTraceSlots];
     for (int i = 0; i < kTraceSlots; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
     cudaMemcpy(g_trace_host_ptr, init, sizeof(init), cudaMemcpyHostToDevice);
 }
-// Shared-memory carve-out preference for every kernel of the fused step (percent of the unified L1/shared array, or
-// < 0 to leave the driver default). Kernels with different carve-outs cannot share an SM without the SM draining to
-// be reconfigured, which would serialise the step's concurrent chains; one common value keeps them co-resident.
-int trl_set_carveout(int percent) {
-    if (percent < 0) return 0;
-    const void* funcs[] = {(const void*)k_pd_tree, (const void*)k_pd_h, (const void*)k_pd_solve<8>, (const void*)k_pd_solve<17>,
-                           (const void*)k_pd_solve<20>, (const void*)k_pd_solve<24>, (const void*)k_pd_solve<26>,
-                           (const void*)k_pd_solve<0>, (const void*)k_kin_thread, (const void*)k_obs_env,
-                           (const void*)k_obs_samples<0, false>, (const void*)k_obs_samples<1, false>,
-                           (const void*)k_obs_samples<2, false>, (const void*)k_obs_samples<3, false>,
-                           (const void*)k_obs_samples<1, true>, (const void*)k_obs_samples<2, true>};
-    for (const void* f : funcs) {
-        cudaError_t err = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-        if (err != cudaSuccess) return (int)err;
-    }
-    return 0;
-}
-
 int trl_trace_enable(int on) {
     cudaDeviceSynchronize();
     if (on && !g_trace_host_ptr) {
@@ -3275,47 +1864,6 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int G, int NLMAX, bool SPLIT>
-static int launch_imp_pd_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
-    constexpr int EPW = 32 / G;
-    const size_t per_warp = (size_t)pd_layout(hm.N, hm.n, hm.nl, NLMAX, SPLIT).total * sizeof(double) * EPW;
-    // warps per block: maximise resident warps per SM under the 227 KB shared-memory budget (1 KB reserved per block)
-    const size_t cst_bytes = (size_t)pd_cst_doubles(hm.N) * sizeof(double);
-    int wpb = 1, best = 0;
-    for (int w = kWarpsPerBlock; w >= 1; w >>= 1) {
-        const size_t blk = per_warp * w + cst_bytes + 2048;
-        const int resident = (int)((227 * 1024) / blk) * w;
-        if (resident > best) { best = resident; wpb = w; }
-    }
-    {
-        static const int wpb_env = env_int("TRL_PD_WPB", 0);  // tuning hook
-        if (wpb_env == 1 || wpb_env == 2 || wpb_env == 4) wpb = wpb_env;
-    }
-    const size_t smem = per_warp * wpb + cst_bytes;
-    int rc = ensure_smem((const void*)k_imp_pd<G, NLMAX, SPLIT>, smem);
-    if (rc) return rc;
-    const int envs_per_block = wpb * EPW;
-    const int blocks = (E + envs_per_block - 1) / envs_per_block;
-    k_imp_pd<G, NLMAX, SPLIT><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p, scratch);
-    return (int)cudaGetLastError();
-}
-
-template <int NL>
-static int launch_pd_solve_t(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, const double* scratch, void* stream) {
-    const PdScratch SC = pd_scratch(hm.n, hm.nl);
-    const size_t per_warp = (size_t)(SC.np + (NL > 0 ? 0 : 3 * hm.nl)) * kTile * sizeof(double);
-    // one warp = one tile of 32 envs; blocks of one warp spread the tiles over the SMs as evenly as possible
-    const int wpb = 1;
-    const size_t smem = per_warp * wpb;
-    if (smem > 227 * 1024 - 2048) return (int)cudaErrorInvalidValue;
-    int rc = ensure_smem((const void*)k_pd_solve<NL>, smem);
-    if (rc) return rc;
-    const int tiles = (E + kTile - 1) / kTile;
-    k_pd_solve<NL><<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, scratch, p.tau, p.tau_accumulate,
-                                                                                    p.status);
-    return (int)cudaGetLastError();
-}
-
 int trl_launch_apply_tau(const DevModel* dm, const DevModel& hm, int E, const double* pose, const double* tau,
                          double* out_tau, double* out_body_wrench, void* stream) {
     const size_t smem = (size_t)hm.num_levels * 12 * kTile * sizeof(double);
@@ -3338,38 +1886,9 @@ int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const d
     return (int)cudaGetLastError();
 }
 
-static int launch_pd_tree(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
-    const size_t per_warp = (size_t)(kTreeHead + hm.num_levels * kSlot) * kTile * sizeof(double);
-    const size_t cst_bytes = (size_t)pd_cst_doubles(hm.N) * sizeof(double);
-    const int wpb = 1;  // one warp = one tile of 32 envs; single-warp blocks spread the tiles evenly over the SMs
-    const size_t smem = per_warp * wpb + cst_bytes;
-    if (smem > 227 * 1024 - 2048) return (int)cudaErrorInvalidValue;
-    int rc = ensure_smem((const void*)k_pd_tree, smem);
-    if (rc) return rc;
-    const int tiles = (E + kTile - 1) / kTile;
-    k_pd_tree<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, E, p, scratch);
-    rc = (int)cudaGetLastError();
-    if (rc) return rc;
-    const size_t hsmem = (size_t)6 * hm.nl * kTile * sizeof(double);
-    rc = ensure_smem((const void*)k_pd_h, hsmem);
-    if (rc) return rc;
-    k_pd_h<<<tiles, kHWarps * 32, hsmem, (cudaStream_t)stream>>>(dm, E, scratch, p.out_mass);
-    return (int)cudaGetLastError();
-}
-
-// lanes per env: heuristic, or forced with the TRL_PD_GROUP environment variable (8 / 16 / 32; tuning and tests)
-static int pd_group_override() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("TRL_PD_GROUP");
-        v = e ? atoi(e) : 0;
-    }
-    return v;
-}
-
 // per env; the allocation is rounded up to whole tiles of kTile envs by the caller (trl_pd_scratch_tile())
 size_t trl_pd_scratch_doubles(const DevModel& hm) {
-    return std::max((size_t)pd_scratch(hm.n, hm.nl).stride, (size_t)hm.bx.aba_slots);
+    return (size_t)std::max(hm.bx.aba_slots, 1);  // k_pd_aba's hand-off between its two walks (k_pd_block keeps everything in shared memory)
 }
 int trl_pd_scratch_tile() { return kTile; }
 
@@ -3398,8 +1917,6 @@ static int launch_pd_block(const DevModel* dm, const DevModel& hm, int E, const 
     const int per_sm = std::max(1, std::min(per_sm_fit, (tiles + num_sms - 1) / num_sms));
     int W = 16 / per_sm;
     W = std::max(4, std::min(16, W));
-    static const int w_env = env_int("TRL_PD_BLOCK_WARPS", 0);  // tuning hook
-    if (w_env >= 1 && w_env <= 16) W = w_env;
     int rc;
     if (te == 32) {
         rc = ensure_smem((const void*)k_pd_block<32>, smem);
@@ -3418,9 +1935,7 @@ static int launch_pd_block(const DevModel* dm, const DevModel& hm, int E, const 
 static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
     if (p.out_mass || p.out_bias || !hm.bx.all_valid || !scratch || hm.N < 2) return -1;
     const int nb = hm.bx.num_branches;
-    int W = std::min(nb, 8);  // one warp per branch
-    static const int w_env = env_int("TRL_PD_ABA_WARPS", 0);  // tuning hook
-    if (w_env >= 1 && w_env <= 8) W = std::min(w_env, nb);
+    const int W = std::min(nb, 8);  // one warp per branch
     const size_t smem = (size_t)pd_cst_doubles(hm.N) * sizeof(double) +
                         (size_t)aba_ws_elems(nb, hm.bx.branch_area, W) * kTile * sizeof(double);
     if (smem > 227 * 1024 - 3072) return -1;
@@ -3433,56 +1948,18 @@ static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const St
 
 // Returns the number of kernels launched (>0) or a negative cudaError.
 int trl_launch_imp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
-    const int nl = hm.nl, N = hm.N;
-    {
-        static const int aba_env = env_int("TRL_PD_ABA", 1);  // A/B hook: 0 = CRBA + LDLT kernels only
-        if (aba_env) {
-            const int rc = launch_pd_aba(dm, hm, E, p, scratch, stream);
-            if (rc == 0) return 1;
-            if (rc > 0) return -rc;
-        }
+    // k_pd_aba (articulated-body elimination, no M) when every body is valid and neither M nor C is asked for; else
+    // k_pd_block (CRBA + RNEA + branch-sparse LTDL, M / C outputs, shape-less bodies). Returns the number of kernels
+    // launched (> 0) or a negative cudaError_t.
+    static const int aba_env = env_int("TRL_PD_ABA", 1);  // A/B hook: 0 = k_pd_block only (the tests run both)
+    if (aba_env) {
+        const int rc = launch_pd_aba(dm, hm, E, p, scratch, stream);
+        if (rc == 0) return 1;
+        if (rc > 0) return -rc;
     }
-    {
-        static const int block_env = env_int("TRL_PD_BLOCK", 1);  // A/B hook: 0 = the thread-per-env three-kernel chain
-        if (block_env) {
-            const int rc = launch_pd_block(dm, hm, E, p, stream);
-            if (rc == 0) return 1;
-            if (rc > 0) return -rc;
-        }
-    }
-    if (nl > 32) {
-        int rc = launch_imp_pd_t<32, 0, false>(dm, hm, E, p, nullptr, stream);
-        return rc ? -rc : 1;
-    }
-    static const int split_env = env_int("TRL_PD_SPLIT", -1);  // tuning hooks (tests exercise both paths)
-    const bool split = (split_env >= 0) ? (split_env != 0) : true;
-    int G = split ? ((N <= 8) ? 8 : (N <= 16 ? 16 : 32)) : 32;
-    const int ov = pd_group_override();
-    if (ov >= N && (ov == 8 || ov == 16 || ov == 32)) G = ov;
-    int rc = -1;
-    static const int tree_env = env_int("TRL_PD_TREE", 1);  // tuning / test hook: 0 = lane-per-joint k_imp_pd<.., SPLIT>
-    const bool use_tree = split && tree_env;
-    if (use_tree) rc = launch_pd_tree(dm, hm, E, p, scratch, stream);
-#define TRL_PD_CASE(GG, NL)                                                                       \
-    if (rc == -1 && G == GG && nl <= NL)                                                          \
-        rc = split ? launch_imp_pd_t<GG, NL, true>(dm, hm, E, p, scratch, stream)                 \
-                   : launch_imp_pd_t<GG, NL, false>(dm, hm, E, p, nullptr, stream);
-    TRL_PD_CASE(8, 8) TRL_PD_CASE(8, 20) TRL_PD_CASE(8, 32)
-    TRL_PD_CASE(16, 18) TRL_PD_CASE(16, 32)
-    TRL_PD_CASE(32, 8) TRL_PD_CASE(32, 18) TRL_PD_CASE(32, 20) TRL_PD_CASE(32, 24) TRL_PD_CASE(32, 26) TRL_PD_CASE(32, 32)
-#undef TRL_PD_CASE
-    if (rc) return rc > 0 ? -rc : rc;
-    if (!split) return 1;
-    static const int generic_env = env_int("TRL_PD_SOLVE_GENERIC", 0);  // tuning / test hook: force the runtime-loop kernel
-    switch (generic_env ? -1 : nl) {  // exact sizes of the bundled characters are unrolled; anything else takes runtime loops
-        case 8: rc = launch_pd_solve_t<8>(dm, hm, E, p, scratch, stream); break;    // hopper
-        case 17: rc = launch_pd_solve_t<17>(dm, hm, E, p, scratch, stream); break;  // biped2d
-        case 20: rc = launch_pd_solve_t<20>(dm, hm, E, p, scratch, stream); break;  // biped3d
-        case 24: rc = launch_pd_solve_t<24>(dm, hm, E, p, scratch, stream); break;  // raptor
-        case 26: rc = launch_pd_solve_t<26>(dm, hm, E, p, scratch, stream); break;  // dog
-        default: rc = launch_pd_solve_t<0>(dm, hm, E, p, scratch, stream); break;
-    }
-    return rc ? -rc : (use_tree ? 3 : 2);
+    const int rc = launch_pd_block(dm, hm, E, p, stream);
+    if (rc == 0) return 1;
+    return rc > 0 ? -rc : -(int)cudaErrorInvalidConfiguration;  // -1: the model's tile does not fit in shared memory
 }
 
 int trl_launch_fk(const DevModel* dm, const DevModel& hm, int E, const double* pose, double* out_joint_world,
@@ -3502,47 +1979,17 @@ int trl_launch_kin_char(const DevModel* dm, const DevModel& hm, const double* fr
     return (int)cudaGetLastError();
 }
 
-template <int G>
-static int launch_kin_t(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
-                        const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
-                        double* out_body_pos, void* stream) {
-    constexpr int EPW = 32 / G;
-    const int wpb = 4;
-    const size_t smem = (size_t)24 * hm.N * sizeof(double) * wpb * EPW;
-    const int epb = wpb * EPW;
-    k_kin<G><<<(E + epb - 1) / epb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot,
-                                                                        out_pose, out_vel, out_body_pos);
-    return (int)cudaGetLastError();
-}
-
-// cKinCharacter::Pose + body positions of the kin pose in one launch (used by trl_step_fused)
 int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames, int E, const double* time,
                    const double* origin_pos, const double* origin_rot, double* out_pose, double* out_vel,
                    double* out_body_pos, void* stream) {
-    static const int thread_env = env_int("TRL_KIN_THREAD", 2);  // tuning / test hook: 2 = warp-per-joint tiles (default),
-                                                                 // 1 = thread-per-env, 0 = lane-per-joint k_kin<G>
-    if (thread_env == 2) {
-        const size_t smem = (size_t)hm.N * 12 * kTile * sizeof(double);
-        int rc = ensure_smem((const void*)k_kin_tile, smem);
-        if (rc) return rc;
-        const int tiles = (E + kTile - 1) / kTile;
-        k_kin_tile<<<tiles, std::min(hm.N, kKinWarps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
-                                                                    out_vel, out_body_pos);
-        return (int)cudaGetLastError();
-    }
-    if (thread_env) {
-        const int wpb = 1;
-        const size_t smem = (size_t)hm.num_levels * 12 * kTile * sizeof(double) * wpb;
-        int rc = ensure_smem((const void*)k_kin_thread, smem);
-        if (rc) return rc;
-        const int tiles = (E + kTile - 1) / kTile;
-        k_kin_thread<<<(tiles + wpb - 1) / wpb, wpb * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos,
-                                                                                      origin_rot, out_pose, out_vel, out_body_pos);
-        return (int)cudaGetLastError();
-    }
-    if (hm.N <= 8) return launch_kin_t<8>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
-    if (hm.N <= 16) return launch_kin_t<16>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
-    return launch_kin_t<32>(dm, hm, frames, E, time, origin_pos, origin_rot, out_pose, out_vel, out_body_pos, stream);
+    // warp per (tile of 32 envs, joint): local transforms [N][12][32] in shared memory
+    const size_t smem = (size_t)hm.N * 12 * kTile * sizeof(double);
+    int rc = ensure_smem((const void*)k_kin_tile, smem);
+    if (rc) return rc;
+    const int tiles = (E + kTile - 1) / kTile;
+    k_kin_tile<<<tiles, std::min(hm.N, kKinWarps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
+                                                                out_vel, out_body_pos);
+    return (int)cudaGetLastError();
 }
 
 template <int G>

@@ -153,3 +153,41 @@ def test_kin_character_identical_and_antipodal_frames(trl, oracle):
         rp, rv = om.kin_char_pose(float(t[e]))
         assert np.abs(pose[e] - rp).max() <= 1e-9 * max(1.0, np.abs(rp).max()), "kin pose at t = %r" % t[e]
         assert np.abs(vel[e] - rv).max() <= 1e-8 * max(1.0, np.abs(rv).max()), "kin vel at t = %r" % t[e]
+
+
+def test_policy_state_zero_fills_slots_of_shape_less_bodies(trl, oracle):
+    """cTerrainRLCharController::BuildPoliStatePose starts from Zero(psize): with a shape-less body the tail of the pose block
+    must be zero, not whatever the output buffer held"""
+    from helpers import oracle_grounds
+    jm, bd, pd = synthetic_character(with_null_body=True)
+    om = oracle.Model(joint_mat=jm, body_defs=bd, pd_params=pd)
+    pm = trl.CharModel.from_dict({"joint_mat": jm, "body_defs": bd, "pd_params": pd})
+    E = 33
+    pose, vel, _, _ = synthetic_state(jm, E)
+    rng = np.random.default_rng(2)
+    body_pos = pose[:, None, :3] + rng.normal(0, 0.3, (E, om.N, 3))
+    body_vel = rng.normal(size=(E, om.N, 3))
+    cfg = trl.make_obs_cfg(obs_kind=0, num_samples=200)
+    ocfg = oracle.obs_cfg(obs_kind=0, num_samples=200)
+    batch = trl.Batch(pm, E, 0, cfg)
+    kind, fields = synth.make_grounds("dog", 3)
+    batch.ground_set_heightfields(kind, fields)
+    grounds = oracle_grounds(oracle, kind, fields)
+    import torch
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in
+           {"pose": pose, "vel": vel, "bp": body_pos, "bv": body_vel}.items()}
+    batch.use_torch_stream()
+    state = batch.build_poli_state(dev["pose"], dev["bp"], dev["bv"], vel=dev["vel"])
+    state.fill_(123.0)  # stale contents; the call below must overwrite every entry
+    p = batch._prep([(dev["pose"], np.float64), (dev["vel"], np.float64), (dev["bp"], np.float64), (dev["bv"], np.float64),
+                     (None, np.float64), (None, np.float64), (None, np.float64), (None, np.float64), (None, np.uint8),
+                     (state, np.float64), (None, np.int32)])
+    from terrainrlsim_b200 import _capi
+    assert _capi.lib().trl_build_poli_state(batch._h, *p) == 0
+    batch.sync()
+    got = state.cpu().numpy()
+    batch.set_stream(None)
+    for e in range(E):
+        ref = oracle.build_poli_state(om, grounds[e % len(grounds)], ocfg, pose[e], vel[e], body_pos[e], body_vel[e])
+        assert np.abs(got[e] - ref).max() <= 1e-9 * max(1.0, np.abs(ref[np.isfinite(ref)]).max()), e
+    assert not np.any(got == 123.0)

@@ -435,10 +435,8 @@ print("VARIANT_OK")
 """
 
 
-@pytest.mark.parametrize("env", [{"TRL_PD_SPLIT": "0"}, {"TRL_PD_SOLVE_GENERIC": "1"}, {"TRL_PD_TREE": "0"},
-                                 {"TRL_PD_TREE": "0", "TRL_PD_GROUP": "32"}, {"TRL_KIN_THREAD": "0"}, {"TRL_KIN_THREAD": "1"},
-                                 {"TRL_STEP_OVERLAP": "0"}, {"TRL_HOST_SLICES": "1"},
-                                 {"TRL_PD_SPLIT": "0", "TRL_PD_GROUP": "16"}])
+@pytest.mark.parametrize("env", [{"TRL_PD_ABA": "0"}, {"TRL_OBS_STAGED": "0"}, {"TRL_OBS_STAGED": "1"},
+                                 {"TRL_STEP_OVERLAP": "0"}, {"TRL_HOST_SLICES": "1"}, {"TRL_HOST_SLICES": "4"}])
 def test_pd_kernel_variants(env):
     """The launcher's tuning hooks select other kernel variants (monolithic warp-per-env PD, runtime-loop solve, wider
     lane groups); each must meet the same 1e-9 bar. Hooks are read once per process, hence the subprocess."""
