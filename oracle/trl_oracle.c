@@ -4,8 +4,15 @@
  * Plain C99, double precision, compile with -O2 -ffp-contract=off so it is a stable
  * reference. Deliberately literal: it keeps the reference's formulation (4x4 homogeneous
  * matrices, dense 6x6 spatial matrices, pivoted LDLT, per-joint chain walks) and order of
- * operations, including the quirks listed in SURVEY.md section 8a-Q. PARITY UNPINNED (no
- * reference golden vectors exist); validated by identities in tests/.
+ * operations, including the quirks listed in SURVEY.md section 8a-Q.
+ *
+ * PARITY PINNED TO THE REFERENCE ITSELF: the reference's own translation units (MathUtil, SpAlg, RBDUtil, RBDModel,
+ * KinTree, Motion, Character, KinCharacter, the PD controllers, Ground / GroundVar2D / 3D, TerrainGen2D / 3D, Rand ...)
+ * are compiled unmodified into oracle/_ref/libtrl_ref.so against stand-in Eigen / Bullet headers (oracle/Makefile target
+ * `ref`), and every function here is compared with them on the same inputs at 1e-13 relative (terrain heights, cell
+ * indices and the random stream bit for bit): tests/test_ref_pin.py. The same comparisons are frozen as fixtures
+ * generated from the reference (tools/make_golden.py -> tests/golden/, tests/test_golden.py) and run everywhere.
+ * Independent identities (tests/test_oracle_identities.py, incl. a 50-digit mpmath solve) bound it a second way.
  */
 #include "trl_oracle.h"
 

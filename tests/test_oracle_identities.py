@@ -1,5 +1,6 @@
-"""The oracle is 'parity unpinned' (the reference ships no golden vectors), so it is pinned here by
-mathematical identities that do not depend on the restatement itself:
+"""A second, independent pin of the oracle (the first is the reference itself: tests/test_ref_pin.py against the
+reference's own translation units, frozen in tests/golden/): mathematical identities that do not depend on the
+restatement:
   * M symmetric, PSD; dead dofs (root slot 6, Q1) exactly zero
   * RNEA(q, qd, qdd) = M qdd + C           (CRBA and RNEA agree)
   * 1/2 qd^T M qd = kinetic energy from finite-differenced FK (independent numpy evaluation)
