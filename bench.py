@@ -4,22 +4,24 @@
     python bench.py --gpus N --steps K --warmup W [--config biped3d] [--impl reference]
 
 One "step" = one pass of the fused hot path (trl_step_fused) over the E environments of one GPU:
-stable-PD torque (CRBA + RNEA + LDL^T), kin-char pose+vel, FK of the kin pose, G terrain samples, F packed
-features. Default workload: biped3D, 16384 envs/GPU -- the configuration
-BASELINE.json's north_star target is quoted on; the other configs' throughput is measured in the same run
-and reported under "other_workloads" (short runs), hopper (configs[1]) included.
+stable-PD torque, kin-char pose+vel, FK of the kin pose, G terrain samples, F packed features.
+Default workload: biped3D, 16384 envs/GPU on 4096 terrains generated on the device from the config's own terrain
+file -- the configuration BASELINE.json's north_star target is quoted on; the other configs run in the same
+invocation on every rank and are reported under "other_workloads".
 
-value  : whole-job env-steps/s with every input already resident in HBM (DEVICE pointer mode, CUDA events,
-         max over ranks). L2 is defeated by rotating over R input/output sets whose total footprint is > 2.5x L2.
-e2e    : same metric through the public HOST-pointer API (pinned host buffers; H2D of every input and D2H of
-         every output inside the timed region, each step).
-roofline: dominant entry point (stable PD = k_pd_tree + k_pd_h + k_pd_solve, one CUDA-event-timed launch group) --
-         algorithmic FP64 flops per launch (SURVEY.md 8d table x E) over its time, against the FP64 DFMA peak measured
-         in this run (MEASURED_PEAKS.json has no FP64 entry); `traffic` = DRAM bytes of the three kernels from the
-         committed ncu captures (profiles/r01_pd_traffic.json);
-         roofline_step_hbm does the same for the whole step's algorithmic bytes against the measured HBM copy peak.
-cpu_baseline / --impl reference: the CPU oracle (a faithful restatement of the reference's algorithms; the
-         reference itself needs Eigen+Bullet and cannot be built here) on all host cores, bounded sample.
+value  : whole-job env-steps/s with every input already resident in HBM (DEVICE pointer mode, CUDA graph replay,
+         CUDA events, max over ranks). L2 is defeated by rotating over R input/output sets (> 2.5x L2 in total).
+e2e    : same metric through the HOST-pointer C ABI (trl_step_fused_ex, pinned host buffers, synchronous calls; H2D of
+         the step's inputs and D2H of torque, f64 state and reward inside the timed region), see measure_e2e();
+         e2e.variants / e2e.pipelined report other transfer contracts beside it.
+roofline: dominant kernel (stable PD = k_pd_aba, CUDA-event-timed alone on the same rotating sets) -- algorithmic FP64
+         flops per launch (SURVEY.md 8d table x E) over its time, against the FP64 DFMA peak measured in this run
+         (MEASURED_PEAKS.json has no FP64 entry); `traffic` = its DRAM bytes from the committed ncu capture
+         (profiles/r02_pd_traffic.json); roofline_step_hbm does the same for the whole step's algorithmic bytes against
+         the measured HBM copy peak.
+cpu_baseline / --impl reference: the CPU oracle (a restatement of the reference's algorithms pinned to the reference's
+         own translation units, tests/test_ref_pin.py) on all host cores, on the same workload: one step = one pass
+         over a GPU's worth of envs on the same number of terrains, built from the same seeds.
 """
 import argparse
 import json
@@ -676,14 +678,14 @@ def run_ours(args, rank, local_rank, world):
         peak_tf = fp64_peak if fp64_peak else nominal
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_pd_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_pd_traffic.json")))
             if tj.get("config") == name and tj.get("envs") == E:
                 traffic = tj["pd_entry_bytes_per_launch"]
         except (OSError, ValueError, KeyError):
             pass
-        roof = {"bound": "fp64", "kernel": "stable-PD entry: k_pd_tree + k_pd_h + k_pd_solve", "achieved": ach_tf,
+        roof = {"bound": "fp64", "kernel": "stable-PD entry: k_pd_aba", "achieved": ach_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
-                "traffic_note": "DRAM bytes per launch of the three kernels under ncu (cold L2; profiles/r01_pd_traffic.json)",
+                "traffic_note": "DRAM bytes of one k_pd_aba launch inside the fused step under ncu --set full (profiles/r02_pd_traffic.json)",
                 "peak_source": "DFMA probe measured in this run" if fp64_peak else "nominal 148 SM x 64 x 2 x 1.965 GHz",
                 "ms_per_launch": ms_pd, "algorithmic_flops_per_launch": pd_flops * E}
         ms_step = ms / args.steps
