@@ -101,7 +101,7 @@ struct DevModel {
     double joint_w[TRL_MAX_JOINTS];  // DiffWeight / sum|DiffWeight| (cScenarioExpImitate::CalcJointWeights)
     // per-joint constants of the stable-PD kernels, packed [N][21]: attach rotation (9), attach point (3), mass, CoM (3),
     // inertia diagonal (3), Kp, Kd -- copied to shared memory as one block
-    double pd_cst[TRL_MAX_JOINTS * 21];
+    alignas(16) double pd_cst[TRL_MAX_JOINTS * 21];
     double torque_lim[TRL_MAX_JOINTS];  // joint_mat TorqueLim / ForceLim (cJoint::ClampTotalTorque / ClampTotalForce)
     double force_lim[TRL_MAX_JOINTS];
     double total_mass;

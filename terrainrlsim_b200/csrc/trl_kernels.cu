@@ -1942,7 +1942,7 @@ static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const St
     int rc = ensure_smem((const void*)k_pd_aba, smem);
     if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
-    k_pd_aba<<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(dm, E, p, scratch, (int)trl_pd_scratch_doubles(hm));
+    k_pd_aba<<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(dm, E, p, scratch, (int)trl_pd_scratch_doubles(hm), hm.N, hm.n);
     return (int)cudaGetLastError();
 }
 
@@ -2090,3 +2090,10 @@ int trl_launch_f64_to_f32(const double* src, float* dst, size_t count, void* str
 }
 
 int trl_obs_state_size(int N, const trl_obs_cfg& cfg) { return obs_dims(N, cfg).F; }
+
+#ifdef TRL_PD_CLK
+// diagnostic build only (tools/pd_phases.py): clock64 stamps of one block of k_pd_aba, [warp][stamp]
+extern "C" int trl_debug_pd_clk(long long* out256) {
+    return (int)cudaMemcpyFromSymbol(out256, g_pd_clk, sizeof(long long) * 8 * 32);
+}
+#endif

@@ -124,65 +124,113 @@ TRL_DEV void aba_column(int kind, int ax, const double* T, double* S) {
 }
 
 // workspace layout, in elements of 32 doubles ([element][lane]):
-//   [0, 12)                       root V, A (second walk: delta of the root in [0, 6))
-//   [12, 12 + 27 nb)              per branch: I^a (21), p^a (6) handed to the root; afterwards the tau staging rows
+//   [0, 18)                       root V, A, f (second walk: delta of the root in [0, 6))
+//   [18, 18 + 27 nb)              per branch: I^a (21), p^a (6) handed to the root; afterwards the tau staging rows
 //   [.., + W x branch_area)       one area per WARP: 22 per level below the root (T12 f6 u3 Kd1; second walk: delta in
 //                                 [0, 6)), then the [V6 A6 IA21 P6] blocks of joints with several children
-__host__ __device__ inline int aba_ws_elems(int nb, int branch_area, int warps) { return 12 + 27 * nb + warps * branch_area; }
+__host__ __device__ inline int aba_ws_elems(int nb, int branch_area, int warps) { return 18 + 27 * nb + warps * branch_area; }
+
+#ifdef TRL_PD_CLK
+__device__ long long g_pd_clk[8][32];
+#define PD_CLK(i) do { if (blockIdx.x == 100 && (threadIdx.x & 31) == 0) g_pd_clk[threadIdx.x >> 5][(i)] = clock64(); } while (0)
+#else
+#define PD_CLK(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(256)
-k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch, int scratch_stride) {
+k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch, int scratch_stride, int N, int n) {
     KTrace trace_(TR_PD_TREE);
     extern __shared__ double smem[];
     __shared__ ModelIdx s_ix;
     __shared__ PdBlkIdx s_bx;
     __shared__ int s_status[32];
-    {
-        const int cnt = M->N * kCst;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) smem[i] = __ldg(M->pd_cst + i);
-        const uint4* src = reinterpret_cast<const uint4*>(&M->bx);
-        uint4* d = reinterpret_cast<uint4*>(&s_bx);
-        for (int i = threadIdx.x; i < (int)(sizeof(PdBlkIdx) / 16); i += blockDim.x) d[i] = __ldg(src + i);
-        if (threadIdx.x < 32) s_status[threadIdx.x] = 0;
-    }
-    stage_model_idx(&s_ix, M);  // contains the barrier
-    const ModelIdx* X = &s_ix;
-    const PdBlkIdx* B = &s_bx;
+    PD_CLK(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int tile = blockIdx.x;
     const int e0 = tile * kTile;
     const int envs = min(kTile, E - e0);
     const bool env_ok = lane < envs;
     const size_t e = (size_t)(e0 + (env_ok ? lane : envs - 1));  // tail lanes redo the last env and store nothing
-    const int N = M->N, n = M->n, nb = B->num_branches;
+    const double* q = p.pose + e * n;
+    const double* qd = p.vel + e * n;
+    const double* tq = p.tar_pose + e * n;
+    const double* tqd = p.tar_vel + e * n;
+    {
+        // The tile's rows of the four input arrays are contiguous ([32][n] doubles each) but every lane walks its own row,
+        // joint by joint: pull them into L2 now, in whole lines, so that the walk's strided loads do not each wait on HBM.
+        const size_t row0 = (size_t)e0 * n * sizeof(double);
+        const int lines = (envs * n * (int)sizeof(double) + 127) >> 7;
+        for (int l = threadIdx.x; l < lines; l += blockDim.x) {
+            const size_t off = row0 + ((size_t)l << 7);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p.pose + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p.vel + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p.tar_pose + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)p.tar_vel + off));
+        }
+    }
+    // the root's coordinates (warp 0 needs them first): in flight while the model tables are staged
+    double q_root[4], qd_root[7], grav[3];
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) grav[i] = M->gravity[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q_root[i] = q[3 + i];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) qd_root[i] = qd[i];
+    }
+    {
+        // per-joint constants, PdBlkIdx, ModelIdx -> shared memory: every load is issued before the first store (one trip)
+        constexpr int kBxQ = (int)(sizeof(PdBlkIdx) / 16), kIxQ = (int)(sizeof(ModelIdx) / 16);
+        const int cstQ = pd_cst_doubles(N) / 2;
+        const int totalQ = cstQ + kBxQ + kIxQ;
+        const uint4* s0 = reinterpret_cast<const uint4*>(M->pd_cst);
+        const uint4* s1 = reinterpret_cast<const uint4*>(&M->bx) - cstQ;
+        const uint4* s2 = reinterpret_cast<const uint4*>(&M->ix) - (cstQ + kBxQ);
+        uint4* d0 = reinterpret_cast<uint4*>(smem);
+        uint4* d1 = reinterpret_cast<uint4*>(&s_bx) - cstQ;
+        uint4* d2 = reinterpret_cast<uint4*>(&s_ix) - (cstQ + kBxQ);
+        for (int base = threadIdx.x; base < totalQ; base += 4 * blockDim.x) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k * blockDim.x;
+                if (i < totalQ) v[k] = __ldg((i < cstQ ? s0 : i < cstQ + kBxQ ? s1 : s2) + i);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k * blockDim.x;
+                if (i < totalQ) (i < cstQ ? d0 : i < cstQ + kBxQ ? d1 : d2)[i] = v[k];
+            }
+        }
+        if (threadIdx.x < 32) s_status[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    PD_CLK(1);
+    const ModelIdx* X = &s_ix;
+    const PdBlkIdx* B = &s_bx;
+    const int nb = B->num_branches;
     const double* cst = smem;
     double* ws0 = smem + pd_cst_doubles(N);  // workspace base (no lane offset)
     double* ws = ws0 + lane;                 // element k of this env: ws[k * 32]
     double* sc = scratch + (size_t)tile * scratch_stride * kTile + lane;
     const double dt = p.dt;
-    const double* q = p.pose + e * n;
-    const double* qd = p.vel + e * n;
-    const double* tq = p.tar_pose + e * n;
-    const double* tqd = p.tar_vel + e * n;
-    const int kOut = 12;
+    const int kOut = 18;
     double* area = ws + (size_t)(kOut + 27 * nb + warp * B->branch_area) * kTile;  // this warp's branch area
     int status = 0;
 
     // ======================= root, down: V_0 = S qd, A_0 = gravity + c_root (warp 0) =======================
-    double fr[6];  // f of the root body (warp 0)
-    double Ir[10];
     if (warp == 0) {
         double rq9[9], Rw[9];  // R(q_root) and the world <- root rotation
-        quat_to_mat(q[3], q[4], q[5], q[6], rq9);
+        quat_to_mat(q_root[0], q_root[1], q_root[2], q_root[3], rq9);
         mat3_mul(cst, rq9, Rw);
         double wr[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) wr[i] = qd[i];
-        const double ng[3] = {-M->gravity[0], -M->gravity[1], -M->gravity[2]};
+        for (int i = 0; i < 7; ++i) wr[i] = qd_root[i];
+        const double ng[3] = {-grav[0], -grav[1], -grav[2]};
         double g0[3];
         mat3T_mulv(Rw, ng, g0);  // a_0 = X_{world->root}(0, -g)  (RBDUtil.cpp:17-18,59-60)
         double dq[4];
-        const double qr4[4] = {q[3], q[4], q[5], q[6]};
+        const double qr4[4] = {q_root[0], q_root[1], q_root[2], q_root[3]};
         quat_diff_mul(qr4, wr + 3, dq);  // c_root (cRBDUtil::BuildCjRoot, RBDUtil.cpp:867-904)
         const double qw = qr4[0], qx = qr4[1], qy = qr4[2], qz = qr4[3];
         const double dw = dq[0], dx = dq[1], dy = dq[2], dz = dq[3];
@@ -205,25 +253,37 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 #pragma unroll
         for (int k = 0; k < 6; ++k) { ws[k * kTile] = V[k]; ws[(6 + k) * kTile] = A[k]; }
         const double Tid[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+        double Ir[10], fr[6];  // f of the root body: parked in shared memory until the root solve
         aba_body(Tid, cst, V, A, Ir, fr);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ws[(12 + k) * kTile] = fr[k];
     }
+    PD_CLK(2);
     __syncthreads();
+    PD_CLK(3);
+#ifdef TRL_PD_CLK
+    int clk_i = 4;
+#endif
 
     // ======================= branches: first walk (down: T V A f u ; up: articulated elimination) =======================
     const int nev_all = 2 * N;
     (void)nev_all;
     for (int b = warp; b < nb; b += W) {
-        double Vc[6], Ac[6];      // V, A of the joint entered last (handed to its first child in registers)
-        double IAc[21], Pc[6];    // articulated inertia / bias force of the joint left last (handed to its parent)
-#pragma unroll
-        for (int i = 0; i < 21; ++i) IAc[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { Pc[i] = 0.0; Vc[i] = 0.0; Ac[i] = 0.0; }
-        int last_entered = -1;
+        // The depth-first event list is walked as alternating RUNS: a run of "enter" events goes down a chain (V / A of
+        // the joint entered last reach its first child in registers), a run of "leave" events comes back up (I^a / p^a
+        // of the joint left last reach its parent in registers when it is an only child). Nothing is carried from one
+        // run into the next -- an enter after a leave is a later child, which reads its parent's block; a leave after an
+        // enter is a leaf -- so each loop keeps only its own hand-off live.
         const int ev0 = B->b_ev0[b], ev1 = B->b_ev1[b];
-        for (int evi = ev0; evi < ev1; ++evi) {
-            const int code = X->dfs_event[evi];
-            if (code >= 0) {
+        int evi = ev0;
+        while (evi < ev1) {
+            double Vc[6], Ac[6];      // V, A of the joint entered last
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { Vc[i] = 0.0; Ac[i] = 0.0; }
+            int last_entered = -1;
+            for (; evi < ev1; ++evi) {
+                const int code = X->dfs_event[evi];
+                if (code < 0) break;
                 // ---------------- enter joint j ----------------
                 const int j = code;
                 const int lv = X->level[j];
@@ -407,7 +467,18 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                     }
                 }
                 sc[(size_t)B->aba_off[j] * kTile] = kdm * dt;  // masked Kd dt, first scratch slot of the joint
-            } else {
+#ifdef TRL_PD_CLK
+                PD_CLK(clk_i); ++clk_i;
+#endif
+            }
+            double IAc[21], Pc[6];    // articulated inertia / bias force of the joint left last
+#pragma unroll
+            for (int i = 0; i < 21; ++i) IAc[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Pc[i] = 0.0;
+            for (; evi < ev1; ++evi) {
+                const int code = X->dfs_event[evi];
+                if (code >= 0) break;
                 // ---------------- leave joint j: its subtree is complete ----------------
                 const int j = -1 - code;
                 const int lv = X->level[j];
@@ -497,10 +568,15 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
 #pragma unroll
                     for (int i = 0; i < 6; ++i) Xp[(33 + i) * kTile] += P[i];
                 }
+#ifdef TRL_PD_CLK
+                PD_CLK(clk_i); ++clk_i;
+#endif
             }
         }
     }
+    PD_CLK(16);
     __syncthreads();
+    PD_CLK(17);
 
     // ======================= root: (S^T I^A S) qdd = -S^T p^A, S = [rows of R(q_root) | e_x e_y e_z] (warp 0) =======================
     const int np = n | 1;
@@ -508,6 +584,9 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     if (warp == 0) {
         double IA[21], P[6];
         {
+            const double Tid[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+            double Ir[10];
+            aba_inertia(Tid, cst, Ir);  // constant: the root body in its own frame
             const double m = Ir[0], h0 = Ir[1], h1 = Ir[2], h2 = Ir[3];
             IA[sym6(0, 0)] = Ir[4]; IA[sym6(0, 1)] = Ir[5]; IA[sym6(0, 2)] = Ir[6];
             IA[sym6(1, 1)] = Ir[7]; IA[sym6(1, 2)] = Ir[8]; IA[sym6(2, 2)] = Ir[9];
@@ -519,7 +598,7 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             IA[sym6(5, 5)] = m;
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) P[i] = fr[i];
+        for (int i = 0; i < 6; ++i) P[i] = ws[(12 + i) * kTile];
         for (int b = 0; b < nb; ++b) {
             const double* O = ws + (size_t)(kOut + 27 * b) * kTile;
 #pragma unroll
@@ -587,7 +666,12 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             ws[r * kTile] = s;  // delta of the root (V is dead)
         }
     }
+    PD_CLK(18);
     __syncthreads();
+    PD_CLK(19);
+#ifdef TRL_PD_CLK
+    clk_i = 20;
+#endif
 
     // ======================= second walk: qdd_j = D^-1 (uh - U^T delta_p), delta_j = delta_p + S_j qdd_j, tau =======================
     // tau is staged as [32][n | 1] rows (conflict-free for the per-env writes here and for the coalesced write below) in the
@@ -645,19 +729,40 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                     put_tau(o + i, sj[(1 + 14 * nc + nd) * kTile]);
                     ++nd;
                 }
+#ifdef TRL_PD_CLK
+            PD_CLK(clk_i); ++clk_i;
+#endif
         }
     }
     if (status) atomicOr(&s_status[lane], status);
+    PD_CLK(28);
     __syncthreads();
+    PD_CLK(29);
     if (staged) {
+        // [32][np] staging rows -> the tile's contiguous [envs][n] block of tau, coalesced. Row / column of a flat index
+        // by a multiply-shift (exact for idx < 2^20 / n), four elements in flight per thread.
         const double* st = ws0 + (size_t)kOut * kTile;
         double* out = p.tau + (size_t)e0 * n;
         const int total = envs * n;
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            const int r = idx / n, c = idx - r * n;
-            const double v = st[r * np + c];
-            out[idx] = p.tau_accumulate ? out[idx] + v : v;
+        const unsigned magic = ((1u << 20) + (unsigned)n - 1u) / (unsigned)n;
+        for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+            double v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = base + k * blockDim.x;
+                if (idx < total) {
+                    const int r = (int)(((unsigned)idx * magic) >> 20), c = idx - r * n;
+                    v[k] = st[r * np + c];
+                    if (p.tau_accumulate) v[k] += out[idx];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = base + k * blockDim.x;
+                if (idx < total) out[idx] = v[k];
+            }
         }
     }
     if (p.status && threadIdx.x < envs) p.status[e0 + threadIdx.x] = s_status[threadIdx.x];
+    PD_CLK(30);
 }
