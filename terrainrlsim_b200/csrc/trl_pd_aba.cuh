@@ -409,16 +409,14 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
                     if (tar[0] * tar[0] + tar[1] * tar[1] + tar[2] * tar[2] + tar[3] * tar[3] == 0.0) tar[0] = 1.0;
                     else quat_normalize(tar);
                     if (world) {  // tar = rel_rot * (world_rot^-1 * tar), PDController.cpp:254-267
+                        // rel_rot = AxisAngleToQuaternion(QuaternionToAxisAngle(q_j)) (util/MathUtil.cpp:399-416): with theta =
+                        // 2 sg asin(st) the round trip is [cos(asin st), sin(sg asin st) q_xyz / st] = [sqrt((1 - st)(1 + st)),
+                        // sg q_xyz] -- no asin, sincos or divisions; the identity below the 1e-4 threshold and for q_w == 0
                         const double st = sqrt(qj[1] * qj[1] + qj[2] * qj[2] + qj[3] * qj[3]);
-                        double ax3[3] = {0, 0, 1}, th = 0.0;
-                        if (st > 0.0001) {
-                            const double sg = (double)((0.0 < qj[0]) - (qj[0] < 0.0));
-                            th = 2 * sg * asin(st);
-                            ax3[0] = qj[1] / st; ax3[1] = qj[2] / st; ax3[2] = qj[3] / st;
-                        }
-                        double sh, ch;
-                        sincos(th / 2, &sh, &ch);
-                        const double rel[4] = {ch, sh * ax3[0], sh * ax3[1], sh * ax3[2]};
+                        const double sg = (double)((0.0 < qj[0]) - (qj[0] < 0.0));
+                        const bool turn = (st > 0.0001) && (sg != 0.0);
+                        const double ch = turn ? sqrt((1.0 - st) * (1.0 + st)) : 1.0;
+                        const double rel[4] = {ch, turn ? sg * qj[1] : 0.0, turn ? sg * qj[2] : 0.0, turn ? sg * qj[3] : 0.0};
                         double wq[4];
                         pb_rot_to_quat(Wm, wq);
                         const double wc[4] = {wq[0], -wq[1], -wq[2], -wq[3]};
@@ -607,23 +605,33 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             for (int i = 0; i < 6; ++i) P[i] += O[(21 + i) * kTile];
         }
         double rq9[9];
-        quat_to_mat(q[3], q[4], q[5], q[6], rq9);
-        double S[6][6];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            S[c][0] = S[c][1] = S[c][2] = 0.0;
-            S[c][3] = rq9[3 * c]; S[c][4] = rq9[3 * c + 1]; S[c][5] = rq9[3 * c + 2];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) S[3 + c][r] = (r == c) ? 1.0 : 0.0;
-        }
+        quat_to_mat(q_root[0], q_root[1], q_root[2], q_root[3], rq9);
+        // S = [0 I; Q^T 0] in (omega; v) rows: the three translation columns are the rows of Q = R(q_root) in the linear part,
+        // the three rotation columns are unit angular vectors. Hence
+        //   A = S^T I^A S = [Q Ivv Q^T, Q Ivw; Iwv Q^T, Iww],   b = -S^T p^A = -[Q p_v; p_w]
+        // with the 3x3 blocks Iww = IA(0:3, 0:3), Iwv = IA(0:3, 3:6), Ivv = IA(3:6, 3:6), Ivw = Iwv^T.
         double A[6][6], bb[6];
+        {
+            double QI[3][3];  // Q Ivv
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            double U[6];
-            sym6_mulv(IA, S[c], U);
-            bb[c] = -dot6(S[c], P);
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int r = 0; r <= c; ++r) A[c][r] = dot6(S[r], U);  // lower triangle
+                for (int c = 0; c < 3; ++c)
+                    QI[r][c] = rq9[3 * r] * IA[sym6(3, 3 + c)] + rq9[3 * r + 1] * IA[sym6(4, 3 + c)] + rq9[3 * r + 2] * IA[sym6(5, 3 + c)];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c <= r; ++c)  // lower triangle of Q Ivv Q^T
+                    A[r][c] = QI[r][0] * rq9[3 * c] + QI[r][1] * rq9[3 * c + 1] + QI[r][2] * rq9[3 * c + 2];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    // A[3 + c][r] = (Iwv Q^T)(c, r) = sum_k IA(c, 3 + k) Q(r, k)
+                    A[3 + c][r] = IA[sym6(c, 3)] * rq9[3 * r] + IA[sym6(c, 4)] * rq9[3 * r + 1] + IA[sym6(c, 5)] * rq9[3 * r + 2];
+                    if (c <= r) A[3 + r][3 + c] = IA[sym6(r, c)];
+                }
+                bb[r] = -(rq9[3 * r] * P[3] + rq9[3 * r + 1] * P[4] + rq9[3 * r + 2] * P[5]);
+                bb[3 + r] = -P[r];
+            }
         }
         // unpivoted LDL^T (S^T I^A S is symmetric positive definite), forward / back substitution
         double Lm[6][6], dd[6], dinv[6];
@@ -659,11 +667,9 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             x[k] = v;
         }
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            double s = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) s += S[c][r] * x[c];
-            ws[r * kTile] = s;  // delta of the root (V is dead)
+        for (int r = 0; r < 3; ++r) {  // delta of the root = S x = (x_ang; Q^T x_lin)  (V is dead)
+            ws[r * kTile] = x[3 + r];
+            ws[(3 + r) * kTile] = rq9[r] * x[0] + rq9[3 + r] * x[1] + rq9[6 + r] * x[2];
         }
     }
     PD_CLK(18);
@@ -705,21 +711,31 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
             const int c0 = X->first_col[j], nc = X->ncol[j];
             const double* sj = sc + (size_t)B->aba_off[j] * kTile;
             const double kdmdt = sj[0];
-            for (int a = nc - 1; a >= 0; --a) {  // reverse order of the elimination
-                double S[6], Us[6];
-                const double u = sj[(1 + a) * kTile];
-                double qdd = sj[(1 + nc + a) * kTile];
+            // every column's hand-off (u, D^-1 uh, S, U D^-1) is requested before the first one is used: one trip to L2 per
+            // joint instead of one per column
+            double cu[3], cq[3], cS[3][6], cU[3][6];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    S[r] = sj[(1 + 2 * nc + 6 * a + r) * kTile];
-                    Us[r] = sj[(1 + 8 * nc + 6 * a + r) * kTile];
+            for (int a = 0; a < 3; ++a) {
+                if (a < nc) {
+                    cu[a] = sj[(1 + a) * kTile];
+                    cq[a] = sj[(1 + nc + a) * kTile];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) {
+                        cS[a][r] = sj[(1 + 2 * nc + 6 * a + r) * kTile];
+                        cU[a][r] = sj[(1 + 8 * nc + 6 * a + r) * kTile];
+                    }
                 }
-                qdd -= dot6(Us, dl);
+            }
 #pragma unroll
-                for (int r = 0; r < 6; ++r) dl[r] += S[r] * qdd;
-                const double tv = u - kdmdt * qdd;
-                if (!isfinite(tv)) status |= 1;
-                put_tau(X->col_dof[c0 + a], tv);
+            for (int a = 2; a >= 0; --a) {  // reverse order of the elimination
+                if (a < nc) {
+                    double qdd = cq[a] - dot6(cU[a], dl);
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) dl[r] += cS[a][r] * qdd;
+                    const double tv = cu[a] - kdmdt * qdd;
+                    if (!isfinite(tv)) status |= 1;
+                    put_tau(X->col_dof[c0 + a], tv);
+                }
             }
 #pragma unroll
             for (int r = 0; r < 6; ++r) Wl[r * kTile] = dl[r];
@@ -744,15 +760,19 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         const double* st = ws0 + (size_t)kOut * kTile;
         double* out = p.tau + (size_t)e0 * n;
         const int total = envs * n;
-        const unsigned magic = ((1u << 20) + (unsigned)n - 1u) / (unsigned)n;
+        const unsigned magic = (np == n) ? 0u : ((1u << 20) + (unsigned)n - 1u) / (unsigned)n;
         for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
             double v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int idx = base + k * blockDim.x;
                 if (idx < total) {
-                    const int r = (int)(((unsigned)idx * magic) >> 20), c = idx - r * n;
-                    v[k] = st[r * np + c];
+                    int si = idx;  // odd n: the staging rows are dense
+                    if (np != n) {
+                        const int r = (int)(((unsigned)idx * magic) >> 20);
+                        si = idx + r;  // r * np + (idx - r * n) with np = n + 1
+                    }
+                    v[k] = st[si];
                     if (p.tau_accumulate) v[k] += out[idx];
                 }
             }

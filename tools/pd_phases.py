@@ -29,7 +29,7 @@ f = _capi.lib().trl_debug_pd_clk
 f.argtypes = [C.c_void_p]
 assert f(buf.ctypes.data) == 0
 names = {0: "start", 1: "staged", 2: "root down", 3: "barrier", 16: "walk1 end", 17: "barrier", 18: "root solve", 19: "barrier",
-         28: "walk2 end", 29: "barrier", 30: "end"}
+         10: "  hip: local trans", 11: "  hip: T V A", 12: "  hip: body f", 14: "  hip: world tar", 13: "  hip: quat_vel_rel", 28: "walk2 end", 29: "barrier", 30: "end"}
 t0 = buf[0, 0]
 for w in range(8):
     if buf[w, 0] == 0:
