@@ -760,8 +760,32 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
         const double* st = ws0 + (size_t)kOut * kTile;
         double* out = p.tau + (size_t)e0 * n;
         const int total = envs * n;
+        const bool dense = (np == n) && ((reinterpret_cast<size_t>(out) & 15) == 0);
+        if (dense) {
+            // odd n, 16-byte aligned block: the staging rows ARE the output block -- a flat 16-byte copy with
+            // eight elements in flight per thread and no index arithmetic
+            const double2* st2 = reinterpret_cast<const double2*>(st);
+            double2* out2 = reinterpret_cast<double2*>(out);
+            const int pairs = total >> 1;
+            for (int base = threadIdx.x; base < pairs; base += 8 * blockDim.x) {
+                double2 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (base + k * (int)blockDim.x < pairs) {
+                        v[k] = st2[base + k * blockDim.x];
+                        if (p.tau_accumulate) {
+                            const double2 o = out2[base + k * blockDim.x];
+                            v[k].x += o.x; v[k].y += o.y;
+                        }
+                    }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (base + k * (int)blockDim.x < pairs) out2[base + k * blockDim.x] = v[k];
+            }
+            if ((total & 1) && threadIdx.x == 0) out[total - 1] = p.tau_accumulate ? out[total - 1] + st[total - 1] : st[total - 1];
+        }
         const unsigned magic = (np == n) ? 0u : ((1u << 20) + (unsigned)n - 1u) / (unsigned)n;
-        for (int base = threadIdx.x; base < total; base += 4 * blockDim.x) {
+        for (int base = threadIdx.x; base < (dense ? 0 : total); base += 4 * blockDim.x) {
             double v[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
