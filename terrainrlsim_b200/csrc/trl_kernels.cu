@@ -996,39 +996,52 @@ struct ObsEnvRec {
     int interior;  // bit 0 (`up` only): the window keeps a cell of distance from the grid's edge, the clamps cannot fire;
                    // bit 1: operands in the range where the division-by-spacing sequence needs no guard
     int staged;    // bit 1 of `interior` holds and the rectangles (of `up`, or of all candidates) fit the patch buffers
+    // --- the sample kernels read the 160 bytes above; k_obs_feat also needs: ---
+    double ground_h;  // ground height under the root as sampled (non-finite outside the terrain, like the reference's)
+    double pad_;
 };
-static_assert(sizeof(ObsEnvRec) == 160, "read with 16-byte loads");
+static_assert(sizeof(ObsEnvRec) == 176 && offsetof(ObsEnvRec, ground_h) == 160, "read with 16-byte loads");
+constexpr int kRecSampleQ = 10;  // 16-byte words of the record the sample kernels read
 
-// k_obs_env: BuildGroundSampleTrans + BuildPoliStatePose/Vel (+ phase / hopper / stance flip) -- kObsG lanes per env (the per-env prologue is redundant across the lanes, so few lanes win).
-// Everything that is per-env (heading, origin transform, ground height under the root) is computed once here.
-constexpr int kObsG = 2;  // measured inside the overlapped step: 1 -> 0.1115 ms, 2 -> 0.1083, 4 -> 0.1136, 8 -> 0.1195
+// k_obs_rec: BuildGroundSampleTrans for one env -- heading, origin transform, ground height under the root, and how the
+// env's sample window maps onto the pieces of its terrain (the record k_obs_samples / k_obs_gather work from). FOUR LANES
+// PER ENV, LANE = TERRAIN PIECE: the reference scans the (<= 4) pieces of a terrain one after the other, and so did the
+// first version of this kernel, one dependent load chain per piece (heading -> piece search -> heights -> cell ranges was
+// 20 k cycles of latency per env at one warp per sub-partition). Here every lane tests / maps its own piece and the group
+// combines the results with one ballot; the per-env arithmetic is simply repeated on the four lanes.
+constexpr int kRecG = 4;
+static_assert(kRecG == 4, "one lane per terrain piece (TRL pieces per field <= 4)");
 
 __global__ void __launch_bounds__(128)
-k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
-          const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
-          const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
-          const double* __restrict__ ground_vel, const double* __restrict__ phase,
+k_obs_rec(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
           const unsigned char* __restrict__ flip_arr, const double* __restrict__ sample_local,
           ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
     KTrace trace_(TR_OBS_ENV);
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = tid % kObsG;
-    const int e_raw = tid / kObsG;
+    const int s = tid & (kRecG - 1);  // this lane's piece
+    const int e_raw = tid / kRecG;
     const bool env_ok = e_raw < E;
     const int e = env_ok ? e_raw : E - 1;
+    const unsigned gshift = (unsigned)(threadIdx.x & 31 & ~(kRecG - 1));  // first lane of the env's group in the warp
     const int N = M->N, n = M->n;
     const ObsDims D = obs_dims(N, cfg);
     const double* q = pose + (size_t)e * n;
-    double* out = out_state + (size_t)e * D.F;
     const int flip = flip_arr ? (flip_arr[e] != 0) : 0;
     const int gkind = g.kind, gP = g.pieces_per_field;
     const bool has_ground = gkind != 0;
+    const bool field = (gkind == 1 || gkind == 2);
+    // this lane's piece: bounds and origin are requested now, before the heading arithmetic needs the root pose
+    const DevPiece* pcs = field ? g.pieces + (long long)ground_field_of_env(g, e) * gP : nullptr;
+    const bool mine = field && s < gP;
+    double b0 = 0, b1 = 0, b2 = 0, b3 = 0, pox = 0, poz = 0;
+    if (mine) {
+        const DevPiece& pc = pcs[s];
+        b0 = pc.bounds[0]; b1 = pc.bounds[1]; b2 = pc.bounds[2]; b3 = pc.bounds[3];
+        pox = pc.origin[0]; poz = pc.origin[2];
+    }
 
     // cKinTree::CalcHeading / BuildOriginTrans (anim/KinTree.cpp:1604-1639): origin = Ry(-heading) * T(-root_xz)
-    const double rx = q[0], ry = q[1], rz = q[2];
+    const double rx = q[0], rz = q[2];
     const double qr[4] = {q[3], q[4], q[5], q[6]};
     const double xdir[3] = {1, 0, 0};
     double rd[3];
@@ -1045,12 +1058,15 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     const double ot1 = oz * nx + o11 * ny + oz * nz;
     const double ot2 = o20 * nx + oz * ny + o22 * nz;
 
-    // ground height under the root (TerrainRLCharController.cpp:261-279,370-380)
+    // ground height under the root (TerrainRLCharController.cpp:261-279,370-380): the first piece (in scan order) that
+    // contains the root position -- every lane tests its own piece, the lowest set bit of the group's ballot wins
     double ground_h = 0.0;
-    if (gkind == 1 || gkind == 2) {
-        const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
+    if (field) {
+        const bool hit = mine && ((gkind == 1) ? (rx >= b0 && rx <= b1) : (rx >= b0 && rx <= b1 && rz >= b2 && rz <= b3));
+        const unsigned hm = (__ballot_sync(0xffffffffu, hit) >> gshift) & 0xfu;
+        const int pi = hm ? (__ffs(hm) - 1) : -1;
         int v0, c0[3];
-        ground_h = ground_sample_pieces(gkind, gP, pcs, g.data, rx, rz, &v0, c0);
+        ground_h = ground_sample_piece(gkind, pcs, pi, g.data, rx, rz, &v0, c0);
     }
     const double ground_h_finite = isfinite(ground_h) ? ground_h : 0.0;
 
@@ -1059,113 +1075,148 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     const double it0 = -(i00 * ot0 + oz * ot1 + i02 * ot2);
     const double it1 = -(oz * ot0 + i11 * ot1 + oz * ot2) + ground_h_finite;
     const double it2 = -(i20 * ot0 + oz * ot1 + i22 * ot2);
-    if (lane == 0 && env_ok) {
-        ObsEnvRec r;
-        r.i00 = i00; r.i02 = i02; r.i20 = i20; r.i22 = i22; r.it0 = it0; r.it1 = it1; r.it2 = it2;
-        r.flip = flip; r.has_ground = has_ground ? 1 : 0;
+
+    // ---- the sample window on the terrain pieces ----
+    int cand = 0xf, up = -1, interior = 0, staged = 0;  // candidates: all pieces unless the bounding-box test narrows them
+    long long my_off = 0;
+    int my_pitch = 0, my_ph = 0, my_shift = 0;
+    if (field && cfg.num_samples > 0 && sample_local) {
+        // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
+        // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
+        // box is widened by a few ulps because the sample kernel may contract the same expression differently.
+        const double* bb = sample_local + 2 * cfg.num_samples;
+        const double lx[2] = {__ldg(bb), __ldg(bb + 1)};
+        double lz[2] = {__ldg(bb + 2), __ldg(bb + 3)};
+        if (flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D)) {
+            const double tt = lz[0];
+            lz[0] = -lz[1];
+            lz[1] = -tt;
+        }
+        double x0 = CUDART_INF, x1 = -CUDART_INF, z0 = CUDART_INF, z1 = -CUDART_INF;
+        bool finite = true;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) { r.src_off[s] = 0; r.pitch[s] = r.ph[s] = r.shift[s] = 0; }
-        r.cand = 0xf;  // candidate pieces of the per-sample search (all, unless the bounding-box test below narrows it)
-        r.up = -1;
-        r.interior = 0;
-        r.staged = 0;
-        if ((gkind == 1 || gkind == 2) && cfg.num_samples > 0 && sample_local) {
-            // Bounding box of all sample positions: the position is affine (hence weakly monotone, also after
-            // rounding) in the local coordinates, so its extremes sit at the corners of the local bounding box. The
-            // box is widened by a few ulps because the sample kernel may contract the same expression differently.
-            const double* bb = sample_local + 2 * cfg.num_samples;
-            const double lx[2] = {__ldg(bb), __ldg(bb + 1)};
-            double lz[2] = {__ldg(bb + 2), __ldg(bb + 3)};
-            if (flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D)) {
-                const double t = lz[0];
-                lz[0] = -lz[1];
-                lz[1] = -t;
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const double px = i00 * lx[a] + i02 * lz[b] + it0;
+                const double pz = i20 * lx[a] + i22 * lz[b] + it2;
+                finite = finite && isfinite(px) && isfinite(pz);
+                x0 = (px < x0) ? px : x0; x1 = (px > x1) ? px : x1;
+                z0 = (pz < z0) ? pz : z0; z1 = (pz > z1) ? pz : z1;
             }
-            double x0 = CUDART_INF, x1 = -CUDART_INF, z0 = CUDART_INF, z1 = -CUDART_INF;
-            bool finite = true;
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const double px = i00 * lx[a] + i02 * lz[b] + it0;
-                    const double pz = i20 * lx[a] + i22 * lz[b] + it2;
-                    finite = finite && isfinite(px) && isfinite(pz);
-                    x0 = (px < x0) ? px : x0; x1 = (px > x1) ? px : x1;
-                    z0 = (pz < z0) ? pz : z0; z1 = (pz > z1) ? pz : z1;
-                }
-            const double ex = 1e-12 * (fabs(x0) + fabs(x1) + 1.0), ez = 1e-12 * (fabs(z0) + fabs(z1) + 1.0);
-            x0 -= ex; x1 += ex; z0 -= ez; z1 += ez;
+        const double ex = 1e-12 * (fabs(x0) + fabs(x1) + 1.0), ez = 1e-12 * (fabs(z0) + fabs(z1) + 1.0);
+        x0 -= ex; x1 += ex; z0 -= ez; z1 += ez;
+        {   // (`finite` is uniform over an env's four lanes but not over the warp: the ballots below are unconditional,
+            // a non-finite box simply touches nothing and the record keeps its defaults)
+            // The staged sample code divides by the grid spacing with the unguarded correction sequence of
+            // div_by_const, exact for operands x = pos - origin with x == 0 or 2^-900 < |x| < 2^900. Every quantity x
+            // is built from being zero or in [2^-300, 2^300] guarantees that (the sample table is checked on the host).
+            auto okmag = [](double v) { const double a = fabs(v); return a == 0.0 || (a >= 0x1p-300 && a <= 0x1p300); };
+            const bool safe0 = g.table_ok != 0 && okmag(i00) && okmag(i02) && okmag(i20) && okmag(i22) && okmag(it0) && okmag(it2) &&
+                               fabs(x0) < 0x1p300 && fabs(x1) < 0x1p300 && fabs(z0) < 0x1p300 && fabs(z1) < 0x1p300;
+            // Cell range of the box in a piece's grid. The estimate (plain arithmetic) is within a tiny fraction of a
+            // cell of the exact coordinate sequence used per sample; one cell of slack on either side absorbs it, one
+            // more on the high side holds the i + 1 / j + 1 vertices.
+            auto range = [](double lo_w, double hi_w, double o, double rs, double half, int res, int& first, int& count, bool& clear) {
+                const double ca = (lo_w - o) * rs + half, cb = (hi_w - o) * rs + half;
+                double lo = (ca < cb) ? ca : cb, hi = (ca < cb) ? cb : ca;
+                lo = clampd(lo, -4.0, 1.0e9);
+                hi = clampd(hi, -4.0, 1.0e9);
+                const int ilo = (int)floor(lo) - 1, ihi = (int)floor(hi) + 2;
+                clear = ilo >= 0 && ihi <= res - 1;
+                first = max(ilo, 0);
+                count = max(min(ihi, res - 1) - first + 1, 0);
+            };
+            // this lane's piece against the box
+            const bool inside = finite && mine && ((gkind == 1) ? (x0 >= b0 && x1 <= b1) : (x0 >= b0 && x1 <= b1 && z0 >= b2 && z1 <= b3));
+            const bool apart = !finite || !mine || ((gkind == 1) ? (x1 < b0 || x0 > b1) : (x1 < b0 || x0 > b1 || z1 < b2 || z0 > b3));
+            const bool origin_ok = apart || (okmag(pox) && okmag(poz));
+            bool p_inner = false, p_fits = false;
+            int pi0 = 0, pj0 = 0;
+            if (!apart && g.patch_nbuf > 0) {  // cell rectangle, only when k_obs_samples stages
+                const DevPiece& pc = pcs[s];
+                bool cx, cz = true;
+                int first_x, count_x, count_z = 1;
+                range(x0, x1, pox, pc.rscale[0], pc.half[0], pc.res_x, first_x, count_x, cx);
+                if (gkind == 2) range(z0, z1, poz, pc.rscale[1], pc.half[1], pc.res_z, pj0, count_z, cz);
+                pi0 = first_x & ~3;  // staged rows start at a column multiple of 4 (16-byte aligned bulk copies)
+                const int pw = first_x + count_x - pi0;
+                my_ph = count_z;
+                my_pitch = pc.pitch;
+                my_off = pc.data_offset + (long long)pj0 * pc.pitch + pi0;
+                p_inner = cx && cz;
+                p_fits = count_x >= 1 && pw <= g.patch_w && count_z >= 1 && count_z <= g.patch_h;
+            }
+            // combine over the pieces (the scan order of the reference = lane order)
+            const unsigned m_touch = (__ballot_sync(0xffffffffu, !apart) >> gshift) & 0xfu;
+            const unsigned m_inside = (__ballot_sync(0xffffffffu, inside) >> gshift) & 0xfu;
+            const unsigned m_ok = (__ballot_sync(0xffffffffu, origin_ok) >> gshift) & 0xfu;
+            const unsigned m_inner = (__ballot_sync(0xffffffffu, p_inner) >> gshift) & 0xfu;
+            const unsigned m_fits = (__ballot_sync(0xffffffffu, p_fits) >> gshift) & 0xfu;
+            // `up`: a piece that holds the whole box with no earlier piece touching it (the scan stops there for every
+            // sample). Scanning in order, that is the last inside-piece at or before the first touching one.
             if (finite) {
-                // The staged sample code divides by the grid spacing with the unguarded correction sequence of
-                // div_by_const, exact for operands x = pos - origin with x == 0 or 2^-900 < |x| < 2^900. Every quantity x
-                // is built from being zero or in [2^-300, 2^300] guarantees that (the sample table is checked on the host).
-                auto okmag = [](double v) { const double a = fabs(v); return a == 0.0 || (a >= 0x1p-300 && a <= 0x1p300); };
-                bool safe = g.table_ok != 0 && okmag(i00) && okmag(i02) && okmag(i20) && okmag(i22) && okmag(it0) && okmag(it2) &&
-                            fabs(x0) < 0x1p300 && fabs(x1) < 0x1p300 && fabs(z0) < 0x1p300 && fabs(z1) < 0x1p300;
-                const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
-                bool open_scan = true;  // no earlier piece touches the box so far
-                int cand = 0;           // pieces the box touches: the only ones a sample of this env can fall into
-                int inner = 0;          // pieces whose rectangle stays clear of the grid's edge
-                int fits = 0;           // pieces whose rectangle fits a patch buffer
-                int pi0[4], pj0[4];
-                // Cell range of the box in a piece's grid. The estimate (plain arithmetic) is within a tiny fraction of a
-                // cell of the exact coordinate sequence used per sample; one cell of slack on either side absorbs it, one
-                // more on the high side holds the i + 1 / j + 1 vertices.
-                auto range = [](double lo_w, double hi_w, double o, double rs, double half, int res, int& first, int& count, bool& clear) {
-                    const double ca = (lo_w - o) * rs + half, cb = (hi_w - o) * rs + half;
-                    double lo = (ca < cb) ? ca : cb, hi = (ca < cb) ? cb : ca;
-                    lo = clampd(lo, -4.0, 1.0e9);
-                    hi = clampd(hi, -4.0, 1.0e9);
-                    const int ilo = (int)floor(lo) - 1, ihi = (int)floor(hi) + 2;
-                    clear = ilo >= 0 && ihi <= res - 1;
-                    first = max(ilo, 0);
-                    count = max(min(ihi, res - 1) - first + 1, 0);
-                };
-#pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    pi0[s] = pj0[s] = 0;
-                    if (s >= gP) continue;
-                    const DevPiece& pc = pcs[s];
-                    const double b0 = pc.bounds[0], b1 = pc.bounds[1], b2 = pc.bounds[2], b3 = pc.bounds[3];
-                    const bool inside = (gkind == 1) ? (x0 >= b0 && x1 <= b1) : (x0 >= b0 && x1 <= b1 && z0 >= b2 && z1 <= b3);
-                    const bool apart = (gkind == 1) ? (x1 < b0 || x0 > b1) : (x1 < b0 || x0 > b1 || z1 < b2 || z0 > b3);
-                    if (open_scan && inside) r.up = s;
-                    if (!apart) {
-                        cand |= 1 << s;
-                        open_scan = false;  // a later piece can only be "first containing" for some samples
-                        safe = safe && okmag(pc.origin[0]) && okmag(pc.origin[2]);
-                    }
-                    if (!apart && g.patch_nbuf > 0) {  // cell rectangle, only when k_obs_samples stages
-                        bool cx, cz = true;
-                        int first_x, count_x, count_z = 1;
-                        range(x0, x1, pc.origin[0], pc.rscale[0], pc.half[0], pc.res_x, first_x, count_x, cx);
-                        if (gkind == 2) range(z0, z1, pc.origin[2], pc.rscale[1], pc.half[1], pc.res_z, pj0[s], count_z, cz);
-                        pi0[s] = first_x & ~3;  // staged rows start at a column multiple of 4 (16-byte aligned bulk copies)
-                        const int pw = first_x + count_x - pi0[s];
-                        r.ph[s] = count_z;
-                        r.pitch[s] = pc.pitch;
-                        r.src_off[s] = pc.data_offset + (long long)pj0[s] * pc.pitch + pi0[s];
-                        if (cx && cz) inner |= 1 << s;
-                        if (count_x >= 1 && pw <= g.patch_w && count_z >= 1 && count_z <= g.patch_h) fits |= 1 << s;
-                    }
-                }
-                r.cand = cand;
-                const int smask = (r.up >= 0) ? (1 << r.up) : cand;
-                int nb = 0;
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    if ((smask >> s) & 1) {
-                        r.shift[s] = nb * g.patch_w * g.patch_h - pj0[s] * g.patch_w - pi0[s];
-                        ++nb;
-                    }
-                r.staged = (safe && smask != 0 && (fits & smask) == smask && nb <= g.patch_nbuf) ? 1 : 0;
-                r.interior = ((r.up >= 0 && ((inner >> r.up) & 1)) ? 1 : 0) | (safe ? 2 : 0);
+                const int first_touch = m_touch ? (__ffs(m_touch) - 1) : 3;
+                const unsigned up_set = m_inside & ((2u << first_touch) - 1u);
+                up = up_set ? (31 - __clz(up_set)) : -1;
+                cand = (int)m_touch;
+                const bool safe = safe0 && m_ok == 0xfu;
+                const unsigned smask = (up >= 0) ? (1u << up) : m_touch;
+                const int nb = __popc(smask);
+                if ((smask >> s) & 1u) my_shift = __popc(smask & ((1u << s) - 1u)) * g.patch_w * g.patch_h - pj0 * g.patch_w - pi0;
+                staged = (safe && smask != 0 && (m_fits & smask) == smask && nb <= g.patch_nbuf) ? 1 : 0;
+                interior = ((up >= 0 && ((m_inner >> up) & 1u)) ? 1 : 0) | (safe ? 2 : 0);
             }
         }
-        rec[e] = r;
     }
-    if (!env_ok) return;
+    if (env_ok) {
+        ObsEnvRec* r = rec + e;
+        r->src_off[s] = my_off; r->pitch[s] = my_pitch; r->ph[s] = my_ph; r->shift[s] = my_shift;
+        if (s == 0) {
+            r->i00 = i00; r->i02 = i02; r->i20 = i20; r->i22 = i22; r->it0 = it0; r->it1 = it1; r->it2 = it2;
+            r->flip = flip; r->has_ground = has_ground ? 1 : 0;
+            r->cand = cand; r->up = up; r->interior = interior; r->staged = staged;
+            r->ground_h = ground_h;
+        }
+        if (!M->bx.all_valid) {  // the reference starts from VectorXd::Zero(psize): slots of shape-less bodies stay zero
+            double* opose = out_state + (size_t)e * D.F + D.G;
+            for (int i = 1 + s; i < D.psize; i += kRecG) opose[i] = 0.0;
+        }
+    }
+}
 
+// k_obs_feat: BuildPoliStatePose / Vel (+ phase / hopper / stance flip) -- THREAD PER (env, body). Each thread rebuilds the
+// origin transform from the env's record (the heading terms are the record's rotation entries) and writes its body's
+// feature slots; body 0's thread also writes the root height and the phase block.
+__global__ void __launch_bounds__(128)
+k_obs_feat(const DevModel* __restrict__ M, trl_obs_cfg cfg, int E, const double* __restrict__ pose,
+           const double* __restrict__ vel, const double* __restrict__ body_pos, const double* __restrict__ body_vel,
+           const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
+           const double* __restrict__ ground_vel, const double* __restrict__ phase,
+           const ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+    const int N = M->N, n = M->n;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long long)E * N) return;
+    const int e = (int)(tid / N);
+    const int i = (int)(tid - (long long)e * N);  // this thread's body
+    const ModelIdx* X = &M->ix;
+    const ObsDims D = obs_dims(N, cfg);
+    const double* q = pose + (size_t)e * n;
+    double* out = out_state + (size_t)e * D.F;
+    const ObsEnvRec* r = rec + e;
+    const double rx = q[0], ry = q[1], rz = q[2];
+    const double qr[4] = {q[3], q[4], q[5], q[6]};
+    const int flip = r->flip;
+    const double ground_h = r->ground_h;
+    // origin transform: the record holds its inverse rotation (i00 = o00, i02 = o20, i20 = o02, i22 = o22)
+    const double ch = r->i00, sh = r->i20;
+    const double o00 = ch, o02 = sh, o20 = -sh, o22 = ch;
+    const double o11 = ch + (1 - ch);
+    const double oz = 0.0;  // structurally-zero entries, kept in the products so inf/NaN propagate like the reference
+    const double nx = -rx, ny = -0.0, nz = -rz;
+    const double ot0 = o00 * nx + oz * ny + o02 * nz;
+    const double ot1 = oz * nx + o11 * ny + oz * nz;
+    const double ot2 = o20 * nx + oz * ny + o22 * nz;
     // ---- pose block ----
     double* opose = out + D.G;
     double* ovel = opose + D.psize;
@@ -1174,7 +1225,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     const double rr0 = o00 * rx + oz * ryg + o02 * rz + ot0;
     const double rr1 = oz * rx + o11 * ryg + oz * rz + ot1;
     const double rr2 = zsign * (o20 * rx + oz * ryg + o22 * rz + ot2);
-    if (lane == 0) opose[0] = rr1;
+    if (i == 0) opose[0] = rr1;
     const int first = D.is_ct ? 0 : 1;
     const int per = D.pos_dim + (D.is3d ? 4 : 0);
     // cBipedController3D::FlipPoliPoseStance (BipedController3D.cpp:1811-1830) swaps the two leg blocks at the tail
@@ -1187,13 +1238,8 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         if (a < 2 * nlp) return idx + nlp;      // first leg block -> second
         return idx;
     };
-    if (!M->bx.all_valid) {  // the reference starts from VectorXd::Zero(psize): slots of shape-less bodies stay zero
-        for (int i = 1 + lane; i < D.psize; i += kObsG) opose[i] = 0.0;
-        __syncwarp();  // the lanes of an env zero each other's slots: order them before the body writes below
-    }
-    for (int i = first + lane; i < N; i += kObsG) {
-        const int slot = D.is_ct ? X->slot_ct[i] : X->slot_base[i];
-        if (slot < 0) continue;
+    const int slot = (i >= first) ? (D.is_ct ? X->slot_ct[i] : X->slot_base[i]) : -1;
+    if (slot >= 0) {
         const double* bp = body_pos + ((size_t)e * N + i) * 3;
         const double bx = bp[0], by = bp[1] - ground_h, bz = bp[2];
         const double f0 = (o00 * bx + oz * by + o02 * bz + ot0) - rr0;
@@ -1220,7 +1266,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     if (ground_vel) { gv[0] = ground_vel[3 * (size_t)e]; gv[1] = ground_vel[3 * (size_t)e + 1]; gv[2] = ground_vel[3 * (size_t)e + 2]; }
     const int vper = D.pos_dim + (D.is3d ? 3 : 0);
     const bool hopper = cfg.obs_kind == TRL_OBS_TERRAIN_RL_HOPPER;
-    for (int i = lane; i < N; i += kObsG) {
+    {
         const double* bv = body_vel + ((size_t)e * N + i) * 3;
         const double vx = bv[0] - gv[0], vy = bv[1] - gv[1], vz = bv[2] - gv[2];
         const int b0 = i * vper;
@@ -1243,7 +1289,7 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
     // cMonopedHopperController::BuildPoliStatePose: the last pose entry is overwritten by the signed root rotation
     // angle (cSimCharacter::GetRootRotation -> RotMatToAxisAngle, util/MathUtil.cpp:239-260). That entry belongs to
     // body N-1, so the write is issued from that body's lane to keep program order.
-    if (hopper && lane == ((N - 1 - first) % kObsG)) {
+    if (hopper && i == N - 1) {
         double R[9];
         quat_to_mat(qr[0], qr[1], qr[2], qr[3], R);
         double c = (R[0] + R[4] + R[8] - 1) * 0.5;
@@ -1257,10 +1303,10 @@ k_obs_env(const DevModel* __restrict__ M, DevGround g, trl_obs_cfg cfg, int E, c
         if (az < 0) theta = -theta;
         opose[D.psize - 1] = theta;
     }
-    if (cfg.num_phase_bins >= 0 && lane == 0) {  // cCtPhaseController::BuildPhaseState (CtPhaseController.cpp:120-139)
+    if (cfg.num_phase_bins >= 0 && i == 0) {  // cCtPhaseController::BuildPhaseState (CtPhaseController.cpp:120-139)
         double* ph = ovel + D.vsize;
         const double pv = phase ? phase[e] : 0.0;
-        for (int i = 0; i < 1 + cfg.num_phase_bins; ++i) ph[i] = 0.0;
+        for (int k = 0; k < 1 + cfg.num_phase_bins; ++k) ph[k] = 0.0;
         ph[0] = pv;
         if (cfg.num_phase_bins > 0) {
             const int bin = (int)(pv * cfg.num_phase_bins);
@@ -1386,7 +1432,7 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
         const uint4* src = reinterpret_cast<const uint4*>(rec + e);
         uint4* dst = reinterpret_cast<uint4*>(&r);
 #pragma unroll
-        for (int k = 0; k < (int)(sizeof(ObsEnvRec) / 16); ++k) dst[k] = __ldg(src + k);
+        for (int k = 0; k < kRecSampleQ; ++k) dst[k] = __ldg(src + k);
     }
     const bool flip_z = r.flip && (cfg.obs_kind == TRL_OBS_CT || cfg.obs_kind == TRL_OBS_CT_3D);
     const double i02 = flip_z ? -r.i02 : r.i02, i22 = flip_z ? -r.i22 : r.i22;  // local z -> -z folded into the map
@@ -1560,7 +1606,7 @@ k_obs_gather(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __rest
     const int gP = g.pieces_per_field;
     const DevPiece* pcs = g.pieces + (long long)ground_field_of_env(g, e) * gP;
     {
-        constexpr int kRecW = (int)(sizeof(ObsEnvRec) / 16);
+        constexpr int kRecW = kRecSampleQ;
         const int pw = gP * (int)(sizeof(DevPiece) / 16);
         for (int t = threadIdx.x; t < pw + kRecW; t += blockDim.x) {
             if (t < pw) reinterpret_cast<uint4*>(s_pieces)[t] = __ldg(reinterpret_cast<const uint4*>(pcs) + t);
@@ -2028,17 +2074,16 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
                           const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream) {
-    (void)hm;
     // staged rows (one contiguous row per env) win on the 2-D heightfields, direct gathers on the 3-D ones (profiles/README.md)
     static const int staged_env = env_int("TRL_OBS_STAGED", -1);  // A/B hook: 0 = always gather, 1 = always stage
     const bool use_staged = g_in.patch_nbuf > 0 && (staged_env >= 0 ? staged_env != 0 : g_in.kind == 1);
     DevGround g = g_in;
     if (!use_staged) g.patch_nbuf = 0;  // k_obs_env skips the cell-rectangle mapping
-    const long long threads = (long long)E * kObsG;
-    const int blocks = (int)((threads + 127) / 128);
-    k_obs_env<<<blocks, 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, vel, body_pos, body_vel, body_quat,
-                                                        body_angvel, ground_vel, phase, flip, sample_local,
-                                                        (ObsEnvRec*)env_rec, out_state);
+    // record (4 lanes per env) -> body features (thread per (env, body)) -> ground samples
+    k_obs_rec<<<(int)(((long long)E * kRecG + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, flip, sample_local,
+                                                                                          (ObsEnvRec*)env_rec, out_state);
+    k_obs_feat<<<(int)(((long long)E * hm.N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        dm, cfg, E, pose, vel, body_pos, body_vel, body_quat, body_angvel, ground_vel, phase, (const ObsEnvRec*)env_rec, out_state);
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
     const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
