@@ -58,6 +58,8 @@ struct trl_batch {
     // observation) run concurrently on the main stream and two side streams (captured as parallel graph branches)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};  // kin chain, observation chain, stable-PD chain (highest priority)
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_pv = nullptr;
+    cudaStream_t obs_side = nullptr;               // k_obs_feat beside the ground-sample kernel
+    cudaEvent_t ev_obs[2] = {nullptr, nullptr};
     // second lane of chain streams: the HOST-pointer step is pipelined over env slices, alternating between the two
     // lanes so one slice's uploads overlap the previous slice's kernels and downloads
     cudaStream_t side2[3] = {nullptr, nullptr, nullptr};
@@ -199,9 +201,11 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
     for (int i = 0; i < 3; ++i) {
-        // side[0] = kin chain (lowest), side[1] = observation chain (middle), side[2] = stable-PD chain (highest): the
-        // measured best of the orderings tried (profiles/README.md, round 1)
-        const int prio = (i == 2) ? prio_hi : (i == 1) ? (prio_lo + prio_hi) / 2 : prio_lo;
+        // side[0] = kin chain (middle), side[1] = observation chain and side[2] = stable-PD chain (highest): the measured
+        // best of the orderings tried (profiles/README.md: round 1, and again in round 2 after the observation chain's
+        // first kernel became short -- kin / obs / PD / body-features as lo-mid-hi-mid 0.0890 ms, mid-hi-hi-mid 0.0870,
+        // hi-hi-hi 0.0960, mid-hi-mid 0.0954)
+        const int prio = (i == 0) ? (prio_lo + prio_hi) / 2 : prio_hi;
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
         if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_join[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
         if (!cuda_ok(cudaStreamCreateWithPriority(&b->side2[i], cudaStreamNonBlocking, prio), "cudaStreamCreate")) return nullptr;
@@ -218,6 +222,17 @@ extern "C" trl_batch* trl_batch_create(const trl_model* m, int num_envs, int dev
     for (int k = 0; k < 3; ++k)
         if (!cuda_ok(cudaStreamCreateWithFlags(&b->up_streams[k], cudaStreamNonBlocking), "cudaStreamCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+    {
+        const char* fsd = getenv("TRL_OBS_FEAT_SIDE");  // A/B hook: 0 = body features before the ground samples on one stream
+        if (!fsd || atoi(fsd) != 0) {
+            // below the observation chain's own priority: at the same (or a higher) one the ground-sample kernel is held
+            // back behind feature blocks that wait for registers while the stable-PD tiles fill the SMs
+            const int obs_prio = (prio_lo + prio_hi) / 2;
+            if (!cuda_ok(cudaStreamCreateWithPriority(&b->obs_side, cudaStreamNonBlocking, obs_prio), "cudaStreamCreate")) return nullptr;
+            for (int i = 0; i < 2; ++i)
+                if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_obs[i], cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
+        }
+    }
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_pv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     if (!cuda_ok(cudaEventCreateWithFlags(&b->ev_bv, cudaEventDisableTiming), "cudaEventCreate")) return nullptr;
     {
@@ -318,6 +333,8 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     for (int k = 0; k < 3; ++k)
         if (b->up_streams[k]) { cudaStreamSynchronize(b->up_streams[k]); cudaStreamDestroy(b->up_streams[k]); }
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    for (int i = 0; i < 2; ++i) if (b->ev_obs[i]) cudaEventDestroy(b->ev_obs[i]);
+    if (b->obs_side) cudaStreamDestroy(b->obs_side);
     if (b->ev_pv) cudaEventDestroy(b->ev_pv);
     if (b->ev_bv) cudaEventDestroy(b->ev_bv);
     if (b->d_zero_nvec) cudaFree(b->d_zero_nvec);
@@ -1166,7 +1183,8 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
     auto launch_obs = [&]() {
         if (rc || !want_obs) return;
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
-                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC);
+                                   nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC,
+                                   b->obs_side, b->ev_obs[0], b->ev_obs[1]);
         b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
         if (!rc && d_state32) {
             rc = trl_launch_f64_to_f32(d_state, d_state32, E * (size_t)b->F, sC);

@@ -214,7 +214,8 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream);
+                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream,
+                          void* side_stream = nullptr, void* ev_fork = nullptr, void* ev_join = nullptr);
 int trl_launch_exp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream);
 int trl_launch_ee_mask(const DevModel* dm, int E, int n, const int* joint_ids, int joint_id_all, double* J, void* stream);
 size_t trl_obs_env_rec_bytes();

@@ -32,7 +32,7 @@ namespace {
 // ---- optional kernel timeline (trl_debug_trace_*): first block start / last block end per kernel, %globaltimer ns ----
 __device__ unsigned long long* g_trace = nullptr;  // [kTraceSlots][2] or null (tracing off: one uniform load per block)
 constexpr int kTraceSlots = 16;
-enum { TR_IMP_PD = 0, TR_PD_TREE, TR_PD_H, TR_PD_SOLVE, TR_KIN, TR_OBS_ENV, TR_OBS_SAMPLES, TR_FK, TR_KIN_CHAR, TR_REWARD };
+enum { TR_IMP_PD = 0, TR_PD_TREE, TR_OBS_FEAT, TR_PD_SOLVE, TR_KIN, TR_OBS_ENV, TR_OBS_SAMPLES, TR_FK, TR_KIN_CHAR, TR_REWARD };
 struct KTrace {
     int id;
     __device__ __forceinline__ explicit KTrace(int id_) : id(id_) {
@@ -1194,6 +1194,7 @@ k_obs_feat(const DevModel* __restrict__ M, trl_obs_cfg cfg, int E, const double*
            const double* __restrict__ body_quat, const double* __restrict__ body_angvel,
            const double* __restrict__ ground_vel, const double* __restrict__ phase,
            const ObsEnvRec* __restrict__ rec, double* __restrict__ out_state) {
+    KTrace trace_(TR_OBS_FEAT);
     const int N = M->N, n = M->n;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= (long long)E * N) return;
@@ -2033,7 +2034,18 @@ int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames,
     int rc = ensure_smem((const void*)k_kin_tile, smem);
     if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
-    k_kin_tile<<<tiles, std::min(hm.N, kKinWarps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
+    static const int kin_warps_env = env_int("TRL_KIN_WARPS", 0);  // A/B hook: warps per tile (joints are looped over)
+    // A batch that fills the GPU shares the SMs with the stable-PD tiles (three or four of them hold 75 - 100 % of an SM's
+    // registers): blocks of half the joints' warps (two joints per warp) still find room beside three of them.
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    const int kin_auto = (tiles > 2 * num_sms) ? (hm.N + 1) / 2 : kKinWarps;
+    const int kin_warps = kin_warps_env > 0 ? std::min(kin_warps_env, kKinWarps) : std::min(kin_auto, kKinWarps);
+    k_kin_tile<<<tiles, std::min(hm.N, kin_warps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
                                                                 out_vel, out_body_pos);
     return (int)cudaGetLastError();
 }
@@ -2073,7 +2085,8 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
                           int E, const double* pose, const double* vel, const double* body_pos,
                           const double* body_vel, const double* body_quat, const double* body_angvel,
                           const double* ground_vel, const double* phase, const unsigned char* flip,
-                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream) {
+                          const double* sample_local, void* env_rec, double* out_state, int* out_cell, void* stream,
+                          void* side_stream, void* ev_fork, void* ev_join) {
     // staged rows (one contiguous row per env) win on the 2-D heightfields, direct gathers on the 3-D ones (profiles/README.md)
     static const int staged_env = env_int("TRL_OBS_STAGED", -1);  // A/B hook: 0 = always gather, 1 = always stage
     const bool use_staged = g_in.patch_nbuf > 0 && (staged_env >= 0 ? staged_env != 0 : g_in.kind == 1);
@@ -2082,8 +2095,16 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
     // record (4 lanes per env) -> body features (thread per (env, body)) -> ground samples
     k_obs_rec<<<(int)(((long long)E * kRecG + 127) / 128), 128, 0, (cudaStream_t)stream>>>(dm, g, cfg, E, pose, flip, sample_local,
                                                                                           (ObsEnvRec*)env_rec, out_state);
-    k_obs_feat<<<(int)(((long long)E * hm.N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    // the body features only need the record: with a side stream they run beside the ground samples instead of before them
+    const bool side = side_stream && ev_fork && ev_join && cfg.num_samples > 0;
+    cudaStream_t fs = side ? (cudaStream_t)side_stream : (cudaStream_t)stream;
+    if (side) {
+        if (cudaEventRecord((cudaEvent_t)ev_fork, (cudaStream_t)stream) != cudaSuccess) return (int)cudaGetLastError();
+        if (cudaStreamWaitEvent(fs, (cudaEvent_t)ev_fork, 0) != cudaSuccess) return (int)cudaGetLastError();
+    }
+    k_obs_feat<<<(int)(((long long)E * hm.N + 127) / 128), 128, 0, fs>>>(
         dm, cfg, E, pose, vel, body_pos, body_vel, body_quat, body_angvel, ground_vel, phase, (const ObsEnvRec*)env_rec, out_state);
+    if (side && cudaEventRecord((cudaEvent_t)ev_join, fs) != cudaSuccess) return (int)cudaGetLastError();
     int rc = (int)cudaGetLastError();
     if (rc || cfg.num_samples <= 0) return rc;
     const ObsEnvRec* er = (const ObsEnvRec*)env_rec;
@@ -2110,7 +2131,9 @@ int trl_launch_poli_state(const DevModel* dm, const DevModel& hm, const DevGroun
     else { TRL_OBS_LAUNCH(0) }
 #undef TRL_OBS_GATHER
 #undef TRL_OBS_LAUNCH
-    return (int)cudaGetLastError();
+    rc = (int)cudaGetLastError();
+    if (!rc && side && cudaStreamWaitEvent(st, (cudaEvent_t)ev_join, 0) != cudaSuccess) rc = (int)cudaGetLastError();
+    return rc;
 }
 
 int trl_launch_exp_pd(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, void* stream) {

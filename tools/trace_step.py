@@ -11,7 +11,7 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 from terrainrlsim_b200 import _capi  # noqa: E402
 
-NAMES = ["-", "k_pd_aba/block", "-", "-", "k_kin_tile", "k_obs_rec", "k_obs_samples/gather"]
+NAMES = ["-", "k_pd_aba/block", "k_obs_feat", "-", "k_kin_tile", "k_obs_rec", "k_obs_samples/gather"]
 
 
 def main():
