@@ -1980,17 +1980,28 @@ static int launch_pd_block(const DevModel* dm, const DevModel& hm, int E, const 
 // k_pd_aba: lane = env, one warp per branch of the tree, one 32-env tile per block. Returns 0, a cudaError_t, or -1
 // when the kernel does not apply (M / C requested, a shape-less body, or a tree too deep for the workspace).
 static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const StepPtrs& p, double* scratch, void* stream) {
+    (void)dm;
     if (p.out_mass || p.out_bias || !hm.bx.all_valid || !scratch || hm.N < 2) return -1;
     const int nb = hm.bx.num_branches;
     const int W = std::min(nb, 8);  // one warp per branch
-    const size_t smem = (size_t)pd_cst_doubles(hm.N) * sizeof(double) +
-                        (size_t)aba_ws_elems(nb, hm.bx.branch_area, W) * kTile * sizeof(double);
+    const size_t smem = (size_t)aba_ws_elems(nb, hm.bx.branch_area, W) * kTile * sizeof(double);
     if (smem > 227 * 1024 - 3072) return -1;
-    int rc = ensure_smem((const void*)k_pd_aba, smem);
-    if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
-    k_pd_aba<<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(dm, E, p, scratch, (int)trl_pd_scratch_doubles(hm), hm.N, hm.n);
-    return (int)cudaGetLastError();
+    const int stride = (int)trl_pd_scratch_doubles(hm);
+    // kernel parameter: index tables + per-joint constants of the (host copy of the) model
+    auto launch = [&](auto tabs_tag) -> int {
+        constexpr int NJ = decltype(tabs_tag)::value;
+        int rc = ensure_smem((const void*)k_pd_aba<NJ>, smem);
+        if (rc) return rc;
+        AbaTables<NJ> tabs;
+        tabs.ix = hm.ix;
+        tabs.bx = hm.bx;
+        memcpy(tabs.cst, hm.pd_cst, sizeof(tabs.cst));
+        k_pd_aba<NJ><<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(tabs, hm.gravity[0], hm.gravity[1], hm.gravity[2], E, p, scratch,
+                                                                   stride, hm.N, hm.n);
+        return (int)cudaGetLastError();
+    };
+    return hm.N <= 12 ? launch(std::integral_constant<int, 12>{}) : launch(std::integral_constant<int, TRL_MAX_JOINTS>{});
 }
 
 // Returns the number of kernels launched (>0) or a negative cudaError.

@@ -137,12 +137,25 @@ __device__ long long g_pd_clk[8][32];
 #define PD_CLK(i) do { } while (0)
 #endif
 
+// The model's index tables and per-joint constants travel as a KERNEL PARAMETER (7.3 KB, __grid_constant__: the constant
+// bank, read with warp-uniform indices -- lane = env, so every table lookup of the walk is uniform): no staging pass at the
+// start of every tile (512 blocks used to pull the same 3 KB through L2: 2.7 k cycles before the first useful instruction),
+// no barrier, and 3 KB of shared memory back per tile.
+// Two sizes: up to 12 joints everything fits the classic 4 KB parameter space (3.9 KB); larger characters use the large
+// parameter space (7.3 KB for 32 joints), whose launches cost about 2 us more outside CUDA graphs.
+template <int NJ>
+struct AbaTables {
+    ModelIdx ix;
+    PdBlkIdx bx;
+    double cst[NJ * kCst];
+};
+
+template <int NJ>
 __global__ void __launch_bounds__(256)
-k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__ scratch, int scratch_stride, int N, int n) {
+k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, double gz, int E, StepPtrs p, double* __restrict__ scratch,
+         int scratch_stride, int N, int n) {
     KTrace trace_(TR_PD_TREE);
     extern __shared__ double smem[];
-    __shared__ ModelIdx s_ix;
-    __shared__ PdBlkIdx s_bx;
     __shared__ int s_status[32];
     PD_CLK(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -171,46 +184,19 @@ k_pd_aba(const DevModel* __restrict__ M, int E, StepPtrs p, double* __restrict__
     // the root's coordinates (warp 0 needs them first): in flight while the model tables are staged
     double q_root[4], qd_root[7], grav[3];
     if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) grav[i] = M->gravity[i];
+        grav[0] = gx; grav[1] = gy; grav[2] = gz;
 #pragma unroll
         for (int i = 0; i < 4; ++i) q_root[i] = q[3 + i];
 #pragma unroll
         for (int i = 0; i < 7; ++i) qd_root[i] = qd[i];
     }
-    {
-        // per-joint constants, PdBlkIdx, ModelIdx -> shared memory: every load is issued before the first store (one trip)
-        constexpr int kBxQ = (int)(sizeof(PdBlkIdx) / 16), kIxQ = (int)(sizeof(ModelIdx) / 16);
-        const int cstQ = pd_cst_doubles(N) / 2;
-        const int totalQ = cstQ + kBxQ + kIxQ;
-        const uint4* s0 = reinterpret_cast<const uint4*>(M->pd_cst);
-        const uint4* s1 = reinterpret_cast<const uint4*>(&M->bx) - cstQ;
-        const uint4* s2 = reinterpret_cast<const uint4*>(&M->ix) - (cstQ + kBxQ);
-        uint4* d0 = reinterpret_cast<uint4*>(smem);
-        uint4* d1 = reinterpret_cast<uint4*>(&s_bx) - cstQ;
-        uint4* d2 = reinterpret_cast<uint4*>(&s_ix) - (cstQ + kBxQ);
-        for (int base = threadIdx.x; base < totalQ; base += 4 * blockDim.x) {
-            uint4 v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = base + k * blockDim.x;
-                if (i < totalQ) v[k] = __ldg((i < cstQ ? s0 : i < cstQ + kBxQ ? s1 : s2) + i);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = base + k * blockDim.x;
-                if (i < totalQ) (i < cstQ ? d0 : i < cstQ + kBxQ ? d1 : d2)[i] = v[k];
-            }
-        }
-        if (threadIdx.x < 32) s_status[threadIdx.x] = 0;
-    }
-    __syncthreads();
+    if (threadIdx.x < 32) s_status[threadIdx.x] = 0;  // (ordered before its first use by the barriers of the walk)
     PD_CLK(1);
-    const ModelIdx* X = &s_ix;
-    const PdBlkIdx* B = &s_bx;
+    const ModelIdx* X = &tabs.ix;
+    const PdBlkIdx* B = &tabs.bx;
     const int nb = B->num_branches;
-    const double* cst = smem;
-    double* ws0 = smem + pd_cst_doubles(N);  // workspace base (no lane offset)
+    const double* cst = tabs.cst;
+    double* ws0 = smem;  // workspace base (no lane offset)
     double* ws = ws0 + lane;                 // element k of this env: ws[k * 32]
     double* sc = scratch + (size_t)tile * scratch_stride * kTile + lane;
     const double dt = p.dt;
