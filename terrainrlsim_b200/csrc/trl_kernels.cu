@@ -584,14 +584,12 @@ k_kin_char(const DevModel* __restrict__ M, const double* __restrict__ frames, in
 // ------------------------------------------------------------------------------------------------
 constexpr int kKinWarps = 16;  // joints beyond this many are looped over
 __global__ void __launch_bounds__(kKinWarps * 32)
-k_kin_tile(const DevModel* __restrict__ M, const double* __restrict__ frames, int E, const double* __restrict__ time,
-           const double* __restrict__ origin_pos, const double* __restrict__ origin_rot, double* __restrict__ out_pose,
-           double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
+k_kin_tile(const DevModel* __restrict__ M, const __grid_constant__ ModelIdx ixp, const double* __restrict__ frames, int E,
+           const double* __restrict__ time, const double* __restrict__ origin_pos, const double* __restrict__ origin_rot,
+           double* __restrict__ out_pose, double* __restrict__ out_vel, double* __restrict__ out_body_pos) {
     KTrace trace_(TR_KIN);
     extern __shared__ double smem[];  // local transforms [N][12][32]
-    __shared__ ModelIdx s_ix;
-    stage_model_idx(&s_ix, M);
-    const ModelIdx* X = &s_ix;
+    const ModelIdx* X = &ixp;  // index tables in the constant bank (kernel parameter): every lookup is warp-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int e0 = blockIdx.x * kTile;
     const int envs = min(kTile, E - e0);
@@ -2056,7 +2054,7 @@ int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames,
     }
     const int kin_auto = (tiles > 2 * num_sms) ? (hm.N + 1) / 2 : kKinWarps;
     const int kin_warps = kin_warps_env > 0 ? std::min(kin_warps_env, kKinWarps) : std::min(kin_auto, kKinWarps);
-    k_kin_tile<<<tiles, std::min(hm.N, kin_warps) * 32, smem, (cudaStream_t)stream>>>(dm, frames, E, time, origin_pos, origin_rot, out_pose,
+    k_kin_tile<<<tiles, std::min(hm.N, kin_warps) * 32, smem, (cudaStream_t)stream>>>(dm, hm.ix, frames, E, time, origin_pos, origin_rot, out_pose,
                                                                 out_vel, out_body_pos);
     return (int)cudaGetLastError();
 }
