@@ -30,7 +30,7 @@
 namespace {
 
 // ---- optional kernel timeline (trl_debug_trace_*): first block start / last block end per kernel, %globaltimer ns ----
-__device__ unsigned long long* g_trace = nullptr;  // [kTraceSlots][2] or null (tracing off: one uniform load per block)
+__constant__ unsigned long long* g_trace = nullptr;  // [kTraceSlots][2] or null. In the constant bank: the test at the start and end of every block is one cached constant load, not a trip to L2 (k_obs_gather runs 16384 short blocks per step)
 constexpr int kTraceSlots = 16;
 enum { TR_IMP_PD = 0, TR_PD_TREE, TR_OBS_FEAT, TR_PD_SOLVE, TR_KIN, TR_OBS_ENV, TR_OBS_SAMPLES, TR_FK, TR_KIN_CHAR, TR_REWARD };
 struct KTrace {
