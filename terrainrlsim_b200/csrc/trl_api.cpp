@@ -881,7 +881,7 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
         return TRL_ERR_CUDA;
     int rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, d_pose, d_vel, d_bp, d_bv,
                                    d_bq, d_ba, d_gv, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, d_cell, b->stream);
-    b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+    b->launches += (b->cfg.num_samples > 0) ? 3 : 2;
     return finish(b, copies, rc);
 }
 
@@ -999,7 +999,7 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
                                        (const double*)at(d_bv, N * 24), nullptr, nullptr, nullptr, (const double*)at(d_ph, 8),
                                        (const unsigned char*)at(d_fl, 1), b->d_sample_local,
                                        static_cast<char*>(b->d_env_rec) + e0 * rec_bytes, (double*)at(d_st, F * 8), nullptr, sC);
-            b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+            b->launches += (b->cfg.num_samples > 0) ? 3 : 2;
             if (!rc && want_f32) {
                 rc = trl_launch_f64_to_f32((const double*)at(d_st, F * 8), (float*)at(d_st32, F * 4), ec * F, sC);
                 b->launches += 1;
@@ -1185,7 +1185,7 @@ extern "C" int trl_step_fused_ex(trl_batch* b, const trl_step_args* a, const trl
         rc = trl_launch_poli_state(b->d_model, b->model->dev, b->ground, b->cfg, b->F, b->E, p.pose, p.vel, d_bp, d_bv,
                                    nullptr, nullptr, nullptr, d_ph, d_fl, b->d_sample_local, b->d_env_rec, d_state, nullptr, sC,
                                    b->obs_side, b->ev_obs[0], b->ev_obs[1]);
-        b->launches += (b->cfg.num_samples > 0) ? 2 : 1;
+        b->launches += (b->cfg.num_samples > 0) ? 3 : 2;
         if (!rc && d_state32) {
             rc = trl_launch_f64_to_f32(d_state, d_state32, E * (size_t)b->F, sC);
             b->launches += 1;
