@@ -124,11 +124,11 @@ TRL_DEV void aba_column(int kind, int ax, const double* T, double* S) {
 }
 
 // workspace layout, in elements of 32 doubles ([element][lane]):
-//   [0, 18)                       root V, A, f (second walk: delta of the root in [0, 6))
-//   [18, 18 + 27 nb)              per branch: I^a (21), p^a (6) handed to the root; afterwards the tau staging rows
+//   [0, 27)                       root V, A, f, world <- root rotation (second walk: delta of the root in [0, 6))
+//   [27, 27 + 27 nb)              per branch: I^a (21), p^a (6) handed to the root; afterwards the tau staging rows
 //   [.., + W x branch_area)       one area per WARP: 22 per level below the root (T12 f6 u3 Kd1; second walk: delta in
 //                                 [0, 6)), then the [V6 A6 IA21 P6] blocks of joints with several children
-__host__ __device__ inline int aba_ws_elems(int nb, int branch_area, int warps) { return 18 + 27 * nb + warps * branch_area; }
+__host__ __device__ inline int aba_ws_elems(int nb, int branch_area, int warps) { return 27 + 27 * nb + warps * branch_area; }
 
 #ifdef TRL_PD_CLK
 __device__ long long g_pd_clk[8][32];
@@ -200,7 +200,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
     double* ws = ws0 + lane;                 // element k of this env: ws[k * 32]
     double* sc = scratch + (size_t)tile * scratch_stride * kTile + lane;
     const double dt = p.dt;
-    const int kOut = 18;
+    const int kOut = 27;
     double* area = ws + (size_t)(kOut + 27 * nb + warp * B->branch_area) * kTile;  // this warp's branch area
     int status = 0;
 
@@ -243,6 +243,8 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
         aba_body(Tid, cst, V, A, Ir, fr);
 #pragma unroll
         for (int k = 0; k < 6; ++k) ws[(12 + k) * kTile] = fr[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) ws[(18 + k) * kTile] = Rw[k];  // for the joints with world-coordinate targets
     }
     PD_CLK(2);
     __syncthreads();
@@ -376,10 +378,10 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 Wl[21 * kTile] = kd;  // unmasked gains go on the diagonal
                 const bool world = B->use_world[j] != 0;
                 double Wm[9];
-                if (world) {  // joint world rotation = (attach_root R(q_root)) R_j
-                    double rq9[9], Rw[9];
-                    quat_to_mat(q[3], q[4], q[5], q[6], rq9);
-                    mat3_mul(cst, rq9, Rw);
+                if (world) {  // joint world rotation = (attach_root R(q_root)) R_j; the first factor is warp 0's, from the root step
+                    double Rw[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Rw[k] = ws[(18 + k) * kTile];
                     mat3_mul(Rw, T, Wm);
                 }
                 double ep[4] = {0, 0, 0, 0};
@@ -422,6 +424,18 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 // per dof: u = Kp e_p + Kd e_v. Live dofs keep u (<= 3 per joint) for the way up; dead slots
                 // (spherical slot 3) are decoupled 1x1 systems and are finished here.
                 int lc = 0, nd = 0;
+                if (sph && X->dof_col[o + 3] < 0 && X->dof_col[o] >= 0 && X->dof_col[o + 1] >= 0 && X->dof_col[o + 2] >= 0) {
+                    // the usual spherical joint (three live dofs, dead slot 3) without the per-dof bookkeeping
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) Wl[(18 + i) * kTile] = kpm * ep[i] + kdm * (tarv[i] - wj[i]);
+                    const double ev3 = 0.0 - wj[3];
+                    const double u3 = kpm * ep[3] + kdm * ev3;
+                    const double dg = dt * kd;
+                    const double acc = (fabs(dg) > DBL_MIN) ? u3 / dg : 0.0;
+                    const double t0 = kpm * ep[3] + kdm * (ev3 - dt * acc);
+                    if (!isfinite(t0)) status |= 1;
+                    sc[(size_t)(B->aba_off[j] + 1 + 14 * nc) * kTile] = t0;
+                } else
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (i >= sz) break;
