@@ -36,14 +36,14 @@ enum { TR_IMP_PD = 0, TR_PD_TREE, TR_OBS_FEAT, TR_PD_SOLVE, TR_KIN, TR_OBS_ENV, 
 struct KTrace {
     int id;
     __device__ __forceinline__ explicit KTrace(int id_) : id(id_) {
-        if (threadIdx.x == 0 && g_trace) {
+        if (g_trace && threadIdx.x == 0) {  // pointer first: tracing off = one uniform constant load and a branch
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             atomicMin(&g_trace[2 * id], t);
         }
     }
     __device__ __forceinline__ ~KTrace() {
-        if (threadIdx.x == 0 && g_trace) {
+        if (g_trace && threadIdx.x == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             atomicMax(&g_trace[2 * id + 1], t);
