@@ -1592,9 +1592,15 @@ k_obs_samples(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __res
 // (3 scattered vertices per sample, a rectangle of ~26 rows to stage per env) this beats the staged kernel, which wins on
 // the 2-D ones (one contiguous row per env): see the ncu A/B in profiles/README.md. Same arithmetic (patch_sample reads
 // "patch" = the piece's device array with its row pitch).
-constexpr int kObsSPT = 4;
+#ifndef TRL_GATHER_SPT
+#define TRL_GATHER_SPT 4
+#endif
+constexpr int kObsSPT = TRL_GATHER_SPT;
 template <int KIND, bool WANT_CELL>
-__global__ void __launch_bounds__(256, 5)
+#ifndef TRL_GATHER_MINB
+#define TRL_GATHER_MINB 8  // 32 registers: all 64 warps of an SM resident (5 -> 8: step 0.0830 -> 0.0782 ms; the kernel waits on HBM)
+#endif
+__global__ void __launch_bounds__(256, TRL_GATHER_MINB)
 k_obs_gather(DevGround g, trl_obs_cfg cfg, int F, int E, const ObsEnvRec* __restrict__ rec,
              const double* __restrict__ sample_local, double* __restrict__ out_state, int* __restrict__ out_cell) {
     KTrace trace_(TR_OBS_SAMPLES);
