@@ -260,6 +260,24 @@ def test_step_fused_matches_oracle(trl, oracle, name):
     assert_close(out["kin_body_pos"].reshape(E, -1), ref["kin_body_pos"].reshape(E, -1), "fused kin body pos")
 
 
+@pytest.mark.parametrize("name,E", [("biped3d", 1), ("biped3d", 7), ("biped3d", 33), ("dog", 3), ("dog", 65), ("hopper", 9),
+                                    ("raptor", 31), ("biped2d", 1)])
+def test_step_fused_small_and_ragged_batches(trl, oracle, name, E):
+    """Batches smaller than one 32-env tile / one 8-env group of k_obs_rec, and just past a tile boundary: every lane
+    mapping (lane = env tiles, 4 lanes per env, thread per (env, body), block per env) has a ragged tail."""
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=3)
+    cfg = oracle_cfg(oracle, name)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    out = batch.step_fused(dt, x)
+    ref = oracle.step_range(om, cfg, dict(x), grounds, dt)
+    assert_close(out["tau"], ref["tau"], "fused tau")
+    assert_close(out["state"], ref["state"], "fused state")
+    assert_close(out["kin_pose"], ref["kin_pose"], "fused kin pose")
+    assert_close(out["kin_vel"], ref["kin_vel"], "fused kin vel", rtol=1e-8)
+    assert_close(out["kin_body_pos"].reshape(E, -1), ref["kin_body_pos"].reshape(E, -1), "fused kin body pos")
+
+
 def test_device_pointer_mode_equals_host_mode(trl, oracle):
     import torch
     name = "biped3d"
