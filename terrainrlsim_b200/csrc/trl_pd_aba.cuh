@@ -288,6 +288,12 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                     tar[i] = in ? tq[o + i] : 0.0;
                     tarv[i] = in ? tqd[o + i] : 0.0;
                 }
+                // the PD terms' own inputs are requested here as well, with the joint's coordinates: asked for where they
+                // are used (after the kinematics) their trip to L2 / HBM would sit on the chain
+                const bool valid = X->pd_valid[j] != 0;
+                const unsigned char ja = (valid && p.joint_active) ? p.joint_active[e * N + j] : (unsigned char)1;
+                const double kp_in = (valid && p.kp) ? p.kp[e * N + j] : cj_[19];
+                const double kd_in = (valid && p.kd) ? p.kd[e * N + j] : cj_[20];
                 double R[9], t[3], T[12];
                 joint_local_trans(X, j, qj, cj_, cj_ + 9, R, t);
                 double Vp[6], Ap[6];
@@ -367,13 +373,8 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 }
                 // PD terms (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196; targets through
                 // cPDController::SetTargetTheta / GetTargetTheta, PDController.cpp:191-273)
-                const bool valid = X->pd_valid[j] != 0;
-                const bool active = valid && (p.joint_active ? (p.joint_active[e * N + j] != 0) : true);
-                double kp = 0.0, kd = 0.0;
-                if (valid) {
-                    kp = p.kp ? p.kp[e * N + j] : cj_[19];
-                    kd = p.kd ? p.kd[e * N + j] : cj_[20];
-                }
+                const bool active = valid && ja != 0;
+                const double kp = valid ? kp_in : 0.0, kd = valid ? kd_in : 0.0;
                 const double kpm = active ? kp : 0.0, kdm = active ? kd : 0.0;
                 Wl[21 * kTile] = kd;  // unmasked gains go on the diagonal
                 const bool world = B->use_world[j] != 0;
