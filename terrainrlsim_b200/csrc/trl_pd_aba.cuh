@@ -577,7 +577,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
     __syncthreads();
     PD_CLK(17);
 
-    // ======================= root: (S^T I^A S) qdd = -S^T p^A, S = [rows of R(q_root) | e_x e_y e_z] (warp 0) =======================
+    // ======================= root: I^A delta = -p^A (warp 0) =======================
     const int np = n | 1;
     const bool staged = np <= 27 * nb;
     if (warp == 0) {
@@ -605,36 +605,18 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
 #pragma unroll
             for (int i = 0; i < 6; ++i) P[i] += O[(21 + i) * kTile];
         }
-        double rq9[9];
-        quat_to_mat(q_root[0], q_root[1], q_root[2], q_root[3], rq9);
-        // S = [0 I; Q^T 0] in (omega; v) rows: the three translation columns are the rows of Q = R(q_root) in the linear part,
-        // the three rotation columns are unit angular vectors. Hence
-        //   A = S^T I^A S = [Q Ivv Q^T, Q Ivw; Iwv Q^T, Iww],   b = -S^T p^A = -[Q p_v; p_w]
-        // with the 3x3 blocks Iww = IA(0:3, 0:3), Iwv = IA(0:3, 3:6), Ivv = IA(3:6, 3:6), Ivw = Iwv^T.
+        // The root's six columns S = [0 I; Q^T 0] (three translations = the rows of Q = R(q_root), three unit rotations) span
+        // all of R^6 and S is orthogonal, so (S^T I^A S) qdd = -S^T p^A is I^A delta = -p^A for delta = S qdd -- the root's
+        // spatial acceleration, which is all the second walk needs (the root has no controller: its tau is 0). The 6 x 6
+        // system is solved on I^A itself: no products with Q, no R(q_root).
         double A[6][6], bb[6];
-        {
-            double QI[3][3];  // Q Ivv
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 6; ++r) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    QI[r][c] = rq9[3 * r] * IA[sym6(3, 3 + c)] + rq9[3 * r + 1] * IA[sym6(4, 3 + c)] + rq9[3 * r + 2] * IA[sym6(5, 3 + c)];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-#pragma unroll
-                for (int c = 0; c <= r; ++c)  // lower triangle of Q Ivv Q^T
-                    A[r][c] = QI[r][0] * rq9[3 * c] + QI[r][1] * rq9[3 * c + 1] + QI[r][2] * rq9[3 * c + 2];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    // A[3 + c][r] = (Iwv Q^T)(c, r) = sum_k IA(c, 3 + k) Q(r, k)
-                    A[3 + c][r] = IA[sym6(c, 3)] * rq9[3 * r] + IA[sym6(c, 4)] * rq9[3 * r + 1] + IA[sym6(c, 5)] * rq9[3 * r + 2];
-                    if (c <= r) A[3 + r][3 + c] = IA[sym6(r, c)];
-                }
-                bb[r] = -(rq9[3 * r] * P[3] + rq9[3 * r + 1] * P[4] + rq9[3 * r + 2] * P[5]);
-                bb[3 + r] = -P[r];
-            }
+            for (int c = 0; c <= r; ++c) A[r][c] = IA[sym6(r, c)];  // lower triangle
+            bb[r] = -P[r];
         }
-        // unpivoted LDL^T (S^T I^A S is symmetric positive definite), forward / back substitution
+        // unpivoted LDL^T (I^A of the whole character is symmetric positive definite), forward / back substitution
         double Lm[6][6], dd[6], dinv[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -668,10 +650,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
             x[k] = v;
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {  // delta of the root = S x = (x_ang; Q^T x_lin)  (V is dead)
-            ws[r * kTile] = x[3 + r];
-            ws[(3 + r) * kTile] = rq9[r] * x[0] + rq9[3 + r] * x[1] + rq9[6 + r] * x[2];
-        }
+        for (int r = 0; r < 6; ++r) ws[r * kTile] = x[r];  // delta of the root (V is dead)
     }
     PD_CLK(18);
     __syncthreads();
