@@ -93,6 +93,26 @@ struct trl_batch {
     double* d_zero_nvec = nullptr;  // [E][n] zeros: tar_vel == NULL (the reference's default target velocity)
     DevBuf kin_tmp;                 // [E][2n + 3N] kin pose / vel / body positions the caller did not ask for (reward epilogue)
     DevBuf state_tmp;               // [E][F] double state behind an fp32-only state output
+    // HOST-pointer step as a CUDA graph: a caller that steps in a loop passes the same host arrays every time, and the
+    // sliced pipeline is ~40 copies / launches / event calls per slice -- the host thread, not PCIe, then limits how fine
+    // the pipeline can be cut. The second call with identical arguments is captured (all copies, kernels and
+    // dependencies of the call) and replayed from then on with one launch; any change of an argument, of the staging
+    // buffers or of the batch's device state drops the graph.
+    struct HostGraph {
+        cudaGraphExec_t exec = nullptr;
+        trl_step_args a{};
+        trl_step_opts o{};
+        bool has_o = false;
+        int seen = 0;                   // calls with these arguments so far (captured on the second one)
+        unsigned long long tick = 0;    // last use (the least recently used entry makes room)
+        long long launches = 0;
+        size_t pool_used = 0;           // staging buffers the captured call was handed (in pool order)
+        std::vector<const void*> snap;  // every device address / setting baked into the graph
+    };
+    static constexpr int kHostGraphs = 4;  // argument sets kept (e.g. the substeps with and without the policy state)
+    std::vector<HostGraph> hgs;
+    bool hg_failed = false;
+    unsigned long long hg_tick = 0;
     cudaEvent_t ev_bv = nullptr;    // body states staged (reward epilogue on the kin stream)
     // staging (host pointer mode): a small pool of grow-only device buffers handed out per call
     std::vector<DevBuf> pool;
@@ -332,6 +352,7 @@ extern "C" void trl_batch_destroy(trl_batch* b) {
     }
     for (int k = 0; k < 3; ++k)
         if (b->up_streams[k]) { cudaStreamSynchronize(b->up_streams[k]); cudaStreamDestroy(b->up_streams[k]); }
+    for (auto& g : b->hgs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     for (int i = 0; i < 2; ++i) if (b->ev_obs[i]) cudaEventDestroy(b->ev_obs[i]);
     if (b->obs_side) cudaStreamDestroy(b->obs_side);
@@ -891,8 +912,8 @@ extern "C" int trl_build_poli_state(trl_batch* b, const double* pose, const doub
 // as its inputs have landed, and one download stream copies results back as each chain of a slice finishes. The copy
 // engines of the two directions and the SMs all work on different slices at the same time; the critical path is one
 // slice's upload + kernels plus the whole download.
-static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const trl_step_opts* o, bool want_pd, bool want_kin,
-                                  bool want_obs) {
+static int step_fused_host_enqueue(trl_batch* b, const trl_step_args* a, const trl_step_opts* o, bool want_pd, bool want_kin,
+                                   bool want_obs, bool capturing) {
     const size_t E = b->E, n = b->model->n, N = b->model->N, F = (size_t)b->F;
     b->pool_next = 0;
     auto dev = [&](const void* host, size_t bytes_per_env) -> char* {
@@ -1078,12 +1099,112 @@ static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const tr
         st_wait(b->stream, b->ev_pv2);
     }
     if (rc) {
-        cudaStreamSynchronize(b->stream);
+        if (!capturing) cudaStreamSynchronize(b->stream);
         trl_set_error(std::string("trl_step_fused: ") + cudaGetErrorString((cudaError_t)rc));
         return TRL_ERR_CUDA;
     }
-    if (b->host_async) return TRL_OK;  // the caller completes the step with trl_batch_sync()
-    return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? TRL_OK : TRL_ERR_CUDA;
+    return TRL_OK;  // enqueued; the caller synchronises (or not: asynchronous host mode)
+}
+
+// everything a captured HOST-pointer step bakes in besides its arguments: the staging buffers it was handed, the batch's
+// device arrays and the settings that shape the pipeline
+static void host_graph_snapshot(const trl_batch* b, std::vector<const void*>* out) {
+    out->clear();
+    for (size_t i = 0; i < b->pool_next && i < b->pool.size(); ++i) out->push_back(b->pool[i].p);
+    const void* fixed[] = {b->d_model, b->d_frames, b->d_status, b->d_sample_local, b->d_env_rec, b->d_pd_scratch,
+                           b->ground.data, b->ground.pieces, b->ground.env_to_field, b->d_zero_nvec, b->kin_tmp.p, b->state_tmp.p,
+                           (const void*)b->stream, (const void*)(size_t)b->host_async, (const void*)(size_t)b->host_slices,
+                           (const void*)(size_t)b->ground.kind, (const void*)(size_t)b->ground.num_fields,
+                           (const void*)(size_t)b->ground.pieces_per_field, (const void*)(size_t)b->ground.patch_nbuf,
+                           (const void*)(size_t)b->ground.patch_w, (const void*)(size_t)b->ground.patch_h,
+                           (const void*)(size_t)b->ground.table_ok, (const void*)(size_t)b->overlap};
+    for (const void* p : fixed) out->push_back(p);
+}
+
+static bool host_args_pinned(const trl_step_args* a, const trl_step_opts* o) {
+    const void* ptrs[] = {a->pose, a->vel, a->tar_pose, a->tar_vel, a->joint_active, a->kin_time, a->origin_pos, a->origin_rot,
+                          a->body_pos, a->body_vel, a->phase, a->flip, a->out_tau, a->out_kin_pose, a->out_kin_vel,
+                          a->out_kin_body_pos, a->out_state, o ? (const void*)o->out_reward : nullptr,
+                          o ? (const void*)o->fallen : nullptr, o ? (const void*)o->out_state_f32 : nullptr};
+    for (const void* p : ptrs) {
+        if (!p) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (at.type != cudaMemoryTypeHost) return false;  // pageable memory: its copies cannot be captured
+    }
+    return true;
+}
+
+static int step_fused_host_sliced(trl_batch* b, const trl_step_args* a, const trl_step_opts* o, bool want_pd, bool want_kin,
+                                  bool want_obs) {
+    static const int graph_env = getenv("TRL_HOST_GRAPH") ? atoi(getenv("TRL_HOST_GRAPH")) : 1;  // A/B hook: 0 = direct submission
+    auto finish = [&]() -> int {
+        if (b->host_async) return TRL_OK;  // the caller completes the step with trl_batch_sync()
+        return cuda_ok(cudaStreamSynchronize(b->stream), "cudaStreamSynchronize") ? TRL_OK : TRL_ERR_CUDA;
+    };
+    trl_batch::HostGraph* g = nullptr;
+    if (graph_env && !b->hg_failed && b->stream != nullptr) {
+        for (auto& c : b->hgs)
+            if (c.has_o == (o != nullptr) && memcmp(&c.a, a, sizeof(*a)) == 0 && (!o || memcmp(&c.o, o, sizeof(*o)) == 0)) g = &c;
+        if (!g) {  // first call with these arguments: remember them (the least recently used set makes room)
+            if ((int)b->hgs.size() < trl_batch::kHostGraphs) {
+                b->hgs.emplace_back();
+                g = &b->hgs.back();
+            } else {
+                g = &b->hgs[0];
+                for (auto& c : b->hgs)
+                    if (c.tick < g->tick) g = &c;
+                if (g->exec) cudaGraphExecDestroy(g->exec);
+                *g = trl_batch::HostGraph();
+            }
+            g->a = *a;
+            g->has_o = o != nullptr;
+            if (o) g->o = *o;
+        }
+        g->tick = ++b->hg_tick;
+        g->seen += 1;
+    }
+    auto drop = [&]() {
+        if (g && g->exec) cudaGraphExecDestroy(g->exec);
+        if (g) g->exec = nullptr;
+    };
+    if (g && g->exec) {  // replay: same arguments, and nothing the graph points at has moved
+        std::vector<const void*> now;
+        b->pool_next = g->pool_used;  // the staging pool hands out the same buffers in the same order
+        host_graph_snapshot(b, &now);
+        if (now == g->snap && cudaGraphLaunch(g->exec, b->stream) == cudaSuccess) {
+            b->launches += g->launches;
+            return finish();
+        }
+        cudaGetLastError();
+        drop();
+    }
+    if (g && g->seen >= 2 && host_args_pinned(a, o)) {  // second (or later) call with these arguments: capture it
+        const long long l0 = b->launches;
+        if (cudaStreamBeginCapture(b->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const int rc = step_fused_host_enqueue(b, a, o, want_pd, want_kin, want_obs, true);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ee = cudaStreamEndCapture(b->stream, &graph);
+            bool ok = rc == TRL_OK && ee == cudaSuccess && graph != nullptr;
+            if (ok) ok = cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                g->launches = b->launches - l0;
+                g->pool_used = b->pool_next;
+                host_graph_snapshot(b, &g->snap);
+                if (cudaGraphLaunch(g->exec, b->stream) == cudaSuccess) return finish();
+            }
+            cudaGetLastError();
+            drop();
+            b->launches = l0;
+        } else {
+            cudaGetLastError();
+        }
+        b->hg_failed = true;  // this batch keeps to direct submission
+    }
+    const int rc = step_fused_host_enqueue(b, a, o, want_pd, want_kin, want_obs, false);
+    if (rc != TRL_OK) return rc;
+    return finish();
 }
 
 extern "C" int trl_batch_set_host_async(trl_batch* b, int on) {

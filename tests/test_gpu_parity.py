@@ -319,6 +319,62 @@ def test_host_pipeline_slices_equal_device_mode(trl, oracle, name, E):
     assert np.all(batch.status() == 0)
 
 
+@pytest.mark.parametrize("name,E", [("biped3d", 2100), ("dog", 2049)])
+def test_host_step_graph_replay(trl, oracle, name, E):
+    """A HOST-pointer step called repeatedly with the same pinned arrays is captured into a CUDA graph on the second call
+    and replayed afterwards: every call must read the arrays' CURRENT contents and equal the directly submitted step
+    (pageable numpy arrays, which cannot be captured) bit for bit; changing an argument falls back and re-captures."""
+    import torch
+    om, pm, batch, x, grounds = _setup(trl, oracle, name, E, num_fields=5)
+    _, _, direct, _, _ = _setup(trl, oracle, name, E, num_fields=5)
+    d = synth.load_model_dict(name)
+    dt = (1.0 / 30) / d["num_update_steps"]
+    n, N, F = pm.num_dof, pm.num_joints, batch.F
+    hin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in x.items()}
+    hout = {"tau": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+            "kin_pose": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+            "kin_vel": torch.empty((E, n), dtype=torch.float64).pin_memory(),
+            "kin_body_pos": torch.empty((E, N, 3), dtype=torch.float64).pin_memory(),
+            "state": torch.empty((E, F), dtype=torch.float64).pin_memory()}
+    args = batch.make_step_args(dt, {k: t.numpy() for k, t in hin.items()}, {k: t.numpy() for k, t in hout.items()})
+    rng = np.random.default_rng(11)
+    l0 = batch.launch_count()
+    per_call = None
+    for it in range(5):
+        # new inputs in the SAME arrays (a fresh pose shift, fresh targets)
+        hin["pose"][:, 0] += float(rng.normal()) * 0.05
+        hin["tar_pose"].add_(torch.from_numpy(rng.normal(size=tuple(hin["tar_pose"].shape)) * 1e-3))
+        hin["kin_time"].add_(0.01)
+        for t in hout.values():
+            t.fill_(float("nan"))
+        assert batch.step_fused_args(args) == 0
+        l1 = batch.launch_count()
+        per_call = per_call or (l1 - l0)
+        assert l1 - l0 == per_call  # replays account for the same launches
+        l0 = l1
+        ref = direct.step_fused(dt, {k: t.numpy().copy() for k, t in hin.items()})
+        for k in hout:
+            assert np.array_equal(hout[k].numpy(), ref[k], equal_nan=True), (it, k)
+    # a different output array: new arguments -> direct call, then a new graph
+    hout["tau"] = torch.empty((E, n), dtype=torch.float64).pin_memory()
+    args = batch.make_step_args(dt, {k: t.numpy() for k, t in hin.items()}, {k: t.numpy() for k, t in hout.items()})
+    for it in range(3):
+        assert batch.step_fused_args(args) == 0
+        ref = direct.step_fused(dt, {k: t.numpy().copy() for k, t in hin.items()})
+        for k in hout:
+            assert np.array_equal(hout[k].numpy(), ref[k], equal_nan=True), (it, k)
+    # another entry point in between (it uses the staging pool) and a new terrain set must not break the replay
+    batch.kin_tree_fk(x["pose"])
+    kind, fields = synth.make_grounds(name, 3)
+    batch.ground_set_heightfields(kind, fields)
+    direct.ground_set_heightfields(kind, fields)
+    for it in range(3):
+        assert batch.step_fused_args(args) == 0
+        ref = direct.step_fused(dt, {k: t.numpy().copy() for k, t in hin.items()})
+        for k in hout:
+            assert np.array_equal(hout[k].numpy(), ref[k], equal_nan=True), (it, k)
+
+
 @pytest.mark.parametrize("name,E", [("hopper", 4096), ("dog", 4096), ("raptor", 8192), ("biped3d", 16384), ("biped2d", 4096)])
 def test_full_size_properties(trl, oracle, name, E):
     """BASELINE.json full sizes: determinism, env-permutation equivariance (bit-exact), and oracle parity on a
