@@ -689,6 +689,26 @@ def run_ours(args, rank, local_rank, world):
         ach_gbs = bytes_step * E / (ms_step * 1e-3) / 1e9
         roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "peak_source": hbm_src, "whole_step_fp64_tflops": total_flops * E / (ms_step * 1e-3) / 1e12}
+        # the step's longest kernel chain since round 2 is the observation (k_obs_rec + k_obs_feat + k_obs_gather): HBM-bound
+        # gathers. Algorithmic bytes per env: pose / vel and body rows in, the vertex floats of every ground sample in, the
+        # [F] double state out.
+        roof_obs = None
+        if kernel_ms and kernel_ms.get("poli_state"):
+            G = w.batch.cfg.num_samples
+            verts = 3 if w.d.get("terrain", "").startswith("var3d") else 2  # vertex floats a sample interpolates
+            obs_bytes = 2 * w.model.num_dof * 8 + 2 * w.model.num_joints * 24 + 9 + G * verts * 4 + w.batch.F * 8
+            ach = obs_bytes * E / (kernel_ms["poli_state"] * 1e-3) / 1e9
+            obs_traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r02_obs_traffic.json")))
+                if tj.get("config") == name and tj.get("envs") == E:
+                    obs_traffic = tj["obs_entry_bytes_per_launch"]
+            except (OSError, ValueError, KeyError):
+                pass
+            roof_obs = {"bound": "hbm", "kernel": "observation entry: k_obs_rec + k_obs_feat + k_obs_gather / k_obs_samples",
+                        "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": obs_traffic,
+                        "ms_per_launch": kernel_ms["poli_state"], "algorithmic_bytes_per_launch": obs_bytes * E,
+                        "peak_source": hbm_src}
         cpu = None
         if not args.no_cpu_baseline:
             if numa.get("all_cpus"):
@@ -707,7 +727,7 @@ def run_ours(args, rank, local_rank, world):
                 "e2e": e2e, "gpu_launches": int(launches), "launch": "direct" if args.no_graph else
                 "CUDA graph of %d fused steps (%d kernels each) replayed" % (w.sets, w.launches_per_step),
                 "clocks": clocks, "roofline": roof,
-                "kernel_ms": kernel_ms, "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
+                "kernel_ms": kernel_ms, "roofline_observation": roof_obs, "roofline_step_hbm": roof_hbm, "roofline_model": roofline_model(name), "cpu_baseline": cpu,
                 "host_cores": os.cpu_count(), "numa": {k: v for k, v in numa.items() if k != "all_cpus"},
                 "other_workloads": others,
                 "episode_stats_allgather": gathered}
