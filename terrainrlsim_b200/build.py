@@ -52,3 +52,15 @@ def build(force=False, verbose=False):
     subprocess.check_call(common + ["-shared", "-o", tmp] + SOURCES + objs, cwd=CSRC)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
+
+
+def build_diagnostic():
+    """libtrl_b200_clk.so: the same library with -DTRL_PD_CLK (clock64 stamps of one k_pd_aba tile, read by
+    tools/pd_phases.py through TRL_LIB=terrainrlsim_b200/lib/libtrl_b200_clk.so). Not loaded by default."""
+    build()
+    nvcc = nvcc_path()
+    out = os.path.join(LIB_DIR, "libtrl_b200_clk.so")
+    objs = [os.path.join(LIB_DIR, os.path.splitext(src)[0] + ".o") for src in STRICT_SOURCES]
+    subprocess.check_call([nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+                           "-diag-suppress", "177,128", "-DTRL_PD_CLK", "-shared", "-o", out] + SOURCES + objs, cwd=CSRC)
+    return out

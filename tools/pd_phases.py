@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
 """Phase timing of one block of k_pd_aba (diagnostic build with -DTRL_PD_CLK, loaded through TRL_LIB).
+build: python -c "from terrainrlsim_b200 import build; build.build_diagnostic()"
 usage: TRL_LIB=terrainrlsim_b200/lib/libtrl_b200_clk.so tools/pd_phases.py [config] [envs]"""
 import ctypes as C
 import os
