@@ -2050,15 +2050,16 @@ int trl_launch_kin(const DevModel* dm, const DevModel& hm, const double* frames,
     if (rc) return rc;
     const int tiles = (E + kTile - 1) / kTile;
     static const int kin_warps_env = env_int("TRL_KIN_WARPS", 0);  // A/B hook: warps per tile (joints are looped over)
-    // A batch that fills the GPU shares the SMs with the stable-PD tiles (three or four of them hold 75 - 100 % of an SM's
-    // registers): blocks of half the joints' warps (two joints per warp) still find room beside three of them.
+    // A batch of more than one tile per SM shares the SMs with the stable-PD tiles (two to four of them hold 50 - 100 % of
+    // an SM's registers): blocks of half the joints' warps (two joints per warp) still find room beside them (biped3D x
+    // 16384: step 0.0923 -> 0.0890 ms; raptor x 8192: 68.7 -> 62.6 us).
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
-    const int kin_auto = (tiles > 2 * num_sms) ? (hm.N + 1) / 2 : kKinWarps;
+    const int kin_auto = (tiles > num_sms) ? (hm.N + 1) / 2 : kKinWarps;
     const int kin_warps = kin_warps_env > 0 ? std::min(kin_warps_env, kKinWarps) : std::min(kin_auto, kKinWarps);
     k_kin_tile<<<tiles, std::min(hm.N, kin_warps) * 32, smem, (cudaStream_t)stream>>>(dm, hm.ix, frames, E, time, origin_pos, origin_rot, out_pose,
                                                                 out_vel, out_body_pos);
