@@ -63,6 +63,7 @@ struct alignas(16) PdBlkIdx {
     signed char b_ev1[TRL_MAX_JOINTS];       //           one past its last event
     signed char b_pre0[TRL_MAX_JOINTS];      //           first joint in `preorder`
     signed char b_pre1[TRL_MAX_JOINTS];      //           one past its last joint
+    signed char b_depth[TRL_MAX_JOINTS];     //           deepest level in it (its level slots come first in its area)
     short xoff[TRL_MAX_JOINTS];              // joints with >= 2 children: offset (elements, within the branch's area) of
                                              // their [V6 A6 IA21 P6] block; -1 otherwise
     int num_branches;

@@ -1939,7 +1939,9 @@ int trl_launch_rbd_extras(const DevModel* dm, const DevModel& hm, int E, const d
 
 // per env; the allocation is rounded up to whole tiles of kTile envs by the caller (trl_pd_scratch_tile())
 size_t trl_pd_scratch_doubles(const DevModel& hm) {
-    return (size_t)std::max(hm.bx.aba_slots, 1);  // k_pd_aba's hand-off between its two walks (k_pd_block keeps everything in shared memory)
+    // k_pd_aba's hand-off between its two walks (+ f6 u3 kd1 per joint for its slim layout); k_pd_block keeps everything in
+    // shared memory
+    return (size_t)std::max(hm.bx.aba_slots, 1) + (size_t)10 * hm.N;
 }
 int trl_pd_scratch_tile() { return kTile; }
 
@@ -1988,24 +1990,58 @@ static int launch_pd_aba(const DevModel* dm, const DevModel& hm, int E, const St
     if (p.out_mass || p.out_bias || !hm.bx.all_valid || !scratch || hm.N < 2) return -1;
     const int nb = hm.bx.num_branches;
     const int W = std::min(nb, 8);  // one warp per branch
-    const size_t smem = (size_t)aba_ws_elems(nb, hm.bx.branch_area, W) * kTile * sizeof(double);
-    if (smem > 227 * 1024 - 3072) return -1;
+    // per-warp area: the branch's level slots (22 doubles per level, 12 in the slim layout) + the blocks of its joints with
+    // several children
+    int area_full = 0, area_slim = 0;
+    for (int b = 0; b < nb; ++b) {
+        int extra = 0;
+        for (int q = hm.bx.b_pre0[b]; q < hm.bx.b_pre1[b]; ++q) extra += hm.bx.nchild[hm.bx.preorder[q]] >= 2 ? 1 : 0;
+        area_full = std::max(area_full, 22 * hm.bx.b_depth[b] + 39 * extra);
+        area_slim = std::max(area_slim, 12 * hm.bx.b_depth[b] + 39 * extra);
+    }
+    const size_t smem_full = (size_t)aba_ws_elems(nb, area_full, W) * kTile * sizeof(double);
+    const size_t smem_slim = (size_t)aba_ws_elems(nb, area_slim, W) * kTile * sizeof(double);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
     const int tiles = (E + kTile - 1) / kTile;
-    const int stride = (int)trl_pd_scratch_doubles(hm);
+    const int by_regs = std::max(1, 65536 / (W * 32 * 256));
+    auto per_sm = [&](size_t smem) { return std::min(by_regs, (int)((227 * 1024) / (smem + 1280))); };
+    auto waves = [&](size_t smem) { const int ps = per_sm(smem); return ps > 0 ? (tiles + num_sms * ps - 1) / (num_sms * ps) : 1 << 20; };
+    static const int slim_env = env_int("TRL_PD_SLIM", -1);  // A/B hook: 0 = never, 1 = always
+    // The slim layout pays a trip to L2 per joint. It wins when it saves a whole wave of tiles (raptor x 8192: PD entry 39.3
+    // -> 25.0 us), when the full one does not fit, and when the resident tiles of the full layout leave less than ~48 KB of
+    // the SM's 256 KB to L1 (biped3D x 16384: four 54 KB tiles per SM; the walk's strided input rows and the hand-off then
+    // miss L1: 27.6 -> 24.2 us with 39 KB tiles). Otherwise the full layout is faster (dog x 4096: 42.7 vs 43.4 us).
+    const bool fits_full = smem_full <= 227 * 1024 - 3072;
+    const int resident_full = std::min(per_sm(smem_full), (tiles + num_sms - 1) / num_sms);
+    const bool l1_squeezed = (size_t)resident_full * (smem_full + 1280) > 208 * 1024 &&
+                             (size_t)resident_full * (smem_full - smem_slim) >= 32 * 1024;
+    const bool slim = slim_env >= 0 ? slim_env != 0 : (!fits_full || waves(smem_slim) < waves(smem_full) || l1_squeezed);
+    const size_t smem = slim ? smem_slim : smem_full;
+    if (smem > 227 * 1024 - 3072) return -1;
+    const int stride = (int)trl_pd_scratch_doubles(hm), fuk_off = std::max(hm.bx.aba_slots, 1);
     // kernel parameter: index tables + per-joint constants of the (host copy of the) model
-    auto launch = [&](auto tabs_tag) -> int {
-        constexpr int NJ = decltype(tabs_tag)::value;
-        int rc = ensure_smem((const void*)k_pd_aba<NJ>, smem);
+    auto launch = [&](auto nj_tag, auto slim_tag) -> int {
+        constexpr int NJ = decltype(nj_tag)::value;
+        constexpr bool SLIM = decltype(slim_tag)::value;
+        int rc = ensure_smem((const void*)k_pd_aba<NJ, SLIM>, smem);
         if (rc) return rc;
         AbaTables<NJ> tabs;
         tabs.ix = hm.ix;
         tabs.bx = hm.bx;
         memcpy(tabs.cst, hm.pd_cst, sizeof(tabs.cst));
-        k_pd_aba<NJ><<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(tabs, hm.gravity[0], hm.gravity[1], hm.gravity[2], E, p, scratch,
-                                                                   stride, hm.N, hm.n);
+        k_pd_aba<NJ, SLIM><<<tiles, 32 * W, smem, (cudaStream_t)stream>>>(tabs, hm.gravity[0], hm.gravity[1], hm.gravity[2], E, p, scratch,
+                                                                         stride, fuk_off, SLIM ? area_slim : area_full, hm.N, hm.n);
         return (int)cudaGetLastError();
     };
-    return hm.N <= 12 ? launch(std::integral_constant<int, 12>{}) : launch(std::integral_constant<int, TRL_MAX_JOINTS>{});
+    using NjS = std::integral_constant<int, 12>;
+    using NjL = std::integral_constant<int, TRL_MAX_JOINTS>;
+    if (hm.N <= 12) return slim ? launch(NjS{}, std::true_type{}) : launch(NjS{}, std::false_type{});
+    return slim ? launch(NjL{}, std::true_type{}) : launch(NjL{}, std::false_type{});
 }
 
 // Returns the number of kernels launched (>0) or a negative cudaError.

@@ -437,6 +437,7 @@ int trl_build_dev_model(trl_model* m) {
                 const int jj = d.ix.dfs_event[q];
                 if (jj >= 0 && b.nchild[jj] >= 2) { b.xoff[jj] = (short)(22 * depth + 39 * extra); ++extra; }
             }
+            b.b_depth[nb] = (signed char)depth;
             area = std::max(area, 22 * depth + 39 * extra);
             ++nb;
             k = k1 + 1;

@@ -150,10 +150,14 @@ struct AbaTables {
     double cst[NJ * kCst];
 };
 
-template <int NJ>
+// SLIM: a level slot keeps only T (12 instead of 22 doubles); the body force, the PD forces and Kd of a joint go through the
+// global scratch between its enter and its leave. For characters whose tile would otherwise allow only one tile per SM
+// while the batch needs more (raptor x 8192: 147 KB per tile, 256 tiles on 148 SMs = two waves; slim 96 KB = one wave).
+template <int NJ, bool SLIM>
 __global__ void __launch_bounds__(256)
 k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, double gz, int E, StepPtrs p, double* __restrict__ scratch,
-         int scratch_stride, int N, int n) {
+         int scratch_stride, int fuk_off, int area_elems, int N, int n) {
+    constexpr int kSlot = SLIM ? 12 : 22;
     KTrace trace_(TR_PD_TREE);
     extern __shared__ double smem[];
     __shared__ int s_status[32];
@@ -201,7 +205,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
     double* sc = scratch + (size_t)tile * scratch_stride * kTile + lane;
     const double dt = p.dt;
     const int kOut = 27;
-    double* area = ws + (size_t)(kOut + 27 * nb + warp * B->branch_area) * kTile;  // this warp's branch area
+    double* area = ws + (size_t)(kOut + 27 * nb + warp * area_elems) * kTile;  // this warp's branch area
     int status = 0;
 
     // ======================= root, down: V_0 = S qd, A_0 = gravity + c_root (warp 0) =======================
@@ -276,7 +280,8 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 const int j = code;
                 const int lv = X->level[j];
                 const int pj = X->parent[j];
-                double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;  // T12 f6 u3 kd1
+                double* Wl = area + (size_t)(kSlot * (lv - 1)) * kTile;  // T12 (f6 u3 kd1)
+                double* Fx = SLIM ? sc + (size_t)(fuk_off + 10 * j) * kTile : Wl + 12 * kTile;  // f6 u3 kd1 of the joint
                 const int o = X->offset[j], sz = X->size[j], type = X->type[j];
                 const double* cj_ = cst + kCst * j;
                 double qj[4], wj[4], tar[4], tarv[4];
@@ -304,7 +309,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
 #pragma unroll
                     for (int k = 0; k < 6; ++k) { Vp[k] = ws[k * kTile]; Ap[k] = ws[(6 + k) * kTile]; }
                 } else {
-                    const double* Wp = area + (size_t)(22 * (lv - 2)) * kTile;
+                    const double* Wp = area + (size_t)(kSlot * (lv - 2)) * kTile;
                     double Tp[12];
 #pragma unroll
                     for (int i = 0; i < 12; ++i) Tp[i] = Wp[i * kTile];
@@ -319,7 +324,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
 #pragma unroll
                         for (int k = 0; k < 6; ++k) { Vp[k] = Vc[k]; Ap[k] = Ac[k]; }
                     } else {                   // later child: the parent owns a block
-                        const double* Xp = area + (size_t)B->xoff[pj] * kTile;
+                        const double* Xp = area + (size_t)(B->xoff[pj] - (SLIM ? 10 * B->b_depth[b] : 0)) * kTile;
 #pragma unroll
                         for (int k = 0; k < 6; ++k) { Vp[k] = Xp[k * kTile]; Ap[k] = Xp[(6 + k) * kTile]; }
                     }
@@ -358,7 +363,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 }
                 last_entered = j;
                 if (B->xoff[j] >= 0) {  // several children: V / A for the later ones, zeroed accumulators
-                    double* Xj = area + (size_t)B->xoff[j] * kTile;
+                    double* Xj = area + (size_t)(B->xoff[j] - (SLIM ? 10 * B->b_depth[b] : 0)) * kTile;
 #pragma unroll
                     for (int k = 0; k < 6; ++k) { Xj[k * kTile] = Vc[k]; Xj[(6 + k) * kTile] = Ac[k]; }
 #pragma unroll
@@ -369,14 +374,14 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                     double Ib[10], f[6];
                     aba_body(T, cj_, Vc, Ac, Ib, f);
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) Wl[(12 + k) * kTile] = f[k];
+                    for (int k = 0; k < 6; ++k) Fx[k * kTile] = f[k];
                 }
                 // PD terms (cImpPDController::CalcControlForces, ImpPDController.cpp:137-196; targets through
                 // cPDController::SetTargetTheta / GetTargetTheta, PDController.cpp:191-273)
                 const bool active = valid && ja != 0;
                 const double kp = valid ? kp_in : 0.0, kd = valid ? kd_in : 0.0;
                 const double kpm = active ? kp : 0.0, kdm = active ? kd : 0.0;
-                Wl[21 * kTile] = kd;  // unmasked gains go on the diagonal
+                Fx[9 * kTile] = kd;  // unmasked gains go on the diagonal
                 const bool world = B->use_world[j] != 0;
                 double Wm[9];
                 if (world) {  // joint world rotation = (attach_root R(q_root)) R_j; the first factor is warp 0's, from the root step
@@ -428,7 +433,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 if (sph && X->dof_col[o + 3] < 0 && X->dof_col[o] >= 0 && X->dof_col[o + 1] >= 0 && X->dof_col[o + 2] >= 0) {
                     // the usual spherical joint (three live dofs, dead slot 3) without the per-dof bookkeeping
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) Wl[(18 + i) * kTile] = kpm * ep[i] + kdm * (tarv[i] - wj[i]);
+                    for (int i = 0; i < 3; ++i) Fx[(6 + i) * kTile] = kpm * ep[i] + kdm * (tarv[i] - wj[i]);
                     const double ev3 = 0.0 - wj[3];
                     const double u3 = kpm * ep[3] + kdm * ev3;
                     const double dg = dt * kd;
@@ -461,7 +466,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                         sc[(size_t)(B->aba_off[j] + 1 + 14 * nc + nd) * kTile] = t0;  // after the joint's live data
                         ++nd;
                     } else {
-                        if (lc < 3) Wl[(18 + lc) * kTile] = u;
+                        if (lc < 3) Fx[(6 + lc) * kTile] = u;
                         ++lc;
                     }
                 }
@@ -482,13 +487,19 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 const int j = -1 - code;
                 const int lv = X->level[j];
                 const int pj = X->parent[j];
-                double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;
+                double* Wl = area + (size_t)(kSlot * (lv - 1)) * kTile;
+                const double* Fx = SLIM ? sc + (size_t)(fuk_off + 10 * j) * kTile : Wl + 12 * kTile;
                 const double* cj_ = cst + kCst * j;
+                double P[6], uk[4];  // requested first (SLIM: a trip to L2 that overlaps the inertia rebuild)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) P[i] = Fx[i * kTile];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) uk[i] = Fx[(6 + i) * kTile];
                 double T[12];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) T[i] = Wl[i * kTile];
                 // I^A = I_j + children, p^A = f_j + children
-                double IA[21], P[6];
+                double IA[21];
                 {
                     double Ib[10];
                     aba_inertia(T, cj_, Ib);
@@ -502,8 +513,6 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                     IA[sym6(4, 4)] = m; IA[sym6(4, 5)] = 0.0;
                     IA[sym6(5, 5)] = m;
                 }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) P[i] = Wl[(12 + i) * kTile];
                 const int nch = B->nchild[j];
                 if (nch == 1) {  // only child: its result is still in registers
 #pragma unroll
@@ -511,7 +520,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
 #pragma unroll
                     for (int i = 0; i < 6; ++i) P[i] += Pc[i];
                 } else if (nch > 1) {
-                    const double* Xj = area + (size_t)B->xoff[j] * kTile;
+                    const double* Xj = area + (size_t)(B->xoff[j] - (SLIM ? 10 * B->b_depth[b] : 0)) * kTile;
 #pragma unroll
                     for (int i = 0; i < 21; ++i) IA[i] += Xj[(12 + i) * kTile];
 #pragma unroll
@@ -519,7 +528,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                 }
                 const int c0 = X->first_col[j], nc = X->ncol[j];
                 double* sj = sc + (size_t)B->aba_off[j] * kTile;  // [kdm dt][u k][uh' k][S 6k][U' 6k][dead tau]
-                const double kdd = dt * Wl[21 * kTile];
+                const double kdd = dt * uk[3];
                 // The joint's columns are eliminated one after the other (a k-dof joint = k stacked 1-dof joints: the same
                 // arithmetic as an LDL^T of its k x k block, with a third of the registers). dt*Kd sits on every diagonal.
                 for (int a = 0; a < nc; ++a) {
@@ -528,7 +537,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
                     sym6_mulv(IA, S, U);
                     const double D = dot6(S, U) + kdd;
                     if (!(D > 0.0)) status |= 2;
-                    const double u = Wl[(18 + a) * kTile];
+                    const double u = (a == 0) ? uk[0] : (a == 1) ? uk[1] : uk[2];
                     const double inv = fast_rcp(D);
                     const double uhs = (u - dot6(S, P)) * inv;
                     double Us[6];
@@ -561,7 +570,7 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
 #pragma unroll
                     for (int i = 0; i < 6; ++i) Pc[i] = P[i];
                 } else {
-                    double* Xp = area + (size_t)B->xoff[pj] * kTile;
+                    double* Xp = area + (size_t)(B->xoff[pj] - (SLIM ? 10 * B->b_depth[b] : 0)) * kTile;
 #pragma unroll
                     for (int i = 0; i < 21; ++i) Xp[(12 + i) * kTile] += IA[i];
 #pragma unroll
@@ -677,8 +686,8 @@ k_pd_aba(const __grid_constant__ AbaTables<NJ> tabs, double gx, double gy, doubl
         for (int pi = p0; pi < p1; ++pi) {
             const int j = B->preorder[pi];
             const int lv = X->level[j];
-            double* Wl = area + (size_t)(22 * (lv - 1)) * kTile;
-            const double* Dp = (lv == 1) ? ws : area + (size_t)(22 * (lv - 2)) * kTile;
+            double* Wl = area + (size_t)(kSlot * (lv - 1)) * kTile;
+            const double* Dp = (lv == 1) ? ws : area + (size_t)(kSlot * (lv - 2)) * kTile;
             if (pi + 1 < p1) {  // the next joint's scratch rows (contiguous, 256 B each): one cooperative L1 prefetch
                 const int jn = B->preorder[pi + 1];
                 const char* base = (const char*)(scratch + ((size_t)tile * scratch_stride + B->aba_off[jn]) * kTile);

@@ -511,7 +511,7 @@ print("VARIANT_OK")
 
 @pytest.mark.parametrize("env", [{"TRL_PD_ABA": "0"}, {"TRL_OBS_STAGED": "0"}, {"TRL_OBS_STAGED": "1"},
                                  {"TRL_STEP_OVERLAP": "0"}, {"TRL_HOST_SLICES": "1"}, {"TRL_HOST_SLICES": "4"},
-                                 {"TRL_OBS_FEAT_SIDE": "0"}, {"TRL_KIN_WARPS": "2"}])
+                                 {"TRL_OBS_FEAT_SIDE": "0"}, {"TRL_KIN_WARPS": "2"}, {"TRL_PD_SLIM": "1"}, {"TRL_PD_SLIM": "0"}])
 def test_pd_kernel_variants(env):
     """The launcher's tuning hooks select other kernel variants (monolithic warp-per-env PD, runtime-loop solve, wider
     lane groups); each must meet the same 1e-9 bar. Hooks are read once per process, hence the subprocess."""
