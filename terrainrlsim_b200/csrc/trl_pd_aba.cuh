@@ -28,13 +28,18 @@
 // limbs, ... are walked concurrently by different warps -- this is what lifts the chain off the single-warp latency
 // floor (16384 envs are only 512 tiles on 592 SM sub-partitions). Warp 0 also does the root. Three block barriers.
 //
-// State: a walker keeps 22 doubles per tree LEVEL of its branch in shared memory (T12, f6, u3, Kd1); the articulated
-// inertia / bias force travel up a chain in REGISTERS (a joint's "leave" is followed by its parent's when it is an only
-// child) and velocities / accelerations travel down in registers (a joint's "enter" is followed by its first child's);
-// only joints with two or more children own a [V6 A6 IA21 P6] block. biped3D: 12 + 2 x 27 + 2 x 66 = 198 doubles per env =
-// 51 KB per tile, so all 512 tiles of 16384 envs are resident at once. What the second walk needs (U D^-1, D^-1 uh, S, u,
-// Kd: 14k+1 doubles per joint with k dofs, plus the finished tau of dead slots) goes through a tile-major global
-// scratch (1.6 KB per env, written and read back by the same warp: L2-resident).
+// State: a walker keeps one slot per tree LEVEL of its branch in shared memory -- T12, f6, u3, Kd1 (22 doubles), or T12
+// alone in the SLIM layout, where f / u / Kd of a joint go through the global scratch between its enter and its leave
+// (chosen by the launcher when it saves a wave of tiles or when the full tiles squeeze L1: see launch_pd_aba). The
+// articulated inertia / bias force travel up a chain in REGISTERS (a joint's "leave" is followed by its parent's when it
+// is an only child) and velocities / accelerations travel down in registers (a joint's "enter" is followed by its first
+// child's); only joints with two or more children own a [V6 A6 IA21 P6] block. The depth-first event list is walked as
+// alternating runs of enters and leaves so that each loop carries only its own hand-off. biped3D, slim: 27 + 2 x 27 +
+// 2 x 36 = 153 doubles per env = 39 KB per tile (full: 213 = 54 KB); all 512 tiles of 16384 envs are resident at once
+// either way. What the second walk needs (U D^-1, D^-1 uh, S, u, Kd: 14k+1 doubles per joint with k dofs, plus the
+// finished tau of dead slots) goes through a tile-major global scratch (1.6 KB per env, written and read back by the same
+// warp: L2-resident). The model's index tables and per-joint constants arrive as a __grid_constant__ kernel parameter
+// (constant bank; every lookup is warp-uniform), the root is solved as I^A delta = -p^A.
 //
 // Restrictions (callers fall back to k_pd_block): every body valid (the reference's handling of shape-less bodies
 // leaves M structurally inconsistent: SURVEY.md, k_rbd_extras note), no M / C output requested.
